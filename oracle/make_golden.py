@@ -1,0 +1,198 @@
+"""Generate golden vectors by running the UNMODIFIED reference (GOPS @ /root/reference) on CPU.
+
+TEST INFRASTRUCTURE.  Run in the build container only (`python oracle/make_golden.py`); the
+outputs under `tests/golden/*.npz` are committed and travel to the GPU box, the reference does
+not.  Every case stores: inputs, the initial `state_dict`, the loss the reference reports
+(`tb_info`), the gradients left in `p.grad` by `local_update`, and the post-update `state_dict`
+(one Adam step, plus Polyak targets for INFADP).
+
+Reference entry points exercised (all through the reference's own factories):
+  create_alg                      gops/create_pkg/create_alg.py:60-97
+  FHADP.local_update              gops/algorithm/fhadp.py:87-125 (+ base.py:94-98)
+  INFADP.local_update             gops/algorithm/infadp.py:101-213
+  create_env_model wrapper chain  gops/create_pkg/create_env_model.py:51-128
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+
+from oracle import ref_shim  # noqa: E402
+from oracle import gops_oracle as orc  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+def _sd(alg):
+    return {k: _np(v).copy() for k, v in alg.state_dict().items()}
+
+
+def base_kwargs(env_id, algorithm, obs_dim, act_dim, hidden, act, policy_name, **extra):
+    kw = dict(
+        env_id=env_id, algorithm=algorithm, seed=0, trainer="off_serial_trainer", cnn_shared=False,
+        use_gpu=False, action_type="continu", obsv_dim=obs_dim, action_dim=act_dim,
+        action_high_limit=np.ones(act_dim, dtype=np.float32), action_low_limit=-np.ones(act_dim, dtype=np.float32),
+        policy_func_name=policy_name, policy_func_type="MLP", policy_hidden_sizes=list(hidden),
+        policy_hidden_activation=act, policy_act_distribution="default", policy_learning_rate=1e-3,
+        value_func_name="StateValue", value_func_type="MLP", value_hidden_sizes=list(hidden),
+        value_hidden_activation=act, value_learning_rate=1e-3,
+    )
+    kw.update(extra)
+    return kw
+
+
+def to_ref_data(env_id, data):
+    """Oracle input dict -> the dict the reference trainer would hand to local_update."""
+    out = {k: v for k, v in data.items() if k != "state" or env_id != "veh3dof_tracking"}
+    B = data["obs"].shape[0]
+    if env_id == "veh3dof_tracking":
+        from gops.env.env_gen_ocp.pyth_base import ContextState, State
+        robot, reference, t = data["state"]
+        out["state"] = State(robot_state=robot.clone(),
+                             context_state=ContextState(reference=reference.clone(), constraint=None, t=t))
+    out.setdefault("act", torch.zeros(B, 1))
+    out.setdefault("rew", torch.zeros(B))
+    out.setdefault("obs2", data["obs"].clone())
+    return out
+
+
+def flat_inputs(env_id, data):
+    d = {}
+    for k, v in data.items():
+        if k == "state" and env_id == "veh3dof_tracking":
+            d["in_robot_state"], d["in_reference"] = _np(v[0]), _np(v[1])
+            d["in_t"] = np.int64(v[2])
+        else:
+            d["in_" + k] = _np(v)
+    return d
+
+
+def run_case(name, kw, data, iterations, trace_n=0, set_params=None, load_ckpt=None):
+    from gops.create_pkg.create_alg import create_alg
+
+    torch.manual_seed(1234)
+    alg = create_alg(**kw)
+    if load_ckpt:
+        alg.load_state_dict(torch.load(load_ckpt, map_location="cpu"))
+    if set_params:
+        alg.set_parameters(set_params)
+    env_id = kw["env_id"]
+    rec = flat_inputs(env_id, data)
+    for k, v in _sd(alg).items():
+        rec["init/" + k] = v
+    if trace_n and kw["algorithm"] == "FHADP":
+        with torch.no_grad():
+            rd = to_ref_data(env_id, data)
+            o, d, info = rd["obs"], rd["done"], rd
+            tr = {"obs": [], "act": [], "rew": [], "done": []}
+            for step in range(kw["pre_horizon"]):
+                a = alg.networks.policy(o, step + 1)
+                o, r, d, info = alg.envmodel.forward(o, a, d, info)
+                tr["obs"].append(_np(o[:trace_n])); tr["act"].append(_np(a[:trace_n]))
+                tr["rew"].append(_np(r[:trace_n])); tr["done"].append(_np(d[:trace_n]))
+            for k, v in tr.items():
+                rec["trace_" + k] = np.stack(v, 0)
+    for it in iterations:
+        tb = alg.local_update(to_ref_data(env_id, data), it)
+        for k, v in tb.items():
+            if "Time" not in k:
+                rec[f"it{it}/tb/{k}"] = np.float64(v)
+        for nm in ("policy", "v"):
+            net = getattr(alg.networks, nm, None)
+            if net is None:
+                continue
+            for pn, p in net.named_parameters():
+                if p.grad is not None:
+                    rec[f"it{it}/grad/{nm}.{pn}"] = _np(p.grad).copy()
+        for k, v in _sd(alg).items():
+            rec[f"it{it}/post/{k}"] = v
+    os.makedirs(OUT, exist_ok=True)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **rec)
+    print(name, {k: float(v) for k, v in rec.items() if "/tb/" in k})
+
+
+def main():
+    ref_shim.install()
+    torch.set_num_threads(4)
+
+    # C1: FHADP idpendulum, FiniteHorizonPolicy [64,64] gelu (fhadp_mlp_idpendulum_serial.py:34-75)
+    for H in (30, 80):
+        kw = base_kwargs("pyth_idpendulum", "FHADP", 6, 1, (64, 64), "gelu", "FiniteHorizonPolicy",
+                         pre_horizon=H, reward_scale=1.0, policy_learning_rate=1e-4)
+        run_case(f"fhadp_idp_h{H}", kw, orc.sample_inputs("pyth_idpendulum", 256, 11), [0],
+                 trace_n=32 if H == 30 else 0)
+    # gamma != 1, relu, and half the batch arriving already done
+    kw = base_kwargs("pyth_idpendulum", "FHADP", 6, 1, (64, 64), "relu", "FiniteHorizonPolicy",
+                     pre_horizon=12, reward_scale=0.5, reward_shift=1.0, gamma=0.97)
+    d = orc.sample_inputs("pyth_idpendulum", 128, 12)
+    d["done"][::2] = 1.0
+    run_case("fhadp_idp_relu_done", kw, d, [0])
+
+    # C5: INFADP LQ s4a2 (infadp_mlp_lqs4a2_offserial.py), PEV then PIM
+    kw = base_kwargs("pyth_lq", "INFADP", 4, 2, (64, 64), "gelu", "DetermPolicy", lq_config="s4a2",
+                     reward_scale=1.0, reward_shift=0.0, policy_learning_rate=8e-4, value_learning_rate=3e-4)
+    run_case("infadp_lq_s4a2", kw, orc.sample_inputs("pyth_lq", 256, 13, lq_config="s4a2"), [0, 1])
+    run_case("infadp_lq_s4a2_n40", kw, orc.sample_inputs("pyth_lq", 128, 14, lq_config="s4a2"), [0, 1],
+             set_params={"forward_step": 40, "tau": 0.2, "gamma": 0.97})
+    # FHADP on LQ s3a1 wide initial box so that ClipObservation is active
+    kw = base_kwargs("pyth_lq", "FHADP", 3, 1, (64, 64), "elu", "FiniteHorizonPolicy", lq_config="s3a1",
+                     pre_horizon=20, reward_scale=0.1)
+    d = orc.sample_inputs("pyth_lq", 128, 15, lq_config="s3a1")
+    d["obs"] = d["obs"] * 4.0
+    run_case("fhadp_lq_s3a1_clip", kw, d, [0])
+
+    # INFADP idpendulum (infadp_mlp_idpendulum_serial.py)
+    kw = base_kwargs("pyth_idpendulum", "INFADP", 6, 1, (64, 64), "relu", "DetermPolicy", reward_scale=1.0)
+    run_case("infadp_idp", kw, orc.sample_inputs("pyth_idpendulum", 256, 16), [0, 1])
+
+    # C2: INFADP veh3dofconti [64,64] relu, P=10 (infadp_mlp_veh3dofconti_offserial.py:34-81)
+    kw = base_kwargs("pyth_veh3dofconti", "INFADP", 46, 2, (64, 64), "relu", "DetermPolicy", pre_horizon=10)
+    run_case("infadp_veh3dofconti", kw, orc.sample_inputs("pyth_veh3dofconti", 256, 17, pre_horizon=10), [0, 1])
+    # FHADP veh3dofconti (fhadp_mlp_veh3dofconti_serial.py:58-71), small P=H
+    kw = base_kwargs("pyth_veh3dofconti", "FHADP", 6 + 4 * 12, 2, (64, 64), "elu", "FiniteHorizonPolicy", pre_horizon=12)
+    run_case("fhadp_veh3dofconti_p12", kw, orc.sample_inputs("pyth_veh3dofconti", 128, 18, pre_horizon=12), [0])
+
+    # C3: FHADP env_gen_ocp veh3dof_tracking, FiniteHorizonPolicy elu
+    kw = base_kwargs("veh3dof_tracking", "FHADP", 6 + 4 * 10, 2, (64, 64), "elu", "FiniteHorizonPolicy", pre_horizon=10)
+    run_case("fhadp_veh3dof_tracking_p10", kw, orc.sample_inputs("veh3dof_tracking", 128, 19, pre_horizon=10), [0])
+    kw = base_kwargs("veh3dof_tracking", "FHADP", 6 + 4 * 60, 2, (256, 256), "elu", "FiniteHorizonPolicy", pre_horizon=60)
+    run_case("fhadp_veh3dof_tracking_p60_w256", kw, orc.sample_inputs("veh3dof_tracking", 32, 20, pre_horizon=60), [0])
+
+    # Known answer from a checkpoint the reference ships (results/FHADP/idpendulum)
+    ck = os.path.join(ref_shim.REFERENCE_ROOT, "results", "FHADP", "idpendulum", "apprfunc", "apprfunc_100000.pkl")
+    if os.path.exists(ck):
+        kw = base_kwargs("pyth_idpendulum", "FHADP", 6, 1, (64, 64), "gelu", "FiniteHorizonPolicy",
+                         pre_horizon=80, reward_scale=1.0, policy_learning_rate=1e-4)
+        run_case("fhadp_idp_trained_h80", kw, orc.sample_inputs("pyth_idpendulum", 256, 21), [0], load_ckpt=ck)
+        from gops.create_pkg.create_alg import create_alg
+        kw = base_kwargs("pyth_idpendulum", "FHADP", 6, 1, (64, 64), "gelu", "FiniteHorizonPolicy",
+                         pre_horizon=80, reward_scale=1.0)
+        alg = create_alg(**kw)
+        alg.load_state_dict(torch.load(ck, map_location="cpu"))
+        rec = {"sd/" + k: v for k, v in _sd(alg).items()}
+        obs = torch.tensor([[-1, 0.05, 0.05, 0, 0.1, 0.1]], dtype=torch.float32)  # example_run/run_idp_fhadp.py:19-20
+        acts = []
+        with torch.no_grad():
+            o, d, info = obs, torch.zeros(1), {}
+            for _ in range(5):
+                a = alg.networks.policy(o)          # evaluator convention: virtual_t = 1
+                acts.append(_np(a)[0])
+                o, r, d, info = alg.envmodel.forward(o, a, d, info)
+            data = {"obs": obs, "done": torch.zeros(1)}
+            loss, _ = alg._compute_loss_policy(data)
+        rec["obs0"], rec["closed_loop_actions"], rec["loss_h80"] = _np(obs), np.stack(acts), np.float64(loss.item())
+        np.savez_compressed(os.path.join(OUT, "ckpt_fhadp_idp.npz"), **rec)
+        print("ckpt_fhadp_idp", rec["closed_loop_actions"].ravel(), rec["loss_h80"])
+
+
+if __name__ == "__main__":
+    main()
