@@ -1,0 +1,176 @@
+"""Algorithm / approximate-function-container base classes (reference: gops/algorithm/base.py:24-120),
+plus the shared plumbing of the fused ADP algorithms: plan creation, batch marshalling, the single
+NCCL all-reduce of the flat gradient, and the fused Adam step."""
+import ctypes as C
+from abc import ABC, ABCMeta, abstractmethod
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from gops_b200 import _lib
+from gops_b200.create_pkg.create_apprfunc import create_apprfunc
+from gops_b200.env.fused import fill_plan_desc, make_batch
+from gops_b200.utils.common_utils import get_apprfunc_dict, set_seed
+from gops_b200.utils.flat_params import GRAD_TAIL, FlatParams
+
+
+class ApprBase(ABC, torch.nn.Module):
+    """Base class of approximate-function containers."""
+
+    def __init__(self, **kwargs):
+        super().__init__()
+        if kwargs.get("cnn_shared"):
+            raise NotImplementedError("gops_b200: cnn_shared feature networks are outside the MLP hot path")
+
+    def init_scheduler(self, **kwargs):
+        assert hasattr(self, "optimizer_dict")
+        self.scheduler_dict = {}
+        for key in [k for k in kwargs if k.endswith("_scheduler")]:
+            self.scheduler_dict[key] = getattr(torch.optim.lr_scheduler, kwargs[key]["name"])(
+                self.optimizer_dict[key.replace("_scheduler", "")], **kwargs[key]["params"])
+
+
+class AlgorithmBase(metaclass=ABCMeta):
+    """Base class of algorithms: same surface as the reference (local_update / get_remote_update_info /
+    remote_update / state_dict / set_parameters ...)."""
+
+    def __init__(self, index, **kwargs):
+        self.networks = None
+        set_seed(kwargs["trainer"], kwargs["seed"], index + 300)
+
+    @property
+    @abstractmethod
+    def adjustable_parameters(self) -> tuple:
+        ...
+
+    def set_parameters(self, param_dict):
+        for key in param_dict:
+            if hasattr(self, key) and key in self.adjustable_parameters:
+                setattr(self, key, param_dict[key])
+            else:
+                raise RuntimeError("param '" + key + "'is not adjustable in algorithm!")
+
+    def get_parameters(self):
+        return dict(zip(self.adjustable_parameters, (getattr(self, p) for p in self.adjustable_parameters)))
+
+    def state_dict(self):
+        return self.networks.state_dict()
+
+    def load_state_dict(self, state_dict):
+        self.networks.load_state_dict(state_dict)
+
+    def local_update(self, data: dict, iteration: int) -> dict:
+        tb_info = self._local_update(data, iteration)
+        for scheduler in self.networks.scheduler_dict.values():
+            scheduler.step()
+        return tb_info
+
+    def remote_update(self, update_info: dict):
+        self._remote_update(update_info)
+        for scheduler in self.networks.scheduler_dict.values():
+            scheduler.step()
+
+    def _local_update(self, data: dict, iteration: int) -> dict:
+        pass
+
+    def get_remote_update_info(self, data: dict, iteration: int) -> Tuple[dict, dict]:
+        raise NotImplementedError
+
+    def _remote_update(self, update_info: dict):
+        raise NotImplementedError
+
+    def to(self, device):
+        self.networks.to(device)
+
+    def train(self):
+        self.networks.train()
+
+    def eval(self):
+        self.networks.eval()
+
+
+class RolloutPlan:
+    """Owns one `gops_b200_plan` (C side) for a fixed (algorithm kind, horizon, gamma, env, nets)."""
+
+    def __init__(self, alg_kind: int, envmodel, policy, value, horizon: int, gamma: float):
+        desc = _lib.PlanDesc()
+        desc.alg, desc.horizon, desc.gamma = alg_kind, int(horizon), float(gamma)
+        desc.policy = policy.mlp_desc()
+        if value is not None:
+            desc.value = value.mlp_desc()
+        fill_plan_desc(desc, envmodel, policy.act_low_lim.detach().cpu().numpy(),
+                       policy.act_high_lim.detach().cpu().numpy())
+        self.handle = C.c_void_p()
+        _lib.check(_lib.lib().gops_b200_plan_create(C.byref(desc), C.byref(self.handle)))
+        _lib.check(_lib.lib().gops_b200_plan_set_gamma(self.handle, float(gamma)))
+        self.key = (alg_kind, int(horizon), float(gamma))
+
+    def __del__(self):
+        try:
+            if self.handle:
+                _lib.lib().gops_b200_plan_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+class FusedADPMixin:
+    """Shared by FHADP / INFADP: device handling, plans cache, fused rollout-gradient call."""
+
+    def _init_fused(self):
+        self._plans: Dict[tuple, RolloutPlan] = {}
+        if torch.cuda.is_available():
+            self.networks.cuda()
+
+    def _device(self) -> torch.device:
+        p = next(self.networks.parameters())
+        if not p.is_cuda:
+            if not torch.cuda.is_available():
+                raise RuntimeError("gops_b200: no CUDA device -- the fused ADP update has no CPU fallback")
+            self.networks.cuda()
+            p = next(self.networks.parameters())
+        return p.device
+
+    def _plan(self, alg_kind, policy, value, horizon, gamma) -> RolloutPlan:
+        key = (alg_kind, int(horizon), float(gamma))
+        plan = self._plans.get(key)
+        if plan is None:
+            plan = self._plans[key] = RolloutPlan(alg_kind, self.envmodel, policy, value, horizon, gamma)
+        return plan
+
+    @staticmethod
+    def _world():
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            return dist, dist.get_world_size()
+        return None, 1
+
+    def _rollout_grad(self, plan: RolloutPlan, data: dict, target: FlatParams, policy: FlatParams,
+                      value: Optional[FlatParams], vtarget: Optional[FlatParams]) -> torch.Tensor:
+        """Runs the fused kernel on this rank's shard and all-reduces [grad | loss | v-mean | #done].
+        Returns the 4-float tail as a device tensor (no host sync here)."""
+        dev = self._device()
+        base = self.envmodel.unwrapped
+        obs = data["obs"]
+        obs_d = obs.to(dev, non_blocking=True) if not obs.is_cuda else obs
+        done = data["done"]
+        done_d = done.to(dev, non_blocking=True) if not done.is_cuda else done
+        dist, world = self._world()
+        B_local = obs_d.shape[0]
+        inv_B = 1.0 / float(B_local * world)       # equal shards: mean over the global batch
+        target.bind_grads()
+        gbuf = target.gbuf
+        n = gbuf.numel() - GRAD_TAIL
+        keep = []
+        with torch.cuda.device(dev):
+            info = {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) and not v.is_cuda else v)
+                    for k, v in data.items() if k not in ("obs", "done")}
+            batch = make_batch(base, obs_d, done_d, info, keep)
+            _lib.check(_lib.lib().gops_b200_rollout_grad(
+                plan.handle, C.byref(batch), _lib.ptr(policy.sync()),
+                _lib.ptr(value.sync()) if value is not None else None,
+                _lib.ptr(vtarget.sync()) if vtarget is not None else None,
+                C.c_float(inv_B), _lib.ptr(gbuf), C.c_void_p(gbuf.data_ptr() + 4 * n), _lib.stream_ptr()))
+            if dist is not None:
+                dist.all_reduce(gbuf, op=dist.ReduceOp.SUM)     # ONE collective per optimizer step
+        return gbuf[n:]

@@ -1,0 +1,125 @@
+"""MLP approximate functions of the ADP hot path, B200 edition.
+
+Same constructor kwargs, class names, `state_dict` keys and init as the reference
+(gops/apprfunc/mlp.py: mlp() :36-41, DetermPolicy :50-77, FiniteHorizonPolicy :80-111,
+StateValue :309-329); `forward` runs the fused sm_100a inference kernel
+(`gops_b200_mlp_forward`) instead of nn.Sequential.  Training never calls `forward`: the
+algorithms hand the flat parameter vector to the fused rollout kernel.
+"""
+__all__ = ["DetermPolicy", "FiniteHorizonPolicy", "StateValue"]
+
+import ctypes as C
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from gops_b200 import _lib
+from gops_b200.utils.act_distribution_cls import Action_Distribution
+from gops_b200.utils.common_utils import activation_name, get_activation_func
+from gops_b200.utils.flat_params import FlatParams
+
+
+def mlp(sizes, activation, output_activation=nn.Identity):
+    """nn.Sequential(Linear, act, ..., Linear, out_act): parameter container with torch default init."""
+    layers = []
+    for j in range(len(sizes) - 1):
+        act = activation if j < len(sizes) - 2 else output_activation
+        layers += [nn.Linear(sizes[j], sizes[j + 1]), act()]
+    return nn.Sequential(*layers)
+
+
+def count_vars(module):
+    return sum([np.prod(p.shape) for p in module.parameters()])
+
+
+class _FusedMlp(nn.Module, Action_Distribution):
+    """Shared plumbing: shape checks, flat parameter view, ctypes descriptor, fused inference."""
+
+    _net_attr = "pi"
+    _time_input = False
+
+    def _build(self, in_dim, out_dim, kwargs):
+        hidden = list(kwargs["hidden_sizes"])
+        if len(hidden) != 2 or hidden[0] != hidden[1]:
+            raise NotImplementedError(
+                f"gops_b200 fused MLP kernels need two equal hidden layers, got hidden_sizes={hidden}")
+        self._obs_dim, self._out_dim, self._hidden = in_dim, out_dim, hidden[0]
+        self._hidden_act = kwargs["hidden_activation"]
+        self._out_act = kwargs.get("output_activation", "linear")
+        net = mlp([in_dim + int(self._time_input)] + hidden + [out_dim],
+                  get_activation_func(self._hidden_act), get_activation_func(self._out_act))
+        setattr(self, self._net_attr, net)
+        self.action_distribution_cls = kwargs["action_distribution_cls"]
+        self.__dict__["_flat_params"] = FlatParams(getattr(self, self._net_attr))
+
+    @property
+    def flat_params(self) -> FlatParams:
+        return self.__dict__["_flat_params"]
+
+    def mlp_desc(self) -> _lib.MlpDesc:
+        return _lib.MlpDesc(self._obs_dim, int(self._time_input), self._hidden, self._out_dim,
+                            _lib.ACT_IDS[self._hidden_act], _lib.ACT_IDS[self._out_act])
+
+    def _infer(self, obs: torch.Tensor, virtual_t: float, squash: bool) -> torch.Tensor:
+        flat = self.flat_params.sync()
+        if not flat.is_cuda:
+            raise RuntimeError("gops_b200 apprfuncs run on a CUDA device only (no CPU fallback); call .cuda()")
+        src_dev = obs.device
+        x = obs.detach().to(flat.device, torch.float32)
+        squeeze = x.dim() == 1
+        x = x.reshape(-1, self._obs_dim).contiguous()
+        out = torch.empty((x.shape[0], self._out_dim), dtype=torch.float32, device=flat.device)
+        lo = hi = None
+        if squash:
+            lo = (C.c_float * self._out_dim)(*self.act_low_lim.detach().cpu().tolist())
+            hi = (C.c_float * self._out_dim)(*self.act_high_lim.detach().cpu().tolist())
+        desc = self.mlp_desc()
+        with torch.cuda.device(flat.device):
+            _lib.check(_lib.lib().gops_b200_mlp_forward(
+                C.byref(desc), _lib.ptr(flat), _lib.ptr(x), x.shape[0], float(virtual_t), lo, hi,
+                _lib.ptr(out), _lib.stream_ptr()))
+        if squeeze:
+            out = out[0]
+        return out.to(src_dev)
+
+
+class DetermPolicy(_FusedMlp):
+    """Deterministic policy: obs -> action (reference mlp.py:50-77)."""
+
+    def __init__(self, **kwargs):
+        super().__init__()
+        self._build(kwargs["obs_dim"], kwargs["act_dim"], kwargs)
+        self.register_buffer("act_high_lim", torch.from_numpy(np.asarray(kwargs["act_high_lim"], dtype=np.float32)))
+        self.register_buffer("act_low_lim", torch.from_numpy(np.asarray(kwargs["act_low_lim"], dtype=np.float32)))
+
+    def forward(self, obs):
+        return self._infer(obs, 0.0, squash=True)
+
+
+class FiniteHorizonPolicy(_FusedMlp):
+    """Finite-horizon deterministic policy: (obs, virtual_t) -> action (reference mlp.py:80-111)."""
+
+    _time_input = True
+
+    def __init__(self, **kwargs):
+        super().__init__()
+        self._build(kwargs["obs_dim"], kwargs["act_dim"], kwargs)
+        self.register_buffer("act_high_lim", torch.from_numpy(np.asarray(kwargs["act_high_lim"], dtype=np.float32)))
+        self.register_buffer("act_low_lim", torch.from_numpy(np.asarray(kwargs["act_low_lim"], dtype=np.float32)))
+
+    def forward(self, obs, virtual_t=1):
+        return self._infer(obs, float(virtual_t), squash=True)
+
+
+class StateValue(_FusedMlp):
+    """State-value function: obs -> v (reference mlp.py:309-329)."""
+
+    _net_attr = "v"
+
+    def __init__(self, **kwargs):
+        super().__init__()
+        self._build(kwargs["obs_dim"], 1, kwargs)
+
+    def forward(self, obs):
+        return torch.squeeze(self._infer(obs, 0.0, squash=False), -1)

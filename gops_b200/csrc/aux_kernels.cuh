@@ -1,0 +1,70 @@
+// Small non-template kernels (packing, partial reduction, Adam, Polyak); included by gops_b200.cu only.
+#pragma once
+#include "rollout.cuh"
+
+namespace gops {
+
+// ---------------------------------------------------------------------------------------------
+// torch-layout flat parameters -> packed blob (both orientations of W1/W2, 16-byte aligned parts)
+// ---------------------------------------------------------------------------------------------
+__global__ void pack_params_kernel(const float* __restrict__ flat, NetL L, float* __restrict__ blob) {
+  const int n = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
+  const float* W1 = flat + L.g_w1;
+  const float* W2 = flat + L.g_w2;
+  const float* W3 = flat + L.g_w3;
+  for (int i = t0; i < L.in * HID; i += n) {
+    const int k = i / HID, o = i - k * HID;
+    blob[L.o_w1t + i] = W1[o * L.in + k];
+  }
+  for (int i = t0; i < HID * L.inp; i += n) {
+    const int o = i / L.inp, k = i - o * L.inp;
+    blob[L.o_w1 + i] = k < L.in ? W1[o * L.in + k] : 0.f;
+  }
+  for (int i = t0; i < HID * HID; i += n) {
+    const int k = i / HID, o = i - k * HID;
+    blob[L.o_w2t + i] = W2[o * HID + k];
+    blob[L.o_w2 + i] = W2[i];
+  }
+  for (int i = t0; i < L.out * HID; i += n) blob[L.o_w3 + i] = W3[i];
+  for (int i = t0; i < HID; i += n) {
+    blob[L.o_b1 + i] = flat[L.g_b1 + i];
+    blob[L.o_b2 + i] = flat[L.g_b2 + i];
+  }
+  for (int i = t0; i < 4; i += n) blob[L.o_b3 + i] = i < L.out ? flat[L.g_b3 + i] : 0.f;
+}
+
+// grad[i] = sum_c partial[c][i] in fixed CTA order; the 3 trailing scalars go to scalars_out
+__global__ void reduce_partials_kernel(const float* __restrict__ partial, int n_cta, int stride, int nparam,
+                                       float* __restrict__ grad, float* __restrict__ scalars) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nparam + 3) return;
+  float s = 0.f;
+  for (int c = 0; c < n_cta; ++c) s += partial[(size_t)c * stride + i];
+  if (i < nparam) {
+    if (grad) grad[i] = s;
+  } else if (scalars) {
+    scalars[i - nparam] = s;
+  }
+}
+
+// torch.optim.Adam, single tensor path (torch/optim/adam.py _single_tensor_adam, no amsgrad/decay)
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, long long n, float omb1, float b2, float omb2, float eps,
+                            float step_size, float bc2_sqrt) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float gi = g[i];
+  const float mi = m[i] + (gi - m[i]) * omb1;           // exp_avg.lerp_(grad, 1 - beta1)
+  const float vi = v[i] * b2 + omb2 * (gi * gi);         // exp_avg_sq.mul_(beta2).addcmul_(g, g, 1-beta2)
+  m[i] = mi;
+  v[i] = vi;
+  const float denom = sqrtf(vi) / bc2_sqrt + eps;              // (sqrt / bias_correction2_sqrt).add_(eps)
+  p[i] = p[i] - step_size * (mi / denom);                      // addcdiv_(exp_avg, denom, value=-step_size)
+}
+
+__global__ void polyak_kernel(float* __restrict__ tgt, const float* __restrict__ src, float tau, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) tgt[i] = tgt[i] * (1.f - tau) + tau * src[i];
+}
+
+}  // namespace gops

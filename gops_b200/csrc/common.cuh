@@ -1,0 +1,98 @@
+// Device-side helpers shared by the gops_b200 kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "gops_b200.h"
+
+namespace gops {
+
+constexpr int MAXA = GOPS_B200_MAX_ACT;
+constexpr int LQN = GOPS_B200_MAX_LQ_N;
+
+// ---------------------------------------------------------------------------------------------
+// mbarrier + TMA (cp.async.bulk) primitives: weights are staged global -> shared by the bulk-copy
+// engine (SASS: UBLKCP) and signalled through an mbarrier transaction count.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// Activations (gops/utils/common_utils.py:26-55 -> torch.nn.{ReLU,ELU,GELU,SELU,Sigmoid,Tanh,Identity})
+// h = g(x), d = g'(x) in fp32 with the accurate libdevice functions (no fast-math).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float act_fwd(int act, float x) {
+  switch (act) {
+    case GOPS_ACT_RELU: return fmaxf(x, 0.f);
+    case GOPS_ACT_ELU: return x > 0.f ? x : expm1f(x);
+    case GOPS_ACT_GELU: return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f));
+    case GOPS_ACT_SELU: return 1.0507009873554805f * (x > 0.f ? x : 1.6732632423543772f * expm1f(x));
+    case GOPS_ACT_SIGMOID: return 1.f / (1.f + expf(-x));
+    case GOPS_ACT_TANH: return tanhf(x);
+    default: return x;
+  }
+}
+__device__ __forceinline__ void act_fwd_grad(int act, float x, float& h, float& d) {
+  switch (act) {
+    case GOPS_ACT_RELU: h = fmaxf(x, 0.f); d = x > 0.f ? 1.f : 0.f; break;
+    case GOPS_ACT_ELU:
+      if (x > 0.f) { h = x; d = 1.f; } else { float e = expf(x); h = expm1f(x); d = e; }
+      break;
+    case GOPS_ACT_GELU: {
+      float cdf = 0.5f * (1.f + erff(x * 0.70710678118654752440f));
+      float pdf = 0.39894228040143267794f * expf(-0.5f * x * x);
+      h = x * cdf; d = cdf + x * pdf;
+    } break;
+    case GOPS_ACT_SELU: {
+      const float sc = 1.0507009873554805f, al = 1.6732632423543772f;
+      if (x > 0.f) { h = sc * x; d = sc; } else { h = sc * al * expm1f(x); d = sc * al * expf(x); }
+    } break;
+    case GOPS_ACT_SIGMOID: h = 1.f / (1.f + expf(-x)); d = h * (1.f - h); break;
+    case GOPS_ACT_TANH: h = tanhf(x); d = 1.f - h * h; break;
+    default: h = x; d = 1.f; break;
+  }
+}
+
+// angle_normalize, gops/utils/math_utils.py:8-11: ((x + pi) % (2 pi)) - pi with floored modulo,
+// evaluated in fp32 like torch.remainder on a float32 tensor.
+__device__ __forceinline__ float angle_normalize(float x) {
+  const float PI_F = 3.14159265358979323846f, TWO_PI_F = 6.28318530717958647692f;
+  float y = __fadd_rn(x, PI_F);
+  float r = fmodf(y, TWO_PI_F);
+  if (r != 0.f && r < 0.f) r = __fadd_rn(r, TWO_PI_F);
+  return __fsub_rn(r, PI_F);
+}
+
+}  // namespace gops

@@ -1,0 +1,509 @@
+// libgops_b200.so: C ABI (include/gops_b200.h) over the fused sm_100a rollout kernels.
+#include "gops_b200.h"
+
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+#include <string>
+#include <vector>
+
+#include "kernel.cuh"
+#include "aux_kernels.cuh"
+
+using namespace gops;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(const std::string& msg) {
+  g_err = msg;
+  return 1;
+}
+#define CUDA_OK(expr)                                                                          \
+  do {                                                                                         \
+    cudaError_t e__ = (expr);                                                                  \
+    if (e__ != cudaSuccess)                                                                    \
+      return fail(std::string(#expr) + ": " + cudaGetErrorString(e__));                        \
+  } while (0)
+
+int round4(int x) { return (x + 3) & ~3; }
+
+bool make_net(const gops_b200_mlp_desc& d, NetL& L, std::string& why) {
+  memset(&L, 0, sizeof(L));
+  if (d.hidden != HID) { why = "hidden width " + std::to_string(d.hidden) + " not built (supported: 64)"; return false; }
+  if (d.out_dim < 1 || d.out_dim > MAXA) { why = "out_dim out of range"; return false; }
+  if (d.out_act != GOPS_ACT_LINEAR) { why = "output_activation other than 'linear' is not supported"; return false; }
+  if (d.hidden_act < 0 || d.hidden_act > GOPS_ACT_LINEAR) { why = "bad hidden activation"; return false; }
+  L.obs = d.in_dim;
+  L.time_input = d.time_input ? 1 : 0;
+  L.in = d.in_dim + L.time_input;
+  L.inp = round4(L.in);
+  L.out = d.out_dim;
+  L.hact = d.hidden_act;
+  L.oact = d.out_act;
+  int o = 0;
+  L.o_w1t = o; o += round4(L.in * HID);
+  L.o_w1 = o; o += HID * L.inp;
+  L.o_w2t = o; o += HID * HID;
+  L.o_w2 = o; o += HID * HID;
+  L.o_w3 = o; o += round4(L.out * HID);
+  L.o_b1 = o; o += HID;
+  L.o_b2 = o; o += HID;
+  L.o_b3 = o; o += 4;
+  L.blob = o;
+  int g = 0;
+  L.g_w1 = g; g += HID * L.in;
+  L.g_b1 = g; g += HID;
+  L.g_w2 = g; g += HID * HID;
+  L.g_b2 = g; g += HID;
+  L.g_w3 = g; g += L.out * HID;
+  L.g_b3 = g; g += L.out;
+  L.nparam = g;
+  return true;
+}
+
+struct Config {
+  int S, NT;
+};
+const Config kConfigs[] = {{128, 256}, {64, 256}, {32, 128}};
+
+typedef void (*RolloutFn)(const KParams);
+typedef void (*StepFn)(const KParams, const float*, int, float*, float*, float*);
+
+}  // namespace
+
+// one translation unit per env model (kernels_<model>.cu), compiled in parallel
+namespace gops {
+RolloutFn rollout_fn_idp(int cfg);
+RolloutFn rollout_fn_lq(int cfg);
+StepFn step_fn_idp();
+StepFn step_fn_lq();
+}  // namespace gops
+
+namespace {
+
+RolloutFn rollout_fn(int model, int cfg) {
+  switch (model) {
+    case GOPS_MODEL_IDPENDULUM: return rollout_fn_idp(cfg);
+    case GOPS_MODEL_LQ: return rollout_fn_lq(cfg);
+    default: return nullptr;
+  }
+}
+StepFn step_fn(int model) {
+  switch (model) {
+    case GOPS_MODEL_IDPENDULUM: return step_fn_idp();
+    case GOPS_MODEL_LQ: return step_fn_lq();
+    default: return nullptr;
+  }
+}
+int model_ns(int model) { return model == GOPS_MODEL_LQ ? LQN : 6; }
+
+}  // namespace
+
+struct gops_b200_plan {
+  gops_b200_plan_desc desc;
+  KParams kp;
+  int device = 0, sm_count = 0, max_smem = 0;
+  float *blob_pol = nullptr, *blob_val = nullptr, *blob_vtg = nullptr, *gpow = nullptr;
+  float* tape = nullptr;
+  size_t tape_floats = 0;
+  float* partial = nullptr;
+  size_t partial_floats = 0;
+  bool attr_set[8][4] = {};
+  bool timing = false;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int last_grid = 0, last_S = 0, last_NT = 0;
+  size_t last_smem = 0;
+};
+
+namespace {
+
+size_t rollout_smem_bytes(const KParams& kp, int S) {
+  const int SP = S + 4;
+  return sizeof(float) * (size_t)(4 + kp.w_floats + kp.dw_floats + kp.inp_max * SP + 4 * HID * SP + 4 * SP);
+}
+size_t infer_smem_bytes(const KParams& kp, int S) {
+  const int SP = S + 4;
+  return sizeof(float) * (size_t)(4 + kp.w_floats + kp.inp_max * SP + 2 * HID * SP + 4 * SP);
+}
+
+int pick_config(const gops_b200_plan* pl, long long B, bool infer) {
+  int best = -1;
+  for (int c = 0; c < 3; ++c) {
+    const size_t sm = infer ? infer_smem_bytes(pl->kp, kConfigs[c].S) : rollout_smem_bytes(pl->kp, kConfigs[c].S);
+    if (sm > (size_t)pl->max_smem) continue;
+    if (best < 0) best = c;
+    const long long tiles = (B + kConfigs[c].S - 1) / kConfigs[c].S;
+    if (tiles >= pl->sm_count) return c;   // largest tile that still fills every SM
+    best = c;                              // otherwise keep shrinking the tile
+  }
+  return best;
+}
+
+int ensure_scratch(gops_b200_plan* pl, int grid, int S, int H) {
+  const size_t need_tape = (size_t)grid * H * (model_ns(pl->desc.model) + 1) * S;
+  if (need_tape > pl->tape_floats) {
+    if (pl->tape) cudaFree(pl->tape);
+    pl->tape = nullptr;
+    CUDA_OK(cudaMalloc(&pl->tape, need_tape * sizeof(float)));
+    pl->tape_floats = need_tape;
+  }
+  const size_t need_part = (size_t)grid * pl->kp.part_stride;
+  if (need_part > pl->partial_floats) {
+    if (pl->partial) cudaFree(pl->partial);
+    pl->partial = nullptr;
+    CUDA_OK(cudaMalloc(&pl->partial, need_part * sizeof(float)));
+    pl->partial_floats = need_part;
+  }
+  return 0;
+}
+
+int launch_pack(const float* flat, const NetL& L, float* blob, cudaStream_t st) {
+  pack_params_kernel<<<8, 256, 0, st>>>(flat, L, blob);
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int launch_rollout(gops_b200_plan* pl, const gops_b200_batch* b, int alg, cudaStream_t st, float* grad_out,
+                   float* scalars_out) {
+  if (!b || b->batch <= 0) return fail("empty batch");
+  if (!b->obs || !b->done) return fail("obs/done pointers are required");
+  KParams& kp = pl->kp;
+  const int cfg = pick_config(pl, b->batch, false);
+  if (cfg < 0) return fail("no kernel configuration fits in shared memory");
+  const int S = kConfigs[cfg].S, NT = kConfigs[cfg].NT;
+  RolloutFn fn = rollout_fn(pl->desc.model, cfg);
+  if (!fn) return fail("env model kind not built into this library");
+  kp.alg = alg;
+  kp.batch = b->batch;
+  kp.n_tiles = (int)((b->batch + S - 1) / S);
+  kp.obs = b->obs; kp.done = b->done; kp.state = b->state; kp.ref_points = b->ref_points;
+  kp.path_num = b->path_num; kp.u_num = b->u_num; kp.ref_time = b->ref_time; kp.reference = b->reference;
+  kp.ref_t = b->ref_t;
+  const int grid = kp.n_tiles < pl->sm_count ? kp.n_tiles : pl->sm_count;
+  const NetL& upd = (alg == ALG_PEV) ? kp.val : kp.pol;
+  kp.part_stride = round4(upd.nparam + 4);
+  kp.dw_floats = round4(upd.nparam);
+  if (ensure_scratch(pl, grid, S, kp.horizon)) return 1;
+  kp.tape = pl->tape;
+  kp.partial = pl->partial;
+  const size_t smem = rollout_smem_bytes(kp, S);
+  if (!pl->attr_set[pl->desc.model][cfg]) {
+    CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, pl->max_smem));
+    pl->attr_set[pl->desc.model][cfg] = true;
+  }
+  if (pl->timing) CUDA_OK(cudaEventRecord(pl->ev0, st));
+  fn<<<grid, NT, smem, st>>>(kp);
+  CUDA_OK(cudaGetLastError());
+  if (pl->timing) CUDA_OK(cudaEventRecord(pl->ev1, st));
+  pl->last_grid = grid; pl->last_S = S; pl->last_NT = NT; pl->last_smem = smem;
+  if (alg != ALG_TRACE) {
+    const int n = upd.nparam + 3;
+    reduce_partials_kernel<<<(n + 255) / 256, 256, 0, st>>>(pl->partial, grid, kp.part_stride, upd.nparam, grad_out,
+                                                           scalars_out);
+    CUDA_OK(cudaGetLastError());
+  }
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int gops_b200_version(void) { return GOPS_B200_ABI_VERSION; }
+const char* gops_b200_last_error(void) { return g_err.c_str(); }
+
+int gops_b200_plan_create(const gops_b200_plan_desc* d, gops_b200_plan** out) {
+  if (!d || !out) return fail("null argument");
+  *out = nullptr;
+  if (d->alg < GOPS_ALG_FHADP || d->alg > GOPS_ALG_INFADP_VALUE) return fail("unknown algorithm kind");
+  if (d->horizon < 1 || d->horizon > 4096) return fail("horizon out of range");
+  if (!rollout_fn(d->model, 0)) return fail("env model kind not built into this library");
+  gops_b200_plan* pl = new (std::nothrow) gops_b200_plan();
+  if (!pl) return fail("out of host memory");
+  pl->desc = *d;
+  KParams& kp = pl->kp;
+  memset(&kp, 0, sizeof(kp));
+  std::string why;
+  if (!make_net(d->policy, kp.pol, why)) { delete pl; return fail("policy: " + why); }
+  const bool infadp = d->alg != GOPS_ALG_FHADP;
+  if (infadp) {
+    if (!make_net(d->value, kp.val, why)) { delete pl; return fail("value: " + why); }
+    if (d->value.out_dim != 1 || d->value.time_input) { delete pl; return fail("value net must be StateValue (out 1)"); }
+    if (d->value.in_dim != d->policy.in_dim) { delete pl; return fail("value/policy obs dims differ"); }
+  } else {
+    kp.val = kp.pol;
+  }
+  const int act_dim = d->policy.out_dim;
+  int obs_dim_model = 0;
+  if (d->model == GOPS_MODEL_IDPENDULUM) obs_dim_model = 6;
+  if (d->model == GOPS_MODEL_LQ) {
+    if (d->lq_n < 1 || d->lq_n > LQN || d->lq_m < 1 || d->lq_m > MAXA) { delete pl; return fail("lq dims out of range"); }
+    obs_dim_model = d->lq_n;
+    if (act_dim != d->lq_m) { delete pl; return fail("policy out_dim != lq action dim"); }
+  }
+  if (d->policy.in_dim != obs_dim_model) { delete pl; return fail("policy in_dim does not match the env model obs_dim"); }
+  if (d->model == GOPS_MODEL_IDPENDULUM && act_dim != 1) { delete pl; return fail("idpendulum has 1 action"); }
+
+  kp.horizon = d->horizon;
+  kp.gamma = d->gamma;
+  kp.w_floats = kp.pol.blob > kp.val.blob ? kp.pol.blob : kp.val.blob;
+  kp.inp_max = kp.pol.inp > kp.val.inp ? kp.pol.inp : kp.val.inp;
+  kp.dw_floats = round4(kp.pol.nparam > kp.val.nparam ? kp.pol.nparam : kp.val.nparam);
+  kp.action_scale = d->action_scale; kp.clip_action = d->clip_action; kp.mask_at_done = d->mask_at_done;
+  kp.reward_shaping = d->reward_shaping; kp.reward_shift = d->reward_shift; kp.reward_scale = d->reward_scale;
+  bool finite_obs_bound = false;
+  for (int j = 0; j < MAXA; ++j) {
+    kp.min_action[j] = d->min_action[j]; kp.max_action[j] = d->max_action[j];
+    kp.act_low[j] = d->act_low[j]; kp.act_high[j] = d->act_high[j];
+    // (act_high_lim - act_low_lim) / 2 and (act_high_lim + act_low_lim) / 2 in fp32, mlp.py:74-76
+    kp.pol_half[j] = (d->pol_act_high[j] - d->pol_act_low[j]) / 2.f;
+    kp.pol_mid[j] = (d->pol_act_high[j] + d->pol_act_low[j]) / 2.f;
+  }
+  for (int f = 0; f < LQN; ++f) {
+    kp.obs_low[f] = f < obs_dim_model ? d->obs_low[f] : -INFINITY;
+    kp.obs_high[f] = f < obs_dim_model ? d->obs_high[f] : INFINITY;
+    if (isfinite(kp.obs_low[f]) || isfinite(kp.obs_high[f])) finite_obs_bound = true;
+  }
+  kp.clip_obs = (d->clip_obs && finite_obs_bound) ? 1 : 0;   // clipping to +-inf is the identity
+  kp.lq_n = d->lq_n; kp.lq_m = d->lq_m; kp.lq_dt = d->lq_dt; kp.lq_rs = d->lq_reward_scale; kp.lq_rsh = d->lq_reward_shift;
+  if (d->model == GOPS_MODEL_LQ) {
+    for (int i = 0; i < d->lq_n; ++i) {
+      for (int j = 0; j < d->lq_n; ++j) kp.lq_inv_IA[i * LQN + j] = d->lq_inv_IA[i * d->lq_n + j];
+      for (int j = 0; j < d->lq_m; ++j) kp.lq_B[i * MAXA + j] = d->lq_B[i * d->lq_m + j];
+      kp.lq_Q[i] = d->lq_Q[i];
+    }
+    for (int j = 0; j < d->lq_m; ++j) kp.lq_R[j] = d->lq_R[j];
+  }
+  kp.rt = d->reftraj;
+  kp.veh_P = d->veh_pre_horizon;
+  kp.ref_len = d->veh_ref_len;
+
+  cudaError_t e = cudaGetDevice(&pl->device);
+  cudaDeviceProp prop;
+  if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, pl->device);
+  if (e != cudaSuccess) { delete pl; return fail(std::string("no CUDA device: ") + cudaGetErrorString(e)); }
+  if (prop.major < 10) { delete pl; return fail("gops_b200 requires an sm_100a (B200) device"); }
+  pl->sm_count = prop.multiProcessorCount;
+  pl->max_smem = (int)prop.sharedMemPerBlockOptin;
+
+  std::vector<float> gp(d->horizon + 1);
+  for (int k = 0; k <= d->horizon; ++k) gp[k] = (float)pow((double)d->gamma, (double)k);
+  // note: python evaluates `gamma ** k` on the python float the caller passed; d->gamma is that value
+  // rounded to fp32, so callers that need bit parity for non-representable gammas can update gpow via
+  // gops_b200_plan_set_gamma (below) with the double value.
+  if (cudaMalloc(&pl->gpow, gp.size() * sizeof(float)) != cudaSuccess ||
+      cudaMalloc(&pl->blob_pol, kp.w_floats * sizeof(float)) != cudaSuccess ||
+      cudaMalloc(&pl->blob_val, kp.w_floats * sizeof(float)) != cudaSuccess ||
+      cudaMalloc(&pl->blob_vtg, kp.w_floats * sizeof(float)) != cudaSuccess) {
+    gops_b200_plan_destroy(pl);
+    return fail("cudaMalloc failed for plan scratch");
+  }
+  cudaMemcpy(pl->gpow, gp.data(), gp.size() * sizeof(float), cudaMemcpyHostToDevice);
+  cudaMemset(pl->blob_pol, 0, kp.w_floats * sizeof(float));
+  cudaMemset(pl->blob_val, 0, kp.w_floats * sizeof(float));
+  cudaMemset(pl->blob_vtg, 0, kp.w_floats * sizeof(float));
+  kp.gpow = pl->gpow;
+  kp.blob_pol = pl->blob_pol; kp.blob_val = pl->blob_val; kp.blob_vtg = pl->blob_vtg;
+  *out = pl;
+  return 0;
+}
+
+int gops_b200_plan_set_gamma(gops_b200_plan* pl, double gamma) {
+  if (!pl) return fail("null plan");
+  std::vector<float> gp(pl->kp.horizon + 1);
+  for (int k = 0; k <= pl->kp.horizon; ++k) gp[k] = (float)pow(gamma, (double)k);
+  pl->kp.gamma = (float)gamma;
+  CUDA_OK(cudaMemcpy(pl->gpow, gp.data(), gp.size() * sizeof(float), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+int gops_b200_plan_enable_timing(gops_b200_plan* pl, int enable) {
+  if (!pl) return fail("null plan");
+  if (enable && !pl->ev0) {
+    CUDA_OK(cudaEventCreate(&pl->ev0));
+    CUDA_OK(cudaEventCreate(&pl->ev1));
+  }
+  pl->timing = enable != 0;
+  return 0;
+}
+
+int gops_b200_plan_last_kernel_ms(gops_b200_plan* pl, float* ms) {
+  if (!pl || !ms || !pl->ev0) return fail("timing not enabled");
+  CUDA_OK(cudaEventSynchronize(pl->ev1));
+  CUDA_OK(cudaEventElapsedTime(ms, pl->ev0, pl->ev1));
+  return 0;
+}
+
+int gops_b200_plan_launch_info(const gops_b200_plan* pl, int32_t* out4) {
+  if (!pl || !out4) return fail("null argument");
+  out4[0] = pl->last_grid; out4[1] = pl->last_NT; out4[2] = pl->last_S; out4[3] = (int32_t)pl->last_smem;
+  return 0;
+}
+
+int gops_b200_plan_destroy(gops_b200_plan* pl) {
+  if (!pl) return 0;
+  if (pl->ev0) { cudaEventDestroy(pl->ev0); cudaEventDestroy(pl->ev1); }
+  cudaFree(pl->gpow); cudaFree(pl->blob_pol); cudaFree(pl->blob_val); cudaFree(pl->blob_vtg);
+  cudaFree(pl->tape); cudaFree(pl->partial);
+  delete pl;
+  return 0;
+}
+
+int64_t gops_b200_plan_param_count(const gops_b200_plan* pl, int which) {
+  if (!pl) return -1;
+  return which == 0 ? pl->kp.pol.nparam : pl->kp.val.nparam;
+}
+
+int gops_b200_rollout_grad(gops_b200_plan* pl, const gops_b200_batch* b, const float* policy_params,
+                           const float* value_params, const float* vtarget_params, float inv_batch_global,
+                           float* grad_out, float* scalars_out, void* stream) {
+  if (!pl || !policy_params || !grad_out || !scalars_out) return fail("null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int alg = pl->desc.alg;
+  if (launch_pack(policy_params, pl->kp.pol, pl->blob_pol, st)) return 1;
+  if (alg != GOPS_ALG_FHADP) {
+    if (!vtarget_params) return fail("vtarget_params required for INFADP");
+    if (launch_pack(vtarget_params, pl->kp.val, pl->blob_vtg, st)) return 1;
+  }
+  if (alg == GOPS_ALG_INFADP_VALUE) {
+    if (!value_params) return fail("value_params required for INFADP value update");
+    if (launch_pack(value_params, pl->kp.val, pl->blob_val, st)) return 1;
+  }
+  pl->kp.inv_B = inv_batch_global;
+  pl->kp.tr_obs = pl->kp.tr_act = pl->kp.tr_rew = pl->kp.tr_done = nullptr;
+  return launch_rollout(pl, b, alg, st, grad_out, scalars_out);
+}
+
+int gops_b200_rollout_trace(gops_b200_plan* pl, const gops_b200_batch* b, const float* policy_params, float* obs_out,
+                            float* act_out, float* rew_out, float* done_out, void* stream) {
+  if (!pl || !policy_params) return fail("null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (launch_pack(policy_params, pl->kp.pol, pl->blob_pol, st)) return 1;
+  pl->kp.inv_B = 1.f;
+  pl->kp.tr_obs = obs_out; pl->kp.tr_act = act_out; pl->kp.tr_rew = rew_out; pl->kp.tr_done = done_out;
+  return launch_rollout(pl, b, ALG_TRACE, st, nullptr, nullptr);
+}
+
+static int infer_common(gops_b200_plan* pl, const float* params, int use_val, const float* obs, int64_t batch,
+                        float virtual_t, float* out, void* stream, bool squash) {
+  if (!pl || !params || !obs || !out) return fail("null argument");
+  if (batch <= 0) return fail("empty batch");
+  cudaStream_t st = (cudaStream_t)stream;
+  const NetL& L = use_val ? pl->kp.val : pl->kp.pol;
+  float* blob = use_val ? pl->blob_val : pl->blob_pol;
+  if (launch_pack(params, L, blob, st)) return 1;
+  const int cfg = pick_config(pl, batch, true);
+  if (cfg < 0) return fail("no kernel configuration fits in shared memory");
+  const int S = kConfigs[cfg].S;
+  const long long tiles = (batch + S - 1) / S;
+  const int grid = (int)(tiles < pl->sm_count ? tiles : pl->sm_count);
+  const size_t smem = infer_smem_bytes(pl->kp, S);
+#define LAUNCH_INFER(SS, NN)                                                                                  \
+  do {                                                                                                        \
+    CUDA_OK(cudaFuncSetAttribute(mlp_infer_kernel<SS, NN>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
+                                 pl->max_smem));                                                              \
+    mlp_infer_kernel<SS, NN><<<grid, NN, smem, st>>>(pl->kp, blob, use_val, obs, batch, virtual_t,            \
+                                                     squash ? 1 : 0, out);                                   \
+  } while (0)
+  if (cfg == 0) LAUNCH_INFER(128, 256);
+  else if (cfg == 1) LAUNCH_INFER(64, 256);
+  else LAUNCH_INFER(32, 128);
+#undef LAUNCH_INFER
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int gops_b200_policy_forward(gops_b200_plan* pl, const float* policy_params, const float* obs, int64_t batch,
+                             float virtual_t, float* act_out, void* stream) {
+  return infer_common(pl, policy_params, 0, obs, batch, virtual_t, act_out, stream, true);
+}
+
+int gops_b200_value_forward(gops_b200_plan* pl, const float* value_params, const float* obs, int64_t batch,
+                            float* v_out, void* stream) {
+  if (pl && pl->desc.alg == GOPS_ALG_FHADP) return fail("plan has no value network");
+  return infer_common(pl, value_params, 1, obs, batch, 0.f, v_out, stream, false);
+}
+
+int gops_b200_mlp_forward(const gops_b200_mlp_desc* net, const float* params, const float* obs, int64_t batch,
+                          float virtual_t, const float* act_low, const float* act_high, float* out, void* stream) {
+  if (!net || !params || !obs || !out) return fail("null argument");
+  if (batch <= 0) return fail("empty batch");
+  static thread_local gops_b200_plan* scratch = nullptr;   // reusable staging blob per host thread
+  static thread_local int scratch_floats = 0;
+  gops_b200_plan tmp;
+  KParams& kp = tmp.kp;
+  memset(&kp, 0, sizeof(kp));
+  std::string why;
+  if (!make_net(*net, kp.pol, why)) return fail(why);
+  kp.val = kp.pol;
+  kp.w_floats = kp.pol.blob;
+  kp.inp_max = kp.pol.inp;
+  for (int j = 0; j < net->out_dim; ++j) {
+    kp.pol_half[j] = act_low ? (act_high[j] - act_low[j]) / 2.f : 1.f;
+    kp.pol_mid[j] = act_low ? (act_high[j] + act_low[j]) / 2.f : 0.f;
+  }
+  cudaDeviceProp prop;
+  int dev = 0;
+  CUDA_OK(cudaGetDevice(&dev));
+  CUDA_OK(cudaGetDeviceProperties(&prop, dev));
+  tmp.sm_count = prop.multiProcessorCount;
+  tmp.max_smem = (int)prop.sharedMemPerBlockOptin;
+  if (!scratch || scratch_floats < kp.w_floats) {
+    if (scratch) { cudaFree(scratch->blob_pol); delete scratch; }
+    scratch = new gops_b200_plan();
+    scratch_floats = kp.w_floats;
+    CUDA_OK(cudaMalloc(&scratch->blob_pol, (size_t)scratch_floats * sizeof(float)));
+  }
+  tmp.blob_pol = scratch->blob_pol;
+  const int rc = infer_common(&tmp, params, 0, obs, batch, virtual_t, out, stream, act_low != nullptr);
+  tmp.blob_pol = nullptr;
+  return rc;
+}
+
+int gops_b200_model_step(gops_b200_plan* pl, const gops_b200_batch* b, const float* action, float* next_obs,
+                         float* reward, float* next_done, float* next_state, float* next_ref_points,
+                         float* next_ref_time, void* stream) {
+  if (!pl || !b || !action || !next_obs || !reward || !next_done) return fail("null argument");
+  if (b->batch <= 0 || !b->obs || !b->done) return fail("bad batch");
+  (void)next_state; (void)next_ref_points; (void)next_ref_time;
+  KParams& kp = pl->kp;
+  kp.batch = b->batch; kp.obs = b->obs; kp.done = b->done;
+  const unsigned grid = (unsigned)((b->batch + 127) / 128);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int act_dim = pl->desc.policy.out_dim;
+  StepFn fn = step_fn(pl->desc.model);
+  if (!fn) return fail("model_step: env model kind not built into this library");
+  fn<<<grid, 128, 0, st>>>(kp, action, act_dim, next_obs, reward, next_done);
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int gops_b200_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                        int32_t step, double lr, double beta1, double beta2, double eps, void* stream) {
+  if (!params || !grads || !exp_avg || !exp_avg_sq) return fail("null argument");
+  if (n <= 0 || step < 1) return fail("bad n/step");
+  // python-side scalars of torch/optim/adam.py are doubles; only the tensor math is fp32
+  const double bc1 = 1.0 - pow(beta1, (double)step);
+  const double bc2 = 1.0 - pow(beta2, (double)step);
+  const float step_size = (float)(lr / bc1);
+  const float bc2_sqrt = (float)sqrt(bc2);
+  adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      params, grads, exp_avg, exp_avg_sq, n, (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2), (float)eps,
+      step_size, bc2_sqrt);
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int gops_b200_polyak(float* target, const float* src, float tau, int64_t n, void* stream) {
+  if (!target || !src || n <= 0) return fail("bad argument");
+  polyak_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(target, src, tau, n);
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"

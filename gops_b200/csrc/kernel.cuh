@@ -1,0 +1,351 @@
+// The fused rollout kernel template: forward sweep, terminal value, reverse sweep, gradient partials.
+#pragma once
+#include "models.cuh"
+
+namespace gops {
+
+template <class M, int S, int NT>
+__global__ void __launch_bounds__(NT, 1) rollout_kernel(const __grid_constant__ KParams p) {
+  constexpr int SP = S + 4, NS = M::NS, TC = NS + 1;
+  extern __shared__ __align__(16) float smem[];
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(smem);
+  Tiles t;
+  t.W = smem + 4;
+  t.dW = t.W + p.w_floats;
+  t.X = t.dW + p.dw_floats;
+  t.H1 = t.X + p.inp_max * SP;
+  t.D1 = t.H1 + HID * SP;
+  t.H2 = t.D1 + HID * SP;
+  t.D2 = t.H2 + HID * SP;
+  t.Z = t.D2 + HID * SP;
+
+  const int tid = threadIdx.x;
+  const bool lane_s = tid < S;
+  const NetL& P = p.pol;
+  const NetL& V = p.val;
+  const int H = p.horizon, obs_dim = P.obs, alg = p.alg;
+  const long long B = p.batch;
+  uint32_t phase = 0;
+
+  if (tid == 0) {
+    mbar_init(mbar, 1);
+    fence_mbar_init();
+  }
+  for (int i = tid; i < p.dw_floats; i += NT) t.dW[i] = 0.f;
+
+  // TMA bulk copy of a packed weight blob into shared memory (all threads wait on the mbarrier)
+  auto stage = [&](const float* gsrc, int floats) {
+    __syncthreads();  // every reader of the previous blob is done
+    if (tid == 0) {
+      fence_proxy_async();
+      const uint32_t bytes = (uint32_t)floats * 4u;
+      mbar_expect_tx(mbar, bytes);
+      for (uint32_t off = 0; off < bytes; off += 32768u) {
+        const uint32_t n = bytes - off < 32768u ? bytes - off : 32768u;
+        tma_bulk_g2s(reinterpret_cast<char*>(t.W) + off, reinterpret_cast<const char*>(gsrc) + off, n, mbar);
+      }
+    }
+    mbar_wait(mbar, phase);
+    phase ^= 1u;
+  };
+  auto load_obs_tile = [&](long long base) {
+    for (int idx = tid; idx < S * obs_dim; idx += NT) {
+      const int s = idx / obs_dim, f = idx - s * obs_dim;
+      const long long gs = base + s;
+      t.X[f * SP + s] = gs < B ? p.obs[gs * obs_dim + f] : 0.f;
+    }
+  };
+
+  stage(p.blob_pol, P.blob);
+
+  float* tape = p.tape + (size_t)blockIdx.x * (size_t)H * TC * S;
+  float loss_acc = 0.f, vmean_acc = 0.f, done_acc = 0.f;
+
+  for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+    const long long base = (long long)tile * S;
+    __syncthreads();
+    load_obs_tile(base);
+    __syncthreads();
+    float st[NS];
+    bool dn = true, valid = false;
+    float vacc = 0.f;
+    const long long gs = base + tid;
+    if (lane_s) {
+      valid = gs < B;
+      dn = valid ? (p.done[gs] != 0.f) : true;
+#pragma unroll
+      for (int f = 0; f < NS; ++f) st[f] = f < obs_dim ? t.X[f * SP + tid] : 0.f;
+    }
+
+    // ================================ forward sweep ================================
+    for (int k = 0; k < H; ++k) {
+      if (lane_s) {
+        if (alg == ALG_FHADP || alg == ALG_PIM) {
+#pragma unroll
+          for (int f = 0; f < NS; ++f) tape[(k * TC + f) * S + tid] = st[f];
+          tape[(k * TC + NS) * S + tid] = dn ? 1.f : 0.f;
+        }
+        if (P.time_input) t.X[(P.in - 1) * SP + tid] = (float)(k + 1);
+      }
+      __syncthreads();
+      mlp_forward<S, NT, false>(P, t);
+      if (lane_s) {
+        float z[MAXA], a[MAXA], g[MAXA], apol[MAXA];
+#pragma unroll
+        for (int j = 0; j < MAXA; ++j) z[j] = j < P.out ? t.Z[j * SP + tid] : 0.f;
+        process_action(p, P.out, z, a, g, apol);
+        const bool active = valid && (p.mask_at_done ? !dn : true);
+        float r = 0.f;
+        if (active) {
+          bool md;
+          M::step(p, st, a, r, md);
+          if (p.clip_obs) {
+#pragma unroll
+            for (int f = 0; f < NS; ++f) st[f] = fminf(fmaxf(st[f], p.obs_low[f]), p.obs_high[f]);
+          }
+          dn = md;
+#pragma unroll
+          for (int f = 0; f < NS; ++f)
+            if (f < obs_dim) t.X[f * SP + tid] = st[f];
+        }
+        if (valid) {
+          // ShapingReward sits outside MaskAtDone: a masked (done) sample still pays (0 + shift) * scale
+          if (p.reward_shaping) r = (r + p.reward_shift) * p.reward_scale;
+          vacc += r * p.gpow[k];
+        }
+        if (alg == ALG_TRACE && valid) {
+          const size_t row = (size_t)k * B + gs;
+          if (p.tr_obs)
+            for (int f = 0; f < obs_dim; ++f) p.tr_obs[row * obs_dim + f] = t.X[f * SP + tid];
+          if (p.tr_act)
+            for (int j = 0; j < P.out; ++j) p.tr_act[row * P.out + j] = apol[j];
+          if (p.tr_rew) p.tr_rew[row] = r;
+          if (p.tr_done) p.tr_done[row] = dn ? 1.f : 0.f;
+        }
+      }
+    }
+    if (lane_s && valid && dn) done_acc += 1.f;
+    if (alg == ALG_TRACE) continue;
+
+    // ============================ terminal value (INFADP) ============================
+    float lam[NS];
+#pragma unroll
+    for (int f = 0; f < NS; ++f) lam[f] = 0.f;
+    if (alg != ALG_FHADP) {
+      stage(p.blob_vtg, V.blob);  // leading __syncthreads also publishes X = o_n
+      if (alg == ALG_PIM) mlp_forward<S, NT, true>(V, t);
+      else mlp_forward<S, NT, false>(V, t);
+      const float gn = p.gpow[H];
+      bool term = false;
+      if (lane_s) {
+        term = valid && !dn;
+        if (term) vacc += gn * t.Z[tid];
+        if (alg == ALG_PIM) t.Z[tid] = term ? -gn * p.inv_B : 0.f;
+      }
+      if (alg == ALG_PIM) {
+        __syncthreads();
+        mlp_backward<S, NT, false>(V, t, true);
+        if (lane_s && term) {
+#pragma unroll
+          for (int f = 0; f < NS; ++f)
+            if (f < obs_dim) lam[f] = t.X[f * SP + tid];
+        }
+      }
+    }
+
+    if (alg == ALG_PEV) {
+      // loss_v = mean((v(o_0) - backup)^2), gradient w.r.t. the value net only
+      stage(p.blob_val, V.blob);
+      load_obs_tile(base);
+      __syncthreads();
+      mlp_forward<S, NT, true>(V, t);
+      if (lane_s) {
+        float zb = 0.f;
+        if (valid) {
+          const float v0 = t.Z[tid];
+          const float diff = v0 - vacc;
+          loss_acc += diff * diff * p.inv_B;
+          vmean_acc += v0 * p.inv_B;
+          zb = 2.f * diff * p.inv_B;
+        }
+        t.Z[tid] = zb;
+      }
+      __syncthreads();
+      mlp_backward<S, NT, true>(V, t, false);
+      stage(p.blob_pol, P.blob);
+      continue;
+    }
+
+    if (lane_s && valid) loss_acc += -vacc * p.inv_B;
+    if (alg == ALG_PIM) stage(p.blob_pol, P.blob);
+
+    // ================================ reverse sweep ================================
+    for (int k = H - 1; k >= 0; --k) {
+      bool dnk = true;
+      if (lane_s) {
+#pragma unroll
+        for (int f = 0; f < NS; ++f) st[f] = tape[(k * TC + f) * S + tid];
+        dnk = tape[(k * TC + NS) * S + tid] != 0.f;
+#pragma unroll
+        for (int f = 0; f < NS; ++f)
+          if (f < obs_dim) t.X[f * SP + tid] = st[f];
+        if (P.time_input) t.X[(P.in - 1) * SP + tid] = (float)(k + 1);
+      }
+      __syncthreads();
+      mlp_forward<S, NT, true>(P, t);
+      bool active = false;
+      if (lane_s) {
+        active = valid && (p.mask_at_done ? !dnk : true);
+        float zb[MAXA];
+#pragma unroll
+        for (int j = 0; j < MAXA; ++j) zb[j] = 0.f;
+        if (active) {
+          float z[MAXA], a[MAXA], g[MAXA], abar[MAXA];
+#pragma unroll
+          for (int j = 0; j < MAXA; ++j) z[j] = j < P.out ? t.Z[j * SP + tid] : 0.f;
+          process_action(p, P.out, z, a, g, nullptr);
+          if (p.clip_obs) {
+            float nx[NS], r;
+            bool md;
+#pragma unroll
+            for (int f = 0; f < NS; ++f) nx[f] = st[f];
+            M::step(p, nx, a, r, md);
+#pragma unroll
+            for (int f = 0; f < NS; ++f)
+              if (nx[f] < p.obs_low[f] || nx[f] > p.obs_high[f]) lam[f] = 0.f;
+          }
+          const float rho = -p.gpow[k] * p.inv_B * (p.reward_shaping ? p.reward_scale : 1.f);
+#pragma unroll
+          for (int j = 0; j < MAXA; ++j) abar[j] = 0.f;
+          M::step_bwd(p, st, a, rho, lam, abar);
+#pragma unroll
+          for (int j = 0; j < MAXA; ++j) zb[j] = abar[j] * g[j];
+        }
+#pragma unroll
+        for (int j = 0; j < MAXA; ++j)
+          if (j < P.out) t.Z[j * SP + tid] = zb[j];
+      }
+      __syncthreads();
+      mlp_backward<S, NT, true>(P, t, k > 0);
+      if (lane_s && active && k > 0) {
+#pragma unroll
+        for (int f = 0; f < NS; ++f)
+          if (f < obs_dim) lam[f] += t.X[f * SP + tid];
+      }
+    }
+  }
+
+  // ============================ per-CTA partials ============================
+  __syncthreads();
+  float* part = p.partial + (size_t)blockIdx.x * p.part_stride;
+  const int nparam = (alg == ALG_PEV) ? V.nparam : P.nparam;
+  if (alg != ALG_TRACE)
+    for (int i = tid; i < nparam; i += NT) part[i] = t.dW[i];
+  // block reduction of the three scalars (fixed order)
+  float* red = t.H1;  // free at this point, HID*(S+4) >= 3*NT floats
+  red[tid] = loss_acc;
+  red[NT + tid] = vmean_acc;
+  red[2 * NT + tid] = done_acc;
+  __syncthreads();
+  if (tid < 3) {
+    float s = 0.f;
+    for (int i = 0; i < NT; ++i) s += red[tid * NT + i];
+    part[nparam + tid] = s;
+  }
+}
+
+// Batched inference of one MLP (policy with tanh squashing when `squash`, else raw value output)
+template <int S, int NT>
+__global__ void __launch_bounds__(NT, 1) mlp_infer_kernel(const __grid_constant__ KParams p, const float* blob, int use_val,
+                                                          const float* __restrict__ obs, long long B, float virtual_t,
+                                                          int squash, float* __restrict__ out) {
+  constexpr int SP = S + 4;
+  extern __shared__ __align__(16) float smem[];
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(smem);
+  const NetL& L = use_val ? p.val : p.pol;
+  Tiles t;
+  t.W = smem + 4;
+  t.dW = t.W + p.w_floats;
+  t.X = t.dW;
+  t.H1 = t.X + p.inp_max * SP;
+  t.D1 = t.H1;
+  t.H2 = t.H1 + HID * SP;
+  t.D2 = t.H2;
+  t.Z = t.H2 + HID * SP;
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    mbar_init(mbar, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    fence_proxy_async();
+    const uint32_t bytes = (uint32_t)L.blob * 4u;
+    mbar_expect_tx(mbar, bytes);
+    for (uint32_t off = 0; off < bytes; off += 32768u) {
+      const uint32_t n = bytes - off < 32768u ? bytes - off : 32768u;
+      tma_bulk_g2s(reinterpret_cast<char*>(t.W) + off, reinterpret_cast<const char*>(blob) + off, n, mbar);
+    }
+  }
+  mbar_wait(mbar, 0);
+  const int n_tiles = (int)((B + S - 1) / S);
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const long long base = (long long)tile * S;
+    __syncthreads();
+    for (int idx = tid; idx < S * L.obs; idx += NT) {
+      const int s = idx / L.obs, f = idx - s * L.obs;
+      t.X[f * SP + s] = base + s < B ? obs[(base + s) * L.obs + f] : 0.f;
+    }
+    if (L.time_input && tid < S) t.X[(L.in - 1) * SP + tid] = virtual_t;
+    __syncthreads();
+    mlp_forward<S, NT, false>(L, t);
+    if (tid < S && base + tid < B) {
+      for (int j = 0; j < L.out; ++j) {
+        float z = t.Z[j * SP + tid];
+        if (squash) z = __fadd_rn(__fmul_rn(p.pol_half[j], tanhf(z)), p.pol_mid[j]);
+        out[(base + tid) * L.out + j] = z;
+      }
+    }
+  }
+}
+
+
+// One wrapped-model step for explicit actions: envmodel.forward(obs, action, done, info) of the
+// reference wrapper chain (create_env_model.py:104-126) for state==obs models.
+template <class M>
+__global__ void model_step_kernel(const __grid_constant__ KParams p, const float* __restrict__ action, int act_dim,
+                                  float* __restrict__ next_obs, float* __restrict__ reward,
+                                  float* __restrict__ next_done) {
+  constexpr int NS = M::NS;
+  const long long gs = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gs >= p.batch) return;
+  const int obs_dim = p.pol.obs;
+  float st[NS], old[NS], a[MAXA];
+#pragma unroll
+  for (int f = 0; f < NS; ++f) old[f] = st[f] = f < obs_dim ? p.obs[gs * obs_dim + f] : 0.f;
+#pragma unroll
+  for (int j = 0; j < MAXA; ++j) {
+    float gg = 1.f;
+    a[j] = j < act_dim ? wrap_action(p, j, action[gs * act_dim + j], gg) : 0.f;
+  }
+  const bool dn = p.done[gs] != 0.f;
+  float r;
+  bool md;
+  M::step(p, st, a, r, md);
+  if (p.mask_at_done && dn) {
+    r = 0.f;
+#pragma unroll
+    for (int f = 0; f < NS; ++f) st[f] = old[f];
+  }
+  if (p.mask_at_done) md = md || dn;
+  if (p.reward_shaping) r = (r + p.reward_shift) * p.reward_scale;
+  if (p.clip_obs) {
+#pragma unroll
+    for (int f = 0; f < NS; ++f) st[f] = fminf(fmaxf(st[f], p.obs_low[f]), p.obs_high[f]);
+  }
+  for (int f = 0; f < obs_dim; ++f) next_obs[gs * obs_dim + f] = st[f];
+  reward[gs] = r;
+  next_done[gs] = md ? 1.f : 0.f;
+}
+
+}  // namespace gops

@@ -1,0 +1,238 @@
+// Per-sample environment-model dynamics and their hand-derived adjoints (one thread = one sample).
+#pragma once
+#include "rollout.cuh"
+
+namespace gops {
+
+// ---------------------------------------------------------------------------------------------
+// Policy output -> model action through tanh squashing + ScaleAction + ClipAction.
+//   mlp.py:73-77 / :103-111          a_pol = (hi-lo)/2 * tanh(z) + (hi+lo)/2
+//   wrapper/scale_action.py:75-83    clip -> affine -> clip
+//   wrapper/clip_action.py:34-40     clip
+// a[j]: action handed to the model, g[j] = d a[j] / d z[j] (clip gradient = 1 inside, inclusive).
+// ---------------------------------------------------------------------------------------------
+// ScaleAction + ClipAction applied to one policy-output component x; gg is multiplied by d(out)/dx
+__device__ __forceinline__ float wrap_action(const KParams& p, int j, float x, float& gg) {
+  const float lo = p.act_low[j], hi = p.act_high[j];
+  if (p.action_scale) {
+    const float mn = p.min_action[j], mx = p.max_action[j];
+    if (x < mn || x > mx) gg = 0.f;
+    x = fminf(fmaxf(x, mn), mx);
+    const float q = __fdiv_rn(__fsub_rn(x, mn), __fsub_rn(mx, mn));
+    x = __fadd_rn(lo, __fmul_rn(__fsub_rn(hi, lo), q));
+    gg *= __fsub_rn(hi, lo) * __fdiv_rn(1.f, __fsub_rn(mx, mn));
+    if (x < lo || x > hi) gg = 0.f;
+    x = fminf(fmaxf(x, lo), hi);
+  }
+  if (p.clip_action) {
+    if (x < lo || x > hi) gg = 0.f;
+    x = fminf(fmaxf(x, lo), hi);
+  }
+  return x;
+}
+
+__device__ __forceinline__ void process_action(const KParams& p, int na, const float* z, float* a, float* g,
+                                               float* apol_out) {
+#pragma unroll
+  for (int j = 0; j < MAXA; ++j) {
+    if (j >= na) { a[j] = 0.f; g[j] = 0.f; if (apol_out) apol_out[j] = 0.f; continue; }
+    const float th = tanhf(z[j]);
+    const float x = __fadd_rn(__fmul_rn(p.pol_half[j], th), p.pol_mid[j]);
+    float gg = p.pol_half[j] * (1.f - th * th);
+    if (apol_out) apol_out[j] = x;
+    a[j] = wrap_action(p, j, x, gg);
+    g[j] = gg;
+  }
+}
+
+// =============================================================================================
+// pyth_idpendulum   (env_ocp/env_model/pyth_idpendulum_model.py)
+// state s = [p, th1, th2, pdot, th1dot, th2dot]; 5 explicit-Euler sub-steps of tau = dt/5 with
+// acceleration x = M(th)^-1 f(th, thdot, u), u = 500 a.
+// =============================================================================================
+struct IdpC {
+  float A, Bc, Cc, D, E, F, G1, G2, tau;
+};
+__device__ __forceinline__ IdpC idp_const() {
+  // constants are formed in double exactly as the python expressions (:21-29, :52-90), then cast
+  constexpr double m = 9.42477796, m1 = 4.1033127, m2 = 4.1033127, l1 = 0.6, l2 = 0.6, g = 9.81;
+  IdpC c;
+  c.A = (float)(m + m1 + m2);
+  c.Bc = (float)(l1 * (0.5 * m1 + m2));
+  c.Cc = (float)(0.5 * m2 * l2);
+  c.D = (float)(l1 * l1 * (0.3333 * m1 + m2));
+  c.E = (float)(0.5 * l1 * l2 * m2);
+  c.F = (float)(0.3333 * l2 * l2 * m2);
+  c.G1 = (float)(g * (0.5 * m1 + m2) * l1);
+  c.G2 = (float)(g * 0.5 * l2 * m2);
+  c.tau = (float)(0.01 / 5);
+  return c;
+}
+
+struct IdpAux {
+  float s1, c1, s2, c2, s12, c12;
+  float i00, i01, i02, i11, i12, i22;  // symmetric inverse mass matrix
+  float x0, x1, x2;                    // accelerations
+};
+
+__device__ __forceinline__ void idp_eval(const float* s, float u, const IdpC& c, IdpAux& q) {
+  sincosf(s[1], &q.s1, &q.c1);
+  sincosf(s[2], &q.s2, &q.c2);
+  sincosf(s[1] - s[2], &q.s12, &q.c12);
+  const float a = c.A, b = c.Bc * q.c1, cc = c.Cc * q.c2, d = c.D, e = c.E * q.c12, f = c.F;
+  const float v1 = s[4], v2 = s[5];
+  const float f0 = (c.Bc * (v1 * v1)) * q.s1 + (c.Cc * (v2 * v2)) * q.s2 + u;
+  const float f1 = (-c.E * (v2 * v2)) * q.s12 + c.G1 * q.s1;
+  const float f2 = (c.E * (v1 * v1)) * q.s12 + c.G2 * q.s2;
+  const float C00 = d * f - e * e, C01 = cc * e - b * f, C02 = b * e - cc * d;
+  const float C11 = a * f - cc * cc, C12 = b * cc - a * e, C22 = a * d - b * b;
+  const float det = a * C00 + b * C01 + cc * C02;
+  const float r = 1.f / det;
+  q.i00 = C00 * r; q.i01 = C01 * r; q.i02 = C02 * r; q.i11 = C11 * r; q.i12 = C12 * r; q.i22 = C22 * r;
+  q.x0 = q.i00 * f0 + q.i01 * f1 + q.i02 * f2;
+  q.x1 = q.i01 * f0 + q.i11 * f1 + q.i12 * f2;
+  q.x2 = q.i02 * f0 + q.i12 * f1 + q.i22 * f2;
+}
+
+__device__ __forceinline__ void idp_substep(float* s, float u, const IdpC& c) {
+  IdpAux q;
+  idp_eval(s, u, c, q);
+  const float t = c.tau;
+  const float n0 = s[0] + t * s[3], n1 = s[1] + t * s[4], n2 = s[2] + t * s[5];
+  s[3] += t * q.x0; s[4] += t * q.x1; s[5] += t * q.x2;
+  s[0] = n0; s[1] = n1; s[2] = n2;
+}
+
+// adjoint of one sub-step: lam (adjoint of s_next) -> lam (adjoint of s); ubar += dL/du
+__device__ __forceinline__ void idp_substep_bwd(const float* s, float u, const IdpC& c, float* lam, float& ubar) {
+  IdpAux q;
+  idp_eval(s, u, c, q);
+  const float t = c.tau, v1 = s[4], v2 = s[5];
+  const float xb0 = t * lam[3], xb1 = t * lam[4], xb2 = t * lam[5];
+  // w = M^-T xb (M symmetric) is the adjoint of f; the adjoint of M is -w x^T
+  const float w0 = q.i00 * xb0 + q.i01 * xb1 + q.i02 * xb2;
+  const float w1 = q.i01 * xb0 + q.i11 * xb1 + q.i12 * xb2;
+  const float w2 = q.i02 * xb0 + q.i12 * xb1 + q.i22 * xb2;
+  const float m01 = -(w0 * q.x1 + w1 * q.x0), m02 = -(w0 * q.x2 + w2 * q.x0), m12 = -(w1 * q.x2 + w2 * q.x1);
+  float th1b = m01 * (-c.Bc * q.s1) + m12 * (-c.E * q.s12);
+  float th2b = m02 * (-c.Cc * q.s2) + m12 * (c.E * q.s12);
+  // f0 = Bc v1^2 s1 + Cc v2^2 s2 + u
+  th1b += w0 * (c.Bc * v1 * v1 * q.c1);
+  th2b += w0 * (c.Cc * v2 * v2 * q.c2);
+  float v1b = w0 * (2.f * c.Bc * v1 * q.s1);
+  float v2b = w0 * (2.f * c.Cc * v2 * q.s2);
+  ubar += w0;
+  // f1 = -E v2^2 s12 + G1 s1
+  th1b += w1 * (-c.E * v2 * v2 * q.c12 + c.G1 * q.c1);
+  th2b += w1 * (c.E * v2 * v2 * q.c12);
+  v2b += w1 * (-2.f * c.E * v2 * q.s12);
+  // f2 = E v1^2 s12 + G2 s2
+  th1b += w2 * (c.E * v1 * v1 * q.c12);
+  th2b += w2 * (-c.E * v1 * v1 * q.c12 + c.G2 * q.c2);
+  v1b += w2 * (2.f * c.E * v1 * q.s12);
+  const float l0 = lam[0], l1 = lam[1], l2 = lam[2];
+  lam[1] = l1 + th1b;
+  lam[2] = l2 + th2b;
+  lam[3] = lam[3] + t * l0;
+  lam[4] = lam[4] + t * l1 + v1b;
+  lam[5] = lam[5] + t * l2 + v2b;
+}
+
+struct ModelIdp {
+  static constexpr int NS = 6;
+  // forward: s <- next state; returns raw model reward and done   (:199-216, :126-172)
+  __device__ static __forceinline__ void step(const KParams&, float* s, const float* a, float& rew, bool& done) {
+    const IdpC c = idp_const();
+    const float u = 500.f * a[0];
+#pragma unroll 1
+    for (int j = 0; j < 5; ++j) idp_substep(s, u, c);
+    const float dist = 0.f * (s[0] * s[0]) + 5.f * (s[1] * s[1]) + 10.f * (s[2] * s[2]);
+    const float vel = 0.5f * (s[3] * s[3]) + 0.5f * (s[4] * s[4]) + 1.f * (s[5] * s[5]);
+    rew = 10.f - dist - vel - a[0] * a[0];
+    const float tip_y = 0.6f * cosf(s[1]) + 0.6f * cosf(s[2]);
+    done = (tip_y <= 1.0f) || (fabsf(s[0]) >= 15.f);
+  }
+  // backward: s = state BEFORE the step, lam = adjoint of the next state (in) / of s (out),
+  // rho = dL/d(raw reward of this step).  abar[j] = dL/d a[j].
+  __device__ static __forceinline__ void step_bwd(const KParams&, const float* s, const float* a, float rho, float* lam,
+                                                  float* abar) {
+    const IdpC c = idp_const();
+    const float u = 500.f * a[0];
+    float sj[5][6];
+#pragma unroll
+    for (int f = 0; f < 6; ++f) sj[0][f] = s[f];
+#pragma unroll
+    for (int j = 1; j < 5; ++j) {
+#pragma unroll
+      for (int f = 0; f < 6; ++f) sj[j][f] = sj[j - 1][f];
+      idp_substep(sj[j], u, c);
+    }
+    float s5[6];
+#pragma unroll
+    for (int f = 0; f < 6; ++f) s5[f] = sj[4][f];
+    idp_substep(s5, u, c);
+    // reward is evaluated on the post-step state
+    lam[1] += rho * (-10.f * s5[1]);
+    lam[2] += rho * (-20.f * s5[2]);
+    lam[3] += rho * (-s5[3]);
+    lam[4] += rho * (-s5[4]);
+    lam[5] += rho * (-2.f * s5[5]);
+    float ubar = 0.f;
+#pragma unroll
+    for (int j = 4; j >= 0; --j) idp_substep_bwd(sj[j], u, c, lam, ubar);
+    abar[0] = rho * (-2.f * a[0]) + 500.f * ubar;
+  }
+};
+
+// =============================================================================================
+// pyth_lq   (env_ocp/resources/lq_base.py:89-141, :343-354)   zero-padded to LQN x MAXA
+// =============================================================================================
+struct ModelLq {
+  static constexpr int NS = LQN;
+  __device__ static __forceinline__ void step(const KParams& p, float* s, const float* a, float& rew, bool& done) {
+    float rs = 0.f, ra = 0.f, tmp[LQN];
+#pragma unroll
+    for (int i = 0; i < LQN; ++i) rs += (s[i] * s[i]) * p.lq_Q[i];
+#pragma unroll
+    for (int j = 0; j < MAXA; ++j) ra += (a[j] * a[j]) * p.lq_R[j];
+    rew = p.lq_rs * (p.lq_rsh - 1.0f * (rs + ra));
+#pragma unroll
+    for (int i = 0; i < LQN; ++i) {
+      float bu = 0.f;
+#pragma unroll
+      for (int j = 0; j < MAXA; ++j) bu = fmaf(p.lq_B[i * MAXA + j], a[j], bu);
+      tmp[i] = bu * p.lq_dt + s[i];
+    }
+#pragma unroll
+    for (int i = 0; i < LQN; ++i) {
+      float acc = 0.f;
+#pragma unroll
+      for (int j = 0; j < LQN; ++j) acc = fmaf(p.lq_inv_IA[i * LQN + j], tmp[j], acc);
+      s[i] = acc;
+    }
+    done = false;
+  }
+  __device__ static __forceinline__ void step_bwd(const KParams& p, const float* s, const float* a, float rho,
+                                                  float* lam, float* abar) {
+    float tb[LQN];
+#pragma unroll
+    for (int j = 0; j < LQN; ++j) {
+      float acc = 0.f;
+#pragma unroll
+      for (int i = 0; i < LQN; ++i) acc = fmaf(p.lq_inv_IA[i * LQN + j], lam[i], acc);
+      tb[j] = acc;
+    }
+    const float rr = rho * p.lq_rs;
+#pragma unroll
+    for (int j = 0; j < MAXA; ++j) {
+      float acc = 0.f;
+#pragma unroll
+      for (int i = 0; i < LQN; ++i) acc = fmaf(p.lq_B[i * MAXA + j], tb[i], acc);
+      abar[j] = p.lq_dt * acc + rr * (-2.f * p.lq_R[j] * a[j]);
+    }
+#pragma unroll
+    for (int i = 0; i < LQN; ++i) lam[i] = tb[i] + rr * (-2.f * p.lq_Q[i] * s[i]);
+  }
+};
+
+}  // namespace gops

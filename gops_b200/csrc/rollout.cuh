@@ -1,0 +1,313 @@
+// Fused rollout + loss + gradient kernel for hidden width 64 (sm_100a).
+//
+// One CTA owns a tile of S samples for the whole horizon:
+//   * per-sample model state lives in the registers of thread t < S for all H steps;
+//   * MLP weights are staged ONCE per CTA into shared memory by the TMA bulk-copy engine;
+//   * MLP activations live in shared memory, feature-major [feature][sample] so that every
+//     dense layer is a CTA-level GEMM with float4 shared-memory operands and FP32 FFMA;
+//   * the reverse sweep re-computes the MLP activations per step from a small state tape
+//     (per-CTA scratch, L2 resident) and accumulates weight gradients in shared memory;
+//   * each CTA writes one gradient partial; a second kernel reduces partials in fixed order
+//     (deterministic, no float atomics).
+#pragma once
+#include "common.cuh"
+
+namespace gops {
+
+constexpr int HID = 64;
+
+// Layout of one network (host computed).
+struct NetL {
+  int in;          // input rows incl. time column
+  int inp;         // in rounded up to 4
+  int obs;         // rows fed from the observation (= in - time_input)
+  int out;         // outputs (<= MAXA)
+  int hact, oact, time_input;
+  // packed weight blob offsets (floats); blob is what TMA copies to shared memory
+  int o_w1t, o_w1, o_w2t, o_w2, o_w3, o_b1, o_b2, o_b3, blob;
+  // torch flat parameter offsets
+  int g_w1, g_b1, g_w2, g_b2, g_w3, g_b3, nparam;
+};
+
+struct KParams {
+  int alg, horizon, n_tiles;
+  long long batch;
+  float gamma, inv_B;
+  const float* gpow;       // fp32(gamma^k), k = 0..H (host-computed in double like python's gamma ** k)
+  NetL pol, val;
+  const float* blob_pol;
+  const float* blob_val;   // v        (INFADP_VALUE)
+  const float* blob_vtg;   // v_target (INFADP_*)
+  // inputs
+  const float* obs;
+  const float* done;
+  const float* state;
+  const float* ref_points;
+  const float* path_num;
+  const float* u_num;
+  const float* ref_time;
+  const float* reference;
+  int ref_t, ref_len, veh_P;
+  // scratch
+  float* tape;             // [grid][H][NS+1][S]
+  float* ext_ref;          // veh3dofconti: [grid][P+1+H][4][S]
+  float* partial;          // [grid][part_stride]
+  int part_stride;
+  // smem carve (floats)
+  int w_floats, dw_floats, inp_max;
+  // trace outputs (alg == ALG_TRACE)
+  float* tr_obs; float* tr_act; float* tr_rew; float* tr_done;
+  // wrappers
+  int action_scale, clip_action, clip_obs, mask_at_done, reward_shaping;
+  float reward_shift, reward_scale;
+  float min_action[MAXA], max_action[MAXA], act_low[MAXA], act_high[MAXA];
+  float pol_half[MAXA], pol_mid[MAXA];
+  float obs_low[LQN], obs_high[LQN];
+  // LQ
+  int lq_n, lq_m;
+  float lq_inv_IA[LQN * LQN], lq_B[LQN * MAXA], lq_Q[LQN], lq_R[MAXA];
+  float lq_dt, lq_rs, lq_rsh;
+  gops_b200_reftraj rt;
+};
+
+constexpr int ALG_FHADP = GOPS_ALG_FHADP, ALG_PIM = GOPS_ALG_INFADP_POLICY, ALG_PEV = GOPS_ALG_INFADP_VALUE,
+              ALG_TRACE = 3;
+
+// ---------------------------------------------------------------------------------------------
+// CTA-level dense primitives on shared-memory tiles
+// ---------------------------------------------------------------------------------------------
+// C[m][n] = sum_k A[k][m] * B[k][n] for m < HID, n < S.   A: [K][HID], B: [K][SP].
+// MODE 0: pre = C + bias[m]; H = act(pre)                      (forward, inference)
+// MODE 1: pre = C + bias[m]; H = act(pre), D = act'(pre)       (forward, recompute for backward)
+// MODE 2: H[m][n] = C * D[m][n]                                (backward through a hidden layer)
+template <int S, int NT, int MODE>
+__device__ __forceinline__ void gemm_hid(const float* __restrict__ A, const float* __restrict__ Bm, int K,
+                                         const float* __restrict__ bias, int act, float* __restrict__ Hout,
+                                         float* __restrict__ Dbuf) {
+  constexpr int SP = S + 4, NTN = S / 4, MG = NT / NTN, TM = HID / MG;
+  static_assert(TM % 4 == 0 && TM >= 4, "bad tile");
+  const int tid = threadIdx.x, nt = tid % NTN, m0 = (tid / NTN) * TM;
+  float acc[TM][4];
+#pragma unroll
+  for (int j = 0; j < TM; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+  const float* bp = Bm + 4 * nt;
+  const float* ap = A + m0;
+#pragma unroll 4
+  for (int k = 0; k < K; ++k) {
+    const float4 b = *reinterpret_cast<const float4*>(bp + k * SP);
+    float a[TM];
+#pragma unroll
+    for (int q = 0; q < TM / 4; ++q) {
+      const float4 av = *reinterpret_cast<const float4*>(ap + k * HID + 4 * q);
+      a[4 * q] = av.x; a[4 * q + 1] = av.y; a[4 * q + 2] = av.z; a[4 * q + 3] = av.w;
+    }
+#pragma unroll
+    for (int j = 0; j < TM; ++j) {
+      acc[j][0] = fmaf(a[j], b.x, acc[j][0]);
+      acc[j][1] = fmaf(a[j], b.y, acc[j][1]);
+      acc[j][2] = fmaf(a[j], b.z, acc[j][2]);
+      acc[j][3] = fmaf(a[j], b.w, acc[j][3]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < TM; ++j) {
+    const int row = m0 + j;
+    float4 h, d;
+    if (MODE == 2) {
+      d = *reinterpret_cast<const float4*>(Dbuf + row * SP + 4 * nt);
+      h.x = acc[j][0] * d.x; h.y = acc[j][1] * d.y; h.z = acc[j][2] * d.z; h.w = acc[j][3] * d.w;
+      *reinterpret_cast<float4*>(Hout + row * SP + 4 * nt) = h;
+    } else {
+      const float bb = bias[row];
+      if (MODE == 1) {
+        act_fwd_grad(act, acc[j][0] + bb, h.x, d.x);
+        act_fwd_grad(act, acc[j][1] + bb, h.y, d.y);
+        act_fwd_grad(act, acc[j][2] + bb, h.z, d.z);
+        act_fwd_grad(act, acc[j][3] + bb, h.w, d.w);
+        *reinterpret_cast<float4*>(Dbuf + row * SP + 4 * nt) = d;
+      } else {
+        h.x = act_fwd(act, acc[j][0] + bb); h.y = act_fwd(act, acc[j][1] + bb);
+        h.z = act_fwd(act, acc[j][2] + bb); h.w = act_fwd(act, acc[j][3] + bb);
+      }
+      *reinterpret_cast<float4*>(Hout + row * SP + 4 * nt) = h;
+    }
+  }
+}
+
+// Z[a][s] = b3[a] + sum_i W3[a][i] * H[i][s]       (output layer, out <= MAXA)
+template <int S, int NT>
+__device__ __forceinline__ void out_layer(const float* __restrict__ W3, const float* __restrict__ b3,
+                                          const float* __restrict__ H, int out, float* __restrict__ Z) {
+  constexpr int SP = S + 4;
+  for (int idx = threadIdx.x; idx < out * S; idx += NT) {
+    const int a = idx / S, s = idx - a * S;
+    float acc = b3[a];
+#pragma unroll 8
+    for (int i = 0; i < HID; ++i) acc = fmaf(W3[a * HID + i], H[i * SP + s], acc);
+    Z[a * SP + s] = acc;
+  }
+}
+
+// D[i][s] <- D[i][s] * sum_a W3[a][i] * Zb[a][s]   (delta of the last hidden layer, in place)
+template <int S, int NT>
+__device__ __forceinline__ void delta_from_out(const float* __restrict__ W3, const float* __restrict__ Zb, int out,
+                                               float* __restrict__ D) {
+  constexpr int SP = S + 4, NTN = S / 4, MG = NT / NTN, TM = HID / MG;
+  const int tid = threadIdx.x, nt = tid % NTN, m0 = (tid / NTN) * TM;
+  float4 zb[MAXA];
+#pragma unroll
+  for (int a = 0; a < MAXA; ++a)
+    zb[a] = a < out ? *reinterpret_cast<const float4*>(Zb + a * SP + 4 * nt) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int j = 0; j < TM; ++j) {
+    const int row = m0 + j;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int a = 0; a < MAXA; ++a)
+      if (a < out) {
+        const float w = W3[a * HID + row];
+        acc.x = fmaf(w, zb[a].x, acc.x); acc.y = fmaf(w, zb[a].y, acc.y);
+        acc.z = fmaf(w, zb[a].z, acc.z); acc.w = fmaf(w, zb[a].w, acc.w);
+      }
+    float4 d = *reinterpret_cast<const float4*>(D + row * SP + 4 * nt);
+    d.x *= acc.x; d.y *= acc.y; d.z *= acc.z; d.w *= acc.w;
+    *reinterpret_cast<float4*>(D + row * SP + 4 * nt) = d;
+  }
+}
+
+// dst[o][i] += sum_s Dl[o][s] * Xl[i][s]   for o < RO, i < RI   (weight gradient; dst row stride ld)
+// Tiles own interleaved rows (o = to + tiles_o*j) so that lanes of a warp touch consecutive rows
+// of the (S+4)-strided tiles -> conflict-free float4 shared loads.
+template <int S, int NT, int TO, int TI>
+__device__ __forceinline__ void dw_accum(const float* __restrict__ Dl, int RO, const float* __restrict__ Xl, int RI,
+                                         float* __restrict__ dst, int ld) {
+  constexpr int SP = S + 4;
+  const int tiles_o = (RO + TO - 1) / TO, tiles_i = (RI + TI - 1) / TI;
+  for (int tile = threadIdx.x; tile < tiles_o * tiles_i; tile += NT) {
+    const int ti = tile % tiles_i, to = tile / tiles_i;
+    float acc[TO][TI];
+#pragma unroll
+    for (int j = 0; j < TO; ++j)
+#pragma unroll
+      for (int q = 0; q < TI; ++q) acc[j][q] = 0.f;
+    const float* dp[TO];
+    const float* xp[TI];
+#pragma unroll
+    for (int j = 0; j < TO; ++j) dp[j] = Dl + min(to + tiles_o * j, RO - 1) * SP;
+#pragma unroll
+    for (int q = 0; q < TI; ++q) xp[q] = Xl + min(ti + tiles_i * q, RI - 1) * SP;
+#pragma unroll 2
+    for (int s = 0; s < S; s += 4) {
+      float4 d[TO], x[TI];
+#pragma unroll
+      for (int j = 0; j < TO; ++j) d[j] = *reinterpret_cast<const float4*>(dp[j] + s);
+#pragma unroll
+      for (int q = 0; q < TI; ++q) x[q] = *reinterpret_cast<const float4*>(xp[q] + s);
+#pragma unroll
+      for (int j = 0; j < TO; ++j)
+#pragma unroll
+        for (int q = 0; q < TI; ++q) {
+          acc[j][q] = fmaf(d[j].x, x[q].x, acc[j][q]);
+          acc[j][q] = fmaf(d[j].y, x[q].y, acc[j][q]);
+          acc[j][q] = fmaf(d[j].z, x[q].z, acc[j][q]);
+          acc[j][q] = fmaf(d[j].w, x[q].w, acc[j][q]);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < TO; ++j) {
+      const int o = to + tiles_o * j;
+#pragma unroll
+      for (int q = 0; q < TI; ++q) {
+        const int i = ti + tiles_i * q;
+        if (o < RO && i < RI) dst[o * ld + i] += acc[j][q];
+      }
+    }
+  }
+}
+
+// dst[o] += sum_s Dl[o][s]        (bias gradient)
+template <int S, int NT>
+__device__ __forceinline__ void rowsum_accum(const float* __restrict__ Dl, int RO, float* __restrict__ dst) {
+  constexpr int SP = S + 4;
+  for (int o = threadIdx.x; o < RO; o += NT) {
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 4
+    for (int s = 0; s < S; s += 4) {
+      const float4 d = *reinterpret_cast<const float4*>(Dl + o * SP + s);
+      a0 += d.x; a1 += d.y; a2 += d.z; a3 += d.w;
+    }
+    dst[o] += (a0 + a1) + (a2 + a3);
+  }
+}
+
+// Xb[i][s] = sum_o W1[o][i] * Dl[o][s]  for i < M (M <= 8*MG)   (input gradient; W1: [HID][ldw])
+template <int S, int NT>
+__device__ __forceinline__ void gemm_dx(const float* __restrict__ W1, int ldw, const float* __restrict__ Dl, int M,
+                                        float* __restrict__ Xb) {
+  constexpr int SP = S + 4, NTN = S / 4, MG = NT / NTN, JM = 8;
+  const int tid = threadIdx.x, nt = tid % NTN, mg = tid / NTN;
+  const int J = (M - mg + MG - 1) / MG;  // rows mg, mg+MG, ... < M
+  if (J <= 0) return;
+  float acc[JM][4];
+#pragma unroll
+  for (int j = 0; j < JM; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+#pragma unroll 2
+  for (int o = 0; o < HID; ++o) {
+    const float4 d = *reinterpret_cast<const float4*>(Dl + o * SP + 4 * nt);
+#pragma unroll
+    for (int j = 0; j < JM; ++j)
+      if (j < J) {
+        const float w = W1[o * ldw + mg + MG * j];
+        acc[j][0] = fmaf(w, d.x, acc[j][0]); acc[j][1] = fmaf(w, d.y, acc[j][1]);
+        acc[j][2] = fmaf(w, d.z, acc[j][2]); acc[j][3] = fmaf(w, d.w, acc[j][3]);
+      }
+  }
+#pragma unroll
+  for (int j = 0; j < JM; ++j)
+    if (j < J)
+      *reinterpret_cast<float4*>(Xb + (mg + MG * j) * SP + 4 * nt) = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
+}
+
+// Shared-memory views of one CTA.
+struct Tiles {
+  float *W, *dW, *X, *H1, *D1, *H2, *D2, *Z;
+};
+
+// X -> H1 -> H2 -> Z.  FULL: also store activation derivatives (needed by mlp_backward).
+template <int S, int NT, bool FULL>
+__device__ __forceinline__ void mlp_forward(const NetL& L, const Tiles& t) {
+  gemm_hid<S, NT, FULL ? 1 : 0>(t.W + L.o_w1t, t.X, L.in, t.W + L.o_b1, L.hact, t.H1, t.D1);
+  __syncthreads();
+  gemm_hid<S, NT, FULL ? 1 : 0>(t.W + L.o_w2t, t.H1, HID, t.W + L.o_b2, L.hact, t.H2, t.D2);
+  __syncthreads();
+  out_layer<S, NT>(t.W + L.o_w3, t.W + L.o_b3, t.H2, L.out, t.Z);
+  __syncthreads();
+}
+
+// Given Zbar in t.Z: accumulate weight grads into t.dW (torch flat layout) if WANT_DW and write
+// the observation gradient into rows [0, L.obs) of t.X if want_dx.  Requires a FULL forward.
+template <int S, int NT, bool WANT_DW>
+__device__ __forceinline__ void mlp_backward(const NetL& L, const Tiles& t, bool want_dx) {
+  if (WANT_DW) {
+    dw_accum<S, NT, 1, 4>(t.Z, L.out, t.H2, HID, t.dW + L.g_w3, HID);
+    rowsum_accum<S, NT>(t.Z, L.out, t.dW + L.g_b3);
+  }
+  delta_from_out<S, NT>(t.W + L.o_w3, t.Z, L.out, t.D2);  // D2 <- delta2
+  __syncthreads();
+  gemm_hid<S, NT, 2>(t.W + L.o_w2, t.D2, HID, nullptr, 0, t.D1, t.D1);  // D1 <- delta1
+  if (WANT_DW) {
+    dw_accum<S, NT, 4, 4>(t.D2, HID, t.H1, HID, t.dW + L.g_w2, HID);
+    rowsum_accum<S, NT>(t.D2, HID, t.dW + L.g_b2);
+  }
+  __syncthreads();
+  if (WANT_DW) {
+    if (L.in <= 16) dw_accum<S, NT, 2, 2>(t.D1, HID, t.X, L.in, t.dW + L.g_w1, L.in);
+    else dw_accum<S, NT, 4, 4>(t.D1, HID, t.X, L.in, t.dW + L.g_w1, L.in);
+    rowsum_accum<S, NT>(t.D1, HID, t.dW + L.g_b1);
+    __syncthreads();
+  }
+  if (want_dx) gemm_dx<S, NT>(t.W + L.o_w1, L.inp, t.D1, L.obs, t.X);
+  __syncthreads();
+}
+
+}  // namespace gops

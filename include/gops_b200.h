@@ -1,0 +1,200 @@
+/*
+ * gops_b200.h -- C ABI of libgops_b200.so: the B200 (sm_100a) implementation of GOPS's batched
+ * model-rollout + ADP-update hot path.
+ *
+ * The reference (GOPS) has no FFI: its boundary for this path is the Python plugin API
+ * (gops/algorithm/{fhadp,infadp}.py, gops/apprfunc/mlp.py, gops/env/.../env_model/*_model.py,
+ * gops/env/wrapper/*.py assembled by gops/create_pkg/create_env_model.py:104-126).  The Python
+ * classes in gops_b200/ mirror that API and call the entry points below through ctypes.  Every
+ * entry point names the reference code it replaces.
+ *
+ * Conventions
+ *   - all data pointers are DEVICE pointers owned by the caller (plain float32 / int32 arrays);
+ *   - `stream` is a cudaStream_t passed as void*; every call is asynchronous on that stream;
+ *   - return value 0 = ok; non-zero = error, message available from gops_b200_last_error();
+ *   - a plan is bound to the device that was current at creation; one plan per host thread.
+ *   - parameter vectors are the torch `parameters()` order of an `mlp()` Sequential, flattened:
+ *     W1[h][in], b1[h], W2[h][h], b2[h], W3[out][h], b3[out]      (gops/apprfunc/mlp.py:36-41)
+ */
+#ifndef GOPS_B200_H
+#define GOPS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GOPS_B200_ABI_VERSION 1
+#define GOPS_B200_MAX_ACT 4   /* action dims supported by the fused kernels            */
+#define GOPS_B200_MAX_LQ_N 8  /* pyth_lq state dim upper bound (configs ship n <= 6)   */
+
+/* algorithm kinds ------------------------------------------------------------------------- */
+enum {
+  GOPS_ALG_FHADP = 0,        /* FHADP._compute_loss_policy        gops/algorithm/fhadp.py:113-125  */
+  GOPS_ALG_INFADP_POLICY = 1,/* INFADP.__compute_loss_policy      gops/algorithm/infadp.py:188-213 */
+  GOPS_ALG_INFADP_VALUE = 2  /* INFADP.__compute_loss_v           gops/algorithm/infadp.py:159-186 */
+};
+
+/* env-model kinds --------------------------------------------------------------------------- */
+enum {
+  GOPS_MODEL_IDPENDULUM = 0,      /* env_ocp/env_model/pyth_idpendulum_model.py:199-216           */
+  GOPS_MODEL_LQ = 1,              /* env_ocp/resources/lq_base.py:343-354                         */
+  GOPS_MODEL_VEH3DOFCONTI = 2,    /* env_ocp/env_model/pyth_veh3dofconti_model.py:91-145          */
+  GOPS_MODEL_VEH3DOF_TRACKING = 3 /* env_gen_ocp/env_model/veh3dof_tracking_model.py:11-102       */
+};
+
+/* activations                      gops/utils/common_utils.py:26-55 ------------------------- */
+enum {
+  GOPS_ACT_RELU = 0, GOPS_ACT_ELU = 1, GOPS_ACT_GELU = 2, GOPS_ACT_SELU = 3,
+  GOPS_ACT_SIGMOID = 4, GOPS_ACT_TANH = 5, GOPS_ACT_LINEAR = 6
+};
+
+/* One `mlp()` network with two hidden layers of equal width. */
+typedef struct gops_b200_mlp_desc {
+  int32_t in_dim;      /* observation features (without the time column)                          */
+  int32_t time_input;  /* 1 = FiniteHorizonPolicy: a column virtual_t is appended (mlp.py:103-111) */
+  int32_t hidden;      /* hidden width (64 / 128 / 256)                                            */
+  int32_t out_dim;     /* act_dim for policies, 1 for StateValue                                   */
+  int32_t hidden_act;  /* GOPS_ACT_*                                                               */
+  int32_t out_act;     /* GOPS_ACT_* (reference default "linear")                                  */
+} gops_b200_mlp_desc;
+
+/* Reference-trajectory generator constants, env_ocp/resources/ref_traj_data.py:19-37 */
+typedef struct gops_b200_reftraj {
+  float sine_A, sine_omega, sine_phi;
+  float dl_t1, dl_t2, dl_t3, dl_t4, dl_y1, dl_y2;
+  float tri_A, tri_T;
+  float circ_r;
+  float sp_A, sp_omega, sp_phi, sp_b, sp_const;
+} gops_b200_reftraj;
+
+typedef struct gops_b200_plan_desc {
+  int32_t alg;          /* GOPS_ALG_*                                                            */
+  int32_t model;        /* GOPS_MODEL_*                                                          */
+  int32_t horizon;      /* FHADP pre_horizon / INFADP forward_step                               */
+  float gamma;
+  gops_b200_mlp_desc policy;
+  gops_b200_mlp_desc value;  /* INFADP only (v and v_target share the shape)                     */
+
+  /* wrapper chain, gops/create_pkg/create_env_model.py:104-126 */
+  int32_t action_scale;      /* ScaleActionModel   wrapper/scale_action.py:75-83                 */
+  int32_t clip_action;       /* ClipActionModel    wrapper/clip_action.py:27-40                  */
+  int32_t clip_obs;          /* ClipObservationModel wrapper/clip_observation.py:27-44           */
+  int32_t mask_at_done;      /* MaskAtDoneModel    wrapper/mask_at_done.py:26-40                 */
+  int32_t reward_shaping;    /* ShapingRewardModel wrapper/shaping_reward.py:77-88               */
+  float reward_shift, reward_scale;
+  float min_action[GOPS_B200_MAX_ACT], max_action[GOPS_B200_MAX_ACT];
+  float act_low[GOPS_B200_MAX_ACT], act_high[GOPS_B200_MAX_ACT];         /* model action bounds  */
+  float pol_act_low[GOPS_B200_MAX_ACT], pol_act_high[GOPS_B200_MAX_ACT]; /* policy tanh limits   */
+  float obs_low[GOPS_B200_MAX_LQ_N], obs_high[GOPS_B200_MAX_LQ_N];       /* state==obs models    */
+
+  /* pyth_lq: x' = inv_IA (B u dt + x), r = rs*(rsh - (sum Q x^2 + sum R u^2))  lq_base.py:89-141 */
+  int32_t lq_n, lq_m;
+  float lq_inv_IA[GOPS_B200_MAX_LQ_N * GOPS_B200_MAX_LQ_N]; /* row-major n x n                   */
+  float lq_B[GOPS_B200_MAX_LQ_N * GOPS_B200_MAX_ACT];       /* row-major n x m                   */
+  float lq_Q[GOPS_B200_MAX_LQ_N], lq_R[GOPS_B200_MAX_ACT];
+  float lq_dt, lq_reward_scale, lq_reward_shift;
+
+  /* vehicle models */
+  int32_t veh_pre_horizon;   /* P: obs_dim = 6 + 4 P                                             */
+  int32_t veh_ref_len;       /* veh3dof_tracking: reference points per sample (2P+1)             */
+  gops_b200_reftraj reftraj;
+} gops_b200_plan_desc;
+
+/* Per-call inputs (one replay batch shard).  Unused pointers are NULL. */
+typedef struct gops_b200_batch {
+  int64_t batch;             /* samples on this device                                           */
+  const float* obs;          /* [batch][obs_dim]   data["obs"]                                   */
+  const float* done;         /* [batch]            data["done"] (float32, replay_buffer.py:103)   */
+  const float* state;        /* [batch][6]         veh: info["state"] / State.robot_state        */
+  const float* ref_points;   /* [batch][P+1][4]    veh3dofconti info["ref_points"]               */
+  const float* path_num;     /* [batch]            float32 as stored by the replay buffer        */
+  const float* u_num;        /* [batch]                                                           */
+  const float* ref_time;     /* [batch]                                                           */
+  const float* reference;    /* [batch][ref_len][4] veh3dof_tracking ContextState.reference      */
+  int32_t ref_t;             /* veh3dof_tracking ContextState.t (shared python int)              */
+} gops_b200_batch;
+
+typedef struct gops_b200_plan gops_b200_plan;
+
+int gops_b200_version(void);
+const char* gops_b200_last_error(void);
+
+/* Plan = compiled shape/constant bundle + device scratch (weight staging blob, rollout tape,
+ * per-CTA gradient partials). */
+int gops_b200_plan_create(const gops_b200_plan_desc* desc, gops_b200_plan** out);
+int gops_b200_plan_destroy(gops_b200_plan* plan);
+/* Re-derive the discount table fp32(gamma ** k), k = 0..horizon, from the python double (the
+ * reference multiplies fp32 rewards by the python float `gamma ** step`, fhadp.py:121). */
+int gops_b200_plan_set_gamma(gops_b200_plan* plan, double gamma);
+/* Measurement aids (bench.py): CUDA events recorded on the launch stream around the fused rollout
+ * kernel only; last_kernel_ms synchronises on the stop event.  launch_info: grid, block, tile S,
+ * dynamic shared memory bytes of the last rollout launch. */
+int gops_b200_plan_enable_timing(gops_b200_plan* plan, int enable);
+int gops_b200_plan_last_kernel_ms(gops_b200_plan* plan, float* ms);
+int gops_b200_plan_launch_info(const gops_b200_plan* plan, int32_t* out4);
+/* number of float32 parameters of the policy (which=0) / value (which=1) network */
+int64_t gops_b200_plan_param_count(const gops_b200_plan* plan, int which);
+
+/*
+ * Fused rollout + loss + gradient.  Replaces, per call:
+ *   FHADP._compute_gradient        fhadp.py:104-111   (alg = GOPS_ALG_FHADP; grads of policy)
+ *   INFADP.__compute_gradient      infadp.py:135-157  (policy branch / value branch)
+ * including policy/value forward (mlp.py), the wrapper chain and envmodel.forward.
+ *   policy_params / value_params / vtarget_params: flat fp32 parameter vectors (see top).
+ *   inv_batch_global: 1 / B_global (so multi-GPU shards sum to the global mean).
+ *   grad_out: flat gradient of the network being updated (policy for FHADP/INFADP_POLICY,
+ *             value for INFADP_VALUE), overwritten.
+ *   scalars_out[4]: [0] loss (already scaled by inv_batch_global, summed over this shard),
+ *                   [1] sum_b v(o_b) * inv_batch_global (INFADP_VALUE: critic avg value),
+ *                   [2] number of samples done at the end of the rollout, [3] reserved.
+ */
+int gops_b200_rollout_grad(gops_b200_plan* plan, const gops_b200_batch* batch,
+                           const float* policy_params, const float* value_params,
+                           const float* vtarget_params, float inv_batch_global,
+                           float* grad_out, float* scalars_out, void* stream);
+
+/* torch.optim.Adam (no weight decay, no amsgrad) over a flat vector; `step` is 1-based.
+ * Replaces policy_optimizer.step() fhadp.py:89 / optimizer_dict[..].step() infadp.py:123-124. */
+int gops_b200_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
+                        int64_t n, int32_t step, double lr, double beta1, double beta2, double eps,
+                        void* stream);
+
+/* p_targ = (1 - tau) * p_targ + tau * p          infadp.py:126-133 */
+int gops_b200_polyak(float* target, const float* src, float tau, int64_t n, void* stream);
+
+/* Batched policy inference: act_out[b] = policy(obs[b], virtual_t).  Replaces
+ * DetermPolicy.forward mlp.py:73-77 / FiniteHorizonPolicy.forward mlp.py:103-111. */
+int gops_b200_policy_forward(gops_b200_plan* plan, const float* policy_params, const float* obs,
+                             int64_t batch, float virtual_t, float* act_out, void* stream);
+
+/* Batched state-value inference (StateValue.forward mlp.py:327-329). */
+int gops_b200_value_forward(gops_b200_plan* plan, const float* value_params, const float* obs,
+                            int64_t batch, float* v_out, void* stream);
+
+/* Plan-free batched MLP inference.  act_low/act_high are HOST pointers (out_dim floats) holding the
+ * policy's act_{low,high}_lim buffers; pass NULL for a raw (StateValue) output. */
+int gops_b200_mlp_forward(const gops_b200_mlp_desc* net, const float* params, const float* obs,
+                          int64_t batch, float virtual_t, const float* act_low, const float* act_high,
+                          float* out, void* stream);
+
+/* One step of the wrapped env model with explicit actions: replaces envmodel.forward(obs, action,
+ * done, info) of the chain built by create_env_model.py:104-126.  `action` is [batch][act_dim] in
+ * the policy's (scaled) action space.  next_state / next_ref_points / next_ref_time receive the
+ * advanced `info` entries of the vehicle models (may be NULL for the other models). */
+int gops_b200_model_step(gops_b200_plan* plan, const gops_b200_batch* batch, const float* action,
+                         float* next_obs, float* reward, float* next_done, float* next_state,
+                         float* next_ref_points, float* next_ref_time, void* stream);
+
+/* Debug / parity aid: run the no-grad rollout and dump per-step tensors
+ * obs_out[H][batch][obs_dim], act_out[H][batch][act_dim] (policy output), rew_out[H][batch],
+ * done_out[H][batch] (as float).  Any output pointer may be NULL. */
+int gops_b200_rollout_trace(gops_b200_plan* plan, const gops_b200_batch* batch,
+                            const float* policy_params, float* obs_out, float* act_out,
+                            float* rew_out, float* done_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GOPS_B200_H */
