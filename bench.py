@@ -1,0 +1,282 @@
+#!/usr/bin/env python
+"""bench.py -- batched env-steps/s of the FHADP rollout+update hot path (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            (N>1: launched under torch.distributed.run)
+  python bench.py --impl reference --gpus N --steps K --warmup W
+
+Workload (config.workload): FHADP on pyth_idpendulum, FiniteHorizonPolicy [64,64] gelu, horizon 30,
+batch 2^18 PER GPU (weak scaling), synthetic initial states from the data env's reset box.
+One step = one `alg.local_update(data, it)` through the plugin API: weight packing, fused rollout
+forward+backward, partial reduction, (NCCL all-reduce of the flat gradient when N>1), fused Adam, and
+the host read of the loss scalar.
+
+value : inputs resident in HBM when the timed region starts (a rotating set of input batches whose total
+        size exceeds L2, so no step finds its inputs in L2);
+e2e   : same call with PINNED HOST tensors -- H2D copy of the batch and D2H read of the loss inside the
+        timed region;
+roofline : the fused rollout kernel alone, timed with CUDA events on its launch stream inside the library
+        (gops_b200_plan_enable_timing).  The kernel is FP32-FMA bound by design, so
+        `achieved`/`peak` are algorithmic TFLOP/s against the FP32 FFMA roof at the SM clock sampled
+        during the run; the HBM and tensor (measured bf16) fractions are reported beside it.
+cpu_baseline : the CPU oracle port (oracle/gops_oracle.py, the reference's algorithm in PyTorch-CPU) on a
+        bounded sample of the same workload, all host threads.
+"""
+import argparse
+import json
+import math
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H = 30
+OBS_DIM, ACT_DIM, HID = 6, 1, 64
+MAC = (OBS_DIM + 1) * HID + HID * HID + HID * ACT_DIM          # 4608
+FLOP_PER_ENV_STEP = 6 * MAC + 1500                             # MLP fwd+bwd + dynamics
+BYTES_PER_ENV_STEP = (OBS_DIM * 4 + 4) / H                     # obs + done read once per sample
+L2_BYTES = 126 * 1024 * 1024
+
+
+def alg_kwargs():
+    import numpy as np
+    return dict(env_id="pyth_idpendulum", algorithm="FHADP", pre_horizon=H, seed=0, trainer="off_serial_trainer",
+                use_gpu=True, action_type="continu", obsv_dim=OBS_DIM, action_dim=ACT_DIM,
+                action_high_limit=np.ones(ACT_DIM, dtype=np.float32), action_low_limit=-np.ones(ACT_DIM, dtype=np.float32),
+                policy_func_name="FiniteHorizonPolicy", policy_func_type="MLP", policy_hidden_sizes=[HID, HID],
+                policy_hidden_activation="gelu", policy_act_distribution="default", policy_learning_rate=1e-4,
+                value_func_type="MLP", reward_scale=1.0)
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi sampling DURING the timed region (B200_PROFILING.md clocks line)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [x.strip() for x in out.strip().split(",")]
+                if len(parts) >= 7:
+                    self.rows.append(parts)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=5)
+        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.rows)}
+
+
+def cpu_update_rate(batch, steps, warmup, threads):
+    """env-steps/s of the CPU oracle port: loss + autograd backward + Adam, as FHADP.local_update."""
+    import torch
+    from oracle import gops_oracle as orc
+    torch.set_num_threads(threads)
+    gen = torch.Generator().manual_seed(0)
+    layers = [(w.requires_grad_(True), b.requires_grad_(True))
+              for w, b in orc.init_mlp([OBS_DIM + 1, HID, HID, ACT_DIM], gen)]
+    pol = orc.NetSpec(layers, "gelu", "linear", torch.ones(ACT_DIM), -torch.ones(ACT_DIM), time_input=True)
+    env = orc.create_env_model("pyth_idpendulum", reward_scale=1.0)
+    opt = torch.optim.Adam(pol.params(), lr=1e-4)
+    data = orc.sample_inputs("pyth_idpendulum", batch, seed=1)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        opt.zero_grad()
+        loss = orc.fhadp_loss(pol, env, data, H)
+        loss.backward()
+        opt.step()
+        loss.item()
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    total = sum(times)
+    return batch * H * len(times) / total, total / len(times)
+
+
+def run_reference(args, rank, world):
+    """Reference arm: the reference's own CPU algorithm (oracle port; the python reference cannot travel
+    to the GPU box) on the host cores, bounded sample per step."""
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    sample_b = args.cpu_batch
+    rate, sec = cpu_update_rate(sample_b, args.steps, args.warmup, threads)
+    line = {
+        "impl": "reference", "metric": "batched env-steps/sec (FHADP rollout+update)", "value": rate,
+        "unit": "env-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"FHADP pyth_idpendulum H={H} FiniteHorizonPolicy[64,64] gelu",
+                   "sample": f"batch {sample_b} per step on CPU"},
+        "cpu_baseline": {"value": rate, "unit": "env-steps/s", "cores": threads, "kind": "port",
+                         "sample": f"B={sample_b}, H={H}, {args.steps} updates (oracle/gops_oracle.py)"},
+        "e2e": {"value": rate, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch-per-gpu", type=int, default=1 << 18)
+    ap.add_argument("--cpu-batch", type=int, default=8192)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from gops_b200.create_pkg.create_alg import create_alg
+    from gops_b200 import _lib
+    from oracle import gops_oracle as orc     # only for synthetic input sampling + the cpu_baseline leg
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    W, K, Bg = max(args.warmup, 3), args.steps, args.batch_per_gpu
+
+    torch.manual_seed(0)                       # identical replicas on every rank
+    alg = create_alg(**alg_kwargs())
+    batch_bytes = Bg * (OBS_DIM + 1) * 4
+    n_sets = max(2, math.ceil(1.5 * L2_BYTES / batch_bytes))
+    host_sets = []
+    for i in range(n_sets):
+        d = orc.sample_inputs("pyth_idpendulum", Bg, seed=1000 * rank + i)
+        host_sets.append({k: v.pin_memory() for k, v in d.items()})
+    dev_sets = [{k: v.to(dev) for k, v in d.items()} for d in host_sets]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(sets, steps, collect_kernel=False):
+        plan = next(iter(alg._plans.values())) if alg._plans else None
+        kms = []
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            alg.local_update(sets[i % len(sets)], i)
+            if collect_kernel and plan is not None:
+                import ctypes as C
+                ms = C.c_float()
+                _lib.check(_lib.lib().gops_b200_plan_last_kernel_ms(plan.handle, C.byref(ms)))
+                kms.append(ms.value)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), kms
+
+    timed(dev_sets, W)                                    # warm-up (creates the plan, compiles nothing)
+    plan = next(iter(alg._plans.values()))
+    _lib.check(_lib.lib().gops_b200_plan_enable_timing(plan.handle, 1))
+    timed(dev_sets, 1)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ms_total, kernel_ms = timed(dev_sets, K, collect_kernel=True)
+    clocks = sampler.stop()
+    _lib.check(_lib.lib().gops_b200_plan_enable_timing(plan.handle, 0))
+    timed(host_sets, W)
+    ms_e2e, _ = timed(host_sets, K)
+
+    env_steps = Bg * world * H
+    value = env_steps * K / (ms_total * 1e-3)
+    e2e = env_steps * K / (ms_e2e * 1e-3)
+
+    if rank == 0:
+        import ctypes as C
+        info = (C.c_int32 * 4)()
+        _lib.check(_lib.lib().gops_b200_plan_launch_info(plan.handle, info))
+        peaks = {}
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                peaks = json.load(f)
+        except Exception:
+            pass
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        tens_peak = peaks.get("bf16_tflops_sustained", 1400.0)
+        peak_src = "measured" if peaks else "fallback"
+        k_ms = statistics.mean(kernel_ms) if kernel_ms else ms_total / K
+        sm_mhz = clocks["sm_mhz"] or peaks.get("sm_max_mhz", 1965.0)
+        n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
+        fp32_peak = n_sm * 128 * 2 * sm_mhz * 1e6 / 1e12
+        ach_tflops = Bg * H * FLOP_PER_ENV_STEP / (k_ms * 1e-3) / 1e12
+        ach_gbs = Bg * H * BYTES_PER_ENV_STEP / (k_ms * 1e-3) / 1e9
+        traffic = None
+        tfile = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tfile):
+            try:
+                traffic = json.load(open(tfile)).get("rollout_kernel_dram_bytes_per_launch")
+            except Exception:
+                pass
+        roof = {"bound": "fp32", "achieved": ach_tflops, "peak": fp32_peak, "unit": "TFLOP/s",
+                "frac": ach_tflops / fp32_peak, "traffic": traffic,
+                "peak_source": f"148 SM x 128 lanes x 2 x {sm_mhz:.0f} MHz sampled under load",
+                "kernel_ms": k_ms, "kernel_share_of_step": k_ms * K / ms_total,
+                "hbm": {"achieved_gbs": ach_gbs, "peak_gbs": hbm_peak, "frac": ach_gbs / hbm_peak, "of": peak_src},
+                "tensor": {"achieved_tflops": ach_tflops, "peak_tflops": tens_peak, "frac": ach_tflops / tens_peak,
+                           "of": peak_src + " bf16 sustained"},
+                "launch": {"grid": info[0], "block": info[1], "tile_samples": info[2], "smem_bytes": info[3]}}
+        cpu = None
+        if not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            rate, sec = cpu_update_rate(args.cpu_batch, 3, 1, threads)
+            cpu = {"value": rate, "unit": "env-steps/s", "cores": threads, "kind": "port",
+                   "sample": f"B={args.cpu_batch}, H={H}, 3 updates after 1 warm-up (oracle/gops_oracle.py)"}
+        line = {
+            "metric": "batched env-steps/sec (FHADP rollout+update)", "value": value, "unit": "env-steps/s",
+            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_total / K, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"FHADP pyth_idpendulum H={H} FiniteHorizonPolicy[64,64] gelu, "
+                                   f"batch {Bg} per GPU (global {Bg * world})",
+                       "parallelism": f"dp{world}", "l2_policy": f"{n_sets} rotating input batches "
+                       f"({n_sets * batch_bytes / 2**20:.0f} MiB total > L2)"},
+            "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+            "e2e": {"value": e2e, "unit": "env-steps/s", "h2d_bytes_per_step": batch_bytes, "d2h_bytes_per_step": 4,
+                    "ms_per_step": ms_e2e / K},
+            "gpu_launches": 4 * K,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
