@@ -88,11 +88,23 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(self.rows)}
 
 
+def usable_cores():
+    """Host cores this process may really use: min(affinity, cgroup cpu quota)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = min(n, max(1, int(float(quota) / float(period))))
+    except Exception:
+        pass
+    return n
+
+
 def cpu_update_rate(batch, steps, warmup, threads):
     """env-steps/s of the CPU oracle port: loss + autograd backward + Adam, as FHADP.local_update."""
     import torch
-    from oracle import gops_oracle as orc
     torch.set_num_threads(threads)
+    from oracle import gops_oracle as orc
     gen = torch.Generator().manual_seed(0)
     layers = [(w.requires_grad_(True), b.requires_grad_(True))
               for w, b in orc.init_mlp([OBS_DIM + 1, HID, HID, ACT_DIM], gen)]
@@ -119,7 +131,7 @@ def run_reference(args, rank, world):
     to the GPU box) on the host cores, bounded sample per step."""
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
+    threads = usable_cores()
     sample_b = args.cpu_batch
     rate, sec = cpu_update_rate(sample_b, args.steps, args.warmup, threads)
     line = {
@@ -156,6 +168,7 @@ def main():
         return
 
     import torch
+    torch.set_num_threads(usable_cores())      # the box reports 128 cpus under a 16-core cgroup quota
     import torch.distributed as dist
     from gops_b200.create_pkg.create_alg import create_alg
     from gops_b200 import _lib
@@ -256,7 +269,7 @@ def main():
                 "launch": {"grid": info[0], "block": info[1], "tile_samples": info[2], "smem_bytes": info[3]}}
         cpu = None
         if not args.no_cpu_baseline:
-            threads = os.cpu_count() or 1
+            threads = usable_cores()
             rate, sec = cpu_update_rate(args.cpu_batch, 3, 1, threads)
             cpu = {"value": rate, "unit": "env-steps/s", "cores": threads, "kind": "port",
                    "sample": f"B={args.cpu_batch}, H={H}, 3 updates after 1 warm-up (oracle/gops_oracle.py)"}

@@ -8,7 +8,23 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
+def _usable_cores():
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = min(n, max(1, int(float(quota) / float(period))))
+    except Exception:
+        pass
+    return n
+
+
 def pytest_configure(config):
+    try:
+        import torch
+        torch.set_num_threads(min(8, _usable_cores()))   # GPU boxes report far more cpus than their quota
+    except Exception:
+        pass
     config.addinivalue_line("markers", "gpu: test needs a CUDA device (run on the B200 box)")
 
 
