@@ -5,25 +5,20 @@
 namespace gops {
 
 // ---------------------------------------------------------------------------------------------
-// torch-layout flat parameters -> packed blob (both orientations of W1/W2, 16-byte aligned parts)
+// torch-layout flat parameters -> packed k-major blob (W1^T, W2^T with row stride HP; 16-byte aligned parts)
 // ---------------------------------------------------------------------------------------------
 __global__ void pack_params_kernel(const float* __restrict__ flat, NetL L, float* __restrict__ blob) {
   const int n = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
   const float* W1 = flat + L.g_w1;
   const float* W2 = flat + L.g_w2;
   const float* W3 = flat + L.g_w3;
-  for (int i = t0; i < L.in * HID; i += n) {
-    const int k = i / HID, o = i - k * HID;
-    blob[L.o_w1t + i] = W1[o * L.in + k];
+  for (int i = t0; i < L.in * HP; i += n) {       // W1^T, k-major, row stride HP (pad columns = 0)
+    const int k = i / HP, o = i - k * HP;
+    blob[L.o_w1 + i] = o < HID ? W1[o * L.in + k] : 0.f;
   }
-  for (int i = t0; i < HID * L.inp; i += n) {
-    const int o = i / L.inp, k = i - o * L.inp;
-    blob[L.o_w1 + i] = k < L.in ? W1[o * L.in + k] : 0.f;
-  }
-  for (int i = t0; i < HID * HID; i += n) {
-    const int k = i / HID, o = i - k * HID;
-    blob[L.o_w2t + i] = W2[o * HID + k];
-    blob[L.o_w2 + i] = W2[i];
+  for (int i = t0; i < HID * HP; i += n) {        // W2^T
+    const int k = i / HP, o = i - k * HP;
+    blob[L.o_w2 + i] = o < HID ? W2[o * HID + k] : 0.f;
   }
   for (int i = t0; i < L.out * HID; i += n) blob[L.o_w3 + i] = W3[i];
   for (int i = t0; i < HID; i += n) {

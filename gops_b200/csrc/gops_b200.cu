@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -46,10 +47,8 @@ bool make_net(const gops_b200_mlp_desc& d, NetL& L, std::string& why) {
   L.hact = d.hidden_act;
   L.oact = d.out_act;
   int o = 0;
-  L.o_w1t = o; o += round4(L.in * HID);
-  L.o_w1 = o; o += HID * L.inp;
-  L.o_w2t = o; o += HID * HID;
-  L.o_w2 = o; o += HID * HID;
+  L.o_w1 = o; o += L.in * HP;
+  L.o_w2 = o; o += HID * HP;
   L.o_w3 = o; o += round4(L.out * HID);
   L.o_b1 = o; o += HID;
   L.o_b2 = o; o += HID;
@@ -78,18 +77,18 @@ typedef void (*StepFn)(const KParams, const float*, int, float*, float*, float*)
 
 // one translation unit per env model (kernels_<model>.cu), compiled in parallel
 namespace gops {
-RolloutFn rollout_fn_idp(int cfg);
-RolloutFn rollout_fn_lq(int cfg);
+RolloutFn rollout_fn_idp(int cfg, int alg);
+RolloutFn rollout_fn_lq(int cfg, int alg);
 StepFn step_fn_idp();
 StepFn step_fn_lq();
 }  // namespace gops
 
 namespace {
 
-RolloutFn rollout_fn(int model, int cfg) {
+RolloutFn rollout_fn(int model, int cfg, int alg) {
   switch (model) {
-    case GOPS_MODEL_IDPENDULUM: return rollout_fn_idp(cfg);
-    case GOPS_MODEL_LQ: return rollout_fn_lq(cfg);
+    case GOPS_MODEL_IDPENDULUM: return rollout_fn_idp(cfg, alg);
+    case GOPS_MODEL_LQ: return rollout_fn_lq(cfg, alg);
     default: return nullptr;
   }
 }
@@ -113,7 +112,7 @@ struct gops_b200_plan {
   size_t tape_floats = 0;
   float* partial = nullptr;
   size_t partial_floats = 0;
-  bool attr_set[8][4] = {};
+  bool attr_set[4][4] = {};   // [alg][cfg]
   bool timing = false;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int last_grid = 0, last_S = 0, last_NT = 0;
@@ -132,16 +131,18 @@ size_t infer_smem_bytes(const KParams& kp, int S) {
 }
 
 int pick_config(const gops_b200_plan* pl, long long B, bool infer) {
-  int best = -1;
-  for (int c = 0; c < 3; ++c) {
+  // preference: (S=64, 256 thr, 2 CTAs/SM) > (S=32, 128 thr) for small batches > (S=128, 256 thr, 1 CTA/SM)
+  const char* force = getenv("GOPS_B200_CFG");
+  auto fits = [&](int c) {
     const size_t sm = infer ? infer_smem_bytes(pl->kp, kConfigs[c].S) : rollout_smem_bytes(pl->kp, kConfigs[c].S);
-    if (sm > (size_t)pl->max_smem) continue;
-    if (best < 0) best = c;
-    const long long tiles = (B + kConfigs[c].S - 1) / kConfigs[c].S;
-    if (tiles >= pl->sm_count) return c;   // largest tile that still fills every SM
-    best = c;                              // otherwise keep shrinking the tile
-  }
-  return best;
+    return sm <= (size_t)pl->max_smem;
+  };
+  if (force && force[0] >= '0' && force[0] <= '2' && fits(force[0] - '0')) return force[0] - '0';
+  const long long tiles64 = (B + 63) / 64;
+  if (fits(1) && tiles64 >= pl->sm_count) return 1;
+  if (fits(2)) return 2;
+  if (fits(1)) return 1;
+  return fits(0) ? 0 : -1;
 }
 
 int ensure_scratch(gops_b200_plan* pl, int grid, int S, int H) {
@@ -176,7 +177,7 @@ int launch_rollout(gops_b200_plan* pl, const gops_b200_batch* b, int alg, cudaSt
   const int cfg = pick_config(pl, b->batch, false);
   if (cfg < 0) return fail("no kernel configuration fits in shared memory");
   const int S = kConfigs[cfg].S, NT = kConfigs[cfg].NT;
-  RolloutFn fn = rollout_fn(pl->desc.model, cfg);
+  RolloutFn fn = rollout_fn(pl->desc.model, cfg, alg);
   if (!fn) return fail("env model kind not built into this library");
   kp.alg = alg;
   kp.batch = b->batch;
@@ -184,18 +185,22 @@ int launch_rollout(gops_b200_plan* pl, const gops_b200_batch* b, int alg, cudaSt
   kp.obs = b->obs; kp.done = b->done; kp.state = b->state; kp.ref_points = b->ref_points;
   kp.path_num = b->path_num; kp.u_num = b->u_num; kp.ref_time = b->ref_time; kp.reference = b->reference;
   kp.ref_t = b->ref_t;
-  const int grid = kp.n_tiles < pl->sm_count ? kp.n_tiles : pl->sm_count;
   const NetL& upd = (alg == ALG_PEV) ? kp.val : kp.pol;
   kp.part_stride = round4(upd.nparam + 4);
   kp.dw_floats = round4(upd.nparam);
+  const size_t smem = rollout_smem_bytes(kp, S);
+  if (!pl->attr_set[alg][cfg]) {
+    CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, pl->max_smem));
+    pl->attr_set[alg][cfg] = true;
+  }
+  int occ = 1;
+  CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, NT, smem));
+  if (occ < 1) return fail("rollout kernel does not fit on an SM");
+  const long long slots = (long long)pl->sm_count * occ;
+  const int grid = (int)(kp.n_tiles < slots ? kp.n_tiles : slots);
   if (ensure_scratch(pl, grid, S, kp.horizon)) return 1;
   kp.tape = pl->tape;
   kp.partial = pl->partial;
-  const size_t smem = rollout_smem_bytes(kp, S);
-  if (!pl->attr_set[pl->desc.model][cfg]) {
-    CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, pl->max_smem));
-    pl->attr_set[pl->desc.model][cfg] = true;
-  }
   if (pl->timing) CUDA_OK(cudaEventRecord(pl->ev0, st));
   fn<<<grid, NT, smem, st>>>(kp);
   CUDA_OK(cudaGetLastError());
@@ -222,7 +227,7 @@ int gops_b200_plan_create(const gops_b200_plan_desc* d, gops_b200_plan** out) {
   *out = nullptr;
   if (d->alg < GOPS_ALG_FHADP || d->alg > GOPS_ALG_INFADP_VALUE) return fail("unknown algorithm kind");
   if (d->horizon < 1 || d->horizon > 4096) return fail("horizon out of range");
-  if (!rollout_fn(d->model, 0)) return fail("env model kind not built into this library");
+  if (!rollout_fn(d->model, 0, d->alg)) return fail("env model kind not built into this library");
   gops_b200_plan* pl = new (std::nothrow) gops_b200_plan();
   if (!pl) return fail("out of host memory");
   pl->desc = *d;

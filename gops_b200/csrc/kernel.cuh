@@ -4,9 +4,13 @@
 
 namespace gops {
 
-template <class M, int S, int NT>
-__global__ void __launch_bounds__(NT, 1) rollout_kernel(const __grid_constant__ KParams p) {
+// min CTAs/SM the register allocator must allow: (S=64,NT=256) -> 2, (S=32,NT=128) -> 4
+constexpr int min_blocks(int S, int NT) { return S == 128 ? 1 : (S == 64 ? 2 : 4); }
+
+template <class M, int S, int NT, int ALG>
+__global__ void __launch_bounds__(NT, min_blocks(S, NT)) rollout_kernel(const __grid_constant__ KParams p) {
   constexpr int SP = S + 4, NS = M::NS, TC = NS + 1;
+  constexpr int alg = ALG;
   extern __shared__ __align__(16) float smem[];
   uint64_t* mbar = reinterpret_cast<uint64_t*>(smem);
   Tiles t;
@@ -23,7 +27,7 @@ __global__ void __launch_bounds__(NT, 1) rollout_kernel(const __grid_constant__ 
   const bool lane_s = tid < S;
   const NetL& P = p.pol;
   const NetL& V = p.val;
-  const int H = p.horizon, obs_dim = P.obs, alg = p.alg;
+  const int H = p.horizon, obs_dim = P.obs;
   const long long B = p.batch;
   uint32_t phase = 0;
 

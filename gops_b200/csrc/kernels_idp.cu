@@ -6,11 +6,21 @@ namespace gops {
 typedef void (*RolloutFn)(const KParams);
 typedef void (*StepFn)(const KParams, const float*, int, float*, float*, float*);
 
-RolloutFn rollout_fn_idp(int cfg) {
+template <int ALG>
+static RolloutFn pick(int cfg) {
   switch (cfg) {
-    case 0: return rollout_kernel<ModelIdp, 128, 256>;
-    case 1: return rollout_kernel<ModelIdp, 64, 256>;
-    default: return rollout_kernel<ModelIdp, 32, 128>;
+    case 0: return rollout_kernel<ModelIdp, 128, 256, ALG>;
+    case 1: return rollout_kernel<ModelIdp, 64, 256, ALG>;
+    default: return rollout_kernel<ModelIdp, 32, 128, ALG>;
+  }
+}
+
+RolloutFn rollout_fn_idp(int cfg, int alg) {
+  switch (alg) {
+    case ALG_FHADP: return pick<ALG_FHADP>(cfg);
+    case ALG_PIM: return pick<ALG_PIM>(cfg);
+    case ALG_PEV: return pick<ALG_PEV>(cfg);
+    default: return pick<ALG_TRACE>(cfg);
   }
 }
 StepFn step_fn_idp() { return model_step_kernel<ModelIdp>; }

@@ -158,19 +158,15 @@ struct ModelIdp {
                                                   float* abar) {
     const IdpC c = idp_const();
     const float u = 500.f * a[0];
-    float sj[5][6];
+    float sj[5][6], s5[6];     // sub-step states: indexed in rolled loops (thread-local stack, L1 resident)
 #pragma unroll
-    for (int f = 0; f < 6; ++f) sj[0][f] = s[f];
+    for (int f = 0; f < 6; ++f) s5[f] = s[f];
+#pragma unroll 1
+    for (int j = 0; j < 5; ++j) {
 #pragma unroll
-    for (int j = 1; j < 5; ++j) {
-#pragma unroll
-      for (int f = 0; f < 6; ++f) sj[j][f] = sj[j - 1][f];
-      idp_substep(sj[j], u, c);
+      for (int f = 0; f < 6; ++f) sj[j][f] = s5[f];
+      idp_substep(s5, u, c);
     }
-    float s5[6];
-#pragma unroll
-    for (int f = 0; f < 6; ++f) s5[f] = sj[4][f];
-    idp_substep(s5, u, c);
     // reward is evaluated on the post-step state
     lam[1] += rho * (-10.f * s5[1]);
     lam[2] += rho * (-20.f * s5[2]);
@@ -178,7 +174,7 @@ struct ModelIdp {
     lam[4] += rho * (-s5[4]);
     lam[5] += rho * (-2.f * s5[5]);
     float ubar = 0.f;
-#pragma unroll
+#pragma unroll 1
     for (int j = 4; j >= 0; --j) idp_substep_bwd(sj[j], u, c, lam, ubar);
     abar[0] = rho * (-2.f * a[0]) + 500.f * ubar;
   }

@@ -1,4 +1,4 @@
-// Fused rollout + loss + gradient kernel for hidden width 64 (sm_100a).
+// Fused rollout + loss + gradient kernel for hidden width 64 (sm_100a): shared-memory tile primitives.
 //
 // One CTA owns a tile of S samples for the whole horizon:
 //   * per-sample model state lives in the registers of thread t < S for all H steps;
@@ -9,12 +9,15 @@
 //     (per-CTA scratch, L2 resident) and accumulates weight gradients in shared memory;
 //   * each CTA writes one gradient partial; a second kernel reduces partials in fixed order
 //     (deterministic, no float atomics).
+// The dense primitives are deliberately NOT inlined: the hot loop must stay I-cache resident
+// (v1 inlined everything: 68k SASS instructions, `no_instruction` was the top stall).
 #pragma once
 #include "common.cuh"
 
 namespace gops {
 
 constexpr int HID = 64;
+constexpr int HP = HID + 4;   // row stride of the k-major weight tiles (bank skew for transposed reads)
 
 // Layout of one network (host computed).
 struct NetL {
@@ -24,7 +27,8 @@ struct NetL {
   int out;         // outputs (<= MAXA)
   int hact, oact, time_input;
   // packed weight blob offsets (floats); blob is what TMA copies to shared memory
-  int o_w1t, o_w1, o_w2t, o_w2, o_w3, o_b1, o_b2, o_b3, blob;
+  //   w1: [in][HP]  (W1^T, k-major)   w2: [HID][HP] (W2^T)   w3: [out][HID]   b1,b2: [HID]   b3: [4]
+  int o_w1, o_w2, o_w3, o_b1, o_b2, o_b3, blob;
   // torch flat parameter offsets
   int g_w1, g_b1, g_w2, g_b2, g_w3, g_b3, nparam;
 };
@@ -73,24 +77,38 @@ struct KParams {
 constexpr int ALG_FHADP = GOPS_ALG_FHADP, ALG_PIM = GOPS_ALG_INFADP_POLICY, ALG_PEV = GOPS_ALG_INFADP_VALUE,
               ALG_TRACE = 3;
 
+// Warp tiling of a [HID x S] output tile: every warp is 4 (feature) x 8 (sample) threads, a thread
+// owns TM features x 4 samples.  One k-step then needs ONE 64 B and ONE 128 B shared wavefront per warp.
+template <int S, int NT>
+struct Map {
+  static constexpr int SP = S + 4, NW = NT / 32, WN = S / 32, WM = NW / WN, TM = HID / (4 * WM);
+  static_assert(S % 32 == 0 && NW % WN == 0 && WM >= 1 && TM >= 1 && TM * 4 * WM == HID && TM % 4 == 0, "bad tiling");
+  int n0, mt;   // first sample column, feature-thread index (0 .. 4*WM-1)
+  __device__ __forceinline__ Map() {
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    n0 = ((w % WN) * 8 + (l & 7)) * 4;
+    mt = (w / WN) * 4 + (l >> 3);
+  }
+};
+
 // ---------------------------------------------------------------------------------------------
-// CTA-level dense primitives on shared-memory tiles
+// P[m][n] = bias[m] + sum_k A[k][m] * B[k][n]   (pre-activations of a hidden layer)
+// A: k-major weights [K][HP], B: [K][SP].  Thread owns CONTIGUOUS features m0 .. m0+TM-1.
 // ---------------------------------------------------------------------------------------------
-// C[m][n] = sum_k A[k][m] * B[k][n] for m < HID, n < S.   A: [K][HID], B: [K][SP].
-// MODE 0: pre = C + bias[m]; H = act(pre)                      (forward, inference)
-// MODE 1: pre = C + bias[m]; H = act(pre), D = act'(pre)       (forward, recompute for backward)
-// MODE 2: H[m][n] = C * D[m][n]                                (backward through a hidden layer)
-template <int S, int NT, int MODE>
-__device__ __forceinline__ void gemm_hid(const float* __restrict__ A, const float* __restrict__ Bm, int K,
-                                         const float* __restrict__ bias, int act, float* __restrict__ Hout,
-                                         float* __restrict__ Dbuf) {
-  constexpr int SP = S + 4, NTN = S / 4, MG = NT / NTN, TM = HID / MG;
-  static_assert(TM % 4 == 0 && TM >= 4, "bad tile");
-  const int tid = threadIdx.x, nt = tid % NTN, m0 = (tid / NTN) * TM;
+template <int S, int NT>
+__device__ __noinline__ void gemm_fwd(const float* __restrict__ A, const float* __restrict__ Bm, int K,
+                                      const float* __restrict__ bias, float* __restrict__ P) {
+  using M = Map<S, NT>;
+  constexpr int SP = M::SP, TM = M::TM;
+  const M mp;
+  const int m0 = mp.mt * TM;
   float acc[TM][4];
 #pragma unroll
-  for (int j = 0; j < TM; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
-  const float* bp = Bm + 4 * nt;
+  for (int j = 0; j < TM; ++j) {
+    const float bb = bias[m0 + j];
+    acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = bb;
+  }
+  const float* bp = Bm + mp.n0;
   const float* ap = A + m0;
 #pragma unroll 4
   for (int k = 0; k < K; ++k) {
@@ -98,7 +116,7 @@ __device__ __forceinline__ void gemm_hid(const float* __restrict__ A, const floa
     float a[TM];
 #pragma unroll
     for (int q = 0; q < TM / 4; ++q) {
-      const float4 av = *reinterpret_cast<const float4*>(ap + k * HID + 4 * q);
+      const float4 av = *reinterpret_cast<const float4*>(ap + k * HP + 4 * q);
       a[4 * q] = av.x; a[4 * q + 1] = av.y; a[4 * q + 2] = av.z; a[4 * q + 3] = av.w;
     }
 #pragma unroll
@@ -110,55 +128,107 @@ __device__ __forceinline__ void gemm_hid(const float* __restrict__ A, const floa
     }
   }
 #pragma unroll
+  for (int j = 0; j < TM; ++j)
+    *reinterpret_cast<float4*>(P + (m0 + j) * SP + mp.n0) = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
+}
+
+// In-place activation of the tile a thread just wrote with gemm_fwd (same ownership -> no barrier):
+// H <- act(P); if D != nullptr also D <- act'(P).  Rolled loop: the activation code exists once.
+template <int S, int NT>
+__device__ __noinline__ void act_pass(float* __restrict__ H, float* __restrict__ D, int act) {
+  using M = Map<S, NT>;
+  constexpr int SP = M::SP, TM = M::TM;
+  const M mp;
+  const int m0 = mp.mt * TM;
+#pragma unroll 1
   for (int j = 0; j < TM; ++j) {
-    const int row = m0 + j;
+    float* hp = H + (m0 + j) * SP + mp.n0;
+    const float4 p = *reinterpret_cast<const float4*>(hp);
     float4 h, d;
-    if (MODE == 2) {
-      d = *reinterpret_cast<const float4*>(Dbuf + row * SP + 4 * nt);
-      h.x = acc[j][0] * d.x; h.y = acc[j][1] * d.y; h.z = acc[j][2] * d.z; h.w = acc[j][3] * d.w;
-      *reinterpret_cast<float4*>(Hout + row * SP + 4 * nt) = h;
+    if (D != nullptr) {
+      act_fwd_grad(act, p.x, h.x, d.x); act_fwd_grad(act, p.y, h.y, d.y);
+      act_fwd_grad(act, p.z, h.z, d.z); act_fwd_grad(act, p.w, h.w, d.w);
+      *reinterpret_cast<float4*>(D + (m0 + j) * SP + mp.n0) = d;
     } else {
-      const float bb = bias[row];
-      if (MODE == 1) {
-        act_fwd_grad(act, acc[j][0] + bb, h.x, d.x);
-        act_fwd_grad(act, acc[j][1] + bb, h.y, d.y);
-        act_fwd_grad(act, acc[j][2] + bb, h.z, d.z);
-        act_fwd_grad(act, acc[j][3] + bb, h.w, d.w);
-        *reinterpret_cast<float4*>(Dbuf + row * SP + 4 * nt) = d;
-      } else {
-        h.x = act_fwd(act, acc[j][0] + bb); h.y = act_fwd(act, acc[j][1] + bb);
-        h.z = act_fwd(act, acc[j][2] + bb); h.w = act_fwd(act, acc[j][3] + bb);
-      }
-      *reinterpret_cast<float4*>(Hout + row * SP + 4 * nt) = h;
+      h.x = act_fwd(act, p.x); h.y = act_fwd(act, p.y); h.z = act_fwd(act, p.z); h.w = act_fwd(act, p.w);
     }
+    *reinterpret_cast<float4*>(hp) = h;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// D[i][n] <- D[i][n] * sum_o A[i][o] * Dl[o][n]     (delta of a hidden layer, in place over D)
+// A: the SAME k-major tile [HID][HP] read transposed; thread owns INTERLEAVED rows i = mt + 4*WM*j so
+// the four feature-threads of a warp read consecutive rows (HP = 68 -> banks skewed by 4, conflict-free).
+// ---------------------------------------------------------------------------------------------
+template <int S, int NT>
+__device__ __noinline__ void gemm_bwd(const float* __restrict__ A, const float* __restrict__ Dl,
+                                      float* __restrict__ D) {
+  using M = Map<S, NT>;
+  constexpr int SP = M::SP, TM = M::TM, RS = 4 * M::WM;
+  const M mp;
+  float acc[TM][4];
+#pragma unroll
+  for (int j = 0; j < TM; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+  const float* ap = A + mp.mt * HP;
+  const float* bp = Dl + mp.n0;
+#pragma unroll 2
+  for (int o = 0; o < HID; o += 4) {
+    float4 b[4];
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) b[kk] = *reinterpret_cast<const float4*>(bp + (o + kk) * SP);
+#pragma unroll
+    for (int j = 0; j < TM; ++j) {
+      const float4 a = *reinterpret_cast<const float4*>(ap + j * RS * HP + o);
+      acc[j][0] = fmaf(a.x, b[0].x, acc[j][0]); acc[j][1] = fmaf(a.x, b[0].y, acc[j][1]);
+      acc[j][2] = fmaf(a.x, b[0].z, acc[j][2]); acc[j][3] = fmaf(a.x, b[0].w, acc[j][3]);
+      acc[j][0] = fmaf(a.y, b[1].x, acc[j][0]); acc[j][1] = fmaf(a.y, b[1].y, acc[j][1]);
+      acc[j][2] = fmaf(a.y, b[1].z, acc[j][2]); acc[j][3] = fmaf(a.y, b[1].w, acc[j][3]);
+      acc[j][0] = fmaf(a.z, b[2].x, acc[j][0]); acc[j][1] = fmaf(a.z, b[2].y, acc[j][1]);
+      acc[j][2] = fmaf(a.z, b[2].z, acc[j][2]); acc[j][3] = fmaf(a.z, b[2].w, acc[j][3]);
+      acc[j][0] = fmaf(a.w, b[3].x, acc[j][0]); acc[j][1] = fmaf(a.w, b[3].y, acc[j][1]);
+      acc[j][2] = fmaf(a.w, b[3].z, acc[j][2]); acc[j][3] = fmaf(a.w, b[3].w, acc[j][3]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < TM; ++j) {
+    float* dp = D + (mp.mt + j * RS) * SP + mp.n0;
+    float4 d = *reinterpret_cast<const float4*>(dp);
+    d.x *= acc[j][0]; d.y *= acc[j][1]; d.z *= acc[j][2]; d.w *= acc[j][3];
+    *reinterpret_cast<float4*>(dp) = d;
   }
 }
 
 // Z[a][s] = b3[a] + sum_i W3[a][i] * H[i][s]       (output layer, out <= MAXA)
 template <int S, int NT>
-__device__ __forceinline__ void out_layer(const float* __restrict__ W3, const float* __restrict__ b3,
-                                          const float* __restrict__ H, int out, float* __restrict__ Z) {
+__device__ __noinline__ void out_layer(const float* __restrict__ W3, const float* __restrict__ b3,
+                                       const float* __restrict__ H, int out, float* __restrict__ Z) {
   constexpr int SP = S + 4;
   for (int idx = threadIdx.x; idx < out * S; idx += NT) {
     const int a = idx / S, s = idx - a * S;
-    float acc = b3[a];
+    float a0 = b3[a], a1 = 0.f;
 #pragma unroll 8
-    for (int i = 0; i < HID; ++i) acc = fmaf(W3[a * HID + i], H[i * SP + s], acc);
-    Z[a * SP + s] = acc;
+    for (int i = 0; i < HID; i += 2) {
+      a0 = fmaf(W3[a * HID + i], H[i * SP + s], a0);
+      a1 = fmaf(W3[a * HID + i + 1], H[(i + 1) * SP + s], a1);
+    }
+    Z[a * SP + s] = a0 + a1;
   }
 }
 
 // D[i][s] <- D[i][s] * sum_a W3[a][i] * Zb[a][s]   (delta of the last hidden layer, in place)
 template <int S, int NT>
-__device__ __forceinline__ void delta_from_out(const float* __restrict__ W3, const float* __restrict__ Zb, int out,
-                                               float* __restrict__ D) {
-  constexpr int SP = S + 4, NTN = S / 4, MG = NT / NTN, TM = HID / MG;
-  const int tid = threadIdx.x, nt = tid % NTN, m0 = (tid / NTN) * TM;
+__device__ __noinline__ void delta_from_out(const float* __restrict__ W3, const float* __restrict__ Zb, int out,
+                                            float* __restrict__ D) {
+  using M = Map<S, NT>;
+  constexpr int SP = M::SP, TM = M::TM;
+  const M mp;
+  const int m0 = mp.mt * TM;
   float4 zb[MAXA];
 #pragma unroll
   for (int a = 0; a < MAXA; ++a)
-    zb[a] = a < out ? *reinterpret_cast<const float4*>(Zb + a * SP + 4 * nt) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
+    zb[a] = a < out ? *reinterpret_cast<const float4*>(Zb + a * SP + mp.n0) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
   for (int j = 0; j < TM; ++j) {
     const int row = m0 + j;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -169,9 +239,9 @@ __device__ __forceinline__ void delta_from_out(const float* __restrict__ W3, con
         acc.x = fmaf(w, zb[a].x, acc.x); acc.y = fmaf(w, zb[a].y, acc.y);
         acc.z = fmaf(w, zb[a].z, acc.z); acc.w = fmaf(w, zb[a].w, acc.w);
       }
-    float4 d = *reinterpret_cast<const float4*>(D + row * SP + 4 * nt);
+    float4 d = *reinterpret_cast<const float4*>(D + row * SP + mp.n0);
     d.x *= acc.x; d.y *= acc.y; d.z *= acc.z; d.w *= acc.w;
-    *reinterpret_cast<float4*>(D + row * SP + 4 * nt) = d;
+    *reinterpret_cast<float4*>(D + row * SP + mp.n0) = d;
   }
 }
 
@@ -179,8 +249,8 @@ __device__ __forceinline__ void delta_from_out(const float* __restrict__ W3, con
 // Tiles own interleaved rows (o = to + tiles_o*j) so that lanes of a warp touch consecutive rows
 // of the (S+4)-strided tiles -> conflict-free float4 shared loads.
 template <int S, int NT, int TO, int TI>
-__device__ __forceinline__ void dw_accum(const float* __restrict__ Dl, int RO, const float* __restrict__ Xl, int RI,
-                                         float* __restrict__ dst, int ld) {
+__device__ __noinline__ void dw_accum(const float* __restrict__ Dl, int RO, const float* __restrict__ Xl, int RI,
+                                      float* __restrict__ dst, int ld) {
   constexpr int SP = S + 4;
   const int tiles_o = (RO + TO - 1) / TO, tiles_i = (RI + TI - 1) / TI;
   for (int tile = threadIdx.x; tile < tiles_o * tiles_i; tile += NT) {
@@ -227,7 +297,7 @@ __device__ __forceinline__ void dw_accum(const float* __restrict__ Dl, int RO, c
 
 // dst[o] += sum_s Dl[o][s]        (bias gradient)
 template <int S, int NT>
-__device__ __forceinline__ void rowsum_accum(const float* __restrict__ Dl, int RO, float* __restrict__ dst) {
+__device__ __noinline__ void rowsum_accum(const float* __restrict__ Dl, int RO, float* __restrict__ dst) {
   constexpr int SP = S + 4;
   for (int o = threadIdx.x; o < RO; o += NT) {
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
@@ -240,10 +310,10 @@ __device__ __forceinline__ void rowsum_accum(const float* __restrict__ Dl, int R
   }
 }
 
-// Xb[i][s] = sum_o W1[o][i] * Dl[o][s]  for i < M (M <= 8*MG)   (input gradient; W1: [HID][ldw])
+// Xb[i][s] = sum_o W1k[i][o] * Dl[o][s]  for i < M (M <= 8*MG)   (input gradient; W1k: [in][HP] k-major)
 template <int S, int NT>
-__device__ __forceinline__ void gemm_dx(const float* __restrict__ W1, int ldw, const float* __restrict__ Dl, int M,
-                                        float* __restrict__ Xb) {
+__device__ __noinline__ void gemm_dx(const float* __restrict__ W1k, const float* __restrict__ Dl, int M,
+                                     float* __restrict__ Xb) {
   constexpr int SP = S + 4, NTN = S / 4, MG = NT / NTN, JM = 8;
   const int tid = threadIdx.x, nt = tid % NTN, mg = tid / NTN;
   const int J = (M - mg + MG - 1) / MG;  // rows mg, mg+MG, ... < M
@@ -251,15 +321,23 @@ __device__ __forceinline__ void gemm_dx(const float* __restrict__ W1, int ldw, c
   float acc[JM][4];
 #pragma unroll
   for (int j = 0; j < JM; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
-#pragma unroll 2
-  for (int o = 0; o < HID; ++o) {
-    const float4 d = *reinterpret_cast<const float4*>(Dl + o * SP + 4 * nt);
+#pragma unroll 1
+  for (int o = 0; o < HID; o += 4) {
+    float4 d[4];
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) d[kk] = *reinterpret_cast<const float4*>(Dl + (o + kk) * SP + 4 * nt);
 #pragma unroll
     for (int j = 0; j < JM; ++j)
       if (j < J) {
-        const float w = W1[o * ldw + mg + MG * j];
-        acc[j][0] = fmaf(w, d.x, acc[j][0]); acc[j][1] = fmaf(w, d.y, acc[j][1]);
-        acc[j][2] = fmaf(w, d.z, acc[j][2]); acc[j][3] = fmaf(w, d.w, acc[j][3]);
+        const float4 w = *reinterpret_cast<const float4*>(W1k + (mg + MG * j) * HP + o);
+        acc[j][0] = fmaf(w.x, d[0].x, acc[j][0]); acc[j][1] = fmaf(w.x, d[0].y, acc[j][1]);
+        acc[j][2] = fmaf(w.x, d[0].z, acc[j][2]); acc[j][3] = fmaf(w.x, d[0].w, acc[j][3]);
+        acc[j][0] = fmaf(w.y, d[1].x, acc[j][0]); acc[j][1] = fmaf(w.y, d[1].y, acc[j][1]);
+        acc[j][2] = fmaf(w.y, d[1].z, acc[j][2]); acc[j][3] = fmaf(w.y, d[1].w, acc[j][3]);
+        acc[j][0] = fmaf(w.z, d[2].x, acc[j][0]); acc[j][1] = fmaf(w.z, d[2].y, acc[j][1]);
+        acc[j][2] = fmaf(w.z, d[2].z, acc[j][2]); acc[j][3] = fmaf(w.z, d[2].w, acc[j][3]);
+        acc[j][0] = fmaf(w.w, d[3].x, acc[j][0]); acc[j][1] = fmaf(w.w, d[3].y, acc[j][1]);
+        acc[j][2] = fmaf(w.w, d[3].z, acc[j][2]); acc[j][3] = fmaf(w.w, d[3].w, acc[j][3]);
       }
   }
 #pragma unroll
@@ -276,9 +354,11 @@ struct Tiles {
 // X -> H1 -> H2 -> Z.  FULL: also store activation derivatives (needed by mlp_backward).
 template <int S, int NT, bool FULL>
 __device__ __forceinline__ void mlp_forward(const NetL& L, const Tiles& t) {
-  gemm_hid<S, NT, FULL ? 1 : 0>(t.W + L.o_w1t, t.X, L.in, t.W + L.o_b1, L.hact, t.H1, t.D1);
+  gemm_fwd<S, NT>(t.W + L.o_w1, t.X, L.in, t.W + L.o_b1, t.H1);
+  act_pass<S, NT>(t.H1, FULL ? t.D1 : nullptr, L.hact);
   __syncthreads();
-  gemm_hid<S, NT, FULL ? 1 : 0>(t.W + L.o_w2t, t.H1, HID, t.W + L.o_b2, L.hact, t.H2, t.D2);
+  gemm_fwd<S, NT>(t.W + L.o_w2, t.H1, HID, t.W + L.o_b2, t.H2);
+  act_pass<S, NT>(t.H2, FULL ? t.D2 : nullptr, L.hact);
   __syncthreads();
   out_layer<S, NT>(t.W + L.o_w3, t.W + L.o_b3, t.H2, L.out, t.Z);
   __syncthreads();
@@ -294,7 +374,7 @@ __device__ __forceinline__ void mlp_backward(const NetL& L, const Tiles& t, bool
   }
   delta_from_out<S, NT>(t.W + L.o_w3, t.Z, L.out, t.D2);  // D2 <- delta2
   __syncthreads();
-  gemm_hid<S, NT, 2>(t.W + L.o_w2, t.D2, HID, nullptr, 0, t.D1, t.D1);  // D1 <- delta1
+  gemm_bwd<S, NT>(t.W + L.o_w2, t.D2, t.D1);              // D1 <- delta1
   if (WANT_DW) {
     dw_accum<S, NT, 4, 4>(t.D2, HID, t.H1, HID, t.dW + L.g_w2, HID);
     rowsum_accum<S, NT>(t.D2, HID, t.dW + L.g_b2);
@@ -306,7 +386,7 @@ __device__ __forceinline__ void mlp_backward(const NetL& L, const Tiles& t, bool
     rowsum_accum<S, NT>(t.D1, HID, t.dW + L.g_b1);
     __syncthreads();
   }
-  if (want_dx) gemm_dx<S, NT>(t.W + L.o_w1, L.inp, t.D1, L.obs, t.X);
+  if (want_dx) gemm_dx<S, NT>(t.W + L.o_w1, t.D1, L.obs, t.X);
   __syncthreads();
 }
 
