@@ -68,7 +68,7 @@ bool make_net(const gops_b200_mlp_desc& d, NetL& L, std::string& why) {
 struct Config {
   int S, NT;
 };
-const Config kConfigs[] = {{128, 256}, {64, 256}, {32, 128}};
+const Config kConfigs[] = {{128, 512}, {64, 256}, {32, 128}};   // sub-tile S, threads (= samples per chunk)
 
 typedef void (*RolloutFn)(const KParams);
 typedef void (*StepFn)(const KParams, const float*, int, float*, float*, float*);
@@ -121,32 +121,35 @@ struct gops_b200_plan {
 
 namespace {
 
-size_t rollout_smem_bytes(const KParams& kp, int S) {
-  const int SP = S + 4;
-  return sizeof(float) * (size_t)(4 + kp.w_floats + kp.dw_floats + kp.inp_max * SP + 4 * HID * SP + 4 * SP);
+size_t rollout_smem_bytes(const KParams& kp, int S, int NT) {
+  const int SP = S + 4, XS = NT + 4;
+  return sizeof(float) * (size_t)(4 + kp.w_floats + kp.dw_floats + kp.inp_max * XS + 4 * HID * SP + 4 * XS);
 }
-size_t infer_smem_bytes(const KParams& kp, int S) {
-  const int SP = S + 4;
-  return sizeof(float) * (size_t)(4 + kp.w_floats + kp.inp_max * SP + 2 * HID * SP + 4 * SP);
+size_t infer_smem_bytes(const KParams& kp, int S, int NT) {
+  const int SP = S + 4, XS = NT + 4;
+  return sizeof(float) * (size_t)(4 + kp.w_floats + kp.inp_max * XS + 2 * HID * SP + 4 * XS);
 }
 
 int pick_config(const gops_b200_plan* pl, long long B, bool infer) {
-  // preference: (S=64, 256 thr, 2 CTAs/SM) > (S=32, 128 thr) for small batches > (S=128, 256 thr, 1 CTA/SM)
+  // the largest chunk (threads per CTA) that still gives every SM at least one CTA
   const char* force = getenv("GOPS_B200_CFG");
   auto fits = [&](int c) {
-    const size_t sm = infer ? infer_smem_bytes(pl->kp, kConfigs[c].S) : rollout_smem_bytes(pl->kp, kConfigs[c].S);
+    const size_t sm = infer ? infer_smem_bytes(pl->kp, kConfigs[c].S, kConfigs[c].NT)
+                            : rollout_smem_bytes(pl->kp, kConfigs[c].S, kConfigs[c].NT);
     return sm <= (size_t)pl->max_smem;
   };
   if (force && force[0] >= '0' && force[0] <= '2' && fits(force[0] - '0')) return force[0] - '0';
-  const long long tiles64 = (B + 63) / 64;
-  if (fits(1) && tiles64 >= pl->sm_count) return 1;
-  if (fits(2)) return 2;
-  if (fits(1)) return 1;
-  return fits(0) ? 0 : -1;
+  int best = -1;
+  for (int c = 0; c < 3; ++c) {
+    if (!fits(c)) continue;
+    best = c;
+    if (B >= (long long)pl->sm_count * kConfigs[c].NT) return c;
+  }
+  return best;
 }
 
-int ensure_scratch(gops_b200_plan* pl, int grid, int S, int H) {
-  const size_t need_tape = (size_t)grid * H * (model_ns(pl->desc.model) + 1) * S;
+int ensure_scratch(gops_b200_plan* pl, int grid, int NT, int H) {
+  const size_t need_tape = (size_t)grid * H * pl->kp.tape_ch * NT;
   if (need_tape > pl->tape_floats) {
     if (pl->tape) cudaFree(pl->tape);
     pl->tape = nullptr;
@@ -181,14 +184,15 @@ int launch_rollout(gops_b200_plan* pl, const gops_b200_batch* b, int alg, cudaSt
   if (!fn) return fail("env model kind not built into this library");
   kp.alg = alg;
   kp.batch = b->batch;
-  kp.n_tiles = (int)((b->batch + S - 1) / S);
+  kp.n_tiles = (int)((b->batch + NT - 1) / NT);
+  kp.tape_ch = model_ns(pl->desc.model) + 1 + kp.pol.out;
   kp.obs = b->obs; kp.done = b->done; kp.state = b->state; kp.ref_points = b->ref_points;
   kp.path_num = b->path_num; kp.u_num = b->u_num; kp.ref_time = b->ref_time; kp.reference = b->reference;
   kp.ref_t = b->ref_t;
   const NetL& upd = (alg == ALG_PEV) ? kp.val : kp.pol;
   kp.part_stride = round4(upd.nparam + 4);
   kp.dw_floats = round4(upd.nparam);
-  const size_t smem = rollout_smem_bytes(kp, S);
+  const size_t smem = rollout_smem_bytes(kp, S, NT);
   if (!pl->attr_set[alg][cfg]) {
     CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, pl->max_smem));
     pl->attr_set[alg][cfg] = true;
@@ -198,7 +202,7 @@ int launch_rollout(gops_b200_plan* pl, const gops_b200_batch* b, int alg, cudaSt
   if (occ < 1) return fail("rollout kernel does not fit on an SM");
   const long long slots = (long long)pl->sm_count * occ;
   const int grid = (int)(kp.n_tiles < slots ? kp.n_tiles : slots);
-  if (ensure_scratch(pl, grid, S, kp.horizon)) return 1;
+  if (ensure_scratch(pl, grid, NT, kp.horizon)) return 1;
   kp.tape = pl->tape;
   kp.partial = pl->partial;
   if (pl->timing) CUDA_OK(cudaEventRecord(pl->ev0, st));
@@ -404,10 +408,11 @@ static int infer_common(gops_b200_plan* pl, const float* params, int use_val, co
   if (launch_pack(params, L, blob, st)) return 1;
   const int cfg = pick_config(pl, batch, true);
   if (cfg < 0) return fail("no kernel configuration fits in shared memory");
-  const int S = kConfigs[cfg].S;
-  const long long tiles = (batch + S - 1) / S;
+  const int S = kConfigs[cfg].S, NTc = kConfigs[cfg].NT;
+  const long long tiles = (batch + NTc - 1) / NTc;
   const int grid = (int)(tiles < pl->sm_count ? tiles : pl->sm_count);
-  const size_t smem = infer_smem_bytes(pl->kp, S);
+  const size_t smem = infer_smem_bytes(pl->kp, S, NTc);
+  (void)S;
 #define LAUNCH_INFER(SS, NN)                                                                                  \
   do {                                                                                                        \
     CUDA_OK(cudaFuncSetAttribute(mlp_infer_kernel<SS, NN>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
@@ -415,7 +420,7 @@ static int infer_common(gops_b200_plan* pl, const float* params, int use_val, co
     mlp_infer_kernel<SS, NN><<<grid, NN, smem, st>>>(pl->kp, blob, use_val, obs, batch, virtual_t,            \
                                                      squash ? 1 : 0, out);                                   \
   } while (0)
-  if (cfg == 0) LAUNCH_INFER(128, 256);
+  if (cfg == 0) LAUNCH_INFER(128, 512);
   else if (cfg == 1) LAUNCH_INFER(64, 256);
   else LAUNCH_INFER(32, 128);
 #undef LAUNCH_INFER

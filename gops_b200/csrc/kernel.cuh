@@ -4,12 +4,11 @@
 
 namespace gops {
 
-// min CTAs/SM the register allocator must allow: (S=64,NT=256) -> 2, (S=32,NT=128) -> 4
-constexpr int min_blocks(int S, int NT) { return S == 128 ? 1 : (S == 64 ? 2 : 4); }
-
+// One CTA = NT threads = NT samples per chunk; MLP GEMMs run over SUB = NT/S sub-tiles of S samples that
+// reuse one set of activation tiles; the per-sample dynamics (forward and adjoint) run on every thread.
 template <class M, int S, int NT, int ALG>
-__global__ void __launch_bounds__(NT, min_blocks(S, NT)) rollout_kernel(const __grid_constant__ KParams p) {
-  constexpr int SP = S + 4, NS = M::NS, TC = NS + 1;
+__global__ void __launch_bounds__(NT, 1) rollout_kernel(const __grid_constant__ KParams p) {
+  constexpr int SP = S + 4, XS = NT + 4, NS = M::NS;
   constexpr int alg = ALG;
   extern __shared__ __align__(16) float smem[];
   uint64_t* mbar = reinterpret_cast<uint64_t*>(smem);
@@ -17,17 +16,16 @@ __global__ void __launch_bounds__(NT, min_blocks(S, NT)) rollout_kernel(const __
   t.W = smem + 4;
   t.dW = t.W + p.w_floats;
   t.X = t.dW + p.dw_floats;
-  t.H1 = t.X + p.inp_max * SP;
+  t.H1 = t.X + p.inp_max * XS;
   t.D1 = t.H1 + HID * SP;
   t.H2 = t.D1 + HID * SP;
   t.D2 = t.H2 + HID * SP;
-  t.Z = t.D2 + HID * SP;
+  t.Z = t.D2 + HID * SP;      // [4][XS]
 
   const int tid = threadIdx.x;
-  const bool lane_s = tid < S;
   const NetL& P = p.pol;
   const NetL& V = p.val;
-  const int H = p.horizon, obs_dim = P.obs;
+  const int H = p.horizon, obs_dim = P.obs, TCH = p.tape_ch;
   const long long B = p.batch;
   uint32_t phase = 0;
 
@@ -52,51 +50,64 @@ __global__ void __launch_bounds__(NT, min_blocks(S, NT)) rollout_kernel(const __
     mbar_wait(mbar, phase);
     phase ^= 1u;
   };
-  auto load_obs_tile = [&](long long base) {
-    for (int idx = tid; idx < S * obs_dim; idx += NT) {
+  // coalesced read of the chunk's [n][obs_dim] rows, transposed into X (columns >= n are zero-filled)
+  auto load_obs_chunk = [&](long long pos, int n, int ncols) {
+    for (int idx = tid; idx < ncols * obs_dim; idx += NT) {
       const int s = idx / obs_dim, f = idx - s * obs_dim;
-      const long long gs = base + s;
-      t.X[f * SP + s] = gs < B ? p.obs[gs * obs_dim + f] : 0.f;
+      t.X[f * XS + s] = s < n ? p.obs[(pos + s) * obs_dim + f] : 0.f;
     }
+  };
+  auto sub_tiles = [&](int sub) {
+    Tiles ts = t;
+    ts.X = t.X + sub * S;
+    ts.Z = t.Z + sub * S;
+    return ts;
   };
 
   stage(p.blob_pol, P.blob);
 
-  float* tape = p.tape + (size_t)blockIdx.x * (size_t)H * TC * S;
+  float* tape = p.tape + (size_t)blockIdx.x * (size_t)H * TCH * NT;
   float loss_acc = 0.f, vmean_acc = 0.f, done_acc = 0.f;
 
-  for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-    const long long base = (long long)tile * S;
+  // balanced contiguous sample range of this CTA, processed in chunks of NT samples
+  const long long r0 = B * blockIdx.x / gridDim.x, r1 = B * (blockIdx.x + 1) / gridDim.x;
+  for (long long pos = r0; pos < r1; pos += NT) {
+    const int nv = (int)((r1 - pos) < NT ? (r1 - pos) : NT);
+    const int nsub = (nv + S - 1) / S;
     __syncthreads();
-    load_obs_tile(base);
+    load_obs_chunk(pos, nv, nsub * S);
     __syncthreads();
     float st[NS];
-    bool dn = true, valid = false;
+    const bool valid = tid < nv;
+    const long long gs = pos + tid;
+    bool dn = valid ? (p.done[gs] != 0.f) : true;
     float vacc = 0.f;
-    const long long gs = base + tid;
-    if (lane_s) {
-      valid = gs < B;
-      dn = valid ? (p.done[gs] != 0.f) : true;
 #pragma unroll
-      for (int f = 0; f < NS; ++f) st[f] = f < obs_dim ? t.X[f * SP + tid] : 0.f;
-    }
+    for (int f = 0; f < NS; ++f) st[f] = f < obs_dim ? t.X[f * XS + tid] : 0.f;
 
     // ================================ forward sweep ================================
     for (int k = 0; k < H; ++k) {
-      if (lane_s) {
-        if (alg == ALG_FHADP || alg == ALG_PIM) {
+      if (alg == ALG_FHADP || alg == ALG_PIM) {
 #pragma unroll
-          for (int f = 0; f < NS; ++f) tape[(k * TC + f) * S + tid] = st[f];
-          tape[(k * TC + NS) * S + tid] = dn ? 1.f : 0.f;
-        }
-        if (P.time_input) t.X[(P.in - 1) * SP + tid] = (float)(k + 1);
+        for (int f = 0; f < NS; ++f) tape[(k * TCH + f) * NT + tid] = st[f];
+        tape[(k * TCH + NS) * NT + tid] = dn ? 1.f : 0.f;
+      }
+      if (P.time_input) t.X[(P.in - 1) * XS + tid] = (float)(k + 1);
+      __syncthreads();
+      for (int sub = 0; sub < nsub; ++sub) {
+        const Tiles ts = sub_tiles(sub);
+        mlp_forward<S, NT, false, true>(P, ts, ts.Z);
       }
       __syncthreads();
-      mlp_forward<S, NT, false>(P, t);
-      if (lane_s) {
+      {
         float z[MAXA], a[MAXA], g[MAXA], apol[MAXA];
 #pragma unroll
-        for (int j = 0; j < MAXA; ++j) z[j] = j < P.out ? t.Z[j * SP + tid] : 0.f;
+        for (int j = 0; j < MAXA; ++j) z[j] = j < P.out ? t.Z[j * XS + tid] : 0.f;
+        if (alg == ALG_FHADP || alg == ALG_PIM) {
+#pragma unroll
+          for (int j = 0; j < MAXA; ++j)
+            if (j < P.out) tape[(k * TCH + NS + 1 + j) * NT + tid] = z[j];
+        }
         process_action(p, P.out, z, a, g, apol);
         const bool active = valid && (p.mask_at_done ? !dn : true);
         float r = 0.f;
@@ -110,7 +121,7 @@ __global__ void __launch_bounds__(NT, min_blocks(S, NT)) rollout_kernel(const __
           dn = md;
 #pragma unroll
           for (int f = 0; f < NS; ++f)
-            if (f < obs_dim) t.X[f * SP + tid] = st[f];
+            if (f < obs_dim) t.X[f * XS + tid] = st[f];
         }
         if (valid) {
           // ShapingReward sits outside MaskAtDone: a masked (done) sample still pays (0 + shift) * scale
@@ -120,7 +131,7 @@ __global__ void __launch_bounds__(NT, min_blocks(S, NT)) rollout_kernel(const __
         if (alg == ALG_TRACE && valid) {
           const size_t row = (size_t)k * B + gs;
           if (p.tr_obs)
-            for (int f = 0; f < obs_dim; ++f) p.tr_obs[row * obs_dim + f] = t.X[f * SP + tid];
+            for (int f = 0; f < obs_dim; ++f) p.tr_obs[row * obs_dim + f] = t.X[f * XS + tid];
           if (p.tr_act)
             for (int j = 0; j < P.out; ++j) p.tr_act[row * P.out + j] = apol[j];
           if (p.tr_rew) p.tr_rew[row] = r;
@@ -128,7 +139,7 @@ __global__ void __launch_bounds__(NT, min_blocks(S, NT)) rollout_kernel(const __
         }
       }
     }
-    if (lane_s && valid && dn) done_acc += 1.f;
+    if (valid && dn) done_acc += 1.f;
     if (alg == ALG_TRACE) continue;
 
     // ============================ terminal value (INFADP) ============================
@@ -137,22 +148,29 @@ __global__ void __launch_bounds__(NT, min_blocks(S, NT)) rollout_kernel(const __
     for (int f = 0; f < NS; ++f) lam[f] = 0.f;
     if (alg != ALG_FHADP) {
       stage(p.blob_vtg, V.blob);  // leading __syncthreads also publishes X = o_n
-      if (alg == ALG_PIM) mlp_forward<S, NT, true>(V, t);
-      else mlp_forward<S, NT, false>(V, t);
       const float gn = p.gpow[H];
-      bool term = false;
-      if (lane_s) {
-        term = valid && !dn;
-        if (term) vacc += gn * t.Z[tid];
-        if (alg == ALG_PIM) t.Z[tid] = term ? -gn * p.inv_B : 0.f;
-      }
+      const bool term = valid && !dn;
       if (alg == ALG_PIM) {
+        t.Z[tid] = term ? -gn * p.inv_B : 0.f;     // row 0: d loss / d v_target(o_n); row 1 receives v
         __syncthreads();
-        mlp_backward<S, NT, false>(V, t, true);
-        if (lane_s && term) {
+      }
+      for (int sub = 0; sub < nsub; ++sub) {
+        const Tiles ts = sub_tiles(sub);
+        if (alg == ALG_PIM) {
+          mlp_forward<S, NT, true, true>(V, ts, ts.Z + XS);
+          __syncthreads();
+          mlp_backward<S, NT, false>(V, ts, true);
+        } else {
+          mlp_forward<S, NT, false, true>(V, ts, ts.Z + XS);
+        }
+      }
+      __syncthreads();
+      if (term) {
+        vacc += gn * t.Z[XS + tid];
+        if (alg == ALG_PIM) {
 #pragma unroll
           for (int f = 0; f < NS; ++f)
-            if (f < obs_dim) lam[f] = t.X[f * SP + tid];
+            if (f < obs_dim) lam[f] = t.X[f * XS + tid];
         }
       }
     }
@@ -160,53 +178,52 @@ __global__ void __launch_bounds__(NT, min_blocks(S, NT)) rollout_kernel(const __
     if (alg == ALG_PEV) {
       // loss_v = mean((v(o_0) - backup)^2), gradient w.r.t. the value net only
       stage(p.blob_val, V.blob);
-      load_obs_tile(base);
+      load_obs_chunk(pos, nv, nsub * S);
       __syncthreads();
-      mlp_forward<S, NT, true>(V, t);
-      if (lane_s) {
-        float zb = 0.f;
-        if (valid) {
-          const float v0 = t.Z[tid];
-          const float diff = v0 - vacc;
-          loss_acc += diff * diff * p.inv_B;
-          vmean_acc += v0 * p.inv_B;
-          zb = 2.f * diff * p.inv_B;
+      for (int sub = 0; sub < nsub; ++sub) {
+        const Tiles ts = sub_tiles(sub);
+        mlp_forward<S, NT, true, true>(V, ts, ts.Z + XS);
+        __syncthreads();
+        if (tid / S == sub) {
+          float zb = 0.f;
+          if (valid) {
+            const float v0 = t.Z[XS + tid];
+            const float diff = v0 - vacc;
+            loss_acc += diff * diff * p.inv_B;
+            vmean_acc += v0 * p.inv_B;
+            zb = 2.f * diff * p.inv_B;
+          }
+          t.Z[tid] = zb;
         }
-        t.Z[tid] = zb;
+        __syncthreads();
+        mlp_backward<S, NT, true>(V, ts, false);
       }
-      __syncthreads();
-      mlp_backward<S, NT, true>(V, t, false);
       stage(p.blob_pol, P.blob);
       continue;
     }
 
-    if (lane_s && valid) loss_acc += -vacc * p.inv_B;
+    if (valid) loss_acc += -vacc * p.inv_B;
     if (alg == ALG_PIM) stage(p.blob_pol, P.blob);
 
     // ================================ reverse sweep ================================
     for (int k = H - 1; k >= 0; --k) {
-      bool dnk = true;
-      if (lane_s) {
+      // per-sample adjoint of step k on every thread (state, done flag and policy output come from the tape)
 #pragma unroll
-        for (int f = 0; f < NS; ++f) st[f] = tape[(k * TC + f) * S + tid];
-        dnk = tape[(k * TC + NS) * S + tid] != 0.f;
+      for (int f = 0; f < NS; ++f) st[f] = tape[(k * TCH + f) * NT + tid];
+      const bool dnk = tape[(k * TCH + NS) * NT + tid] != 0.f;
 #pragma unroll
-        for (int f = 0; f < NS; ++f)
-          if (f < obs_dim) t.X[f * SP + tid] = st[f];
-        if (P.time_input) t.X[(P.in - 1) * SP + tid] = (float)(k + 1);
-      }
-      __syncthreads();
-      mlp_forward<S, NT, true>(P, t);
-      bool active = false;
-      if (lane_s) {
-        active = valid && (p.mask_at_done ? !dnk : true);
+      for (int f = 0; f < NS; ++f)
+        if (f < obs_dim) t.X[f * XS + tid] = st[f];
+      if (P.time_input) t.X[(P.in - 1) * XS + tid] = (float)(k + 1);
+      const bool active = valid && (p.mask_at_done ? !dnk : true);
+      {
         float zb[MAXA];
 #pragma unroll
         for (int j = 0; j < MAXA; ++j) zb[j] = 0.f;
         if (active) {
           float z[MAXA], a[MAXA], g[MAXA], abar[MAXA];
 #pragma unroll
-          for (int j = 0; j < MAXA; ++j) z[j] = j < P.out ? t.Z[j * SP + tid] : 0.f;
+          for (int j = 0; j < MAXA; ++j) z[j] = j < P.out ? tape[(k * TCH + NS + 1 + j) * NT + tid] : 0.f;
           process_action(p, P.out, z, a, g, nullptr);
           if (p.clip_obs) {
             float nx[NS], r;
@@ -227,14 +244,19 @@ __global__ void __launch_bounds__(NT, min_blocks(S, NT)) rollout_kernel(const __
         }
 #pragma unroll
         for (int j = 0; j < MAXA; ++j)
-          if (j < P.out) t.Z[j * SP + tid] = zb[j];
+          if (j < P.out) t.Z[j * XS + tid] = zb[j];
       }
       __syncthreads();
-      mlp_backward<S, NT, true>(P, t, k > 0);
-      if (lane_s && active && k > 0) {
+      // MLP: re-compute the hidden activations of step k per sub-tile, then back-propagate Zbar
+      for (int sub = 0; sub < nsub; ++sub) {
+        const Tiles ts = sub_tiles(sub);
+        mlp_forward<S, NT, true, false>(P, ts, nullptr);
+        mlp_backward<S, NT, true>(P, ts, k > 0);
+      }
+      if (active && k > 0) {
 #pragma unroll
         for (int f = 0; f < NS; ++f)
-          if (f < obs_dim) lam[f] += t.X[f * SP + tid];
+          if (f < obs_dim) lam[f] += t.X[f * XS + tid];
       }
     }
   }
@@ -263,7 +285,7 @@ template <int S, int NT>
 __global__ void __launch_bounds__(NT, 1) mlp_infer_kernel(const __grid_constant__ KParams p, const float* blob, int use_val,
                                                           const float* __restrict__ obs, long long B, float virtual_t,
                                                           int squash, float* __restrict__ out) {
-  constexpr int SP = S + 4;
+  constexpr int SP = S + 4, XS = NT + 4;
   extern __shared__ __align__(16) float smem[];
   uint64_t* mbar = reinterpret_cast<uint64_t*>(smem);
   const NetL& L = use_val ? p.val : p.pol;
@@ -271,7 +293,7 @@ __global__ void __launch_bounds__(NT, 1) mlp_infer_kernel(const __grid_constant_
   t.W = smem + 4;
   t.dW = t.W + p.w_floats;
   t.X = t.dW;
-  t.H1 = t.X + p.inp_max * SP;
+  t.H1 = t.X + p.inp_max * XS;
   t.D1 = t.H1;
   t.H2 = t.H1 + HID * SP;
   t.D2 = t.H2;
@@ -292,27 +314,34 @@ __global__ void __launch_bounds__(NT, 1) mlp_infer_kernel(const __grid_constant_
     }
   }
   mbar_wait(mbar, 0);
-  const int n_tiles = (int)((B + S - 1) / S);
-  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const long long base = (long long)tile * S;
+  const long long n_chunks = (B + NT - 1) / NT;
+  for (long long c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+    const long long base = c * NT;
+    const int nv = (int)((B - base) < NT ? (B - base) : NT);
+    const int nsub = (nv + S - 1) / S;
     __syncthreads();
-    for (int idx = tid; idx < S * L.obs; idx += NT) {
+    for (int idx = tid; idx < nsub * S * L.obs; idx += NT) {
       const int s = idx / L.obs, f = idx - s * L.obs;
-      t.X[f * SP + s] = base + s < B ? obs[(base + s) * L.obs + f] : 0.f;
+      t.X[f * XS + s] = s < nv ? obs[(base + s) * L.obs + f] : 0.f;
     }
-    if (L.time_input && tid < S) t.X[(L.in - 1) * SP + tid] = virtual_t;
+    if (L.time_input) t.X[(L.in - 1) * XS + tid] = virtual_t;
     __syncthreads();
-    mlp_forward<S, NT, false>(L, t);
-    if (tid < S && base + tid < B) {
+    for (int sub = 0; sub < nsub; ++sub) {
+      Tiles ts = t;
+      ts.X = t.X + sub * S;
+      ts.Z = t.Z + sub * S;
+      mlp_forward<S, NT, false, true>(L, ts, ts.Z);
+    }
+    __syncthreads();
+    if (tid < nv) {
       for (int j = 0; j < L.out; ++j) {
-        float z = t.Z[j * SP + tid];
+        float z = t.Z[j * XS + tid];
         if (squash) z = __fadd_rn(__fmul_rn(p.pol_half[j], tanhf(z)), p.pol_mid[j]);
         out[(base + tid) * L.out + j] = z;
       }
     }
   }
 }
-
 
 // One wrapped-model step for explicit actions: envmodel.forward(obs, action, done, info) of the
 // reference wrapper chain (create_env_model.py:104-126) for state==obs models.

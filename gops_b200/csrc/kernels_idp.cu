@@ -9,7 +9,7 @@ typedef void (*StepFn)(const KParams, const float*, int, float*, float*, float*)
 template <int ALG>
 static RolloutFn pick(int cfg) {
   switch (cfg) {
-    case 0: return rollout_kernel<ModelIdp, 128, 256, ALG>;
+    case 0: return rollout_kernel<ModelIdp, 128, 512, ALG>;
     case 1: return rollout_kernel<ModelIdp, 64, 256, ALG>;
     default: return rollout_kernel<ModelIdp, 32, 128, ALG>;
   }

@@ -1,7 +1,7 @@
 // Fused rollout + loss + gradient kernel for hidden width 64 (sm_100a): shared-memory tile primitives.
 //
-// One CTA owns a tile of S samples for the whole horizon:
-//   * per-sample model state lives in the registers of thread t < S for all H steps;
+// One CTA owns chunks of NT samples (one per thread) for the whole horizon:
+//   * per-sample model state lives in the registers of its thread for all H steps;
 //   * MLP weights are staged ONCE per CTA into shared memory by the TMA bulk-copy engine;
 //   * MLP activations live in shared memory, feature-major [feature][sample] so that every
 //     dense layer is a CTA-level GEMM with float4 shared-memory operands and FP32 FFMA;
@@ -53,7 +53,8 @@ struct KParams {
   const float* reference;
   int ref_t, ref_len, veh_P;
   // scratch
-  float* tape;             // [grid][H][NS+1][S]
+  float* tape;             // [grid][H][tape_ch][NT]  (state, done flag, policy pre-activation z)
+  int tape_ch;
   float* ext_ref;          // veh3dofconti: [grid][P+1+H][4][S]
   float* partial;          // [grid][part_stride]
   int part_stride;
@@ -96,7 +97,7 @@ struct Map {
 // A: k-major weights [K][HP], B: [K][SP].  Thread owns CONTIGUOUS features m0 .. m0+TM-1.
 // ---------------------------------------------------------------------------------------------
 template <int S, int NT>
-__device__ __noinline__ void gemm_fwd(const float* __restrict__ A, const float* __restrict__ Bm, int K,
+__device__ __noinline__ void gemm_fwd(const float* __restrict__ A, const float* __restrict__ Bm, int ldb, int K,
                                       const float* __restrict__ bias, float* __restrict__ P) {
   using M = Map<S, NT>;
   constexpr int SP = M::SP, TM = M::TM;
@@ -112,7 +113,7 @@ __device__ __noinline__ void gemm_fwd(const float* __restrict__ A, const float* 
   const float* ap = A + m0;
 #pragma unroll 4
   for (int k = 0; k < K; ++k) {
-    const float4 b = *reinterpret_cast<const float4*>(bp + k * SP);
+    const float4 b = *reinterpret_cast<const float4*>(bp + k * ldb);
     float a[TM];
 #pragma unroll
     for (int q = 0; q < TM / 4; ++q) {
@@ -202,7 +203,7 @@ __device__ __noinline__ void gemm_bwd(const float* __restrict__ A, const float* 
 // Z[a][s] = b3[a] + sum_i W3[a][i] * H[i][s]       (output layer, out <= MAXA)
 template <int S, int NT>
 __device__ __noinline__ void out_layer(const float* __restrict__ W3, const float* __restrict__ b3,
-                                       const float* __restrict__ H, int out, float* __restrict__ Z) {
+                                       const float* __restrict__ H, int out, float* __restrict__ Z, int ldz) {
   constexpr int SP = S + 4;
   for (int idx = threadIdx.x; idx < out * S; idx += NT) {
     const int a = idx / S, s = idx - a * S;
@@ -212,13 +213,13 @@ __device__ __noinline__ void out_layer(const float* __restrict__ W3, const float
       a0 = fmaf(W3[a * HID + i], H[i * SP + s], a0);
       a1 = fmaf(W3[a * HID + i + 1], H[(i + 1) * SP + s], a1);
     }
-    Z[a * SP + s] = a0 + a1;
+    Z[a * ldz + s] = a0 + a1;
   }
 }
 
 // D[i][s] <- D[i][s] * sum_a W3[a][i] * Zb[a][s]   (delta of the last hidden layer, in place)
 template <int S, int NT>
-__device__ __noinline__ void delta_from_out(const float* __restrict__ W3, const float* __restrict__ Zb, int out,
+__device__ __noinline__ void delta_from_out(const float* __restrict__ W3, const float* __restrict__ Zb, int ldz, int out,
                                             float* __restrict__ D) {
   using M = Map<S, NT>;
   constexpr int SP = M::SP, TM = M::TM;
@@ -227,7 +228,7 @@ __device__ __noinline__ void delta_from_out(const float* __restrict__ W3, const 
   float4 zb[MAXA];
 #pragma unroll
   for (int a = 0; a < MAXA; ++a)
-    zb[a] = a < out ? *reinterpret_cast<const float4*>(Zb + a * SP + mp.n0) : make_float4(0.f, 0.f, 0.f, 0.f);
+    zb[a] = a < out ? *reinterpret_cast<const float4*>(Zb + a * ldz + mp.n0) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 1
   for (int j = 0; j < TM; ++j) {
     const int row = m0 + j;
@@ -249,9 +250,8 @@ __device__ __noinline__ void delta_from_out(const float* __restrict__ W3, const 
 // Tiles own interleaved rows (o = to + tiles_o*j) so that lanes of a warp touch consecutive rows
 // of the (S+4)-strided tiles -> conflict-free float4 shared loads.
 template <int S, int NT, int TO, int TI>
-__device__ __noinline__ void dw_accum(const float* __restrict__ Dl, int RO, const float* __restrict__ Xl, int RI,
-                                      float* __restrict__ dst, int ld) {
-  constexpr int SP = S + 4;
+__device__ __noinline__ void dw_accum(const float* __restrict__ Dl, int ldd, int RO, const float* __restrict__ Xl,
+                                      int ldx, int RI, float* __restrict__ dst, int ld) {
   const int tiles_o = (RO + TO - 1) / TO, tiles_i = (RI + TI - 1) / TI;
   for (int tile = threadIdx.x; tile < tiles_o * tiles_i; tile += NT) {
     const int ti = tile % tiles_i, to = tile / tiles_i;
@@ -263,9 +263,9 @@ __device__ __noinline__ void dw_accum(const float* __restrict__ Dl, int RO, cons
     const float* dp[TO];
     const float* xp[TI];
 #pragma unroll
-    for (int j = 0; j < TO; ++j) dp[j] = Dl + min(to + tiles_o * j, RO - 1) * SP;
+    for (int j = 0; j < TO; ++j) dp[j] = Dl + min(to + tiles_o * j, RO - 1) * ldd;
 #pragma unroll
-    for (int q = 0; q < TI; ++q) xp[q] = Xl + min(ti + tiles_i * q, RI - 1) * SP;
+    for (int q = 0; q < TI; ++q) xp[q] = Xl + min(ti + tiles_i * q, RI - 1) * ldx;
 #pragma unroll 2
     for (int s = 0; s < S; s += 4) {
       float4 d[TO], x[TI];
@@ -297,13 +297,12 @@ __device__ __noinline__ void dw_accum(const float* __restrict__ Dl, int RO, cons
 
 // dst[o] += sum_s Dl[o][s]        (bias gradient)
 template <int S, int NT>
-__device__ __noinline__ void rowsum_accum(const float* __restrict__ Dl, int RO, float* __restrict__ dst) {
-  constexpr int SP = S + 4;
+__device__ __noinline__ void rowsum_accum(const float* __restrict__ Dl, int ldd, int RO, float* __restrict__ dst) {
   for (int o = threadIdx.x; o < RO; o += NT) {
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll 4
     for (int s = 0; s < S; s += 4) {
-      const float4 d = *reinterpret_cast<const float4*>(Dl + o * SP + s);
+      const float4 d = *reinterpret_cast<const float4*>(Dl + o * ldd + s);
       a0 += d.x; a1 += d.y; a2 += d.z; a3 += d.w;
     }
     dst[o] += (a0 + a1) + (a2 + a3);
@@ -313,7 +312,7 @@ __device__ __noinline__ void rowsum_accum(const float* __restrict__ Dl, int RO, 
 // Xb[i][s] = sum_o W1k[i][o] * Dl[o][s]  for i < M (M <= 8*MG)   (input gradient; W1k: [in][HP] k-major)
 template <int S, int NT>
 __device__ __noinline__ void gemm_dx(const float* __restrict__ W1k, const float* __restrict__ Dl, int M,
-                                     float* __restrict__ Xb) {
+                                     float* __restrict__ Xb, int ldx) {
   constexpr int SP = S + 4, NTN = S / 4, MG = NT / NTN, JM = 8;
   const int tid = threadIdx.x, nt = tid % NTN, mg = tid / NTN;
   const int J = (M - mg + MG - 1) / MG;  // rows mg, mg+MG, ... < M
@@ -343,50 +342,55 @@ __device__ __noinline__ void gemm_dx(const float* __restrict__ W1k, const float*
 #pragma unroll
   for (int j = 0; j < JM; ++j)
     if (j < J)
-      *reinterpret_cast<float4*>(Xb + (mg + MG * j) * SP + 4 * nt) = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
+      *reinterpret_cast<float4*>(Xb + (mg + MG * j) * ldx + 4 * nt) = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
 }
 
-// Shared-memory views of one CTA.
+// Shared-memory views of one CTA.  X and Z hold one column per THREAD (row stride XS = NT + 4); the
+// activation tiles H1/D1/H2/D2 hold one S-sample sub-tile (row stride SP = S + 4) and are reused by the
+// NT/S sub-tiles of a chunk.  X/Z pointers passed to the mlp_* helpers are already offset to the sub-tile.
 struct Tiles {
   float *W, *dW, *X, *H1, *D1, *H2, *D2, *Z;
 };
 
-// X -> H1 -> H2 -> Z.  FULL: also store activation derivatives (needed by mlp_backward).
-template <int S, int NT, bool FULL>
-__device__ __forceinline__ void mlp_forward(const NetL& L, const Tiles& t) {
-  gemm_fwd<S, NT>(t.W + L.o_w1, t.X, L.in, t.W + L.o_b1, t.H1);
+// X -> H1 -> H2 (-> Zout).  FULL: also store activation derivatives (needed by mlp_backward).
+// No trailing barrier: the caller synchronises once after its sub-tile loop / before consuming Zout.
+template <int S, int NT, bool FULL, bool OUT>
+__device__ __forceinline__ void mlp_forward(const NetL& L, const Tiles& t, float* Zout) {
+  constexpr int XS = NT + 4;
+  gemm_fwd<S, NT>(t.W + L.o_w1, t.X, XS, L.in, t.W + L.o_b1, t.H1);
   act_pass<S, NT>(t.H1, FULL ? t.D1 : nullptr, L.hact);
   __syncthreads();
-  gemm_fwd<S, NT>(t.W + L.o_w2, t.H1, HID, t.W + L.o_b2, t.H2);
+  gemm_fwd<S, NT>(t.W + L.o_w2, t.H1, S + 4, HID, t.W + L.o_b2, t.H2);
   act_pass<S, NT>(t.H2, FULL ? t.D2 : nullptr, L.hact);
   __syncthreads();
-  out_layer<S, NT>(t.W + L.o_w3, t.W + L.o_b3, t.H2, L.out, t.Z);
-  __syncthreads();
+  if (OUT) out_layer<S, NT>(t.W + L.o_w3, t.W + L.o_b3, t.H2, L.out, Zout, XS);
 }
 
-// Given Zbar in t.Z: accumulate weight grads into t.dW (torch flat layout) if WANT_DW and write
-// the observation gradient into rows [0, L.obs) of t.X if want_dx.  Requires a FULL forward.
+// Given Zbar in t.Z (rows 0..out-1): accumulate weight grads into t.dW (torch flat layout) if WANT_DW and
+// write the observation gradient into rows [0, L.obs) of t.X if want_dx.  Requires a FULL forward of the
+// same sub-tile.  Ends with a barrier (the activation tiles may be reused afterwards).
 template <int S, int NT, bool WANT_DW>
 __device__ __forceinline__ void mlp_backward(const NetL& L, const Tiles& t, bool want_dx) {
+  constexpr int XS = NT + 4, SP = S + 4;
   if (WANT_DW) {
-    dw_accum<S, NT, 1, 4>(t.Z, L.out, t.H2, HID, t.dW + L.g_w3, HID);
-    rowsum_accum<S, NT>(t.Z, L.out, t.dW + L.g_b3);
+    dw_accum<S, NT, 1, 4>(t.Z, XS, L.out, t.H2, SP, HID, t.dW + L.g_w3, HID);
+    rowsum_accum<S, NT>(t.Z, XS, L.out, t.dW + L.g_b3);
   }
-  delta_from_out<S, NT>(t.W + L.o_w3, t.Z, L.out, t.D2);  // D2 <- delta2
+  delta_from_out<S, NT>(t.W + L.o_w3, t.Z, XS, L.out, t.D2);  // D2 <- delta2
   __syncthreads();
-  gemm_bwd<S, NT>(t.W + L.o_w2, t.D2, t.D1);              // D1 <- delta1
+  gemm_bwd<S, NT>(t.W + L.o_w2, t.D2, t.D1);                  // D1 <- delta1
   if (WANT_DW) {
-    dw_accum<S, NT, 4, 4>(t.D2, HID, t.H1, HID, t.dW + L.g_w2, HID);
-    rowsum_accum<S, NT>(t.D2, HID, t.dW + L.g_b2);
+    dw_accum<S, NT, 4, 4>(t.D2, SP, HID, t.H1, SP, HID, t.dW + L.g_w2, HID);
+    rowsum_accum<S, NT>(t.D2, SP, HID, t.dW + L.g_b2);
   }
   __syncthreads();
   if (WANT_DW) {
-    if (L.in <= 16) dw_accum<S, NT, 2, 2>(t.D1, HID, t.X, L.in, t.dW + L.g_w1, L.in);
-    else dw_accum<S, NT, 4, 4>(t.D1, HID, t.X, L.in, t.dW + L.g_w1, L.in);
-    rowsum_accum<S, NT>(t.D1, HID, t.dW + L.g_b1);
-    __syncthreads();
+    if (L.in <= 16) dw_accum<S, NT, 2, 2>(t.D1, SP, HID, t.X, XS, L.in, t.dW + L.g_w1, L.in);
+    else dw_accum<S, NT, 4, 4>(t.D1, SP, HID, t.X, XS, L.in, t.dW + L.g_w1, L.in);
+    rowsum_accum<S, NT>(t.D1, SP, HID, t.dW + L.g_b1);
+    if (want_dx) __syncthreads();
   }
-  if (want_dx) gemm_dx<S, NT>(t.W + L.o_w1, t.D1, L.obs, t.X);
+  if (want_dx) gemm_dx<S, NT>(t.W + L.o_w1, t.D1, L.obs, t.X, XS);
   __syncthreads();
 }
 
