@@ -22,7 +22,7 @@ class MlpDesc(C.Structure):
 
 
 class RefTraj(C.Structure):
-    _fields_ = [(n, C.c_float) for n in (
+    _fields_ = [(n, C.c_double) for n in (
         "sine_A", "sine_omega", "sine_phi", "dl_t1", "dl_t2", "dl_t3", "dl_t4", "dl_y1", "dl_y2",
         "tri_A", "tri_T", "circ_r", "sp_A", "sp_omega", "sp_phi", "sp_b", "sp_const")]
 
@@ -42,14 +42,14 @@ class PlanDesc(C.Structure):
         ("lq_inv_IA", C.c_float * (MAX_LQ_N * MAX_LQ_N)), ("lq_B", C.c_float * (MAX_LQ_N * MAX_ACT)),
         ("lq_Q", C.c_float * MAX_LQ_N), ("lq_R", C.c_float * MAX_ACT),
         ("lq_dt", C.c_float), ("lq_reward_scale", C.c_float), ("lq_reward_shift", C.c_float),
-        ("veh_pre_horizon", C.c_int32), ("veh_ref_len", C.c_int32), ("reftraj", RefTraj),
+        ("veh_pre_horizon", C.c_int32), ("reftraj", RefTraj),
     ]
 
 
 class Batch(C.Structure):
     _fields_ = [("batch", C.c_int64), ("obs", C.c_void_p), ("done", C.c_void_p), ("state", C.c_void_p),
                 ("ref_points", C.c_void_p), ("path_num", C.c_void_p), ("u_num", C.c_void_p),
-                ("ref_time", C.c_void_p), ("reference", C.c_void_p), ("ref_t", C.c_int32)]
+                ("ref_time", C.c_void_p), ("reference", C.c_void_p), ("ref_t", C.c_int32), ("ref_len", C.c_int32)]
 
 
 # name -> (restype, argtypes); the parity test `test_abi_symbols` checks these against the header

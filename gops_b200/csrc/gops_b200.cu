@@ -79,6 +79,8 @@ typedef void (*StepFn)(const KParams, const float*, int, float*, float*, float*)
 namespace gops {
 RolloutFn rollout_fn_idp(int cfg, int alg);
 RolloutFn rollout_fn_lq(int cfg, int alg);
+RolloutFn rollout_fn_vehconti(int cfg, int alg);
+RolloutFn rollout_fn_vehtrack(int cfg, int alg);
 StepFn step_fn_idp();
 StepFn step_fn_lq();
 }  // namespace gops
@@ -89,6 +91,8 @@ RolloutFn rollout_fn(int model, int cfg, int alg) {
   switch (model) {
     case GOPS_MODEL_IDPENDULUM: return rollout_fn_idp(cfg, alg);
     case GOPS_MODEL_LQ: return rollout_fn_lq(cfg, alg);
+    case GOPS_MODEL_VEH3DOFCONTI: return rollout_fn_vehconti(cfg, alg);
+    case GOPS_MODEL_VEH3DOF_TRACKING: return rollout_fn_vehtrack(cfg, alg);
     default: return nullptr;
   }
 }
@@ -99,7 +103,7 @@ StepFn step_fn(int model) {
     default: return nullptr;
   }
 }
-int model_ns(int model) { return model == GOPS_MODEL_LQ ? LQN : 6; }
+int model_ns(int model) { return model == GOPS_MODEL_LQ ? LQN : (model == GOPS_MODEL_VEH3DOFCONTI ? 7 : 6); }
 
 }  // namespace
 
@@ -112,6 +116,8 @@ struct gops_b200_plan {
   size_t tape_floats = 0;
   float* partial = nullptr;
   size_t partial_floats = 0;
+  float* ext_ref = nullptr;
+  size_t ext_ref_floats = 0;
   bool attr_set[4][4] = {};   // [alg][cfg]
   bool timing = false;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -156,6 +162,16 @@ int ensure_scratch(gops_b200_plan* pl, int grid, int NT, int H) {
     CUDA_OK(cudaMalloc(&pl->tape, need_tape * sizeof(float)));
     pl->tape_floats = need_tape;
   }
+  if (pl->desc.model == GOPS_MODEL_VEH3DOFCONTI) {
+    const size_t need = (size_t)grid * (pl->kp.veh_P + 1 + H) * 4 * NT;
+    if (need > pl->ext_ref_floats) {
+      if (pl->ext_ref) cudaFree(pl->ext_ref);
+      pl->ext_ref = nullptr;
+      CUDA_OK(cudaMalloc(&pl->ext_ref, need * sizeof(float)));
+      CUDA_OK(cudaMemset(pl->ext_ref, 0, need * sizeof(float)));
+      pl->ext_ref_floats = need;
+    }
+  }
   const size_t need_part = (size_t)grid * pl->kp.part_stride;
   if (need_part > pl->partial_floats) {
     if (pl->partial) cudaFree(pl->partial);
@@ -176,6 +192,14 @@ int launch_rollout(gops_b200_plan* pl, const gops_b200_batch* b, int alg, cudaSt
                    float* scalars_out) {
   if (!b || b->batch <= 0) return fail("empty batch");
   if (!b->obs || !b->done) return fail("obs/done pointers are required");
+  if (pl->desc.model == GOPS_MODEL_VEH3DOFCONTI &&
+      (!b->state || !b->ref_points || !b->path_num || !b->u_num || !b->ref_time))
+    return fail("pyth_veh3dofconti needs state, ref_points, path_num, u_num, ref_time");
+  if (pl->desc.model == GOPS_MODEL_VEH3DOF_TRACKING) {
+    if (!b->state || !b->reference) return fail("veh3dof_tracking needs state (robot_state) and reference");
+    if (b->ref_t < 0 || b->ref_t + pl->kp.horizon + pl->kp.veh_P + 1 > b->ref_len)
+      return fail("veh3dof_tracking: reference too short for t + horizon + pre_horizon + 1 points");
+  }
   KParams& kp = pl->kp;
   const int cfg = pick_config(pl, b->batch, false);
   if (cfg < 0) return fail("no kernel configuration fits in shared memory");
@@ -189,6 +213,7 @@ int launch_rollout(gops_b200_plan* pl, const gops_b200_batch* b, int alg, cudaSt
   kp.obs = b->obs; kp.done = b->done; kp.state = b->state; kp.ref_points = b->ref_points;
   kp.path_num = b->path_num; kp.u_num = b->u_num; kp.ref_time = b->ref_time; kp.reference = b->reference;
   kp.ref_t = b->ref_t;
+  kp.ref_len = b->ref_len;
   const NetL& upd = (alg == ALG_PEV) ? kp.val : kp.pol;
   kp.part_stride = round4(upd.nparam + 4);
   kp.dw_floats = round4(upd.nparam);
@@ -204,6 +229,7 @@ int launch_rollout(gops_b200_plan* pl, const gops_b200_batch* b, int alg, cudaSt
   const int grid = (int)(kp.n_tiles < slots ? kp.n_tiles : slots);
   if (ensure_scratch(pl, grid, NT, kp.horizon)) return 1;
   kp.tape = pl->tape;
+  kp.ext_ref = pl->ext_ref;
   kp.partial = pl->partial;
   if (pl->timing) CUDA_OK(cudaEventRecord(pl->ev0, st));
   fn<<<grid, NT, smem, st>>>(kp);
@@ -255,6 +281,14 @@ int gops_b200_plan_create(const gops_b200_plan_desc* d, gops_b200_plan** out) {
     obs_dim_model = d->lq_n;
     if (act_dim != d->lq_m) { delete pl; return fail("policy out_dim != lq action dim"); }
   }
+  if (d->model == GOPS_MODEL_VEH3DOFCONTI || d->model == GOPS_MODEL_VEH3DOF_TRACKING) {
+    if (d->veh_pre_horizon < 1) { delete pl; return fail("veh_pre_horizon must be >= 1"); }
+    obs_dim_model = 6 + 4 * d->veh_pre_horizon;
+    if (act_dim != 2) { delete pl; return fail("vehicle models have 2 actions"); }
+    if (d->clip_obs) {
+      // the vehicle models declare +-inf observation bounds (pyth_veh3dofconti_model.py:79-88): identity clip
+    }
+  }
   if (d->policy.in_dim != obs_dim_model) { delete pl; return fail("policy in_dim does not match the env model obs_dim"); }
   if (d->model == GOPS_MODEL_IDPENDULUM && act_dim != 1) { delete pl; return fail("idpendulum has 1 action"); }
 
@@ -273,9 +307,10 @@ int gops_b200_plan_create(const gops_b200_plan_desc* d, gops_b200_plan** out) {
     kp.pol_half[j] = (d->pol_act_high[j] - d->pol_act_low[j]) / 2.f;
     kp.pol_mid[j] = (d->pol_act_high[j] + d->pol_act_low[j]) / 2.f;
   }
+  const bool state_is_obs = d->model == GOPS_MODEL_IDPENDULUM || d->model == GOPS_MODEL_LQ;
   for (int f = 0; f < LQN; ++f) {
-    kp.obs_low[f] = f < obs_dim_model ? d->obs_low[f] : -INFINITY;
-    kp.obs_high[f] = f < obs_dim_model ? d->obs_high[f] : INFINITY;
+    kp.obs_low[f] = (state_is_obs && f < obs_dim_model) ? d->obs_low[f] : -INFINITY;
+    kp.obs_high[f] = (state_is_obs && f < obs_dim_model) ? d->obs_high[f] : INFINITY;
     if (isfinite(kp.obs_low[f]) || isfinite(kp.obs_high[f])) finite_obs_bound = true;
   }
   kp.clip_obs = (d->clip_obs && finite_obs_bound) ? 1 : 0;   // clipping to +-inf is the identity
@@ -288,9 +323,23 @@ int gops_b200_plan_create(const gops_b200_plan_desc* d, gops_b200_plan** out) {
     }
     for (int j = 0; j < d->lq_m; ++j) kp.lq_R[j] = d->lq_R[j];
   }
-  kp.rt = d->reftraj;
+  {
+    const gops_b200_reftraj& r = d->reftraj;
+    RtC& q = kp.rt;
+    q.sine_A = (float)r.sine_A; q.sine_omega = (float)r.sine_omega; q.sine_phi = (float)r.sine_phi;
+    q.dl_t1 = (float)r.dl_t1; q.dl_t2 = (float)r.dl_t2; q.dl_t3 = (float)r.dl_t3; q.dl_t4 = (float)r.dl_t4;
+    q.dl_y1 = (float)r.dl_y1; q.dl_y2 = (float)r.dl_y2;
+    q.dl_k1 = (float)((r.dl_y2 - r.dl_y1) / (r.dl_t2 - r.dl_t1));
+    q.dl_k2 = (float)((r.dl_y1 - r.dl_y2) / (r.dl_t4 - r.dl_t3));
+    q.tri_k1 = (float)(2 * r.tri_A / r.tri_T); q.tri_k2 = (float)(-2 * r.tri_A / r.tri_T);
+    q.tri_T = (float)r.tri_T; q.tri_half = (float)(r.tri_T / 2);
+    q.circ_r = (float)r.circ_r;
+    q.sp_A = (float)r.sp_A; q.sp_omega = (float)r.sp_omega; q.sp_phi = (float)r.sp_phi; q.sp_b = (float)r.sp_b;
+    q.sp_c1 = (float)(-r.sp_A / r.sp_omega); q.sp_c3 = (float)(r.sp_A / r.sp_omega * cos(r.sp_phi));
+    q.sp_const = (float)r.sp_const;
+  }
   kp.veh_P = d->veh_pre_horizon;
-  kp.ref_len = d->veh_ref_len;
+  kp.veh_Pdt = (float)((double)d->veh_pre_horizon * 0.1);   // self.pre_horizon * self.dt
 
   cudaError_t e = cudaGetDevice(&pl->device);
   cudaDeviceProp prop;
@@ -358,7 +407,7 @@ int gops_b200_plan_destroy(gops_b200_plan* pl) {
   if (!pl) return 0;
   if (pl->ev0) { cudaEventDestroy(pl->ev0); cudaEventDestroy(pl->ev1); }
   cudaFree(pl->gpow); cudaFree(pl->blob_pol); cudaFree(pl->blob_val); cudaFree(pl->blob_vtg);
-  cudaFree(pl->tape); cudaFree(pl->partial);
+  cudaFree(pl->tape); cudaFree(pl->partial); cudaFree(pl->ext_ref);
   delete pl;
   return 0;
 }

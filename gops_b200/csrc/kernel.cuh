@@ -82,8 +82,35 @@ __global__ void __launch_bounds__(NT, 1) rollout_kernel(const __grid_constant__ 
     const long long gs = pos + tid;
     bool dn = valid ? (p.done[gs] != 0.f) : true;
     float vacc = 0.f;
+    int path = 0, spd = 0;                       // vehicle models: reference path / speed profile ids
+    RefWindow<M::KIND, NT> win;
+    win.base = nullptr; win.k0 = 0;
+    if constexpr (M::KIND == 0) {
 #pragma unroll
-    for (int f = 0; f < NS; ++f) st[f] = f < obs_dim ? t.X[f * XS + tid] : 0.f;
+      for (int f = 0; f < NS; ++f) st[f] = f < obs_dim ? t.X[f * XS + tid] : 0.f;
+    } else {
+#pragma unroll
+      for (int f = 0; f < NS; ++f) st[f] = 0.f;
+      if (valid) {
+#pragma unroll
+        for (int f = 0; f < 6; ++f) st[f] = p.state[gs * 6 + f];
+      }
+      if constexpr (M::KIND == 1) {
+        float* er = p.ext_ref + (size_t)blockIdx.x * (size_t)(p.veh_P + 1 + H) * 4 * NT + tid;
+        win.base = er;
+        if (valid) {
+          st[6] = p.ref_time[gs];
+          path = (int)p.path_num[gs];
+          spd = (int)p.u_num[gs];
+        }
+        for (int i = 0; i <= p.veh_P; ++i)
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            er[(size_t)(i * 4 + c) * NT] = valid ? p.ref_points[(gs * (p.veh_P + 1) + i) * 4 + c] : 0.f;
+      } else {
+        win.base = p.reference + (size_t)(valid ? gs : 0) * p.ref_len * 4;
+      }
+    }
 
     // ================================ forward sweep ================================
     for (int k = 0; k < H; ++k) {
@@ -113,15 +140,52 @@ __global__ void __launch_bounds__(NT, 1) rollout_kernel(const __grid_constant__ 
         float r = 0.f;
         if (active) {
           bool md;
-          M::step(p, st, a, r, md);
-          if (p.clip_obs) {
+          if constexpr (M::KIND == 0) {
+            M::step(p, st, a, r, md);
+            if (p.clip_obs) {
 #pragma unroll
-            for (int f = 0; f < NS; ++f) st[f] = fminf(fmaxf(st[f], p.obs_low[f]), p.obs_high[f]);
+              for (int f = 0; f < NS; ++f) st[f] = fminf(fmaxf(st[f], p.obs_low[f]), p.obs_high[f]);
+            }
+#pragma unroll
+            for (int f = 0; f < NS; ++f)
+              if (f < obs_dim) t.X[f * XS + tid] = st[f];
+          } else {
+            const VehC vc = veh_const();
+            float o6[6];
+            if constexpr (M::KIND == 1) {
+              // reward from the INCOMING observation (Veh3dofcontiModel.compute_reward :161-177)
+#pragma unroll
+              for (int f = 0; f < 6; ++f) o6[f] = t.X[f * XS + tid];
+              r = -(0.04f * (o6[0] * o6[0]) + 0.04f * (o6[1] * o6[1]) + 0.02f * (o6[2] * o6[2]) +
+                    0.02f * (o6[3] * o6[3]) + 0.01f * (o6[5] * o6[5]) + 0.01f * (a[0] * a[0]) + 0.01f * (a[1] * a[1]));
+              veh_step(vc, st, a);
+              st[6] = st[6] + vc.dt;
+              const float tq = st[6] + p.veh_Pdt;
+              float* nr = const_cast<float*>(win.base) + (size_t)(k + p.veh_P + 1) * 4 * NT;
+              nr[0] = rt_x(p.rt, tq, path, spd);
+              nr[NT] = rt_y(p.rt, tq, path, spd);
+              nr[2 * NT] = rt_phi(p.rt, tq, path, spd);
+              nr[3 * NT] = rt_u(p.rt, tq, spd);
+              win.k0 = k + 1;
+              veh_write_obs<M::KIND, NT>(st, win, p.veh_P, t.X + tid, XS, o6);
+              md = (fabsf(o6[0]) > 10.f) || (fabsf(o6[1]) > 10.f) || (fabsf(o6[2]) > 3.14159265358979323846f);
+            } else {
+              // reward from the CURRENT state against reference[:, t] (veh3dof_tracking_model.py:59-73)
+              float q[4];
+              win.k0 = p.ref_t + k;
+              win.get(0, q);
+              const float ex = st[0] - q[0], ey = st[1] - q[1], ep = angle_normalize(st[2] - q[2]), eu = st[3] - q[3];
+              r = -(0.04f * (ex * ex) + 0.04f * (ey * ey) + 0.02f * (ep * ep) + 0.02f * (eu * eu) +
+                    0.01f * (st[5] * st[5]) + 0.01f * (a[0] * a[0]) + 0.01f * (a[1] * a[1]));
+              veh_step(vc, st, a);
+              win.k0 = p.ref_t + k + 1;
+              veh_write_obs<M::KIND, NT>(st, win, p.veh_P, t.X + tid, XS, o6);
+              win.get(0, q);
+              md = (fabsf(st[0] - q[0]) > 5.f) || (fabsf(st[1] - q[1]) > 2.f) ||
+                   (fabsf(angle_normalize(st[2] - q[2])) > 3.14159265358979323846f);
+            }
           }
           dn = md;
-#pragma unroll
-          for (int f = 0; f < NS; ++f)
-            if (f < obs_dim) t.X[f * XS + tid] = st[f];
         }
         if (valid) {
           // ShapingReward sits outside MaskAtDone: a masked (done) sample still pays (0 + shift) * scale
@@ -168,9 +232,16 @@ __global__ void __launch_bounds__(NT, 1) rollout_kernel(const __grid_constant__ 
       if (term) {
         vacc += gn * t.Z[XS + tid];
         if (alg == ALG_PIM) {
+          if constexpr (M::KIND == 0) {
 #pragma unroll
-          for (int f = 0; f < NS; ++f)
-            if (f < obs_dim) lam[f] = t.X[f * XS + tid];
+            for (int f = 0; f < NS; ++f)
+              if (f < obs_dim) lam[f] = t.X[f * XS + tid];
+          } else {
+            // o_n = get_obs(state_n, window_n): pull the value gradient back onto the robot state
+            const float zero6[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            win.k0 = (M::KIND == 1 ? 0 : p.ref_t) + H;
+            veh_obs_bwd<M::KIND, NT>(st, win, p.veh_P, t.X + tid, XS, zero6, lam);
+          }
         }
       }
     }
@@ -208,14 +279,42 @@ __global__ void __launch_bounds__(NT, 1) rollout_kernel(const __grid_constant__ 
     // ================================ reverse sweep ================================
     for (int k = H - 1; k >= 0; --k) {
       // per-sample adjoint of step k on every thread (state, done flag and policy output come from the tape)
+      if constexpr (M::KIND != 0) {
+        if (k == 0) {             // step 0 consumes the caller's observation, not a re-derived one
+          __syncthreads();
+          load_obs_chunk(pos, nv, nsub * S);
+          __syncthreads();
+        }
+      }
 #pragma unroll
       for (int f = 0; f < NS; ++f) st[f] = tape[(k * TCH + f) * NT + tid];
       const bool dnk = tape[(k * TCH + NS) * NT + tid] != 0.f;
+      float o6[6];                // vehicle models: first six observation entries of step k
+      if constexpr (M::KIND == 0) {
 #pragma unroll
-      for (int f = 0; f < NS; ++f)
-        if (f < obs_dim) t.X[f * XS + tid] = st[f];
+        for (int f = 0; f < NS; ++f)
+          if (f < obs_dim) t.X[f * XS + tid] = st[f];
+      } else {
+        win.k0 = (M::KIND == 1 ? 0 : p.ref_t) + k;
+        if (k > 0) {
+          // only samples that were live at step k have a fully written window; the others get zeros
+          // (their deltas are zero anyway, but 0 * garbage must never reach the weight gradients)
+          if (valid && !(p.mask_at_done && dnk)) veh_write_obs<M::KIND, NT>(st, win, p.veh_P, t.X + tid, XS, o6);
+          else {
+            for (int f = 0; f < obs_dim; ++f) t.X[f * XS + tid] = 0.f;
+#pragma unroll
+            for (int f = 0; f < 6; ++f) o6[f] = 0.f;
+          }
+        } else {
+#pragma unroll
+          for (int f = 0; f < 6; ++f) o6[f] = t.X[f * XS + tid];
+        }
+      }
       if (P.time_input) t.X[(P.in - 1) * XS + tid] = (float)(k + 1);
       const bool active = valid && (p.mask_at_done ? !dnk : true);
+      float ro6[6];               // KIND 1: d loss / d obs_k[0..5] through the reward
+#pragma unroll
+      for (int f = 0; f < 6; ++f) ro6[f] = 0.f;
       {
         float zb[MAXA];
 #pragma unroll
@@ -225,20 +324,40 @@ __global__ void __launch_bounds__(NT, 1) rollout_kernel(const __grid_constant__ 
 #pragma unroll
           for (int j = 0; j < MAXA; ++j) z[j] = j < P.out ? tape[(k * TCH + NS + 1 + j) * NT + tid] : 0.f;
           process_action(p, P.out, z, a, g, nullptr);
-          if (p.clip_obs) {
-            float nx[NS], r;
-            bool md;
-#pragma unroll
-            for (int f = 0; f < NS; ++f) nx[f] = st[f];
-            M::step(p, nx, a, r, md);
-#pragma unroll
-            for (int f = 0; f < NS; ++f)
-              if (nx[f] < p.obs_low[f] || nx[f] > p.obs_high[f]) lam[f] = 0.f;
-          }
           const float rho = -p.gpow[k] * p.inv_B * (p.reward_shaping ? p.reward_scale : 1.f);
 #pragma unroll
           for (int j = 0; j < MAXA; ++j) abar[j] = 0.f;
-          M::step_bwd(p, st, a, rho, lam, abar);
+          if constexpr (M::KIND == 0) {
+            if (p.clip_obs) {
+              float nx[NS], r;
+              bool md;
+#pragma unroll
+              for (int f = 0; f < NS; ++f) nx[f] = st[f];
+              M::step(p, nx, a, r, md);
+#pragma unroll
+              for (int f = 0; f < NS; ++f)
+                if (nx[f] < p.obs_low[f] || nx[f] > p.obs_high[f]) lam[f] = 0.f;
+            }
+            M::step_bwd(p, st, a, rho, lam, abar);
+          } else {
+            const VehC vc = veh_const();
+            veh_step_bwd(vc, st, a, lam, abar);
+            abar[0] += rho * (-0.02f * a[0]);
+            abar[1] += rho * (-0.02f * a[1]);
+            if constexpr (M::KIND == 1) {
+              ro6[0] = rho * (-0.08f * o6[0]); ro6[1] = rho * (-0.08f * o6[1]);
+              ro6[2] = rho * (-0.04f * o6[2]); ro6[3] = rho * (-0.04f * o6[3]);
+              ro6[5] = rho * (-0.02f * o6[5]);
+            } else {
+              float q[4];
+              win.get(0, q);
+              lam[0] += rho * (-0.08f * (st[0] - q[0]));
+              lam[1] += rho * (-0.08f * (st[1] - q[1]));
+              lam[2] += rho * (-0.04f * angle_normalize(st[2] - q[2]));
+              lam[3] += rho * (-0.04f * (st[3] - q[3]));
+              lam[5] += rho * (-0.02f * st[5]);
+            }
+          }
 #pragma unroll
           for (int j = 0; j < MAXA; ++j) zb[j] = abar[j] * g[j];
         }
@@ -254,9 +373,13 @@ __global__ void __launch_bounds__(NT, 1) rollout_kernel(const __grid_constant__ 
         mlp_backward<S, NT, true>(P, ts, k > 0);
       }
       if (active && k > 0) {
+        if constexpr (M::KIND == 0) {
 #pragma unroll
-        for (int f = 0; f < NS; ++f)
-          if (f < obs_dim) lam[f] += t.X[f * XS + tid];
+          for (int f = 0; f < NS; ++f)
+            if (f < obs_dim) lam[f] += t.X[f * XS + tid];
+        } else {
+          veh_obs_bwd<M::KIND, NT>(st, win, p.veh_P, t.X + tid, XS, ro6, lam);
+        }
       }
     }
   }

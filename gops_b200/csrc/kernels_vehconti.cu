@@ -1,0 +1,26 @@
+// Instantiations of the fused rollout kernel for ModelVehConti (own translation unit: parallel build).
+#include "kernel.cuh"
+
+namespace gops {
+
+typedef void (*RolloutFn)(const KParams);
+typedef void (*StepFn)(const KParams, const float*, int, float*, float*, float*);
+
+template <int ALG>
+static RolloutFn pick(int cfg) {
+  switch (cfg) {
+    case 0: return rollout_kernel<ModelVehConti, 128, 512, ALG>;
+    case 1: return rollout_kernel<ModelVehConti, 64, 256, ALG>;
+    default: return rollout_kernel<ModelVehConti, 32, 128, ALG>;
+  }
+}
+
+RolloutFn rollout_fn_vehconti(int cfg, int alg) {
+  switch (alg) {
+    case ALG_FHADP: return pick<ALG_FHADP>(cfg);
+    case ALG_PIM: return pick<ALG_PIM>(cfg);
+    case ALG_PEV: return pick<ALG_PEV>(cfg);
+    default: return pick<ALG_TRACE>(cfg);
+  }
+}
+}  // namespace gops

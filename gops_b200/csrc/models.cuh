@@ -1,6 +1,7 @@
 // Per-sample environment-model dynamics and their hand-derived adjoints (one thread = one sample).
 #pragma once
 #include "rollout.cuh"
+#include "models_veh.cuh"
 
 namespace gops {
 
@@ -139,7 +140,7 @@ __device__ __forceinline__ void idp_substep_bwd(const float* s, float u, const I
 }
 
 struct ModelIdp {
-  static constexpr int NS = 6;
+  static constexpr int NS = 6, KIND = 0;
   // forward: s <- next state; returns raw model reward and done   (:199-216, :126-172)
   __device__ static __forceinline__ void step(const KParams&, float* s, const float* a, float& rew, bool& done) {
     const IdpC c = idp_const();
@@ -184,7 +185,7 @@ struct ModelIdp {
 // pyth_lq   (env_ocp/resources/lq_base.py:89-141, :343-354)   zero-padded to LQN x MAXA
 // =============================================================================================
 struct ModelLq {
-  static constexpr int NS = LQN;
+  static constexpr int NS = LQN, KIND = 0;
   __device__ static __forceinline__ void step(const KParams& p, float* s, const float* a, float& rew, bool& done) {
     float rs = 0.f, ra = 0.f, tmp[LQN];
 #pragma unroll
@@ -230,5 +231,80 @@ struct ModelLq {
     for (int i = 0; i < LQN; ++i) lam[i] = tb[i] + rr * (-2.f * p.lq_Q[i] * s[i]);
   }
 };
+
+// =============================================================================================
+// Vehicle models: the observation is a function of (robot state, reference window); the kernel keeps the
+// robot state (+ reference time for pyth_veh3dofconti) per thread and rebuilds observations on the fly.
+// KIND 1: pyth_veh3dofconti (analytic reference generator, window kept in a per-CTA global scratch)
+// KIND 2: env_gen_ocp veh3dof_tracking (window = slice of the caller's reference tensor)
+// =============================================================================================
+struct ModelVehConti {
+  static constexpr int NS = 7, KIND = 1;   // x, y, phi, u, v, w, ref_time
+};
+struct ModelVehTrack {
+  static constexpr int NS = 6, KIND = 2;
+};
+
+// Accessor of the (P+1)-point reference window of one sample at horizon step k.
+template <int KIND, int NT>
+struct RefWindow {
+  const float* base;   // KIND 1: ext_ref + tid (point-major, stride NT)   KIND 2: reference + gs*L*4
+  int k0;              // first point of the window
+  __device__ __forceinline__ void get(int i, float* q) const {
+    if (KIND == 1) {
+      const float* b = base + (size_t)(k0 + i) * 4 * NT;
+      q[0] = b[0]; q[1] = b[NT]; q[2] = b[2 * NT]; q[3] = b[3 * NT];
+    } else {
+      const float4 v = *reinterpret_cast<const float4*>(base + (size_t)(k0 + i) * 4);
+      q[0] = v.x; q[1] = v.y; q[2] = v.z; q[3] = v.w;
+    }
+  }
+};
+
+// obs = get_obs(state, window) written into column `col` of X (row stride ld); returns first 6 entries in o6
+template <int KIND, int NT>
+__device__ __forceinline__ void veh_write_obs(const float* s, const RefWindow<KIND, NT>& w, int P, float* col, int ld,
+                                              float* o6) {
+  float sn, cs;
+  sincosf(-s[2], &sn, &cs);
+  float q[4], o4[4];
+  w.get(0, q);
+  ego_obs(s, cs, sn, q[0], q[1], q[2], q[3], o4);
+  o6[0] = o4[0]; o6[1] = o4[1]; o6[2] = o4[2]; o6[3] = o4[3]; o6[4] = s[4]; o6[5] = s[5];
+#pragma unroll
+  for (int f = 0; f < 6; ++f) col[f * ld] = o6[f];
+  for (int i = 1; i <= P; ++i) {
+    w.get(i, q);
+    ego_obs(s, cs, sn, q[0], q[1], q[2], q[3], o4);
+    float* c = col + (6 + 4 * (i - 1)) * ld;
+    c[0] = o4[0]; c[ld] = o4[1]; c[2 * ld] = o4[2]; c[3 * ld] = o4[3];
+  }
+}
+
+// adjoint of get_obs w.r.t. the robot state: lam[0..5] += O^T xbar, xbar read from column `col` of X;
+// extra6 = additional adjoint on the first 6 observation entries (reward-on-observation term)
+template <int KIND, int NT>
+__device__ __forceinline__ void veh_obs_bwd(const float* s, const RefWindow<KIND, NT>& w, int P, const float* col,
+                                            int ld, const float* extra6, float* lam) {
+  float sn, cs;
+  sincosf(-s[2], &sn, &cs);
+  float bx = 0.f, by = 0.f, bphi = 0.f, bu = 0.f;
+  for (int i = 0; i <= P; ++i) {
+    float q[4];
+    w.get(i, q);
+    const float* c = col + (i == 0 ? 0 : (6 + 4 * (i - 1))) * ld;
+    float ox = c[0], oy = c[ld], op = c[2 * ld], ou = c[3 * ld];
+    if (i == 0) { ox += extra6[0]; oy += extra6[1]; op += extra6[2]; ou += extra6[3]; }
+    const float dx = q[0] - s[0], dy = q[1] - s[1];
+    const float vx = dx * cs - dy * sn, vy = dx * sn + dy * cs;   // the forward observation entries
+    bx += -cs * ox - sn * oy;
+    by += sn * ox - cs * oy;
+    bphi += vy * ox - vx * oy - op;      // d cos(-phi)/dphi = sin(-phi), d sin(-phi)/dphi = -cos(-phi)
+    bu += -ou;
+  }
+  lam[0] += bx; lam[1] += by; lam[2] += bphi; lam[3] += bu;
+  lam[4] += col[4 * ld] + extra6[4];
+  lam[5] += col[5 * ld] + extra6[5];
+}
 
 }  // namespace gops

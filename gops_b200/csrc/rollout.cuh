@@ -19,6 +19,15 @@ namespace gops {
 constexpr int HID = 64;
 constexpr int HP = HID + 4;   // row stride of the k-major weight tiles (bank skew for transposed reads)
 
+// Reference-trajectory constants as fp32 values derived on the host in double precision.
+struct RtC {
+  float sine_A, sine_omega, sine_phi;
+  float dl_t1, dl_t2, dl_t3, dl_t4, dl_y1, dl_y2, dl_k1, dl_k2;   // k1 = (y2-y1)/(t2-t1), k2 = (y1-y2)/(t4-t3)
+  float tri_k1, tri_k2, tri_T, tri_half;                         // 2A/T, -2A/T, T, T/2
+  float circ_r;
+  float sp_A, sp_omega, sp_phi, sp_b, sp_c1, sp_c3, sp_const;    // c1 = -A/omega, c3 = A/omega*cos(phi)
+};
+
 // Layout of one network (host computed).
 struct NetL {
   int in;          // input rows incl. time column
@@ -52,10 +61,11 @@ struct KParams {
   const float* ref_time;
   const float* reference;
   int ref_t, ref_len, veh_P;
+  float veh_Pdt;           // fp32(pre_horizon * dt) as formed by the reference in python doubles
   // scratch
   float* tape;             // [grid][H][tape_ch][NT]  (state, done flag, policy pre-activation z)
   int tape_ch;
-  float* ext_ref;          // veh3dofconti: [grid][P+1+H][4][S]
+  float* ext_ref;          // veh3dofconti: [grid][P+1+H][4][NT] raw reference points (window slides by one per step)
   float* partial;          // [grid][part_stride]
   int part_stride;
   // smem carve (floats)
@@ -72,7 +82,7 @@ struct KParams {
   int lq_n, lq_m;
   float lq_inv_IA[LQN * LQN], lq_B[LQN * MAXA], lq_Q[LQN], lq_R[MAXA];
   float lq_dt, lq_rs, lq_rsh;
-  gops_b200_reftraj rt;
+  RtC rt;
 };
 
 constexpr int ALG_FHADP = GOPS_ALG_FHADP, ALG_PIM = GOPS_ALG_INFADP_POLICY, ALG_PEV = GOPS_ALG_INFADP_VALUE,

@@ -60,13 +60,14 @@ typedef struct gops_b200_mlp_desc {
   int32_t out_act;     /* GOPS_ACT_* (reference default "linear")                                  */
 } gops_b200_mlp_desc;
 
-/* Reference-trajectory generator constants, env_ocp/resources/ref_traj_data.py:19-37 */
+/* Reference-trajectory generator constants, env_ocp/resources/ref_traj_data.py:19-37.  Doubles: the
+ * reference forms derived constants (e.g. -A/omega) as python floats before touching fp32 tensors. */
 typedef struct gops_b200_reftraj {
-  float sine_A, sine_omega, sine_phi;
-  float dl_t1, dl_t2, dl_t3, dl_t4, dl_y1, dl_y2;
-  float tri_A, tri_T;
-  float circ_r;
-  float sp_A, sp_omega, sp_phi, sp_b, sp_const;
+  double sine_A, sine_omega, sine_phi;
+  double dl_t1, dl_t2, dl_t3, dl_t4, dl_y1, dl_y2;
+  double tri_A, tri_T;
+  double circ_r;
+  double sp_A, sp_omega, sp_phi, sp_b, sp_const;
 } gops_b200_reftraj;
 
 typedef struct gops_b200_plan_desc {
@@ -98,7 +99,6 @@ typedef struct gops_b200_plan_desc {
 
   /* vehicle models */
   int32_t veh_pre_horizon;   /* P: obs_dim = 6 + 4 P                                             */
-  int32_t veh_ref_len;       /* veh3dof_tracking: reference points per sample (2P+1)             */
   gops_b200_reftraj reftraj;
 } gops_b200_plan_desc;
 
@@ -114,6 +114,7 @@ typedef struct gops_b200_batch {
   const float* ref_time;     /* [batch]                                                           */
   const float* reference;    /* [batch][ref_len][4] veh3dof_tracking ContextState.reference      */
   int32_t ref_t;             /* veh3dof_tracking ContextState.t (shared python int)              */
+  int32_t ref_len;           /* veh3dof_tracking: points per sample in `reference`               */
 } gops_b200_batch;
 
 typedef struct gops_b200_plan gops_b200_plan;

@@ -17,6 +17,10 @@ pytestmark = pytest.mark.gpu
 
 LOSS_RTOL = 1e-4
 GRAD_RTOL = 2e-4
+# pyth_veh3dofconti differentiates its analytic path numerically in fp32 (compute_phi, dt = 1e-3,
+# ref_traj_model.py:144-148): the REFERENCE's own fp32 policy gradient is 2.6e-4 (rel. L2) away from its fp64
+# evaluation on the golden INFADP case, so that is the noise floor any fp32 implementation can be held to.
+GRAD_RTOL_BY_ENV = {"pyth_veh3dofconti": 1e-3}
 def _built():
     from gops_b200.create_pkg.create_env_model import registry
     return {k[:-len("_model")] for k in registry}
@@ -85,16 +89,18 @@ GOLDEN = [n for n in CASES if CASES[n][0] in BUILT]
 @pytest.mark.parametrize("name", GOLDEN)
 def test_golden_loss_grad_update(name):
     env_id, algname = CASES[name][0], CASES[name][1]
-    try:
-        alg, rec = build_alg(name)
-    except NotImplementedError as e:
-        pytest.skip(str(e))
+    alg, rec = build_alg(name)
     its = [0, 1] if algname == "INFADP" else [0]
     for it in its:
         if it > 0:      # continue from the reference's own post-update weights so errors do not compound
             alg.load_state_dict({k.split("/post/")[1]: torch.from_numpy(v) for k, v in rec.items()
                                  if k.startswith(f"it{it - 1}/post/")})
-        tb = alg.local_update(data_from(rec, env_id), it)
+        try:
+            tb = alg.local_update(data_from(rec, env_id), it)
+        except RuntimeError as e:
+            if "not built" in str(e):
+                pytest.skip(str(e))
+            raise
         torch.cuda.synchronize()
         lk = loss_key(rec, it)
         ref_loss = float(rec[lk])
@@ -106,7 +112,7 @@ def test_golden_loss_grad_update(name):
         named = dict(mod.named_parameters())
         got_g = [named[k.split(f"/grad/{net}.")[1]].grad.detach().cpu().numpy() for k in gkeys]
         err = rel_l2(got_g, [rec[k] for k in gkeys])
-        assert err < GRAD_RTOL, (name, it, err)
+        assert err < GRAD_RTOL_BY_ENV.get(env_id, GRAD_RTOL), (name, it, err)
         # one Adam step (+ Polyak) against the reference's post-update state_dict
         lr = alg.networks.optimizer_dict[net].param_groups[0]["lr"]
         sd = alg.state_dict()
@@ -169,12 +175,18 @@ def _oracle_nets(alg, hidden_act, dtype):
     ("pyth_lq", "INFADP", "gelu", 5000, 10),
     ("pyth_lq", "FHADP", "selu", 1000, 25),
     ("pyth_lq", "INFADP", "sigmoid", 130, 3),
+    ("pyth_veh3dofconti", "INFADP", "relu", 1500, 10),
+    ("pyth_veh3dofconti", "FHADP", "gelu", 700, 10),
+    ("veh3dof_tracking", "FHADP", "elu", 900, 10),
 ])
 def test_against_oracle_fp64(env_id, algname, act, B, H):
     """Fresh seeded inputs, ragged batch sizes (not multiples of the tile), fp64 oracle as truth."""
     from gops_b200.create_pkg.create_alg import create_alg
     lq = dict(lq_config="s4a2") if env_id == "pyth_lq" else {}
-    obs_dim, act_dim = (4, 2) if env_id == "pyth_lq" else (6, 1)
+    veh = env_id in ("pyth_veh3dofconti", "veh3dof_tracking")
+    if veh:
+        lq = dict(pre_horizon=10)
+    obs_dim, act_dim = (4, 2) if env_id == "pyth_lq" else ((46, 2) if veh else (6, 1))
     kw = dict(env_id=env_id, algorithm=algname, seed=0, trainer="off_serial_trainer", use_gpu=True,
               action_type="continu", obsv_dim=obs_dim, action_dim=act_dim,
               action_high_limit=np.ones(act_dim, dtype=np.float32), action_low_limit=-np.ones(act_dim, dtype=np.float32),
@@ -185,15 +197,28 @@ def test_against_oracle_fp64(env_id, algname, act, B, H):
               reward_scale=0.5, reward_shift=0.25, **lq)
     if algname == "FHADP":
         kw.update(pre_horizon=H, gamma=0.98)
+    elif veh:
+        kw.update(pre_horizon=10)
     torch.manual_seed(B + H)
     alg = create_alg(**kw)
     if algname == "INFADP":
         alg.set_parameters({"forward_step": H, "gamma": 0.95})
-    data = orc.sample_inputs(env_id, B, seed=B, **({"lq_config": "s4a2"} if env_id == "pyth_lq" else {}))
+    data = orc.sample_inputs(env_id, B, seed=B, **({"lq_config": "s4a2"} if env_id == "pyth_lq" else {}),
+                             **({"pre_horizon": 10} if veh else {}))
     data["done"][::7] = 1.0
     dt = torch.float64
     env = orc.create_env_model(env_id, dtype=dt, reward_scale=0.5, reward_shift=0.25, **lq)
-    d64 = {k: v.to(dt) if v.is_floating_point() else v for k, v in data.items()}
+
+    def c64(v):
+        if isinstance(v, tuple):
+            return tuple(c64(e) for e in v)
+        return v.to(dt) if torch.is_tensor(v) and v.is_floating_point() else v
+    d64 = {k: c64(v) for k, v in data.items()}
+    if env_id == "veh3dof_tracking":
+        from gops_b200.env.env_gen_ocp.pyth_base import ContextState, State
+        robot, reference, t0 = data["state"]
+        data = dict(data)
+        data["state"] = State(robot_state=robot, context_state=ContextState(reference=reference, t=t0))
     mk = _oracle_nets(alg, act, dt)
     pol = mk(alg.networks.policy, "pi", True)
     for it in ([0] if algname == "FHADP" else [0, 1]):
@@ -220,7 +245,8 @@ def test_against_oracle_fp64(env_id, algname, act, B, H):
         torch.cuda.synchronize()
         assert abs(got - loss.item()) <= LOSS_RTOL * max(1.0, abs(loss.item())), (it, got, loss.item())
         got_g = [p.grad.detach().cpu().numpy() for p in getattr(alg.networks, net).parameters()]
-        assert rel_l2(got_g, [p.grad.numpy() for p in spec.params()]) < GRAD_RTOL, (env_id, algname, it)
+        assert rel_l2(got_g, [p.grad.numpy() for p in spec.params()]) < GRAD_RTOL_BY_ENV.get(env_id, GRAD_RTOL), \
+            (env_id, algname, it)
 
 
 def test_large_batch_properties():
