@@ -114,6 +114,21 @@ class RolloutPlan:
             pass
 
 
+def shard_inv_batch(local_batch: int, world: int) -> float:
+    """1 / B_global for equal shards: every rank scales its partial loss/gradient sums by this, so that the
+    SUM all-reduce yields the global batch mean -- the semantics of the reference's OffSyncTrainer, which
+    averages the replicas' gradients (gops/trainer/off_sync_trainer.py:183-208)."""
+    return 1.0 / float(local_batch * world)
+
+
+def allreduce_flat(gbuf: torch.Tensor):
+    """ONE collective per optimizer step over [flat gradient | loss | critic mean | #done]."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(gbuf, op=dist.ReduceOp.SUM)
+    return gbuf
+
+
 class FusedADPMixin:
     """Shared by FHADP / INFADP: device handling, plans cache, fused rollout-gradient call."""
 
@@ -157,7 +172,7 @@ class FusedADPMixin:
         done_d = done.to(dev, non_blocking=True) if not done.is_cuda else done
         dist, world = self._world()
         B_local = obs_d.shape[0]
-        inv_B = 1.0 / float(B_local * world)       # equal shards: mean over the global batch
+        inv_B = shard_inv_batch(B_local, world)
         target.bind_grads()
         gbuf = target.gbuf
         n = gbuf.numel() - GRAD_TAIL
@@ -171,6 +186,5 @@ class FusedADPMixin:
                 _lib.ptr(value.sync()) if value is not None else None,
                 _lib.ptr(vtarget.sync()) if vtarget is not None else None,
                 C.c_float(inv_B), _lib.ptr(gbuf), C.c_void_p(gbuf.data_ptr() + 4 * n), _lib.stream_ptr()))
-            if dist is not None:
-                dist.all_reduce(gbuf, op=dist.ReduceOp.SUM)     # ONE collective per optimizer step
+            allreduce_flat(gbuf)
         return gbuf[n:]

@@ -175,9 +175,9 @@ def _oracle_nets(alg, hidden_act, dtype):
     ("pyth_lq", "INFADP", "gelu", 5000, 10),
     ("pyth_lq", "FHADP", "selu", 1000, 25),
     ("pyth_lq", "INFADP", "sigmoid", 130, 3),
-    ("pyth_veh3dofconti", "INFADP", "relu", 1500, 10),
-    ("pyth_veh3dofconti", "FHADP", "gelu", 700, 10),
-    ("veh3dof_tracking", "FHADP", "elu", 900, 10),
+    ("pyth_veh3dofconti", "INFADP", "relu", 300, 10),
+    ("pyth_veh3dofconti", "FHADP", "gelu", 200, 10),
+    ("veh3dof_tracking", "FHADP", "elu", 250, 10),
 ])
 def test_against_oracle_fp64(env_id, algname, act, B, H):
     """Fresh seeded inputs, ragged batch sizes (not multiples of the tile), fp64 oracle as truth."""
