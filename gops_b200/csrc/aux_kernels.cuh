@@ -7,7 +7,8 @@ namespace gops {
 // ---------------------------------------------------------------------------------------------
 // torch-layout flat parameters -> packed k-major blob (W1^T, W2^T with row stride HP; 16-byte aligned parts)
 // ---------------------------------------------------------------------------------------------
-__global__ void pack_params_kernel(const float* __restrict__ flat, NetL L, float* __restrict__ blob) {
+__global__ void pack_params_kernel(const float* __restrict__ flat, NetL L, int HID, float* __restrict__ blob) {
+  const int HP = HID + 4;
   const int n = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
   const float* W1 = flat + L.g_w1;
   const float* W2 = flat + L.g_w2;

@@ -35,7 +35,11 @@ int round4(int x) { return (x + 3) & ~3; }
 
 bool make_net(const gops_b200_mlp_desc& d, NetL& L, std::string& why) {
   memset(&L, 0, sizeof(L));
-  if (d.hidden != HID) { why = "hidden width " + std::to_string(d.hidden) + " not built (supported: 64)"; return false; }
+  if (d.hidden != 64 && d.hidden != 256) {
+    why = "hidden width " + std::to_string(d.hidden) + " not built (supported: 64, 256)";
+    return false;
+  }
+  const int HID = d.hidden, HP = HID + 4;
   if (d.out_dim < 1 || d.out_dim > MAXA) { why = "out_dim out of range"; return false; }
   if (d.out_act != GOPS_ACT_LINEAR) { why = "output_activation other than 'linear' is not supported"; return false; }
   if (d.hidden_act < 0 || d.hidden_act > GOPS_ACT_LINEAR) { why = "bad hidden activation"; return false; }
@@ -70,6 +74,8 @@ struct Config {
 };
 const Config kConfigs[] = {{128, 512}, {64, 256}, {32, 128}};   // sub-tile S, threads (= samples per chunk)
 
+const Config kWideConfig = {32, 256};   // hidden 256: activations only in smem, 8 sub-tiles per chunk
+
 typedef void (*RolloutFn)(const KParams);
 typedef void (*StepFn)(const KParams, const float*, int, float*, float*, float*);
 
@@ -77,22 +83,22 @@ typedef void (*StepFn)(const KParams, const float*, int, float*, float*, float*)
 
 // one translation unit per env model (kernels_<model>.cu), compiled in parallel
 namespace gops {
-RolloutFn rollout_fn_idp(int cfg, int alg);
-RolloutFn rollout_fn_lq(int cfg, int alg);
-RolloutFn rollout_fn_vehconti(int cfg, int alg);
-RolloutFn rollout_fn_vehtrack(int cfg, int alg);
+RolloutFn rollout_fn_idp(int hid, int cfg, int alg);
+RolloutFn rollout_fn_lq(int hid, int cfg, int alg);
+RolloutFn rollout_fn_vehconti(int hid, int cfg, int alg);
+RolloutFn rollout_fn_vehtrack(int hid, int cfg, int alg);
 StepFn step_fn_idp();
 StepFn step_fn_lq();
 }  // namespace gops
 
 namespace {
 
-RolloutFn rollout_fn(int model, int cfg, int alg) {
+RolloutFn rollout_fn(int model, int hid, int cfg, int alg) {
   switch (model) {
-    case GOPS_MODEL_IDPENDULUM: return rollout_fn_idp(cfg, alg);
-    case GOPS_MODEL_LQ: return rollout_fn_lq(cfg, alg);
-    case GOPS_MODEL_VEH3DOFCONTI: return rollout_fn_vehconti(cfg, alg);
-    case GOPS_MODEL_VEH3DOF_TRACKING: return rollout_fn_vehtrack(cfg, alg);
+    case GOPS_MODEL_IDPENDULUM: return rollout_fn_idp(hid, cfg, alg);
+    case GOPS_MODEL_LQ: return rollout_fn_lq(hid, cfg, alg);
+    case GOPS_MODEL_VEH3DOFCONTI: return rollout_fn_vehconti(hid, cfg, alg);
+    case GOPS_MODEL_VEH3DOF_TRACKING: return rollout_fn_vehtrack(hid, cfg, alg);
     default: return nullptr;
   }
 }
@@ -118,6 +124,8 @@ struct gops_b200_plan {
   size_t partial_floats = 0;
   float* ext_ref = nullptr;
   size_t ext_ref_floats = 0;
+  float* xbuf = nullptr;
+  size_t xbuf_floats = 0;
   bool attr_set[4][4] = {};   // [alg][cfg]
   bool timing = false;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -128,15 +136,20 @@ struct gops_b200_plan {
 namespace {
 
 size_t rollout_smem_bytes(const KParams& kp, int S, int NT) {
-  const int SP = S + 4, XS = NT + 4;
+  const int SP = S + 4, XS = NT + 4, HID = kp.hid;
+  if (HID > 64) return sizeof(float) * (size_t)(4 + 4 * HID * SP + 4 * XS);
   return sizeof(float) * (size_t)(4 + kp.w_floats + kp.dw_floats + kp.inp_max * XS + 4 * HID * SP + 4 * XS);
 }
 size_t infer_smem_bytes(const KParams& kp, int S, int NT) {
-  const int SP = S + 4, XS = NT + 4;
+  const int SP = S + 4, XS = NT + 4, HID = kp.hid;
+  if (HID > 64) return sizeof(float) * (size_t)(4 + 2 * HID * SP + 4 * XS);
   return sizeof(float) * (size_t)(4 + kp.w_floats + kp.inp_max * XS + 2 * HID * SP + 4 * XS);
 }
 
+Config config_of(const gops_b200_plan* pl, int cfg) { return pl->kp.hid > 64 ? kWideConfig : kConfigs[cfg]; }
+
 int pick_config(const gops_b200_plan* pl, long long B, bool infer) {
+  if (pl->kp.hid > 64) return 0;
   // the largest chunk (threads per CTA) that still gives every SM at least one CTA
   const char* force = getenv("GOPS_B200_CFG");
   auto fits = [&](int c) {
@@ -165,11 +178,21 @@ int ensure_scratch(gops_b200_plan* pl, int grid, int NT, int H) {
   if (pl->desc.model == GOPS_MODEL_VEH3DOFCONTI) {
     const size_t need = (size_t)grid * (pl->kp.veh_P + 1 + H) * 4 * NT;
     if (need > pl->ext_ref_floats) {
-      if (pl->ext_ref) cudaFree(pl->ext_ref);
+      if (pl->ext_ref) cudaFree(pl->ext_ref); cudaFree(pl->xbuf);
       pl->ext_ref = nullptr;
       CUDA_OK(cudaMalloc(&pl->ext_ref, need * sizeof(float)));
       CUDA_OK(cudaMemset(pl->ext_ref, 0, need * sizeof(float)));
       pl->ext_ref_floats = need;
+    }
+  }
+  if (pl->kp.hid > 64) {
+    const size_t need = (size_t)grid * pl->kp.inp_max * (NT + 4);
+    if (need > pl->xbuf_floats) {
+      if (pl->xbuf) cudaFree(pl->xbuf);
+      pl->xbuf = nullptr;
+      CUDA_OK(cudaMalloc(&pl->xbuf, need * sizeof(float)));
+      CUDA_OK(cudaMemset(pl->xbuf, 0, need * sizeof(float)));
+      pl->xbuf_floats = need;
     }
   }
   const size_t need_part = (size_t)grid * pl->kp.part_stride;
@@ -182,8 +205,8 @@ int ensure_scratch(gops_b200_plan* pl, int grid, int NT, int H) {
   return 0;
 }
 
-int launch_pack(const float* flat, const NetL& L, float* blob, cudaStream_t st) {
-  pack_params_kernel<<<8, 256, 0, st>>>(flat, L, blob);
+int launch_pack(const float* flat, const NetL& L, int hid, float* blob, cudaStream_t st) {
+  pack_params_kernel<<<hid > 64 ? 64 : 8, 256, 0, st>>>(flat, L, hid, blob);
   CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -203,8 +226,8 @@ int launch_rollout(gops_b200_plan* pl, const gops_b200_batch* b, int alg, cudaSt
   KParams& kp = pl->kp;
   const int cfg = pick_config(pl, b->batch, false);
   if (cfg < 0) return fail("no kernel configuration fits in shared memory");
-  const int S = kConfigs[cfg].S, NT = kConfigs[cfg].NT;
-  RolloutFn fn = rollout_fn(pl->desc.model, cfg, alg);
+  const int S = config_of(pl, cfg).S, NT = config_of(pl, cfg).NT;
+  RolloutFn fn = rollout_fn(pl->desc.model, kp.hid, cfg, alg);
   if (!fn) return fail("env model kind not built into this library");
   kp.alg = alg;
   kp.batch = b->batch;
@@ -230,6 +253,7 @@ int launch_rollout(gops_b200_plan* pl, const gops_b200_batch* b, int alg, cudaSt
   if (ensure_scratch(pl, grid, NT, kp.horizon)) return 1;
   kp.tape = pl->tape;
   kp.ext_ref = pl->ext_ref;
+  kp.xbuf = pl->xbuf;
   kp.partial = pl->partial;
   if (pl->timing) CUDA_OK(cudaEventRecord(pl->ev0, st));
   fn<<<grid, NT, smem, st>>>(kp);
@@ -257,7 +281,7 @@ int gops_b200_plan_create(const gops_b200_plan_desc* d, gops_b200_plan** out) {
   *out = nullptr;
   if (d->alg < GOPS_ALG_FHADP || d->alg > GOPS_ALG_INFADP_VALUE) return fail("unknown algorithm kind");
   if (d->horizon < 1 || d->horizon > 4096) return fail("horizon out of range");
-  if (!rollout_fn(d->model, 0, d->alg)) return fail("env model kind not built into this library");
+  if (!rollout_fn(d->model, d->policy.hidden == 256 ? 256 : 64, 0, d->alg)) return fail("env model kind not built into this library");
   gops_b200_plan* pl = new (std::nothrow) gops_b200_plan();
   if (!pl) return fail("out of host memory");
   pl->desc = *d;
@@ -293,6 +317,8 @@ int gops_b200_plan_create(const gops_b200_plan_desc* d, gops_b200_plan** out) {
   if (d->model == GOPS_MODEL_IDPENDULUM && act_dim != 1) { delete pl; return fail("idpendulum has 1 action"); }
 
   kp.horizon = d->horizon;
+  kp.hid = d->policy.hidden;
+  if (infadp && d->value.hidden != d->policy.hidden) { delete pl; return fail("policy and value hidden widths differ"); }
   kp.gamma = d->gamma;
   kp.w_floats = kp.pol.blob > kp.val.blob ? kp.pol.blob : kp.val.blob;
   kp.inp_max = kp.pol.inp > kp.val.inp ? kp.pol.inp : kp.val.inp;
@@ -407,7 +433,7 @@ int gops_b200_plan_destroy(gops_b200_plan* pl) {
   if (!pl) return 0;
   if (pl->ev0) { cudaEventDestroy(pl->ev0); cudaEventDestroy(pl->ev1); }
   cudaFree(pl->gpow); cudaFree(pl->blob_pol); cudaFree(pl->blob_val); cudaFree(pl->blob_vtg);
-  cudaFree(pl->tape); cudaFree(pl->partial); cudaFree(pl->ext_ref);
+  cudaFree(pl->tape); cudaFree(pl->partial); cudaFree(pl->ext_ref); cudaFree(pl->xbuf);
   delete pl;
   return 0;
 }
@@ -423,14 +449,14 @@ int gops_b200_rollout_grad(gops_b200_plan* pl, const gops_b200_batch* b, const f
   if (!pl || !policy_params || !grad_out || !scalars_out) return fail("null argument");
   cudaStream_t st = (cudaStream_t)stream;
   const int alg = pl->desc.alg;
-  if (launch_pack(policy_params, pl->kp.pol, pl->blob_pol, st)) return 1;
+  if (launch_pack(policy_params, pl->kp.pol, pl->kp.hid, pl->blob_pol, st)) return 1;
   if (alg != GOPS_ALG_FHADP) {
     if (!vtarget_params) return fail("vtarget_params required for INFADP");
-    if (launch_pack(vtarget_params, pl->kp.val, pl->blob_vtg, st)) return 1;
+    if (launch_pack(vtarget_params, pl->kp.val, pl->kp.hid, pl->blob_vtg, st)) return 1;
   }
   if (alg == GOPS_ALG_INFADP_VALUE) {
     if (!value_params) return fail("value_params required for INFADP value update");
-    if (launch_pack(value_params, pl->kp.val, pl->blob_val, st)) return 1;
+    if (launch_pack(value_params, pl->kp.val, pl->kp.hid, pl->blob_val, st)) return 1;
   }
   pl->kp.inv_B = inv_batch_global;
   pl->kp.tr_obs = pl->kp.tr_act = pl->kp.tr_rew = pl->kp.tr_done = nullptr;
@@ -441,7 +467,7 @@ int gops_b200_rollout_trace(gops_b200_plan* pl, const gops_b200_batch* b, const 
                             float* act_out, float* rew_out, float* done_out, void* stream) {
   if (!pl || !policy_params) return fail("null argument");
   cudaStream_t st = (cudaStream_t)stream;
-  if (launch_pack(policy_params, pl->kp.pol, pl->blob_pol, st)) return 1;
+  if (launch_pack(policy_params, pl->kp.pol, pl->kp.hid, pl->blob_pol, st)) return 1;
   pl->kp.inv_B = 1.f;
   pl->kp.tr_obs = obs_out; pl->kp.tr_act = act_out; pl->kp.tr_rew = rew_out; pl->kp.tr_done = done_out;
   return launch_rollout(pl, b, ALG_TRACE, st, nullptr, nullptr);
@@ -454,24 +480,35 @@ static int infer_common(gops_b200_plan* pl, const float* params, int use_val, co
   cudaStream_t st = (cudaStream_t)stream;
   const NetL& L = use_val ? pl->kp.val : pl->kp.pol;
   float* blob = use_val ? pl->blob_val : pl->blob_pol;
-  if (launch_pack(params, L, blob, st)) return 1;
+  if (launch_pack(params, L, pl->kp.hid, blob, st)) return 1;
   const int cfg = pick_config(pl, batch, true);
   if (cfg < 0) return fail("no kernel configuration fits in shared memory");
-  const int S = kConfigs[cfg].S, NTc = kConfigs[cfg].NT;
+  const int S = config_of(pl, cfg).S, NTc = config_of(pl, cfg).NT;
   const long long tiles = (batch + NTc - 1) / NTc;
   const int grid = (int)(tiles < pl->sm_count ? tiles : pl->sm_count);
   const size_t smem = infer_smem_bytes(pl->kp, S, NTc);
   (void)S;
-#define LAUNCH_INFER(SS, NN)                                                                                  \
+#define LAUNCH_INFER(HH, SS, NN)                                                                                  \
   do {                                                                                                        \
-    CUDA_OK(cudaFuncSetAttribute(mlp_infer_kernel<SS, NN>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
+    CUDA_OK(cudaFuncSetAttribute(mlp_infer_kernel<HH, SS, NN>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
                                  pl->max_smem));                                                              \
-    mlp_infer_kernel<SS, NN><<<grid, NN, smem, st>>>(pl->kp, blob, use_val, obs, batch, virtual_t,            \
-                                                     squash ? 1 : 0, out);                                   \
+    mlp_infer_kernel<HH, SS, NN><<<grid, NN, smem, st>>>(pl->kp, blob, use_val, obs, batch, virtual_t,        \
+                                                         squash ? 1 : 0, out);                               \
   } while (0)
-  if (cfg == 0) LAUNCH_INFER(128, 512);
-  else if (cfg == 1) LAUNCH_INFER(64, 256);
-  else LAUNCH_INFER(32, 128);
+  if (pl->kp.hid > 64) {
+    if ((size_t)grid * pl->kp.inp_max * (NTc + 4) > pl->xbuf_floats) {
+      if (pl->xbuf) cudaFree(pl->xbuf);
+      pl->xbuf = nullptr; pl->xbuf_floats = 0;
+      const size_t need = (size_t)pl->sm_count * pl->kp.inp_max * (NTc + 4);
+      CUDA_OK(cudaMalloc(&pl->xbuf, need * sizeof(float)));
+      CUDA_OK(cudaMemset(pl->xbuf, 0, need * sizeof(float)));
+      pl->xbuf_floats = need;
+    }
+    pl->kp.xbuf = pl->xbuf;
+    LAUNCH_INFER(256, 32, 256);
+  } else if (cfg == 0) LAUNCH_INFER(64, 128, 512);
+  else if (cfg == 1) LAUNCH_INFER(64, 64, 256);
+  else LAUNCH_INFER(64, 32, 128);
 #undef LAUNCH_INFER
   CUDA_OK(cudaGetLastError());
   return 0;
@@ -500,6 +537,7 @@ int gops_b200_mlp_forward(const gops_b200_mlp_desc* net, const float* params, co
   std::string why;
   if (!make_net(*net, kp.pol, why)) return fail(why);
   kp.val = kp.pol;
+  kp.hid = net->hidden;
   kp.w_floats = kp.pol.blob;
   kp.inp_max = kp.pol.inp;
   for (int j = 0; j < net->out_dim; ++j) {
@@ -519,8 +557,13 @@ int gops_b200_mlp_forward(const gops_b200_mlp_desc* net, const float* params, co
     CUDA_OK(cudaMalloc(&scratch->blob_pol, (size_t)scratch_floats * sizeof(float)));
   }
   tmp.blob_pol = scratch->blob_pol;
+  tmp.xbuf = scratch->xbuf;
+  tmp.xbuf_floats = scratch->xbuf_floats;
   const int rc = infer_common(&tmp, params, 0, obs, batch, virtual_t, out, stream, act_low != nullptr);
+  scratch->xbuf = tmp.xbuf;              // infer_common may have (re)allocated the wide-net scratch
+  scratch->xbuf_floats = tmp.xbuf_floats;
   tmp.blob_pol = nullptr;
+  tmp.xbuf = nullptr;
   return rc;
 }
 

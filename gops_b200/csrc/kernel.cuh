@@ -6,17 +6,30 @@ namespace gops {
 
 // One CTA = NT threads = NT samples per chunk; MLP GEMMs run over SUB = NT/S sub-tiles of S samples that
 // reuse one set of activation tiles; the per-sample dynamics (forward and adjoint) run on every thread.
-template <class M, int S, int NT, int ALG>
+// HD = 64: weights (TMA-staged), weight-gradient accumulators and X live in shared memory.
+// HD = 256 (WG): they do not fit (519 KB of weights) -> weights are read from the packed blob in global memory
+// (L2 resident, generic loads), gradients accumulate directly in this CTA's global partial, X is a per-CTA global
+// scratch; only the activation tiles stay in shared memory.
+template <class M, int HD, int S, int NT, int ALG>
 __global__ void __launch_bounds__(NT, 1) rollout_kernel(const __grid_constant__ KParams p) {
-  constexpr int SP = S + 4, XS = NT + 4, NS = M::NS;
+  constexpr int SP = S + 4, XS = NT + 4, NS = M::NS, HID = HD;
   constexpr int alg = ALG;
+  constexpr bool WG = HD > 64;
   extern __shared__ __align__(16) float smem[];
   uint64_t* mbar = reinterpret_cast<uint64_t*>(smem);
+  float* part = p.partial + (size_t)blockIdx.x * p.part_stride;
   Tiles t;
-  t.W = smem + 4;
-  t.dW = t.W + p.w_floats;
-  t.X = t.dW + p.dw_floats;
-  t.H1 = t.X + p.inp_max * XS;
+  if (WG) {
+    t.W = const_cast<float*>(p.blob_pol);
+    t.dW = part;
+    t.X = p.xbuf + (size_t)blockIdx.x * p.inp_max * XS;
+    t.H1 = smem + 4;
+  } else {
+    t.W = smem + 4;
+    t.dW = t.W + p.w_floats;
+    t.X = t.dW + p.dw_floats;
+    t.H1 = t.X + p.inp_max * XS;
+  }
   t.D1 = t.H1 + HID * SP;
   t.H2 = t.D1 + HID * SP;
   t.D2 = t.H2 + HID * SP;
@@ -38,6 +51,10 @@ __global__ void __launch_bounds__(NT, 1) rollout_kernel(const __grid_constant__ 
   // TMA bulk copy of a packed weight blob into shared memory (all threads wait on the mbarrier)
   auto stage = [&](const float* gsrc, int floats) {
     __syncthreads();  // every reader of the previous blob is done
+    if (WG) {         // wide nets: just switch the global blob the GEMMs read from
+      t.W = const_cast<float*>(gsrc);
+      return;
+    }
     if (tid == 0) {
       fence_proxy_async();
       const uint32_t bytes = (uint32_t)floats * 4u;
@@ -123,7 +140,7 @@ __global__ void __launch_bounds__(NT, 1) rollout_kernel(const __grid_constant__ 
       __syncthreads();
       for (int sub = 0; sub < nsub; ++sub) {
         const Tiles ts = sub_tiles(sub);
-        mlp_forward<S, NT, false, true>(P, ts, ts.Z);
+        mlp_forward<HD, S, NT, false, true>(P, ts, ts.Z);
       }
       __syncthreads();
       {
@@ -221,11 +238,11 @@ __global__ void __launch_bounds__(NT, 1) rollout_kernel(const __grid_constant__ 
       for (int sub = 0; sub < nsub; ++sub) {
         const Tiles ts = sub_tiles(sub);
         if (alg == ALG_PIM) {
-          mlp_forward<S, NT, true, true>(V, ts, ts.Z + XS);
+          mlp_forward<HD, S, NT, true, true>(V, ts, ts.Z + XS);
           __syncthreads();
-          mlp_backward<S, NT, false>(V, ts, true);
+          mlp_backward<HD, S, NT, false>(V, ts, true);
         } else {
-          mlp_forward<S, NT, false, true>(V, ts, ts.Z + XS);
+          mlp_forward<HD, S, NT, false, true>(V, ts, ts.Z + XS);
         }
       }
       __syncthreads();
@@ -253,7 +270,7 @@ __global__ void __launch_bounds__(NT, 1) rollout_kernel(const __grid_constant__ 
       __syncthreads();
       for (int sub = 0; sub < nsub; ++sub) {
         const Tiles ts = sub_tiles(sub);
-        mlp_forward<S, NT, true, true>(V, ts, ts.Z + XS);
+        mlp_forward<HD, S, NT, true, true>(V, ts, ts.Z + XS);
         __syncthreads();
         if (tid / S == sub) {
           float zb = 0.f;
@@ -267,7 +284,7 @@ __global__ void __launch_bounds__(NT, 1) rollout_kernel(const __grid_constant__ 
           t.Z[tid] = zb;
         }
         __syncthreads();
-        mlp_backward<S, NT, true>(V, ts, false);
+        mlp_backward<HD, S, NT, true>(V, ts, false);
       }
       stage(p.blob_pol, P.blob);
       continue;
@@ -369,8 +386,8 @@ __global__ void __launch_bounds__(NT, 1) rollout_kernel(const __grid_constant__ 
       // MLP: re-compute the hidden activations of step k per sub-tile, then back-propagate Zbar
       for (int sub = 0; sub < nsub; ++sub) {
         const Tiles ts = sub_tiles(sub);
-        mlp_forward<S, NT, true, false>(P, ts, nullptr);
-        mlp_backward<S, NT, true>(P, ts, k > 0);
+        mlp_forward<HD, S, NT, true, false>(P, ts, nullptr);
+        mlp_backward<HD, S, NT, true>(P, ts, k > 0);
       }
       if (active && k > 0) {
         if constexpr (M::KIND == 0) {
@@ -386,9 +403,8 @@ __global__ void __launch_bounds__(NT, 1) rollout_kernel(const __grid_constant__ 
 
   // ============================ per-CTA partials ============================
   __syncthreads();
-  float* part = p.partial + (size_t)blockIdx.x * p.part_stride;
   const int nparam = (alg == ALG_PEV) ? V.nparam : P.nparam;
-  if (alg != ALG_TRACE)
+  if (alg != ALG_TRACE && !WG)
     for (int i = tid; i < nparam; i += NT) part[i] = t.dW[i];
   // block reduction of the three scalars (fixed order)
   float* red = t.H1;  // free at this point, HID*(S+4) >= 3*NT floats
@@ -404,19 +420,26 @@ __global__ void __launch_bounds__(NT, 1) rollout_kernel(const __grid_constant__ 
 }
 
 // Batched inference of one MLP (policy with tanh squashing when `squash`, else raw value output)
-template <int S, int NT>
+template <int HD, int S, int NT>
 __global__ void __launch_bounds__(NT, 1) mlp_infer_kernel(const __grid_constant__ KParams p, const float* blob, int use_val,
                                                           const float* __restrict__ obs, long long B, float virtual_t,
                                                           int squash, float* __restrict__ out) {
-  constexpr int SP = S + 4, XS = NT + 4;
+  constexpr int SP = S + 4, XS = NT + 4, HID = HD;
+  constexpr bool WG = HD > 64;
   extern __shared__ __align__(16) float smem[];
   uint64_t* mbar = reinterpret_cast<uint64_t*>(smem);
   const NetL& L = use_val ? p.val : p.pol;
   Tiles t;
-  t.W = smem + 4;
-  t.dW = t.W + p.w_floats;
-  t.X = t.dW;
-  t.H1 = t.X + p.inp_max * XS;
+  if (WG) {
+    t.W = const_cast<float*>(blob);
+    t.X = p.xbuf + (size_t)blockIdx.x * p.inp_max * XS;
+    t.H1 = smem + 4;
+  } else {
+    t.W = smem + 4;
+    t.X = t.W + p.w_floats;
+    t.H1 = t.X + p.inp_max * XS;
+  }
+  t.dW = nullptr;
   t.D1 = t.H1;
   t.H2 = t.H1 + HID * SP;
   t.D2 = t.H2;
@@ -427,16 +450,18 @@ __global__ void __launch_bounds__(NT, 1) mlp_infer_kernel(const __grid_constant_
     fence_mbar_init();
   }
   __syncthreads();
-  if (tid == 0) {
-    fence_proxy_async();
-    const uint32_t bytes = (uint32_t)L.blob * 4u;
-    mbar_expect_tx(mbar, bytes);
-    for (uint32_t off = 0; off < bytes; off += 32768u) {
-      const uint32_t n = bytes - off < 32768u ? bytes - off : 32768u;
-      tma_bulk_g2s(reinterpret_cast<char*>(t.W) + off, reinterpret_cast<const char*>(blob) + off, n, mbar);
+  if (!WG) {
+    if (tid == 0) {
+      fence_proxy_async();
+      const uint32_t bytes = (uint32_t)L.blob * 4u;
+      mbar_expect_tx(mbar, bytes);
+      for (uint32_t off = 0; off < bytes; off += 32768u) {
+        const uint32_t n = bytes - off < 32768u ? bytes - off : 32768u;
+        tma_bulk_g2s(reinterpret_cast<char*>(t.W) + off, reinterpret_cast<const char*>(blob) + off, n, mbar);
+      }
     }
+    mbar_wait(mbar, 0);
   }
-  mbar_wait(mbar, 0);
   const long long n_chunks = (B + NT - 1) / NT;
   for (long long c = blockIdx.x; c < n_chunks; c += gridDim.x) {
     const long long base = c * NT;
@@ -453,7 +478,7 @@ __global__ void __launch_bounds__(NT, 1) mlp_infer_kernel(const __grid_constant_
       Tiles ts = t;
       ts.X = t.X + sub * S;
       ts.Z = t.Z + sub * S;
-      mlp_forward<S, NT, false, true>(L, ts, ts.Z);
+      mlp_forward<HD, S, NT, false, true>(L, ts, ts.Z);
     }
     __syncthreads();
     if (tid < nv) {

@@ -16,8 +16,9 @@
 
 namespace gops {
 
-constexpr int HID = 64;
-constexpr int HP = HID + 4;   // row stride of the k-major weight tiles (bank skew for transposed reads)
+// Hidden width HD is a template parameter of every primitive (64: everything in shared memory; 256: weights,
+// weight-gradient accumulators and the observation tile live in global memory / L2, activations in smem).
+// k-major weight tiles have row stride HD + 4 (bank skew for the transposed reads of the backward GEMM).
 
 // Reference-trajectory constants as fp32 values derived on the host in double precision.
 struct RtC {
@@ -67,6 +68,8 @@ struct KParams {
   int tape_ch;
   float* ext_ref;          // veh3dofconti: [grid][P+1+H][4][NT] raw reference points (window slides by one per step)
   float* partial;          // [grid][part_stride]
+  float* xbuf;             // wide nets: [grid][inp_max][NT+4] observation tile in global memory
+  int hid;                 // hidden width of both networks (64 or 256)
   int part_stride;
   // smem carve (floats)
   int w_floats, dw_floats, inp_max;
@@ -90,8 +93,9 @@ constexpr int ALG_FHADP = GOPS_ALG_FHADP, ALG_PIM = GOPS_ALG_INFADP_POLICY, ALG_
 
 // Warp tiling of a [HID x S] output tile: every warp is 4 (feature) x 8 (sample) threads, a thread
 // owns TM features x 4 samples.  One k-step then needs ONE 64 B and ONE 128 B shared wavefront per warp.
-template <int S, int NT>
+template <int HD, int S, int NT>
 struct Map {
+  static constexpr int HID = HD, HP = HD + 4;
   static constexpr int SP = S + 4, NW = NT / 32, WN = S / 32, WM = NW / WN, TM = HID / (4 * WM);
   static_assert(S % 32 == 0 && NW % WN == 0 && WM >= 1 && TM >= 1 && TM * 4 * WM == HID && TM % 4 == 0, "bad tiling");
   int n0, mt;   // first sample column, feature-thread index (0 .. 4*WM-1)
@@ -106,10 +110,11 @@ struct Map {
 // P[m][n] = bias[m] + sum_k A[k][m] * B[k][n]   (pre-activations of a hidden layer)
 // A: k-major weights [K][HP], B: [K][SP].  Thread owns CONTIGUOUS features m0 .. m0+TM-1.
 // ---------------------------------------------------------------------------------------------
-template <int S, int NT>
+template <int HD, int S, int NT>
 __device__ __noinline__ void gemm_fwd(const float* __restrict__ A, const float* __restrict__ Bm, int ldb, int K,
                                       const float* __restrict__ bias, float* __restrict__ P) {
-  using M = Map<S, NT>;
+  using M = Map<HD, S, NT>;
+  constexpr int HID = HD, HP = HD + 4;
   constexpr int SP = M::SP, TM = M::TM;
   const M mp;
   const int m0 = mp.mt * TM;
@@ -145,9 +150,10 @@ __device__ __noinline__ void gemm_fwd(const float* __restrict__ A, const float* 
 
 // In-place activation of the tile a thread just wrote with gemm_fwd (same ownership -> no barrier):
 // H <- act(P); if D != nullptr also D <- act'(P).  Rolled loop: the activation code exists once.
-template <int S, int NT>
+template <int HD, int S, int NT>
 __device__ __noinline__ void act_pass(float* __restrict__ H, float* __restrict__ D, int act) {
-  using M = Map<S, NT>;
+  using M = Map<HD, S, NT>;
+  constexpr int HID = HD, HP = HD + 4;
   constexpr int SP = M::SP, TM = M::TM;
   const M mp;
   const int m0 = mp.mt * TM;
@@ -172,10 +178,11 @@ __device__ __noinline__ void act_pass(float* __restrict__ H, float* __restrict__
 // A: the SAME k-major tile [HID][HP] read transposed; thread owns INTERLEAVED rows i = mt + 4*WM*j so
 // the four feature-threads of a warp read consecutive rows (HP = 68 -> banks skewed by 4, conflict-free).
 // ---------------------------------------------------------------------------------------------
-template <int S, int NT>
+template <int HD, int S, int NT>
 __device__ __noinline__ void gemm_bwd(const float* __restrict__ A, const float* __restrict__ Dl,
                                       float* __restrict__ D) {
-  using M = Map<S, NT>;
+  using M = Map<HD, S, NT>;
+  constexpr int HID = HD, HP = HD + 4;
   constexpr int SP = M::SP, TM = M::TM, RS = 4 * M::WM;
   const M mp;
   float acc[TM][4];
@@ -211,10 +218,10 @@ __device__ __noinline__ void gemm_bwd(const float* __restrict__ A, const float* 
 }
 
 // Z[a][s] = b3[a] + sum_i W3[a][i] * H[i][s]       (output layer, out <= MAXA)
-template <int S, int NT>
+template <int HD, int S, int NT>
 __device__ __noinline__ void out_layer(const float* __restrict__ W3, const float* __restrict__ b3,
                                        const float* __restrict__ H, int out, float* __restrict__ Z, int ldz) {
-  constexpr int SP = S + 4;
+  constexpr int SP = S + 4, HID = HD;
   for (int idx = threadIdx.x; idx < out * S; idx += NT) {
     const int a = idx / S, s = idx - a * S;
     float a0 = b3[a], a1 = 0.f;
@@ -228,10 +235,11 @@ __device__ __noinline__ void out_layer(const float* __restrict__ W3, const float
 }
 
 // D[i][s] <- D[i][s] * sum_a W3[a][i] * Zb[a][s]   (delta of the last hidden layer, in place)
-template <int S, int NT>
+template <int HD, int S, int NT>
 __device__ __noinline__ void delta_from_out(const float* __restrict__ W3, const float* __restrict__ Zb, int ldz, int out,
                                             float* __restrict__ D) {
-  using M = Map<S, NT>;
+  using M = Map<HD, S, NT>;
+  constexpr int HID = HD, HP = HD + 4;
   constexpr int SP = M::SP, TM = M::TM;
   const M mp;
   const int m0 = mp.mt * TM;
@@ -259,7 +267,7 @@ __device__ __noinline__ void delta_from_out(const float* __restrict__ W3, const 
 // dst[o][i] += sum_s Dl[o][s] * Xl[i][s]   for o < RO, i < RI   (weight gradient; dst row stride ld)
 // Tiles own interleaved rows (o = to + tiles_o*j) so that lanes of a warp touch consecutive rows
 // of the (S+4)-strided tiles -> conflict-free float4 shared loads.
-template <int S, int NT, int TO, int TI>
+template <int HD, int S, int NT, int TO, int TI>
 __device__ __noinline__ void dw_accum(const float* __restrict__ Dl, int ldd, int RO, const float* __restrict__ Xl,
                                       int ldx, int RI, float* __restrict__ dst, int ld) {
   const int tiles_o = (RO + TO - 1) / TO, tiles_i = (RI + TI - 1) / TI;
@@ -306,7 +314,7 @@ __device__ __noinline__ void dw_accum(const float* __restrict__ Dl, int ldd, int
 }
 
 // dst[o] += sum_s Dl[o][s]        (bias gradient)
-template <int S, int NT>
+template <int HD, int S, int NT>
 __device__ __noinline__ void rowsum_accum(const float* __restrict__ Dl, int ldd, int RO, float* __restrict__ dst) {
   for (int o = threadIdx.x; o < RO; o += NT) {
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
@@ -320,10 +328,10 @@ __device__ __noinline__ void rowsum_accum(const float* __restrict__ Dl, int ldd,
 }
 
 // Xb[i][s] = sum_o W1k[i][o] * Dl[o][s]  for i < M (M <= 8*MG)   (input gradient; W1k: [in][HP] k-major)
-template <int S, int NT>
+template <int HD, int S, int NT>
 __device__ __noinline__ void gemm_dx(const float* __restrict__ W1k, const float* __restrict__ Dl, int M,
                                      float* __restrict__ Xb, int ldx) {
-  constexpr int SP = S + 4, NTN = S / 4, MG = NT / NTN, JM = 8;
+  constexpr int SP = S + 4, NTN = S / 4, MG = NT / NTN, JM = 8, HID = HD, HP = HD + 4;
   const int tid = threadIdx.x, nt = tid % NTN, mg = tid / NTN;
   const int J = (M - mg + MG - 1) / MG;  // rows mg, mg+MG, ... < M
   if (J <= 0) return;
@@ -364,43 +372,43 @@ struct Tiles {
 
 // X -> H1 -> H2 (-> Zout).  FULL: also store activation derivatives (needed by mlp_backward).
 // No trailing barrier: the caller synchronises once after its sub-tile loop / before consuming Zout.
-template <int S, int NT, bool FULL, bool OUT>
+template <int HD, int S, int NT, bool FULL, bool OUT>
 __device__ __forceinline__ void mlp_forward(const NetL& L, const Tiles& t, float* Zout) {
-  constexpr int XS = NT + 4;
-  gemm_fwd<S, NT>(t.W + L.o_w1, t.X, XS, L.in, t.W + L.o_b1, t.H1);
-  act_pass<S, NT>(t.H1, FULL ? t.D1 : nullptr, L.hact);
+  constexpr int XS = NT + 4, HID = HD;
+  gemm_fwd<HD, S, NT>(t.W + L.o_w1, t.X, XS, L.in, t.W + L.o_b1, t.H1);
+  act_pass<HD, S, NT>(t.H1, FULL ? t.D1 : nullptr, L.hact);
   __syncthreads();
-  gemm_fwd<S, NT>(t.W + L.o_w2, t.H1, S + 4, HID, t.W + L.o_b2, t.H2);
-  act_pass<S, NT>(t.H2, FULL ? t.D2 : nullptr, L.hact);
+  gemm_fwd<HD, S, NT>(t.W + L.o_w2, t.H1, S + 4, HID, t.W + L.o_b2, t.H2);
+  act_pass<HD, S, NT>(t.H2, FULL ? t.D2 : nullptr, L.hact);
   __syncthreads();
-  if (OUT) out_layer<S, NT>(t.W + L.o_w3, t.W + L.o_b3, t.H2, L.out, Zout, XS);
+  if (OUT) out_layer<HD, S, NT>(t.W + L.o_w3, t.W + L.o_b3, t.H2, L.out, Zout, XS);
 }
 
 // Given Zbar in t.Z (rows 0..out-1): accumulate weight grads into t.dW (torch flat layout) if WANT_DW and
 // write the observation gradient into rows [0, L.obs) of t.X if want_dx.  Requires a FULL forward of the
 // same sub-tile.  Ends with a barrier (the activation tiles may be reused afterwards).
-template <int S, int NT, bool WANT_DW>
+template <int HD, int S, int NT, bool WANT_DW>
 __device__ __forceinline__ void mlp_backward(const NetL& L, const Tiles& t, bool want_dx) {
-  constexpr int XS = NT + 4, SP = S + 4;
+  constexpr int XS = NT + 4, SP = S + 4, HID = HD;
   if (WANT_DW) {
-    dw_accum<S, NT, 1, 4>(t.Z, XS, L.out, t.H2, SP, HID, t.dW + L.g_w3, HID);
-    rowsum_accum<S, NT>(t.Z, XS, L.out, t.dW + L.g_b3);
+    dw_accum<HD, S, NT, 1, 4>(t.Z, XS, L.out, t.H2, SP, HID, t.dW + L.g_w3, HID);
+    rowsum_accum<HD, S, NT>(t.Z, XS, L.out, t.dW + L.g_b3);
   }
-  delta_from_out<S, NT>(t.W + L.o_w3, t.Z, XS, L.out, t.D2);  // D2 <- delta2
+  delta_from_out<HD, S, NT>(t.W + L.o_w3, t.Z, XS, L.out, t.D2);  // D2 <- delta2
   __syncthreads();
-  gemm_bwd<S, NT>(t.W + L.o_w2, t.D2, t.D1);                  // D1 <- delta1
+  gemm_bwd<HD, S, NT>(t.W + L.o_w2, t.D2, t.D1);                  // D1 <- delta1
   if (WANT_DW) {
-    dw_accum<S, NT, 4, 4>(t.D2, SP, HID, t.H1, SP, HID, t.dW + L.g_w2, HID);
-    rowsum_accum<S, NT>(t.D2, SP, HID, t.dW + L.g_b2);
+    dw_accum<HD, S, NT, 4, 4>(t.D2, SP, HID, t.H1, SP, HID, t.dW + L.g_w2, HID);
+    rowsum_accum<HD, S, NT>(t.D2, SP, HID, t.dW + L.g_b2);
   }
   __syncthreads();
   if (WANT_DW) {
-    if (L.in <= 16) dw_accum<S, NT, 2, 2>(t.D1, SP, HID, t.X, XS, L.in, t.dW + L.g_w1, L.in);
-    else dw_accum<S, NT, 4, 4>(t.D1, SP, HID, t.X, XS, L.in, t.dW + L.g_w1, L.in);
-    rowsum_accum<S, NT>(t.D1, SP, HID, t.dW + L.g_b1);
+    if (L.in <= 16) dw_accum<HD, S, NT, 2, 2>(t.D1, SP, HID, t.X, XS, L.in, t.dW + L.g_w1, L.in);
+    else dw_accum<HD, S, NT, 4, 4>(t.D1, SP, HID, t.X, XS, L.in, t.dW + L.g_w1, L.in);
+    rowsum_accum<HD, S, NT>(t.D1, SP, HID, t.dW + L.g_b1);
     if (want_dx) __syncthreads();
   }
-  if (want_dx) gemm_dx<S, NT>(t.W + L.o_w1, t.D1, L.obs, t.X, XS);
+  if (want_dx) gemm_dx<HD, S, NT>(t.W + L.o_w1, t.D1, L.obs, t.X, XS);
   __syncthreads();
 }
 

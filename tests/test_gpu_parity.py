@@ -178,10 +178,14 @@ def _oracle_nets(alg, hidden_act, dtype):
     ("pyth_veh3dofconti", "INFADP", "relu", 300, 10),
     ("pyth_veh3dofconti", "FHADP", "gelu", 200, 10),
     ("veh3dof_tracking", "FHADP", "elu", 250, 10),
+    ("pyth_idpendulum", "FHADP", "gelu256", 300, 8),
+    ("pyth_lq", "INFADP", "relu256", 200, 5),
 ])
 def test_against_oracle_fp64(env_id, algname, act, B, H):
     """Fresh seeded inputs, ragged batch sizes (not multiples of the tile), fp64 oracle as truth."""
     from gops_b200.create_pkg.create_alg import create_alg
+    hid = 256 if act.endswith("256") else 64
+    act = act.replace("256", "")
     lq = dict(lq_config="s4a2") if env_id == "pyth_lq" else {}
     veh = env_id in ("pyth_veh3dofconti", "veh3dof_tracking")
     if veh:
@@ -191,9 +195,9 @@ def test_against_oracle_fp64(env_id, algname, act, B, H):
               action_type="continu", obsv_dim=obs_dim, action_dim=act_dim,
               action_high_limit=np.ones(act_dim, dtype=np.float32), action_low_limit=-np.ones(act_dim, dtype=np.float32),
               policy_func_name="FiniteHorizonPolicy" if algname == "FHADP" else "DetermPolicy", policy_func_type="MLP",
-              policy_hidden_sizes=[64, 64], policy_hidden_activation=act, policy_act_distribution="default",
+              policy_hidden_sizes=[hid, hid], policy_hidden_activation=act, policy_act_distribution="default",
               policy_learning_rate=1e-3, value_func_name="StateValue", value_func_type="MLP",
-              value_hidden_sizes=[64, 64], value_hidden_activation=act, value_learning_rate=1e-3,
+              value_hidden_sizes=[hid, hid], value_hidden_activation=act, value_learning_rate=1e-3,
               reward_scale=0.5, reward_shift=0.25, **lq)
     if algname == "FHADP":
         kw.update(pre_horizon=H, gamma=0.98)
