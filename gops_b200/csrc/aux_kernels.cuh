@@ -8,18 +8,36 @@ namespace gops {
 // torch-layout flat parameters -> packed k-major blob (W1^T, W2^T with row stride HP; 16-byte aligned parts)
 // ---------------------------------------------------------------------------------------------
 __global__ void pack_params_kernel(const float* __restrict__ flat, NetL L, int HID, float* __restrict__ blob) {
-  const int HP = HID + 4;
+  const int HP = HID == 64 ? 72 : HID + 4;
+  const bool split = HID == 64;          // 64-wide nets: hi / lo planes for the 3xTF32 tensor-core GEMMs
   const int n = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
   const float* W1 = flat + L.g_w1;
   const float* W2 = flat + L.g_w2;
   const float* W3 = flat + L.g_w3;
-  for (int i = t0; i < L.in * HP; i += n) {       // W1^T, k-major, row stride HP (pad columns = 0)
+  const int rows1 = split ? L.in8 : L.in;
+  for (int i = t0; i < rows1 * HP; i += n) {       // W1^T, k-major, row stride HP (pad rows / columns = 0)
     const int k = i / HP, o = i - k * HP;
-    blob[L.o_w1 + i] = o < HID ? W1[o * L.in + k] : 0.f;
+    const float w = (o < HID && k < L.in) ? W1[o * L.in + k] : 0.f;
+    if (split) {
+      uint32_t hi;
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(w));
+      blob[L.o_w1 + i] = __uint_as_float(hi);
+      blob[L.o_w1l + i] = w - __uint_as_float(hi);
+    } else {
+      blob[L.o_w1 + i] = w;
+    }
   }
-  for (int i = t0; i < HID * HP; i += n) {        // W2^T
+  for (int i = t0; i < HID * HP; i += n) {         // W2^T
     const int k = i / HP, o = i - k * HP;
-    blob[L.o_w2 + i] = o < HID ? W2[o * HID + k] : 0.f;
+    const float w = o < HID ? W2[o * HID + k] : 0.f;
+    if (split) {
+      uint32_t hi;
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(w));
+      blob[L.o_w2 + i] = __uint_as_float(hi);
+      blob[L.o_w2l + i] = w - __uint_as_float(hi);
+    } else {
+      blob[L.o_w2 + i] = w;
+    }
   }
   for (int i = t0; i < L.out * HID; i += n) blob[L.o_w3 + i] = W3[i];
   for (int i = t0; i < HID; i += n) {

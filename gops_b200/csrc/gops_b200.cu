@@ -39,20 +39,29 @@ bool make_net(const gops_b200_mlp_desc& d, NetL& L, std::string& why) {
     why = "hidden width " + std::to_string(d.hidden) + " not built (supported: 64, 256)";
     return false;
   }
-  const int HID = d.hidden, HP = HID + 4;
+  const int HID = d.hidden, HP = HID == 64 ? 72 : HID + 4;
   if (d.out_dim < 1 || d.out_dim > MAXA) { why = "out_dim out of range"; return false; }
   if (d.out_act != GOPS_ACT_LINEAR) { why = "output_activation other than 'linear' is not supported"; return false; }
   if (d.hidden_act < 0 || d.hidden_act > GOPS_ACT_LINEAR) { why = "bad hidden activation"; return false; }
   L.obs = d.in_dim;
   L.time_input = d.time_input ? 1 : 0;
   L.in = d.in_dim + L.time_input;
-  L.inp = round4(L.in);
+  L.in8 = (L.in + 7) & ~7;
+  L.inp = L.in8;      // rows of the observation tile (pad rows stay zero)
   L.out = d.out_dim;
   L.hact = d.hidden_act;
   L.oact = d.out_act;
   int o = 0;
-  L.o_w1 = o; o += L.in * HP;
-  L.o_w2 = o; o += HID * HP;
+  if (HID == 64) {
+    L.o_w1 = o; o += L.in8 * HP;
+    L.o_w1l = o; o += L.in8 * HP;
+    L.o_w2 = o; o += HID * HP;
+    L.o_w2l = o; o += HID * HP;
+  } else {
+    L.o_w1 = o; o += L.in * HP;
+    L.o_w2 = o; o += HID * HP;
+    L.o_w1l = L.o_w1; L.o_w2l = L.o_w2;
+  }
   L.o_w3 = o; o += round4(L.out * HID);
   L.o_b1 = o; o += HID;
   L.o_b2 = o; o += HID;

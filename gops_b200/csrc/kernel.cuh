@@ -47,6 +47,7 @@ __global__ void __launch_bounds__(NT, 1) rollout_kernel(const __grid_constant__ 
     fence_mbar_init();
   }
   for (int i = tid; i < p.dw_floats; i += NT) t.dW[i] = 0.f;
+  for (int i = tid; i < p.inp_max * XS; i += NT) t.X[i] = 0.f;   // pad rows of the observation tile stay zero
 
   // TMA bulk copy of a packed weight blob into shared memory (all threads wait on the mbarrier)
   auto stage = [&](const float* gsrc, int floats) {
@@ -439,6 +440,7 @@ __global__ void __launch_bounds__(NT, 1) mlp_infer_kernel(const __grid_constant_
     t.X = t.W + p.w_floats;
     t.H1 = t.X + p.inp_max * XS;
   }
+  for (int i = threadIdx.x; i < p.inp_max * XS; i += NT) t.X[i] = 0.f;
   t.dW = nullptr;
   t.D1 = t.H1;
   t.H2 = t.H1 + HID * SP;

@@ -1,0 +1,201 @@
+// Tensor-core versions of the three dense primitives (hidden width 64 path): warp-level
+// mma.sync.m16n8k8 TF32 with the 3xTF32 error-compensated split (hi*hi + hi*lo + lo*hi, FP32 accumulate).
+// plain TF32 operands break the 1e-4 loss budget (8e-4 .. 5e-3), the split keeps ~2e-6.
+//
+// Operand roles (g = lane >> 2, t = lane & 3):
+//   A (16 x 8, row)  a0 = A[g][t]      a1 = A[g+8][t]    a2 = A[g][t+4]   a3 = A[g+8][t+4]
+//   B ( 8 x 8, col)  b0 = B[t][g]      b1 = B[t+4][g]
+//   C (16 x 8)       c0 = C[g][2t]     c1 = C[g][2t+1]   c2 = C[g+8][2t]  c3 = C[g+8][2t+1]
+// Activations are [feature][sample] tiles, so "row of A" = sample and k = feature for the layer GEMMs, and
+// k = sample for the weight-gradient GEMM.  Weights are pre-split into hi / lo planes by pack_params_kernel.
+#pragma once
+#include "common.cuh"
+
+namespace gops {
+
+__device__ __forceinline__ void mma_tf32(float* d, const uint32_t* a, const uint32_t* b) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+// x = hi + lo exactly; hi carries the top 11 mantissa bits (round-to-nearest), the tensor core truncates lo
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+  lo = __float_as_uint(x - __uint_as_float(hi));
+}
+// d += a * b with the three significant partial products (small ones first)
+__device__ __forceinline__ void mma_3xtf32(float* d, const uint32_t* ah, const uint32_t* al, const uint32_t* bh,
+                                           const uint32_t* bl) {
+  mma_tf32(d, al, bh);
+  mma_tf32(d, ah, bl);
+  mma_tf32(d, ah, bh);
+}
+
+// Warp tiling of a [S samples x 64 features] layer output: warp w -> 16 samples (w >> 1) x 32 features (w & 1).
+template <int S, int NT>
+struct MmaMap {
+  static_assert(NT == 4 * S, "layer-GEMM warp tiling assumes NT = 4 S (two warps per 16-sample stripe)");
+  int s0, m0, g, t;
+  __device__ __forceinline__ MmaMap() {
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    s0 = (w >> 1) * 16;
+    m0 = (w & 1) * 32;
+    g = l >> 2;
+    t = l & 3;
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// P[m][s] = bias[m] + sum_k W[k][m] * B[k][s]      (hidden-layer pre-activations), K8 = K rounded up to 8
+// (rows K..K8-1 of B and of the weight planes are zero).  Whi/Wlo: [K8][HP] planes, B: [K8][ldb].
+// The fragment owners store P, then `act_pass_frag` re-reads exactly the same elements (no barrier).
+// ---------------------------------------------------------------------------------------------
+template <int S, int NT, int HP>
+__device__ __noinline__ void gemm_fwd_mma(const float* __restrict__ Whi, const float* __restrict__ Wlo,
+                                          const float* __restrict__ Bm, int ldb, int K8,
+                                          const float* __restrict__ bias, float* __restrict__ P) {
+  constexpr int SP = S + 4;
+  const MmaMap<S, NT> mp;
+  float c[4][4];
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt) {
+    const float b0 = bias[mp.m0 + 8 * nt + 2 * mp.t], b1 = bias[mp.m0 + 8 * nt + 2 * mp.t + 1];
+    c[nt][0] = b0; c[nt][1] = b1; c[nt][2] = b0; c[nt][3] = b1;
+  }
+  const float* ap = Bm + mp.t * ldb + mp.s0 + mp.g;
+  const float* wh = Whi + mp.t * HP + mp.m0 + mp.g;
+  const float* wl = Wlo + mp.t * HP + mp.m0 + mp.g;
+#pragma unroll 2
+  for (int k0 = 0; k0 < K8; k0 += 8) {
+    uint32_t ah[4], al[4];
+    split_tf32(ap[k0 * ldb], ah[0], al[0]);
+    split_tf32(ap[k0 * ldb + 8], ah[1], al[1]);
+    split_tf32(ap[(k0 + 4) * ldb], ah[2], al[2]);
+    split_tf32(ap[(k0 + 4) * ldb + 8], ah[3], al[3]);
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      uint32_t bh[2], bl[2];
+      bh[0] = __float_as_uint(wh[k0 * HP + 8 * nt]);
+      bh[1] = __float_as_uint(wh[(k0 + 4) * HP + 8 * nt]);
+      bl[0] = __float_as_uint(wl[k0 * HP + 8 * nt]);
+      bl[1] = __float_as_uint(wl[(k0 + 4) * HP + 8 * nt]);
+      mma_3xtf32(c[nt], ah, al, bh, bl);
+    }
+  }
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt) {
+    float* p = P + (mp.m0 + 8 * nt + 2 * mp.t) * SP + mp.s0 + mp.g;
+    p[0] = c[nt][0]; p[SP] = c[nt][1]; p[8] = c[nt][2]; p[SP + 8] = c[nt][3];
+  }
+}
+
+// In-place activation with the SAME element ownership as gemm_fwd_mma's epilogue: H <- act(P), D <- act'(P).
+template <int S, int NT>
+__device__ __noinline__ void act_pass_frag(float* __restrict__ H, float* __restrict__ D, int act) {
+  constexpr int SP = S + 4;
+  const MmaMap<S, NT> mp;
+#pragma unroll 1
+  for (int nt = 0; nt < 4; ++nt) {
+    const int base = (mp.m0 + 8 * nt + 2 * mp.t) * SP + mp.s0 + mp.g;
+    float* hp = H + base;
+    const float p0 = hp[0], p1 = hp[SP], p2 = hp[8], p3 = hp[SP + 8];
+    float h0, h1, h2, h3;
+    if (D != nullptr) {
+      float d0, d1, d2, d3;
+      act_fwd_grad(act, p0, h0, d0); act_fwd_grad(act, p1, h1, d1);
+      act_fwd_grad(act, p2, h2, d2); act_fwd_grad(act, p3, h3, d3);
+      float* dp = D + base;
+      dp[0] = d0; dp[SP] = d1; dp[8] = d2; dp[SP + 8] = d3;
+    } else {
+      h0 = act_fwd(act, p0); h1 = act_fwd(act, p1); h2 = act_fwd(act, p2); h3 = act_fwd(act, p3);
+    }
+    hp[0] = h0; hp[SP] = h1; hp[8] = h2; hp[SP + 8] = h3;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// D[i][s] <- D[i][s] * sum_o W[i][o] * Dl[o][s]     (delta of a hidden layer, in place over D)
+// The k-major weight planes [64][HP] are read transposed as the B operand: B[k = o][n = i] = W[i][o].
+// ---------------------------------------------------------------------------------------------
+template <int S, int NT, int HP>
+__device__ __noinline__ void gemm_bwd_mma(const float* __restrict__ Whi, const float* __restrict__ Wlo,
+                                          const float* __restrict__ Dl, float* __restrict__ D) {
+  constexpr int SP = S + 4;
+  const MmaMap<S, NT> mp;
+  float c[4][4];
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt) c[nt][0] = c[nt][1] = c[nt][2] = c[nt][3] = 0.f;
+  const float* ap = Dl + mp.t * SP + mp.s0 + mp.g;
+  const float* wh = Whi + (mp.m0 + mp.g) * HP + mp.t;
+  const float* wl = Wlo + (mp.m0 + mp.g) * HP + mp.t;
+#pragma unroll 2
+  for (int k0 = 0; k0 < 64; k0 += 8) {
+    uint32_t ah[4], al[4];
+    split_tf32(ap[k0 * SP], ah[0], al[0]);
+    split_tf32(ap[k0 * SP + 8], ah[1], al[1]);
+    split_tf32(ap[(k0 + 4) * SP], ah[2], al[2]);
+    split_tf32(ap[(k0 + 4) * SP + 8], ah[3], al[3]);
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      uint32_t bh[2], bl[2];
+      bh[0] = __float_as_uint(wh[8 * nt * HP + k0]);
+      bh[1] = __float_as_uint(wh[8 * nt * HP + k0 + 4]);
+      bl[0] = __float_as_uint(wl[8 * nt * HP + k0]);
+      bl[1] = __float_as_uint(wl[8 * nt * HP + k0 + 4]);
+      mma_3xtf32(c[nt], ah, al, bh, bl);
+    }
+  }
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt) {
+    float* p = D + (mp.m0 + 8 * nt + 2 * mp.t) * SP + mp.s0 + mp.g;
+    p[0] *= c[nt][0]; p[SP] *= c[nt][1]; p[8] *= c[nt][2]; p[SP + 8] *= c[nt][3];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// dst[o][i] += sum_s Dl[o][s] * Xl[i][s]   for o < 64, i < RI   (weight gradient, k = sample)
+// Work unit = 16 (o) x 16 (i) block (two n-tiles), units are dealt round-robin to the warps; both operands
+// are activations and are split on the fly.  Rows RI .. round8(RI)-1 of Xl must be finite (they are zero).
+// ---------------------------------------------------------------------------------------------
+template <int S, int NT>
+__device__ __noinline__ void dw_accum_mma(const float* __restrict__ Dl, int ldd, const float* __restrict__ Xl, int ldx,
+                                          int RI, float* __restrict__ dst, int ld) {
+  constexpr int NW = NT / 32;
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31, g = l >> 2, t = l & 3;
+  const int ntiles = (RI + 7) >> 3, npairs = (ntiles + 1) >> 1;
+  for (int unit = w; unit < 4 * npairs; unit += NW) {
+    const int o0 = (unit & 3) * 16, i0 = (unit >> 2) * 16;
+    const bool two = (i0 + 8) < 8 * ntiles;
+    float c[2][4];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) c[q][0] = c[q][1] = c[q][2] = c[q][3] = 0.f;
+    const float* ap = Dl + (o0 + g) * ldd + t;
+    const float* bp = Xl + (i0 + g) * ldx + t;
+#pragma unroll 2
+    for (int s = 0; s < S; s += 8) {
+      uint32_t ah[4], al[4], bh[2], bl[2];
+      split_tf32(ap[s], ah[0], al[0]);
+      split_tf32(ap[8 * ldd + s], ah[1], al[1]);
+      split_tf32(ap[s + 4], ah[2], al[2]);
+      split_tf32(ap[8 * ldd + s + 4], ah[3], al[3]);
+      split_tf32(bp[s], bh[0], bl[0]);
+      split_tf32(bp[s + 4], bh[1], bl[1]);
+      mma_3xtf32(c[0], ah, al, bh, bl);
+      if (two) {
+        split_tf32(bp[8 * ldx + s], bh[0], bl[0]);
+        split_tf32(bp[8 * ldx + s + 4], bh[1], bl[1]);
+        mma_3xtf32(c[1], ah, al, bh, bl);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int i = i0 + 8 * q + 2 * t;
+      if (q == 1 && !two) break;
+      if (i < RI) { dst[(o0 + g) * ld + i] += c[q][0]; dst[(o0 + g + 8) * ld + i] += c[q][2]; }
+      if (i + 1 < RI) { dst[(o0 + g) * ld + i + 1] += c[q][1]; dst[(o0 + g + 8) * ld + i + 1] += c[q][3]; }
+    }
+  }
+}
+
+}  // namespace gops

@@ -13,12 +13,15 @@
 // (v1 inlined everything: 68k SASS instructions, `no_instruction` was the top stall).
 #pragma once
 #include "common.cuh"
+#include "mma_tiles.cuh"
 
 namespace gops {
 
 // Hidden width HD is a template parameter of every primitive (64: everything in shared memory; 256: weights,
 // weight-gradient accumulators and the observation tile live in global memory / L2, activations in smem).
-// k-major weight tiles have row stride HD + 4 (bank skew for the transposed reads of the backward GEMM).
+// k-major weight tiles have row stride hp_of(HD): HD + 4 for the FFMA path (bank skew 4 for the transposed
+// reads), 72 for the 64-wide tensor-core path (bank skew 8: conflict-free B-fragment loads of the forward GEMMs).
+__host__ __device__ constexpr int hp_of(int HD) { return HD == 64 ? 72 : HD + 4; }
 
 // Reference-trajectory constants as fp32 values derived on the host in double precision.
 struct RtC {
@@ -39,6 +42,8 @@ struct NetL {
   // packed weight blob offsets (floats); blob is what TMA copies to shared memory
   //   w1: [in][HP]  (W1^T, k-major)   w2: [HID][HP] (W2^T)   w3: [out][HID]   b1,b2: [HID]   b3: [4]
   int o_w1, o_w2, o_w3, o_b1, o_b2, o_b3, blob;
+  int o_w1l, o_w2l;   // 64-wide path: lo planes of the 3xTF32 split (o_w1 / o_w2 then hold the hi planes)
+  int in8;            // in rounded up to 8 (k extent of the layer-1 tensor-core GEMM)
   // torch flat parameter offsets
   int g_w1, g_b1, g_w2, g_b2, g_w3, g_b3, nparam;
 };
@@ -95,7 +100,7 @@ constexpr int ALG_FHADP = GOPS_ALG_FHADP, ALG_PIM = GOPS_ALG_INFADP_POLICY, ALG_
 // owns TM features x 4 samples.  One k-step then needs ONE 64 B and ONE 128 B shared wavefront per warp.
 template <int HD, int S, int NT>
 struct Map {
-  static constexpr int HID = HD, HP = HD + 4;
+  static constexpr int HID = HD, HP = hp_of(HD);
   static constexpr int SP = S + 4, NW = NT / 32, WN = S / 32, WM = NW / WN, TM = HID / (4 * WM);
   static_assert(S % 32 == 0 && NW % WN == 0 && WM >= 1 && TM >= 1 && TM * 4 * WM == HID && TM % 4 == 0, "bad tiling");
   int n0, mt;   // first sample column, feature-thread index (0 .. 4*WM-1)
@@ -114,7 +119,7 @@ template <int HD, int S, int NT>
 __device__ __noinline__ void gemm_fwd(const float* __restrict__ A, const float* __restrict__ Bm, int ldb, int K,
                                       const float* __restrict__ bias, float* __restrict__ P) {
   using M = Map<HD, S, NT>;
-  constexpr int HID = HD, HP = HD + 4;
+  constexpr int HID = HD, HP = hp_of(HD);
   constexpr int SP = M::SP, TM = M::TM;
   const M mp;
   const int m0 = mp.mt * TM;
@@ -153,7 +158,7 @@ __device__ __noinline__ void gemm_fwd(const float* __restrict__ A, const float* 
 template <int HD, int S, int NT>
 __device__ __noinline__ void act_pass(float* __restrict__ H, float* __restrict__ D, int act) {
   using M = Map<HD, S, NT>;
-  constexpr int HID = HD, HP = HD + 4;
+  constexpr int HID = HD, HP = hp_of(HD);
   constexpr int SP = M::SP, TM = M::TM;
   const M mp;
   const int m0 = mp.mt * TM;
@@ -182,7 +187,7 @@ template <int HD, int S, int NT>
 __device__ __noinline__ void gemm_bwd(const float* __restrict__ A, const float* __restrict__ Dl,
                                       float* __restrict__ D) {
   using M = Map<HD, S, NT>;
-  constexpr int HID = HD, HP = HD + 4;
+  constexpr int HID = HD, HP = hp_of(HD);
   constexpr int SP = M::SP, TM = M::TM, RS = 4 * M::WM;
   const M mp;
   float acc[TM][4];
@@ -239,7 +244,7 @@ template <int HD, int S, int NT>
 __device__ __noinline__ void delta_from_out(const float* __restrict__ W3, const float* __restrict__ Zb, int ldz, int out,
                                             float* __restrict__ D) {
   using M = Map<HD, S, NT>;
-  constexpr int HID = HD, HP = HD + 4;
+  constexpr int HID = HD, HP = hp_of(HD);
   constexpr int SP = M::SP, TM = M::TM;
   const M mp;
   const int m0 = mp.mt * TM;
@@ -329,9 +334,9 @@ __device__ __noinline__ void rowsum_accum(const float* __restrict__ Dl, int ldd,
 
 // Xb[i][s] = sum_o W1k[i][o] * Dl[o][s]  for i < M (M <= 8*MG)   (input gradient; W1k: [in][HP] k-major)
 template <int HD, int S, int NT>
-__device__ __noinline__ void gemm_dx(const float* __restrict__ W1k, const float* __restrict__ Dl, int M,
-                                     float* __restrict__ Xb, int ldx) {
-  constexpr int SP = S + 4, NTN = S / 4, MG = NT / NTN, JM = 8, HID = HD, HP = HD + 4;
+__device__ __noinline__ void gemm_dx(const float* __restrict__ W1k, const float* __restrict__ W1lo,
+                                     const float* __restrict__ Dl, int M, float* __restrict__ Xb, int ldx) {
+  constexpr int SP = S + 4, NTN = S / 4, MG = NT / NTN, JM = 8, HID = HD, HP = hp_of(HD);
   const int tid = threadIdx.x, nt = tid % NTN, mg = tid / NTN;
   const int J = (M - mg + MG - 1) / MG;  // rows mg, mg+MG, ... < M
   if (J <= 0) return;
@@ -346,7 +351,11 @@ __device__ __noinline__ void gemm_dx(const float* __restrict__ W1k, const float*
 #pragma unroll
     for (int j = 0; j < JM; ++j)
       if (j < J) {
-        const float4 w = *reinterpret_cast<const float4*>(W1k + (mg + MG * j) * HP + o);
+        float4 w = *reinterpret_cast<const float4*>(W1k + (mg + MG * j) * HP + o);
+        if (W1lo != nullptr) {   // hi + lo == the fp32 weight exactly
+          const float4 wl = *reinterpret_cast<const float4*>(W1lo + (mg + MG * j) * HP + o);
+          w.x += wl.x; w.y += wl.y; w.z += wl.z; w.w += wl.w;
+        }
         acc[j][0] = fmaf(w.x, d[0].x, acc[j][0]); acc[j][1] = fmaf(w.x, d[0].y, acc[j][1]);
         acc[j][2] = fmaf(w.x, d[0].z, acc[j][2]); acc[j][3] = fmaf(w.x, d[0].w, acc[j][3]);
         acc[j][0] = fmaf(w.y, d[1].x, acc[j][0]); acc[j][1] = fmaf(w.y, d[1].y, acc[j][1]);
@@ -372,14 +381,23 @@ struct Tiles {
 
 // X -> H1 -> H2 (-> Zout).  FULL: also store activation derivatives (needed by mlp_backward).
 // No trailing barrier: the caller synchronises once after its sub-tile loop / before consuming Zout.
+// HD == 64: tensor-core GEMMs (3xTF32 mma.sync, mma_tiles.cuh); HD == 256: FP32 FFMA GEMMs.
 template <int HD, int S, int NT, bool FULL, bool OUT>
 __device__ __forceinline__ void mlp_forward(const NetL& L, const Tiles& t, float* Zout) {
   constexpr int XS = NT + 4, HID = HD;
-  gemm_fwd<HD, S, NT>(t.W + L.o_w1, t.X, XS, L.in, t.W + L.o_b1, t.H1);
-  act_pass<HD, S, NT>(t.H1, FULL ? t.D1 : nullptr, L.hact);
-  __syncthreads();
-  gemm_fwd<HD, S, NT>(t.W + L.o_w2, t.H1, S + 4, HID, t.W + L.o_b2, t.H2);
-  act_pass<HD, S, NT>(t.H2, FULL ? t.D2 : nullptr, L.hact);
+  if constexpr (HD == 64) {
+    gemm_fwd_mma<S, NT, hp_of(HD)>(t.W + L.o_w1, t.W + L.o_w1l, t.X, XS, L.in8, t.W + L.o_b1, t.H1);
+    act_pass_frag<S, NT>(t.H1, FULL ? t.D1 : nullptr, L.hact);
+    __syncthreads();
+    gemm_fwd_mma<S, NT, hp_of(HD)>(t.W + L.o_w2, t.W + L.o_w2l, t.H1, S + 4, HID, t.W + L.o_b2, t.H2);
+    act_pass_frag<S, NT>(t.H2, FULL ? t.D2 : nullptr, L.hact);
+  } else {
+    gemm_fwd<HD, S, NT>(t.W + L.o_w1, t.X, XS, L.in, t.W + L.o_b1, t.H1);
+    act_pass<HD, S, NT>(t.H1, FULL ? t.D1 : nullptr, L.hact);
+    __syncthreads();
+    gemm_fwd<HD, S, NT>(t.W + L.o_w2, t.H1, S + 4, HID, t.W + L.o_b2, t.H2);
+    act_pass<HD, S, NT>(t.H2, FULL ? t.D2 : nullptr, L.hact);
+  }
   __syncthreads();
   if (OUT) out_layer<HD, S, NT>(t.W + L.o_w3, t.W + L.o_b3, t.H2, L.out, Zout, XS);
 }
@@ -396,19 +414,21 @@ __device__ __forceinline__ void mlp_backward(const NetL& L, const Tiles& t, bool
   }
   delta_from_out<HD, S, NT>(t.W + L.o_w3, t.Z, XS, L.out, t.D2);  // D2 <- delta2
   __syncthreads();
-  gemm_bwd<HD, S, NT>(t.W + L.o_w2, t.D2, t.D1);                  // D1 <- delta1
+  if constexpr (HD == 64) gemm_bwd_mma<S, NT, hp_of(HD)>(t.W + L.o_w2, t.W + L.o_w2l, t.D2, t.D1);   // D1 <- delta1
+  else gemm_bwd<HD, S, NT>(t.W + L.o_w2, t.D2, t.D1);
   if (WANT_DW) {
-    dw_accum<HD, S, NT, 4, 4>(t.D2, SP, HID, t.H1, SP, HID, t.dW + L.g_w2, HID);
+    if constexpr (HD == 64) dw_accum_mma<S, NT>(t.D2, SP, t.H1, SP, HID, t.dW + L.g_w2, HID);
+    else dw_accum<HD, S, NT, 4, 4>(t.D2, SP, HID, t.H1, SP, HID, t.dW + L.g_w2, HID);
     rowsum_accum<HD, S, NT>(t.D2, SP, HID, t.dW + L.g_b2);
   }
   __syncthreads();
   if (WANT_DW) {
-    if (L.in <= 16) dw_accum<HD, S, NT, 2, 2>(t.D1, SP, HID, t.X, XS, L.in, t.dW + L.g_w1, L.in);
+    if constexpr (HD == 64) dw_accum_mma<S, NT>(t.D1, SP, t.X, XS, L.in, t.dW + L.g_w1, L.in);
     else dw_accum<HD, S, NT, 4, 4>(t.D1, SP, HID, t.X, XS, L.in, t.dW + L.g_w1, L.in);
     rowsum_accum<HD, S, NT>(t.D1, SP, HID, t.dW + L.g_b1);
     if (want_dx) __syncthreads();
   }
-  if (want_dx) gemm_dx<HD, S, NT>(t.W + L.o_w1, t.D1, L.obs, t.X, XS);
+  if (want_dx) gemm_dx<HD, S, NT>(t.W + L.o_w1, HD == 64 ? t.W + L.o_w1l : nullptr, t.D1, L.obs, t.X, XS);
   __syncthreads();
 }
 
