@@ -73,15 +73,21 @@ __device__ __noinline__ void gemm_fwd_mma(const float* __restrict__ Whi, const f
     split_tf32(ap[k0 * ldb + 8], ah[1], al[1]);
     split_tf32(ap[(k0 + 4) * ldb], ah[2], al[2]);
     split_tf32(ap[(k0 + 4) * ldb + 8], ah[3], al[3]);
+    uint32_t bh[4][2], bl[4][2];
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt) {
-      uint32_t bh[2], bl[2];
-      bh[0] = __float_as_uint(wh[k0 * HP + 8 * nt]);
-      bh[1] = __float_as_uint(wh[(k0 + 4) * HP + 8 * nt]);
-      bl[0] = __float_as_uint(wl[k0 * HP + 8 * nt]);
-      bl[1] = __float_as_uint(wl[(k0 + 4) * HP + 8 * nt]);
-      mma_3xtf32(c[nt], ah, al, bh, bl);
+      bh[nt][0] = __float_as_uint(wh[k0 * HP + 8 * nt]);
+      bh[nt][1] = __float_as_uint(wh[(k0 + 4) * HP + 8 * nt]);
+      bl[nt][0] = __float_as_uint(wl[k0 * HP + 8 * nt]);
+      bl[nt][1] = __float_as_uint(wl[(k0 + 4) * HP + 8 * nt]);
     }
+    // three passes over the four independent accumulators: no back-to-back dependent HMMA
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) mma_tf32(c[nt], al, bh[nt]);
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) mma_tf32(c[nt], ah, bl[nt]);
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) mma_tf32(c[nt], ah, bh[nt]);
   }
 #pragma unroll
   for (int nt = 0; nt < 4; ++nt) {
@@ -136,15 +142,20 @@ __device__ __noinline__ void gemm_bwd_mma(const float* __restrict__ Whi, const f
     split_tf32(ap[k0 * SP + 8], ah[1], al[1]);
     split_tf32(ap[(k0 + 4) * SP], ah[2], al[2]);
     split_tf32(ap[(k0 + 4) * SP + 8], ah[3], al[3]);
+    uint32_t bh[4][2], bl[4][2];
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt) {
-      uint32_t bh[2], bl[2];
-      bh[0] = __float_as_uint(wh[8 * nt * HP + k0]);
-      bh[1] = __float_as_uint(wh[8 * nt * HP + k0 + 4]);
-      bl[0] = __float_as_uint(wl[8 * nt * HP + k0]);
-      bl[1] = __float_as_uint(wl[8 * nt * HP + k0 + 4]);
-      mma_3xtf32(c[nt], ah, al, bh, bl);
+      bh[nt][0] = __float_as_uint(wh[8 * nt * HP + k0]);
+      bh[nt][1] = __float_as_uint(wh[8 * nt * HP + k0 + 4]);
+      bl[nt][0] = __float_as_uint(wl[8 * nt * HP + k0]);
+      bl[nt][1] = __float_as_uint(wl[8 * nt * HP + k0 + 4]);
     }
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) mma_tf32(c[nt], al, bh[nt]);
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) mma_tf32(c[nt], ah, bl[nt]);
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) mma_tf32(c[nt], ah, bh[nt]);
   }
 #pragma unroll
   for (int nt = 0; nt < 4; ++nt) {
@@ -179,13 +190,17 @@ __device__ __noinline__ void dw_accum_mma(const float* __restrict__ Dl, int ldd,
       split_tf32(ap[8 * ldd + s], ah[1], al[1]);
       split_tf32(ap[s + 4], ah[2], al[2]);
       split_tf32(ap[8 * ldd + s + 4], ah[3], al[3]);
+      uint32_t ch[2], cl[2];
       split_tf32(bp[s], bh[0], bl[0]);
       split_tf32(bp[s + 4], bh[1], bl[1]);
-      mma_3xtf32(c[0], ah, al, bh, bl);
       if (two) {
-        split_tf32(bp[8 * ldx + s], bh[0], bl[0]);
-        split_tf32(bp[8 * ldx + s + 4], bh[1], bl[1]);
-        mma_3xtf32(c[1], ah, al, bh, bl);
+        split_tf32(bp[8 * ldx + s], ch[0], cl[0]);
+        split_tf32(bp[8 * ldx + s + 4], ch[1], cl[1]);
+        mma_tf32(c[0], al, bh); mma_tf32(c[1], al, ch);
+        mma_tf32(c[0], ah, bl); mma_tf32(c[1], ah, cl);
+        mma_tf32(c[0], ah, bh); mma_tf32(c[1], ah, ch);
+      } else {
+        mma_3xtf32(c[0], ah, al, bh, bl);
       }
     }
 #pragma unroll
