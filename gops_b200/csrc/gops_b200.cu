@@ -146,13 +146,13 @@ namespace {
 
 size_t rollout_smem_bytes(const KParams& kp, int S, int NT) {
   const int SP = S + 4, XS = NT + 4, HID = kp.hid;
-  if (HID > 64) return sizeof(float) * (size_t)(4 + 4 * HID * SP + 4 * XS);
-  return sizeof(float) * (size_t)(4 + kp.w_floats + kp.dw_floats + kp.inp_max * XS + 4 * HID * SP + 4 * XS);
+  if (HID > 64) return sizeof(float) * (size_t)(4 + 4 * HID * SP + 8 * XS);
+  return sizeof(float) * (size_t)(4 + kp.w_floats + kp.dw_floats + kp.inp_max * XS + 4 * HID * SP + 8 * XS);
 }
 size_t infer_smem_bytes(const KParams& kp, int S, int NT) {
   const int SP = S + 4, XS = NT + 4, HID = kp.hid;
-  if (HID > 64) return sizeof(float) * (size_t)(4 + 2 * HID * SP + 4 * XS);
-  return sizeof(float) * (size_t)(4 + kp.w_floats + kp.inp_max * XS + 2 * HID * SP + 4 * XS);
+  if (HID > 64) return sizeof(float) * (size_t)(4 + 2 * HID * SP + 8 * XS);
+  return sizeof(float) * (size_t)(4 + kp.w_floats + kp.inp_max * XS + 2 * HID * SP + 8 * XS);
 }
 
 Config config_of(const gops_b200_plan* pl, int cfg) { return pl->kp.hid > 64 ? kWideConfig : kConfigs[cfg]; }

@@ -33,9 +33,17 @@ __global__ void __launch_bounds__(NT, 1) rollout_kernel(const __grid_constant__ 
   t.D1 = t.H1 + HID * SP;
   t.H2 = t.D1 + HID * SP;
   t.D2 = t.H2 + HID * SP;
-  t.Z = t.D2 + HID * SP;      // [4][XS]
+  t.Z = t.D2 + HID * SP;      // [8][XS]: rows a (+ 4 + a: second half-stripe partial of the fused output layer)
 
   const int tid = threadIdx.x;
+  // column (= sample slot of the chunk) owned by this thread.  Tensor-core path: the 64 threads of warp pair p own
+  // exactly the 16-sample stripes {sub * S + 16 p .. + 15} that the pair's MLP GEMMs produce, so the pair never has
+  // to synchronise with the rest of the CTA outside the weight-gradient reductions.
+  const int col = WG ? tid : (((tid & 63) >> 4) * S + 16 * (tid >> 6) + (tid & 15));
+  auto scope_sync = [&]() {
+    if (WG) __syncthreads();
+    else pair_sync();
+  };
   const NetL& P = p.pol;
   const NetL& V = p.val;
   const int H = p.horizon, obs_dim = P.obs, TCH = p.tape_ch;
@@ -48,6 +56,7 @@ __global__ void __launch_bounds__(NT, 1) rollout_kernel(const __grid_constant__ 
   }
   for (int i = tid; i < p.dw_floats; i += NT) t.dW[i] = 0.f;
   for (int i = tid; i < p.inp_max * XS; i += NT) t.X[i] = 0.f;   // pad rows of the observation tile stay zero
+  for (int i = tid; i < 8 * XS; i += NT) t.Z[i] = 0.f;
 
   // TMA bulk copy of a packed weight blob into shared memory (all threads wait on the mbarrier)
   auto stage = [&](const float* gsrc, int floats) {
@@ -96,8 +105,8 @@ __global__ void __launch_bounds__(NT, 1) rollout_kernel(const __grid_constant__ 
     load_obs_chunk(pos, nv, nsub * S);
     __syncthreads();
     float st[NS];
-    const bool valid = tid < nv;
-    const long long gs = pos + tid;
+    const bool valid = col < nv;
+    const long long gs = pos + col;
     bool dn = valid ? (p.done[gs] != 0.f) : true;
     float vacc = 0.f;
     int path = 0, spd = 0;                       // vehicle models: reference path / speed profile ids
@@ -105,7 +114,7 @@ __global__ void __launch_bounds__(NT, 1) rollout_kernel(const __grid_constant__ 
     win.base = nullptr; win.k0 = 0;
     if constexpr (M::KIND == 0) {
 #pragma unroll
-      for (int f = 0; f < NS; ++f) st[f] = f < obs_dim ? t.X[f * XS + tid] : 0.f;
+      for (int f = 0; f < NS; ++f) st[f] = f < obs_dim ? t.X[f * XS + col] : 0.f;
     } else {
 #pragma unroll
       for (int f = 0; f < NS; ++f) st[f] = 0.f;
@@ -137,17 +146,16 @@ __global__ void __launch_bounds__(NT, 1) rollout_kernel(const __grid_constant__ 
         for (int f = 0; f < NS; ++f) tape[(k * TCH + f) * NT + tid] = st[f];
         tape[(k * TCH + NS) * NT + tid] = dn ? 1.f : 0.f;
       }
-      if (P.time_input) t.X[(P.in - 1) * XS + tid] = (float)(k + 1);
-      __syncthreads();
+      if (P.time_input) t.X[(P.in - 1) * XS + col] = (float)(k + 1);
+      scope_sync();
       for (int sub = 0; sub < nsub; ++sub) {
         const Tiles ts = sub_tiles(sub);
         mlp_forward<HD, S, NT, false, true>(P, ts, ts.Z);
       }
-      __syncthreads();
       {
         float z[MAXA], a[MAXA], g[MAXA], apol[MAXA];
 #pragma unroll
-        for (int j = 0; j < MAXA; ++j) z[j] = j < P.out ? t.Z[j * XS + tid] : 0.f;
+        for (int j = 0; j < MAXA; ++j) z[j] = j < P.out ? t.Z[j * XS + col] + t.Z[(4 + j) * XS + col] : 0.f;
         if (alg == ALG_FHADP || alg == ALG_PIM) {
 #pragma unroll
           for (int j = 0; j < MAXA; ++j)
@@ -166,14 +174,14 @@ __global__ void __launch_bounds__(NT, 1) rollout_kernel(const __grid_constant__ 
             }
 #pragma unroll
             for (int f = 0; f < NS; ++f)
-              if (f < obs_dim) t.X[f * XS + tid] = st[f];
+              if (f < obs_dim) t.X[f * XS + col] = st[f];
           } else {
             const VehC vc = veh_const();
             float o6[6];
             if constexpr (M::KIND == 1) {
               // reward from the INCOMING observation (Veh3dofcontiModel.compute_reward :161-177)
 #pragma unroll
-              for (int f = 0; f < 6; ++f) o6[f] = t.X[f * XS + tid];
+              for (int f = 0; f < 6; ++f) o6[f] = t.X[f * XS + col];
               r = -(0.04f * (o6[0] * o6[0]) + 0.04f * (o6[1] * o6[1]) + 0.02f * (o6[2] * o6[2]) +
                     0.02f * (o6[3] * o6[3]) + 0.01f * (o6[5] * o6[5]) + 0.01f * (a[0] * a[0]) + 0.01f * (a[1] * a[1]));
               veh_step(vc, st, a);
@@ -185,7 +193,7 @@ __global__ void __launch_bounds__(NT, 1) rollout_kernel(const __grid_constant__ 
               nr[2 * NT] = rt_phi(p.rt, tq, path, spd);
               nr[3 * NT] = rt_u(p.rt, tq, spd);
               win.k0 = k + 1;
-              veh_write_obs<M::KIND, NT>(st, win, p.veh_P, t.X + tid, XS, o6);
+              veh_write_obs<M::KIND, NT>(st, win, p.veh_P, t.X + col, XS, o6);
               md = (fabsf(o6[0]) > 10.f) || (fabsf(o6[1]) > 10.f) || (fabsf(o6[2]) > 3.14159265358979323846f);
             } else {
               // reward from the CURRENT state against reference[:, t] (veh3dof_tracking_model.py:59-73)
@@ -197,7 +205,7 @@ __global__ void __launch_bounds__(NT, 1) rollout_kernel(const __grid_constant__ 
                     0.01f * (st[5] * st[5]) + 0.01f * (a[0] * a[0]) + 0.01f * (a[1] * a[1]));
               veh_step(vc, st, a);
               win.k0 = p.ref_t + k + 1;
-              veh_write_obs<M::KIND, NT>(st, win, p.veh_P, t.X + tid, XS, o6);
+              veh_write_obs<M::KIND, NT>(st, win, p.veh_P, t.X + col, XS, o6);
               win.get(0, q);
               md = (fabsf(st[0] - q[0]) > 5.f) || (fabsf(st[1] - q[1]) > 2.f) ||
                    (fabsf(angle_normalize(st[2] - q[2])) > 3.14159265358979323846f);
@@ -213,7 +221,7 @@ __global__ void __launch_bounds__(NT, 1) rollout_kernel(const __grid_constant__ 
         if (alg == ALG_TRACE && valid) {
           const size_t row = (size_t)k * B + gs;
           if (p.tr_obs)
-            for (int f = 0; f < obs_dim; ++f) p.tr_obs[row * obs_dim + f] = t.X[f * XS + tid];
+            for (int f = 0; f < obs_dim; ++f) p.tr_obs[row * obs_dim + f] = t.X[f * XS + col];
           if (p.tr_act)
             for (int j = 0; j < P.out; ++j) p.tr_act[row * P.out + j] = apol[j];
           if (p.tr_rew) p.tr_rew[row] = r;
@@ -233,32 +241,30 @@ __global__ void __launch_bounds__(NT, 1) rollout_kernel(const __grid_constant__ 
       const float gn = p.gpow[H];
       const bool term = valid && !dn;
       if (alg == ALG_PIM) {
-        t.Z[tid] = term ? -gn * p.inv_B : 0.f;     // row 0: d loss / d v_target(o_n); row 1 receives v
-        __syncthreads();
+        t.Z[col] = term ? -gn * p.inv_B : 0.f;     // row 0: d loss / d v_target(o_n); rows 1 (+5) receive v
+        scope_sync();
       }
       for (int sub = 0; sub < nsub; ++sub) {
         const Tiles ts = sub_tiles(sub);
         if (alg == ALG_PIM) {
           mlp_forward<HD, S, NT, true, true>(V, ts, ts.Z + XS);
-          __syncthreads();
           mlp_backward<HD, S, NT, false>(V, ts, true);
         } else {
           mlp_forward<HD, S, NT, false, true>(V, ts, ts.Z + XS);
         }
       }
-      __syncthreads();
       if (term) {
-        vacc += gn * t.Z[XS + tid];
+        vacc += gn * (t.Z[XS + col] + t.Z[5 * XS + col]);
         if (alg == ALG_PIM) {
           if constexpr (M::KIND == 0) {
 #pragma unroll
             for (int f = 0; f < NS; ++f)
-              if (f < obs_dim) lam[f] = t.X[f * XS + tid];
+              if (f < obs_dim) lam[f] = t.X[f * XS + col];
           } else {
             // o_n = get_obs(state_n, window_n): pull the value gradient back onto the robot state
             const float zero6[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
             win.k0 = (M::KIND == 1 ? 0 : p.ref_t) + H;
-            veh_obs_bwd<M::KIND, NT>(st, win, p.veh_P, t.X + tid, XS, zero6, lam);
+            veh_obs_bwd<M::KIND, NT>(st, win, p.veh_P, t.X + col, XS, zero6, lam);
           }
         }
       }
@@ -272,19 +278,18 @@ __global__ void __launch_bounds__(NT, 1) rollout_kernel(const __grid_constant__ 
       for (int sub = 0; sub < nsub; ++sub) {
         const Tiles ts = sub_tiles(sub);
         mlp_forward<HD, S, NT, true, true>(V, ts, ts.Z + XS);
-        __syncthreads();
-        if (tid / S == sub) {
+        if (col / S == sub) {
           float zb = 0.f;
           if (valid) {
-            const float v0 = t.Z[XS + tid];
+            const float v0 = t.Z[XS + col] + t.Z[5 * XS + col];
             const float diff = v0 - vacc;
             loss_acc += diff * diff * p.inv_B;
             vmean_acc += v0 * p.inv_B;
             zb = 2.f * diff * p.inv_B;
           }
-          t.Z[tid] = zb;
+          t.Z[col] = zb;
         }
-        __syncthreads();
+        scope_sync();
         mlp_backward<HD, S, NT, true>(V, ts, false);
       }
       stage(p.blob_pol, P.blob);
@@ -311,24 +316,24 @@ __global__ void __launch_bounds__(NT, 1) rollout_kernel(const __grid_constant__ 
       if constexpr (M::KIND == 0) {
 #pragma unroll
         for (int f = 0; f < NS; ++f)
-          if (f < obs_dim) t.X[f * XS + tid] = st[f];
+          if (f < obs_dim) t.X[f * XS + col] = st[f];
       } else {
         win.k0 = (M::KIND == 1 ? 0 : p.ref_t) + k;
         if (k > 0) {
           // only samples that were live at step k have a fully written window; the others get zeros
           // (their deltas are zero anyway, but 0 * garbage must never reach the weight gradients)
-          if (valid && !(p.mask_at_done && dnk)) veh_write_obs<M::KIND, NT>(st, win, p.veh_P, t.X + tid, XS, o6);
+          if (valid && !(p.mask_at_done && dnk)) veh_write_obs<M::KIND, NT>(st, win, p.veh_P, t.X + col, XS, o6);
           else {
-            for (int f = 0; f < obs_dim; ++f) t.X[f * XS + tid] = 0.f;
+            for (int f = 0; f < obs_dim; ++f) t.X[f * XS + col] = 0.f;
 #pragma unroll
             for (int f = 0; f < 6; ++f) o6[f] = 0.f;
           }
         } else {
 #pragma unroll
-          for (int f = 0; f < 6; ++f) o6[f] = t.X[f * XS + tid];
+          for (int f = 0; f < 6; ++f) o6[f] = t.X[f * XS + col];
         }
       }
-      if (P.time_input) t.X[(P.in - 1) * XS + tid] = (float)(k + 1);
+      if (P.time_input) t.X[(P.in - 1) * XS + col] = (float)(k + 1);
       const bool active = valid && (p.mask_at_done ? !dnk : true);
       float ro6[6];               // KIND 1: d loss / d obs_k[0..5] through the reward
 #pragma unroll
@@ -381,9 +386,9 @@ __global__ void __launch_bounds__(NT, 1) rollout_kernel(const __grid_constant__ 
         }
 #pragma unroll
         for (int j = 0; j < MAXA; ++j)
-          if (j < P.out) t.Z[j * XS + tid] = zb[j];
+          if (j < P.out) t.Z[j * XS + col] = zb[j];
       }
-      __syncthreads();
+      scope_sync();
       // MLP: re-compute the hidden activations of step k per sub-tile, then back-propagate Zbar
       for (int sub = 0; sub < nsub; ++sub) {
         const Tiles ts = sub_tiles(sub);
@@ -394,9 +399,9 @@ __global__ void __launch_bounds__(NT, 1) rollout_kernel(const __grid_constant__ 
         if constexpr (M::KIND == 0) {
 #pragma unroll
           for (int f = 0; f < NS; ++f)
-            if (f < obs_dim) lam[f] += t.X[f * XS + tid];
+            if (f < obs_dim) lam[f] += t.X[f * XS + col];
         } else {
-          veh_obs_bwd<M::KIND, NT>(st, win, p.veh_P, t.X + tid, XS, ro6, lam);
+          veh_obs_bwd<M::KIND, NT>(st, win, p.veh_P, t.X + col, XS, ro6, lam);
         }
       }
     }
@@ -446,6 +451,7 @@ __global__ void __launch_bounds__(NT, 1) mlp_infer_kernel(const __grid_constant_
   t.H2 = t.H1 + HID * SP;
   t.D2 = t.H2;
   t.Z = t.H2 + HID * SP;
+  for (int i = threadIdx.x; i < 8 * XS; i += NT) t.Z[i] = 0.f;
   const int tid = threadIdx.x;
   if (tid == 0) {
     mbar_init(mbar, 1);
@@ -485,7 +491,7 @@ __global__ void __launch_bounds__(NT, 1) mlp_infer_kernel(const __grid_constant_
     __syncthreads();
     if (tid < nv) {
       for (int j = 0; j < L.out; ++j) {
-        float z = t.Z[j * XS + tid];
+        float z = t.Z[j * XS + tid] + t.Z[(4 + j) * XS + tid];
         if (squash) z = __fadd_rn(__fmul_rn(p.pol_half[j], tanhf(z)), p.pol_mid[j]);
         out[(base + tid) * L.out + j] = z;
       }

@@ -96,14 +96,28 @@ __device__ __noinline__ void gemm_fwd_mma(const float* __restrict__ Whi, const f
   }
 }
 
+// 64-thread named barrier of the warp pair that owns one 16-sample stripe (ids 1..NT/64; id 0 = __syncthreads)
+__device__ __forceinline__ void pair_sync() {
+  asm volatile("bar.sync %0, 64;" ::"r"(1 + (int)(threadIdx.x >> 6)) : "memory");
+}
+
 // In-place activation with the SAME element ownership as gemm_fwd_mma's epilogue: H <- act(P), D <- act'(P).
+// If W3 != nullptr the output layer is fused: every thread dots its 8 features x 2 samples with W3, the quad
+// (4 lanes, 32 features) is reduced by shuffles and lane t == 0 stores the half-stripe partial
+//   Zout[(4 * half + a) * ldz + s]   (half 0 also adds the bias b3[a]); consumers add the two halves.
 template <int S, int NT>
-__device__ __noinline__ void act_pass_frag(float* __restrict__ H, float* __restrict__ D, int act) {
+__device__ __noinline__ void act_pass_frag(float* __restrict__ H, float* __restrict__ D, int act,
+                                           const float* __restrict__ W3, const float* __restrict__ b3, int out,
+                                           float* __restrict__ Zout, int ldz) {
   constexpr int SP = S + 4;
   const MmaMap<S, NT> mp;
+  float z0[MAXA], z1[MAXA];
+#pragma unroll
+  for (int a = 0; a < MAXA; ++a) z0[a] = z1[a] = 0.f;
 #pragma unroll 1
   for (int nt = 0; nt < 4; ++nt) {
-    const int base = (mp.m0 + 8 * nt + 2 * mp.t) * SP + mp.s0 + mp.g;
+    const int m = mp.m0 + 8 * nt + 2 * mp.t;
+    const int base = m * SP + mp.s0 + mp.g;
     float* hp = H + base;
     const float p0 = hp[0], p1 = hp[SP], p2 = hp[8], p3 = hp[SP + 8];
     float h0, h1, h2, h3;
@@ -117,6 +131,89 @@ __device__ __noinline__ void act_pass_frag(float* __restrict__ H, float* __restr
       h0 = act_fwd(act, p0); h1 = act_fwd(act, p1); h2 = act_fwd(act, p2); h3 = act_fwd(act, p3);
     }
     hp[0] = h0; hp[SP] = h1; hp[8] = h2; hp[SP + 8] = h3;
+    if (W3 != nullptr) {
+#pragma unroll
+      for (int a = 0; a < MAXA; ++a)
+        if (a < out) {
+          const float w0 = W3[a * 64 + m], w1 = W3[a * 64 + m + 1];
+          z0[a] = fmaf(w1, h1, fmaf(w0, h0, z0[a]));     // sample s0 + g
+          z1[a] = fmaf(w1, h3, fmaf(w0, h2, z1[a]));     // sample s0 + g + 8
+        }
+    }
+  }
+  if (W3 != nullptr) {
+    const int half = mp.m0 >> 5;
+#pragma unroll
+    for (int a = 0; a < MAXA; ++a)
+      if (a < out) {
+        float u = z0[a], v = z1[a];
+        u += __shfl_xor_sync(0xffffffffu, u, 1); v += __shfl_xor_sync(0xffffffffu, v, 1);
+        u += __shfl_xor_sync(0xffffffffu, u, 2); v += __shfl_xor_sync(0xffffffffu, v, 2);
+        if (mp.t == 0) {
+          const float bb = half == 0 ? b3[a] : 0.f;
+          Zout[(4 * half + a) * ldz + mp.s0 + mp.g] = u + bb;
+          Zout[(4 * half + a) * ldz + mp.s0 + mp.g + 8] = v + bb;
+        }
+      }
+  }
+}
+
+// D[m][s] <- D[m][s] * sum_a W3[a][m] * Zb[a][s] on the fragment-owned elements (stripe-local delta2)
+template <int S, int NT>
+__device__ __noinline__ void delta_from_out_frag(const float* __restrict__ W3, const float* __restrict__ Zb, int ldz,
+                                                 int out, float* __restrict__ D) {
+  constexpr int SP = S + 4;
+  const MmaMap<S, NT> mp;
+  float za[MAXA], zb[MAXA];
+#pragma unroll
+  for (int a = 0; a < MAXA; ++a) {
+    za[a] = a < out ? Zb[a * ldz + mp.s0 + mp.g] : 0.f;
+    zb[a] = a < out ? Zb[a * ldz + mp.s0 + mp.g + 8] : 0.f;
+  }
+#pragma unroll 1
+  for (int nt = 0; nt < 4; ++nt) {
+    const int m = mp.m0 + 8 * nt + 2 * mp.t;
+    float* p = D + m * SP + mp.s0 + mp.g;
+    float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;
+#pragma unroll
+    for (int a = 0; a < MAXA; ++a)
+      if (a < out) {
+        const float w0 = W3[a * 64 + m], w1 = W3[a * 64 + m + 1];
+        c0 = fmaf(w0, za[a], c0); c1 = fmaf(w1, za[a], c1);
+        c2 = fmaf(w0, zb[a], c2); c3 = fmaf(w1, zb[a], c3);
+      }
+    p[0] *= c0; p[SP] *= c1; p[8] *= c2; p[SP + 8] *= c3;
+  }
+}
+
+// Xb[i][s] = sum_o W1[i][o] * Dl[o][s] for i < M (stripe-local input gradient); n-tiles alternate between the
+// two warps of the pair.  W1 planes: [round8(in)][HP] k-major, read transposed like gemm_bwd_mma.
+template <int S, int NT, int HP>
+__device__ __noinline__ void gemm_dx_mma(const float* __restrict__ Whi, const float* __restrict__ Wlo,
+                                         const float* __restrict__ Dl, int M, float* __restrict__ Xb, int ldx) {
+  constexpr int SP = S + 4;
+  const MmaMap<S, NT> mp;
+  const int half = mp.m0 >> 5, ntiles = (M + 7) >> 3;
+  const float* ap = Dl + mp.t * SP + mp.s0 + mp.g;
+  for (int nt = half; nt < ntiles; nt += 2) {
+    float c[4] = {0.f, 0.f, 0.f, 0.f};
+    const float* wh = Whi + (8 * nt + mp.g) * HP + mp.t;
+    const float* wl = Wlo + (8 * nt + mp.g) * HP + mp.t;
+#pragma unroll 2
+    for (int k0 = 0; k0 < 64; k0 += 8) {
+      uint32_t ah[4], al[4], bh[2], bl[2];
+      split_tf32(ap[k0 * SP], ah[0], al[0]);
+      split_tf32(ap[k0 * SP + 8], ah[1], al[1]);
+      split_tf32(ap[(k0 + 4) * SP], ah[2], al[2]);
+      split_tf32(ap[(k0 + 4) * SP + 8], ah[3], al[3]);
+      bh[0] = __float_as_uint(wh[k0]); bh[1] = __float_as_uint(wh[k0 + 4]);
+      bl[0] = __float_as_uint(wl[k0]); bl[1] = __float_as_uint(wl[k0 + 4]);
+      mma_3xtf32(c, ah, al, bh, bl);
+    }
+    const int i = 8 * nt + 2 * mp.t;
+    float* p = Xb + i * ldx + mp.s0 + mp.g;
+    if (i < M) { p[0] = c[0]; p[8] = c[2]; }
+    if (i + 1 < M) { p[ldx] = c[1]; p[ldx + 8] = c[3]; }
   }
 }
 
@@ -171,9 +268,9 @@ __device__ __noinline__ void gemm_bwd_mma(const float* __restrict__ Whi, const f
 // ---------------------------------------------------------------------------------------------
 template <int S, int NT>
 __device__ __noinline__ void dw_accum_mma(const float* __restrict__ Dl, int ldd, const float* __restrict__ Xl, int ldx,
-                                          int RI, float* __restrict__ dst, int ld) {
+                                          int RI, float* __restrict__ dst, int ld, int woff) {
   constexpr int NW = NT / 32;
-  const int w = threadIdx.x >> 5, l = threadIdx.x & 31, g = l >> 2, t = l & 3;
+  const int w = ((threadIdx.x >> 5) + NW - (woff % NW)) % NW, l = threadIdx.x & 31, g = l >> 2, t = l & 3;
   const int ntiles = (RI + 7) >> 3, npairs = (ntiles + 1) >> 1;
   for (int unit = w; unit < 4 * npairs; unit += NW) {
     const int o0 = (unit & 3) * 16, i0 = (unit >> 2) * 16;

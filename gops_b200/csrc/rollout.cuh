@@ -274,9 +274,9 @@ __device__ __noinline__ void delta_from_out(const float* __restrict__ W3, const 
 // of the (S+4)-strided tiles -> conflict-free float4 shared loads.
 template <int HD, int S, int NT, int TO, int TI>
 __device__ __noinline__ void dw_accum(const float* __restrict__ Dl, int ldd, int RO, const float* __restrict__ Xl,
-                                      int ldx, int RI, float* __restrict__ dst, int ld) {
+                                      int ldx, int RI, float* __restrict__ dst, int ld, int toff = 0) {
   const int tiles_o = (RO + TO - 1) / TO, tiles_i = (RI + TI - 1) / TI;
-  for (int tile = threadIdx.x; tile < tiles_o * tiles_i; tile += NT) {
+  for (int tile = (threadIdx.x + NT - (toff % NT)) % NT; tile < tiles_o * tiles_i; tile += NT) {
     const int ti = tile % tiles_i, to = tile / tiles_i;
     float acc[TO][TI];
 #pragma unroll
@@ -320,8 +320,9 @@ __device__ __noinline__ void dw_accum(const float* __restrict__ Dl, int ldd, int
 
 // dst[o] += sum_s Dl[o][s]        (bias gradient)
 template <int HD, int S, int NT>
-__device__ __noinline__ void rowsum_accum(const float* __restrict__ Dl, int ldd, int RO, float* __restrict__ dst) {
-  for (int o = threadIdx.x; o < RO; o += NT) {
+__device__ __noinline__ void rowsum_accum(const float* __restrict__ Dl, int ldd, int RO, float* __restrict__ dst,
+                                          int toff = 0) {
+  for (int o = (threadIdx.x + NT - (toff % NT)) % NT; o < RO; o += NT) {
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll 4
     for (int s = 0; s < S; s += 4) {
@@ -379,57 +380,86 @@ struct Tiles {
   float *W, *dW, *X, *H1, *D1, *H2, *D2, *Z;
 };
 
-// X -> H1 -> H2 (-> Zout).  FULL: also store activation derivatives (needed by mlp_backward).
-// No trailing barrier: the caller synchronises once after its sub-tile loop / before consuming Zout.
-// HD == 64: tensor-core GEMMs (3xTF32 mma.sync, mma_tiles.cuh); HD == 256: FP32 FFMA GEMMs.
+// X -> H1 -> H2 (-> Zout rows a and 4 + a: consumers add the two).  FULL: also store activation derivatives.
+// HD == 64 (tensor-core path): every step is local to the 16-sample stripe owned by one warp pair, so only the
+// pair's 64-thread named barrier is used and the pairs of a CTA run asynchronously.  HD == 256 (FFMA path):
+// CTA-wide tiles and barriers.  Ends with a barrier of the respective scope.
 template <int HD, int S, int NT, bool FULL, bool OUT>
 __device__ __forceinline__ void mlp_forward(const NetL& L, const Tiles& t, float* Zout) {
   constexpr int XS = NT + 4, HID = HD;
   if constexpr (HD == 64) {
     gemm_fwd_mma<S, NT, hp_of(HD)>(t.W + L.o_w1, t.W + L.o_w1l, t.X, XS, L.in8, t.W + L.o_b1, t.H1);
-    act_pass_frag<S, NT>(t.H1, FULL ? t.D1 : nullptr, L.hact);
-    __syncthreads();
+    act_pass_frag<S, NT>(t.H1, FULL ? t.D1 : nullptr, L.hact, nullptr, nullptr, 0, nullptr, 0);
+    pair_sync();
     gemm_fwd_mma<S, NT, hp_of(HD)>(t.W + L.o_w2, t.W + L.o_w2l, t.H1, S + 4, HID, t.W + L.o_b2, t.H2);
-    act_pass_frag<S, NT>(t.H2, FULL ? t.D2 : nullptr, L.hact);
+    act_pass_frag<S, NT>(t.H2, FULL ? t.D2 : nullptr, L.hact, OUT ? t.W + L.o_w3 : nullptr, t.W + L.o_b3, L.out,
+                         Zout, XS);
+    pair_sync();
   } else {
     gemm_fwd<HD, S, NT>(t.W + L.o_w1, t.X, XS, L.in, t.W + L.o_b1, t.H1);
     act_pass<HD, S, NT>(t.H1, FULL ? t.D1 : nullptr, L.hact);
     __syncthreads();
     gemm_fwd<HD, S, NT>(t.W + L.o_w2, t.H1, S + 4, HID, t.W + L.o_b2, t.H2);
     act_pass<HD, S, NT>(t.H2, FULL ? t.D2 : nullptr, L.hact);
+    __syncthreads();
+    if (OUT) {
+      out_layer<HD, S, NT>(t.W + L.o_w3, t.W + L.o_b3, t.H2, L.out, Zout, XS);
+      __syncthreads();
+    }
   }
-  __syncthreads();
-  if (OUT) out_layer<HD, S, NT>(t.W + L.o_w3, t.W + L.o_b3, t.H2, L.out, Zout, XS);
 }
 
 // Given Zbar in t.Z (rows 0..out-1): accumulate weight grads into t.dW (torch flat layout) if WANT_DW and
 // write the observation gradient into rows [0, L.obs) of t.X if want_dx.  Requires a FULL forward of the
-// same sub-tile.  Ends with a barrier (the activation tiles may be reused afterwards).
+// same sub-tile.  HD == 64: delta2 / delta1 / dX are stripe-local (pair barriers); only the weight-gradient
+// reductions over samples are bracketed by CTA barriers, with the small jobs dealt to different warps.
 template <int HD, int S, int NT, bool WANT_DW>
 __device__ __forceinline__ void mlp_backward(const NetL& L, const Tiles& t, bool want_dx) {
   constexpr int XS = NT + 4, SP = S + 4, HID = HD;
-  if (WANT_DW) {
-    dw_accum<HD, S, NT, 1, 4>(t.Z, XS, L.out, t.H2, SP, HID, t.dW + L.g_w3, HID);
-    rowsum_accum<HD, S, NT>(t.Z, XS, L.out, t.dW + L.g_b3);
+  if constexpr (HD == 64) {
+    constexpr int HPc = hp_of(HD);
+    if (WANT_DW) {   // delta2 overwrites D2 in place: dW3 needs H2 only, db3 needs Zbar only -> do them in the dW phase
+    }
+    delta_from_out_frag<S, NT>(t.W + L.o_w3, t.Z, XS, L.out, t.D2);               // D2 <- delta2 (stripe)
+    pair_sync();
+    gemm_bwd_mma<S, NT, HPc>(t.W + L.o_w2, t.W + L.o_w2l, t.D2, t.D1);            // D1 <- delta1 (stripe)
+    if (WANT_DW) {
+      __syncthreads();                                                            // every stripe's deltas are ready
+      dw_accum_mma<S, NT>(t.D2, SP, t.H1, SP, HID, t.dW + L.g_w2, HID, 0);
+      dw_accum_mma<S, NT>(t.D1, SP, t.X, XS, L.in, t.dW + L.g_w1, L.in, NT / 64);
+      rowsum_accum<HD, S, NT>(t.D2, SP, HID, t.dW + L.g_b2, NT / 4);
+      rowsum_accum<HD, S, NT>(t.D1, SP, HID, t.dW + L.g_b1, NT / 4 + 64);
+      dw_accum<HD, S, NT, 1, 4>(t.Z, XS, L.out, t.H2, SP, HID, t.dW + L.g_w3, HID, 3 * NT / 4);
+      rowsum_accum<HD, S, NT>(t.Z, XS, L.out, t.dW + L.g_b3, 3 * NT / 4 + 32);
+      __syncthreads();                                                            // X / tiles may be overwritten
+    } else {
+      pair_sync();
+    }
+    if (want_dx) {
+      gemm_dx_mma<S, NT, HPc>(t.W + L.o_w1, t.W + L.o_w1l, t.D1, L.obs, t.X, XS);
+      pair_sync();
+    }
+  } else {
+    if (WANT_DW) {
+      dw_accum<HD, S, NT, 1, 4>(t.Z, XS, L.out, t.H2, SP, HID, t.dW + L.g_w3, HID);
+      rowsum_accum<HD, S, NT>(t.Z, XS, L.out, t.dW + L.g_b3);
+    }
+    delta_from_out<HD, S, NT>(t.W + L.o_w3, t.Z, XS, L.out, t.D2);  // D2 <- delta2
+    __syncthreads();
+    gemm_bwd<HD, S, NT>(t.W + L.o_w2, t.D2, t.D1);                  // D1 <- delta1
+    if (WANT_DW) {
+      dw_accum<HD, S, NT, 4, 4>(t.D2, SP, HID, t.H1, SP, HID, t.dW + L.g_w2, HID);
+      rowsum_accum<HD, S, NT>(t.D2, SP, HID, t.dW + L.g_b2);
+    }
+    __syncthreads();
+    if (WANT_DW) {
+      dw_accum<HD, S, NT, 4, 4>(t.D1, SP, HID, t.X, XS, L.in, t.dW + L.g_w1, L.in);
+      rowsum_accum<HD, S, NT>(t.D1, SP, HID, t.dW + L.g_b1);
+      if (want_dx) __syncthreads();
+    }
+    if (want_dx) gemm_dx<HD, S, NT>(t.W + L.o_w1, nullptr, t.D1, L.obs, t.X, XS);
+    __syncthreads();
   }
-  delta_from_out<HD, S, NT>(t.W + L.o_w3, t.Z, XS, L.out, t.D2);  // D2 <- delta2
-  __syncthreads();
-  if constexpr (HD == 64) gemm_bwd_mma<S, NT, hp_of(HD)>(t.W + L.o_w2, t.W + L.o_w2l, t.D2, t.D1);   // D1 <- delta1
-  else gemm_bwd<HD, S, NT>(t.W + L.o_w2, t.D2, t.D1);
-  if (WANT_DW) {
-    if constexpr (HD == 64) dw_accum_mma<S, NT>(t.D2, SP, t.H1, SP, HID, t.dW + L.g_w2, HID);
-    else dw_accum<HD, S, NT, 4, 4>(t.D2, SP, HID, t.H1, SP, HID, t.dW + L.g_w2, HID);
-    rowsum_accum<HD, S, NT>(t.D2, SP, HID, t.dW + L.g_b2);
-  }
-  __syncthreads();
-  if (WANT_DW) {
-    if constexpr (HD == 64) dw_accum_mma<S, NT>(t.D1, SP, t.X, XS, L.in, t.dW + L.g_w1, L.in);
-    else dw_accum<HD, S, NT, 4, 4>(t.D1, SP, HID, t.X, XS, L.in, t.dW + L.g_w1, L.in);
-    rowsum_accum<HD, S, NT>(t.D1, SP, HID, t.dW + L.g_b1);
-    if (want_dx) __syncthreads();
-  }
-  if (want_dx) gemm_dx<HD, S, NT>(t.W + L.o_w1, HD == 64 ? t.W + L.o_w1l : nullptr, t.D1, L.obs, t.X, XS);
-  __syncthreads();
 }
 
 }  // namespace gops
