@@ -77,9 +77,11 @@ struct IdpAux {
 };
 
 __device__ __forceinline__ void idp_eval(const float* s, float u, const IdpC& c, IdpAux& q) {
-  sincosf(s[1], &q.s1, &q.c1);
-  sincosf(s[2], &q.s2, &q.c2);
-  sincosf(s[1] - s[2], &q.s12, &q.c12);
+  // pendulum angles stay within a few radians: the MUFU sine/cosine (abs. error ~5e-7 on [-pi, pi]) is inside
+  // the fp32 noise of the reference here; the parity tests (loss 1e-4, gradient 2e-4, exact termination step) gate it
+  __sincosf(s[1], &q.s1, &q.c1);
+  __sincosf(s[2], &q.s2, &q.c2);
+  __sincosf(s[1] - s[2], &q.s12, &q.c12);
   const float a = c.A, b = c.Bc * q.c1, cc = c.Cc * q.c2, d = c.D, e = c.E * q.c12, f = c.F;
   const float v1 = s[4], v2 = s[5];
   const float f0 = (c.Bc * (v1 * v1)) * q.s1 + (c.Cc * (v2 * v2)) * q.s2 + u;
