@@ -34,6 +34,8 @@ class PlanDesc(C.Structure):
         ("action_scale", C.c_int32), ("clip_action", C.c_int32), ("clip_obs", C.c_int32),
         ("mask_at_done", C.c_int32), ("reward_shaping", C.c_int32),
         ("reward_shift", C.c_float), ("reward_scale", C.c_float),
+        ("obs_scaling", C.c_int32), ("obs_scale", C.POINTER(C.c_float)), ("obs_shift", C.POINTER(C.c_float)),
+        ("repeat_num", C.c_int32), ("sum_reward", C.c_int32),
         ("min_action", C.c_float * MAX_ACT), ("max_action", C.c_float * MAX_ACT),
         ("act_low", C.c_float * MAX_ACT), ("act_high", C.c_float * MAX_ACT),
         ("pol_act_low", C.c_float * MAX_ACT), ("pol_act_high", C.c_float * MAX_ACT),

@@ -98,8 +98,8 @@ class RolloutPlan:
         desc.policy = policy.mlp_desc()
         if value is not None:
             desc.value = value.mlp_desc()
-        fill_plan_desc(desc, envmodel, policy.act_low_lim.detach().cpu().numpy(),
-                       policy.act_high_lim.detach().cpu().numpy())
+        keep = fill_plan_desc(desc, envmodel, policy.act_low_lim.detach().cpu().numpy(),   # noqa: F841 (keeps arrays alive)
+                              policy.act_high_lim.detach().cpu().numpy())
         self.handle = C.c_void_p()
         _lib.check(_lib.lib().gops_b200_plan_create(C.byref(desc), C.byref(self.handle)))
         _lib.check(_lib.lib().gops_b200_plan_set_gamma(self.handle, float(gamma)))

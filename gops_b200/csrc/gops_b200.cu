@@ -135,6 +135,7 @@ struct gops_b200_plan {
   size_t ext_ref_floats = 0;
   float* xbuf = nullptr;
   size_t xbuf_floats = 0;
+  float* osc = nullptr;   // obs scale | shift, 2 * obs_dim floats
   bool attr_set[4][4] = {};   // [alg][cfg]
   bool timing = false;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -187,7 +188,7 @@ int ensure_scratch(gops_b200_plan* pl, int grid, int NT, int H) {
   if (pl->desc.model == GOPS_MODEL_VEH3DOFCONTI) {
     const size_t need = (size_t)grid * (pl->kp.veh_P + 1 + H) * 4 * NT;
     if (need > pl->ext_ref_floats) {
-      if (pl->ext_ref) cudaFree(pl->ext_ref); cudaFree(pl->xbuf);
+      if (pl->ext_ref) cudaFree(pl->ext_ref); cudaFree(pl->xbuf); cudaFree(pl->osc);
       pl->ext_ref = nullptr;
       CUDA_OK(cudaMalloc(&pl->ext_ref, need * sizeof(float)));
       CUDA_OK(cudaMemset(pl->ext_ref, 0, need * sizeof(float)));
@@ -334,6 +335,15 @@ int gops_b200_plan_create(const gops_b200_plan_desc* d, gops_b200_plan** out) {
   kp.dw_floats = round4(kp.pol.nparam > kp.val.nparam ? kp.pol.nparam : kp.val.nparam);
   kp.action_scale = d->action_scale; kp.clip_action = d->clip_action; kp.mask_at_done = d->mask_at_done;
   kp.reward_shaping = d->reward_shaping; kp.reward_shift = d->reward_shift; kp.reward_scale = d->reward_scale;
+  kp.obs_scaling = d->obs_scaling ? 1 : 0;
+  kp.repeat_num = d->repeat_num > 0 ? d->repeat_num : 0;
+  kp.sum_reward = d->sum_reward ? 1 : 0;
+  if (kp.repeat_num > 0 && !(d->model == GOPS_MODEL_IDPENDULUM || d->model == GOPS_MODEL_LQ)) {
+    delete pl;
+    return fail("repeat_num (ActionRepeat) is supported for state==obs models only (not built for vehicle models)");
+  }
+  if (kp.repeat_num > 16) { delete pl; return fail("repeat_num > 16 not supported"); }
+  if (kp.obs_scaling && (!d->obs_scale || !d->obs_shift)) { delete pl; return fail("obs_scaling without obs_scale/obs_shift arrays"); }
   bool finite_obs_bound = false;
   for (int j = 0; j < MAXA; ++j) {
     kp.min_action[j] = d->min_action[j]; kp.max_action[j] = d->max_action[j];
@@ -397,6 +407,14 @@ int gops_b200_plan_create(const gops_b200_plan_desc* d, gops_b200_plan** out) {
     return fail("cudaMalloc failed for plan scratch");
   }
   cudaMemcpy(pl->gpow, gp.data(), gp.size() * sizeof(float), cudaMemcpyHostToDevice);
+  if (kp.obs_scaling) {
+    const int od = d->policy.in_dim;
+    if (cudaMalloc(&pl->osc, 2 * od * sizeof(float)) != cudaSuccess) { gops_b200_plan_destroy(pl); return fail("cudaMalloc failed"); }
+    cudaMemcpy(pl->osc, d->obs_scale, od * sizeof(float), cudaMemcpyHostToDevice);
+    cudaMemcpy(pl->osc + od, d->obs_shift, od * sizeof(float), cudaMemcpyHostToDevice);
+    kp.osc = pl->osc;
+    kp.osh = pl->osc + od;
+  }
   cudaMemset(pl->blob_pol, 0, kp.w_floats * sizeof(float));
   cudaMemset(pl->blob_val, 0, kp.w_floats * sizeof(float));
   cudaMemset(pl->blob_vtg, 0, kp.w_floats * sizeof(float));
@@ -442,7 +460,7 @@ int gops_b200_plan_destroy(gops_b200_plan* pl) {
   if (!pl) return 0;
   if (pl->ev0) { cudaEventDestroy(pl->ev0); cudaEventDestroy(pl->ev1); }
   cudaFree(pl->gpow); cudaFree(pl->blob_pol); cudaFree(pl->blob_val); cudaFree(pl->blob_vtg);
-  cudaFree(pl->tape); cudaFree(pl->partial); cudaFree(pl->ext_ref); cudaFree(pl->xbuf);
+  cudaFree(pl->tape); cudaFree(pl->partial); cudaFree(pl->ext_ref); cudaFree(pl->xbuf); cudaFree(pl->osc);
   delete pl;
   return 0;
 }

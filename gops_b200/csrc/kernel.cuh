@@ -164,24 +164,47 @@ __global__ void __launch_bounds__(NT, 1) rollout_kernel(const __grid_constant__ 
         process_action(p, P.out, z, a, g, apol);
         const bool active = valid && (p.mask_at_done ? !dn : true);
         float r = 0.f;
-        if (active) {
-          bool md;
-          if constexpr (M::KIND == 0) {
-            M::step(p, st, a, r, md);
-            if (p.clip_obs) {
-#pragma unroll
-              for (int f = 0; f < NS; ++f) st[f] = fminf(fmaxf(st[f], p.obs_low[f]), p.obs_high[f]);
-            }
+        if constexpr (M::KIND == 0) {
+          // state==obs models: `st` is the wrapper-level (outer) observation; ScaleObservation maps it to the
+          // model's inner state and back, ActionRepeat repeats the masked model step with the same action
+          if (valid) {
+            float in[NS];
 #pragma unroll
             for (int f = 0; f < NS; ++f)
-              if (f < obs_dim) t.X[f * XS + col] = st[f];
+              in[f] = (p.obs_scaling && f < obs_dim) ? st[f] / p.osc[f] - p.osh[f] : st[f];
+            if (active) {
+              bool md = false;
+              const int reps = p.repeat_num > 0 ? p.repeat_num : 1;
+              float rsum = 0.f, rj = 0.f;
+              for (int j = 0; j < reps; ++j) {
+                M::step(p, in, a, rj, md);
+                rsum += rj;
+              }
+              r = (p.repeat_num > 0 && p.sum_reward) ? rsum : rj;
+              dn = md;
+            }
+#pragma unroll
+            for (int f = 0; f < NS; ++f) {
+              float o = (p.obs_scaling && f < obs_dim) ? (in[f] + p.osh[f]) * p.osc[f] : in[f];
+              if (p.clip_obs) o = fminf(fmaxf(o, p.obs_low[f]), p.obs_high[f]);
+              st[f] = o;
+              if (f < obs_dim) t.X[f * XS + col] = o;
+            }
+          }
+        }
+        if (M::KIND != 0 && active) {
+          bool md;
+          if constexpr (M::KIND == 0) {
           } else {
             const VehC vc = veh_const();
             float o6[6];
             if constexpr (M::KIND == 1) {
               // reward from the INCOMING observation (Veh3dofcontiModel.compute_reward :161-177)
 #pragma unroll
-              for (int f = 0; f < 6; ++f) o6[f] = t.X[f * XS + col];
+              for (int f = 0; f < 6; ++f) {
+                o6[f] = t.X[f * XS + col];
+                if (p.obs_scaling) o6[f] = o6[f] / p.osc[f] - p.osh[f];
+              }
               r = -(0.04f * (o6[0] * o6[0]) + 0.04f * (o6[1] * o6[1]) + 0.02f * (o6[2] * o6[2]) +
                     0.02f * (o6[3] * o6[3]) + 0.01f * (o6[5] * o6[5]) + 0.01f * (a[0] * a[0]) + 0.01f * (a[1] * a[1]));
               veh_step(vc, st, a);
@@ -194,6 +217,7 @@ __global__ void __launch_bounds__(NT, 1) rollout_kernel(const __grid_constant__ 
               nr[3 * NT] = rt_u(p.rt, tq, spd);
               win.k0 = k + 1;
               veh_write_obs<M::KIND, NT>(st, win, p.veh_P, t.X + col, XS, o6);
+              if (p.obs_scaling) veh_scale_obs(p, obs_dim, t.X + col, XS);
               md = (fabsf(o6[0]) > 10.f) || (fabsf(o6[1]) > 10.f) || (fabsf(o6[2]) > 3.14159265358979323846f);
             } else {
               // reward from the CURRENT state against reference[:, t] (veh3dof_tracking_model.py:59-73)
@@ -206,6 +230,7 @@ __global__ void __launch_bounds__(NT, 1) rollout_kernel(const __grid_constant__ 
               veh_step(vc, st, a);
               win.k0 = p.ref_t + k + 1;
               veh_write_obs<M::KIND, NT>(st, win, p.veh_P, t.X + col, XS, o6);
+              if (p.obs_scaling) veh_scale_obs(p, obs_dim, t.X + col, XS);
               win.get(0, q);
               md = (fabsf(st[0] - q[0]) > 5.f) || (fabsf(st[1] - q[1]) > 2.f) ||
                    (fabsf(angle_normalize(st[2] - q[2])) > 3.14159265358979323846f);
@@ -264,7 +289,7 @@ __global__ void __launch_bounds__(NT, 1) rollout_kernel(const __grid_constant__ 
             // o_n = get_obs(state_n, window_n): pull the value gradient back onto the robot state
             const float zero6[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
             win.k0 = (M::KIND == 1 ? 0 : p.ref_t) + H;
-            veh_obs_bwd<M::KIND, NT>(st, win, p.veh_P, t.X + col, XS, zero6, lam);
+            veh_obs_bwd<M::KIND, NT>(st, win, p.veh_P, t.X + col, XS, zero6, p.obs_scaling ? p.osc : nullptr, lam);
           }
         }
       }
@@ -322,15 +347,24 @@ __global__ void __launch_bounds__(NT, 1) rollout_kernel(const __grid_constant__ 
         if (k > 0) {
           // only samples that were live at step k have a fully written window; the others get zeros
           // (their deltas are zero anyway, but 0 * garbage must never reach the weight gradients)
-          if (valid && !(p.mask_at_done && dnk)) veh_write_obs<M::KIND, NT>(st, win, p.veh_P, t.X + col, XS, o6);
-          else {
+          if (valid && !(p.mask_at_done && dnk)) {
+            veh_write_obs<M::KIND, NT>(st, win, p.veh_P, t.X + col, XS, o6);
+            if (p.obs_scaling) {
+              veh_scale_obs(p, obs_dim, t.X + col, XS);
+#pragma unroll
+              for (int f = 0; f < 6; ++f) o6[f] = t.X[f * XS + col] / p.osc[f] - p.osh[f];   // as the forward sweep saw it
+            }
+          } else {
             for (int f = 0; f < obs_dim; ++f) t.X[f * XS + col] = 0.f;
 #pragma unroll
             for (int f = 0; f < 6; ++f) o6[f] = 0.f;
           }
         } else {
 #pragma unroll
-          for (int f = 0; f < 6; ++f) o6[f] = t.X[f * XS + col];
+          for (int f = 0; f < 6; ++f) {
+            o6[f] = t.X[f * XS + col];
+            if (p.obs_scaling) o6[f] = o6[f] / p.osc[f] - p.osh[f];
+          }
         }
       }
       if (P.time_input) t.X[(P.in - 1) * XS + col] = (float)(k + 1);
@@ -351,17 +385,49 @@ __global__ void __launch_bounds__(NT, 1) rollout_kernel(const __grid_constant__ 
 #pragma unroll
           for (int j = 0; j < MAXA; ++j) abar[j] = 0.f;
           if constexpr (M::KIND == 0) {
-            if (p.clip_obs) {
-              float nx[NS], r;
+            // lam = adjoint of the OUTER observation obs_{k+1}.  Chain of step k:
+            //   obs_k -(1/scale, -shift)-> inner_0 -[model step x reps, same action]-> inner_reps
+            //         -(+shift, *scale)-> clip -> obs_{k+1}
+            const int reps = p.repeat_num > 0 ? p.repeat_num : 1;
+            float in0[NS], cur[NS];
+#pragma unroll
+            for (int f = 0; f < NS; ++f)
+              in0[f] = (p.obs_scaling && f < obs_dim) ? st[f] / p.osc[f] - p.osh[f] : st[f];
+            if (p.clip_obs) {            // clip passes gradient only where the raw next observation is inside
+              float rr;
               bool md;
 #pragma unroll
-              for (int f = 0; f < NS; ++f) nx[f] = st[f];
-              M::step(p, nx, a, r, md);
+              for (int f = 0; f < NS; ++f) cur[f] = in0[f];
+              for (int j = 0; j < reps; ++j) M::step(p, cur, a, rr, md);
+#pragma unroll
+              for (int f = 0; f < NS; ++f) {
+                const float o = (p.obs_scaling && f < obs_dim) ? (cur[f] + p.osh[f]) * p.osc[f] : cur[f];
+                if (o < p.obs_low[f] || o > p.obs_high[f]) lam[f] = 0.f;
+              }
+            }
+            if (p.obs_scaling) {
 #pragma unroll
               for (int f = 0; f < NS; ++f)
-                if (nx[f] < p.obs_low[f] || nx[f] > p.obs_high[f]) lam[f] = 0.f;
+                if (f < obs_dim) lam[f] *= p.osc[f];
             }
-            M::step_bwd(p, st, a, rho, lam, abar);
+            for (int j = reps - 1; j >= 0; --j) {
+              float rr, aj[MAXA];
+              bool md;
+#pragma unroll
+              for (int f = 0; f < NS; ++f) cur[f] = in0[f];
+              for (int q = 0; q < j; ++q) M::step(p, cur, a, rr, md);      // state before repeat j
+              const float rho_j = (p.repeat_num == 0 || p.sum_reward || j == reps - 1) ? rho : 0.f;
+#pragma unroll
+              for (int q = 0; q < MAXA; ++q) aj[q] = 0.f;
+              M::step_bwd(p, cur, a, rho_j, lam, aj);
+#pragma unroll
+              for (int q = 0; q < MAXA; ++q) abar[q] += aj[q];
+            }
+            if (p.obs_scaling) {
+#pragma unroll
+              for (int f = 0; f < NS; ++f)
+                if (f < obs_dim) lam[f] /= p.osc[f];
+            }
           } else {
             const VehC vc = veh_const();
             veh_step_bwd(vc, st, a, lam, abar);
@@ -401,7 +467,7 @@ __global__ void __launch_bounds__(NT, 1) rollout_kernel(const __grid_constant__ 
           for (int f = 0; f < NS; ++f)
             if (f < obs_dim) lam[f] += t.X[f * XS + col];
         } else {
-          veh_obs_bwd<M::KIND, NT>(st, win, p.veh_P, t.X + col, XS, ro6, lam);
+          veh_obs_bwd<M::KIND, NT>(st, win, p.veh_P, t.X + col, XS, ro6, p.obs_scaling ? p.osc : nullptr, lam);
         }
       }
     }
@@ -518,19 +584,27 @@ __global__ void model_step_kernel(const __grid_constant__ KParams p, const float
     a[j] = j < act_dim ? wrap_action(p, j, action[gs * act_dim + j], gg) : 0.f;
   }
   const bool dn = p.done[gs] != 0.f;
-  float r;
-  bool md;
-  M::step(p, st, a, r, md);
-  if (p.mask_at_done && dn) {
-    r = 0.f;
+  float r = 0.f;
+  bool md = false;
 #pragma unroll
-    for (int f = 0; f < NS; ++f) st[f] = old[f];
+  for (int f = 0; f < NS; ++f)
+    if (p.obs_scaling && f < obs_dim) st[f] = st[f] / p.osc[f] - p.osh[f];
+  if (!(p.mask_at_done && dn)) {
+    const int reps = p.repeat_num > 0 ? p.repeat_num : 1;
+    float rsum = 0.f, rj = 0.f;
+    for (int j = 0; j < reps; ++j) {
+      M::step(p, st, a, rj, md);
+      rsum += rj;
+    }
+    r = (p.repeat_num > 0 && p.sum_reward) ? rsum : rj;
   }
+  (void)old;
   if (p.mask_at_done) md = md || dn;
   if (p.reward_shaping) r = (r + p.reward_shift) * p.reward_scale;
-  if (p.clip_obs) {
 #pragma unroll
-    for (int f = 0; f < NS; ++f) st[f] = fminf(fmaxf(st[f], p.obs_low[f]), p.obs_high[f]);
+  for (int f = 0; f < NS; ++f) {
+    if (p.obs_scaling && f < obs_dim) st[f] = (st[f] + p.osh[f]) * p.osc[f];
+    if (p.clip_obs) st[f] = fminf(fmaxf(st[f], p.obs_low[f]), p.obs_high[f]);
   }
   for (int f = 0; f < obs_dim; ++f) next_obs[gs * obs_dim + f] = st[f];
   reward[gs] = r;

@@ -283,19 +283,26 @@ __device__ __forceinline__ void veh_write_obs(const float* s, const RefWindow<KI
   }
 }
 
+// ScaleObservationModel on a freshly written observation column: obs <- (obs + shift) * scale
+__device__ __forceinline__ void veh_scale_obs(const KParams& p, int obs_dim, float* col, int ld) {
+  for (int f = 0; f < obs_dim; ++f) col[f * ld] = (col[f * ld] + p.osh[f]) * p.osc[f];
+}
+
 // adjoint of get_obs w.r.t. the robot state: lam[0..5] += O^T xbar, xbar read from column `col` of X;
 // extra6 = additional adjoint on the first 6 observation entries (reward-on-observation term)
 template <int KIND, int NT>
 __device__ __forceinline__ void veh_obs_bwd(const float* s, const RefWindow<KIND, NT>& w, int P, const float* col,
-                                            int ld, const float* extra6, float* lam) {
+                                            int ld, const float* extra6, const float* osc, float* lam) {
   float sn, cs;
   sincosf(-s[2], &sn, &cs);
   float bx = 0.f, by = 0.f, bphi = 0.f, bu = 0.f;
   for (int i = 0; i <= P; ++i) {
     float q[4];
     w.get(i, q);
-    const float* c = col + (i == 0 ? 0 : (6 + 4 * (i - 1))) * ld;
+    const int f0 = i == 0 ? 0 : (6 + 4 * (i - 1));
+    const float* c = col + f0 * ld;
     float ox = c[0], oy = c[ld], op = c[2 * ld], ou = c[3 * ld];
+    if (osc != nullptr) { ox *= osc[f0]; oy *= osc[f0 + 1]; op *= osc[f0 + 2]; ou *= osc[f0 + 3]; }   // outer -> inner
     if (i == 0) { ox += extra6[0]; oy += extra6[1]; op += extra6[2]; ou += extra6[3]; }
     const float dx = q[0] - s[0], dy = q[1] - s[1];
     const float vx = dx * cs - dy * sn, vy = dx * sn + dy * cs;   // the forward observation entries
@@ -305,8 +312,8 @@ __device__ __forceinline__ void veh_obs_bwd(const float* s, const RefWindow<KIND
     bu += -ou;
   }
   lam[0] += bx; lam[1] += by; lam[2] += bphi; lam[3] += bu;
-  lam[4] += col[4 * ld] + extra6[4];
-  lam[5] += col[5 * ld] + extra6[5];
+  lam[4] += col[4 * ld] * (osc != nullptr ? osc[4] : 1.f) + extra6[4];
+  lam[5] += col[5 * ld] * (osc != nullptr ? osc[5] : 1.f) + extra6[5];
 }
 
 }  // namespace gops

@@ -83,6 +83,9 @@ struct KParams {
   // wrappers
   int action_scale, clip_action, clip_obs, mask_at_done, reward_shaping;
   float reward_shift, reward_scale;
+  int obs_scaling, repeat_num, sum_reward;   // ScaleObservation / ActionRepeat (repeat_num 0 = absent)
+  const float* osc;        // device arrays [obs_dim]: observation scale / shift
+  const float* osh;
   float min_action[MAXA], max_action[MAXA], act_low[MAXA], act_high[MAXA];
   float pol_half[MAXA], pol_mid[MAXA];
   float obs_low[LQN], obs_high[LQN];

@@ -15,7 +15,8 @@ from gops_b200 import _lib
 
 def collect_chain(top) -> dict:
     cfg = dict(action_scale=0, clip_action=0, clip_obs=0, mask_at_done=0, reward_shaping=0,
-               reward_shift=0.0, reward_scale=1.0, min_action=None, max_action=None)
+               reward_shift=0.0, reward_scale=1.0, min_action=None, max_action=None,
+               obs_scaling=0, obs_scale=None, obs_shift=None, repeat_num=0, sum_reward=1)
     m = top
     while hasattr(m, "model"):
         m.describe(cfg)
@@ -47,6 +48,14 @@ def fill_plan_desc(desc: _lib.PlanDesc, top, policy_low, policy_high):
     _fill(desc.max_action, cfg["max_action"] if cfg["max_action"] is not None else np.ones(na), na)
     _fill(desc.pol_act_low, policy_low if policy_low is not None else -np.ones(na), na)
     _fill(desc.pol_act_high, policy_high if policy_high is not None else np.ones(na), na)
+    desc.repeat_num, desc.sum_reward = int(cfg["repeat_num"]), int(cfg["sum_reward"])
+    desc.obs_scaling = int(cfg["obs_scaling"])
+    if cfg["obs_scaling"]:
+        n = base.obs_dim
+        sc = (C.c_float * n)(*[float(v) for v in cfg["obs_scale"]])
+        sh = (C.c_float * n)(*[float(v) for v in cfg["obs_shift"]])
+        desc.obs_scale, desc.obs_shift = C.cast(sc, C.POINTER(C.c_float)), C.cast(sh, C.POINTER(C.c_float))
+        cfg["_keepalive"] = (sc, sh)      # the C side copies the arrays during plan_create
     base.fill_plan_desc(desc)
     return cfg
 
@@ -61,7 +70,7 @@ class _StepPlan:
         desc = _lib.PlanDesc()
         desc.alg, desc.horizon, desc.gamma = _lib.ALG_FHADP, 1, 1.0
         desc.policy = _dummy_mlp(base.obs_dim, base.action_dim)
-        fill_plan_desc(desc, top, None, None)
+        keep = fill_plan_desc(desc, top, None, None)
         self.handle = C.c_void_p()
         _lib.check(_lib.lib().gops_b200_plan_create(C.byref(desc), C.byref(self.handle)))
 

@@ -85,6 +85,11 @@ typedef struct gops_b200_plan_desc {
   int32_t mask_at_done;      /* MaskAtDoneModel    wrapper/mask_at_done.py:26-40                 */
   int32_t reward_shaping;    /* ShapingRewardModel wrapper/shaping_reward.py:77-88               */
   float reward_shift, reward_scale;
+  int32_t obs_scaling;       /* ScaleObservationModel wrapper/scale_observation.py:104-116       */
+  const float* obs_scale;    /* HOST arrays of obs_dim floats (copied at plan creation) or NULL   */
+  const float* obs_shift;
+  int32_t repeat_num;        /* ActionRepeatModel wrapper/action_repeat.py:71-87 (0 = absent);   */
+  int32_t sum_reward;        /*   state==obs models only                                         */
   float min_action[GOPS_B200_MAX_ACT], max_action[GOPS_B200_MAX_ACT];
   float act_low[GOPS_B200_MAX_ACT], act_high[GOPS_B200_MAX_ACT];         /* model action bounds  */
   float pol_act_low[GOPS_B200_MAX_ACT], pol_act_high[GOPS_B200_MAX_ACT]; /* policy tanh limits   */

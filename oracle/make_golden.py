@@ -154,6 +154,31 @@ def main():
     kw = base_kwargs("pyth_idpendulum", "INFADP", 6, 1, (64, 64), "relu", "DetermPolicy", reward_scale=1.0)
     run_case("infadp_idp", kw, orc.sample_inputs("pyth_idpendulum", 256, 16), [0, 1])
 
+    # optional wrappers of the chain: ScaleObservation, ActionRepeat (create_env_model.py:109-122)
+    scale6 = [0.5, 2.0, 2.0, 1.0, 0.25, 0.5]
+    shift6 = [0.1, 0.0, -0.05, 0.0, 0.2, 0.0]
+    kw = base_kwargs("pyth_idpendulum", "FHADP", 6, 1, (64, 64), "gelu", "FiniteHorizonPolicy", pre_horizon=15,
+                     reward_scale=0.2, obs_scale=scale6, obs_shift=shift6)
+    d = orc.sample_inputs("pyth_idpendulum", 128, 31)
+    d["obs"] = (d["obs"] + torch.tensor(shift6)) * torch.tensor(scale6)
+    d["done"][::5] = 1.0
+    run_case("fhadp_idp_obsscale", kw, d, [0])
+    kw = base_kwargs("pyth_lq", "INFADP", 4, 2, (64, 64), "tanh", "DetermPolicy", lq_config="s4a2", reward_scale=0.1,
+                     obs_scale=[2.0, 0.5, 1.5, 1.0], repeat_num=3)
+    d = orc.sample_inputs("pyth_lq", 128, 32, lq_config="s4a2")
+    d["obs"] = d["obs"] * torch.tensor([2.0, 0.5, 1.5, 1.0]) * 6.0       # wide enough for ClipObservation to bite
+    run_case("infadp_lq_obsscale_repeat3", kw, d, [0, 1])
+    kw = base_kwargs("pyth_idpendulum", "FHADP", 6, 1, (64, 64), "elu", "FiniteHorizonPolicy", pre_horizon=6,
+                     reward_scale=1.0, repeat_num=2, sum_reward=False)
+    run_case("fhadp_idp_repeat2_last", kw, orc.sample_inputs("pyth_idpendulum", 128, 33), [0])
+    sc46 = (1.0 + 0.5 * torch.rand(46, generator=torch.Generator().manual_seed(7))).tolist()
+    sh46 = (0.2 * torch.rand(46, generator=torch.Generator().manual_seed(8)) - 0.1).tolist()
+    kw = base_kwargs("pyth_veh3dofconti", "INFADP", 46, 2, (64, 64), "relu", "DetermPolicy", pre_horizon=10,
+                     obs_scale=sc46, obs_shift=sh46)
+    d = orc.sample_inputs("pyth_veh3dofconti", 128, 34, pre_horizon=10)
+    d["obs"] = (d["obs"] + torch.tensor(sh46)) * torch.tensor(sc46)
+    run_case("infadp_veh3dofconti_obsscale", kw, d, [0, 1])
+
     # C2: INFADP veh3dofconti [64,64] relu, P=10 (infadp_mlp_veh3dofconti_offserial.py:34-81)
     kw = base_kwargs("pyth_veh3dofconti", "INFADP", 46, 2, (64, 64), "relu", "DetermPolicy", pre_horizon=10)
     run_case("infadp_veh3dofconti", kw, orc.sample_inputs("pyth_veh3dofconti", 256, 17, pre_horizon=10), [0, 1])

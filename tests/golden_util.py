@@ -14,6 +14,9 @@ from oracle import gops_oracle as orc  # noqa: E402
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
+_SC46 = (1.0 + 0.5 * torch.rand(46, generator=torch.Generator().manual_seed(7))).tolist()
+_SH46 = (0.2 * torch.rand(46, generator=torch.Generator().manual_seed(8)) - 0.1).tolist()
+
 # name -> (env_id, algorithm, hidden_act, model kwargs, wrapper kwargs, alg kwargs)
 CASES = {
     "fhadp_idp_h30": ("pyth_idpendulum", "FHADP", "gelu", {}, dict(reward_scale=1.0), dict(pre_horizon=30)),
@@ -31,6 +34,15 @@ CASES = {
     "fhadp_veh3dofconti_p12": ("pyth_veh3dofconti", "FHADP", "elu", dict(pre_horizon=12), {}, dict(pre_horizon=12)),
     "fhadp_veh3dof_tracking_p10": ("veh3dof_tracking", "FHADP", "elu", dict(pre_horizon=10), {}, dict(pre_horizon=10)),
     "fhadp_veh3dof_tracking_p60_w256": ("veh3dof_tracking", "FHADP", "elu", dict(pre_horizon=60), {}, dict(pre_horizon=60)),
+    "fhadp_idp_obsscale": ("pyth_idpendulum", "FHADP", "gelu", {},
+                           dict(reward_scale=0.2, obs_scale=[0.5, 2.0, 2.0, 1.0, 0.25, 0.5],
+                                obs_shift=[0.1, 0.0, -0.05, 0.0, 0.2, 0.0]), dict(pre_horizon=15)),
+    "infadp_lq_obsscale_repeat3": ("pyth_lq", "INFADP", "tanh", dict(lq_config="s4a2"),
+                                   dict(reward_scale=0.1, obs_scale=[2.0, 0.5, 1.5, 1.0], repeat_num=3), {}),
+    "fhadp_idp_repeat2_last": ("pyth_idpendulum", "FHADP", "elu", {},
+                               dict(reward_scale=1.0, repeat_num=2, sum_reward=False), dict(pre_horizon=6)),
+    "infadp_veh3dofconti_obsscale": ("pyth_veh3dofconti", "INFADP", "relu", dict(pre_horizon=10),
+                                     dict(obs_scale=_SC46, obs_shift=_SH46), {}),
 }
 DEFAULT_LR = {"fhadp_idp_h30": 1e-4, "fhadp_idp_h80": 1e-4, "fhadp_idp_trained_h80": 1e-4}
 

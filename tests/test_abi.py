@@ -76,5 +76,7 @@ def test_wrapper_chain_order_matches_reference():
     cfg = collect_chain(m)
     assert cfg["reward_scale"] == 0.5 and cfg["mask_at_done"] == 1 and cfg["clip_obs"] == 1
     assert m.action_lower_bound.tolist() == [-1.0, -1.0] and m.unwrapped.action_upper_bound.tolist() == [8.0, 8.0]
-    with pytest.raises(NotImplementedError):
-        create_env_model("pyth_lq", repeat_num=2)
+    m2 = create_env_model("pyth_lq", lq_config="s4a2", repeat_num=2, obs_scale=[1.0, 2.0, 1.0, 0.5])
+    cfg2 = collect_chain(m2)
+    assert cfg2["repeat_num"] == 2 and cfg2["obs_scaling"] == 1 and list(cfg2["obs_scale"]) == [1.0, 2.0, 1.0, 0.5]
+    assert list(cfg2["obs_shift"]) == [0.0] * 4
