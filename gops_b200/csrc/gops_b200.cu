@@ -31,6 +31,21 @@ int fail(const std::string& msg) {
       return fail(std::string(#expr) + ": " + cudaGetErrorString(e__));                        \
   } while (0)
 
+#define CUDA_OK_L(expr, label)                                                                 \
+  do {                                                                                         \
+    cudaError_t e__ = (expr);                                                                  \
+    if (e__ != cudaSuccess)                                                                    \
+      return fail(std::string(label) + " " + #expr + ": " + cudaGetErrorString(e__));          \
+  } while (0)
+
+// A CUDA error left behind by an earlier (possibly foreign) call must not be blamed on the next launch.
+#define ENTRY(name)                                                                            \
+  do {                                                                                         \
+    cudaError_t e0__ = cudaGetLastError();                                                     \
+    if (e0__ != cudaSuccess && getenv("GOPS_B200_DEBUG"))                                      \
+      fprintf(stderr, "[gops_b200] stale CUDA error at entry of %s: %s\n", name, cudaGetErrorString(e0__)); \
+  } while (0)
+
 int round4(int x) { return (x + 3) & ~3; }
 
 bool make_net(const gops_b200_mlp_desc& d, NetL& L, std::string& why) {
@@ -217,7 +232,7 @@ int ensure_scratch(gops_b200_plan* pl, int grid, int NT, int H) {
 
 int launch_pack(const float* flat, const NetL& L, int hid, float* blob, cudaStream_t st) {
   pack_params_kernel<<<hid > 64 ? 64 : 8, 256, 0, st>>>(flat, L, hid, blob);
-  CUDA_OK(cudaGetLastError());
+  CUDA_OK_L(cudaGetLastError(), "launch#1");
   return 0;
 }
 
@@ -267,14 +282,14 @@ int launch_rollout(gops_b200_plan* pl, const gops_b200_batch* b, int alg, cudaSt
   kp.partial = pl->partial;
   if (pl->timing) CUDA_OK(cudaEventRecord(pl->ev0, st));
   fn<<<grid, NT, smem, st>>>(kp);
-  CUDA_OK(cudaGetLastError());
+  CUDA_OK_L(cudaGetLastError(), "launch#2");
   if (pl->timing) CUDA_OK(cudaEventRecord(pl->ev1, st));
   pl->last_grid = grid; pl->last_S = S; pl->last_NT = NT; pl->last_smem = smem;
   if (alg != ALG_TRACE) {
     const int n = upd.nparam + 3;
     reduce_partials_kernel<<<(n + 255) / 256, 256, 0, st>>>(pl->partial, grid, kp.part_stride, upd.nparam, grad_out,
                                                            scalars_out);
-    CUDA_OK(cudaGetLastError());
+    CUDA_OK_L(cudaGetLastError(), "launch#3");
   }
   return 0;
 }
@@ -287,6 +302,7 @@ int gops_b200_version(void) { return GOPS_B200_ABI_VERSION; }
 const char* gops_b200_last_error(void) { return g_err.c_str(); }
 
 int gops_b200_plan_create(const gops_b200_plan_desc* d, gops_b200_plan** out) {
+  ENTRY("gops_b200_plan_create(const gops_b200_pl");
   if (!d || !out) return fail("null argument");
   *out = nullptr;
   if (d->alg < GOPS_ALG_FHADP || d->alg > GOPS_ALG_INFADP_VALUE) return fail("unknown algorithm kind");
@@ -406,12 +422,18 @@ int gops_b200_plan_create(const gops_b200_plan_desc* d, gops_b200_plan** out) {
     gops_b200_plan_destroy(pl);
     return fail("cudaMalloc failed for plan scratch");
   }
-  cudaMemcpy(pl->gpow, gp.data(), gp.size() * sizeof(float), cudaMemcpyHostToDevice);
+  if (cudaMemcpy(pl->gpow, gp.data(), gp.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) {
+    gops_b200_plan_destroy(pl);
+    return fail("cudaMemcpy(gpow) failed");
+  }
   if (kp.obs_scaling) {
     const int od = d->policy.in_dim;
     if (cudaMalloc(&pl->osc, 2 * od * sizeof(float)) != cudaSuccess) { gops_b200_plan_destroy(pl); return fail("cudaMalloc failed"); }
-    cudaMemcpy(pl->osc, d->obs_scale, od * sizeof(float), cudaMemcpyHostToDevice);
-    cudaMemcpy(pl->osc + od, d->obs_shift, od * sizeof(float), cudaMemcpyHostToDevice);
+    if (cudaMemcpy(pl->osc, d->obs_scale, od * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(pl->osc + od, d->obs_shift, od * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) {
+      gops_b200_plan_destroy(pl);
+      return fail("cudaMemcpy(obs scale/shift) failed");
+    }
     kp.osc = pl->osc;
     kp.osh = pl->osc + od;
   }
@@ -457,6 +479,7 @@ int gops_b200_plan_launch_info(const gops_b200_plan* pl, int32_t* out4) {
 }
 
 int gops_b200_plan_destroy(gops_b200_plan* pl) {
+  ENTRY("gops_b200_plan_destroy(gops_b200_plan* p");
   if (!pl) return 0;
   if (pl->ev0) { cudaEventDestroy(pl->ev0); cudaEventDestroy(pl->ev1); }
   cudaFree(pl->gpow); cudaFree(pl->blob_pol); cudaFree(pl->blob_val); cudaFree(pl->blob_vtg);
@@ -473,6 +496,7 @@ int64_t gops_b200_plan_param_count(const gops_b200_plan* pl, int which) {
 int gops_b200_rollout_grad(gops_b200_plan* pl, const gops_b200_batch* b, const float* policy_params,
                            const float* value_params, const float* vtarget_params, float inv_batch_global,
                            float* grad_out, float* scalars_out, void* stream) {
+  ENTRY("float* grad_out, float* scalars_out, voi");
   if (!pl || !policy_params || !grad_out || !scalars_out) return fail("null argument");
   cudaStream_t st = (cudaStream_t)stream;
   const int alg = pl->desc.alg;
@@ -492,6 +516,7 @@ int gops_b200_rollout_grad(gops_b200_plan* pl, const gops_b200_batch* b, const f
 
 int gops_b200_rollout_trace(gops_b200_plan* pl, const gops_b200_batch* b, const float* policy_params, float* obs_out,
                             float* act_out, float* rew_out, float* done_out, void* stream) {
+  ENTRY("float* act_out, float* rew_out, float* d");
   if (!pl || !policy_params) return fail("null argument");
   cudaStream_t st = (cudaStream_t)stream;
   if (launch_pack(policy_params, pl->kp.pol, pl->kp.hid, pl->blob_pol, st)) return 1;
@@ -537,7 +562,7 @@ static int infer_common(gops_b200_plan* pl, const float* params, int use_val, co
   else if (cfg == 1) LAUNCH_INFER(64, 64, 256);
   else LAUNCH_INFER(64, 32, 128);
 #undef LAUNCH_INFER
-  CUDA_OK(cudaGetLastError());
+  CUDA_OK_L(cudaGetLastError(), "launch#4");
   return 0;
 }
 
@@ -554,6 +579,7 @@ int gops_b200_value_forward(gops_b200_plan* pl, const float* value_params, const
 
 int gops_b200_mlp_forward(const gops_b200_mlp_desc* net, const float* params, const float* obs, int64_t batch,
                           float virtual_t, const float* act_low, const float* act_high, float* out, void* stream) {
+  ENTRY("float virtual_t, const float* act_low, c");
   if (!net || !params || !obs || !out) return fail("null argument");
   if (batch <= 0) return fail("empty batch");
   static thread_local gops_b200_plan* scratch = nullptr;   // reusable staging blob per host thread
@@ -597,6 +623,7 @@ int gops_b200_mlp_forward(const gops_b200_mlp_desc* net, const float* params, co
 int gops_b200_model_step(gops_b200_plan* pl, const gops_b200_batch* b, const float* action, float* next_obs,
                          float* reward, float* next_done, float* next_state, float* next_ref_points,
                          float* next_ref_time, void* stream) {
+  ENTRY("float* next_ref_time, void* stream) {");
   if (!pl || !b || !action || !next_obs || !reward || !next_done) return fail("null argument");
   if (b->batch <= 0 || !b->obs || !b->done) return fail("bad batch");
   (void)next_state; (void)next_ref_points; (void)next_ref_time;
@@ -608,12 +635,13 @@ int gops_b200_model_step(gops_b200_plan* pl, const gops_b200_batch* b, const flo
   StepFn fn = step_fn(pl->desc.model);
   if (!fn) return fail("model_step: env model kind not built into this library");
   fn<<<grid, 128, 0, st>>>(kp, action, act_dim, next_obs, reward, next_done);
-  CUDA_OK(cudaGetLastError());
+  CUDA_OK_L(cudaGetLastError(), "launch#5");
   return 0;
 }
 
 int gops_b200_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
                         int32_t step, double lr, double beta1, double beta2, double eps, void* stream) {
+  ENTRY("int32_t step, double lr, double beta1, d");
   if (!params || !grads || !exp_avg || !exp_avg_sq) return fail("null argument");
   if (n <= 0 || step < 1) return fail("bad n/step");
   // python-side scalars of torch/optim/adam.py are doubles; only the tensor math is fp32
@@ -624,14 +652,15 @@ int gops_b200_adam_step(float* params, const float* grads, float* exp_avg, float
   adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       params, grads, exp_avg, exp_avg_sq, n, (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2), (float)eps,
       step_size, bc2_sqrt);
-  CUDA_OK(cudaGetLastError());
+  CUDA_OK_L(cudaGetLastError(), "launch#6");
   return 0;
 }
 
 int gops_b200_polyak(float* target, const float* src, float tau, int64_t n, void* stream) {
+  ENTRY("int gops_b200_polyak(float* target, cons");
   if (!target || !src || n <= 0) return fail("bad argument");
   polyak_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(target, src, tau, n);
-  CUDA_OK(cudaGetLastError());
+  CUDA_OK_L(cudaGetLastError(), "launch#7");
   return 0;
 }
 
