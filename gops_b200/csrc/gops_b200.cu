@@ -203,7 +203,7 @@ int ensure_scratch(gops_b200_plan* pl, int grid, int NT, int H) {
   if (pl->desc.model == GOPS_MODEL_VEH3DOFCONTI) {
     const size_t need = (size_t)grid * (pl->kp.veh_P + 1 + H) * 4 * NT;
     if (need > pl->ext_ref_floats) {
-      if (pl->ext_ref) cudaFree(pl->ext_ref); cudaFree(pl->xbuf); cudaFree(pl->osc);
+      if (pl->ext_ref) cudaFree(pl->ext_ref);
       pl->ext_ref = nullptr;
       CUDA_OK(cudaMalloc(&pl->ext_ref, need * sizeof(float)));
       CUDA_OK(cudaMemset(pl->ext_ref, 0, need * sizeof(float)));
@@ -482,8 +482,20 @@ int gops_b200_plan_destroy(gops_b200_plan* pl) {
   ENTRY("gops_b200_plan_destroy(gops_b200_plan* p");
   if (!pl) return 0;
   if (pl->ev0) { cudaEventDestroy(pl->ev0); cudaEventDestroy(pl->ev1); }
-  cudaFree(pl->gpow); cudaFree(pl->blob_pol); cudaFree(pl->blob_val); cudaFree(pl->blob_vtg);
-  cudaFree(pl->tape); cudaFree(pl->partial); cudaFree(pl->ext_ref); cudaFree(pl->xbuf); cudaFree(pl->osc);
+  void* ptrs[] = {pl->gpow, pl->blob_pol, pl->blob_val, pl->blob_vtg, pl->tape, pl->partial, pl->ext_ref, pl->xbuf, pl->osc};
+  const char* names[] = {"gpow", "blob_pol", "blob_val", "blob_vtg", "tape", "partial", "ext_ref", "xbuf", "osc"};
+  if (getenv("GOPS_B200_DEBUG")) {
+    fprintf(stderr, "[gops_b200] destroy plan %p alg %d model %d:", (void*)pl, pl->desc.alg, pl->desc.model);
+    for (int i = 0; i < 9; ++i) fprintf(stderr, " %s=%p", names[i], ptrs[i]);
+    fprintf(stderr, "\n");
+  }
+  for (int i = 0; i < 9; ++i) {
+    const cudaError_t e = cudaFree(ptrs[i]);
+    if (e != cudaSuccess) {
+      (void)cudaGetLastError();
+      if (getenv("GOPS_B200_DEBUG")) fprintf(stderr, "[gops_b200] cudaFree(%s) failed: %s\n", names[i], cudaGetErrorString(e));
+    }
+  }
   delete pl;
   return 0;
 }
