@@ -307,3 +307,57 @@ def test_policy_forward_matches_checkpoint_known_answer():
     alg._compute_gradient({"obs": obs, "done": torch.zeros(1)})
     got = alg.tb_info["Loss/Actor loss-RL iter"]
     assert abs(got - float(rec["loss_h80"])) < LOSS_RTOL * abs(float(rec["loss_h80"]))
+
+
+@pytest.mark.parametrize("B,H", [(1, 1), (1, 5), (17, 1), (129, 2), (513, 3)])
+def test_edge_shapes_against_oracle(B, H):
+    """Degenerate shapes the reference handles: single sample, horizon 1, batches that straddle tile boundaries."""
+    from gops_b200.create_pkg.create_alg import create_alg
+    kw, _ = make_kwargs("fhadp_idp_h30")
+    kw["pre_horizon"] = H
+    torch.manual_seed(B * 31 + H)
+    alg = create_alg(**kw)
+    data = orc.sample_inputs("pyth_idpendulum", B, seed=7 * B + H)
+    pi = alg.networks.policy.pi
+    layers = [(pi[j].weight.detach().cpu().double().requires_grad_(True),
+               pi[j].bias.detach().cpu().double().requires_grad_(True)) for j in (0, 2, 4)]
+    pol = orc.NetSpec(layers, "gelu", "linear", torch.ones(1, dtype=torch.float64), -torch.ones(1, dtype=torch.float64),
+                      time_input=True)
+    env = orc.create_env_model("pyth_idpendulum", dtype=torch.float64, reward_scale=1.0)
+    loss = orc.fhadp_loss(pol, env, {k: v.double() for k, v in data.items()}, H)
+    loss.backward()
+    alg._compute_gradient(data)
+    got = alg.tb_info["Loss/Actor loss-RL iter"]
+    assert abs(got - loss.item()) <= LOSS_RTOL * max(1.0, abs(loss.item()))
+    got_g = [p.grad.detach().cpu().numpy() for p in alg.networks.policy.parameters()]
+    assert rel_l2(got_g, [p.grad.numpy() for p in pol.params()]) < GRAD_RTOL
+
+
+def test_inputs_are_not_mutated_and_cpu_inputs_accepted():
+    """`data` belongs to the trainer (the reference deep-copies it, fhadp.py:107): host tensors are accepted as they
+    come out of the replay buffer and are left untouched."""
+    alg, rec = build_alg("infadp_veh3dofconti")
+    data = data_from(rec, "pyth_veh3dofconti")
+    before = {k: v.clone() for k, v in data.items()}
+    alg.local_update(data, 0)
+    alg.local_update(data, 1)
+    for k, v in data.items():
+        assert v.device.type == "cpu" and torch.equal(v, before[k]), k
+
+
+def test_unsupported_configurations_raise():
+    from gops_b200.create_pkg.create_alg import create_alg
+    kw, rec = make_kwargs("fhadp_idp_h30")
+    kw["policy_hidden_sizes"] = [64, 32]
+    with pytest.raises(NotImplementedError):
+        create_alg(**kw)
+    kw, rec = make_kwargs("fhadp_idp_h30")
+    kw["policy_hidden_sizes"] = [128, 128]
+    alg = create_alg(**kw)
+    with pytest.raises(RuntimeError, match="not built"):
+        alg.local_update(data_from(rec, "pyth_idpendulum"), 0)
+    kw, rec = make_kwargs("fhadp_veh3dofconti_p12")
+    kw["repeat_num"] = 2
+    alg = create_alg(**kw)
+    with pytest.raises(RuntimeError, match="ActionRepeat"):
+        alg.local_update(data_from(rec, "pyth_veh3dofconti"), 0)
