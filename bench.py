@@ -15,9 +15,9 @@ value : inputs resident in HBM when the timed region starts (a rotating set of i
 e2e   : same call with PINNED HOST tensors -- H2D copy of the batch and D2H read of the loss inside the
         timed region;
 roofline : the fused rollout kernel alone, timed with CUDA events on its launch stream inside the library
-        (gops_b200_plan_enable_timing).  The kernel is FP32-FMA bound by design, so
-        `achieved`/`peak` are algorithmic TFLOP/s against the FP32 FFMA roof at the SM clock sampled
-        during the run; the HBM and tensor (measured bf16) fractions are reported beside it.
+        (gops_b200_plan_enable_timing).  The kernel is compute bound by design: `achieved` is
+        algorithmic TFLOP/s, `peak` the tensor roof for FP32-accurate (3xTF32) GEMMs derived from the measured bf16
+        peak; the FP32-FFMA, HBM and raw bf16 fractions are reported beside it.
 cpu_baseline : the CPU oracle port (oracle/gops_oracle.py, the reference's algorithm in PyTorch-CPU) on a
         bounded sample of the same workload, all host threads.
 """
@@ -263,13 +263,20 @@ def main():
                 traffic = json.load(open(tfile)).get("rollout_kernel_dram_bytes_per_launch")
             except Exception:
                 pass
-        roof = {"bound": "fp32", "achieved": ach_tflops, "peak": fp32_peak, "unit": "TFLOP/s",
-                "frac": ach_tflops / fp32_peak, "traffic": traffic,
-                "peak_source": f"148 SM x 128 lanes x 2 x {sm_mhz:.0f} MHz sampled under load",
+        # Tensor roof for FP32-accurate GEMMs: the MLP layers run as 3xTF32 mma.sync (three TF32 MMAs per product);
+        # TF32 dense peak = measured bf16 peak / 2.  The FP32 FFMA roof is the one SURVEY 8(d) names for a CUDA-core
+        # implementation; both are reported, plus HBM.
+        tf32x3_peak = tens_peak / 2.0 / 3.0
+        roof = {"bound": "tensor", "achieved": ach_tflops, "peak": tf32x3_peak, "unit": "TFLOP/s",
+                "frac": ach_tflops / tf32x3_peak, "traffic": traffic,
+                "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peak_src}) / 2 (TF32) / 3 (3xTF32 split)",
                 "kernel_ms": k_ms, "kernel_share_of_step": k_ms * K / ms_total,
+                "algorithmic_flop_per_env_step": FLOP_PER_ENV_STEP, "algorithmic_bytes_per_env_step": BYTES_PER_ENV_STEP,
+                "fp32_ffma": {"achieved_tflops": ach_tflops, "peak_tflops": fp32_peak, "frac": ach_tflops / fp32_peak,
+                              "of": f"{n_sm} SM x 128 lanes x 2 x {sm_mhz:.0f} MHz sampled under load"},
                 "hbm": {"achieved_gbs": ach_gbs, "peak_gbs": hbm_peak, "frac": ach_gbs / hbm_peak, "of": peak_src},
-                "tensor": {"achieved_tflops": ach_tflops, "peak_tflops": tens_peak, "frac": ach_tflops / tens_peak,
-                           "of": peak_src + " bf16 sustained"},
+                "tensor_bf16": {"achieved_tflops": ach_tflops, "peak_tflops": tens_peak, "frac": ach_tflops / tens_peak,
+                                "of": peak_src + " bf16 sustained"},
                 "launch": {"grid": info[0], "block": info[1], "tile_samples": info[2], "smem_bytes": info[3]}}
         cpu = None
         if not args.no_cpu_baseline:

@@ -638,12 +638,27 @@ int gops_b200_model_step(gops_b200_plan* pl, const gops_b200_batch* b, const flo
   ENTRY("float* next_ref_time, void* stream) {");
   if (!pl || !b || !action || !next_obs || !reward || !next_done) return fail("null argument");
   if (b->batch <= 0 || !b->obs || !b->done) return fail("bad batch");
-  (void)next_state; (void)next_ref_points; (void)next_ref_time;
   KParams& kp = pl->kp;
   kp.batch = b->batch; kp.obs = b->obs; kp.done = b->done;
   const unsigned grid = (unsigned)((b->batch + 127) / 128);
   cudaStream_t st = (cudaStream_t)stream;
   const int act_dim = pl->desc.policy.out_dim;
+  if (pl->desc.model == GOPS_MODEL_VEH3DOFCONTI || pl->desc.model == GOPS_MODEL_VEH3DOF_TRACKING) {
+    const bool conti = pl->desc.model == GOPS_MODEL_VEH3DOFCONTI;
+    if (!b->state || !next_state) return fail("model_step: vehicle models need state and next_state");
+    if (conti && (!b->ref_points || !b->path_num || !b->u_num || !b->ref_time || !next_ref_points || !next_ref_time))
+      return fail("model_step: pyth_veh3dofconti needs ref_points, path_num, u_num, ref_time and their outputs");
+    if (!conti && (!b->reference || b->ref_t < 0 || b->ref_t + kp.veh_P + 2 > b->ref_len))
+      return fail("model_step: veh3dof_tracking reference too short for t + 1 + pre_horizon + 1 points");
+    kp.state = b->state; kp.ref_points = b->ref_points; kp.path_num = b->path_num; kp.u_num = b->u_num;
+    kp.ref_time = b->ref_time; kp.reference = b->reference; kp.ref_t = b->ref_t; kp.ref_len = b->ref_len;
+    if (conti) veh_step_kernel<1><<<grid, 128, 0, st>>>(kp, action, next_obs, reward, next_done, next_state,
+                                                        next_ref_points, next_ref_time);
+    else veh_step_kernel<2><<<grid, 128, 0, st>>>(kp, action, next_obs, reward, next_done, next_state,
+                                                  next_ref_points, next_ref_time);
+    CUDA_OK_L(cudaGetLastError(), "veh_step launch");
+    return 0;
+  }
   StepFn fn = step_fn(pl->desc.model);
   if (!fn) return fail("model_step: env model kind not built into this library");
   fn<<<grid, 128, 0, st>>>(kp, action, act_dim, next_obs, reward, next_done);

@@ -611,4 +611,85 @@ __global__ void model_step_kernel(const __grid_constant__ KParams p, const float
   next_done[gs] = md ? 1.f : 0.f;
 }
 
+
+// envmodel.forward(obs, action, done, info) for the vehicle models (one thread per sample, global memory only).
+// Mirrors Veh3dofcontiModel.forward (pyth_veh3dofconti_model.py:91-145) / EnvModel.forward
+// (env_gen_ocp/env_model/pyth_base_model.py:109-119) inside the wrapper chain: `info` is advanced even for masked
+// (done) samples, exactly like the reference (MaskAtDone does not touch next_info).
+template <int KIND>
+__global__ void veh_step_kernel(const __grid_constant__ KParams p, const float* __restrict__ action,
+                                float* __restrict__ next_obs, float* __restrict__ reward, float* __restrict__ next_done,
+                                float* __restrict__ next_state, float* __restrict__ next_ref_points,
+                                float* __restrict__ next_ref_time) {
+  const long long gs = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gs >= p.batch) return;
+  const int obs_dim = p.pol.obs, P = p.veh_P;
+  const VehC vc = veh_const();
+  float a[MAXA], s[6];
+#pragma unroll
+  for (int j = 0; j < MAXA; ++j) {
+    float gg = 1.f;
+    a[j] = j < 2 ? wrap_action(p, j, action[gs * 2 + j], gg) : 0.f;
+  }
+#pragma unroll
+  for (int f = 0; f < 6; ++f) s[f] = p.state[gs * 6 + f];
+  const bool dn = p.done[gs] != 0.f;
+  const float* obs = p.obs + gs * obs_dim;
+  float* nobs = next_obs + gs * obs_dim;
+  float r;
+  bool md;
+  if (KIND == 1) {
+    float o[6];
+#pragma unroll
+    for (int f = 0; f < 6; ++f) o[f] = p.obs_scaling ? obs[f] / p.osc[f] - p.osh[f] : obs[f];
+    r = -(0.04f * (o[0] * o[0]) + 0.04f * (o[1] * o[1]) + 0.02f * (o[2] * o[2]) + 0.02f * (o[3] * o[3]) +
+          0.01f * (o[5] * o[5]) + 0.01f * (a[0] * a[0]) + 0.01f * (a[1] * a[1]));
+    veh_step(vc, s, a);
+    const float nt = p.ref_time[gs] + vc.dt, tq = nt + p.veh_Pdt;
+    const int path = (int)p.path_num[gs], spd = (int)p.u_num[gs];
+    const float* rp = p.ref_points + gs * (P + 1) * 4;
+    float* nrp = next_ref_points + gs * (P + 1) * 4;
+    for (int i = 0; i < P; ++i)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) nrp[i * 4 + c] = rp[(i + 1) * 4 + c];
+    nrp[P * 4 + 0] = rt_x(p.rt, tq, path, spd);
+    nrp[P * 4 + 1] = rt_y(p.rt, tq, path, spd);
+    nrp[P * 4 + 2] = rt_phi(p.rt, tq, path, spd);
+    nrp[P * 4 + 3] = rt_u(p.rt, tq, spd);
+    next_ref_time[gs] = nt;
+    RefWindow<2, 1> w;             // sample-major [P+1][4] window in global memory
+    w.base = nrp; w.k0 = 0;
+    float o6[6];
+    veh_write_obs<2, 1>(s, w, P, nobs, 1, o6);
+    md = (fabsf(o6[0]) > 10.f) || (fabsf(o6[1]) > 10.f) || (fabsf(o6[2]) > 3.14159265358979323846f);
+  } else {
+    RefWindow<2, 1> w;
+    w.base = p.reference + gs * (size_t)p.ref_len * 4; w.k0 = p.ref_t;
+    float q[4];
+    w.get(0, q);
+    const float ex = s[0] - q[0], ey = s[1] - q[1], ep = angle_normalize(s[2] - q[2]), eu = s[3] - q[3];
+    r = -(0.04f * (ex * ex) + 0.04f * (ey * ey) + 0.02f * (ep * ep) + 0.02f * (eu * eu) + 0.01f * (s[5] * s[5]) +
+          0.01f * (a[0] * a[0]) + 0.01f * (a[1] * a[1]));
+    veh_step(vc, s, a);
+    w.k0 = p.ref_t + 1;
+    float o6[6];
+    veh_write_obs<2, 1>(s, w, P, nobs, 1, o6);
+    w.get(0, q);
+    md = (fabsf(s[0] - q[0]) > 5.f) || (fabsf(s[1] - q[1]) > 2.f) ||
+         (fabsf(angle_normalize(s[2] - q[2])) > 3.14159265358979323846f);
+  }
+#pragma unroll
+  for (int f = 0; f < 6; ++f) next_state[gs * 6 + f] = s[f];
+  if (p.mask_at_done && dn) {     // MaskAtDone: frozen (inner) observation, zero reward
+    r = 0.f;
+    for (int f = 0; f < obs_dim; ++f) nobs[f] = p.obs_scaling ? obs[f] / p.osc[f] - p.osh[f] : obs[f];
+  }
+  if (p.mask_at_done) md = md || dn;
+  if (p.reward_shaping) r = (r + p.reward_shift) * p.reward_scale;
+  if (p.obs_scaling)
+    for (int f = 0; f < obs_dim; ++f) nobs[f] = (nobs[f] + p.osh[f]) * p.osc[f];
+  reward[gs] = r;
+  next_done[gs] = md ? 1.f : 0.f;
+}
+
 }  // namespace gops

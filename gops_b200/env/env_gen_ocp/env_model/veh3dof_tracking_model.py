@@ -37,5 +37,16 @@ class Veh3DoFTrackingModel(PythBaseModel):
         batch.ref_len = int(ref.shape[1])
 
 
+    def alloc_next_info(self, B, dev):
+        return {"state": torch.empty((B, 6), dtype=torch.float32, device=dev)}
+
+    def make_next_info(self, info, extra):
+        st = info["state"]
+        ctx = st.context_state
+        return {"state": State(robot_state=extra["state"].to(st.robot_state.device),
+                               context_state=ContextState(reference=ctx.reference, constraint=ctx.constraint,
+                                                          t=ctx.t + 1))}
+
+
 def env_model_creator(**kwargs) -> Veh3DoFTrackingModel:
     return Veh3DoFTrackingModel(**kwargs)

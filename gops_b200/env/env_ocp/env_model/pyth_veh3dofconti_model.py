@@ -55,6 +55,19 @@ class Veh3dofcontiModel(PythBaseModel):
             raise RuntimeError(f"ref_points must be [B, {self.pre_horizon + 1}, 4], got {tuple(keep[-4].shape)}")
 
 
+    def alloc_next_info(self, B, dev):
+        return {"state": torch.empty((B, 6), dtype=torch.float32, device=dev),
+                "ref_points": torch.empty((B, self.pre_horizon + 1, 4), dtype=torch.float32, device=dev),
+                "ref_time": torch.empty(B, dtype=torch.float32, device=dev)}
+
+    def make_next_info(self, info, extra):
+        next_info = {k: (v.detach().clone() if torch.is_tensor(v) else v) for k, v in info.items()}
+        dev = info["state"].device
+        next_info.update({"state": extra["state"].to(dev), "ref_points": extra["ref_points"].to(dev),
+                          "path_num": info["path_num"], "u_num": info["u_num"], "ref_time": extra["ref_time"].to(dev)})
+        return next_info
+
+
 def env_model_creator(**kwargs):
     """make env model `pyth_veh3dofconti`"""
     return Veh3dofcontiModel(**kwargs)

@@ -106,7 +106,8 @@ def fused_forward(top, obs, action, done, info):
     keep = []
     obs_d = obs.detach().to(dev, torch.float32)
     with torch.cuda.device(dev):
-        b = make_batch(base, obs_d, done.to(dev), info, keep)
+        info_d = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in (info or {}).items()}
+        b = make_batch(base, obs_d, done.to(dev), info_d, keep)
         act = action.detach().to(dev, torch.float32).contiguous()
         B = obs_d.shape[0]
         nobs = torch.empty((B, base.obs_dim), dtype=torch.float32, device=dev)

@@ -361,3 +361,39 @@ def test_unsupported_configurations_raise():
     alg = create_alg(**kw)
     with pytest.raises(RuntimeError, match="ActionRepeat"):
         alg.local_update(data_from(rec, "pyth_veh3dofconti"), 0)
+
+
+@pytest.mark.parametrize("env_id", ["pyth_veh3dofconti", "veh3dof_tracking", "pyth_lq"])
+def test_envmodel_forward_single_step_matches_oracle(env_id):
+    """envmodel.forward(obs, action, done, info) of the fused wrapper chain vs. the oracle chain (fp32)."""
+    from gops_b200.create_pkg.create_env_model import create_env_model
+    from gops_b200.env.env_gen_ocp.pyth_base import ContextState, State
+    B = 257
+    kw = dict(pre_horizon=10) if env_id != "pyth_lq" else dict(lq_config="s4a2")
+    wk = dict(reward_scale=0.5, reward_shift=0.1)
+    model = create_env_model(env_id, **kw, **wk)
+    ref = orc.create_env_model(env_id, **kw, **wk)
+    data = orc.sample_inputs(env_id, B, seed=77, **kw)
+    data["done"][::3] = 1.0
+    g = torch.Generator().manual_seed(5)
+    act = torch.rand(B, ref.action_dim, generator=g) * 2.4 - 1.2        # partly outside [-1, 1]
+    info = {k: v for k, v in data.items() if k not in ("obs", "done")}
+    obs, done = data["obs"], data["done"]
+    for step in range(3):
+        o_ref, r_ref, d_ref, info_ref = ref.forward(obs, act, done, info)
+        info_gpu = dict(info)
+        if env_id == "veh3dof_tracking":
+            robot, reference, t = info["state"]
+            info_gpu["state"] = State(robot_state=robot, context_state=ContextState(reference=reference, t=t))
+        o, r, d, info_new = model.forward(obs, act, done, info_gpu)
+        np.testing.assert_allclose(o.cpu().numpy(), o_ref.numpy(), rtol=2e-5, atol=2e-5)
+        np.testing.assert_allclose(r.cpu().numpy(), r_ref.numpy(), rtol=2e-5, atol=2e-6)
+        assert torch.equal(d.cpu(), d_ref)
+        if env_id == "pyth_veh3dofconti":
+            np.testing.assert_allclose(info_new["state"].cpu().numpy(), info_ref["state"].numpy(), rtol=2e-5, atol=2e-5)
+            np.testing.assert_allclose(info_new["ref_points"].cpu().numpy(), info_ref["ref_points"].numpy(), rtol=1e-4,
+                                       atol=2e-3)   # newest phi: fp32 finite difference with dt = 1e-3
+            np.testing.assert_allclose(info_new["ref_time"].cpu().numpy(), info_ref["ref_time"].numpy(), rtol=1e-6)
+        if env_id == "veh3dof_tracking":
+            assert info_new["state"].context_state.t == info_ref["state"][2]
+        obs, done, info = o_ref, d_ref.float(), info_ref
