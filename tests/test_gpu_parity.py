@@ -386,13 +386,22 @@ def test_envmodel_forward_single_step_matches_oracle(env_id):
             robot, reference, t = info["state"]
             info_gpu["state"] = State(robot_state=robot, context_state=ContextState(reference=reference, t=t))
         o, r, d, info_new = model.forward(obs, act, done, info_gpu)
-        np.testing.assert_allclose(o.cpu().numpy(), o_ref.numpy(), rtol=2e-5, atol=2e-5)
+        on, orf = o.cpu().numpy(), o_ref.numpy()
+        live = ~done.bool().numpy()
+        if env_id == "pyth_veh3dofconti":
+            # heading of the NEWEST reference point comes from compute_phi's fp32 finite difference (dt = 1e-3,
+            # ref_traj_model.py:144-148): sin/cos ulps are amplified to ~1e-3 rad (SURVEY hard-parts list)
+            np.testing.assert_allclose(on[live, 44], orf[live, 44], rtol=0, atol=8e-3)
+            on, orf = np.delete(on, 44, axis=1), np.delete(orf, 44, axis=1)
+        np.testing.assert_allclose(on, orf, rtol=2e-5, atol=2e-5)
         np.testing.assert_allclose(r.cpu().numpy(), r_ref.numpy(), rtol=2e-5, atol=2e-6)
         assert torch.equal(d.cpu(), d_ref)
         if env_id == "pyth_veh3dofconti":
             np.testing.assert_allclose(info_new["state"].cpu().numpy(), info_ref["state"].numpy(), rtol=2e-5, atol=2e-5)
-            np.testing.assert_allclose(info_new["ref_points"].cpu().numpy(), info_ref["ref_points"].numpy(), rtol=1e-4,
-                                       atol=2e-3)   # newest phi: fp32 finite difference with dt = 1e-3
+            rp, rpr = info_new["ref_points"].cpu().numpy().copy(), info_ref["ref_points"].numpy().copy()
+            np.testing.assert_allclose(rp[:, -1, 2], rpr[:, -1, 2], rtol=0, atol=8e-3)   # newest phi (see above)
+            rp[:, -1, 2] = rpr[:, -1, 2] = 0.0
+            np.testing.assert_allclose(rp, rpr, rtol=2e-5, atol=2e-5)
             np.testing.assert_allclose(info_new["ref_time"].cpu().numpy(), info_ref["ref_time"].numpy(), rtol=1e-6)
         if env_id == "veh3dof_tracking":
             assert info_new["state"].context_state.t == info_ref["state"][2]
