@@ -162,12 +162,15 @@ namespace {
 
 size_t rollout_smem_bytes(const KParams& kp, int S, int NT) {
   const int SP = S + 4, XS = NT + 4, HID = kp.hid;
-  if (HID > 64) return sizeof(float) * (size_t)(4 + 4 * HID * SP + 8 * XS);
+  // wide nets: + staging region R = max(obs sub-tile + 2 forward k-slices, 2 column slices)
+  const size_t stage = (size_t)kp.inp_max * SP + 2 * 16 * (HID + 4);
+  const size_t stage2 = 2 * (size_t)HID * 20;
+  if (HID > 64) return sizeof(float) * (size_t)(4 + 4 * HID * SP + 8 * XS + (stage > stage2 ? stage : stage2));
   return sizeof(float) * (size_t)(4 + kp.w_floats + kp.dw_floats + kp.inp_max * XS + 4 * HID * SP + 8 * XS);
 }
 size_t infer_smem_bytes(const KParams& kp, int S, int NT) {
   const int SP = S + 4, XS = NT + 4, HID = kp.hid;
-  if (HID > 64) return sizeof(float) * (size_t)(4 + 2 * HID * SP + 8 * XS);
+  if (HID > 64) return sizeof(float) * (size_t)(4 + 2 * HID * SP + 8 * XS + (size_t)kp.inp_max * SP + 2 * 16 * (HID + 4));
   return sizeof(float) * (size_t)(4 + kp.w_floats + kp.inp_max * XS + 2 * HID * SP + 8 * XS);
 }
 
@@ -273,8 +276,11 @@ int launch_rollout(gops_b200_plan* pl, const gops_b200_batch* b, int alg, cudaSt
   int occ = 1;
   CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, NT, smem));
   if (occ < 1) return fail("rollout kernel does not fit on an SM");
+  // one CTA per SM slot as long as every CTA still gets at least one S-sample sub-tile: the kernel splits the
+  // batch into balanced contiguous ranges, so small batches spread over all SMs with partially filled chunks
   const long long slots = (long long)pl->sm_count * occ;
-  const int grid = (int)(kp.n_tiles < slots ? kp.n_tiles : slots);
+  const long long subtiles = (b->batch + S - 1) / S;
+  const int grid = (int)(subtiles < slots ? subtiles : slots);
   if (ensure_scratch(pl, grid, NT, kp.horizon)) return 1;
   kp.tape = pl->tape;
   kp.ext_ref = pl->ext_ref;

@@ -34,6 +34,7 @@ __global__ void __launch_bounds__(NT, 1) rollout_kernel(const __grid_constant__ 
   t.H2 = t.D1 + HID * SP;
   t.D2 = t.H2 + HID * SP;
   t.Z = t.D2 + HID * SP;      // [8][XS]: rows a (+ 4 + a: second half-stripe partial of the fused output layer)
+  t.R = t.Z + 8 * XS;         // wide nets only: staging region
 
   const int tid = threadIdx.x;
   // column (= sample slot of the chunk) owned by this thread.  Tensor-core path: the 64 threads of warp pair p own
@@ -517,6 +518,7 @@ __global__ void __launch_bounds__(NT, 1) mlp_infer_kernel(const __grid_constant_
   t.H2 = t.H1 + HID * SP;
   t.D2 = t.H2;
   t.Z = t.H2 + HID * SP;
+  t.R = t.Z + 8 * XS;
   for (int i = threadIdx.x; i < 8 * XS; i += NT) t.Z[i] = 0.f;
   const int tid = threadIdx.x;
   if (tid == 0) {

@@ -99,6 +99,16 @@ struct KParams {
 constexpr int ALG_FHADP = GOPS_ALG_FHADP, ALG_PIM = GOPS_ALG_INFADP_POLICY, ALG_PEV = GOPS_ALG_INFADP_VALUE,
               ALG_TRACE = 3;
 
+// cp.async (LDGSTS) helpers for the wide-net path: weight k-slices are staged global -> shared, double buffered
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
 // Warp tiling of a [HID x S] output tile: every warp is 4 (feature) x 8 (sample) threads, a thread
 // owns TM features x 4 samples.  One k-step then needs ONE 64 B and ONE 128 B shared wavefront per warp.
 template <int HD, int S, int NT>
@@ -376,11 +386,191 @@ __device__ __noinline__ void gemm_dx(const float* __restrict__ W1k, const float*
       *reinterpret_cast<float4*>(Xb + (mg + MG * j) * ldx + 4 * nt) = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Wide nets (HD = 256): the weights live in global memory (L2); the GEMMs stream them through shared memory in
+// double-buffered k-slices (cp.async), so the inner loops read shared memory only.
+// ---------------------------------------------------------------------------------------------
+// P[m][n] = bias[m] + sum_k A[k][m] * B[k][n];  A: global [K][HP];  B: shared [K][ldb];  Wsl: 2 x KS x HP floats
+template <int HD, int S, int NT>
+__device__ __noinline__ void gemm_fwd_ws(const float* __restrict__ A, const float* __restrict__ Bm, int ldb, int K,
+                                         const float* __restrict__ bias, float* __restrict__ P,
+                                         float* __restrict__ Wsl) {
+  using M = Map<HD, S, NT>;
+  constexpr int HP = hp_of(HD), SP = M::SP, TM = M::TM, KS = 16, R4 = HP / 4;
+  const M mp;
+  const int m0 = mp.mt * TM, tid = threadIdx.x;
+  float acc[TM][4];
+#pragma unroll
+  for (int j = 0; j < TM; ++j) {
+    const float bb = bias[m0 + j];
+    acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = bb;
+  }
+  const int nsl = (K + KS - 1) / KS;
+  auto load = [&](int sl, int buf) {
+    const int rows = min(KS, K - sl * KS);
+    const float* src = A + (size_t)sl * KS * HP;
+    float* dst = Wsl + buf * KS * HP;
+    for (int idx = tid; idx < rows * R4; idx += NT) cp_async16(dst + 4 * idx, src + 4 * idx);
+    cp_async_commit();
+  };
+  load(0, 0);
+  for (int sl = 0; sl < nsl; ++sl) {
+    if (sl + 1 < nsl) load(sl + 1, (sl + 1) & 1);
+    else cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
+    const int rows = min(KS, K - sl * KS);
+    const float* ap = Wsl + (sl & 1) * KS * HP + m0;
+    const float* bp = Bm + (size_t)sl * KS * ldb + mp.n0;
+#pragma unroll 4
+    for (int k = 0; k < rows; ++k) {
+      const float4 b = *reinterpret_cast<const float4*>(bp + k * ldb);
+      float a[TM];
+#pragma unroll
+      for (int q = 0; q < TM / 4; ++q) {
+        const float4 av = *reinterpret_cast<const float4*>(ap + k * HP + 4 * q);
+        a[4 * q] = av.x; a[4 * q + 1] = av.y; a[4 * q + 2] = av.z; a[4 * q + 3] = av.w;
+      }
+#pragma unroll
+      for (int j = 0; j < TM; ++j) {
+        acc[j][0] = fmaf(a[j], b.x, acc[j][0]); acc[j][1] = fmaf(a[j], b.y, acc[j][1]);
+        acc[j][2] = fmaf(a[j], b.z, acc[j][2]); acc[j][3] = fmaf(a[j], b.w, acc[j][3]);
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int j = 0; j < TM; ++j)
+    *reinterpret_cast<float4*>(P + (m0 + j) * SP + mp.n0) = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
+}
+
+// Column slices [rows][OS] of a global k-major tile [rows][HP] staged as [rows][OS + 4] (bank skew 20 -> conflict-free
+// float4 reads by the four feature-threads of a warp).  Shared by the backward-delta and input-gradient GEMMs.
+constexpr int OS = 16, OSP = OS + 4;
+template <int NT>
+__device__ __forceinline__ void load_col_slice(const float* __restrict__ A, int HP, int rows, int o0, float* dst) {
+  for (int idx = threadIdx.x; idx < rows * (OS / 4); idx += NT) {
+    const int r = idx / (OS / 4), c4 = idx - r * (OS / 4);
+    cp_async16(dst + r * OSP + 4 * c4, A + (size_t)r * HP + o0 + 4 * c4);
+  }
+  cp_async_commit();
+}
+
+// D[i][n] <- D[i][n] * sum_o A[i][o] * Dl[o][n];  A: global [HID][HP];  Wsl: 2 x HID x OSP floats
+template <int HD, int S, int NT>
+__device__ __noinline__ void gemm_bwd_ws(const float* __restrict__ A, const float* __restrict__ Dl,
+                                         float* __restrict__ D, float* __restrict__ Wsl) {
+  using M = Map<HD, S, NT>;
+  constexpr int HID = HD, HP = hp_of(HD), SP = M::SP, TM = M::TM, RS = 4 * M::WM;
+  const M mp;
+  float acc[TM][4];
+#pragma unroll
+  for (int j = 0; j < TM; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+  constexpr int nsl = HID / OS;
+  load_col_slice<NT>(A, HP, HID, 0, Wsl);
+  for (int sl = 0; sl < nsl; ++sl) {
+    if (sl + 1 < nsl) load_col_slice<NT>(A, HP, HID, (sl + 1) * OS, Wsl + ((sl + 1) & 1) * HID * OSP);
+    else cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
+    const float* ap = Wsl + (sl & 1) * HID * OSP + mp.mt * OSP;
+    const float* bp = Dl + (size_t)sl * OS * SP + mp.n0;
+#pragma unroll
+    for (int o = 0; o < OS; o += 4) {
+      float4 b[4];
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) b[kk] = *reinterpret_cast<const float4*>(bp + (o + kk) * SP);
+#pragma unroll
+      for (int j = 0; j < TM; ++j) {
+        const float4 a = *reinterpret_cast<const float4*>(ap + j * RS * OSP + o);
+        acc[j][0] = fmaf(a.x, b[0].x, acc[j][0]); acc[j][1] = fmaf(a.x, b[0].y, acc[j][1]);
+        acc[j][2] = fmaf(a.x, b[0].z, acc[j][2]); acc[j][3] = fmaf(a.x, b[0].w, acc[j][3]);
+        acc[j][0] = fmaf(a.y, b[1].x, acc[j][0]); acc[j][1] = fmaf(a.y, b[1].y, acc[j][1]);
+        acc[j][2] = fmaf(a.y, b[1].z, acc[j][2]); acc[j][3] = fmaf(a.y, b[1].w, acc[j][3]);
+        acc[j][0] = fmaf(a.z, b[2].x, acc[j][0]); acc[j][1] = fmaf(a.z, b[2].y, acc[j][1]);
+        acc[j][2] = fmaf(a.z, b[2].z, acc[j][2]); acc[j][3] = fmaf(a.z, b[2].w, acc[j][3]);
+        acc[j][0] = fmaf(a.w, b[3].x, acc[j][0]); acc[j][1] = fmaf(a.w, b[3].y, acc[j][1]);
+        acc[j][2] = fmaf(a.w, b[3].z, acc[j][2]); acc[j][3] = fmaf(a.w, b[3].w, acc[j][3]);
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int j = 0; j < TM; ++j) {
+    float* dp = D + (mp.mt + j * RS) * SP + mp.n0;
+    float4 d = *reinterpret_cast<const float4*>(dp);
+    d.x *= acc[j][0]; d.y *= acc[j][1]; d.z *= acc[j][2]; d.w *= acc[j][3];
+    *reinterpret_cast<float4*>(dp) = d;
+  }
+}
+
+// Xb[i][s] = sum_o W1k[i][o] * Dl[o][s], i < M;  W1k: global [in][HP];  Wsl: 2 x rows8 x OSP floats
+template <int HD, int S, int NT>
+__device__ __noinline__ void gemm_dx_ws(const float* __restrict__ W1k, const float* __restrict__ Dl, int M,
+                                        float* __restrict__ Xb, int ldx, float* __restrict__ Wsl) {
+  constexpr int SP = S + 4, NTN = S / 4, MG = NT / NTN, JM = 8, HID = HD, HP = hp_of(HD);
+  const int tid = threadIdx.x, nt = tid % NTN, mg = tid / NTN;
+  const int J = max(0, (M - mg + MG - 1) / MG);
+  const int rows = (M + 3) & ~3;       // <= in rows of the blob (pad rows are zero there)
+  float acc[JM][4];
+#pragma unroll
+  for (int j = 0; j < JM; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+  constexpr int nsl = HID / OS;
+  const int stride = ((rows + 7) & ~7) * OSP;
+  load_col_slice<NT>(W1k, HP, M, 0, Wsl);
+  for (int sl = 0; sl < nsl; ++sl) {
+    if (sl + 1 < nsl) load_col_slice<NT>(W1k, HP, M, (sl + 1) * OS, Wsl + ((sl + 1) & 1) * stride);
+    else cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
+    const float* wp = Wsl + (sl & 1) * stride;
+    const float* dp = Dl + (size_t)sl * OS * SP + 4 * nt;
+#pragma unroll
+    for (int o = 0; o < OS; o += 4) {
+      float4 d[4];
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) d[kk] = *reinterpret_cast<const float4*>(dp + (o + kk) * SP);
+#pragma unroll
+      for (int j = 0; j < JM; ++j)
+        if (j < J) {
+          const float4 w = *reinterpret_cast<const float4*>(wp + (mg + MG * j) * OSP + o);
+          acc[j][0] = fmaf(w.x, d[0].x, acc[j][0]); acc[j][1] = fmaf(w.x, d[0].y, acc[j][1]);
+          acc[j][2] = fmaf(w.x, d[0].z, acc[j][2]); acc[j][3] = fmaf(w.x, d[0].w, acc[j][3]);
+          acc[j][0] = fmaf(w.y, d[1].x, acc[j][0]); acc[j][1] = fmaf(w.y, d[1].y, acc[j][1]);
+          acc[j][2] = fmaf(w.y, d[1].z, acc[j][2]); acc[j][3] = fmaf(w.y, d[1].w, acc[j][3]);
+          acc[j][0] = fmaf(w.z, d[2].x, acc[j][0]); acc[j][1] = fmaf(w.z, d[2].y, acc[j][1]);
+          acc[j][2] = fmaf(w.z, d[2].z, acc[j][2]); acc[j][3] = fmaf(w.z, d[2].w, acc[j][3]);
+          acc[j][0] = fmaf(w.w, d[3].x, acc[j][0]); acc[j][1] = fmaf(w.w, d[3].y, acc[j][1]);
+          acc[j][2] = fmaf(w.w, d[3].z, acc[j][2]); acc[j][3] = fmaf(w.w, d[3].w, acc[j][3]);
+        }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int j = 0; j < JM; ++j)
+    if (j < J)
+      *reinterpret_cast<float4*>(Xb + (mg + MG * j) * ldx + 4 * nt) = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
+}
+
+// Copy rows [0, nrows) x S columns of the global observation tile (row stride ldx) into shared memory [nrows][S + 4]
+template <int S, int NT>
+__device__ __forceinline__ void stage_x_tile(const float* __restrict__ Xg, int ldx, int nrows, float* __restrict__ Xs) {
+  constexpr int SP = S + 4, C4 = S / 4;
+  for (int idx = threadIdx.x; idx < nrows * C4; idx += NT) {
+    const int r = idx / C4, c4 = idx - r * C4;
+    cp_async16(Xs + r * SP + 4 * c4, Xg + (size_t)r * ldx + 4 * c4);
+  }
+  cp_async_commit();
+  cp_async_wait<0>();
+  __syncthreads();
+}
+
 // Shared-memory views of one CTA.  X and Z hold one column per THREAD (row stride XS = NT + 4); the
 // activation tiles H1/D1/H2/D2 hold one S-sample sub-tile (row stride SP = S + 4) and are reused by the
 // NT/S sub-tiles of a chunk.  X/Z pointers passed to the mlp_* helpers are already offset to the sub-tile.
 struct Tiles {
   float *W, *dW, *X, *H1, *D1, *H2, *D2, *Z;
+  float* R;   // wide nets: shared staging region (observation sub-tile + double-buffered weight slices)
 };
 
 // X -> H1 -> H2 (-> Zout rows a and 4 + a: consumers add the two).  FULL: also store activation derivatives.
@@ -399,10 +589,14 @@ __device__ __forceinline__ void mlp_forward(const NetL& L, const Tiles& t, float
                          Zout, XS);
     pair_sync();
   } else {
-    gemm_fwd<HD, S, NT>(t.W + L.o_w1, t.X, XS, L.in, t.W + L.o_b1, t.H1);
+    // R = [ observation sub-tile  Xs: inp x (S+4) | weight slices ]
+    float* Xs = t.R;
+    float* Wsl = t.R + L.inp * (S + 4);
+    stage_x_tile<S, NT>(t.X, XS, L.in, Xs);
+    gemm_fwd_ws<HD, S, NT>(t.W + L.o_w1, Xs, S + 4, L.in, t.W + L.o_b1, t.H1, Wsl);
     act_pass<HD, S, NT>(t.H1, FULL ? t.D1 : nullptr, L.hact);
     __syncthreads();
-    gemm_fwd<HD, S, NT>(t.W + L.o_w2, t.H1, S + 4, HID, t.W + L.o_b2, t.H2);
+    gemm_fwd_ws<HD, S, NT>(t.W + L.o_w2, t.H1, S + 4, HID, t.W + L.o_b2, t.H2, Wsl);
     act_pass<HD, S, NT>(t.H2, FULL ? t.D2 : nullptr, L.hact);
     __syncthreads();
     if (OUT) {
@@ -449,18 +643,19 @@ __device__ __forceinline__ void mlp_backward(const NetL& L, const Tiles& t, bool
     }
     delta_from_out<HD, S, NT>(t.W + L.o_w3, t.Z, XS, L.out, t.D2);  // D2 <- delta2
     __syncthreads();
-    gemm_bwd<HD, S, NT>(t.W + L.o_w2, t.D2, t.D1);                  // D1 <- delta1
+    gemm_bwd_ws<HD, S, NT>(t.W + L.o_w2, t.D2, t.D1, t.R);          // D1 <- delta1 (weight slices through R)
     if (WANT_DW) {
       dw_accum<HD, S, NT, 4, 4>(t.D2, SP, HID, t.H1, SP, HID, t.dW + L.g_w2, HID);
       rowsum_accum<HD, S, NT>(t.D2, SP, HID, t.dW + L.g_b2);
     }
     __syncthreads();
     if (WANT_DW) {
-      dw_accum<HD, S, NT, 4, 4>(t.D1, SP, HID, t.X, XS, L.in, t.dW + L.g_w1, L.in);
+      stage_x_tile<S, NT>(t.X, XS, L.in, t.R);                      // observation sub-tile back into shared memory
+      dw_accum<HD, S, NT, 4, 4>(t.D1, SP, HID, t.R, SP, L.in, t.dW + L.g_w1, L.in);
       rowsum_accum<HD, S, NT>(t.D1, SP, HID, t.dW + L.g_b1);
-      if (want_dx) __syncthreads();
+      __syncthreads();
     }
-    if (want_dx) gemm_dx<HD, S, NT>(t.W + L.o_w1, nullptr, t.D1, L.obs, t.X, XS);
+    if (want_dx) gemm_dx_ws<HD, S, NT>(t.W + L.o_w1, t.D1, L.obs, t.X, XS, t.R);
     __syncthreads();
   }
 }
