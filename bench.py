@@ -130,13 +130,23 @@ def cpu_update_rate(batch, steps, warmup, threads):
     return batch * H * len(times) / total, total / len(times)
 
 
+def best_cpu_threads(batch):
+    """The reference's tiny-op eager path does not scale to many threads; give it the better of (all usable cores)
+    and (16 threads) so the baseline is not handicapped by oversubscription."""
+    cands = sorted({usable_cores(), min(usable_cores(), 16)})
+    if len(cands) == 1:
+        return cands[0]
+    rates = {c: cpu_update_rate(batch, 1, 1, c)[0] for c in cands}
+    return max(rates, key=rates.get)
+
+
 def run_reference(args, rank, world):
     """Reference arm: the reference's own CPU algorithm (oracle port; the python reference cannot travel
     to the GPU box) on the host cores, bounded sample per step."""
     if rank != 0:
         return
-    threads = usable_cores()
     sample_b = args.cpu_batch
+    threads = best_cpu_threads(sample_b)
     rate, sec = cpu_update_rate(sample_b, args.steps, args.warmup, threads)
     line = {
         "impl": "reference", "metric": "batched env-steps/sec (FHADP rollout+update)", "value": rate,
@@ -280,7 +290,7 @@ def main():
                 "launch": {"grid": info[0], "block": info[1], "tile_samples": info[2], "smem_bytes": info[3]}}
         cpu = None
         if not args.no_cpu_baseline:
-            threads = usable_cores()
+            threads = best_cpu_threads(args.cpu_batch)
             rate, sec = cpu_update_rate(args.cpu_batch, 3, 1, threads)
             cpu = {"value": rate, "unit": "env-steps/s", "cores": threads, "kind": "port",
                    "sample": f"B={args.cpu_batch}, H={H}, 3 updates after 1 warm-up (oracle/gops_oracle.py)"}
