@@ -21,8 +21,9 @@ __global__ void pack_params_kernel(const float* __restrict__ flat, NetL L, int H
     if (split) {
       uint32_t hi;
       asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(w));
-      blob[L.o_w1 + i] = __uint_as_float(hi);
-      blob[L.o_w1l + i] = w - __uint_as_float(hi);
+      const int is = k * HP + (o < HID ? (o ^ (((k >> 2) & 1) << 2)) : o);   // bank swizzle, see gemm_fwd_mma
+      blob[L.o_w1 + is] = __uint_as_float(hi);
+      blob[L.o_w1l + is] = w - __uint_as_float(hi);
     } else {
       blob[L.o_w1 + i] = w;
     }
@@ -33,8 +34,9 @@ __global__ void pack_params_kernel(const float* __restrict__ flat, NetL L, int H
     if (split) {
       uint32_t hi;
       asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(w));
-      blob[L.o_w2 + i] = __uint_as_float(hi);
-      blob[L.o_w2l + i] = w - __uint_as_float(hi);
+      const int is = k * HP + (o < HID ? (o ^ (((k >> 2) & 1) << 2)) : o);
+      blob[L.o_w2 + is] = __uint_as_float(hi);
+      blob[L.o_w2l + is] = w - __uint_as_float(hi);
     } else {
       blob[L.o_w2 + i] = w;
     }

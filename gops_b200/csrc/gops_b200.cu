@@ -90,6 +90,17 @@ bool make_net(const gops_b200_mlp_desc& d, NetL& L, std::string& why) {
   L.g_w3 = g; g += L.out * HID;
   L.g_b3 = g; g += L.out;
   L.nparam = g;
+  // shared-memory accumulator layout (64-wide tensor-core path pads W2 rows to 68 floats; wide nets accumulate in
+  // the global partial in torch layout)
+  L.ldw2 = HID == 64 ? 68 : HID;
+  int a = 0;
+  L.d_w1 = a; a += HID * L.in;
+  L.d_b1 = a; a += HID;
+  L.d_w2 = a; a += HID * L.ldw2;
+  L.d_b2 = a; a += HID;
+  L.d_w3 = a; a += L.out * HID;
+  L.d_b3 = a; a += L.out;
+  L.nacc = a;
   return true;
 }
 
@@ -267,7 +278,7 @@ int launch_rollout(gops_b200_plan* pl, const gops_b200_batch* b, int alg, cudaSt
   kp.ref_len = b->ref_len;
   const NetL& upd = (alg == ALG_PEV) ? kp.val : kp.pol;
   kp.part_stride = round4(upd.nparam + 4);
-  kp.dw_floats = round4(upd.nparam);
+  kp.dw_floats = round4(upd.nacc);
   const size_t smem = rollout_smem_bytes(kp, S, NT);
   if (!pl->attr_set[alg][cfg]) {
     CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, pl->max_smem));
@@ -354,7 +365,7 @@ int gops_b200_plan_create(const gops_b200_plan_desc* d, gops_b200_plan** out) {
   kp.gamma = d->gamma;
   kp.w_floats = kp.pol.blob > kp.val.blob ? kp.pol.blob : kp.val.blob;
   kp.inp_max = kp.pol.inp > kp.val.inp ? kp.pol.inp : kp.val.inp;
-  kp.dw_floats = round4(kp.pol.nparam > kp.val.nparam ? kp.pol.nparam : kp.val.nparam);
+  kp.dw_floats = round4(kp.pol.nacc > kp.val.nacc ? kp.pol.nacc : kp.val.nacc);
   kp.action_scale = d->action_scale; kp.clip_action = d->clip_action; kp.mask_at_done = d->mask_at_done;
   kp.reward_shaping = d->reward_shaping; kp.reward_shift = d->reward_shift; kp.reward_scale = d->reward_scale;
   kp.obs_scaling = d->obs_scaling ? 1 : 0;

@@ -477,8 +477,16 @@ __global__ void __launch_bounds__(NT, 1) rollout_kernel(const __grid_constant__ 
   // ============================ per-CTA partials ============================
   __syncthreads();
   const int nparam = (alg == ALG_PEV) ? V.nparam : P.nparam;
-  if (alg != ALG_TRACE && !WG)
-    for (int i = tid; i < nparam; i += NT) part[i] = t.dW[i];
+  if (alg != ALG_TRACE && !WG) {
+    const NetL& U = (alg == ALG_PEV) ? V : P;
+    for (int i = tid; i < nparam; i += NT) {      // accumulator layout -> torch flat layout
+      int j;
+      if (i < U.g_w2) j = i;                                                    // W1, b1 (offsets coincide)
+      else if (i < U.g_b2) { const int q = i - U.g_w2; j = U.d_w2 + (q / HID) * U.ldw2 + (q % HID); }
+      else j = i - U.g_b2 + U.d_b2;                                             // b2, W3, b3
+      part[i] = t.dW[j];
+    }
+  }
   // block reduction of the three scalars (fixed order)
   float* red = t.H1;  // free at this point, HID*(S+4) >= 3*NT floats
   red[tid] = loss_acc;

@@ -54,7 +54,7 @@ struct MmaMap {
 template <int S, int NT, int HP>
 __device__ __noinline__ void gemm_fwd_mma(const float* __restrict__ Whi, const float* __restrict__ Wlo,
                                           const float* __restrict__ Bm, int ldb, int K8,
-                                          const float* __restrict__ bias, float* __restrict__ P) {
+                                          const float* __restrict__ bias, float* __restrict__ P, bool swz_b) {
   constexpr int SP = S + 4;
   const MmaMap<S, NT> mp;
   float c[4][4];
@@ -64,22 +64,26 @@ __device__ __noinline__ void gemm_fwd_mma(const float* __restrict__ Whi, const f
     c[nt][0] = b0; c[nt][1] = b1; c[nt][2] = b0; c[nt][3] = b1;
   }
   const float* ap = Bm + mp.t * ldb + mp.s0 + mp.g;
+  // weight planes are stored with column ^= ((row >> 2) & 1) << 2 (bank swizzle that makes BOTH this k-major read
+  // and the transposed read of the backward GEMMs conflict-free): rows k0+t keep their columns, rows k0+4+t flip bit 2
   const float* wh = Whi + mp.t * HP + mp.m0 + mp.g;
   const float* wl = Wlo + mp.t * HP + mp.m0 + mp.g;
+  const float* wh4 = Whi + (mp.t + 4) * HP + mp.m0 + (mp.g ^ 4);
+  const float* wl4 = Wlo + (mp.t + 4) * HP + mp.m0 + (mp.g ^ 4);
 #pragma unroll 2
   for (int k0 = 0; k0 < K8; k0 += 8) {
     uint32_t ah[4], al[4];
     split_tf32(ap[k0 * ldb], ah[0], al[0]);
-    split_tf32(ap[k0 * ldb + 8], ah[1], al[1]);
+    split_tf32(ap8[k0 * ldb], ah[1], al[1]);
     split_tf32(ap[(k0 + 4) * ldb], ah[2], al[2]);
-    split_tf32(ap[(k0 + 4) * ldb + 8], ah[3], al[3]);
+    split_tf32(ap8[(k0 + 4) * ldb], ah[3], al[3]);
     uint32_t bh[4][2], bl[4][2];
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt) {
       bh[nt][0] = __float_as_uint(wh[k0 * HP + 8 * nt]);
-      bh[nt][1] = __float_as_uint(wh[(k0 + 4) * HP + 8 * nt]);
+      bh[nt][1] = __float_as_uint(wh4[k0 * HP + 8 * nt]);
       bl[nt][0] = __float_as_uint(wl[k0 * HP + 8 * nt]);
-      bl[nt][1] = __float_as_uint(wl[(k0 + 4) * HP + 8 * nt]);
+      bl[nt][1] = __float_as_uint(wl4[k0 * HP + 8 * nt]);
     }
     // three passes over the four independent accumulators: no back-to-back dependent HMMA
 #pragma unroll
@@ -92,7 +96,7 @@ __device__ __noinline__ void gemm_fwd_mma(const float* __restrict__ Whi, const f
 #pragma unroll
   for (int nt = 0; nt < 4; ++nt) {
     float* p = P + (mp.m0 + 8 * nt + 2 * mp.t) * SP + mp.s0 + mp.g;
-    p[0] = c[nt][0]; p[SP] = c[nt][1]; p[8] = c[nt][2]; p[SP + 8] = c[nt][3];
+    p[0] = c[nt][0]; p[SP + 8] = c[nt][1]; p[8] = c[nt][2]; p[SP] = c[nt][3];   // odd feature row: column ^ 8
   }
 }
 
@@ -119,18 +123,19 @@ __device__ __noinline__ void act_pass_frag(float* __restrict__ H, float* __restr
     const int m = mp.m0 + 8 * nt + 2 * mp.t;
     const int base = m * SP + mp.s0 + mp.g;
     float* hp = H + base;
-    const float p0 = hp[0], p1 = hp[SP], p2 = hp[8], p3 = hp[SP + 8];
+    // elements (m, g) (m+1, g) (m, g+8) (m+1, g+8); the odd row m+1 is stored with its column ^ 8
+    const float p0 = hp[0], p1 = hp[SP + 8], p2 = hp[8], p3 = hp[SP];
     float h0, h1, h2, h3;
     if (D != nullptr) {
       float d0, d1, d2, d3;
       act_fwd_grad(act, p0, h0, d0); act_fwd_grad(act, p1, h1, d1);
       act_fwd_grad(act, p2, h2, d2); act_fwd_grad(act, p3, h3, d3);
       float* dp = D + base;
-      dp[0] = d0; dp[SP] = d1; dp[8] = d2; dp[SP + 8] = d3;
+      dp[0] = d0; dp[SP + 8] = d1; dp[8] = d2; dp[SP] = d3;
     } else {
       h0 = act_fwd(act, p0); h1 = act_fwd(act, p1); h2 = act_fwd(act, p2); h3 = act_fwd(act, p3);
     }
-    hp[0] = h0; hp[SP] = h1; hp[8] = h2; hp[SP + 8] = h3;
+    hp[0] = h0; hp[SP + 8] = h1; hp[8] = h2; hp[SP] = h3;
     if (W3 != nullptr) {
 #pragma unroll
       for (int a = 0; a < MAXA; ++a)
@@ -182,7 +187,7 @@ __device__ __noinline__ void delta_from_out_frag(const float* __restrict__ W3, c
         c0 = fmaf(w0, za[a], c0); c1 = fmaf(w1, za[a], c1);
         c2 = fmaf(w0, zb[a], c2); c3 = fmaf(w1, zb[a], c3);
       }
-    p[0] *= c0; p[SP] *= c1; p[8] *= c2; p[SP + 8] *= c3;
+    p[0] *= c0; p[SP + 8] *= c1; p[8] *= c2; p[SP] *= c3;
   }
 }
 
@@ -194,20 +199,25 @@ __device__ __noinline__ void gemm_dx_mma(const float* __restrict__ Whi, const fl
   constexpr int SP = S + 4;
   const MmaMap<S, NT> mp;
   const int half = mp.m0 >> 5, ntiles = (M + 7) >> 3;
-  const float* ap = Dl + mp.t * SP + mp.s0 + mp.g;
+  const int sw = (mp.t & 1) << 3;
+  const float* ap = Dl + mp.t * SP + mp.s0 + (mp.g ^ sw);
+  const float* ap8 = Dl + mp.t * SP + mp.s0 + ((mp.g + 8) ^ sw);
   for (int nt = half; nt < ntiles; nt += 2) {
     float c[4] = {0.f, 0.f, 0.f, 0.f};
-    const float* wh = Whi + (8 * nt + mp.g) * HP + mp.t;
-    const float* wl = Wlo + (8 * nt + mp.g) * HP + mp.t;
+    const int swz = mp.g & 4;
+    const float* wh = Whi + (8 * nt + mp.g) * HP + (mp.t ^ swz);
+    const float* wl = Wlo + (8 * nt + mp.g) * HP + (mp.t ^ swz);
+    const float* wh4 = Whi + (8 * nt + mp.g) * HP + ((mp.t + 4) ^ swz);
+    const float* wl4 = Wlo + (8 * nt + mp.g) * HP + ((mp.t + 4) ^ swz);
 #pragma unroll 2
     for (int k0 = 0; k0 < 64; k0 += 8) {
       uint32_t ah[4], al[4], bh[2], bl[2];
       split_tf32(ap[k0 * SP], ah[0], al[0]);
-      split_tf32(ap[k0 * SP + 8], ah[1], al[1]);
+      split_tf32(ap8[k0 * SP], ah[1], al[1]);
       split_tf32(ap[(k0 + 4) * SP], ah[2], al[2]);
-      split_tf32(ap[(k0 + 4) * SP + 8], ah[3], al[3]);
-      bh[0] = __float_as_uint(wh[k0]); bh[1] = __float_as_uint(wh[k0 + 4]);
-      bl[0] = __float_as_uint(wl[k0]); bl[1] = __float_as_uint(wl[k0 + 4]);
+      split_tf32(ap8[(k0 + 4) * SP], ah[3], al[3]);
+      bh[0] = __float_as_uint(wh[k0]); bh[1] = __float_as_uint(wh4[k0]);
+      bl[0] = __float_as_uint(wl[k0]); bl[1] = __float_as_uint(wl4[k0]);
       mma_3xtf32(c, ah, al, bh, bl);
     }
     const int i = 8 * nt + 2 * mp.t;
@@ -229,23 +239,28 @@ __device__ __noinline__ void gemm_bwd_mma(const float* __restrict__ Whi, const f
   float c[4][4];
 #pragma unroll
   for (int nt = 0; nt < 4; ++nt) c[nt][0] = c[nt][1] = c[nt][2] = c[nt][3] = 0.f;
-  const float* ap = Dl + mp.t * SP + mp.s0 + mp.g;
-  const float* wh = Whi + (mp.m0 + mp.g) * HP + mp.t;
-  const float* wl = Wlo + (mp.m0 + mp.g) * HP + mp.t;
+  const int sw = (mp.t & 1) << 3;       // activation-tile swizzle of the delta rows k0+t / k0+4+t
+  const float* ap = Dl + mp.t * SP + mp.s0 + (mp.g ^ sw);
+  const float* ap8 = Dl + mp.t * SP + mp.s0 + ((mp.g + 8) ^ sw);
+  const int swz = mp.g & 4;             // row (m0 + 8 nt + g) has bit 2 == bit 2 of g: its columns are stored ^ 4
+  const float* wh = Whi + (mp.m0 + mp.g) * HP + (mp.t ^ swz);
+  const float* wl = Wlo + (mp.m0 + mp.g) * HP + (mp.t ^ swz);
+  const float* wh4 = Whi + (mp.m0 + mp.g) * HP + ((mp.t + 4) ^ swz);
+  const float* wl4 = Wlo + (mp.m0 + mp.g) * HP + ((mp.t + 4) ^ swz);
 #pragma unroll 2
   for (int k0 = 0; k0 < 64; k0 += 8) {
     uint32_t ah[4], al[4];
     split_tf32(ap[k0 * SP], ah[0], al[0]);
-    split_tf32(ap[k0 * SP + 8], ah[1], al[1]);
+    split_tf32(ap8[k0 * SP], ah[1], al[1]);
     split_tf32(ap[(k0 + 4) * SP], ah[2], al[2]);
-    split_tf32(ap[(k0 + 4) * SP + 8], ah[3], al[3]);
+    split_tf32(ap8[(k0 + 4) * SP], ah[3], al[3]);
     uint32_t bh[4][2], bl[4][2];
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt) {
       bh[nt][0] = __float_as_uint(wh[8 * nt * HP + k0]);
-      bh[nt][1] = __float_as_uint(wh[8 * nt * HP + k0 + 4]);
+      bh[nt][1] = __float_as_uint(wh4[8 * nt * HP + k0]);
       bl[nt][0] = __float_as_uint(wl[8 * nt * HP + k0]);
-      bl[nt][1] = __float_as_uint(wl[8 * nt * HP + k0 + 4]);
+      bl[nt][1] = __float_as_uint(wl4[8 * nt * HP + k0]);
     }
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt) mma_tf32(c[nt], al, bh[nt]);
@@ -257,7 +272,7 @@ __device__ __noinline__ void gemm_bwd_mma(const float* __restrict__ Whi, const f
 #pragma unroll
   for (int nt = 0; nt < 4; ++nt) {
     float* p = D + (mp.m0 + 8 * nt + 2 * mp.t) * SP + mp.s0 + mp.g;
-    p[0] *= c[nt][0]; p[SP] *= c[nt][1]; p[8] *= c[nt][2]; p[SP + 8] *= c[nt][3];
+    p[0] *= c[nt][0]; p[SP + 8] *= c[nt][1]; p[8] *= c[nt][2]; p[SP] *= c[nt][3];
   }
 }
 
@@ -268,7 +283,7 @@ __device__ __noinline__ void gemm_bwd_mma(const float* __restrict__ Whi, const f
 // ---------------------------------------------------------------------------------------------
 template <int S, int NT>
 __device__ __noinline__ void dw_accum_mma(const float* __restrict__ Dl, int ldd, const float* __restrict__ Xl, int ldx,
-                                          int RI, float* __restrict__ dst, int ld, int woff) {
+                                          int RI, float* __restrict__ dst, int ld, int woff, bool swz_x) {
   constexpr int NW = NT / 32;
   const int w = ((threadIdx.x >> 5) + NW - (woff % NW)) % NW, l = threadIdx.x & 31, g = l >> 2, t = l & 3;
   const int ntiles = (RI + 7) >> 3, npairs = (ntiles + 1) >> 1;
@@ -278,21 +293,24 @@ __device__ __noinline__ void dw_accum_mma(const float* __restrict__ Dl, int ldd,
     float c[2][4];
 #pragma unroll
     for (int q = 0; q < 2; ++q) c[q][0] = c[q][1] = c[q][2] = c[q][3] = 0.f;
+    // both delta rows (o0+g, o0+g+8) and X rows (i0+g, i0+8+g) have parity g & 1: activation-tile column swizzle
+    const int swa = (g & 1) << 3, swb = swz_x ? swa : 0;
     const float* ap = Dl + (o0 + g) * ldd + t;
     const float* bp = Xl + (i0 + g) * ldx + t;
 #pragma unroll 2
     for (int s = 0; s < S; s += 8) {
       uint32_t ah[4], al[4], bh[2], bl[2];
-      split_tf32(ap[s], ah[0], al[0]);
-      split_tf32(ap[8 * ldd + s], ah[1], al[1]);
-      split_tf32(ap[s + 4], ah[2], al[2]);
-      split_tf32(ap[8 * ldd + s + 4], ah[3], al[3]);
+      const int sa = s ^ swa, sb = s ^ swb;
+      split_tf32(ap[sa], ah[0], al[0]);
+      split_tf32(ap[8 * ldd + sa], ah[1], al[1]);
+      split_tf32(ap[sa + 4], ah[2], al[2]);
+      split_tf32(ap[8 * ldd + sa + 4], ah[3], al[3]);
       uint32_t ch[2], cl[2];
-      split_tf32(bp[s], bh[0], bl[0]);
-      split_tf32(bp[s + 4], bh[1], bl[1]);
+      split_tf32(bp[sb], bh[0], bl[0]);
+      split_tf32(bp[sb + 4], bh[1], bl[1]);
       if (two) {
-        split_tf32(bp[8 * ldx + s], ch[0], cl[0]);
-        split_tf32(bp[8 * ldx + s + 4], ch[1], cl[1]);
+        split_tf32(bp[8 * ldx + sb], ch[0], cl[0]);
+        split_tf32(bp[8 * ldx + sb + 4], ch[1], cl[1]);
         mma_tf32(c[0], al, bh); mma_tf32(c[1], al, ch);
         mma_tf32(c[0], ah, bl); mma_tf32(c[1], ah, cl);
         mma_tf32(c[0], ah, bh); mma_tf32(c[1], ah, ch);

@@ -46,6 +46,9 @@ struct NetL {
   int in8;            // in rounded up to 8 (k extent of the layer-1 tensor-core GEMM)
   // torch flat parameter offsets
   int g_w1, g_b1, g_w2, g_b2, g_w3, g_b3, nparam;
+  // accumulator layout in shared memory (= torch layout except that W2 rows are padded to ldw2 floats so that the
+  // fragment-wise read-modify-write of dw_accum_mma is not an 8-way bank conflict)
+  int d_w1, d_b1, d_w2, d_b2, d_w3, d_b3, ldw2, nacc;
 };
 
 struct KParams {
@@ -287,7 +290,8 @@ __device__ __noinline__ void delta_from_out(const float* __restrict__ W3, const 
 // of the (S+4)-strided tiles -> conflict-free float4 shared loads.
 template <int HD, int S, int NT, int TO, int TI>
 __device__ __noinline__ void dw_accum(const float* __restrict__ Dl, int ldd, int RO, const float* __restrict__ Xl,
-                                      int ldx, int RI, float* __restrict__ dst, int ld, int toff = 0) {
+                                      int ldx, int RI, float* __restrict__ dst, int ld, int toff = 0,
+                                      bool swz_x = false) {
   const int tiles_o = (RO + TO - 1) / TO, tiles_i = (RI + TI - 1) / TI;
   for (int tile = (threadIdx.x + NT - (toff % NT)) % NT; tile < tiles_o * tiles_i; tile += NT) {
     const int ti = tile % tiles_i, to = tile / tiles_i;
@@ -298,17 +302,22 @@ __device__ __noinline__ void dw_accum(const float* __restrict__ Dl, int ldd, int
       for (int q = 0; q < TI; ++q) acc[j][q] = 0.f;
     const float* dp[TO];
     const float* xp[TI];
+    int swx[TI];      // activation-tile swizzle: odd rows are stored with column ^ 8
 #pragma unroll
     for (int j = 0; j < TO; ++j) dp[j] = Dl + min(to + tiles_o * j, RO - 1) * ldd;
 #pragma unroll
-    for (int q = 0; q < TI; ++q) xp[q] = Xl + min(ti + tiles_i * q, RI - 1) * ldx;
+    for (int q = 0; q < TI; ++q) {
+      const int row = min(ti + tiles_i * q, RI - 1);
+      xp[q] = Xl + row * ldx;
+      swx[q] = swz_x ? (row & 1) << 3 : 0;
+    }
 #pragma unroll 2
     for (int s = 0; s < S; s += 4) {
       float4 d[TO], x[TI];
 #pragma unroll
       for (int j = 0; j < TO; ++j) d[j] = *reinterpret_cast<const float4*>(dp[j] + s);
 #pragma unroll
-      for (int q = 0; q < TI; ++q) x[q] = *reinterpret_cast<const float4*>(xp[q] + s);
+      for (int q = 0; q < TI; ++q) x[q] = *reinterpret_cast<const float4*>(xp[q] + (s ^ swx[q]));
 #pragma unroll
       for (int j = 0; j < TO; ++j)
 #pragma unroll
@@ -581,10 +590,10 @@ template <int HD, int S, int NT, bool FULL, bool OUT>
 __device__ __forceinline__ void mlp_forward(const NetL& L, const Tiles& t, float* Zout) {
   constexpr int XS = NT + 4, HID = HD;
   if constexpr (HD == 64) {
-    gemm_fwd_mma<S, NT, hp_of(HD)>(t.W + L.o_w1, t.W + L.o_w1l, t.X, XS, L.in8, t.W + L.o_b1, t.H1);
+    gemm_fwd_mma<S, NT, hp_of(HD)>(t.W + L.o_w1, t.W + L.o_w1l, t.X, XS, L.in8, t.W + L.o_b1, t.H1, false);
     act_pass_frag<S, NT>(t.H1, FULL ? t.D1 : nullptr, L.hact, nullptr, nullptr, 0, nullptr, 0);
     pair_sync();
-    gemm_fwd_mma<S, NT, hp_of(HD)>(t.W + L.o_w2, t.W + L.o_w2l, t.H1, S + 4, HID, t.W + L.o_b2, t.H2);
+    gemm_fwd_mma<S, NT, hp_of(HD)>(t.W + L.o_w2, t.W + L.o_w2l, t.H1, S + 4, HID, t.W + L.o_b2, t.H2, true);
     act_pass_frag<S, NT>(t.H2, FULL ? t.D2 : nullptr, L.hact, OUT ? t.W + L.o_w3 : nullptr, t.W + L.o_b3, L.out,
                          Zout, XS);
     pair_sync();
@@ -622,12 +631,12 @@ __device__ __forceinline__ void mlp_backward(const NetL& L, const Tiles& t, bool
     gemm_bwd_mma<S, NT, HPc>(t.W + L.o_w2, t.W + L.o_w2l, t.D2, t.D1);            // D1 <- delta1 (stripe)
     if (WANT_DW) {
       __syncthreads();                                                            // every stripe's deltas are ready
-      dw_accum_mma<S, NT>(t.D2, SP, t.H1, SP, HID, t.dW + L.g_w2, HID, 0);
-      dw_accum_mma<S, NT>(t.D1, SP, t.X, XS, L.in, t.dW + L.g_w1, L.in, NT / 64);
-      rowsum_accum<HD, S, NT>(t.D2, SP, HID, t.dW + L.g_b2, NT / 4);
-      rowsum_accum<HD, S, NT>(t.D1, SP, HID, t.dW + L.g_b1, NT / 4 + 64);
-      dw_accum<HD, S, NT, 1, 4>(t.Z, XS, L.out, t.H2, SP, HID, t.dW + L.g_w3, HID, 3 * NT / 4);
-      rowsum_accum<HD, S, NT>(t.Z, XS, L.out, t.dW + L.g_b3, 3 * NT / 4 + 32);
+      dw_accum_mma<S, NT>(t.D2, SP, t.H1, SP, HID, t.dW + L.d_w2, L.ldw2, 0, true);
+      dw_accum_mma<S, NT>(t.D1, SP, t.X, XS, L.in, t.dW + L.d_w1, L.in, NT / 64, false);
+      rowsum_accum<HD, S, NT>(t.D2, SP, HID, t.dW + L.d_b2, NT / 4);
+      rowsum_accum<HD, S, NT>(t.D1, SP, HID, t.dW + L.d_b1, NT / 4 + 64);
+      dw_accum<HD, S, NT, 1, 4>(t.Z, XS, L.out, t.H2, SP, HID, t.dW + L.d_w3, HID, 3 * NT / 4, true);
+      rowsum_accum<HD, S, NT>(t.Z, XS, L.out, t.dW + L.d_b3, 3 * NT / 4 + 32);
       __syncthreads();                                                            // X / tiles may be overwritten
     } else {
       pair_sync();
