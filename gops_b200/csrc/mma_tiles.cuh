@@ -19,9 +19,11 @@ __device__ __forceinline__ void mma_tf32(float* d, const uint32_t* a, const uint
       : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
-// x = hi + lo exactly; hi carries the top 11 mantissa bits (round-to-nearest), the tensor core truncates lo
+// x = hi + lo exactly; hi carries the top 11 mantissa bits (round-to-nearest, ties away: integer add of half an ulp,
+// then mask -- 2 instructions; cvt.rna.tf32.f32 compiles to 4 on sm_100a because it also screens Inf/NaN, which
+// poison the result either way here), the tensor core truncates lo
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+  hi = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
   lo = __float_as_uint(x - __uint_as_float(hi));
 }
 // d += a * b with the three significant partial products (small ones first)
@@ -63,7 +65,10 @@ __device__ __noinline__ void gemm_fwd_mma(const float* __restrict__ Whi, const f
     const float b0 = bias[mp.m0 + 8 * nt + 2 * mp.t], b1 = bias[mp.m0 + 8 * nt + 2 * mp.t + 1];
     c[nt][0] = b0; c[nt][1] = b1; c[nt][2] = b0; c[nt][3] = b1;
   }
-  const float* ap = Bm + mp.t * ldb + mp.s0 + mp.g;
+  // activation tiles are stored with column ^= (row & 1) << 3: rows k0+t / k0+4+t have parity t & 1
+  const int sw = swz_b ? (mp.t & 1) << 3 : 0;
+  const float* ap = Bm + mp.t * ldb + mp.s0 + (mp.g ^ sw);
+  const float* ap8 = Bm + mp.t * ldb + mp.s0 + ((mp.g + 8) ^ sw);
   // weight planes are stored with column ^= ((row >> 2) & 1) << 2 (bank swizzle that makes BOTH this k-major read
   // and the transposed read of the backward GEMMs conflict-free): rows k0+t keep their columns, rows k0+4+t flip bit 2
   const float* wh = Whi + mp.t * HP + mp.m0 + mp.g;
