@@ -104,6 +104,49 @@ __device__ __forceinline__ void act_fwd_grad(int act, float x, float& h, float& 
   }
 }
 
+// Compile-time activation variants: the per-element `switch (act)` of act_fwd / act_fwd_grad is a branch region per
+// element, which stops the compiler from interleaving independent elements (every element then costs its full
+// dependent-chain latency).  Hot loops dispatch ONCE on the activation id and run a loop specialised on ACT.
+template <int ACT>
+__device__ __forceinline__ float act_fwd_t(float x) {
+  if constexpr (ACT == GOPS_ACT_RELU) return fmaxf(x, 0.f);
+  else if constexpr (ACT == GOPS_ACT_ELU) return x > 0.f ? x : expm1f(x);
+  else if constexpr (ACT == GOPS_ACT_GELU) { float c, q; gelu_parts(x, c, q); return x * c; }
+  else if constexpr (ACT == GOPS_ACT_SELU) return 1.0507009873554805f * (x > 0.f ? x : 1.6732632423543772f * expm1f(x));
+  else if constexpr (ACT == GOPS_ACT_SIGMOID) return 1.f / (1.f + expf(-x));
+  else if constexpr (ACT == GOPS_ACT_TANH) return tanhf(x);
+  else return x;
+}
+template <int ACT>
+__device__ __forceinline__ void act_fwd_grad_t(float x, float& h, float& d) {
+  if constexpr (ACT == GOPS_ACT_RELU) { h = fmaxf(x, 0.f); d = x > 0.f ? 1.f : 0.f; }
+  else if constexpr (ACT == GOPS_ACT_ELU) {
+    const float e = expf(x), em = expm1f(x);
+    h = x > 0.f ? x : em; d = x > 0.f ? 1.f : e;
+  } else if constexpr (ACT == GOPS_ACT_GELU) {
+    float cdf, pdf;
+    gelu_parts(x, cdf, pdf);
+    h = x * cdf; d = cdf + x * pdf;
+  } else if constexpr (ACT == GOPS_ACT_SELU) {
+    const float sc = 1.0507009873554805f, al = 1.6732632423543772f;
+    const float e = expf(x), em = expm1f(x);
+    h = x > 0.f ? sc * x : sc * al * em; d = x > 0.f ? sc : sc * al * e;
+  } else if constexpr (ACT == GOPS_ACT_SIGMOID) { h = 1.f / (1.f + expf(-x)); d = h * (1.f - h); }
+  else if constexpr (ACT == GOPS_ACT_TANH) { h = tanhf(x); d = 1.f - h * h; }
+  else { h = x; d = 1.f; }
+}
+// GOPS_ACT_SWITCH(act, M): expands M(ACT) for the runtime activation id `act` (M is a one-argument macro)
+#define GOPS_ACT_SWITCH(act, M)                 \
+  switch (act) {                                \
+    case GOPS_ACT_RELU: M(GOPS_ACT_RELU); break;       \
+    case GOPS_ACT_ELU: M(GOPS_ACT_ELU); break;         \
+    case GOPS_ACT_GELU: M(GOPS_ACT_GELU); break;       \
+    case GOPS_ACT_SELU: M(GOPS_ACT_SELU); break;       \
+    case GOPS_ACT_SIGMOID: M(GOPS_ACT_SIGMOID); break; \
+    case GOPS_ACT_TANH: M(GOPS_ACT_TANH); break;       \
+    default: M(GOPS_ACT_LINEAR); break;                \
+  }
+
 // angle_normalize, gops/utils/math_utils.py:8-11: ((x + pi) % (2 pi)) - pi with floored modulo,
 // evaluated in fp32 like torch.remainder on a float32 tensor.
 __device__ __forceinline__ float angle_normalize(float x) {

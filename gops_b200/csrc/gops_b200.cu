@@ -13,6 +13,7 @@
 
 #include "kernel.cuh"
 #include "aux_kernels.cuh"
+#include "mlp_tc.cuh"
 
 using namespace gops;
 
@@ -161,6 +162,8 @@ struct gops_b200_plan {
   size_t ext_ref_floats = 0;
   float* xbuf = nullptr;
   size_t xbuf_floats = 0;
+  float* blob_tc = nullptr;     // tcgen05 inference path: chunk-major hi / lo weight planes
+  int blob_tc_floats = 0;
   float* osc = nullptr;   // obs scale | shift, 2 * obs_dim floats
   bool attr_set[4][4] = {};   // [alg][cfg]
   bool timing = false;
@@ -499,14 +502,15 @@ int gops_b200_plan_destroy(gops_b200_plan* pl) {
   ENTRY("gops_b200_plan_destroy(gops_b200_plan* p");
   if (!pl) return 0;
   if (pl->ev0) { cudaEventDestroy(pl->ev0); cudaEventDestroy(pl->ev1); }
-  void* ptrs[] = {pl->gpow, pl->blob_pol, pl->blob_val, pl->blob_vtg, pl->tape, pl->partial, pl->ext_ref, pl->xbuf, pl->osc};
-  const char* names[] = {"gpow", "blob_pol", "blob_val", "blob_vtg", "tape", "partial", "ext_ref", "xbuf", "osc"};
+  void* ptrs[] = {pl->gpow, pl->blob_pol, pl->blob_val, pl->blob_vtg, pl->tape, pl->partial, pl->ext_ref, pl->xbuf, pl->osc,
+                  pl->blob_tc};
+  const char* names[] = {"gpow", "blob_pol", "blob_val", "blob_vtg", "tape", "partial", "ext_ref", "xbuf", "osc", "blob_tc"};
   if (getenv("GOPS_B200_DEBUG")) {
     fprintf(stderr, "[gops_b200] destroy plan %p alg %d model %d:", (void*)pl, pl->desc.alg, pl->desc.model);
-    for (int i = 0; i < 9; ++i) fprintf(stderr, " %s=%p", names[i], ptrs[i]);
+    for (int i = 0; i < 10; ++i) fprintf(stderr, " %s=%p", names[i], ptrs[i]);
     fprintf(stderr, "\n");
   }
-  for (int i = 0; i < 9; ++i) {
+  for (int i = 0; i < 10; ++i) {
     const cudaError_t e = cudaFree(ptrs[i]);
     if (e != cudaSuccess) {
       (void)cudaGetLastError();
@@ -554,12 +558,66 @@ int gops_b200_rollout_trace(gops_b200_plan* pl, const gops_b200_batch* b, const 
   return launch_rollout(pl, b, ALG_TRACE, st, nullptr, nullptr);
 }
 
+// tcgen05 / TMEM inference (mlp_tc.cuh).  GOPS_B200_INFER=tc|mma forces one of the two 64-wide paths.
+static bool infer_use_tc(const gops_b200_plan* pl, int64_t batch) {
+  if (pl->kp.hid != 64) return false;
+  const char* e = getenv("GOPS_B200_INFER");
+  if (e && !strcmp(e, "mma")) return false;
+  if (e && !strcmp(e, "tc")) return true;
+  return batch >= 4096;
+}
+
+static int infer_tc(gops_b200_plan* pl, const float* params, const NetL& L, const float* obs, int64_t batch,
+                    float virtual_t, float* out, cudaStream_t st, bool squash) {
+  TcNet T;
+  memset(&T, 0, sizeof(T));
+  T.in = L.in; T.obs = L.obs; T.out = L.out; T.hact = L.hact; T.time_input = L.time_input; T.k1 = L.in8;
+  T.g_w1 = L.g_w1; T.g_b1 = L.g_b1; T.g_w2 = L.g_w2; T.g_b2 = L.g_b2; T.g_w3 = L.g_w3; T.g_b3 = L.g_b3;
+  int o = 0;
+  T.o_w1h = o; o += 64 * T.k1;
+  T.o_w1l = o; o += 64 * T.k1;
+  T.o_w2h = o; o += 64 * 64;
+  T.o_w2l = o; o += 64 * 64;
+  T.o_w3 = o; o += round4(T.out * 64);
+  T.o_b1 = o; o += 64;
+  T.o_b2 = o; o += 64;
+  T.o_b3 = o; o += 4;
+  T.blob = o;
+  T.squash = squash ? 1 : 0;
+  for (int j = 0; j < MAXA; ++j) { T.half[j] = pl->kp.pol_half[j]; T.mid[j] = pl->kp.pol_mid[j]; }
+  const int wgs = tc_infer_smem_bytes(T, 2) <= (size_t)pl->max_smem ? 2 : 1;
+  const size_t smem = tc_infer_smem_bytes(T, wgs);
+  if (smem > (size_t)pl->max_smem) return fail("tcgen05 inference: input width does not fit in shared memory");
+  if (pl->blob_tc_floats < T.blob) {
+    if (pl->blob_tc) cudaFree(pl->blob_tc);
+    pl->blob_tc = nullptr; pl->blob_tc_floats = 0;
+    CUDA_OK(cudaMalloc(&pl->blob_tc, (size_t)T.blob * sizeof(float)));
+    pl->blob_tc_floats = T.blob;
+  }
+  pack_params_tc_kernel<<<8, 256, 0, st>>>(params, T, pl->blob_tc);
+  CUDA_OK_L(cudaGetLastError(), "launch#tc-pack");
+  static bool attr = false;
+  if (!attr) {
+    CUDA_OK(cudaFuncSetAttribute(mlp_infer_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, pl->max_smem));
+    CUDA_OK(cudaFuncSetAttribute(mlp_infer_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, pl->max_smem));
+    attr = true;
+  }
+  const long long tiles = (batch + TC_TILE - 1) / TC_TILE;
+  const long long ctas = (tiles + wgs - 1) / wgs;
+  const int grid = (int)(ctas < pl->sm_count ? ctas : pl->sm_count);
+  if (wgs == 2) mlp_infer_tc_kernel<2><<<grid, 256, smem, st>>>(T, pl->blob_tc, obs, batch, virtual_t, out);
+  else mlp_infer_tc_kernel<1><<<grid, 128, smem, st>>>(T, pl->blob_tc, obs, batch, virtual_t, out);
+  CUDA_OK_L(cudaGetLastError(), "launch#tc-infer");
+  return 0;
+}
+
 static int infer_common(gops_b200_plan* pl, const float* params, int use_val, const float* obs, int64_t batch,
                         float virtual_t, float* out, void* stream, bool squash) {
   if (!pl || !params || !obs || !out) return fail("null argument");
   if (batch <= 0) return fail("empty batch");
   cudaStream_t st = (cudaStream_t)stream;
   const NetL& L = use_val ? pl->kp.val : pl->kp.pol;
+  if (infer_use_tc(pl, batch)) return infer_tc(pl, params, L, obs, batch, virtual_t, out, st, squash);
   float* blob = use_val ? pl->blob_val : pl->blob_pol;
   if (launch_pack(params, L, pl->kp.hid, blob, st)) return 1;
   const int cfg = pick_config(pl, batch, true);
@@ -641,11 +699,16 @@ int gops_b200_mlp_forward(const gops_b200_mlp_desc* net, const float* params, co
   tmp.blob_pol = scratch->blob_pol;
   tmp.xbuf = scratch->xbuf;
   tmp.xbuf_floats = scratch->xbuf_floats;
+  tmp.blob_tc = scratch->blob_tc;
+  tmp.blob_tc_floats = scratch->blob_tc_floats;
   const int rc = infer_common(&tmp, params, 0, obs, batch, virtual_t, out, stream, act_low != nullptr);
   scratch->xbuf = tmp.xbuf;              // infer_common may have (re)allocated the wide-net scratch
   scratch->xbuf_floats = tmp.xbuf_floats;
+  scratch->blob_tc = tmp.blob_tc;
+  scratch->blob_tc_floats = tmp.blob_tc_floats;
   tmp.blob_pol = nullptr;
   tmp.xbuf = nullptr;
+  tmp.blob_tc = nullptr;
   return rc;
 }
 

@@ -114,10 +114,12 @@ __device__ __forceinline__ void pair_sync() {
 // If W3 != nullptr the output layer is fused: every thread dots its 8 features x 2 samples with W3, the quad
 // (4 lanes, 32 features) is reduced by shuffles and lane t == 0 stores the half-stripe partial
 //   Zout[(4 * half + a) * ldz + s]   (half 0 also adds the bias b3[a]); consumers add the two halves.
-template <int S, int NT>
-__device__ __noinline__ void act_pass_frag(float* __restrict__ H, float* __restrict__ D, int act,
-                                           const float* __restrict__ W3, const float* __restrict__ b3, int out,
-                                           float* __restrict__ Zout, int ldz) {
+// ACT / FULL are compile-time so that the four independent elements of an iteration interleave (a per-element
+// `switch (act)` is a branch region per element and serialises their dependent chains).
+template <int S, int NT, int ACT, bool FULL>
+__device__ __noinline__ void act_pass_frag_t(float* __restrict__ H, float* __restrict__ D,
+                                             const float* __restrict__ W3, const float* __restrict__ b3, int out,
+                                             float* __restrict__ Zout, int ldz) {
   constexpr int SP = S + 4;
   const MmaMap<S, NT> mp;
   float z0[MAXA], z1[MAXA];
@@ -131,14 +133,14 @@ __device__ __noinline__ void act_pass_frag(float* __restrict__ H, float* __restr
     // elements (m, g) (m+1, g) (m, g+8) (m+1, g+8); the odd row m+1 is stored with its column ^ 8
     const float p0 = hp[0], p1 = hp[SP + 8], p2 = hp[8], p3 = hp[SP];
     float h0, h1, h2, h3;
-    if (D != nullptr) {
+    if constexpr (FULL) {
       float d0, d1, d2, d3;
-      act_fwd_grad(act, p0, h0, d0); act_fwd_grad(act, p1, h1, d1);
-      act_fwd_grad(act, p2, h2, d2); act_fwd_grad(act, p3, h3, d3);
+      act_fwd_grad_t<ACT>(p0, h0, d0); act_fwd_grad_t<ACT>(p1, h1, d1);
+      act_fwd_grad_t<ACT>(p2, h2, d2); act_fwd_grad_t<ACT>(p3, h3, d3);
       float* dp = D + base;
       dp[0] = d0; dp[SP + 8] = d1; dp[8] = d2; dp[SP] = d3;
     } else {
-      h0 = act_fwd(act, p0); h1 = act_fwd(act, p1); h2 = act_fwd(act, p2); h3 = act_fwd(act, p3);
+      h0 = act_fwd_t<ACT>(p0); h1 = act_fwd_t<ACT>(p1); h2 = act_fwd_t<ACT>(p2); h3 = act_fwd_t<ACT>(p3);
     }
     hp[0] = h0; hp[SP + 8] = h1; hp[8] = h2; hp[SP] = h3;
     if (W3 != nullptr) {
@@ -166,6 +168,19 @@ __device__ __noinline__ void act_pass_frag(float* __restrict__ H, float* __restr
         }
       }
   }
+}
+
+template <int S, int NT>
+__device__ __forceinline__ void act_pass_frag(float* __restrict__ H, float* __restrict__ D, int act,
+                                              const float* __restrict__ W3, const float* __restrict__ b3, int out,
+                                              float* __restrict__ Zout, int ldz) {
+#define GOPS_APF(A)                                                                  \
+  do {                                                                               \
+    if (D != nullptr) act_pass_frag_t<S, NT, A, true>(H, D, W3, b3, out, Zout, ldz); \
+    else act_pass_frag_t<S, NT, A, false>(H, D, W3, b3, out, Zout, ldz);             \
+  } while (0)
+  GOPS_ACT_SWITCH(act, GOPS_APF)
+#undef GOPS_APF
 }
 
 // D[m][s] <- D[m][s] * sum_a W3[a][m] * Zb[a][s] on the fragment-owned elements (stripe-local delta2)
