@@ -125,6 +125,8 @@ RolloutFn rollout_fn_vehconti(int hid, int cfg, int alg);
 RolloutFn rollout_fn_vehtrack(int hid, int cfg, int alg);
 StepFn step_fn_idp();
 StepFn step_fn_lq();
+RolloutFn rollout_fn_hy_idp(int alg);   // hybrid kernels: tcgen05 forward sweep + mma.sync reverse sweep
+RolloutFn rollout_fn_hy_lq(int alg);
 }  // namespace gops
 
 namespace {
@@ -135,6 +137,13 @@ RolloutFn rollout_fn(int model, int hid, int cfg, int alg) {
     case GOPS_MODEL_LQ: return rollout_fn_lq(hid, cfg, alg);
     case GOPS_MODEL_VEH3DOFCONTI: return rollout_fn_vehconti(hid, cfg, alg);
     case GOPS_MODEL_VEH3DOF_TRACKING: return rollout_fn_vehtrack(hid, cfg, alg);
+    default: return nullptr;
+  }
+}
+RolloutFn rollout_fn_hy(int model, int alg) {
+  switch (model) {
+    case GOPS_MODEL_IDPENDULUM: return rollout_fn_hy_idp(alg);
+    case GOPS_MODEL_LQ: return rollout_fn_hy_lq(alg);
     default: return nullptr;
   }
 }
@@ -164,6 +173,11 @@ struct gops_b200_plan {
   size_t xbuf_floats = 0;
   float* blob_tc = nullptr;     // tcgen05 inference path: chunk-major hi / lo weight planes
   int blob_tc_floats = 0;
+  // hybrid rollout kernel (tcgen05 forward sweep): policy NetL with chunk-major blob offsets + its packed blob
+  bool hy_ok = false;
+  NetL pol_tc;
+  float* blob_pol_tc = nullptr;
+  bool hy_attr_set[4] = {};
   float* osc = nullptr;   // obs scale | shift, 2 * obs_dim floats
   bool attr_set[4][4] = {};   // [alg][cfg]
   bool timing = false;
@@ -186,6 +200,40 @@ size_t infer_smem_bytes(const KParams& kp, int S, int NT) {
   const int SP = S + 4, XS = NT + 4, HID = kp.hid;
   if (HID > 64) return sizeof(float) * (size_t)(4 + 2 * HID * SP + 8 * XS + (size_t)kp.inp_max * SP + 2 * 16 * (HID + 4));
   return sizeof(float) * (size_t)(4 + kp.w_floats + kp.inp_max * XS + 2 * HID * SP + 8 * XS);
+}
+
+// NetL of the tcgen05 forward: same geometry, blob = chunk-major planes (W1 padded to TC_K1 inputs)
+void make_net_tc(const NetL& base, NetL& L) {
+  L = base;
+  int o = 0;
+  L.o_w1 = o; o += 64 * TC_K1;
+  L.o_w1l = o; o += 64 * TC_K1;
+  L.o_w2 = o; o += 64 * 64;
+  L.o_w2l = o; o += 64 * 64;
+  L.o_w3 = o; o += round4(L.out * 64);
+  L.o_b1 = o; o += 64;
+  L.o_b2 = o; o += 64;
+  L.o_b3 = o; o += 4;
+  L.blob = o;
+}
+// GOPS_B200_ROLLOUT=hy|mma forces the hybrid (tcgen05 forward sweep) / pure mma.sync rollout kernel
+bool rollout_use_hy(const gops_b200_plan* pl, long long batch) {
+  if (!pl->hy_ok) return false;
+  const char* e = getenv("GOPS_B200_ROLLOUT");
+  if (e && !strcmp(e, "mma")) return false;
+  if (e && !strcmp(e, "hy")) return true;
+  return batch >= (long long)pl->sm_count * 512;     // the S = 128 / NT = 512 configuration is the one in use
+}
+int launch_pack_tc(const float* flat, const NetL& L, float* blob, cudaStream_t st) {
+  TcNet T;
+  memset(&T, 0, sizeof(T));
+  T.in = L.in; T.obs = L.obs; T.out = L.out; T.hact = L.hact; T.time_input = L.time_input; T.k1 = TC_K1;
+  T.g_w1 = L.g_w1; T.g_b1 = L.g_b1; T.g_w2 = L.g_w2; T.g_b2 = L.g_b2; T.g_w3 = L.g_w3; T.g_b3 = L.g_b3;
+  T.o_w1h = L.o_w1; T.o_w1l = L.o_w1l; T.o_w2h = L.o_w2; T.o_w2l = L.o_w2l;
+  T.o_w3 = L.o_w3; T.o_b1 = L.o_b1; T.o_b2 = L.o_b2; T.o_b3 = L.o_b3; T.blob = L.blob;
+  pack_params_tc_kernel<<<8, 256, 0, st>>>(flat, T, blob);
+  CUDA_OK_L(cudaGetLastError(), "launch#tc-pack2");
+  return 0;
 }
 
 Config config_of(const gops_b200_plan* pl, int cfg) { return pl->kp.hid > 64 ? kWideConfig : kConfigs[cfg]; }
@@ -266,11 +314,18 @@ int launch_rollout(gops_b200_plan* pl, const gops_b200_batch* b, int alg, cudaSt
       return fail("veh3dof_tracking: reference too short for t + horizon + pre_horizon + 1 points");
   }
   KParams& kp = pl->kp;
-  const int cfg = pick_config(pl, b->batch, false);
+  const bool hy = rollout_use_hy(pl, b->batch);
+  const int cfg = hy ? 0 : pick_config(pl, b->batch, false);
   if (cfg < 0) return fail("no kernel configuration fits in shared memory");
   const int S = config_of(pl, cfg).S, NT = config_of(pl, cfg).NT;
-  RolloutFn fn = rollout_fn(pl->desc.model, kp.hid, cfg, alg);
+  RolloutFn fn = hy ? rollout_fn_hy(pl->desc.model, alg) : rollout_fn(pl->desc.model, kp.hid, cfg, alg);
   if (!fn) return fail("env model kind not built into this library");
+  const int w_floats_plan = kp.w_floats;
+  if (hy) {
+    kp.pol_tc = pl->pol_tc;
+    kp.blob_pol_tc = pl->blob_pol_tc;
+    if (pl->pol_tc.blob > kp.w_floats) kp.w_floats = pl->pol_tc.blob;   // one staging region for both blob layouts
+  }
   kp.alg = alg;
   kp.batch = b->batch;
   kp.n_tiles = (int)((b->batch + NT - 1) / NT);
@@ -282,10 +337,12 @@ int launch_rollout(gops_b200_plan* pl, const gops_b200_batch* b, int alg, cudaSt
   const NetL& upd = (alg == ALG_PEV) ? kp.val : kp.pol;
   kp.part_stride = round4(upd.nparam + 4);
   kp.dw_floats = round4(upd.nacc);
-  const size_t smem = rollout_smem_bytes(kp, S, NT);
-  if (!pl->attr_set[alg][cfg]) {
+  const size_t smem = rollout_smem_bytes(kp, S, NT) + (hy ? 12 * sizeof(float) : 0);   // hybrid: 16-float header
+  if (smem > (size_t)pl->max_smem) { kp.w_floats = w_floats_plan; return fail("rollout kernel does not fit in shared memory"); }
+  bool& attr = hy ? pl->hy_attr_set[alg] : pl->attr_set[alg][cfg];
+  if (!attr) {
     CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, pl->max_smem));
-    pl->attr_set[alg][cfg] = true;
+    attr = true;
   }
   int occ = 1;
   CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, NT, smem));
@@ -302,6 +359,7 @@ int launch_rollout(gops_b200_plan* pl, const gops_b200_batch* b, int alg, cudaSt
   kp.partial = pl->partial;
   if (pl->timing) CUDA_OK(cudaEventRecord(pl->ev0, st));
   fn<<<grid, NT, smem, st>>>(kp);
+  kp.w_floats = w_floats_plan;
   CUDA_OK_L(cudaGetLastError(), "launch#2");
   if (pl->timing) CUDA_OK(cudaEventRecord(pl->ev1, st));
   pl->last_grid = grid; pl->last_S = S; pl->last_NT = NT; pl->last_smem = smem;
@@ -457,6 +515,16 @@ int gops_b200_plan_create(const gops_b200_plan_desc* d, gops_b200_plan** out) {
     kp.osc = pl->osc;
     kp.osh = pl->osc + od;
   }
+  // hybrid rollout kernel: 64-wide policy whose inputs fit one 16-wide K block, state == obs models
+  if (kp.hid == 64 && kp.pol.in <= TC_K1 && rollout_fn_hy(d->model, d->alg)) {
+    make_net_tc(kp.pol, pl->pol_tc);
+    if (cudaMalloc(&pl->blob_pol_tc, (size_t)pl->pol_tc.blob * sizeof(float)) != cudaSuccess) {
+      gops_b200_plan_destroy(pl);
+      return fail("cudaMalloc failed for plan scratch (tcgen05 policy blob)");
+    }
+    cudaMemset(pl->blob_pol_tc, 0, (size_t)pl->pol_tc.blob * sizeof(float));
+    pl->hy_ok = true;
+  }
   cudaMemset(pl->blob_pol, 0, kp.w_floats * sizeof(float));
   cudaMemset(pl->blob_val, 0, kp.w_floats * sizeof(float));
   cudaMemset(pl->blob_vtg, 0, kp.w_floats * sizeof(float));
@@ -503,14 +571,15 @@ int gops_b200_plan_destroy(gops_b200_plan* pl) {
   if (!pl) return 0;
   if (pl->ev0) { cudaEventDestroy(pl->ev0); cudaEventDestroy(pl->ev1); }
   void* ptrs[] = {pl->gpow, pl->blob_pol, pl->blob_val, pl->blob_vtg, pl->tape, pl->partial, pl->ext_ref, pl->xbuf, pl->osc,
-                  pl->blob_tc};
-  const char* names[] = {"gpow", "blob_pol", "blob_val", "blob_vtg", "tape", "partial", "ext_ref", "xbuf", "osc", "blob_tc"};
+                  pl->blob_tc, pl->blob_pol_tc};
+  const char* names[] = {"gpow", "blob_pol", "blob_val", "blob_vtg", "tape", "partial", "ext_ref", "xbuf", "osc", "blob_tc",
+                         "blob_pol_tc"};
   if (getenv("GOPS_B200_DEBUG")) {
     fprintf(stderr, "[gops_b200] destroy plan %p alg %d model %d:", (void*)pl, pl->desc.alg, pl->desc.model);
-    for (int i = 0; i < 10; ++i) fprintf(stderr, " %s=%p", names[i], ptrs[i]);
+    for (int i = 0; i < 11; ++i) fprintf(stderr, " %s=%p", names[i], ptrs[i]);
     fprintf(stderr, "\n");
   }
-  for (int i = 0; i < 10; ++i) {
+  for (int i = 0; i < 11; ++i) {
     const cudaError_t e = cudaFree(ptrs[i]);
     if (e != cudaSuccess) {
       (void)cudaGetLastError();
@@ -534,6 +603,7 @@ int gops_b200_rollout_grad(gops_b200_plan* pl, const gops_b200_batch* b, const f
   cudaStream_t st = (cudaStream_t)stream;
   const int alg = pl->desc.alg;
   if (launch_pack(policy_params, pl->kp.pol, pl->kp.hid, pl->blob_pol, st)) return 1;
+  if (b && rollout_use_hy(pl, b->batch) && launch_pack_tc(policy_params, pl->pol_tc, pl->blob_pol_tc, st)) return 1;
   if (alg != GOPS_ALG_FHADP) {
     if (!vtarget_params) return fail("vtarget_params required for INFADP");
     if (launch_pack(vtarget_params, pl->kp.val, pl->kp.hid, pl->blob_vtg, st)) return 1;
@@ -553,6 +623,7 @@ int gops_b200_rollout_trace(gops_b200_plan* pl, const gops_b200_batch* b, const 
   if (!pl || !policy_params) return fail("null argument");
   cudaStream_t st = (cudaStream_t)stream;
   if (launch_pack(policy_params, pl->kp.pol, pl->kp.hid, pl->blob_pol, st)) return 1;
+  if (b && rollout_use_hy(pl, b->batch) && launch_pack_tc(policy_params, pl->pol_tc, pl->blob_pol_tc, st)) return 1;
   pl->kp.inv_B = 1.f;
   pl->kp.tr_obs = obs_out; pl->kp.tr_act = act_out; pl->kp.tr_rew = rew_out; pl->kp.tr_done = done_out;
   return launch_rollout(pl, b, ALG_TRACE, st, nullptr, nullptr);

@@ -1,6 +1,7 @@
 // The fused rollout kernel template: forward sweep, terminal value, reverse sweep, gradient partials.
 #pragma once
 #include "models.cuh"
+#include "mlp_tc_fwd.cuh"
 
 namespace gops {
 
@@ -10,11 +11,16 @@ namespace gops {
 // HD = 256 (WG): they do not fit (519 KB of weights) -> weights are read from the packed blob in global memory
 // (L2 resident, generic loads), gradients accumulate directly in this CTA's global partial, X is a per-CTA global
 // scratch; only the activation tiles stay in shared memory.
-template <class M, int HD, int S, int NT, int ALG>
+// HY (hybrid, HD = 64 / S = 128 / NT = 512, policy inputs <= 16): the forward sweep's policy MLP runs on the tcgen05
+// tensor cores with a TMEM accumulator (mlp_tc_fwd.cuh); its operand planes alias the activation tiles, the policy
+// blob is re-staged per chunk in the layout of the sweep that is about to run (chunk-major planes / mma.sync planes).
+template <class M, int HD, int S, int NT, int ALG, bool HY = false>
 __global__ void __launch_bounds__(NT, 1) rollout_kernel(const __grid_constant__ KParams p) {
   constexpr int SP = S + 4, XS = NT + 4, NS = M::NS, HID = HD;
   constexpr int alg = ALG;
   constexpr bool WG = HD > 64;
+  constexpr int HDR = HY ? 16 : 4;     // header floats: weight mbarrier (+ MMA mbarrier, TMEM slot)
+  static_assert(!HY || (HD == 64 && S == 128 && NT == 512), "hybrid tcgen05 forward: 64-wide nets, S = 128, NT = 512");
   extern __shared__ __align__(16) float smem[];
   uint64_t* mbar = reinterpret_cast<uint64_t*>(smem);
   float* part = p.partial + (size_t)blockIdx.x * p.part_stride;
@@ -25,7 +31,7 @@ __global__ void __launch_bounds__(NT, 1) rollout_kernel(const __grid_constant__ 
     t.X = p.xbuf + (size_t)blockIdx.x * p.inp_max * XS;
     t.H1 = smem + 4;
   } else {
-    t.W = smem + 4;
+    t.W = smem + HDR;
     t.dW = t.W + p.w_floats;
     t.X = t.dW + p.dw_floats;
     t.H1 = t.X + p.inp_max * XS;
@@ -35,6 +41,16 @@ __global__ void __launch_bounds__(NT, 1) rollout_kernel(const __grid_constant__ 
   t.D2 = t.H2 + HID * SP;
   t.Z = t.D2 + HID * SP;      // [8][XS]: rows a (+ 4 + a: second half-stripe partial of the fused output layer)
   t.R = t.Z + 8 * XS;         // wide nets only: staging region
+
+  TcCtx cx;                     // hybrid: tcgen05 operand planes inside the (forward-sweep-dead) activation tiles
+  cx.W = t.W;
+  cx.Xp = t.H1;
+  cx.P = cx.Xp + 2 * TC_XPLANE;
+  cx.Zp = cx.P + 2 * TC_PLANE;
+  cx.bar = mbar + 1;
+  cx.ph = 0u;
+  cx.tmem = 0u;
+  static_assert(!HY || 2 * TC_XPLANE + 2 * TC_PLANE + 4 * MAXA * 128 <= 4 * HD * (S + 4), "tcgen05 planes must fit in the tiles");
 
   const int tid = threadIdx.x;
   // column (= sample slot of the chunk) owned by this thread.  Tensor-core path: the 64 threads of warp pair p own
@@ -53,11 +69,20 @@ __global__ void __launch_bounds__(NT, 1) rollout_kernel(const __grid_constant__ 
 
   if (tid == 0) {
     mbar_init(mbar, 1);
+    if (HY) mbar_init(cx.bar, 1);
     fence_mbar_init();
   }
   for (int i = tid; i < p.dw_floats; i += NT) t.dW[i] = 0.f;
   for (int i = tid; i < p.inp_max * XS; i += NT) t.X[i] = 0.f;   // pad rows of the observation tile stay zero
   for (int i = tid; i < 8 * XS; i += NT) t.Z[i] = 0.f;
+  if constexpr (HY) {
+    uint32_t* tslot = reinterpret_cast<uint32_t*>(smem + 4);
+    if (tid < 32) umma::tmem_alloc(tslot, TC_FWD_COLS);
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    cx.tmem = *tslot;
+  }
 
   // TMA bulk copy of a packed weight blob into shared memory (all threads wait on the mbarrier)
   auto stage = [&](const float* gsrc, int floats) {
@@ -92,7 +117,7 @@ __global__ void __launch_bounds__(NT, 1) rollout_kernel(const __grid_constant__ 
     return ts;
   };
 
-  stage(p.blob_pol, P.blob);
+  if (!HY) stage(p.blob_pol, P.blob);
 
   float* tape = p.tape + (size_t)blockIdx.x * (size_t)H * TCH * NT;
   float loss_acc = 0.f, vmean_acc = 0.f, done_acc = 0.f;
@@ -102,7 +127,8 @@ __global__ void __launch_bounds__(NT, 1) rollout_kernel(const __grid_constant__ 
   for (long long pos = r0; pos < r1; pos += NT) {
     const int nv = (int)((r1 - pos) < NT ? (r1 - pos) : NT);
     const int nsub = (nv + S - 1) / S;
-    __syncthreads();
+    if (HY) stage(p.blob_pol_tc, p.pol_tc.blob);   // forward sweep reads the chunk-major planes (leading barrier inside)
+    else __syncthreads();
     load_obs_chunk(pos, nv, nsub * S);
     __syncthreads();
     float st[NS];
@@ -148,15 +174,18 @@ __global__ void __launch_bounds__(NT, 1) rollout_kernel(const __grid_constant__ 
         tape[(k * TCH + NS) * NT + tid] = dn ? 1.f : 0.f;
       }
       if (P.time_input) t.X[(P.in - 1) * XS + col] = (float)(k + 1);
-      scope_sync();
+      if (HY) __syncthreads();     // the tcgen05 forward gathers X columns written by other warp pairs
+      else scope_sync();
       for (int sub = 0; sub < nsub; ++sub) {
         const Tiles ts = sub_tiles(sub);
-        mlp_forward<HD, S, NT, false, true>(P, ts, ts.Z);
+        if constexpr (HY) mlp_forward_tc<NT>(p.pol_tc, cx, ts.X, XS, p.inp_max, ts.Z);
+        else mlp_forward<HD, S, NT, false, true>(P, ts, ts.Z);
       }
       {
         float z[MAXA], a[MAXA], g[MAXA], apol[MAXA];
 #pragma unroll
-        for (int j = 0; j < MAXA; ++j) z[j] = j < P.out ? t.Z[j * XS + col] + t.Z[(4 + j) * XS + col] : 0.f;
+        for (int j = 0; j < MAXA; ++j)   // mma.sync path: two half-stripe partials; tcgen05 path: complete sums in row j
+          z[j] = j < P.out ? (HY ? t.Z[j * XS + col] : t.Z[j * XS + col] + t.Z[(4 + j) * XS + col]) : 0.f;
         if (alg == ALG_FHADP || alg == ALG_PIM) {
 #pragma unroll
           for (int j = 0; j < MAXA; ++j)
@@ -323,7 +352,7 @@ __global__ void __launch_bounds__(NT, 1) rollout_kernel(const __grid_constant__ 
     }
 
     if (valid) loss_acc += -vacc * p.inv_B;
-    if (alg == ALG_PIM) stage(p.blob_pol, P.blob);
+    if (alg == ALG_PIM || HY) stage(p.blob_pol, P.blob);   // reverse sweep: mma.sync planes of the policy
 
     // ================================ reverse sweep ================================
     for (int k = H - 1; k >= 0; --k) {
@@ -497,6 +526,11 @@ __global__ void __launch_bounds__(NT, 1) rollout_kernel(const __grid_constant__ 
     float s = 0.f;
     for (int i = 0; i < NT; ++i) s += red[tid * NT + i];
     part[nparam + tid] = s;
+  }
+  if constexpr (HY) {
+    umma::fence_before_sync();
+    __syncthreads();
+    if (tid < 32) umma::tmem_dealloc(cx.tmem, TC_FWD_COLS);
   }
 }
 

@@ -24,6 +24,14 @@ RolloutFn rollout_fn_lq(int hid, int cfg, int alg) {
     default: return pick<ALG_TRACE>(hid, cfg);
   }
 }
+RolloutFn rollout_fn_hy_lq(int alg) {   // tcgen05 forward sweep + mma.sync reverse sweep
+  switch (alg) {
+    case ALG_FHADP: return rollout_kernel<ModelLq, 64, 128, 512, ALG_FHADP, true>;
+    case ALG_PIM: return rollout_kernel<ModelLq, 64, 128, 512, ALG_PIM, true>;
+    case ALG_PEV: return rollout_kernel<ModelLq, 64, 128, 512, ALG_PEV, true>;
+    default: return rollout_kernel<ModelLq, 64, 128, 512, ALG_TRACE, true>;
+  }
+}
 StepFn step_fn_lq() { return model_step_kernel<ModelLq>; }
 
 }  // namespace gops
