@@ -294,6 +294,12 @@ def main():
             rate, sec = cpu_update_rate(args.cpu_batch, 3, 1, threads)
             cpu = {"value": rate, "unit": "env-steps/s", "cores": threads, "kind": "port",
                    "sample": f"B={args.cpu_batch}, H={H}, 3 updates after 1 warm-up (oracle/gops_oracle.py)"}
+        # kernels of this library per update: pack_params, [pack_params_tc,] rollout_kernel, reduce_partials, adam
+        sm_count = torch.cuda.get_device_properties(0).multi_processor_count
+        hybrid = os.environ.get("GOPS_B200_ROLLOUT", "") != "mma" and Bg >= sm_count * 512
+        launches_per_step = 5 if hybrid else 4
+        roof["launch"]["kernel_path"] = ("hybrid: tcgen05/TMEM forward sweep + mma.sync reverse sweep" if hybrid
+                                         else "mma.sync forward and reverse sweeps")
         line = {
             "metric": "batched env-steps/sec (FHADP rollout+update)", "value": value, "unit": "env-steps/s",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_total / K, "higher_is_better": True,
@@ -305,7 +311,7 @@ def main():
             "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
             "e2e": {"value": e2e, "unit": "env-steps/s", "h2d_bytes_per_step": batch_bytes, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / K},
-            "gpu_launches": 4 * K,
+            "gpu_launches": launches_per_step * K,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
