@@ -14,6 +14,7 @@
 #include "kernel.cuh"
 #include "aux_kernels.cuh"
 #include "mlp_tc.cuh"
+#include <cuda_bf16.h>
 
 using namespace gops;
 
@@ -127,6 +128,8 @@ StepFn step_fn_idp();
 StepFn step_fn_lq();
 RolloutFn rollout_fn_hy_idp(int alg);   // hybrid kernels: tcgen05 forward sweep + mma.sync reverse sweep
 RolloutFn rollout_fn_hy_lq(int alg);
+RolloutFn rollout_fn_tc_idp(int alg);   // full tcgen05 kernels (BF16x3, TMEM-resident weight gradients)
+RolloutFn rollout_fn_tc_lq(int alg);
 }  // namespace gops
 
 namespace {
@@ -144,6 +147,13 @@ RolloutFn rollout_fn_hy(int model, int alg) {
   switch (model) {
     case GOPS_MODEL_IDPENDULUM: return rollout_fn_hy_idp(alg);
     case GOPS_MODEL_LQ: return rollout_fn_hy_lq(alg);
+    default: return nullptr;
+  }
+}
+RolloutFn rollout_fn_tc(int model, int alg) {
+  switch (model) {
+    case GOPS_MODEL_IDPENDULUM: return rollout_fn_tc_idp(alg);
+    case GOPS_MODEL_LQ: return rollout_fn_tc_lq(alg);
     default: return nullptr;
   }
 }
@@ -178,6 +188,12 @@ struct gops_b200_plan {
   NetL pol_tc;
   float* blob_pol_tc = nullptr;
   bool hy_attr_set[4] = {};
+  // full tcgen05 rollout kernel (BF16x3): NetL with the bf16-plane blob offsets, packed blobs
+  bool tc_ok = false;
+  NetL pol_tcf, val_tcf;
+  int w_floats_tcf = 0;
+  float *blob_pol_tcf = nullptr, *blob_val_tcf = nullptr, *blob_vtg_tcf = nullptr;
+  bool tc_attr_set[4] = {};
   float* osc = nullptr;   // obs scale | shift, 2 * obs_dim floats
   bool attr_set[4][4] = {};   // [alg][cfg]
   bool timing = false;
@@ -216,6 +232,65 @@ void make_net_tc(const NetL& base, NetL& L) {
   L.o_b3 = o; o += 4;
   L.blob = o;
 }
+// NetL of the full tcgen05 path: blob = 3 bf16 planes of W1 ([2][64][8]) and W2 ([8][64][8]), then fp32 W3, b1, b2, b3
+// (offsets in floats); shared-memory accumulators only for W3 / b3 (the rest accumulates in TMEM)
+void make_net_tcf(const NetL& base, NetL& L) {
+  L = base;
+  int o = 0;
+  L.o_w1 = o; o += 3 * tcf::W1PLANE / 4;
+  L.o_w1l = L.o_w1;
+  L.o_w2 = o; o += 3 * tcf::W2PLANE / 4;
+  L.o_w2l = L.o_w2;
+  L.o_w3 = o; o += round4(L.out * 64);
+  L.o_b1 = o; o += 64;
+  L.o_b2 = o; o += 64;
+  L.o_b3 = o; o += 4;
+  L.blob = o;
+  L.d_w3 = 0;
+  L.d_b3 = L.out * 64;
+  L.nacc = L.out * 64 + L.out;
+}
+size_t rollout_smem_bytes_tcf(const KParams& kp) {
+  return sizeof(float) * (size_t)(64 + kp.w_floats + kp.dw_floats + tcf::RED + kp.inp_max * 516 + 8 * 516) +
+         6 * tcf::HPLANE + 3 * tcf::XPLANE + tcf::ONES_B;
+}
+bool rollout_use_tc(const gops_b200_plan* pl) {
+  if (!pl->tc_ok) return false;
+  const char* e = getenv("GOPS_B200_ROLLOUT");
+  return e && !strcmp(e, "tc");
+}
+__global__ void pack_params_tcf_kernel(const float* __restrict__ flat, NetL L, float* __restrict__ blob) {
+  const int n = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
+  __nv_bfloat16* w1 = reinterpret_cast<__nv_bfloat16*>(blob + L.o_w1);
+  __nv_bfloat16* w2 = reinterpret_cast<__nv_bfloat16*>(blob + L.o_w2);
+  auto put3 = [](float w, __nv_bfloat16* dst, int stride) {
+    const __nv_bfloat16 b0 = __float2bfloat16_rn(w);
+    const float r1 = w - __bfloat162float(b0);
+    const __nv_bfloat16 b1 = __float2bfloat16_rn(r1);
+    const float r2 = r1 - __bfloat162float(b1);
+    dst[0] = b0; dst[stride] = b1; dst[2 * stride] = __float2bfloat16_rn(r2);
+  };
+  for (int i = t0; i < 2 * 64 * 8; i += n) {        // plane[kc][row n][8]: W1[n][8 kc + e]
+    const int kc = i / 512, o = (i >> 3) & 63, k = 8 * kc + (i & 7);
+    put3(k < L.in ? flat[L.g_w1 + o * L.in + k] : 0.f, w1 + i, 2 * 64 * 8);
+  }
+  for (int i = t0; i < 8 * 64 * 8; i += n) {
+    const int kc = i / 512, o = (i >> 3) & 63, k = 8 * kc + (i & 7);
+    put3(flat[L.g_w2 + o * 64 + k], w2 + i, 8 * 64 * 8);
+  }
+  for (int i = t0; i < L.out * 64; i += n) blob[L.o_w3 + i] = flat[L.g_w3 + i];
+  for (int i = t0; i < 64; i += n) {
+    blob[L.o_b1 + i] = flat[L.g_b1 + i];
+    blob[L.o_b2 + i] = flat[L.g_b2 + i];
+  }
+  for (int i = t0; i < 4; i += n) blob[L.o_b3 + i] = i < L.out ? flat[L.g_b3 + i] : 0.f;
+}
+int launch_pack_tcf(const float* flat, const NetL& L, float* blob, cudaStream_t st) {
+  pack_params_tcf_kernel<<<8, 256, 0, st>>>(flat, L, blob);
+  CUDA_OK_L(cudaGetLastError(), "launch#tcf-pack");
+  return 0;
+}
+
 // GOPS_B200_ROLLOUT=hy|mma forces the hybrid (tcgen05 forward sweep) / pure mma.sync rollout kernel
 bool rollout_use_hy(const gops_b200_plan* pl, long long batch) {
   if (!pl->hy_ok) return false;
@@ -314,6 +389,55 @@ int launch_rollout(gops_b200_plan* pl, const gops_b200_batch* b, int alg, cudaSt
       return fail("veh3dof_tracking: reference too short for t + horizon + pre_horizon + 1 points");
   }
   KParams& kp = pl->kp;
+  if (rollout_use_tc(pl)) {
+    RolloutFn fn = rollout_fn_tc(pl->desc.model, alg);
+    if (!fn) return fail("full tcgen05 rollout kernel not built for this env model");
+    const int S = 128, NT = 512;
+    KParams k2 = kp;
+    k2.pol = pl->pol_tcf;
+    k2.val = pl->val_tcf;
+    k2.blob_pol = pl->blob_pol_tcf; k2.blob_val = pl->blob_val_tcf; k2.blob_vtg = pl->blob_vtg_tcf;
+    k2.w_floats = pl->w_floats_tcf;
+    k2.alg = alg;
+    k2.batch = b->batch;
+    k2.n_tiles = (int)((b->batch + NT - 1) / NT);
+    k2.tape_ch = model_ns(pl->desc.model) + 1 + k2.pol.out;
+    kp.tape_ch = k2.tape_ch;                        // ensure_scratch sizes the tape / partials from the plan's copy
+    k2.obs = b->obs; k2.done = b->done; k2.state = b->state; k2.ref_points = b->ref_points;
+    k2.path_num = b->path_num; k2.u_num = b->u_num; k2.ref_time = b->ref_time; k2.reference = b->reference;
+    k2.ref_t = b->ref_t;
+    k2.ref_len = b->ref_len;
+    const NetL& upd = (alg == ALG_PEV) ? k2.val : k2.pol;
+    k2.part_stride = round4(upd.nparam + 4);
+    kp.part_stride = k2.part_stride;
+    k2.dw_floats = round4(upd.nacc);
+    const size_t smem = rollout_smem_bytes_tcf(k2);
+    if (smem > (size_t)pl->max_smem) return fail("full tcgen05 rollout kernel does not fit in shared memory");
+    if (!pl->tc_attr_set[alg]) {
+      CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, pl->max_smem));
+      pl->tc_attr_set[alg] = true;
+    }
+    const long long slots = pl->sm_count;          // one CTA per SM (all 512 TMEM columns)
+    const long long subtiles = (b->batch + S - 1) / S;
+    const int grid = (int)(subtiles < slots ? subtiles : slots);
+    if (ensure_scratch(pl, grid, NT, k2.horizon)) return 1;
+    k2.tape = pl->tape;
+    k2.ext_ref = pl->ext_ref;
+    k2.xbuf = pl->xbuf;
+    k2.partial = pl->partial;
+    if (pl->timing) CUDA_OK(cudaEventRecord(pl->ev0, st));
+    fn<<<grid, NT, smem, st>>>(k2);
+    CUDA_OK_L(cudaGetLastError(), "launch#2-tc");
+    if (pl->timing) CUDA_OK(cudaEventRecord(pl->ev1, st));
+    pl->last_grid = grid; pl->last_S = S; pl->last_NT = NT; pl->last_smem = smem;
+    if (alg != ALG_TRACE) {
+      const int n = upd.nparam + 3;
+      reduce_partials_kernel<<<(n + 255) / 256, 256, 0, st>>>(pl->partial, grid, k2.part_stride, upd.nparam, grad_out,
+                                                             scalars_out);
+      CUDA_OK_L(cudaGetLastError(), "launch#3-tc");
+    }
+    return 0;
+  }
   const bool hy = rollout_use_hy(pl, b->batch);
   const int cfg = hy ? 0 : pick_config(pl, b->batch, false);
   if (cfg < 0) return fail("no kernel configuration fits in shared memory");
@@ -525,6 +649,20 @@ int gops_b200_plan_create(const gops_b200_plan_desc* d, gops_b200_plan** out) {
     cudaMemset(pl->blob_pol_tc, 0, (size_t)pl->pol_tc.blob * sizeof(float));
     pl->hy_ok = true;
   }
+  // full tcgen05 rollout kernel: 64-wide nets whose inputs fit one 16-wide K block, state == obs models
+  if (kp.hid == 64 && kp.pol.in <= tcf::K1 && (!infadp || kp.val.in <= tcf::K1) && rollout_fn_tc(d->model, d->alg)) {
+    make_net_tcf(kp.pol, pl->pol_tcf);
+    if (infadp) make_net_tcf(kp.val, pl->val_tcf); else pl->val_tcf = pl->pol_tcf;
+    pl->w_floats_tcf = pl->pol_tcf.blob > pl->val_tcf.blob ? pl->pol_tcf.blob : pl->val_tcf.blob;
+    const size_t nb = (size_t)pl->w_floats_tcf * sizeof(float);
+    if (cudaMalloc(&pl->blob_pol_tcf, nb) != cudaSuccess || cudaMalloc(&pl->blob_val_tcf, nb) != cudaSuccess ||
+        cudaMalloc(&pl->blob_vtg_tcf, nb) != cudaSuccess) {
+      gops_b200_plan_destroy(pl);
+      return fail("cudaMalloc failed for plan scratch (tcgen05 blobs)");
+    }
+    cudaMemset(pl->blob_pol_tcf, 0, nb); cudaMemset(pl->blob_val_tcf, 0, nb); cudaMemset(pl->blob_vtg_tcf, 0, nb);
+    pl->tc_ok = true;
+  }
   cudaMemset(pl->blob_pol, 0, kp.w_floats * sizeof(float));
   cudaMemset(pl->blob_val, 0, kp.w_floats * sizeof(float));
   cudaMemset(pl->blob_vtg, 0, kp.w_floats * sizeof(float));
@@ -571,15 +709,15 @@ int gops_b200_plan_destroy(gops_b200_plan* pl) {
   if (!pl) return 0;
   if (pl->ev0) { cudaEventDestroy(pl->ev0); cudaEventDestroy(pl->ev1); }
   void* ptrs[] = {pl->gpow, pl->blob_pol, pl->blob_val, pl->blob_vtg, pl->tape, pl->partial, pl->ext_ref, pl->xbuf, pl->osc,
-                  pl->blob_tc, pl->blob_pol_tc};
+                  pl->blob_tc, pl->blob_pol_tc, pl->blob_pol_tcf, pl->blob_val_tcf, pl->blob_vtg_tcf};
   const char* names[] = {"gpow", "blob_pol", "blob_val", "blob_vtg", "tape", "partial", "ext_ref", "xbuf", "osc", "blob_tc",
-                         "blob_pol_tc"};
+                         "blob_pol_tc", "blob_pol_tcf", "blob_val_tcf", "blob_vtg_tcf"};
   if (getenv("GOPS_B200_DEBUG")) {
     fprintf(stderr, "[gops_b200] destroy plan %p alg %d model %d:", (void*)pl, pl->desc.alg, pl->desc.model);
-    for (int i = 0; i < 11; ++i) fprintf(stderr, " %s=%p", names[i], ptrs[i]);
+    for (int i = 0; i < 14; ++i) fprintf(stderr, " %s=%p", names[i], ptrs[i]);
     fprintf(stderr, "\n");
   }
-  for (int i = 0; i < 11; ++i) {
+  for (int i = 0; i < 14; ++i) {
     const cudaError_t e = cudaFree(ptrs[i]);
     if (e != cudaSuccess) {
       (void)cudaGetLastError();
@@ -602,15 +740,19 @@ int gops_b200_rollout_grad(gops_b200_plan* pl, const gops_b200_batch* b, const f
   if (!pl || !policy_params || !grad_out || !scalars_out) return fail("null argument");
   cudaStream_t st = (cudaStream_t)stream;
   const int alg = pl->desc.alg;
-  if (launch_pack(policy_params, pl->kp.pol, pl->kp.hid, pl->blob_pol, st)) return 1;
-  if (b && rollout_use_hy(pl, b->batch) && launch_pack_tc(policy_params, pl->pol_tc, pl->blob_pol_tc, st)) return 1;
+  const bool tcr = rollout_use_tc(pl);
+  if (tcr ? launch_pack_tcf(policy_params, pl->pol_tcf, pl->blob_pol_tcf, st)
+          : launch_pack(policy_params, pl->kp.pol, pl->kp.hid, pl->blob_pol, st)) return 1;
+  if (!tcr && b && rollout_use_hy(pl, b->batch) && launch_pack_tc(policy_params, pl->pol_tc, pl->blob_pol_tc, st)) return 1;
   if (alg != GOPS_ALG_FHADP) {
     if (!vtarget_params) return fail("vtarget_params required for INFADP");
-    if (launch_pack(vtarget_params, pl->kp.val, pl->kp.hid, pl->blob_vtg, st)) return 1;
+    if (tcr ? launch_pack_tcf(vtarget_params, pl->val_tcf, pl->blob_vtg_tcf, st)
+            : launch_pack(vtarget_params, pl->kp.val, pl->kp.hid, pl->blob_vtg, st)) return 1;
   }
   if (alg == GOPS_ALG_INFADP_VALUE) {
     if (!value_params) return fail("value_params required for INFADP value update");
-    if (launch_pack(value_params, pl->kp.val, pl->kp.hid, pl->blob_val, st)) return 1;
+    if (tcr ? launch_pack_tcf(value_params, pl->val_tcf, pl->blob_val_tcf, st)
+            : launch_pack(value_params, pl->kp.val, pl->kp.hid, pl->blob_val, st)) return 1;
   }
   pl->kp.inv_B = inv_batch_global;
   pl->kp.tr_obs = pl->kp.tr_act = pl->kp.tr_rew = pl->kp.tr_done = nullptr;
@@ -622,8 +764,10 @@ int gops_b200_rollout_trace(gops_b200_plan* pl, const gops_b200_batch* b, const 
   ENTRY("float* act_out, float* rew_out, float* d");
   if (!pl || !policy_params) return fail("null argument");
   cudaStream_t st = (cudaStream_t)stream;
-  if (launch_pack(policy_params, pl->kp.pol, pl->kp.hid, pl->blob_pol, st)) return 1;
-  if (b && rollout_use_hy(pl, b->batch) && launch_pack_tc(policy_params, pl->pol_tc, pl->blob_pol_tc, st)) return 1;
+  if (rollout_use_tc(pl) ? launch_pack_tcf(policy_params, pl->pol_tcf, pl->blob_pol_tcf, st)
+                         : launch_pack(policy_params, pl->kp.pol, pl->kp.hid, pl->blob_pol, st)) return 1;
+  if (!rollout_use_tc(pl) && b && rollout_use_hy(pl, b->batch) &&
+      launch_pack_tc(policy_params, pl->pol_tc, pl->blob_pol_tc, st)) return 1;
   pl->kp.inv_B = 1.f;
   pl->kp.tr_obs = obs_out; pl->kp.tr_act = act_out; pl->kp.tr_rew = rew_out; pl->kp.tr_done = done_out;
   return launch_rollout(pl, b, ALG_TRACE, st, nullptr, nullptr);

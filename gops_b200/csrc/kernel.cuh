@@ -2,6 +2,7 @@
 #pragma once
 #include "models.cuh"
 #include "mlp_tc_fwd.cuh"
+#include "mlp_tc_full.cuh"
 
 namespace gops {
 
@@ -14,18 +15,41 @@ namespace gops {
 // HY (hybrid, HD = 64 / S = 128 / NT = 512, policy inputs <= 16): the forward sweep's policy MLP runs on the tcgen05
 // tensor cores with a TMEM accumulator (mlp_tc_fwd.cuh); its operand planes alias the activation tiles, the policy
 // blob is re-staged per chunk in the layout of the sweep that is about to run (chunk-major planes / mma.sync planes).
-template <class M, int HD, int S, int NT, int ALG, bool HY = false>
+// TC (full tcgen05, HD = 64 / S = 128 / NT = 512, inputs <= 16): every dense product incl. the weight gradients runs
+// on the tensor cores in BF16x3 (mlp_tc_full.cuh); shared memory holds the operand planes instead of activation tiles,
+// the W1 / b1 / W2 / b2 gradient accumulators live in TMEM for the whole kernel.
+template <class M, int HD, int S, int NT, int ALG, bool HY = false, bool TC = false>
 __global__ void __launch_bounds__(NT, 1) rollout_kernel(const __grid_constant__ KParams p) {
   constexpr int SP = S + 4, XS = NT + 4, NS = M::NS, HID = HD;
   constexpr int alg = ALG;
   constexpr bool WG = HD > 64;
   constexpr int HDR = HY ? 16 : 4;     // header floats: weight mbarrier (+ MMA mbarrier, TMEM slot)
   static_assert(!HY || (HD == 64 && S == 128 && NT == 512), "hybrid tcgen05 forward: 64-wide nets, S = 128, NT = 512");
+  static_assert(!TC || (!HY && HD == 64 && S == 128 && NT == 512), "full tcgen05 path: 64-wide nets, S = 128, NT = 512");
   extern __shared__ __align__(16) float smem[];
   uint64_t* mbar = reinterpret_cast<uint64_t*>(smem);
   float* part = p.partial + (size_t)blockIdx.x * p.part_stride;
   Tiles t;
-  if (WG) {
+  TcfCtx cf;
+  if (TC) {
+    // [64 hdr: 0 weight mbarrier, 2 / 4 MMA mbarriers, 8 TMEM slot] W blob | dWs | red | P | Q | Xp | ones | X | Z
+    // (P's and Q's third plane must be followed by >= 16 KB of mapped shared memory: the masked b2 MMA reads M = 128)
+    t.W = smem + 64;
+    t.dW = t.W + p.w_floats;
+    cf.dWs = t.dW;
+    cf.red = t.dW + p.dw_floats;
+    cf.P = reinterpret_cast<unsigned char*>(cf.red + tcf::RED);
+    cf.Q = cf.P + 3 * tcf::HPLANE;
+    cf.Xp = cf.Q + 3 * tcf::HPLANE;
+    cf.ones = cf.Xp + 3 * tcf::XPLANE;
+    t.X = reinterpret_cast<float*>(cf.ones + tcf::ONES_B);
+    t.Z = t.X + p.inp_max * XS;
+    cf.bar = mbar + 1;
+    cf.ph0 = cf.ph1 = 0u;
+    cf.tmem = 0u;
+    t.H1 = reinterpret_cast<float*>(cf.P);   // scratch of the final scalar reduction
+    t.D1 = t.H2 = t.D2 = t.R = nullptr;
+  } else if (WG) {
     t.W = const_cast<float*>(p.blob_pol);
     t.dW = part;
     t.X = p.xbuf + (size_t)blockIdx.x * p.inp_max * XS;
@@ -36,11 +60,13 @@ __global__ void __launch_bounds__(NT, 1) rollout_kernel(const __grid_constant__ 
     t.X = t.dW + p.dw_floats;
     t.H1 = t.X + p.inp_max * XS;
   }
-  t.D1 = t.H1 + HID * SP;
-  t.H2 = t.D1 + HID * SP;
-  t.D2 = t.H2 + HID * SP;
-  t.Z = t.D2 + HID * SP;      // [8][XS]: rows a (+ 4 + a: second half-stripe partial of the fused output layer)
-  t.R = t.Z + 8 * XS;         // wide nets only: staging region
+  if (!TC) {
+    t.D1 = t.H1 + HID * SP;
+    t.H2 = t.D1 + HID * SP;
+    t.D2 = t.H2 + HID * SP;
+    t.Z = t.D2 + HID * SP;      // [8][XS]: rows a (+ 4 + a: second half-stripe partial of the fused output layer)
+    t.R = t.Z + 8 * XS;         // wide nets only: staging region
+  }
 
   TcCtx cx;                     // hybrid: tcgen05 operand planes inside the (forward-sweep-dead) activation tiles
   cx.W = t.W;
@@ -56,11 +82,28 @@ __global__ void __launch_bounds__(NT, 1) rollout_kernel(const __grid_constant__ 
   // column (= sample slot of the chunk) owned by this thread.  Tensor-core path: the 64 threads of warp pair p own
   // exactly the 16-sample stripes {sub * S + 16 p .. + 15} that the pair's MLP GEMMs produce, so the pair never has
   // to synchronise with the rest of the CTA outside the weight-gradient reductions.
-  const int col = WG ? tid : (((tid & 63) >> 4) * S + 16 * (tid >> 6) + (tid & 15));
+  const int col = (WG || TC) ? tid : (((tid & 63) >> 4) * S + 16 * (tid >> 6) + (tid & 15));
   auto scope_sync = [&]() {
-    if (WG) __syncthreads();
+    if (WG || TC) __syncthreads();
     else pair_sync();
   };
+  // the staged blob of the full tcgen05 path: bf16 planes of W1 / W2, then fp32 W3, b1, b2, b3 (make_net_tcf offsets)
+  auto bind_tcf = [&](const NetL& L) {
+    cf.W1 = reinterpret_cast<unsigned char*>(t.W + L.o_w1);
+    cf.W2 = reinterpret_cast<unsigned char*>(t.W + L.o_w2);
+    cf.W3 = t.W + L.o_w3; cf.b1 = t.W + L.o_b1; cf.b2 = t.W + L.o_b2; cf.b3 = t.W + L.o_b3;
+  };
+// forward / backward of one sub-tile on the path this instantiation was built for
+#define MLP_FWD(FULL, OUT, L, ts, Zout)                                                           \
+  do {                                                                                            \
+    if constexpr (TC) { bind_tcf(L); mlp_forward_tcf<NT, FULL, OUT>(L, cf, (ts).X, XS, p.inp_max, Zout); } \
+    else mlp_forward<HD, S, NT, FULL, OUT>(L, ts, Zout);                                          \
+  } while (0)
+#define MLP_BWD(WANT_DW, L, ts, want_dx)                                                          \
+  do {                                                                                            \
+    if constexpr (TC) { bind_tcf(L); mlp_backward_tcf<NT, WANT_DW>(L, cf, (ts).X, XS, (ts).Z, want_dx); } \
+    else mlp_backward<HD, S, NT, WANT_DW>(L, ts, want_dx);                                        \
+  } while (0)
   const NetL& P = p.pol;
   const NetL& V = p.val;
   const int H = p.horizon, obs_dim = P.obs, TCH = p.tape_ch;
@@ -82,6 +125,33 @@ __global__ void __launch_bounds__(NT, 1) rollout_kernel(const __grid_constant__ 
     __syncthreads();
     umma::fence_after_sync();
     cx.tmem = *tslot;
+  }
+  if constexpr (TC) {
+    uint32_t* tslot = reinterpret_cast<uint32_t*>(smem + 8);
+    if (tid == 0) {
+      mbar_init(cf.bar, 1);
+      mbar_init(cf.bar + 1, 1);
+      fence_mbar_init();
+    }
+    {  // `ones`: [2 mn-groups][16 rows][8 bf16], feature 0 = 1.0
+      uint16_t* o16 = reinterpret_cast<uint16_t*>(cf.ones);
+      if (tid < 256) o16[tid] = (tid < 128 && (tid & 7) == 0) ? (uint16_t)0x3f80 : (uint16_t)0;
+    }
+    if (tid < 32) umma::tmem_alloc(tslot, tcf::COLS);
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    cf.tmem = *tslot;
+    {  // zero the weight-gradient accumulators (TMEM columns DW2 .. DB1 + 16): thread (q, c) -> 16-column groups
+      const uint32_t tq = cf.tmem + ((uint32_t)(32 * ((tid >> 5) & 3)) << 16);
+      float z16[16];
+#pragma unroll
+      for (int e = 0; e < 16; ++e) z16[e] = 0.f;
+      for (uint32_t g = tid >> 7; g < (tcf::DB1 + 16 - tcf::DW2) / 16; g += 4) umma::tmem_st16(tq + tcf::DW2 + 16 * g, z16);
+      umma::tmem_wait_st();
+    }
+    fence_proxy_async();
+    umma::fence_before_sync();
   }
 
   // TMA bulk copy of a packed weight blob into shared memory (all threads wait on the mbarrier)
@@ -179,13 +249,13 @@ __global__ void __launch_bounds__(NT, 1) rollout_kernel(const __grid_constant__ 
       for (int sub = 0; sub < nsub; ++sub) {
         const Tiles ts = sub_tiles(sub);
         if constexpr (HY) mlp_forward_tc<NT>(p.pol_tc, cx, ts.X, XS, p.inp_max, ts.Z);
-        else mlp_forward<HD, S, NT, false, true>(P, ts, ts.Z);
+        else MLP_FWD(false, true, P, ts, ts.Z);
       }
       {
         float z[MAXA], a[MAXA], g[MAXA], apol[MAXA];
 #pragma unroll
         for (int j = 0; j < MAXA; ++j)   // mma.sync path: two half-stripe partials; tcgen05 path: complete sums in row j
-          z[j] = j < P.out ? (HY ? t.Z[j * XS + col] : t.Z[j * XS + col] + t.Z[(4 + j) * XS + col]) : 0.f;
+          z[j] = j < P.out ? ((HY || TC) ? t.Z[j * XS + col] : t.Z[j * XS + col] + t.Z[(4 + j) * XS + col]) : 0.f;
         if (alg == ALG_FHADP || alg == ALG_PIM) {
 #pragma unroll
           for (int j = 0; j < MAXA; ++j)
@@ -302,10 +372,10 @@ __global__ void __launch_bounds__(NT, 1) rollout_kernel(const __grid_constant__ 
       for (int sub = 0; sub < nsub; ++sub) {
         const Tiles ts = sub_tiles(sub);
         if (alg == ALG_PIM) {
-          mlp_forward<HD, S, NT, true, true>(V, ts, ts.Z + XS);
-          mlp_backward<HD, S, NT, false>(V, ts, true);
+          MLP_FWD(true, true, V, ts, ts.Z + XS);
+          MLP_BWD(false, V, ts, true);
         } else {
-          mlp_forward<HD, S, NT, false, true>(V, ts, ts.Z + XS);
+          MLP_FWD(false, true, V, ts, ts.Z + XS);
         }
       }
       if (term) {
@@ -332,7 +402,7 @@ __global__ void __launch_bounds__(NT, 1) rollout_kernel(const __grid_constant__ 
       __syncthreads();
       for (int sub = 0; sub < nsub; ++sub) {
         const Tiles ts = sub_tiles(sub);
-        mlp_forward<HD, S, NT, true, true>(V, ts, ts.Z + XS);
+        MLP_FWD(true, true, V, ts, ts.Z + XS);
         if (col / S == sub) {
           float zb = 0.f;
           if (valid) {
@@ -345,7 +415,7 @@ __global__ void __launch_bounds__(NT, 1) rollout_kernel(const __grid_constant__ 
           t.Z[col] = zb;
         }
         scope_sync();
-        mlp_backward<HD, S, NT, true>(V, ts, false);
+        MLP_BWD(true, V, ts, false);
       }
       stage(p.blob_pol, P.blob);
       continue;
@@ -488,8 +558,8 @@ __global__ void __launch_bounds__(NT, 1) rollout_kernel(const __grid_constant__ 
       // MLP: re-compute the hidden activations of step k per sub-tile, then back-propagate Zbar
       for (int sub = 0; sub < nsub; ++sub) {
         const Tiles ts = sub_tiles(sub);
-        mlp_forward<HD, S, NT, true, false>(P, ts, nullptr);
-        mlp_backward<HD, S, NT, true>(P, ts, k > 0);
+        MLP_FWD(true, false, P, ts, nullptr);
+        MLP_BWD(true, P, ts, k > 0);
       }
       if (active && k > 0) {
         if constexpr (M::KIND == 0) {
@@ -506,7 +576,45 @@ __global__ void __launch_bounds__(NT, 1) rollout_kernel(const __grid_constant__ 
   // ============================ per-CTA partials ============================
   __syncthreads();
   const int nparam = (alg == ALG_PEV) ? V.nparam : P.nparam;
-  if (alg != ALG_TRACE && !WG) {
+  if constexpr (TC) {
+    if (alg != ALG_TRACE) {
+      // TMEM accumulators -> shared scratch -> torch flat layout.  Lanes 0..63: b0 (+ b2) part, lanes 64..127: b1 part of
+      // the stacked delta operand: dW[j][.] = acc[j][.] + acc[64 + j][.]
+      const NetL& U = (alg == ALG_PEV) ? V : P;
+      const int q = (tid >> 5) & 3, c = tid >> 7, r = 32 * q + (tid & 31);
+      const uint32_t tq = cf.tmem + ((uint32_t)(32 * q) << 16);
+      float* S2 = reinterpret_cast<float*>(cf.P);      // [128][64]
+      float* S1 = S2 + 128 * 64;                         // [128][16] | b1 [128] | b2 [128]
+      float v[16];
+      umma::fence_after_sync();
+      umma::tmem_ld16(tq + tcf::DW2 + 16 * c, v);
+#pragma unroll
+      for (int e = 0; e < 16; ++e) S2[r * 64 + 16 * c + e] = v[e];
+      if (c == 0) {
+        umma::tmem_ld16(tq + tcf::DW1, v);
+#pragma unroll
+        for (int e = 0; e < 16; ++e) S1[r * 16 + e] = v[e];
+      } else if (c == 1) {
+        umma::tmem_ld16(tq + tcf::DB1, v);
+        S1[2048 + r] = v[0];
+      } else if (c == 2) {
+        umma::tmem_ld16(tq + tcf::DB2, v);
+        S1[2048 + 128 + r] = v[0];
+      }
+      __syncthreads();
+      for (int i = tid; i < nparam; i += NT) {
+        float g;
+        if (i < U.g_b1) { const int j = i / U.in, k = i - j * U.in; g = S1[j * 16 + k] + S1[(64 + j) * 16 + k]; }
+        else if (i < U.g_w2) { const int j = i - U.g_b1; g = S1[2048 + j] + S1[2048 + 64 + j]; }
+        else if (i < U.g_b2) { const int e = i - U.g_w2; g = S2[e] + S2[64 * 64 + e]; }
+        else if (i < U.g_w3) { const int j = i - U.g_b2; g = S1[2048 + 128 + j] + S1[2048 + 128 + 64 + j]; }
+        else if (i < U.g_b3) g = t.dW[U.d_w3 + i - U.g_w3];
+        else g = t.dW[U.d_b3 + i - U.g_b3];
+        part[i] = g;
+      }
+      __syncthreads();
+    }
+  } else if (alg != ALG_TRACE && !WG) {
     const NetL& U = (alg == ALG_PEV) ? V : P;
     for (int i = tid; i < nparam; i += NT) {      // accumulator layout -> torch flat layout
       int j;
@@ -532,6 +640,13 @@ __global__ void __launch_bounds__(NT, 1) rollout_kernel(const __grid_constant__ 
     __syncthreads();
     if (tid < 32) umma::tmem_dealloc(cx.tmem, TC_FWD_COLS);
   }
+  if constexpr (TC) {
+    umma::fence_before_sync();
+    __syncthreads();
+    if (tid < 32) umma::tmem_dealloc(cf.tmem, tcf::COLS);
+  }
+#undef MLP_FWD
+#undef MLP_BWD
 }
 
 // Batched inference of one MLP (policy with tanh squashing when `squash`, else raw value output)

@@ -1,0 +1,422 @@
+// Full tcgen05 / TMEM MLP forward + backward for the fused rollout kernel (64-wide nets, inputs <= 16): every dense
+// product of the update -- layer GEMMs, delta back-propagation, input gradient AND the weight gradients (contraction
+// over samples) -- runs on the 5th-generation tensor cores; the weight gradients accumulate in TMEM for the whole kernel.
+//
+// Arithmetic: BF16x3.  x = b0 + b1 + b2 (three bf16 planes, residual <= 2^-27 |x|), a product keeps the six terms of
+// order <= 2 (b0b0, b0b1, b1b0, b1b1, b0b2, b2b0; neglected <= 2^-26), FP32 accumulation in TMEM: at least as accurate
+// as the 3xTF32 split of the other paths (parity tests hold it to the same bars).  Why bf16 and not tf32: tcgen05 reads
+// a 16-bit operand transposed (MN-major) from the plain no-swizzle layout, so ONE shared-memory buffer [sample][feature]
+// serves the layer products (K-major: contraction over features) and the weight-gradient products (MN-major:
+// contraction over samples); 32-bit operands need a second, 128B_BASE32B copy of every activation, which does not fit
+// (tools/umma_probe*.cu, profiles/r01_umma_probe*.txt).
+//
+// Operand layout: plane[p][k/8][row][8] bf16 (p = 0..2), i.e. the no-swizzle canonical layout with chunk stride
+// rows*16 B and 8-row group stride 128 B.  K-major view: rows = M/N, K along k.  MN-major view (same bytes): M/N along
+// k, K = rows.  Thread (q, c) of the CTA owns sample r = 32 q + lane and the 16-column slice c: it writes two 16-byte
+// chunks per plane (a warp covers 512 contiguous bytes).
+//
+// Weight gradients: A = [delta_b0 | delta_b1] stacked to M = 128 (planes are contiguous), so one MMA does two terms;
+// rows 0..63 of the accumulator collect b0.(B0+B1+B2) + b2.B0 (the b2 MMA disables output lanes 64..127), rows 64..127
+// collect b1.(B0+B1+B2); the kernel epilogue adds the halves.  Bias gradients: B = `ones`.
+#pragma once
+#include "rollout.cuh"
+#include "umma.cuh"
+
+namespace gops {
+
+namespace tcf {
+constexpr uint32_t ACC = 0, D1S = 64, D2S = 128, H2S = 192, DW2 = 256, DB2 = 320, DW1 = 336, DB1 = 352, COLS = 512;
+constexpr int K1 = 16;                           // layer-1 K extent (inputs padded to 16)
+constexpr int HPLANE = 8 * 128 * 16;             // bytes of one hidden-activation plane ([8 chunks][128 rows][16 B])
+constexpr int XPLANE = 2 * 128 * 16;             // bytes of one observation plane
+constexpr int W2PLANE = 8 * 64 * 16, W1PLANE = 2 * 64 * 16;
+constexpr int RED = 4 * (MAXA * 64 + MAXA);      // floats: quarter partials of dW3 / db3
+constexpr int ONES_B = 2 * 16 * 16;              // bytes: [2 mn-groups][16 rows][16 B]
+}  // namespace tcf
+
+struct TcfCtx {
+  unsigned char* W1;   // 3 planes [2][64][8] bf16
+  unsigned char* W2;   // 3 planes [8][64][8] bf16
+  const float* W3;     // fp32 [out][64]
+  const float *b1, *b2, *b3;
+  unsigned char* Xp;   // 3 planes [2][128][8]
+  unsigned char* P;    // 3 planes [8][128][8]   H1, later delta1
+  unsigned char* Q;    // 3 planes [8][128][8]   delta2 (forward: fp32 output-partial scratch)
+  unsigned char* ones; // [2][16][8] bf16: feature 0 = 1
+  float* dWs;          // dW3 [out][64] | db3 [out]
+  float* red;          // [tcf::RED]
+  uint64_t* bar;       // bar[0]: critical-path MMA group, bar[1]: weight-gradient MMA group
+  uint32_t ph0, ph1;
+  uint32_t tmem;
+};
+
+namespace tcf {
+
+__host__ __device__ constexpr uint32_t idesc_bf16(int M, int N, bool a_mn, bool b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// D[tmem] (+)= A . B^T, kind::f16 (bf16 operands, K = 16), `upper_off`: do not write accumulator lanes 64..127
+__device__ __forceinline__ void mma_bf16(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc,
+                                         bool upper_off = false) {
+  const uint32_t m = upper_off ? 0xffffffffu : 0u;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t}\n" ::"r"(d),
+      "l"(a), "l"(b), "r"(idesc), "r"(acc), "r"(0), "r"(0), "r"(m), "r"(m)
+      : "memory");
+}
+
+struct Op {            // one operand: smem address of plane 0, plane stride, descriptor strides, advance per K = 16 step
+  uint32_t base, pstride, lbo, sbo, kadv;
+};
+__device__ __forceinline__ Op k_act(const unsigned char* b, int plane_bytes) {     // activations K-major, 128 rows
+  return Op{smem_u32(b), (uint32_t)plane_bytes, 2048u, 128u, 4096u};
+}
+__device__ __forceinline__ Op k_w(const unsigned char* b, int plane_bytes) {       // weights K-major, 64 rows
+  return Op{smem_u32(b), (uint32_t)plane_bytes, 1024u, 128u, 2048u};
+}
+__device__ __forceinline__ Op mn_act(const unsigned char* b, int plane_bytes) {    // activations transposed: K = samples
+  return Op{smem_u32(b), (uint32_t)plane_bytes, 128u, 2048u, 256u};
+}
+__device__ __forceinline__ Op mn_w(const unsigned char* b, int plane_bytes) {      // weights transposed: K = output rows
+  return Op{smem_u32(b), (uint32_t)plane_bytes, 128u, 1024u, 256u};
+}
+__device__ __forceinline__ uint64_t dsc(const Op& o, int plane) {
+  return umma::smem_desc(o.base + plane * o.pstride, o.lbo, o.sbo);
+}
+
+// D = A . B^T with the six BF16x3 terms (small ones first), KS steps of K = 16; the first MMA overwrites D
+template <int KS>
+__device__ __forceinline__ void issue6(uint32_t d, const Op& A, const Op& B, uint32_t idesc) {
+  const uint64_t a0 = dsc(A, 0), a1 = dsc(A, 1), a2 = dsc(A, 2), b0 = dsc(B, 0), b1 = dsc(B, 1), b2 = dsc(B, 2);
+  const uint64_t ka = A.kadv >> 4, kb = B.kadv >> 4;
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks) mma_bf16(d, a2 + ks * ka, b0 + ks * kb, idesc, ks > 0 ? 1u : 0u);
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks) mma_bf16(d, a0 + ks * ka, b2 + ks * kb, idesc, 1u);
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks) mma_bf16(d, a1 + ks * ka, b1 + ks * kb, idesc, 1u);
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks) mma_bf16(d, a1 + ks * ka, b0 + ks * kb, idesc, 1u);
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks) mma_bf16(d, a0 + ks * ka, b1 + ks * kb, idesc, 1u);
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks) mma_bf16(d, a0 + ks * ka, b0 + ks * kb, idesc, 1u);
+}
+// D += [A_b0 | A_b1]-stacked^T . (B0 + B1 + B2) + (A_b2^T . B0 on lanes 0..63), 8 steps of 16 samples
+__device__ __forceinline__ void issue_stack(uint32_t d, const Op& A, const Op& B, uint32_t idesc, int bplanes) {
+  const uint64_t a01 = dsc(A, 0), a2 = dsc(A, 2), ka = A.kadv >> 4, kb = B.kadv >> 4;
+  for (int p = bplanes - 1; p >= 0; --p) {
+    const uint64_t b = dsc(B, p);
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) mma_bf16(d, a01 + ks * ka, b + ks * kb, idesc, 1u);
+  }
+  const uint64_t b0 = dsc(B, 0);
+#pragma unroll
+  for (int ks = 0; ks < 8; ++ks) mma_bf16(d, a2 + ks * ka, b0 + ks * kb, idesc, 1u, true);
+}
+
+__device__ __forceinline__ void wait0(TcfCtx& cx) {
+  mbar_wait(cx.bar, cx.ph0);
+  cx.ph0 ^= 1u;
+  umma::fence_after_sync();
+}
+__device__ __forceinline__ void wait1(TcfCtx& cx) {
+  mbar_wait(cx.bar + 1, cx.ph1);
+  cx.ph1 ^= 1u;
+  umma::fence_after_sync();
+}
+__device__ __forceinline__ void publish_sync() {
+  fence_proxy_async();
+  umma::fence_before_sync();
+  __syncthreads();
+}
+
+// (x0, x1) -> packed bf16x2 words of the three planes (low half = x0)
+__device__ __forceinline__ void split3(float x0, float x1, uint32_t& p0, uint32_t& p1, uint32_t& p2) {
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(p0) : "f"(x1), "f"(x0));
+  float r0 = x0 - __uint_as_float(p0 << 16), r1 = x1 - __uint_as_float(p0 & 0xffff0000u);
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(p1) : "f"(r1), "f"(r0));
+  r0 -= __uint_as_float(p1 << 16);
+  r1 -= __uint_as_float(p1 & 0xffff0000u);
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(p2) : "f"(r1), "f"(r0));
+}
+// 16 values of thread (q, c) -> its two 16-byte chunks (kc = 2c, 2c+1) of row r in the three planes of `buf`
+__device__ __forceinline__ void store16(unsigned char* buf, int plane_bytes, int c, int r, const float* v) {
+  uint32_t w[3][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) split3(v[2 * i], v[2 * i + 1], w[0][i], w[1][i], w[2][i]);
+#pragma unroll
+  for (int p = 0; p < 3; ++p) {
+    uint4* dst = reinterpret_cast<uint4*>(buf + p * plane_bytes + ((2 * c) * 128 + r) * 16);
+    dst[0] = make_uint4(w[p][0], w[p][1], w[p][2], w[p][3]);
+    dst[128] = make_uint4(w[p][4], w[p][5], w[p][6], w[p][7]);      // next chunk: + 128 rows * 16 B
+  }
+}
+
+__device__ __forceinline__ int col16(int lane) {
+  return ((lane & 16) ? 8 : 0) + ((lane & 8) ? 4 : 0) + ((lane & 4) ? 2 : 0) + ((lane & 2) ? 1 : 0);
+}
+// sum over the warp's 32 lanes of 16 per-lane values: on return v[0] of lane l holds column col16(l)
+__device__ __forceinline__ void warp_reduce16(float* v, int lane) {
+  {
+    const bool up = lane & 16;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float send = up ? v[i] : v[i + 8], keep = up ? v[i + 8] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+  }
+  {
+    const bool up = lane & 8;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float send = up ? v[i] : v[i + 4], keep = up ? v[i + 4] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+  }
+  {
+    const bool up = lane & 4;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const float send = up ? v[i] : v[i + 2], keep = up ? v[i + 2] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+  }
+  {
+    const bool up = lane & 2;
+    const float send = up ? v[0] : v[1], keep = up ? v[1] : v[0];
+    v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  }
+  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+
+// hidden-layer epilogue: 16 accumulator columns -> + bias -> activation (FULL: park the derivative in TMEM) -> planes
+template <int ACT, bool FULL>
+__device__ __forceinline__ void epi_hidden(uint32_t t_acc, uint32_t t_dscr, const float* __restrict__ bias16,
+                                           unsigned char* planes, int c, int r) {
+  float v[16], d[16];
+  umma::tmem_ld16(t_acc, v);
+#pragma unroll
+  for (int e = 0; e < 16; ++e) {
+    const float pre = v[e] + bias16[e];
+    if constexpr (FULL) act_fwd_grad_t<ACT>(pre, v[e], d[e]);
+    else v[e] = act_fwd_t<ACT>(pre);
+  }
+  store16(planes, HPLANE, c, r, v);
+  if constexpr (FULL) {
+    umma::tmem_st16(t_dscr, d);
+    umma::tmem_wait_st();
+  }
+}
+// last hidden layer (FULL: derivative and activation parked in TMEM); OUT: this slice's output dot products
+template <int ACT, bool FULL, bool OUT>
+__device__ __forceinline__ void epi_last(uint32_t t_acc, uint32_t t_d2, uint32_t t_h2, const float* __restrict__ bias16,
+                                         const float* __restrict__ W3, int out, int c, float* zp) {
+  float v[16], d[16];
+  umma::tmem_ld16(t_acc, v);
+#pragma unroll
+  for (int e = 0; e < 16; ++e) {
+    const float pre = v[e] + bias16[e];
+    if constexpr (FULL) act_fwd_grad_t<ACT>(pre, v[e], d[e]);
+    else v[e] = act_fwd_t<ACT>(pre);
+  }
+  if constexpr (FULL) {
+    umma::tmem_st16(t_d2, d);
+    umma::tmem_st16(t_h2, v);
+    umma::tmem_wait_st();
+  }
+  if constexpr (OUT) {
+#pragma unroll
+    for (int a = 0; a < MAXA; ++a) {
+      zp[a] = 0.f;
+      if (a < out) {
+        const float* w = W3 + a * 64 + 16 * c;
+#pragma unroll
+        for (int e = 0; e < 16; ++e) zp[a] = fmaf(w[e], v[e], zp[a]);
+      }
+    }
+  }
+}
+
+}  // namespace tcf
+
+// X sub-tile ([feature][sample], leading dimension XS, `xrows` rows) -> Zout[a * XS + r] (OUT).  FULL: derivative of
+// layer 1, derivative and activation of layer 2 are parked in TMEM for mlp_backward_tcf.  Ends with a CTA barrier.
+template <int NT, bool FULL, bool OUT>
+__device__ __forceinline__ void mlp_forward_tcf(const NetL& L, TcfCtx& cx, const float* __restrict__ Xsub, int XS,
+                                                int xrows, float* __restrict__ Zout) {
+  static_assert(NT == 512, "cooperative tcgen05 MLP: 16 warps = 4 lane quarters x 4 column slices");
+  using namespace tcf;
+  const int tid = threadIdx.x, lane = tid & 31, q = (tid >> 5) & 3, c = tid >> 7, r = 32 * q + lane;
+  const uint32_t tl = cx.tmem + ((uint32_t)(32 * q) << 16) + 16 * c;
+  if (tid < 256) {   // observation planes: thread = (chunk tid >> 7, row tid & 127), 8 features
+    const int row = tid & 127, ch = tid >> 7;
+    uint32_t w[3][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int f = 8 * ch + 2 * i;
+      split3(f < xrows ? Xsub[f * XS + row] : 0.f, f + 1 < xrows ? Xsub[(f + 1) * XS + row] : 0.f, w[0][i], w[1][i],
+             w[2][i]);
+    }
+#pragma unroll
+    for (int p = 0; p < 3; ++p)
+      *reinterpret_cast<uint4*>(cx.Xp + p * XPLANE + (ch * 128 + row) * 16) = make_uint4(w[p][0], w[p][1], w[p][2], w[p][3]);
+  }
+  publish_sync();
+  if (tid == 0) {
+    umma::fence_after_sync();
+    issue6<1>(cx.tmem + ACC, k_act(cx.Xp, XPLANE), k_w(cx.W1, W1PLANE), idesc_bf16(128, 64, false, false));
+    umma::commit(cx.bar);
+  }
+  wait0(cx);
+#define GOPS_TCF_H(A) epi_hidden<A, FULL>(tl + ACC, tl + D1S, cx.b1 + 16 * c, cx.P, c, r)
+  GOPS_ACT_SWITCH(L.hact, GOPS_TCF_H)
+#undef GOPS_TCF_H
+  publish_sync();
+  if (tid == 0) {
+    umma::fence_after_sync();
+    issue6<4>(cx.tmem + ACC, k_act(cx.P, HPLANE), k_w(cx.W2, W2PLANE), idesc_bf16(128, 64, false, false));
+    umma::commit(cx.bar);
+  }
+  wait0(cx);
+  float zp[MAXA];
+#define GOPS_TCF_L(A) epi_last<A, FULL, OUT>(tl + ACC, tl + D2S, tl + H2S, cx.b2 + 16 * c, cx.W3, L.out, c, zp)
+  GOPS_ACT_SWITCH(L.hact, GOPS_TCF_L)
+#undef GOPS_TCF_L
+  if constexpr (OUT) {
+    float* Zp = reinterpret_cast<float*>(cx.Q);          // [4 slices][MAXA][128] scratch (Q is free in the forward)
+#pragma unroll
+    for (int a = 0; a < MAXA; ++a)
+      if (a < L.out) Zp[(c * MAXA + a) * 128 + r] = zp[a];
+    umma::fence_before_sync();
+    __syncthreads();
+    if (tid < 128) {
+#pragma unroll
+      for (int a = 0; a < MAXA; ++a)
+        if (a < L.out)
+          Zout[a * XS + tid] = cx.b3[a] + ((Zp[a * 128 + tid] + Zp[(MAXA + a) * 128 + tid]) +
+                                           (Zp[(2 * MAXA + a) * 128 + tid] + Zp[(3 * MAXA + a) * 128 + tid]));
+    }
+    __syncthreads();
+  } else {
+    umma::fence_before_sync();
+    __syncthreads();
+  }
+}
+
+// Zbar in Zsub rows 0..out-1.  WANT_DW: accumulate the weight gradients (TMEM: W1, b1, W2, b2; shared: W3, b3);
+// want_dx: observation gradient into rows [0, L.obs) of the X sub-tile.  Needs a FULL forward of the same sub-tile.
+template <int NT, bool WANT_DW>
+__device__ __forceinline__ void mlp_backward_tcf(const NetL& L, TcfCtx& cx, float* __restrict__ Xsub, int XS,
+                                                 const float* __restrict__ Zsub, bool want_dx) {
+  using namespace tcf;
+  const int tid = threadIdx.x, lane = tid & 31, q = (tid >> 5) & 3, c = tid >> 7, r = 32 * q + lane;
+  const uint32_t tl = cx.tmem + ((uint32_t)(32 * q) << 16) + 16 * c;
+  // ---- delta2 = (W3^T zbar) * act'(pre2) -> Q planes;  dW3 / db3 quarter partials
+  {
+    float zb[MAXA];
+#pragma unroll
+    for (int a = 0; a < MAXA; ++a) zb[a] = a < L.out ? Zsub[a * XS + r] : 0.f;
+    float d[16];
+    umma::tmem_ld16(tl + D2S, d);
+#pragma unroll
+    for (int e = 0; e < 16; ++e) {
+      float g = 0.f;
+#pragma unroll
+      for (int a = 0; a < MAXA; ++a)
+        if (a < L.out) g = fmaf(cx.W3[a * 64 + 16 * c + e], zb[a], g);
+      d[e] *= g;
+    }
+    store16(cx.Q, HPLANE, c, r, d);
+    if constexpr (WANT_DW) {
+      float h2[16];
+      umma::tmem_ld16(tl + H2S, h2);
+#pragma unroll
+      for (int a = 0; a < MAXA; ++a)
+        if (a < L.out) {
+          float v[16];
+#pragma unroll
+          for (int e = 0; e < 16; ++e) v[e] = zb[a] * h2[e];
+          warp_reduce16(v, lane);
+          if ((lane & 1) == 0) cx.red[(q * MAXA + a) * 64 + 16 * c + col16(lane)] = v[0];
+          if (c == 0) {
+            float s = zb[a];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (lane == 0) cx.red[4 * MAXA * 64 + q * MAXA + a] = s;
+          }
+        }
+    }
+  }
+  publish_sync();
+  if constexpr (WANT_DW) {   // fixed-order sum of the four lane quarters
+    if (tid < L.out * 64) {
+      const int a = tid >> 6, j = tid & 63;
+      cx.dWs[L.d_w3 + tid] += (cx.red[(0 * MAXA + a) * 64 + j] + cx.red[(1 * MAXA + a) * 64 + j]) +
+                              (cx.red[(2 * MAXA + a) * 64 + j] + cx.red[(3 * MAXA + a) * 64 + j]);
+    } else if (tid >= 256 && tid < 256 + L.out) {
+      const int a = tid - 256, o = 4 * MAXA * 64;
+      cx.dWs[L.d_b3 + a] += (cx.red[o + a] + cx.red[o + MAXA + a]) + (cx.red[o + 2 * MAXA + a] + cx.red[o + 3 * MAXA + a]);
+    }
+  }
+  if (tid == 0) {
+    umma::fence_after_sync();
+    issue6<4>(cx.tmem + ACC, k_act(cx.Q, HPLANE), mn_w(cx.W2, W2PLANE), idesc_bf16(128, 64, false, true));
+    umma::commit(cx.bar);
+    if constexpr (WANT_DW) {
+      const Op A = mn_act(cx.Q, HPLANE);
+      issue_stack(cx.tmem + DW2, A, mn_act(cx.P, HPLANE), idesc_bf16(128, 64, true, true), 3);
+      const Op one{smem_u32(cx.ones), 0u, 128u, 256u, 0u};
+      issue_stack(cx.tmem + DB2, A, one, idesc_bf16(128, 16, true, true), 1);
+      umma::commit(cx.bar + 1);
+    }
+  }
+  // ---- delta1 = (delta2 . W2) * act'(pre1) -> P planes (H1 is dead once the dW2 products have completed)
+  wait0(cx);
+  {
+    float v[16], d1[16];
+    umma::tmem_ld16(tl + ACC, v);
+    umma::tmem_ld16(tl + D1S, d1);
+#pragma unroll
+    for (int e = 0; e < 16; ++e) v[e] *= d1[e];
+    if constexpr (WANT_DW) wait1(cx);
+    store16(cx.P, HPLANE, c, r, v);
+  }
+  if (!WANT_DW && !want_dx) {
+    umma::fence_before_sync();
+    __syncthreads();
+    return;
+  }
+  publish_sync();
+  if (tid == 0) {
+    umma::fence_after_sync();
+    if (want_dx) {
+      issue6<4>(cx.tmem + ACC, k_act(cx.P, HPLANE), mn_w(cx.W1, W1PLANE), idesc_bf16(128, 16, false, true));
+      umma::commit(cx.bar);
+    }
+    if constexpr (WANT_DW) {
+      const Op A = mn_act(cx.P, HPLANE);
+      issue_stack(cx.tmem + DW1, A, mn_act(cx.Xp, XPLANE), idesc_bf16(128, 16, true, true), 3);
+      const Op one{smem_u32(cx.ones), 0u, 128u, 256u, 0u};
+      issue_stack(cx.tmem + DB1, A, one, idesc_bf16(128, 16, true, true), 1);
+      umma::commit(cx.bar + 1);
+    }
+  }
+  if (want_dx) {
+    wait0(cx);
+    if (c == 0) {
+      float v[16];
+      umma::tmem_ld16(tl + ACC, v);
+#pragma unroll
+      for (int f = 0; f < 16; ++f)
+        if (f < L.obs) Xsub[f * XS + r] = v[f];
+    }
+  }
+  if constexpr (WANT_DW) wait1(cx);
+  umma::fence_before_sync();
+  __syncthreads();
+}
+
+}  // namespace gops

@@ -11,13 +11,14 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import test_gpu_parity as base  # noqa: E402
 
 name = sys.argv[1] if len(sys.argv) > 1 else "fhadp_idp_h30"
+MODE = sys.argv[2] if len(sys.argv) > 2 else "hy"
 env_id, algname = base.CASES[name][0], base.CASES[name][1]
 alg, rec = base.build_alg(name)
 data = base.data_from(rec, env_id)
 its = [0, 1] if algname == "INFADP" else [0]
 for it in its:
     out = {}
-    for mode in ("mma", "hy"):
+    for mode in ("mma", MODE):
         os.environ["GOPS_B200_ROLLOUT"] = mode
         alg2, _ = base.build_alg(name)
         if it > 0:
@@ -30,7 +31,7 @@ for it in its:
         out[mode] = {k: p.grad.detach().cpu().numpy().copy() for k, p in mod.named_parameters()}
         print(mode, it, {k: float(v) for k, v in alg2.tb_info.items() if "oss" in k})
     for k in out["mma"]:
-        a, b = out["hy"][k], out["mma"][k]
+        a, b = out[MODE][k], out["mma"][k]
         err = np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30)
         cos = float((a * b).sum() / max(np.linalg.norm(a) * np.linalg.norm(b), 1e-30))
         print(f"it{it} {k:12s} shape {str(a.shape):10s} rel {err:.3e} cos {cos:+.6f} |hy| {np.linalg.norm(a):.4e} |mma| {np.linalg.norm(b):.4e}")
