@@ -16,7 +16,7 @@ e2e   : same call with PINNED HOST tensors -- H2D copy of the batch and D2H read
         timed region;
 roofline : the fused rollout kernel alone, timed with CUDA events on its launch stream inside the library
         (gops_b200_plan_enable_timing).  The kernel is compute bound by design: `achieved` is
-        algorithmic TFLOP/s, `peak` the tensor roof for FP32-accurate (3xTF32) GEMMs derived from the measured bf16
+        algorithmic TFLOP/s, `peak` the tensor roof for FP32-accurate (BF16x3 / 3xTF32) GEMMs derived from the measured bf16
         peak; the FP32-FFMA, HBM and raw bf16 fractions are reported beside it.
 cpu_baseline : the CPU oracle port (oracle/gops_oracle.py, the reference's algorithm in PyTorch-CPU) on a
         bounded sample of the same workload, all host threads.
@@ -294,12 +294,18 @@ def main():
             rate, sec = cpu_update_rate(args.cpu_batch, 3, 1, threads)
             cpu = {"value": rate, "unit": "env-steps/s", "cores": threads, "kind": "port",
                    "sample": f"B={args.cpu_batch}, H={H}, 3 updates after 1 warm-up (oracle/gops_oracle.py)"}
-        # kernels of this library per update: pack_params, [pack_params_tc,] rollout_kernel, reduce_partials, adam
+        # kernels of this library per update: pack_params[_tcf], [pack_params_tc,] rollout_kernel, reduce_partials, adam
         sm_count = torch.cuda.get_device_properties(0).multi_processor_count
-        hybrid = os.environ.get("GOPS_B200_ROLLOUT", "") != "mma" and Bg >= sm_count * 512
-        launches_per_step = 5 if hybrid else 4
-        roof["launch"]["kernel_path"] = ("hybrid: tcgen05/TMEM forward sweep + mma.sync reverse sweep" if hybrid
-                                         else "mma.sync forward and reverse sweeps")
+        forced = os.environ.get("GOPS_B200_ROLLOUT", "")
+        path = forced if forced in ("tc", "hy", "mma") else ("tc" if Bg >= sm_count * 512 else "mma")
+        launches_per_step = 5 if path == "hy" else 4
+        roof["launch"]["kernel_path"] = {
+            "tc": "full tcgen05: BF16x3 UMMA for every dense product, weight gradients accumulate in TMEM",
+            "hy": "hybrid: tcgen05/TMEM (3xTF32) forward sweep + mma.sync reverse sweep",
+            "mma": "mma.sync (3xTF32) forward and reverse sweeps"}[path]
+        if path == "tc":   # six bf16 MMAs per FP32-accurate product: the same roof as three TF32 MMAs at half the bf16 rate
+            roof["peak_source"] = (f"MEASURED_PEAKS.json bf16_tflops_sustained ({peak_src}) / 6 "
+                                   "(BF16x3: six bf16 products per FP32-accurate product)")
         line = {
             "metric": "batched env-steps/sec (FHADP rollout+update)", "value": value, "unit": "env-steps/s",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_total / K, "higher_is_better": True,

@@ -252,12 +252,16 @@ void make_net_tcf(const NetL& base, NetL& L) {
 }
 size_t rollout_smem_bytes_tcf(const KParams& kp) {
   return sizeof(float) * (size_t)(64 + kp.w_floats + kp.dw_floats + tcf::RED + kp.inp_max * 516 + 8 * 516) +
-         6 * tcf::HPLANE + 3 * tcf::XPLANE + tcf::ONES_B;
+         9 * tcf::HPLANE + 3 * tcf::XPLANE + tcf::ONES_B;
 }
-bool rollout_use_tc(const gops_b200_plan* pl) {
+// GOPS_B200_ROLLOUT=tc|hy|mma forces the full tcgen05 / hybrid / pure mma.sync rollout kernel; default: full tcgen05
+// once the batch fills one 512-sample chunk per SM (the S = 128 / NT = 512 configuration)
+bool rollout_use_tc(const gops_b200_plan* pl, long long batch) {
   if (!pl->tc_ok) return false;
   const char* e = getenv("GOPS_B200_ROLLOUT");
-  return e && !strcmp(e, "tc");
+  if (e && (!strcmp(e, "mma") || !strcmp(e, "hy"))) return false;
+  if (e && !strcmp(e, "tc")) return true;
+  return batch >= (long long)pl->sm_count * 512;
 }
 __global__ void pack_params_tcf_kernel(const float* __restrict__ flat, NetL L, float* __restrict__ blob) {
   const int n = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
@@ -297,7 +301,8 @@ bool rollout_use_hy(const gops_b200_plan* pl, long long batch) {
   const char* e = getenv("GOPS_B200_ROLLOUT");
   if (e && !strcmp(e, "mma")) return false;
   if (e && !strcmp(e, "hy")) return true;
-  return batch >= (long long)pl->sm_count * 512;     // the S = 128 / NT = 512 configuration is the one in use
+  if (e && !strcmp(e, "tc")) return false;
+  return !pl->tc_ok && batch >= (long long)pl->sm_count * 512;   // default only where the full tcgen05 kernel is not built
 }
 int launch_pack_tc(const float* flat, const NetL& L, float* blob, cudaStream_t st) {
   TcNet T;
@@ -389,7 +394,7 @@ int launch_rollout(gops_b200_plan* pl, const gops_b200_batch* b, int alg, cudaSt
       return fail("veh3dof_tracking: reference too short for t + horizon + pre_horizon + 1 points");
   }
   KParams& kp = pl->kp;
-  if (rollout_use_tc(pl)) {
+  if (rollout_use_tc(pl, b->batch)) {
     RolloutFn fn = rollout_fn_tc(pl->desc.model, alg);
     if (!fn) return fail("full tcgen05 rollout kernel not built for this env model");
     const int S = 128, NT = 512;
@@ -740,7 +745,7 @@ int gops_b200_rollout_grad(gops_b200_plan* pl, const gops_b200_batch* b, const f
   if (!pl || !policy_params || !grad_out || !scalars_out) return fail("null argument");
   cudaStream_t st = (cudaStream_t)stream;
   const int alg = pl->desc.alg;
-  const bool tcr = rollout_use_tc(pl);
+  const bool tcr = b && rollout_use_tc(pl, b->batch);
   if (tcr ? launch_pack_tcf(policy_params, pl->pol_tcf, pl->blob_pol_tcf, st)
           : launch_pack(policy_params, pl->kp.pol, pl->kp.hid, pl->blob_pol, st)) return 1;
   if (!tcr && b && rollout_use_hy(pl, b->batch) && launch_pack_tc(policy_params, pl->pol_tc, pl->blob_pol_tc, st)) return 1;
@@ -764,9 +769,10 @@ int gops_b200_rollout_trace(gops_b200_plan* pl, const gops_b200_batch* b, const 
   ENTRY("float* act_out, float* rew_out, float* d");
   if (!pl || !policy_params) return fail("null argument");
   cudaStream_t st = (cudaStream_t)stream;
-  if (rollout_use_tc(pl) ? launch_pack_tcf(policy_params, pl->pol_tcf, pl->blob_pol_tcf, st)
-                         : launch_pack(policy_params, pl->kp.pol, pl->kp.hid, pl->blob_pol, st)) return 1;
-  if (!rollout_use_tc(pl) && b && rollout_use_hy(pl, b->batch) &&
+  const bool tcr = b && rollout_use_tc(pl, b->batch);
+  if (tcr ? launch_pack_tcf(policy_params, pl->pol_tcf, pl->blob_pol_tcf, st)
+          : launch_pack(policy_params, pl->kp.pol, pl->kp.hid, pl->blob_pol, st)) return 1;
+  if (!tcr && b && rollout_use_hy(pl, b->batch) &&
       launch_pack_tc(policy_params, pl->pol_tc, pl->blob_pol_tc, st)) return 1;
   pl->kp.inv_B = 1.f;
   pl->kp.tr_obs = obs_out; pl->kp.tr_act = act_out; pl->kp.tr_rew = rew_out; pl->kp.tr_done = done_out;

@@ -32,20 +32,21 @@ __global__ void __launch_bounds__(NT, 1) rollout_kernel(const __grid_constant__ 
   Tiles t;
   TcfCtx cf;
   if (TC) {
-    // [64 hdr: 0 weight mbarrier, 2 / 4 MMA mbarriers, 8 TMEM slot] W blob | dWs | red | P | Q | Xp | ones | X | Z
-    // (P's and Q's third plane must be followed by >= 16 KB of mapped shared memory: the masked b2 MMA reads M = 128)
+    // [64 hdr: 0 weight mbarrier, 2 / 4 / 6 MMA mbarriers, 8 TMEM slot] W blob | dWs | red | R | P | Q | Xp | ones | X | Z
+    // (R's, P's and Q's third plane must be followed by >= 16 KB of mapped shared memory: the masked b2 MMA reads M = 128)
     t.W = smem + 64;
     t.dW = t.W + p.w_floats;
     cf.dWs = t.dW;
     cf.red = t.dW + p.dw_floats;
-    cf.P = reinterpret_cast<unsigned char*>(cf.red + tcf::RED);
+    cf.R = reinterpret_cast<unsigned char*>(cf.red + tcf::RED);
+    cf.P = cf.R + 3 * tcf::HPLANE;
     cf.Q = cf.P + 3 * tcf::HPLANE;
     cf.Xp = cf.Q + 3 * tcf::HPLANE;
     cf.ones = cf.Xp + 3 * tcf::XPLANE;
     t.X = reinterpret_cast<float*>(cf.ones + tcf::ONES_B);
     t.Z = t.X + p.inp_max * XS;
     cf.bar = mbar + 1;
-    cf.ph0 = cf.ph1 = 0u;
+    cf.ph0 = cf.ph1 = cf.ph2 = 0u;
     cf.tmem = 0u;
     t.H1 = reinterpret_cast<float*>(cf.P);   // scratch of the final scalar reduction
     t.D1 = t.H2 = t.D2 = t.R = nullptr;
@@ -131,6 +132,7 @@ __global__ void __launch_bounds__(NT, 1) rollout_kernel(const __grid_constant__ 
     if (tid == 0) {
       mbar_init(cf.bar, 1);
       mbar_init(cf.bar + 1, 1);
+      mbar_init(cf.bar + 2, 1);
       fence_mbar_init();
     }
     {  // `ones`: [2 mn-groups][16 rows][8 bf16], feature 0 = 1.0

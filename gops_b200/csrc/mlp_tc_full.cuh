@@ -40,13 +40,14 @@ struct TcfCtx {
   const float* W3;     // fp32 [out][64]
   const float *b1, *b2, *b3;
   unsigned char* Xp;   // 3 planes [2][128][8]
-  unsigned char* P;    // 3 planes [8][128][8]   H1, later delta1
+  unsigned char* P;    // 3 planes [8][128][8]   H1
   unsigned char* Q;    // 3 planes [8][128][8]   delta2 (forward: fp32 output-partial scratch)
+  unsigned char* R;    // 3 planes [8][128][8]   delta1 (own buffer: H1 stays readable for the dW2 products in flight)
   unsigned char* ones; // [2][16][8] bf16: feature 0 = 1
   float* dWs;          // dW3 [out][64] | db3 [out]
   float* red;          // [tcf::RED]
-  uint64_t* bar;       // bar[0]: critical-path MMA group, bar[1]: weight-gradient MMA group
-  uint32_t ph0, ph1;
+  uint64_t* bar;       // bar[0]: critical-path MMA groups (thread 0), bar[1] / bar[2]: dW2 / dW1 groups (thread 128)
+  uint32_t ph0, ph1, ph2;
   uint32_t tmem;
 };
 
@@ -127,11 +128,17 @@ __device__ __forceinline__ void wait1(TcfCtx& cx) {
   cx.ph1 ^= 1u;
   umma::fence_after_sync();
 }
+__device__ __forceinline__ void wait2(TcfCtx& cx) {
+  mbar_wait(cx.bar + 2, cx.ph2);
+  cx.ph2 ^= 1u;
+  umma::fence_after_sync();
+}
 __device__ __forceinline__ void publish_sync() {
   fence_proxy_async();
   umma::fence_before_sync();
   __syncthreads();
 }
+constexpr int DW_ISSUER = 128;   // thread that issues the weight-gradient MMA groups (warp 4): off the critical path
 
 // (x0, x1) -> packed bf16x2 words of the three planes (low half = x0)
 __device__ __forceinline__ void split3(float x0, float x1, uint32_t& p0, uint32_t& p1, uint32_t& p2) {
@@ -365,7 +372,10 @@ __device__ __forceinline__ void mlp_backward_tcf(const NetL& L, TcfCtx& cx, floa
     umma::fence_after_sync();
     issue6<4>(cx.tmem + ACC, k_act(cx.Q, HPLANE), mn_w(cx.W2, W2PLANE), idesc_bf16(128, 64, false, true));
     umma::commit(cx.bar);
-    if constexpr (WANT_DW) {
+  }
+  if constexpr (WANT_DW) {
+    if (tid == DW_ISSUER) {
+      umma::fence_after_sync();
       const Op A = mn_act(cx.Q, HPLANE);
       issue_stack(cx.tmem + DW2, A, mn_act(cx.P, HPLANE), idesc_bf16(128, 64, true, true), 3);
       const Op one{smem_u32(cx.ones), 0u, 128u, 256u, 0u};
@@ -373,7 +383,7 @@ __device__ __forceinline__ void mlp_backward_tcf(const NetL& L, TcfCtx& cx, floa
       umma::commit(cx.bar + 1);
     }
   }
-  // ---- delta1 = (delta2 . W2) * act'(pre1) -> P planes (H1 is dead once the dW2 products have completed)
+  // ---- delta1 = (delta2 . W2) * act'(pre1) -> R planes
   wait0(cx);
   {
     float v[16], d1[16];
@@ -381,8 +391,7 @@ __device__ __forceinline__ void mlp_backward_tcf(const NetL& L, TcfCtx& cx, floa
     umma::tmem_ld16(tl + D1S, d1);
 #pragma unroll
     for (int e = 0; e < 16; ++e) v[e] *= d1[e];
-    if constexpr (WANT_DW) wait1(cx);
-    store16(cx.P, HPLANE, c, r, v);
+    store16(cx.R, HPLANE, c, r, v);
   }
   if (!WANT_DW && !want_dx) {
     umma::fence_before_sync();
@@ -390,18 +399,19 @@ __device__ __forceinline__ void mlp_backward_tcf(const NetL& L, TcfCtx& cx, floa
     return;
   }
   publish_sync();
-  if (tid == 0) {
+  if (tid == 0 && want_dx) {
     umma::fence_after_sync();
-    if (want_dx) {
-      issue6<4>(cx.tmem + ACC, k_act(cx.P, HPLANE), mn_w(cx.W1, W1PLANE), idesc_bf16(128, 16, false, true));
-      umma::commit(cx.bar);
-    }
-    if constexpr (WANT_DW) {
-      const Op A = mn_act(cx.P, HPLANE);
+    issue6<4>(cx.tmem + ACC, k_act(cx.R, HPLANE), mn_w(cx.W1, W1PLANE), idesc_bf16(128, 16, false, true));
+    umma::commit(cx.bar);
+  }
+  if constexpr (WANT_DW) {
+    if (tid == DW_ISSUER) {
+      umma::fence_after_sync();
+      const Op A = mn_act(cx.R, HPLANE);
       issue_stack(cx.tmem + DW1, A, mn_act(cx.Xp, XPLANE), idesc_bf16(128, 16, true, true), 3);
       const Op one{smem_u32(cx.ones), 0u, 128u, 256u, 0u};
       issue_stack(cx.tmem + DB1, A, one, idesc_bf16(128, 16, true, true), 1);
-      umma::commit(cx.bar + 1);
+      umma::commit(cx.bar + 2);
     }
   }
   if (want_dx) {
@@ -414,7 +424,10 @@ __device__ __forceinline__ void mlp_backward_tcf(const NetL& L, TcfCtx& cx, floa
         if (f < L.obs) Xsub[f * XS + r] = v[f];
     }
   }
-  if constexpr (WANT_DW) wait1(cx);
+  if constexpr (WANT_DW) {   // the operand planes are rewritten by the next sub-tile
+    wait1(cx);
+    wait2(cx);
+  }
   umma::fence_before_sync();
   __syncthreads();
 }
