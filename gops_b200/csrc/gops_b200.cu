@@ -337,7 +337,7 @@ int pick_config(const gops_b200_plan* pl, long long B, bool infer) {
   return best;
 }
 
-int ensure_scratch(gops_b200_plan* pl, int grid, int NT, int H) {
+int ensure_scratch(gops_b200_plan* pl, int grid, int NT, int H, int part_rows_per_cta = 1) {
   const size_t need_tape = (size_t)grid * H * pl->kp.tape_ch * NT;
   if (need_tape > pl->tape_floats) {
     if (pl->tape) cudaFree(pl->tape);
@@ -365,7 +365,7 @@ int ensure_scratch(gops_b200_plan* pl, int grid, int NT, int H) {
       pl->xbuf_floats = need;
     }
   }
-  const size_t need_part = (size_t)grid * pl->kp.part_stride;
+  const size_t need_part = (size_t)grid * part_rows_per_cta * pl->kp.part_stride;
   if (need_part > pl->partial_floats) {
     if (pl->partial) cudaFree(pl->partial);
     pl->partial = nullptr;

@@ -144,14 +144,8 @@ __global__ void __launch_bounds__(NT, 1) rollout_kernel(const __grid_constant__ 
     __syncthreads();
     umma::fence_after_sync();
     cf.tmem = *tslot;
-    {  // zero the weight-gradient accumulators (TMEM columns DW2 .. DB1 + 16): thread (q, c) -> 16-column groups
-      const uint32_t tq = cf.tmem + ((uint32_t)(32 * ((tid >> 5) & 3)) << 16);
-      float z16[16];
-#pragma unroll
-      for (int e = 0; e < 16; ++e) z16[e] = 0.f;
-      for (uint32_t g = tid >> 7; g < (tcf::DB1 + 16 - tcf::DW2) / 16; g += 4) umma::tmem_st16(tq + tcf::DW2 + 16 * g, z16);
-      umma::tmem_wait_st();
-    }
+    cf.fresh = 1u;
+    for (int i = tid; i < p.part_stride; i += NT) part[i] = 0.f;      // FP32 accumulators of the per-step flushes
     fence_proxy_async();
     umma::fence_before_sync();
   }
@@ -419,6 +413,7 @@ __global__ void __launch_bounds__(NT, 1) rollout_kernel(const __grid_constant__ 
         scope_sync();
         MLP_BWD(true, V, ts, false);
       }
+      if constexpr (TC) tcf_flush<NT>(V, cf, part);
       stage(p.blob_pol, P.blob);
       continue;
     }
@@ -563,6 +558,7 @@ __global__ void __launch_bounds__(NT, 1) rollout_kernel(const __grid_constant__ 
         MLP_FWD(true, false, P, ts, nullptr);
         MLP_BWD(true, P, ts, k > 0);
       }
+      if constexpr (TC) tcf_flush<NT>(P, cf, part);
       if (active && k > 0) {
         if constexpr (M::KIND == 0) {
 #pragma unroll
@@ -579,42 +575,10 @@ __global__ void __launch_bounds__(NT, 1) rollout_kernel(const __grid_constant__ 
   __syncthreads();
   const int nparam = (alg == ALG_PEV) ? V.nparam : P.nparam;
   if constexpr (TC) {
-    if (alg != ALG_TRACE) {
-      // TMEM accumulators -> shared scratch -> torch flat layout.  Lanes 0..63: b0 (+ b2) part, lanes 64..127: b1 part of
-      // the stacked delta operand: dW[j][.] = acc[j][.] + acc[64 + j][.]
+    if (alg != ALG_TRACE) {   // W1, b1, W2, b2 were flushed per sub-tile (mlp_backward_tcf); W3 / b3 come from shared memory
       const NetL& U = (alg == ALG_PEV) ? V : P;
-      const int q = (tid >> 5) & 3, c = tid >> 7, r = 32 * q + (tid & 31);
-      const uint32_t tq = cf.tmem + ((uint32_t)(32 * q) << 16);
-      float* S2 = reinterpret_cast<float*>(cf.P);      // [128][64]
-      float* S1 = S2 + 128 * 64;                         // [128][16] | b1 [128] | b2 [128]
-      float v[16];
-      umma::fence_after_sync();
-      umma::tmem_ld16(tq + tcf::DW2 + 16 * c, v);
-#pragma unroll
-      for (int e = 0; e < 16; ++e) S2[r * 64 + 16 * c + e] = v[e];
-      if (c == 0) {
-        umma::tmem_ld16(tq + tcf::DW1, v);
-#pragma unroll
-        for (int e = 0; e < 16; ++e) S1[r * 16 + e] = v[e];
-      } else if (c == 1) {
-        umma::tmem_ld16(tq + tcf::DB1, v);
-        S1[2048 + r] = v[0];
-      } else if (c == 2) {
-        umma::tmem_ld16(tq + tcf::DB2, v);
-        S1[2048 + 128 + r] = v[0];
-      }
-      __syncthreads();
-      for (int i = tid; i < nparam; i += NT) {
-        float g;
-        if (i < U.g_b1) { const int j = i / U.in, k = i - j * U.in; g = S1[j * 16 + k] + S1[(64 + j) * 16 + k]; }
-        else if (i < U.g_w2) { const int j = i - U.g_b1; g = S1[2048 + j] + S1[2048 + 64 + j]; }
-        else if (i < U.g_b2) { const int e = i - U.g_w2; g = S2[e] + S2[64 * 64 + e]; }
-        else if (i < U.g_w3) { const int j = i - U.g_b2; g = S1[2048 + 128 + j] + S1[2048 + 128 + 64 + j]; }
-        else if (i < U.g_b3) g = t.dW[U.d_w3 + i - U.g_w3];
-        else g = t.dW[U.d_b3 + i - U.g_b3];
-        part[i] = g;
-      }
-      __syncthreads();
+      for (int i = U.g_w3 + tid; i < nparam; i += NT)
+        part[i] = i < U.g_b3 ? t.dW[U.d_w3 + i - U.g_w3] : t.dW[U.d_b3 + i - U.g_b3];
     }
   } else if (alg != ALG_TRACE && !WG) {
     const NetL& U = (alg == ALG_PEV) ? V : P;

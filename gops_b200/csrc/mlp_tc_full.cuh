@@ -45,6 +45,7 @@ struct TcfCtx {
   unsigned char* R;    // 3 planes [8][128][8]   delta1 (own buffer: H1 stays readable for the dW2 products in flight)
   unsigned char* ones; // [2][16][8] bf16: feature 0 = 1
   float* dWs;          // dW3 [out][64] | db3 [out]
+  uint32_t fresh;      // 1: the next weight-gradient MMA groups overwrite their TMEM accumulators (just flushed)
   float* red;          // [tcf::RED]
   uint64_t* bar;       // bar[0]: critical-path MMA groups (thread 0), bar[1] / bar[2]: dW2 / dW1 groups (thread 128)
   uint32_t ph0, ph1, ph2;
@@ -105,13 +106,16 @@ __device__ __forceinline__ void issue6(uint32_t d, const Op& A, const Op& B, uin
 #pragma unroll
   for (int ks = 0; ks < KS; ++ks) mma_bf16(d, a0 + ks * ka, b0 + ks * kb, idesc, 1u);
 }
-// D += [A_b0 | A_b1]-stacked^T . (B0 + B1 + B2) + (A_b2^T . B0 on lanes 0..63), 8 steps of 16 samples
-__device__ __forceinline__ void issue_stack(uint32_t d, const Op& A, const Op& B, uint32_t idesc, int bplanes) {
+// D = [A_b0 | A_b1]-stacked^T . (B0 + B1 + B2) + (A_b2^T . B0 on lanes 0..63), 8 steps of 16 samples
+// (`fresh`: the first MMA overwrites D -- the accumulators were just flushed, see tcf_flush)
+__device__ __forceinline__ void issue_stack(uint32_t d, const Op& A, const Op& B, uint32_t idesc, int bplanes,
+                                            uint32_t fresh) {
   const uint64_t a01 = dsc(A, 0), a2 = dsc(A, 2), ka = A.kadv >> 4, kb = B.kadv >> 4;
   for (int p = bplanes - 1; p >= 0; --p) {
     const uint64_t b = dsc(B, p);
 #pragma unroll
-    for (int ks = 0; ks < 8; ++ks) mma_bf16(d, a01 + ks * ka, b + ks * kb, idesc, 1u);
+    for (int ks = 0; ks < 8; ++ks)
+      mma_bf16(d, a01 + ks * ka, b + ks * kb, idesc, (fresh && p == bplanes - 1 && ks == 0) ? 0u : 1u);
   }
   const uint64_t b0 = dsc(B, 0);
 #pragma unroll
@@ -377,9 +381,9 @@ __device__ __forceinline__ void mlp_backward_tcf(const NetL& L, TcfCtx& cx, floa
     if (tid == DW_ISSUER) {
       umma::fence_after_sync();
       const Op A = mn_act(cx.Q, HPLANE);
-      issue_stack(cx.tmem + DW2, A, mn_act(cx.P, HPLANE), idesc_bf16(128, 64, true, true), 3);
+      issue_stack(cx.tmem + DW2, A, mn_act(cx.P, HPLANE), idesc_bf16(128, 64, true, true), 3, cx.fresh);
       const Op one{smem_u32(cx.ones), 0u, 128u, 256u, 0u};
-      issue_stack(cx.tmem + DB2, A, one, idesc_bf16(128, 16, true, true), 1);
+      issue_stack(cx.tmem + DB2, A, one, idesc_bf16(128, 16, true, true), 1, cx.fresh);
       umma::commit(cx.bar + 1);
     }
   }
@@ -408,9 +412,9 @@ __device__ __forceinline__ void mlp_backward_tcf(const NetL& L, TcfCtx& cx, floa
     if (tid == DW_ISSUER) {
       umma::fence_after_sync();
       const Op A = mn_act(cx.R, HPLANE);
-      issue_stack(cx.tmem + DW1, A, mn_act(cx.Xp, XPLANE), idesc_bf16(128, 16, true, true), 3);
+      issue_stack(cx.tmem + DW1, A, mn_act(cx.Xp, XPLANE), idesc_bf16(128, 16, true, true), 3, cx.fresh);
       const Op one{smem_u32(cx.ones), 0u, 128u, 256u, 0u};
-      issue_stack(cx.tmem + DB1, A, one, idesc_bf16(128, 16, true, true), 1);
+      issue_stack(cx.tmem + DB1, A, one, idesc_bf16(128, 16, true, true), 1, cx.fresh);
       umma::commit(cx.bar + 2);
     }
   }
@@ -427,9 +431,55 @@ __device__ __forceinline__ void mlp_backward_tcf(const NetL& L, TcfCtx& cx, floa
   if constexpr (WANT_DW) {   // the operand planes are rewritten by the next sub-tile
     wait1(cx);
     wait2(cx);
+    cx.fresh = 0u;
   }
   umma::fence_before_sync();
   __syncthreads();
+}
+
+// Move the weight-gradient accumulators W1, b1, W2, b2 from TMEM into the CTA's FP32 global partial (torch flat layout,
+// round-to-nearest adds, fixed thread ownership, coalesced) and mark them fresh.  Called once per horizon step: the
+// tensor core ADDS INTO ITS ACCUMULATOR WITH TRUNCATION, and a chain of ~1e4 accumulations over the whole kernel biased
+// the gradient by ~1e-4 at B = 2^18 (caught by the batch-linearity test); 4 sub-tiles x 32 MMAs per flush keeps the
+// bias at the 1e-6 level of the mma.sync path.  All MMA groups must have been waited for (end of mlp_backward_tcf);
+// uses the P planes as scratch.
+template <int NT>
+__device__ __forceinline__ void tcf_flush(const NetL& L, TcfCtx& cx, float* __restrict__ part) {
+  using namespace tcf;
+  const int tid = threadIdx.x, lane = tid & 31, q = (tid >> 5) & 3, c = tid >> 7, r = 32 * q + lane;
+  const uint32_t tl = cx.tmem + ((uint32_t)(32 * q) << 16);
+  float* S2 = reinterpret_cast<float*>(cx.P);          // [128][68]: lanes 0..63 b0 (+ b2) share, 64..127 b1 share
+  float* S1 = S2 + 128 * 68;                             // [128][16] | b1 [128] | b2 [128]
+  float v[16];
+  umma::tmem_ld16(tl + DW2 + 16 * c, v);
+#pragma unroll
+  for (int e4 = 0; e4 < 4; ++e4)
+    *reinterpret_cast<float4*>(S2 + r * 68 + 16 * c + 4 * e4) = make_float4(v[4 * e4], v[4 * e4 + 1], v[4 * e4 + 2], v[4 * e4 + 3]);
+  if (c == 0) {
+    umma::tmem_ld16(tl + DW1, v);
+#pragma unroll
+    for (int e = 0; e < 16; ++e) S1[r * 16 + e] = v[e];
+  } else if (c == 1) {
+    umma::tmem_ld16(tl + DB1, v);
+    S1[2048 + r] = v[0];
+  } else if (c == 2) {
+    umma::tmem_ld16(tl + DB2, v);
+    S1[2048 + 128 + r] = v[0];
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  for (int i = tid; i < 64 * 64; i += NT) {
+    const int j = i >> 6, k = i & 63;
+    part[L.g_w2 + i] += S2[j * 68 + k] + S2[(64 + j) * 68 + k];
+  }
+  for (int i = tid; i < 64 * L.in; i += NT) {
+    const int j = i / L.in, k = i - j * L.in;
+    part[L.g_w1 + i] += S1[j * 16 + k] + S1[(64 + j) * 16 + k];
+  }
+  if (tid < 64) part[L.g_b1 + tid] += S1[2048 + tid] + S1[2048 + 64 + tid];
+  else if (tid < 128) part[L.g_b2 + tid - 64] += S1[2048 + 128 + tid - 64] + S1[2048 + 128 + tid];
+  __syncthreads();
+  cx.fresh = 1u;
 }
 
 }  // namespace gops
