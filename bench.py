@@ -104,6 +104,15 @@ def usable_cores():
     return n
 
 
+def idp_init_batch(batch, seed):
+    """Synthetic inputs of the GPU arm: the initial-state box of pyth_idpendulum (reference pyth_idpendulum.py:36-38,
+    pyth_base_env.py:61-65): obs ~ U(-h, h), nobody done.  (The oracle is only imported by the CPU legs below.)"""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    h = torch.tensor([5, 0.1, 0.1, 0.3, 0.3, 0.3])
+    return {"obs": (torch.rand(batch, 6, generator=g, dtype=torch.float32) * 2 - 1) * h, "done": torch.zeros(batch)}
+
+
 def cpu_update_rate(batch, steps, warmup, threads):
     """env-steps/s of the CPU oracle port: loss + autograd backward + Adam, as FHADP.local_update."""
     import torch
@@ -186,7 +195,6 @@ def main():
     import torch.distributed as dist
     from gops_b200.create_pkg.create_alg import create_alg
     from gops_b200 import _lib
-    from oracle import gops_oracle as orc     # only for synthetic input sampling + the cpu_baseline leg
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local_rank)
@@ -202,7 +210,7 @@ def main():
     n_sets = max(2, math.ceil(1.5 * L2_BYTES / batch_bytes))
     host_sets = []
     for i in range(n_sets):
-        d = orc.sample_inputs("pyth_idpendulum", Bg, seed=1000 * rank + i)
+        d = idp_init_batch(Bg, seed=1000 * rank + i)
         host_sets.append({k: v.pin_memory() for k, v in d.items()})
     dev_sets = [{k: v.to(dev) for k, v in d.items()} for d in host_sets]
 
