@@ -84,3 +84,37 @@ def test_truncating_accumulation_bias_grows_with_chain_length():
     assert 0 <= short < 8e-6
     assert 5e-5 < long_ < 1e-3
     assert long_ > 20 * short
+
+
+def test_bf16x3_mlp_forward_emulation_is_fp32_accurate():
+    """The full tcgen05 path's layer arithmetic emulated on the CPU (bf16x3 planes of activations and weights, six
+    product terms, FP32-or-better accumulation): a 7 -> 64 -> 64 -> 1 gelu policy stays within 2e-6 of float64 --
+    the same margin the GPU parity tests measure (profiles/r01_parity_report.txt) -- while plain bf16 operands are
+    three orders of magnitude worse (why a split is needed at all)."""
+    g = torch.Generator().manual_seed(3)
+    B = 4096
+    x = torch.randn(B, 7, generator=g) * 1.5
+    W1, b1 = torch.randn(64, 7, generator=g) * 0.4, torch.randn(64, generator=g) * 0.1
+    W2, b2 = torch.randn(64, 64, generator=g) * 0.15, torch.randn(64, generator=g) * 0.1
+    W3, b3 = torch.randn(1, 64, generator=g) * 0.2, torch.randn(1, generator=g) * 0.1
+    gelu = torch.nn.functional.gelu
+
+    def mm6(a, w):          # a [B, K], w [N, K]: six-term BF16x3 product, accumulated in float64, rounded to fp32
+        as_, ws = _split3(a), _split3(w)
+        acc = sum(as_[i].double() @ ws[j].double().T for i, j in [(2, 0), (0, 2), (1, 1), (1, 0), (0, 1), (0, 0)])
+        return acc.float()
+
+    def mm1(a, w):          # single bf16 plane
+        return (_bf16(a).double() @ _bf16(w).double().T).float()
+
+    def net(mm):
+        h1 = gelu(mm(x, W1) + b1)
+        h2 = gelu(mm(h1, W2) + b2)
+        return (h2 @ W3.T + b3).double()
+
+    ref = (gelu(gelu(x.double() @ W1.double().T + b1.double()) @ W2.double().T + b2.double()) @ W3.double().T
+           + b3.double())
+    err3 = float((net(mm6) - ref).abs().max())
+    err1 = float((net(mm1) - ref).abs().max())
+    assert err3 < 2e-6, err3
+    assert err1 > 100 * err3, (err1, err3)
