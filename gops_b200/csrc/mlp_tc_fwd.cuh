@@ -2,11 +2,12 @@
 // sweep's two hidden-layer GEMMs run on the 5th-generation tensor cores, the reverse sweep stays on the mma.sync
 // path of rollout.cuh / mma_tiles.cuh.
 //
-// Why only the forward sweep: tcgen05 kind::tf32 reads a shared-memory operand transposed (MN-major) only in the
-// SWIZZLE_128B_BASE32B layout, which no K-major read accepts, so the weight-gradient products (contraction over
-// samples) and the layer products (contraction over features) cannot share one operand buffer; with the 3xTF32
-// hi | lo planes the two copies of every activation of a 128-sample sub-tile do not fit in 227 KB next to the
-// weights.  The forward pass needs K-major operands only ("tcgen05 on the rollout path").
+// Status: kept as the A/B reference (GOPS_B200_ROLLOUT=hy, 9.0 ms vs 6.3 ms on C1) of the full tcgen05 kernel
+// (mlp_tc_full.cuh), which runs the whole update on the tensor cores with BF16x3 operands.  This TF32 variant stops at
+// the forward sweep because tcgen05 kind::tf32 reads a shared-memory operand transposed (MN-major) only in the
+// SWIZZLE_128B_BASE32B layout, which no K-major read accepts: the weight-gradient products (contraction over samples)
+// and the layer products (contraction over features) cannot share one fp32 operand buffer, and two copies of every
+// activation of a 128-sample sub-tile do not fit in 227 KB (tools/umma_probe.cu).
 //
 // All NT = 512 threads cooperate on one 128-sample sub-tile: warp w owns TMEM lane quarter q = w & 3 (samples
 // r = 32 q + lane) and the 16-column slice c = w >> 2 of the accumulator:
