@@ -11,6 +11,8 @@ MAX_LQ_N = 8
 
 ALG_FHADP, ALG_INFADP_POLICY, ALG_INFADP_VALUE = 0, 1, 2
 MODEL_IDPENDULUM, MODEL_LQ, MODEL_VEH3DOFCONTI, MODEL_VEH3DOF_TRACKING = 0, 1, 2, 3
+PATH_AUTO, PATH_MMA, PATH_TC = 0, 1, 2
+PATH_NAMES = {0: "none", 1: "mma", 2: "tc"}
 ACT_IDS = {"relu": 0, "elu": 1, "gelu": 2, "selu": 3, "sigmoid": 4, "tanh": 5, "linear": 6}
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libgops_b200.so")
@@ -58,12 +60,15 @@ class Batch(C.Structure):
 PROTOTYPES = {
     "gops_b200_version": (C.c_int, []),
     "gops_b200_last_error": (C.c_char_p, []),
+    "gops_b200_launch_count": (C.c_int64, []),
     "gops_b200_plan_create": (C.c_int, [C.POINTER(PlanDesc), C.POINTER(C.c_void_p)]),
     "gops_b200_plan_destroy": (C.c_int, [C.c_void_p]),
     "gops_b200_plan_set_gamma": (C.c_int, [C.c_void_p, C.c_double]),
     "gops_b200_plan_enable_timing": (C.c_int, [C.c_void_p, C.c_int]),
     "gops_b200_plan_last_kernel_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "gops_b200_plan_launch_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),
+    "gops_b200_plan_set_path": (C.c_int, [C.c_void_p, C.c_int]),
+    "gops_b200_plan_last_path": (C.c_int, [C.c_void_p]),
     "gops_b200_plan_param_count": (C.c_int64, [C.c_void_p, C.c_int]),
     "gops_b200_rollout_grad": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_void_p, C.c_void_p, C.c_void_p,
                                          C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -92,7 +92,12 @@ class AlgorithmBase(metaclass=ABCMeta):
 class RolloutPlan:
     """Owns one `gops_b200_plan` (C side) for a fixed (algorithm kind, horizon, gamma, env, nets)."""
 
-    def __init__(self, alg_kind: int, envmodel, policy, value, horizon: int, gamma: float):
+    def __init__(self, alg_kind: int, envmodel, policy, value, horizon: int, gamma: float, device=None):
+        self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        with torch.cuda.device(self.device):     # the C side allocates its scratch on the current device
+            self._create(alg_kind, envmodel, policy, value, horizon, gamma)
+
+    def _create(self, alg_kind, envmodel, policy, value, horizon, gamma):
         desc = _lib.PlanDesc()
         desc.alg, desc.horizon, desc.gamma = alg_kind, int(horizon), float(gamma)
         desc.policy = policy.mlp_desc()
@@ -103,7 +108,22 @@ class RolloutPlan:
         self.handle = C.c_void_p()
         _lib.check(_lib.lib().gops_b200_plan_create(C.byref(desc), C.byref(self.handle)))
         _lib.check(_lib.lib().gops_b200_plan_set_gamma(self.handle, float(gamma)))
-        self.key = (alg_kind, int(horizon), float(gamma))
+        self.gamma = float(gamma)
+        self.key = (alg_kind, int(horizon))
+
+    def set_gamma(self, gamma: float):
+        if float(gamma) != self.gamma:
+            _lib.check(_lib.lib().gops_b200_plan_set_gamma(self.handle, float(gamma)))
+            self.gamma = float(gamma)
+
+    def set_path(self, path: str):
+        """'auto' | 'mma' | 'tc': kernel path of the fused rollout (raises if 'tc' is not built for this plan)."""
+        _lib.check(_lib.lib().gops_b200_plan_set_path(
+            self.handle, {"auto": _lib.PATH_AUTO, "mma": _lib.PATH_MMA, "tc": _lib.PATH_TC}[path]))
+
+    def last_path(self) -> str:
+        """Kernel path the most recent rollout launch of this plan took ('none' before the first launch)."""
+        return _lib.PATH_NAMES[_lib.lib().gops_b200_plan_last_path(self.handle)]
 
     def __del__(self):
         try:
@@ -146,12 +166,53 @@ class FusedADPMixin:
             p = next(self.networks.parameters())
         return p.device
 
+    kernel_path = "auto"     # 'auto' | 'mma' | 'tc' (RolloutPlan.set_path); tests state and assert the path here
+    MAX_PLANS = 4            # LRU: annealing pre_horizon must not leak one tape + blobs per distinct value
+
     def _plan(self, alg_kind, policy, value, horizon, gamma) -> RolloutPlan:
-        key = (alg_kind, int(horizon), float(gamma))
-        plan = self._plans.get(key)
+        dev = self._device()
+        key = (alg_kind, int(horizon), dev.index)
+        plan = self._plans.pop(key, None)
         if plan is None:
-            plan = self._plans[key] = RolloutPlan(alg_kind, self.envmodel, policy, value, horizon, gamma)
+            plan = RolloutPlan(alg_kind, self.envmodel, policy, value, horizon, gamma, device=dev)
+            while len(self._plans) >= self.MAX_PLANS:
+                self._plans.pop(next(iter(self._plans)))          # least recently used; its __del__ frees the C plan
+        self._plans[key] = plan                                   # most recently used last
+        plan.set_gamma(gamma)                                     # gamma is a table in the plan, not a new plan
+        if plan.__dict__.get("_path") != self.kernel_path:
+            plan.set_path(self.kernel_path)
+            plan._path = self.kernel_path
         return plan
+
+    # ---- loss read-back -------------------------------------------------------------------------------------------
+    # The reference reads `loss.item()` inside _compute_gradient, i.e. BEFORE the optimizer step is launched; here that
+    # would idle the GPU between the rollout and Adam.  The 4-float tail [loss | v-mean | #done | pad] is instead copied
+    # to pinned host memory AFTER the optimizer launches of the step:
+    #   loss_lag = 0 (default): wait for this step's copy -> tb_info carries this step's loss (reference semantics);
+    #   loss_lag = 1: tb_info carries the PREVIOUS step's loss (this step's on the first call), so the host runs one
+    #                 step ahead of the device and no launch gap is exposed (bench.py states which mode it times).
+    loss_lag = 0
+
+    def _tail_to_host(self, tail: torch.Tensor):
+        ring = self.__dict__.get("_tail_ring")
+        if ring is None or ring[0][0].device != torch.device("cpu"):
+            ring = [(torch.zeros(GRAD_TAIL, dtype=torch.float32).pin_memory(), torch.cuda.Event()) for _ in range(2)]
+            self.__dict__["_tail_ring"] = ring
+            self.__dict__["_tail_n"] = 0
+        n = self.__dict__["_tail_n"]
+        buf, ev = ring[n % 2]
+        with torch.cuda.device(tail.device):
+            buf.copy_(tail, non_blocking=True)
+            ev.record()
+        self.__dict__["_tail_n"] = n + 1
+        if self.loss_lag and n > 0:
+            buf, ev = ring[(n - 1) % 2]
+        ev.synchronize()
+        return buf.tolist()
+
+    def last_kernel_path(self) -> str:
+        """Path of the most recent fused rollout launch ('mma' | 'tc'), for tests and bench bookkeeping."""
+        return next(reversed(self._plans.values())).last_path() if self._plans else "none"
 
     @staticmethod
     def _world():

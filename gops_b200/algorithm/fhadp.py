@@ -54,8 +54,10 @@ class FHADP(AlgorithmBase, FusedADPMixin):
         return ("pre_horizon", "gamma")
 
     def _local_update(self, data: DataDict, iteration: int) -> InfoDict:
-        self._compute_gradient(data)
-        self.networks.policy_optimizer.step()
+        start_time = time.time()
+        tail = self._launch_gradient(data)
+        self.networks.policy_optimizer.step()          # launched behind the rollout: no host sync in between
+        self._publish(tail, start_time)
         return self.tb_info
 
     def get_remote_update_info(self, data: DataDict, iteration: int) -> Tuple[InfoDict, DataDict]:
@@ -69,14 +71,20 @@ class FHADP(AlgorithmBase, FusedADPMixin):
 
     def _compute_gradient(self, data: DataDict):
         start_time = time.time()
-        loss_policy, loss_info = self._compute_loss_policy(data)
-        self.tb_info.update(loss_info)
+        self._publish(self._launch_gradient(data), start_time)
+
+    def _publish(self, tail: torch.Tensor, start_time: float):
+        self.tb_info[tb_tags["loss_actor"]] = self._tail_to_host(tail)[0]
         self.tb_info[tb_tags["alg_time"]] = (time.time() - start_time) * 1000  # ms
 
-    def _compute_loss_policy(self, data: DataDict) -> Tuple[torch.Tensor, InfoDict]:
-        """Loss AND gradient in one fused launch (the gradient lands in the policy's `.grad`)."""
+    def _launch_gradient(self, data: DataDict) -> torch.Tensor:
+        """Loss AND gradient in one fused launch (the gradient lands in the policy's `.grad`); returns the device
+        tail [loss | - | #done | -] without synchronising."""
         pol = self.networks.policy
         plan = self._plan(_lib.ALG_FHADP, pol, None, self.pre_horizon, self.gamma)
-        tail = self._rollout_grad(plan, data, pol.flat_params, pol.flat_params, None, None)
-        loss_policy = tail[0]
-        return loss_policy, {tb_tags["loss_actor"]: loss_policy.item()}
+        return self._rollout_grad(plan, data, pol.flat_params, pol.flat_params, None, None)
+
+    def _compute_loss_policy(self, data: DataDict) -> Tuple[torch.Tensor, InfoDict]:
+        """Reference signature (fhadp.py:113-125): (loss, info); the gradient is already in `.grad`."""
+        tail = self._launch_gradient(data)
+        return tail[0], {tb_tags["loss_actor"]: tail[0].item()}

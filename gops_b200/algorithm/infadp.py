@@ -67,12 +67,16 @@ class INFADP(AlgorithmBase, FusedADPMixin):
         return ("gamma", "tau", "pev_step", "pim_step", "forward_step", "reward_scale")
 
     def local_update(self, data: dict, iteration: int) -> dict:
-        update_list = self.__compute_gradient(data, iteration)
-        self.__update(update_list)
+        start_time = time.time()
+        update_list, tail = self.__launch_gradient(data, iteration)
+        self.__update(update_list)                   # Adam + Polyak launched behind the rollout, no sync in between
+        self.__publish(update_list, tail, start_time)
         return self.tb_info
 
     def get_remote_update_info(self, data: dict, iteration: int) -> Tuple[dict, dict]:
-        update_list = self.__compute_gradient(data, iteration)
+        start_time = time.time()
+        update_list, tail = self.__launch_gradient(data, iteration)
+        self.__publish(update_list, tail, start_time)
         update_info = {name: [p.grad for p in self.networks.net_dict[name].parameters()] for name in update_list}
         return self.tb_info, update_info
 
@@ -89,20 +93,20 @@ class INFADP(AlgorithmBase, FusedADPMixin):
             polyak_update(self.networks.target_net_dict[net_name].flat_params,
                           self.networks.net_dict[net_name].flat_params, self.tau)
 
-    def __compute_gradient(self, data, iteration):
-        update_list = []
-        start_time = time.time()
+    def __launch_gradient(self, data, iteration):
+        """infadp.py:135-157: value branch on PEV iterations, policy branch on PIM iterations (no host sync)."""
         if iteration % (self.pev_step + self.pim_step) < self.pev_step:
-            loss_v, v = self.__compute_loss_v(data)
-            self.tb_info[tb_tags["loss_critic"]] = loss_v.item()
-            self.tb_info[tb_tags["critic_avg_value"]] = v.item()
-            update_list.append("v")
+            return ["v"], self.__compute_loss_v(data)
+        return ["policy"], self.__compute_loss_policy(data)
+
+    def __publish(self, update_list, tail, start_time):
+        host = self._tail_to_host(tail)
+        if update_list[0] == "v":
+            self.tb_info[tb_tags["loss_critic"]] = host[0]
+            self.tb_info[tb_tags["critic_avg_value"]] = host[1]
         else:
-            loss_policy = self.__compute_loss_policy(data)
-            self.tb_info[tb_tags["loss_actor"]] = loss_policy.item()
-            update_list.append("policy")
+            self.tb_info[tb_tags["loss_actor"]] = host[0]
         self.tb_info[tb_tags["alg_time"]] = (time.time() - start_time) * 1000  # ms
-        return update_list
 
     def __compute_loss_v(self, data):
         """mean((v(o) - [sum_k gamma^k r_k + (~d) gamma^n v_target(o_n)])^2), gradient -> v.grad."""
@@ -110,7 +114,7 @@ class INFADP(AlgorithmBase, FusedADPMixin):
         plan = self._plan(_lib.ALG_INFADP_VALUE, nets.policy, nets.v, self.forward_step, self.gamma)
         tail = self._rollout_grad(plan, data, nets.v.flat_params, nets.policy.flat_params, nets.v.flat_params,
                                   nets.v_target.flat_params)
-        return tail[0], tail[1]
+        return tail
 
     def __compute_loss_policy(self, data):
         """-mean(sum_k gamma^k r_k + (~d) gamma^n v_target(o_n)), gradient -> policy.grad."""
@@ -118,4 +122,4 @@ class INFADP(AlgorithmBase, FusedADPMixin):
         plan = self._plan(_lib.ALG_INFADP_POLICY, nets.policy, nets.v, self.forward_step, self.gamma)
         tail = self._rollout_grad(plan, data, nets.policy.flat_params, nets.policy.flat_params, None,
                                   nets.v_target.flat_params)
-        return tail[0]
+        return tail

@@ -44,9 +44,13 @@ class _FusedMlp(nn.Module, Action_Distribution):
         if len(hidden) != 2 or hidden[0] != hidden[1]:
             raise NotImplementedError(
                 f"gops_b200 fused MLP kernels need two equal hidden layers, got hidden_sizes={hidden}")
+        if hidden[0] not in (64, 256):
+            raise NotImplementedError(f"gops_b200 fused MLP kernels are built for hidden widths 64 and 256, got {hidden[0]}")
         self._obs_dim, self._out_dim, self._hidden = in_dim, out_dim, hidden[0]
         self._hidden_act = kwargs["hidden_activation"]
         self._out_act = kwargs.get("output_activation", "linear")
+        if self._out_act != "linear":
+            raise NotImplementedError("gops_b200 fused MLP kernels support output_activation='linear' only")
         net = mlp([in_dim + int(self._time_input)] + hidden + [out_dim],
                   get_activation_func(self._hidden_act), get_activation_func(self._out_act))
         setattr(self, self._net_attr, net)

@@ -7,6 +7,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
 #include <new>
 #include <string>
 #include <vector>
@@ -21,6 +22,7 @@ using namespace gops;
 namespace {
 
 thread_local std::string g_err;
+std::atomic<long long> g_launches{0};     // kernels launched by this library (gops_b200_launch_count)
 
 int fail(const std::string& msg) {
   g_err = msg;
@@ -49,6 +51,28 @@ int fail(const std::string& msg) {
   } while (0)
 
 int round4(int x) { return (x + 3) & ~3; }
+
+// Every entry point runs on the device that owns its plan / buffers, whatever the caller's current device is
+// (networks on cuda:1 while cuda:0 is current must not put scratch on one GPU and the launch on the other).
+struct DevGuard {
+  int prev = -1;
+  bool switched = false;
+  explicit DevGuard(int dev) {
+    if (cudaGetDevice(&prev) == cudaSuccess && dev >= 0 && prev != dev) switched = cudaSetDevice(dev) == cudaSuccess;
+  }
+  ~DevGuard() {
+    if (switched) cudaSetDevice(prev);
+  }
+};
+int device_of(const void* p) {
+  cudaPointerAttributes a;
+  if (p && cudaPointerGetAttributes(&a, p) == cudaSuccess && a.type == cudaMemoryTypeDevice) return a.device;
+  (void)cudaGetLastError();
+  int d = 0;
+  cudaGetDevice(&d);
+  return d;
+}
+constexpr int kMaxDevices = 64;
 
 bool make_net(const gops_b200_mlp_desc& d, NetL& L, std::string& why) {
   memset(&L, 0, sizeof(L));
@@ -126,8 +150,6 @@ RolloutFn rollout_fn_vehconti(int hid, int cfg, int alg);
 RolloutFn rollout_fn_vehtrack(int hid, int cfg, int alg);
 StepFn step_fn_idp();
 StepFn step_fn_lq();
-RolloutFn rollout_fn_hy_idp(int alg);   // hybrid kernels: tcgen05 forward sweep + mma.sync reverse sweep
-RolloutFn rollout_fn_hy_lq(int alg);
 RolloutFn rollout_fn_tc_idp(int alg);   // full tcgen05 kernels (BF16x3, TMEM-resident weight gradients)
 RolloutFn rollout_fn_tc_lq(int alg);
 }  // namespace gops
@@ -140,13 +162,6 @@ RolloutFn rollout_fn(int model, int hid, int cfg, int alg) {
     case GOPS_MODEL_LQ: return rollout_fn_lq(hid, cfg, alg);
     case GOPS_MODEL_VEH3DOFCONTI: return rollout_fn_vehconti(hid, cfg, alg);
     case GOPS_MODEL_VEH3DOF_TRACKING: return rollout_fn_vehtrack(hid, cfg, alg);
-    default: return nullptr;
-  }
-}
-RolloutFn rollout_fn_hy(int model, int alg) {
-  switch (model) {
-    case GOPS_MODEL_IDPENDULUM: return rollout_fn_hy_idp(alg);
-    case GOPS_MODEL_LQ: return rollout_fn_hy_lq(alg);
     default: return nullptr;
   }
 }
@@ -183,11 +198,6 @@ struct gops_b200_plan {
   size_t xbuf_floats = 0;
   float* blob_tc = nullptr;     // tcgen05 inference path: chunk-major hi / lo weight planes
   int blob_tc_floats = 0;
-  // hybrid rollout kernel (tcgen05 forward sweep): policy NetL with chunk-major blob offsets + its packed blob
-  bool hy_ok = false;
-  NetL pol_tc;
-  float* blob_pol_tc = nullptr;
-  bool hy_attr_set[4] = {};
   // full tcgen05 rollout kernel (BF16x3): NetL with the bf16-plane blob offsets, packed blobs
   bool tc_ok = false;
   NetL pol_tcf, val_tcf;
@@ -198,6 +208,7 @@ struct gops_b200_plan {
   bool attr_set[4][4] = {};   // [alg][cfg]
   bool timing = false;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int path = GOPS_PATH_AUTO, last_path = 0;
   int last_grid = 0, last_S = 0, last_NT = 0;
   size_t last_smem = 0;
 };
@@ -218,20 +229,6 @@ size_t infer_smem_bytes(const KParams& kp, int S, int NT) {
   return sizeof(float) * (size_t)(4 + kp.w_floats + kp.inp_max * XS + 2 * HID * SP + 8 * XS);
 }
 
-// NetL of the tcgen05 forward: same geometry, blob = chunk-major planes (W1 padded to TC_K1 inputs)
-void make_net_tc(const NetL& base, NetL& L) {
-  L = base;
-  int o = 0;
-  L.o_w1 = o; o += 64 * TC_K1;
-  L.o_w1l = o; o += 64 * TC_K1;
-  L.o_w2 = o; o += 64 * 64;
-  L.o_w2l = o; o += 64 * 64;
-  L.o_w3 = o; o += round4(L.out * 64);
-  L.o_b1 = o; o += 64;
-  L.o_b2 = o; o += 64;
-  L.o_b3 = o; o += 4;
-  L.blob = o;
-}
 // NetL of the full tcgen05 path: blob = 3 bf16 planes of W1 ([2][64][8]) and W2 ([8][64][8]), then fp32 W3, b1, b2, b3
 // (offsets in floats); shared-memory accumulators only for W3 / b3 (the rest accumulates in TMEM)
 void make_net_tcf(const NetL& base, NetL& L) {
@@ -254,13 +251,16 @@ size_t rollout_smem_bytes_tcf(const KParams& kp) {
   return sizeof(float) * (size_t)(64 + kp.w_floats + kp.dw_floats + tcf::RED + kp.inp_max * 516 + 8 * 516) +
          9 * tcf::HPLANE + 3 * tcf::XPLANE + tcf::ONES_B;
 }
-// GOPS_B200_ROLLOUT=tc|hy|mma forces the full tcgen05 / hybrid / pure mma.sync rollout kernel; default: full tcgen05
-// once the batch fills one 512-sample chunk per SM (the S = 128 / NT = 512 configuration)
+// Path of a launch: the plan option (gops_b200_plan_set_path), overridden by GOPS_B200_ROLLOUT=tc|mma; AUTO takes the
+// tcgen05 kernel wherever it is built for the plan (64-wide nets, <= 16 inputs, state == obs models)
 bool rollout_use_tc(const gops_b200_plan* pl, long long batch) {
   if (!pl->tc_ok) return false;
+  int path = pl->path;
   const char* e = getenv("GOPS_B200_ROLLOUT");
-  if (e && (!strcmp(e, "mma") || !strcmp(e, "hy"))) return false;
-  if (e && !strcmp(e, "tc")) return true;
+  if (e && !strcmp(e, "mma")) path = GOPS_PATH_MMA;
+  if (e && !strcmp(e, "tc")) path = GOPS_PATH_TC;
+  if (path == GOPS_PATH_MMA) return false;
+  if (path == GOPS_PATH_TC) return true;
   return batch >= (long long)pl->sm_count * 512;
 }
 __global__ void pack_params_tcf_kernel(const float* __restrict__ flat, NetL L, float* __restrict__ blob) {
@@ -291,28 +291,8 @@ __global__ void pack_params_tcf_kernel(const float* __restrict__ flat, NetL L, f
 }
 int launch_pack_tcf(const float* flat, const NetL& L, float* blob, cudaStream_t st) {
   pack_params_tcf_kernel<<<8, 256, 0, st>>>(flat, L, blob);
+  ++g_launches;
   CUDA_OK_L(cudaGetLastError(), "launch#tcf-pack");
-  return 0;
-}
-
-// GOPS_B200_ROLLOUT=hy|mma forces the hybrid (tcgen05 forward sweep) / pure mma.sync rollout kernel
-bool rollout_use_hy(const gops_b200_plan* pl, long long batch) {
-  if (!pl->hy_ok) return false;
-  const char* e = getenv("GOPS_B200_ROLLOUT");
-  if (e && !strcmp(e, "mma")) return false;
-  if (e && !strcmp(e, "hy")) return true;
-  if (e && !strcmp(e, "tc")) return false;
-  return !pl->tc_ok && batch >= (long long)pl->sm_count * 512;   // default only where the full tcgen05 kernel is not built
-}
-int launch_pack_tc(const float* flat, const NetL& L, float* blob, cudaStream_t st) {
-  TcNet T;
-  memset(&T, 0, sizeof(T));
-  T.in = L.in; T.obs = L.obs; T.out = L.out; T.hact = L.hact; T.time_input = L.time_input; T.k1 = TC_K1;
-  T.g_w1 = L.g_w1; T.g_b1 = L.g_b1; T.g_w2 = L.g_w2; T.g_b2 = L.g_b2; T.g_w3 = L.g_w3; T.g_b3 = L.g_b3;
-  T.o_w1h = L.o_w1; T.o_w1l = L.o_w1l; T.o_w2h = L.o_w2; T.o_w2l = L.o_w2l;
-  T.o_w3 = L.o_w3; T.o_b1 = L.o_b1; T.o_b2 = L.o_b2; T.o_b3 = L.o_b3; T.blob = L.blob;
-  pack_params_tc_kernel<<<8, 256, 0, st>>>(flat, T, blob);
-  CUDA_OK_L(cudaGetLastError(), "launch#tc-pack2");
   return 0;
 }
 
@@ -377,6 +357,7 @@ int ensure_scratch(gops_b200_plan* pl, int grid, int NT, int H, int part_rows_pe
 
 int launch_pack(const float* flat, const NetL& L, int hid, float* blob, cudaStream_t st) {
   pack_params_kernel<<<hid > 64 ? 64 : 8, 256, 0, st>>>(flat, L, hid, blob);
+  ++g_launches;
   CUDA_OK_L(cudaGetLastError(), "launch#1");
   return 0;
 }
@@ -432,29 +413,24 @@ int launch_rollout(gops_b200_plan* pl, const gops_b200_batch* b, int alg, cudaSt
     k2.partial = pl->partial;
     if (pl->timing) CUDA_OK(cudaEventRecord(pl->ev0, st));
     fn<<<grid, NT, smem, st>>>(k2);
+    ++g_launches;
     CUDA_OK_L(cudaGetLastError(), "launch#2-tc");
     if (pl->timing) CUDA_OK(cudaEventRecord(pl->ev1, st));
-    pl->last_grid = grid; pl->last_S = S; pl->last_NT = NT; pl->last_smem = smem;
+    pl->last_grid = grid; pl->last_S = S; pl->last_NT = NT; pl->last_smem = smem; pl->last_path = GOPS_PATH_TC;
     if (alg != ALG_TRACE) {
       const int n = upd.nparam + 3;
       reduce_partials_kernel<<<(n + 255) / 256, 256, 0, st>>>(pl->partial, grid, k2.part_stride, upd.nparam, grad_out,
                                                              scalars_out);
+      ++g_launches;
       CUDA_OK_L(cudaGetLastError(), "launch#3-tc");
     }
     return 0;
   }
-  const bool hy = rollout_use_hy(pl, b->batch);
-  const int cfg = hy ? 0 : pick_config(pl, b->batch, false);
+  const int cfg = pick_config(pl, b->batch, false);
   if (cfg < 0) return fail("no kernel configuration fits in shared memory");
   const int S = config_of(pl, cfg).S, NT = config_of(pl, cfg).NT;
-  RolloutFn fn = hy ? rollout_fn_hy(pl->desc.model, alg) : rollout_fn(pl->desc.model, kp.hid, cfg, alg);
+  RolloutFn fn = rollout_fn(pl->desc.model, kp.hid, cfg, alg);
   if (!fn) return fail("env model kind not built into this library");
-  const int w_floats_plan = kp.w_floats;
-  if (hy) {
-    kp.pol_tc = pl->pol_tc;
-    kp.blob_pol_tc = pl->blob_pol_tc;
-    if (pl->pol_tc.blob > kp.w_floats) kp.w_floats = pl->pol_tc.blob;   // one staging region for both blob layouts
-  }
   kp.alg = alg;
   kp.batch = b->batch;
   kp.n_tiles = (int)((b->batch + NT - 1) / NT);
@@ -466,9 +442,9 @@ int launch_rollout(gops_b200_plan* pl, const gops_b200_batch* b, int alg, cudaSt
   const NetL& upd = (alg == ALG_PEV) ? kp.val : kp.pol;
   kp.part_stride = round4(upd.nparam + 4);
   kp.dw_floats = round4(upd.nacc);
-  const size_t smem = rollout_smem_bytes(kp, S, NT) + (hy ? 12 * sizeof(float) : 0);   // hybrid: 16-float header
-  if (smem > (size_t)pl->max_smem) { kp.w_floats = w_floats_plan; return fail("rollout kernel does not fit in shared memory"); }
-  bool& attr = hy ? pl->hy_attr_set[alg] : pl->attr_set[alg][cfg];
+  const size_t smem = rollout_smem_bytes(kp, S, NT);
+  if (smem > (size_t)pl->max_smem) return fail("rollout kernel does not fit in shared memory");
+  bool& attr = pl->attr_set[alg][cfg];
   if (!attr) {
     CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, pl->max_smem));
     attr = true;
@@ -488,14 +464,15 @@ int launch_rollout(gops_b200_plan* pl, const gops_b200_batch* b, int alg, cudaSt
   kp.partial = pl->partial;
   if (pl->timing) CUDA_OK(cudaEventRecord(pl->ev0, st));
   fn<<<grid, NT, smem, st>>>(kp);
-  kp.w_floats = w_floats_plan;
+  ++g_launches;
   CUDA_OK_L(cudaGetLastError(), "launch#2");
   if (pl->timing) CUDA_OK(cudaEventRecord(pl->ev1, st));
-  pl->last_grid = grid; pl->last_S = S; pl->last_NT = NT; pl->last_smem = smem;
+  pl->last_grid = grid; pl->last_S = S; pl->last_NT = NT; pl->last_smem = smem; pl->last_path = GOPS_PATH_MMA;
   if (alg != ALG_TRACE) {
     const int n = upd.nparam + 3;
     reduce_partials_kernel<<<(n + 255) / 256, 256, 0, st>>>(pl->partial, grid, kp.part_stride, upd.nparam, grad_out,
                                                            scalars_out);
+    ++g_launches;
     CUDA_OK_L(cudaGetLastError(), "launch#3");
   }
   return 0;
@@ -506,6 +483,7 @@ int launch_rollout(gops_b200_plan* pl, const gops_b200_batch* b, int alg, cudaSt
 extern "C" {
 
 int gops_b200_version(void) { return GOPS_B200_ABI_VERSION; }
+int64_t gops_b200_launch_count(void) { return (int64_t)g_launches.load(); }
 const char* gops_b200_last_error(void) { return g_err.c_str(); }
 
 int gops_b200_plan_create(const gops_b200_plan_desc* d, gops_b200_plan** out) {
@@ -644,16 +622,6 @@ int gops_b200_plan_create(const gops_b200_plan_desc* d, gops_b200_plan** out) {
     kp.osc = pl->osc;
     kp.osh = pl->osc + od;
   }
-  // hybrid rollout kernel: 64-wide policy whose inputs fit one 16-wide K block, state == obs models
-  if (kp.hid == 64 && kp.pol.in <= TC_K1 && rollout_fn_hy(d->model, d->alg)) {
-    make_net_tc(kp.pol, pl->pol_tc);
-    if (cudaMalloc(&pl->blob_pol_tc, (size_t)pl->pol_tc.blob * sizeof(float)) != cudaSuccess) {
-      gops_b200_plan_destroy(pl);
-      return fail("cudaMalloc failed for plan scratch (tcgen05 policy blob)");
-    }
-    cudaMemset(pl->blob_pol_tc, 0, (size_t)pl->pol_tc.blob * sizeof(float));
-    pl->hy_ok = true;
-  }
   // full tcgen05 rollout kernel: 64-wide nets whose inputs fit one 16-wide K block, state == obs models
   if (kp.hid == 64 && kp.pol.in <= tcf::K1 && (!infadp || kp.val.in <= tcf::K1) && rollout_fn_tc(d->model, d->alg)) {
     make_net_tcf(kp.pol, pl->pol_tcf);
@@ -679,6 +647,7 @@ int gops_b200_plan_create(const gops_b200_plan_desc* d, gops_b200_plan** out) {
 
 int gops_b200_plan_set_gamma(gops_b200_plan* pl, double gamma) {
   if (!pl) return fail("null plan");
+  DevGuard dg(pl->device);
   std::vector<float> gp(pl->kp.horizon + 1);
   for (int k = 0; k <= pl->kp.horizon; ++k) gp[k] = (float)pow(gamma, (double)k);
   pl->kp.gamma = (float)gamma;
@@ -688,6 +657,7 @@ int gops_b200_plan_set_gamma(gops_b200_plan* pl, double gamma) {
 
 int gops_b200_plan_enable_timing(gops_b200_plan* pl, int enable) {
   if (!pl) return fail("null plan");
+  DevGuard dg(pl->device);
   if (enable && !pl->ev0) {
     CUDA_OK(cudaEventCreate(&pl->ev0));
     CUDA_OK(cudaEventCreate(&pl->ev1));
@@ -703,6 +673,16 @@ int gops_b200_plan_last_kernel_ms(gops_b200_plan* pl, float* ms) {
   return 0;
 }
 
+int gops_b200_plan_set_path(gops_b200_plan* pl, int path) {
+  if (!pl) return fail("null plan");
+  if (path != GOPS_PATH_AUTO && path != GOPS_PATH_MMA && path != GOPS_PATH_TC) return fail("unknown kernel path");
+  if (path == GOPS_PATH_TC && !pl->tc_ok)
+    return fail("the tcgen05 rollout kernel is not built for this plan (needs 64-wide nets, <= 16 inputs, idpendulum / lq)");
+  pl->path = path;
+  return 0;
+}
+int gops_b200_plan_last_path(const gops_b200_plan* pl) { return pl ? pl->last_path : -1; }
+
 int gops_b200_plan_launch_info(const gops_b200_plan* pl, int32_t* out4) {
   if (!pl || !out4) return fail("null argument");
   out4[0] = pl->last_grid; out4[1] = pl->last_NT; out4[2] = pl->last_S; out4[3] = (int32_t)pl->last_smem;
@@ -712,17 +692,18 @@ int gops_b200_plan_launch_info(const gops_b200_plan* pl, int32_t* out4) {
 int gops_b200_plan_destroy(gops_b200_plan* pl) {
   ENTRY("gops_b200_plan_destroy(gops_b200_plan* p");
   if (!pl) return 0;
+  DevGuard dg(pl->device);
   if (pl->ev0) { cudaEventDestroy(pl->ev0); cudaEventDestroy(pl->ev1); }
   void* ptrs[] = {pl->gpow, pl->blob_pol, pl->blob_val, pl->blob_vtg, pl->tape, pl->partial, pl->ext_ref, pl->xbuf, pl->osc,
-                  pl->blob_tc, pl->blob_pol_tc, pl->blob_pol_tcf, pl->blob_val_tcf, pl->blob_vtg_tcf};
+                  pl->blob_tc, pl->blob_pol_tcf, pl->blob_val_tcf, pl->blob_vtg_tcf};
   const char* names[] = {"gpow", "blob_pol", "blob_val", "blob_vtg", "tape", "partial", "ext_ref", "xbuf", "osc", "blob_tc",
-                         "blob_pol_tc", "blob_pol_tcf", "blob_val_tcf", "blob_vtg_tcf"};
+                         "blob_pol_tcf", "blob_val_tcf", "blob_vtg_tcf"};
   if (getenv("GOPS_B200_DEBUG")) {
     fprintf(stderr, "[gops_b200] destroy plan %p alg %d model %d:", (void*)pl, pl->desc.alg, pl->desc.model);
-    for (int i = 0; i < 14; ++i) fprintf(stderr, " %s=%p", names[i], ptrs[i]);
+    for (int i = 0; i < 13; ++i) fprintf(stderr, " %s=%p", names[i], ptrs[i]);
     fprintf(stderr, "\n");
   }
-  for (int i = 0; i < 14; ++i) {
+  for (int i = 0; i < 13; ++i) {
     const cudaError_t e = cudaFree(ptrs[i]);
     if (e != cudaSuccess) {
       (void)cudaGetLastError();
@@ -743,12 +724,12 @@ int gops_b200_rollout_grad(gops_b200_plan* pl, const gops_b200_batch* b, const f
                            float* grad_out, float* scalars_out, void* stream) {
   ENTRY("float* grad_out, float* scalars_out, voi");
   if (!pl || !policy_params || !grad_out || !scalars_out) return fail("null argument");
+  DevGuard dg(pl->device);
   cudaStream_t st = (cudaStream_t)stream;
   const int alg = pl->desc.alg;
   const bool tcr = b && rollout_use_tc(pl, b->batch);
   if (tcr ? launch_pack_tcf(policy_params, pl->pol_tcf, pl->blob_pol_tcf, st)
           : launch_pack(policy_params, pl->kp.pol, pl->kp.hid, pl->blob_pol, st)) return 1;
-  if (!tcr && b && rollout_use_hy(pl, b->batch) && launch_pack_tc(policy_params, pl->pol_tc, pl->blob_pol_tc, st)) return 1;
   if (alg != GOPS_ALG_FHADP) {
     if (!vtarget_params) return fail("vtarget_params required for INFADP");
     if (tcr ? launch_pack_tcf(vtarget_params, pl->val_tcf, pl->blob_vtg_tcf, st)
@@ -768,22 +749,29 @@ int gops_b200_rollout_trace(gops_b200_plan* pl, const gops_b200_batch* b, const 
                             float* act_out, float* rew_out, float* done_out, void* stream) {
   ENTRY("float* act_out, float* rew_out, float* d");
   if (!pl || !policy_params) return fail("null argument");
+  DevGuard dg(pl->device);
   cudaStream_t st = (cudaStream_t)stream;
   const bool tcr = b && rollout_use_tc(pl, b->batch);
   if (tcr ? launch_pack_tcf(policy_params, pl->pol_tcf, pl->blob_pol_tcf, st)
           : launch_pack(policy_params, pl->kp.pol, pl->kp.hid, pl->blob_pol, st)) return 1;
-  if (!tcr && b && rollout_use_hy(pl, b->batch) &&
-      launch_pack_tc(policy_params, pl->pol_tc, pl->blob_pol_tc, st)) return 1;
   pl->kp.inv_B = 1.f;
   pl->kp.tr_obs = obs_out; pl->kp.tr_act = act_out; pl->kp.tr_rew = rew_out; pl->kp.tr_done = done_out;
   return launch_rollout(pl, b, ALG_TRACE, st, nullptr, nullptr);
 }
 
 // tcgen05 / TMEM inference (mlp_tc.cuh).  GOPS_B200_INFER=tc|mma forces one of the two 64-wide paths.
-static bool infer_use_tc(const gops_b200_plan* pl, int64_t batch) {
+static bool infer_use_tc(const gops_b200_plan* pl, int64_t batch, int use_val) {
   if (pl->kp.hid != 64) return false;
   const char* e = getenv("GOPS_B200_INFER");
   if (e && !strcmp(e, "mma")) return false;
+  // the tcgen05 inference kernel keeps the input planes in shared memory: wide inputs stay on the mma.sync kernel
+  // whatever the batch size is (no batch-dependent failure)
+  const NetL& L = use_val ? pl->kp.val : pl->kp.pol;
+  TcNet T;
+  memset(&T, 0, sizeof(T));
+  T.k1 = L.in8;
+  T.blob = 2 * 64 * T.k1 + 2 * 64 * 64 + round4(L.out * 64) + 64 + 64 + 4;
+  if (tc_infer_smem_bytes(T, 1) > (size_t)pl->max_smem) return false;
   if (e && !strcmp(e, "tc")) return true;
   return batch >= 4096;
 }
@@ -816,8 +804,10 @@ static int infer_tc(gops_b200_plan* pl, const float* params, const NetL& L, cons
     pl->blob_tc_floats = T.blob;
   }
   pack_params_tc_kernel<<<8, 256, 0, st>>>(params, T, pl->blob_tc);
+  ++g_launches;
   CUDA_OK_L(cudaGetLastError(), "launch#tc-pack");
-  static bool attr = false;
+  static bool attr_of[kMaxDevices] = {};     // function attributes are per device
+  bool& attr = attr_of[pl->device >= 0 && pl->device < kMaxDevices ? pl->device : 0];
   if (!attr) {
     CUDA_OK(cudaFuncSetAttribute(mlp_infer_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, pl->max_smem));
     CUDA_OK(cudaFuncSetAttribute(mlp_infer_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, pl->max_smem));
@@ -828,6 +818,7 @@ static int infer_tc(gops_b200_plan* pl, const float* params, const NetL& L, cons
   const int grid = (int)(ctas < pl->sm_count ? ctas : pl->sm_count);
   if (wgs == 2) mlp_infer_tc_kernel<2><<<grid, 256, smem, st>>>(T, pl->blob_tc, obs, batch, virtual_t, out);
   else mlp_infer_tc_kernel<1><<<grid, 128, smem, st>>>(T, pl->blob_tc, obs, batch, virtual_t, out);
+  ++g_launches;
   CUDA_OK_L(cudaGetLastError(), "launch#tc-infer");
   return 0;
 }
@@ -836,9 +827,10 @@ static int infer_common(gops_b200_plan* pl, const float* params, int use_val, co
                         float virtual_t, float* out, void* stream, bool squash) {
   if (!pl || !params || !obs || !out) return fail("null argument");
   if (batch <= 0) return fail("empty batch");
+  DevGuard dg(pl->device);
   cudaStream_t st = (cudaStream_t)stream;
   const NetL& L = use_val ? pl->kp.val : pl->kp.pol;
-  if (infer_use_tc(pl, batch)) return infer_tc(pl, params, L, obs, batch, virtual_t, out, st, squash);
+  if (infer_use_tc(pl, batch, use_val)) return infer_tc(pl, params, L, obs, batch, virtual_t, out, st, squash);
   float* blob = use_val ? pl->blob_val : pl->blob_pol;
   if (launch_pack(params, L, pl->kp.hid, blob, st)) return 1;
   const int cfg = pick_config(pl, batch, true);
@@ -854,6 +846,7 @@ static int infer_common(gops_b200_plan* pl, const float* params, int use_val, co
                                  pl->max_smem));                                                              \
     mlp_infer_kernel<HH, SS, NN><<<grid, NN, smem, st>>>(pl->kp, blob, use_val, obs, batch, virtual_t,        \
                                                          squash ? 1 : 0, out);                               \
+    ++g_launches;                                                                                             \
   } while (0)
   if (pl->kp.hid > 64) {
     if ((size_t)grid * pl->kp.inp_max * (NTc + 4) > pl->xbuf_floats) {
@@ -890,9 +883,15 @@ int gops_b200_mlp_forward(const gops_b200_mlp_desc* net, const float* params, co
   ENTRY("float virtual_t, const float* act_low, c");
   if (!net || !params || !obs || !out) return fail("null argument");
   if (batch <= 0) return fail("empty batch");
-  static thread_local gops_b200_plan* scratch = nullptr;   // reusable staging blob per host thread
-  static thread_local int scratch_floats = 0;
+  const int dev = device_of(params);
+  if (dev < 0 || dev >= kMaxDevices) return fail("device index out of range");
+  DevGuard dg(dev);
+  static thread_local gops_b200_plan* scratch_of[kMaxDevices] = {};   // reusable staging blob per host thread and device
+  static thread_local int scratch_floats_of[kMaxDevices] = {};
+  gops_b200_plan*& scratch = scratch_of[dev];
+  int& scratch_floats = scratch_floats_of[dev];
   gops_b200_plan tmp;
+  tmp.device = dev;
   KParams& kp = tmp.kp;
   memset(&kp, 0, sizeof(kp));
   std::string why;
@@ -906,8 +905,6 @@ int gops_b200_mlp_forward(const gops_b200_mlp_desc* net, const float* params, co
     kp.pol_mid[j] = act_low ? (act_high[j] + act_low[j]) / 2.f : 0.f;
   }
   cudaDeviceProp prop;
-  int dev = 0;
-  CUDA_OK(cudaGetDevice(&dev));
   CUDA_OK(cudaGetDeviceProperties(&prop, dev));
   tmp.sm_count = prop.multiProcessorCount;
   tmp.max_smem = (int)prop.sharedMemPerBlockOptin;
@@ -939,6 +936,7 @@ int gops_b200_model_step(gops_b200_plan* pl, const gops_b200_batch* b, const flo
   ENTRY("float* next_ref_time, void* stream) {");
   if (!pl || !b || !action || !next_obs || !reward || !next_done) return fail("null argument");
   if (b->batch <= 0 || !b->obs || !b->done) return fail("bad batch");
+  DevGuard dg(pl->device);
   KParams& kp = pl->kp;
   kp.batch = b->batch; kp.obs = b->obs; kp.done = b->done;
   const unsigned grid = (unsigned)((b->batch + 127) / 128);
@@ -957,12 +955,14 @@ int gops_b200_model_step(gops_b200_plan* pl, const gops_b200_batch* b, const flo
                                                         next_ref_points, next_ref_time);
     else veh_step_kernel<2><<<grid, 128, 0, st>>>(kp, action, next_obs, reward, next_done, next_state,
                                                   next_ref_points, next_ref_time);
+    ++g_launches;
     CUDA_OK_L(cudaGetLastError(), "veh_step launch");
     return 0;
   }
   StepFn fn = step_fn(pl->desc.model);
   if (!fn) return fail("model_step: env model kind not built into this library");
   fn<<<grid, 128, 0, st>>>(kp, action, act_dim, next_obs, reward, next_done);
+  ++g_launches;
   CUDA_OK_L(cudaGetLastError(), "launch#5");
   return 0;
 }
@@ -972,6 +972,7 @@ int gops_b200_adam_step(float* params, const float* grads, float* exp_avg, float
   ENTRY("int32_t step, double lr, double beta1, d");
   if (!params || !grads || !exp_avg || !exp_avg_sq) return fail("null argument");
   if (n <= 0 || step < 1) return fail("bad n/step");
+  DevGuard dg(device_of(params));
   // python-side scalars of torch/optim/adam.py are doubles; only the tensor math is fp32
   const double bc1 = 1.0 - pow(beta1, (double)step);
   const double bc2 = 1.0 - pow(beta2, (double)step);
@@ -980,6 +981,7 @@ int gops_b200_adam_step(float* params, const float* grads, float* exp_avg, float
   adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       params, grads, exp_avg, exp_avg_sq, n, (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2), (float)eps,
       step_size, bc2_sqrt);
+  ++g_launches;
   CUDA_OK_L(cudaGetLastError(), "launch#6");
   return 0;
 }
@@ -987,7 +989,9 @@ int gops_b200_adam_step(float* params, const float* grads, float* exp_avg, float
 int gops_b200_polyak(float* target, const float* src, float tau, int64_t n, void* stream) {
   ENTRY("int gops_b200_polyak(float* target, cons");
   if (!target || !src || n <= 0) return fail("bad argument");
+  DevGuard dg(device_of(target));
   polyak_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(target, src, tau, n);
+  ++g_launches;
   CUDA_OK_L(cudaGetLastError(), "launch#7");
   return 0;
 }

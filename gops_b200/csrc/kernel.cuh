@@ -1,7 +1,6 @@
 // The fused rollout kernel template: forward sweep, terminal value, reverse sweep, gradient partials.
 #pragma once
 #include "models.cuh"
-#include "mlp_tc_fwd.cuh"
 #include "mlp_tc_full.cuh"
 
 namespace gops {
@@ -12,20 +11,16 @@ namespace gops {
 // HD = 256 (WG): they do not fit (519 KB of weights) -> weights are read from the packed blob in global memory
 // (L2 resident, generic loads), gradients accumulate directly in this CTA's global partial, X is a per-CTA global
 // scratch; only the activation tiles stay in shared memory.
-// HY (hybrid, HD = 64 / S = 128 / NT = 512, policy inputs <= 16): the forward sweep's policy MLP runs on the tcgen05
-// tensor cores with a TMEM accumulator (mlp_tc_fwd.cuh); its operand planes alias the activation tiles, the policy
-// blob is re-staged per chunk in the layout of the sweep that is about to run (chunk-major planes / mma.sync planes).
 // TC (full tcgen05, HD = 64 / S = 128 / NT = 512, inputs <= 16): every dense product incl. the weight gradients runs
 // on the tensor cores in BF16x3 (mlp_tc_full.cuh); shared memory holds the operand planes instead of activation tiles,
 // the W1 / b1 / W2 / b2 gradient accumulators live in TMEM for the whole kernel.
-template <class M, int HD, int S, int NT, int ALG, bool HY = false, bool TC = false>
+template <class M, int HD, int S, int NT, int ALG, bool TC = false>
 __global__ void __launch_bounds__(NT, 1) rollout_kernel(const __grid_constant__ KParams p) {
   constexpr int SP = S + 4, XS = NT + 4, NS = M::NS, HID = HD;
   constexpr int alg = ALG;
   constexpr bool WG = HD > 64;
-  constexpr int HDR = HY ? 16 : 4;     // header floats: weight mbarrier (+ MMA mbarrier, TMEM slot)
-  static_assert(!HY || (HD == 64 && S == 128 && NT == 512), "hybrid tcgen05 forward: 64-wide nets, S = 128, NT = 512");
-  static_assert(!TC || (!HY && HD == 64 && S == 128 && NT == 512), "full tcgen05 path: 64-wide nets, S = 128, NT = 512");
+  constexpr int HDR = 4;               // header floats: weight mbarrier
+  static_assert(!TC || (HD == 64 && S == 128 && NT == 512), "full tcgen05 path: 64-wide nets, S = 128, NT = 512");
   extern __shared__ __align__(16) float smem[];
   uint64_t* mbar = reinterpret_cast<uint64_t*>(smem);
   float* part = p.partial + (size_t)blockIdx.x * p.part_stride;
@@ -69,16 +64,6 @@ __global__ void __launch_bounds__(NT, 1) rollout_kernel(const __grid_constant__ 
     t.R = t.Z + 8 * XS;         // wide nets only: staging region
   }
 
-  TcCtx cx;                     // hybrid: tcgen05 operand planes inside the (forward-sweep-dead) activation tiles
-  cx.W = t.W;
-  cx.Xp = t.H1;
-  cx.P = cx.Xp + 2 * TC_XPLANE;
-  cx.Zp = cx.P + 2 * TC_PLANE;
-  cx.bar = mbar + 1;
-  cx.ph = 0u;
-  cx.tmem = 0u;
-  static_assert(!HY || 2 * TC_XPLANE + 2 * TC_PLANE + 4 * MAXA * 128 <= 4 * HD * (S + 4), "tcgen05 planes must fit in the tiles");
-
   const int tid = threadIdx.x;
   // column (= sample slot of the chunk) owned by this thread.  Tensor-core path: the 64 threads of warp pair p own
   // exactly the 16-sample stripes {sub * S + 16 p .. + 15} that the pair's MLP GEMMs produce, so the pair never has
@@ -113,20 +98,11 @@ __global__ void __launch_bounds__(NT, 1) rollout_kernel(const __grid_constant__ 
 
   if (tid == 0) {
     mbar_init(mbar, 1);
-    if (HY) mbar_init(cx.bar, 1);
     fence_mbar_init();
   }
   for (int i = tid; i < p.dw_floats; i += NT) t.dW[i] = 0.f;
   for (int i = tid; i < p.inp_max * XS; i += NT) t.X[i] = 0.f;   // pad rows of the observation tile stay zero
   for (int i = tid; i < 8 * XS; i += NT) t.Z[i] = 0.f;
-  if constexpr (HY) {
-    uint32_t* tslot = reinterpret_cast<uint32_t*>(smem + 4);
-    if (tid < 32) umma::tmem_alloc(tslot, TC_FWD_COLS);
-    umma::fence_before_sync();
-    __syncthreads();
-    umma::fence_after_sync();
-    cx.tmem = *tslot;
-  }
   if constexpr (TC) {
     uint32_t* tslot = reinterpret_cast<uint32_t*>(smem + 8);
     if (tid == 0) {
@@ -183,7 +159,7 @@ __global__ void __launch_bounds__(NT, 1) rollout_kernel(const __grid_constant__ 
     return ts;
   };
 
-  if (!HY) stage(p.blob_pol, P.blob);
+  stage(p.blob_pol, P.blob);
 
   float* tape = p.tape + (size_t)blockIdx.x * (size_t)H * TCH * NT;
   float loss_acc = 0.f, vmean_acc = 0.f, done_acc = 0.f;
@@ -193,8 +169,7 @@ __global__ void __launch_bounds__(NT, 1) rollout_kernel(const __grid_constant__ 
   for (long long pos = r0; pos < r1; pos += NT) {
     const int nv = (int)((r1 - pos) < NT ? (r1 - pos) : NT);
     const int nsub = (nv + S - 1) / S;
-    if (HY) stage(p.blob_pol_tc, p.pol_tc.blob);   // forward sweep reads the chunk-major planes (leading barrier inside)
-    else __syncthreads();
+    __syncthreads();
     load_obs_chunk(pos, nv, nsub * S);
     __syncthreads();
     float st[NS];
@@ -240,18 +215,16 @@ __global__ void __launch_bounds__(NT, 1) rollout_kernel(const __grid_constant__ 
         tape[(k * TCH + NS) * NT + tid] = dn ? 1.f : 0.f;
       }
       if (P.time_input) t.X[(P.in - 1) * XS + col] = (float)(k + 1);
-      if (HY) __syncthreads();     // the tcgen05 forward gathers X columns written by other warp pairs
-      else scope_sync();
+      scope_sync();
       for (int sub = 0; sub < nsub; ++sub) {
         const Tiles ts = sub_tiles(sub);
-        if constexpr (HY) mlp_forward_tc<NT>(p.pol_tc, cx, ts.X, XS, p.inp_max, ts.Z);
-        else MLP_FWD(false, true, P, ts, ts.Z);
+        MLP_FWD(false, true, P, ts, ts.Z);
       }
       {
         float z[MAXA], a[MAXA], g[MAXA], apol[MAXA];
 #pragma unroll
         for (int j = 0; j < MAXA; ++j)   // mma.sync path: two half-stripe partials; tcgen05 path: complete sums in row j
-          z[j] = j < P.out ? ((HY || TC) ? t.Z[j * XS + col] : t.Z[j * XS + col] + t.Z[(4 + j) * XS + col]) : 0.f;
+          z[j] = j < P.out ? (TC ? t.Z[j * XS + col] : t.Z[j * XS + col] + t.Z[(4 + j) * XS + col]) : 0.f;
         if (alg == ALG_FHADP || alg == ALG_PIM) {
 #pragma unroll
           for (int j = 0; j < MAXA; ++j)
@@ -419,7 +392,7 @@ __global__ void __launch_bounds__(NT, 1) rollout_kernel(const __grid_constant__ 
     }
 
     if (valid) loss_acc += -vacc * p.inv_B;
-    if (alg == ALG_PIM || HY) stage(p.blob_pol, P.blob);   // reverse sweep: mma.sync planes of the policy
+    if (alg == ALG_PIM) stage(p.blob_pol, P.blob);
 
     // ================================ reverse sweep ================================
     for (int k = H - 1; k >= 0; --k) {
@@ -600,11 +573,6 @@ __global__ void __launch_bounds__(NT, 1) rollout_kernel(const __grid_constant__ 
     float s = 0.f;
     for (int i = 0; i < NT; ++i) s += red[tid * NT + i];
     part[nparam + tid] = s;
-  }
-  if constexpr (HY) {
-    umma::fence_before_sync();
-    __syncthreads();
-    if (tid < 32) umma::tmem_dealloc(cx.tmem, TC_FWD_COLS);
   }
   if constexpr (TC) {
     umma::fence_before_sync();

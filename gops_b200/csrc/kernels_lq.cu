@@ -24,20 +24,12 @@ RolloutFn rollout_fn_lq(int hid, int cfg, int alg) {
     default: return pick<ALG_TRACE>(hid, cfg);
   }
 }
-RolloutFn rollout_fn_hy_lq(int alg) {   // tcgen05 forward sweep + mma.sync reverse sweep
+RolloutFn rollout_fn_tc_lq(int alg) {   // full tcgen05 / TMEM path (BF16x3)
   switch (alg) {
     case ALG_FHADP: return rollout_kernel<ModelLq, 64, 128, 512, ALG_FHADP, true>;
     case ALG_PIM: return rollout_kernel<ModelLq, 64, 128, 512, ALG_PIM, true>;
     case ALG_PEV: return rollout_kernel<ModelLq, 64, 128, 512, ALG_PEV, true>;
     default: return rollout_kernel<ModelLq, 64, 128, 512, ALG_TRACE, true>;
-  }
-}
-RolloutFn rollout_fn_tc_lq(int alg) {   // full tcgen05 / TMEM path (BF16x3)
-  switch (alg) {
-    case ALG_FHADP: return rollout_kernel<ModelLq, 64, 128, 512, ALG_FHADP, false, true>;
-    case ALG_PIM: return rollout_kernel<ModelLq, 64, 128, 512, ALG_PIM, false, true>;
-    case ALG_PEV: return rollout_kernel<ModelLq, 64, 128, 512, ALG_PEV, false, true>;
-    default: return rollout_kernel<ModelLq, 64, 128, 512, ALG_TRACE, false, true>;
   }
 }
 StepFn step_fn_lq() { return model_step_kernel<ModelLq>; }

@@ -57,8 +57,6 @@ struct KParams {
   float gamma, inv_B;
   const float* gpow;       // fp32(gamma^k), k = 0..H (host-computed in double like python's gamma ** k)
   NetL pol, val;
-  NetL pol_tc;             // hybrid kernel: policy with the chunk-major blob offsets of the tcgen05 forward
-  const float* blob_pol_tc;
   const float* blob_pol;
   const float* blob_val;   // v        (INFADP_VALUE)
   const float* blob_vtg;   // v_target (INFADP_*)

@@ -65,7 +65,11 @@ def _dummy_mlp(obs_dim, act_dim):
 
 
 class _StepPlan:
-    def __init__(self, top):
+    def __init__(self, top, device):
+        with torch.cuda.device(device):
+            self._create(top)
+
+    def _create(self, top):
         base = top.unwrapped
         desc = _lib.PlanDesc()
         desc.alg, desc.horizon, desc.gamma = _lib.ALG_FHADP, 1, 1.0
@@ -99,9 +103,10 @@ def fused_forward(top, obs, action, done, info):
         raise RuntimeError("gops_b200 env models run on a CUDA device only (no CPU fallback)")
     src = obs.device
     dev = obs.device if obs.is_cuda else torch.device("cuda", torch.cuda.current_device())
-    plan = top.__dict__.get("_step_plan")
+    plans = top.__dict__.setdefault("_step_plans", {})     # one per device
+    plan = plans.get(dev.index)
     if plan is None:
-        plan = top.__dict__["_step_plan"] = _StepPlan(top)
+        plan = plans[dev.index] = _StepPlan(top, dev)
     base = top.unwrapped
     keep = []
     obs_d = obs.detach().to(dev, torch.float32)

@@ -112,9 +112,10 @@ class FusedAdam(torch.optim.Optimizer):
             self._v = torch.zeros_like(flat)
         self._step += 1
         g = self.param_groups[0]
-        _lib.check(_lib.lib().gops_b200_adam_step(
-            _lib.ptr(flat), _lib.ptr(fp.gbuf), _lib.ptr(self._m), _lib.ptr(self._v), flat.numel(), self._step,
-            float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]), _lib.stream_ptr()))
+        with torch.cuda.device(flat.device):      # launch on the parameters' device and its current stream
+            _lib.check(_lib.lib().gops_b200_adam_step(
+                _lib.ptr(flat), _lib.ptr(fp.gbuf), _lib.ptr(self._m), _lib.ptr(self._v), flat.numel(), self._step,
+                float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]), _lib.stream_ptr()))
 
 
 @torch.no_grad()
@@ -122,4 +123,5 @@ def polyak_update(target: FlatParams, src: FlatParams, tau: float):
     t, s = target.sync(), src.sync()
     if not t.is_cuda:
         raise RuntimeError("gops_b200.polyak_update: parameters must live on a CUDA device (no CPU fallback)")
-    _lib.check(_lib.lib().gops_b200_polyak(_lib.ptr(t), _lib.ptr(s), float(tau), t.numel(), _lib.stream_ptr()))
+    with torch.cuda.device(t.device):
+        _lib.check(_lib.lib().gops_b200_polyak(_lib.ptr(t), _lib.ptr(s), float(tau), t.numel(), _lib.stream_ptr()))

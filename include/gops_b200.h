@@ -54,7 +54,7 @@ enum {
 typedef struct gops_b200_mlp_desc {
   int32_t in_dim;      /* observation features (without the time column)                          */
   int32_t time_input;  /* 1 = FiniteHorizonPolicy: a column virtual_t is appended (mlp.py:103-111) */
-  int32_t hidden;      /* hidden width (64 / 128 / 256)                                            */
+  int32_t hidden;      /* hidden width: 64 or 256 (two equal hidden layers)                           */
   int32_t out_dim;     /* act_dim for policies, 1 for StateValue                                   */
   int32_t hidden_act;  /* GOPS_ACT_*                                                               */
   int32_t out_act;     /* GOPS_ACT_* (reference default "linear")                                  */
@@ -126,6 +126,9 @@ typedef struct gops_b200_plan gops_b200_plan;
 
 int gops_b200_version(void);
 const char* gops_b200_last_error(void);
+/* Number of CUDA kernels this library has launched in this process so far (all plans, all devices): bench.py reports
+ * the difference over its timed region as `gpu_launches`. */
+int64_t gops_b200_launch_count(void);
 
 /* Plan = compiled shape/constant bundle + device scratch (weight staging blob, rollout tape,
  * per-CTA gradient partials). */
@@ -140,6 +143,15 @@ int gops_b200_plan_set_gamma(gops_b200_plan* plan, double gamma);
 int gops_b200_plan_enable_timing(gops_b200_plan* plan, int enable);
 int gops_b200_plan_last_kernel_ms(gops_b200_plan* plan, float* ms);
 int gops_b200_plan_launch_info(const gops_b200_plan* plan, int32_t* out4);
+/* Kernel path of the fused rollout.  AUTO (default) picks per launch: tcgen05 / TMEM (BF16x3) where the nets are
+ * 64-wide with <= 16 inputs, the mma.sync (3xTF32) / FFMA kernels elsewhere.  A plan option instead of an environment
+ * switch so that a test can state AND assert which kernel ran (the env var GOPS_B200_ROLLOUT=tc|mma still overrides
+ * for A/B runs from the shell).  last_path: path of the most recent rollout launch of this plan (GOPS_PATH_*). */
+#define GOPS_PATH_AUTO 0
+#define GOPS_PATH_MMA 1
+#define GOPS_PATH_TC 2
+int gops_b200_plan_set_path(gops_b200_plan* plan, int path);
+int gops_b200_plan_last_path(const gops_b200_plan* plan);
 /* number of float32 parameters of the policy (which=0) / value (which=1) network */
 int64_t gops_b200_plan_param_count(const gops_b200_plan* plan, int which);
 

@@ -120,9 +120,70 @@ def run_case(name, kw, data, iterations, trace_n=0, set_params=None, load_ckpt=N
     print(name, {k: float(v) for k, v in rec.items() if "/tb/" in k})
 
 
+def run_trajectory(name, kw, batches, n_updates, remote_every=0):
+    """K consecutive updates on a rotating set of fixed batches (incl. LR scheduler steps, base.py:94-98): stores the
+    loss of every update and the weights after updates 1, K/2 and K.  `remote_every` = m > 0 routes every m-th update
+    through get_remote_update_info + remote_update (base.py:100-104, fhadp.py:92-102), the Ray-replica entry points."""
+    from gops.create_pkg.create_alg import create_alg
+
+    torch.manual_seed(4321)
+    alg = create_alg(**kw)
+    env_id = kw["env_id"]
+    rec = {}
+    for j, data in enumerate(batches):
+        for k, v in flat_inputs(env_id, data).items():
+            rec[f"b{j}/{k}"] = v
+    for k, v in _sd(alg).items():
+        rec["init/" + k] = v
+    losses, lrs = [], []
+    keep = {1, n_updates // 2, n_updates}
+    for it in range(n_updates):
+        data = to_ref_data(env_id, batches[it % len(batches)])
+        if remote_every and it % remote_every == remote_every - 1:
+            tb, upd = alg.get_remote_update_info(data, it)
+            alg.remote_update(upd)
+        else:
+            tb = alg.local_update(data, it)
+        key = "Loss/Critic loss-RL iter" if (kw["algorithm"] == "INFADP" and it % 2 == 0) else "Loss/Actor loss-RL iter"
+        losses.append(tb[key])
+        lrs.append(alg.networks.policy_optimizer.param_groups[0]["lr"])
+        if it + 1 in keep:
+            for k, v in _sd(alg).items():
+                rec[f"after{it + 1}/{k}"] = v
+    rec["losses"], rec["lrs"] = np.asarray(losses, np.float64), np.asarray(lrs, np.float64)
+    # trained-policy actions: what the evaluator would see after the K updates
+    with torch.no_grad():
+        o = batches[0]["obs"][:64]
+        rec["final_actions"] = _np(alg.networks.policy(o, 1) if kw["policy_func_name"] == "FiniteHorizonPolicy"
+                                   else alg.networks.policy(o))
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **rec)
+    print(name, "losses", losses[0], losses[-1], "lr", lrs[0], lrs[-1])
+
+
 def main():
     ref_shim.install()
     torch.set_num_threads(4)
+
+    # K = 20 consecutive updates, LinearLR scheduler, every 5th through the remote-update entry points
+    kw = base_kwargs("pyth_idpendulum", "FHADP", 6, 1, (64, 64), "gelu", "FiniteHorizonPolicy", pre_horizon=30,
+                     reward_scale=1.0, policy_learning_rate=3e-4,
+                     policy_scheduler={"name": "LinearLR", "params": {"start_factor": 1.0, "end_factor": 0.25,
+                                                                      "total_iters": 16}})
+    run_trajectory("traj_fhadp_idp_k20", kw, [orc.sample_inputs("pyth_idpendulum", 512, 40 + j) for j in range(3)], 20,
+                   remote_every=5)
+    kw = base_kwargs("pyth_lq", "INFADP", 4, 2, (64, 64), "gelu", "DetermPolicy", lq_config="s4a2",
+                     reward_scale=1.0, reward_shift=0.0, policy_learning_rate=8e-4, value_learning_rate=3e-4)
+    run_trajectory("traj_infadp_lq_k20", kw, [orc.sample_inputs("pyth_lq", 256, 50 + j, lq_config="s4a2")
+                                              for j in range(2)], 20)
+    # long horizon with every sample alive to the end (MaskAtDone off): the h80 case above is degenerate, every sample
+    # of an untrained policy terminates by step ~24 and the tail of the tape / reverse sweep is masked out
+    kw = base_kwargs("pyth_idpendulum", "FHADP", 6, 1, (64, 64), "gelu", "FiniteHorizonPolicy",
+                     pre_horizon=80, reward_scale=1.0, policy_learning_rate=1e-4, mask_at_done=False)
+    d = orc.sample_inputs("pyth_idpendulum", 128, 22)
+    d["obs"] = d["obs"] * torch.tensor([1.0, 0.2, 0.2, 0.2, 0.2, 0.2])     # near upright: finite 80-step rollouts
+    run_case("fhadp_idp_h80_nomask", kw, d, [0])
+    if "--only-new" in sys.argv:
+        return
 
     # C1: FHADP idpendulum, FiniteHorizonPolicy [64,64] gelu (fhadp_mlp_idpendulum_serial.py:34-75)
     for H in (30, 80):

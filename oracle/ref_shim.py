@@ -16,7 +16,14 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("GOPS_REFERENCE_ROOT", "/root/reference")
+def _default_root():
+    """/root/reference in the build container; the travelled copy oracle/_ref (oracle/build_ref.py) on the GPU box."""
+    if os.path.isdir("/root/reference/gops"):
+        return "/root/reference"
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+
+
+REFERENCE_ROOT = os.environ.get("GOPS_REFERENCE_ROOT") or _default_root()
 
 _STUBBED = (
     "gym", "gymnasium", "ray", "matplotlib", "seaborn", "pygame", "Box2D", "slxpy",

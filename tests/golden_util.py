@@ -21,6 +21,8 @@ _SH46 = (0.2 * torch.rand(46, generator=torch.Generator().manual_seed(8)) - 0.1)
 CASES = {
     "fhadp_idp_h30": ("pyth_idpendulum", "FHADP", "gelu", {}, dict(reward_scale=1.0), dict(pre_horizon=30)),
     "fhadp_idp_h80": ("pyth_idpendulum", "FHADP", "gelu", {}, dict(reward_scale=1.0), dict(pre_horizon=80)),
+    "fhadp_idp_h80_nomask": ("pyth_idpendulum", "FHADP", "gelu", {}, dict(reward_scale=1.0, mask_at_done=False),
+                             dict(pre_horizon=80)),
     "fhadp_idp_trained_h80": ("pyth_idpendulum", "FHADP", "gelu", {}, dict(reward_scale=1.0), dict(pre_horizon=80)),
     "fhadp_idp_relu_done": ("pyth_idpendulum", "FHADP", "relu", {}, dict(reward_scale=0.5, reward_shift=1.0),
                             dict(pre_horizon=12, gamma=0.97)),
@@ -44,7 +46,7 @@ CASES = {
     "infadp_veh3dofconti_obsscale": ("pyth_veh3dofconti", "INFADP", "relu", dict(pre_horizon=10),
                                      dict(obs_scale=_SC46, obs_shift=_SH46), {}),
 }
-DEFAULT_LR = {"fhadp_idp_h30": 1e-4, "fhadp_idp_h80": 1e-4, "fhadp_idp_trained_h80": 1e-4}
+DEFAULT_LR = {"fhadp_idp_h30": 1e-4, "fhadp_idp_h80": 1e-4, "fhadp_idp_trained_h80": 1e-4, "fhadp_idp_h80_nomask": 1e-4}
 
 
 def load(name):
@@ -122,3 +124,37 @@ def rel_l2(a, b):
     a = np.concatenate([np.asarray(x, dtype=np.float64).ravel() for x in a])
     b = np.concatenate([np.asarray(x, dtype=np.float64).ravel() for x in b])
     return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+
+def slice_data(data, lo, hi):
+    """Rows [lo, hi) of an oracle input dict (veh3dof_tracking carries (robot_state, reference, t) under 'state')."""
+    out = {}
+    for k, v in data.items():
+        if isinstance(v, tuple):
+            out[k] = (v[0][lo:hi], v[1][lo:hi], v[2])
+        elif torch.is_tensor(v) and v.dim() > 0:
+            out[k] = v[lo:hi]
+        else:
+            out[k] = v
+    return out
+
+
+def oracle_chunked(loss_of_chunk, data, params, chunk=32768):
+    """Batch-mean loss and gradient of the CPU oracle evaluated in chunks (the loss is a mean over independent samples,
+    so it is the size-weighted sum of chunk means): keeps autograd memory bounded at BASELINE batch sizes.
+    `loss_of_chunk(d)` returns the chunk-mean loss tensor or a tuple (loss, *extras); extras are size-weighted too."""
+    B = data["obs"].shape[0]
+    for p in params:
+        p.grad = None
+    total, extras = 0.0, None
+    for lo in range(0, B, chunk):
+        hi = min(B, lo + chunk)
+        out = loss_of_chunk(slice_data(data, lo, hi))
+        loss = out[0] if isinstance(out, tuple) else out
+        w = (hi - lo) / B
+        (loss * w).backward()
+        total += float(loss) * w
+        if isinstance(out, tuple):
+            ex = [float(e) * w for e in out[1:]]
+            extras = ex if extras is None else [a + b for a, b in zip(extras, ex)]
+    return total, [p.grad.detach().clone() for p in params], extras

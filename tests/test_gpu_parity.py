@@ -122,6 +122,12 @@ def test_golden_loss_grad_update(name):
             delta = np.abs(new_w - ref_w)
             assert delta.max() <= 2.1 * lr, (name, pk, delta.max())
             assert np.mean(delta <= 2e-2 * lr + 1e-7) > 0.98, (name, pk)
+            # the first Adam step moves a weight by lr * g / (|g| + eps) = lr * sign(g): a sign flip is admissible ONLY
+            # where the reference gradient itself is zero within the parity noise of the gradient
+            g_ref = rec[k]
+            noise = GRAD_RTOL_BY_ENV.get(env_id, GRAD_RTOL) * np.linalg.norm(g_ref) / np.sqrt(g_ref.size)
+            solid = np.abs(g_ref) > 20.0 * noise + 1e-7
+            assert (delta[solid] <= 2e-2 * lr + 1e-7).all(), (name, pk, float(delta[solid].max()))
             if algname == "INFADP":
                 tk = pk.replace(net + ".", net + "_target.", 1)
                 np.testing.assert_allclose(sd[tk].detach().cpu().numpy(), rec[f"it{it}/post/{tk}"], rtol=0,
@@ -353,9 +359,8 @@ def test_unsupported_configurations_raise():
         create_alg(**kw)
     kw, rec = make_kwargs("fhadp_idp_h30")
     kw["policy_hidden_sizes"] = [128, 128]
-    alg = create_alg(**kw)
-    with pytest.raises(RuntimeError, match="not built"):
-        alg.local_update(data_from(rec, "pyth_idpendulum"), 0)
+    with pytest.raises(NotImplementedError, match="64 and 256"):      # at construction, not at the first update
+        create_alg(**kw)
     kw, rec = make_kwargs("fhadp_veh3dofconti_p12")
     kw["repeat_num"] = 2
     alg = create_alg(**kw)
