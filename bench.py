@@ -4,24 +4,34 @@
   python bench.py --gpus N --steps K --warmup W            (N>1: launched under torch.distributed.run)
   python bench.py --impl reference --gpus N --steps K --warmup W
 
-Workload (config.workload): FHADP on pyth_idpendulum, FiniteHorizonPolicy [64,64] gelu, horizon 30,
-batch 2^18 PER GPU (weak scaling), synthetic initial states from the data env's reset box.
-One step = one `alg.local_update(data, it)` through the plugin API: weight packing, fused rollout
-forward+backward, partial reduction, (NCCL all-reduce of the flat gradient when N>1), fused Adam, and
-the host read of the loss scalar.
+Workload (config.workload): FHADP on pyth_idpendulum, FiniteHorizonPolicy [64,64] gelu, horizon 30, synthetic initial
+states from the data env's reset box.  N = 1: batch 2^18 on the GPU (the configuration BASELINE.json quotes).
+N > 1: STRONG scaling by default -- the north-star configuration itself, GLOBAL batch 2^18 sharded over the N GPUs
+(2^18 / N samples each) with one NCCL all-reduce of the flat gradient per update; the weak-scaling figure (2^18 per
+GPU) is measured in the same run and reported in the `weak` sub-object (`--scaling weak` swaps the two).
+One step = one `alg.local_update(data, it)` through the plugin API: weight packing, fused rollout forward+backward,
+partial reduction, (all-reduce), fused Adam, and the host read of the loss scalar.
 
-value : inputs resident in HBM when the timed region starts (a rotating set of input batches whose total
-        size exceeds L2, so no step finds its inputs in L2);
-e2e   : same call with PINNED HOST tensors -- H2D copy of the batch and D2H read of the loss inside the
-        timed region;
+value : inputs resident in HBM when the timed region starts (a rotating set of input batches whose total size exceeds
+        L2, so no step finds its inputs in L2);
+e2e   : same call with PINNED HOST tensors -- H2D copy of the batch and D2H read of the loss inside the timed region.
+        Loss read-back mode (config.loss_readback): every step copies its 4-float result tail to pinned host memory and
+        the host reads it; "pipelined" = the host reads step i-1's loss while step i runs (alg.loss_lag = 1; the last
+        loss is read before the closing synchronize), "synchronous" = it waits for step i's own loss (reference
+        semantics; reported beside it as `sync_loss`).
 roofline : the fused rollout kernel alone, timed with CUDA events on its launch stream inside the library
-        (gops_b200_plan_enable_timing).  The kernel is compute bound by design: `achieved` is
-        algorithmic TFLOP/s, `peak` the tensor roof for FP32-accurate (BF16x3 / 3xTF32) GEMMs derived from the measured bf16
-        peak; the FP32-FFMA, HBM and raw bf16 fractions are reported beside it.
-cpu_baseline : the CPU oracle port (oracle/gops_oracle.py, the reference's algorithm in PyTorch-CPU) on a
-        bounded sample of the same workload, all host threads.
+        (gops_b200_plan_enable_timing).  Compute bound by design: `achieved` = algorithmic TFLOP/s,
+        `peak` = tensor roof for FP32-accurate (BF16x3) GEMMs = measured BURST bf16 peak / 6 (the kernel is timed alone);
+        FP32-FFMA, HBM, raw-bf16 and sustained-peak fractions beside it.
+cpu_baseline : the UNMODIFIED reference's `alg.local_update` (oracle/_ref, kind "reference") on the host cores, on a
+        bounded sample of the same workload -- or the oracle port (kind "port") if the reference tree is absent.
+gpu_eager_baseline : the unmodified reference with use_gpu=True on the same B200 (PyTorch eager; SURVEY 8(d)'s
+        "existing Blackwell path").
+configs : the other BASELINE.json configurations, each one timed update (device-resident inputs, L2 flushed between
+        iterations) with its own kernel path and roofline line.
 """
 import argparse
+import ctypes as C
 import json
 import math
 import os
@@ -39,16 +49,21 @@ MAC = (OBS_DIM + 1) * HID + HID * HID + HID * ACT_DIM          # 4608
 FLOP_PER_ENV_STEP = 6 * MAC + 1500                             # MLP fwd+bwd + dynamics
 BYTES_PER_ENV_STEP = (OBS_DIM * 4 + 4) / H                     # obs + done read once per sample
 L2_BYTES = 126 * 1024 * 1024
+GLOBAL_BATCH = 1 << 18
 
 
-def alg_kwargs():
+def alg_kwargs(env_id="pyth_idpendulum", algorithm="FHADP", hid=HID, act="gelu", obs_dim=OBS_DIM, act_dim=ACT_DIM, **kw):
     import numpy as np
-    return dict(env_id="pyth_idpendulum", algorithm="FHADP", pre_horizon=H, seed=0, trainer="off_serial_trainer",
-                use_gpu=True, action_type="continu", obsv_dim=OBS_DIM, action_dim=ACT_DIM,
-                action_high_limit=np.ones(ACT_DIM, dtype=np.float32), action_low_limit=-np.ones(ACT_DIM, dtype=np.float32),
-                policy_func_name="FiniteHorizonPolicy", policy_func_type="MLP", policy_hidden_sizes=[HID, HID],
-                policy_hidden_activation="gelu", policy_act_distribution="default", policy_learning_rate=1e-4,
-                value_func_type="MLP", reward_scale=1.0)
+    base = dict(env_id=env_id, algorithm=algorithm, seed=0, trainer="off_serial_trainer",
+                use_gpu=True, action_type="continu", obsv_dim=obs_dim, action_dim=act_dim,
+                action_high_limit=np.ones(act_dim, dtype=np.float32), action_low_limit=-np.ones(act_dim, dtype=np.float32),
+                policy_func_name="FiniteHorizonPolicy" if algorithm.startswith("FHADP") else "DetermPolicy",
+                policy_func_type="MLP", policy_hidden_sizes=[hid, hid],
+                policy_hidden_activation=act, policy_act_distribution="default", policy_learning_rate=1e-4,
+                value_func_name="StateValue", value_func_type="MLP", value_hidden_sizes=[hid, hid],
+                value_hidden_activation=act, value_learning_rate=1e-3)
+    base.update(kw)
+    return base
 
 
 class ClockSampler:
@@ -113,7 +128,10 @@ def idp_init_batch(batch, seed):
     return {"obs": (torch.rand(batch, 6, generator=g, dtype=torch.float32) * 2 - 1) * h, "done": torch.zeros(batch)}
 
 
-def cpu_update_rate(batch, steps, warmup, threads):
+# ----------------------------------------------------------------------------------------------------------------
+# CPU legs (the only places that import oracle/)
+# ----------------------------------------------------------------------------------------------------------------
+def port_update_rate(batch, steps, warmup, threads):
     """env-steps/s of the CPU oracle port: loss + autograd backward + Adam, as FHADP.local_update."""
     import torch
     torch.set_num_threads(threads)
@@ -139,37 +157,208 @@ def cpu_update_rate(batch, steps, warmup, threads):
     return batch * H * len(times) / total, total / len(times)
 
 
-def best_cpu_threads(batch):
-    """The reference's tiny-op eager path does not scale to many threads; give it the better of (all usable cores)
-    and (16 threads) so the baseline is not handicapped by oversubscription."""
-    cands = sorted({usable_cores(), min(usable_cores(), 16)})
-    if len(cands) == 1:
-        return cands[0]
-    rates = {c: cpu_update_rate(batch, 1, 1, c)[0] for c in cands}
-    return max(rates, key=rates.get)
+def cpu_reference_leg(batch, steps, warmup):
+    """The reference's own CPU implementation on the host cores: at all usable cores (the headline `value`) and at
+    the reference's own default of 4 torch threads for `*serial*` trainers (init_args.py:29-35)."""
+    cores = usable_cores()
+    try:
+        from oracle import ref_runner
+        have_ref = ref_runner.available()
+    except Exception:
+        have_ref = False
+    if have_ref:
+        rate, sec = ref_runner.time_reference_updates(batch, steps, warmup, threads=cores, H=H)
+        rate4, _ = ref_runner.time_reference_updates(batch, min(steps, 2), 1, threads=min(4, cores), H=H)
+        kind, what = "reference", "unmodified gops FHADP.local_update (oracle/_ref via oracle/ref_shim.py)"
+    else:
+        rate, sec = port_update_rate(batch, steps, warmup, cores)
+        rate4, _ = port_update_rate(batch, min(steps, 2), 1, min(4, cores))
+        kind, what = "port", "oracle/gops_oracle.py (reference tree not reachable)"
+    return {"value": rate, "unit": "env-steps/s", "cores": cores, "kind": kind, "sec_per_update": sec,
+            "sample": f"B={batch}, H={H}, {steps} updates after {warmup} warm-up: {what}",
+            "at_reference_default_threads": {"threads": min(4, cores), "value": rate4}}
 
 
-def run_reference(args, rank, world):
-    """Reference arm: the reference's own CPU algorithm (oracle port; the python reference cannot travel
-    to the GPU box) on the host cores, bounded sample per step."""
+def run_reference(args, rank):
+    """Reference arm: the reference's own CPU implementation of the path, bounded sample per step."""
     if rank != 0:
         return
-    sample_b = args.cpu_batch
-    threads = best_cpu_threads(sample_b)
-    rate, sec = cpu_update_rate(sample_b, args.steps, args.warmup, threads)
+    cpu = cpu_reference_leg(args.cpu_batch, args.steps, args.warmup)
     line = {
-        "impl": "reference", "metric": "batched env-steps/sec (FHADP rollout+update)", "value": rate,
+        "impl": "reference", "metric": "batched env-steps/sec (FHADP rollout+update)", "value": cpu["value"],
         "unit": "env-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
+        "ms_per_step": cpu["sec_per_update"] * 1e3, "higher_is_better": True, "scaling": args.scaling,
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"FHADP pyth_idpendulum H={H} FiniteHorizonPolicy[64,64] gelu",
-                   "sample": f"batch {sample_b} per step on CPU"},
-        "cpu_baseline": {"value": rate, "unit": "env-steps/s", "cores": threads, "kind": "port",
-                         "sample": f"B={sample_b}, H={H}, {args.steps} updates (oracle/gops_oracle.py)"},
-        "e2e": {"value": rate, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                   "sample": f"batch {args.cpu_batch} per step on the host CPU ({cpu['cores']} threads)"},
+        "cpu_baseline": cpu,
+        "e2e": {"value": cpu["value"], "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------------------------
+class Harness:
+    def __init__(self, rank, local_rank, world):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.rank, self.world = rank, world
+        self.dev = torch.device("cuda", local_rank)
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def timed(self, alg, sets, steps, plan=None):
+        """K steps between barrier+synchronize pairs; device time by CUDA events, max over ranks."""
+        from gops_b200 import _lib
+        torch = self.torch
+        kms = []
+        self.barrier()
+        n0 = _lib.lib().gops_b200_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            alg.local_update(sets[i % len(sets)], i)
+            if plan is not None:
+                ms = C.c_float()
+                _lib.check(_lib.lib().gops_b200_plan_last_kernel_ms(plan.handle, C.byref(ms)))
+                kms.append(ms.value)
+        e1.record()
+        self.barrier()
+        launches = _lib.lib().gops_b200_launch_count() - n0
+        ms = torch.tensor([e0.elapsed_time(e1)], device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(ms, op=self.dist.ReduceOp.MAX)
+        return float(ms.item()), kms, launches
+
+
+def measure_c1(hx, batch_per_gpu, K, W, want_kernel=True, want_e2e=True, want_sync=True):
+    """The C1 update on this rank's shard: returns dict(value-side timings, kernel ms, e2e timings, launches)."""
+    import torch
+    from gops_b200.create_pkg.create_alg import create_alg
+    from gops_b200 import _lib
+    torch.manual_seed(0)                       # identical replicas on every rank
+    alg = create_alg(**alg_kwargs(pre_horizon=H, reward_scale=1.0))
+    alg.loss_lag = 1
+    batch_bytes = batch_per_gpu * (OBS_DIM + 1) * 4
+    n_sets = max(2, math.ceil(1.5 * L2_BYTES / batch_bytes))
+    host_sets = [{k: v.pin_memory() for k, v in idp_init_batch(batch_per_gpu, seed=1000 * hx.rank + i).items()}
+                 for i in range(n_sets)]
+    dev_sets = [{k: v.to(hx.dev) for k, v in d.items()} for d in host_sets]
+    out = {"batch_bytes": batch_bytes, "n_sets": n_sets}
+    hx.timed(alg, dev_sets, W)                                    # warm-up (creates the plan)
+    plan = next(iter(alg._plans.values()))
+    if want_kernel:
+        _lib.check(_lib.lib().gops_b200_plan_enable_timing(plan.handle, 1))
+        hx.timed(alg, dev_sets, 1)
+        _, out["kernel_ms"], _ = hx.timed(alg, dev_sets, K, plan=plan)
+        _lib.check(_lib.lib().gops_b200_plan_enable_timing(plan.handle, 0))
+        hx.timed(alg, dev_sets, 2)
+    sampler = ClockSampler(hx.dev.index)
+    sampler.start()
+    out["ms_total"], _, out["launches"] = hx.timed(alg, dev_sets, K)
+    out["clocks"] = sampler.stop()
+    if want_sync:
+        alg.loss_lag = 0
+        hx.timed(alg, dev_sets, 2)
+        out["ms_total_sync"], _, _ = hx.timed(alg, dev_sets, K)
+        alg.loss_lag = 1
+    if want_e2e:
+        hx.timed(alg, host_sets, W)
+        out["ms_e2e"], _, _ = hx.timed(alg, host_sets, K)
+    info = (C.c_int32 * 4)()
+    _lib.check(_lib.lib().gops_b200_plan_launch_info(plan.handle, info))
+    out["launch"] = {"grid": info[0], "block": info[1], "tile_samples": info[2], "smem_bytes": info[3],
+                     "kernel_path": alg.last_kernel_path()}
+    return out
+
+
+PATH_TEXT = {"tc": "tcgen05: BF16x3 UMMA for every dense product, weight gradients accumulate in TMEM",
+             "mma": "mma.sync 3xTF32 (64-wide nets) / FP32 FFMA (256-wide nets)"}
+
+
+def secondary_configs(hx, peaks, K=10, W=3):
+    """The other BASELINE.json configurations on one GPU: one timed update each (device-resident inputs, L2 flushed by a
+    256 MiB memset between iterations, per-iteration CUDA events), kernel-only time, path, roofline."""
+    import numpy as np
+    import torch
+    from gops_b200.create_pkg.create_alg import create_alg
+    from gops_b200 import _lib
+    from gops_b200.trainer import device_sampler as ds
+    dev = hx.dev
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    burst = peaks.get("bf16_tflops", 1700.0)
+    n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
+    ffma_peak = n_sm * 128 * 2 * peaks.get("sm_max_mhz", 1965.0) * 1e6 / 1e12
+    rows = []
+
+    def run(name, kw, data, horizon, flop_pev, flop_pim, set_params=None):
+        torch.manual_seed(0)
+        alg = create_alg(**kw)
+        if set_params:
+            alg.set_parameters(set_params)
+        infadp = kw["algorithm"] == "INFADP"
+        B = data["obs"].shape[0]
+        for phase in ((0, 1) if infadp else (0,)):
+            it_of = (lambda i: 2 * i + phase) if infadp else (lambda i: i)
+            for i in range(W):
+                alg.local_update(data, it_of(i))
+            torch.cuda.synchronize()
+            plan = next(reversed(alg._plans.values()))
+            _lib.check(_lib.lib().gops_b200_plan_enable_timing(plan.handle, 1))
+            tot, kms = 0.0, []
+            for i in range(K):
+                flush.zero_()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                alg.local_update(data, it_of(i))
+                e1.record()
+                torch.cuda.synchronize()
+                tot += e0.elapsed_time(e1)
+                ms = C.c_float()
+                _lib.check(_lib.lib().gops_b200_plan_last_kernel_ms(plan.handle, C.byref(ms)))
+                kms.append(ms.value)
+            _lib.check(_lib.lib().gops_b200_plan_enable_timing(plan.handle, 0))
+            path = alg.last_kernel_path()
+            flop = (flop_pev if phase == 0 else flop_pim) if infadp else flop_pim
+            k_ms = statistics.mean(kms)
+            ach = B * horizon * flop / (k_ms * 1e-3) / 1e12
+            wide_ffma = kw["policy_hidden_sizes"][0] > 64
+            peak = ffma_peak if wide_ffma else burst / 6.0
+            rows.append({
+                "name": name + ((" PEV" if phase == 0 else " PIM") if infadp else ""), "batch": B, "horizon": horizon,
+                "value": B * horizon * K / (tot * 1e-3), "unit": "env-steps/s", "ms_per_step": tot / K,
+                "kernel_ms": k_ms, "kernel_path": path,
+                "roofline": {"bound": "fp32_ffma" if wide_ffma else "tensor", "achieved": ach, "peak": peak,
+                             "unit": "TFLOP/s", "frac": ach / peak, "algorithmic_flop_per_env_step": flop}})
+        del alg
+
+    # C1 at the reference's own CPU-runnable size
+    run("C1 FHADP idpendulum B=256", alg_kwargs(pre_horizon=H, reward_scale=1.0),
+        {k: v.to(dev) for k, v in idp_init_batch(256, 5).items()}, H, None, FLOP_PER_ENV_STEP)
+    # C2 INFADP veh3dofconti, B=4096, P=10, forward_step=10, [64,64] relu
+    d = ds.sample_veh3dofconti(4096, 10, dev, seed=3)
+    run("C2 INFADP veh3dofconti B=4096", alg_kwargs("pyth_veh3dofconti", "INFADP", 64, "relu", 46, 2, pre_horizon=10,
+                                                    policy_learning_rate=1e-3), d, 10, 2.0e4, 4.6e4)
+    # C3 FHADP veh3dof_tracking P=H=60 [256,256] elu, one GPU's shard (8192) of the 65 536 batch
+    d = ds.sample_veh3dof_tracking(8192, 60, dev, seed=4)
+    run("C3 FHADP veh3dof_tracking H=60 [256,256] B=8192/GPU",
+        alg_kwargs("veh3dof_tracking", "FHADP", 256, "elu", 6 + 4 * 60, 2, pre_horizon=60, policy_learning_rate=1e-3),
+        d, 60, None, 7.8e5)
+    # C5 INFADP LQ s4a2 batch sweep
+    for e in (10, 12, 14, 16, 18, 20):
+        B = 1 << e
+        d = ds.sample_lq(B, "s4a2", dev, seed=e)
+        run(f"C5 INFADP lq s4a2 B=2^{e}",
+            alg_kwargs("pyth_lq", "INFADP", 64, "gelu", 4, 2, lq_config="s4a2", reward_scale=1.0, reward_shift=0.0,
+                       policy_learning_rate=8e-4, value_learning_rate=3e-4), d, 10, 1.25e4, 2.9e4)
+    return rows
 
 
 def main():
@@ -178,102 +367,64 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch-per-gpu", type=int, default=1 << 18)
-    ap.add_argument("--cpu-batch", type=int, default=8192)
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
+    ap.add_argument("--global-batch", type=int, default=GLOBAL_BATCH)
+    ap.add_argument("--cpu-batch", type=int, default=32768)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true")
+    ap.add_argument("--no-eager", action="store_true")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        run_reference(args, rank)
         return
 
     import torch
     torch.set_num_threads(usable_cores())      # the box reports 128 cpus under a 16-core cgroup quota
     import torch.distributed as dist
-    from gops_b200.create_pkg.create_alg import create_alg
-    from gops_b200 import _lib
-
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
-    W, K, Bg = max(args.warmup, 3), args.steps, args.batch_per_gpu
+    hx = Harness(rank, local_rank, world)
+    W, K = max(args.warmup, 3), args.steps
 
-    torch.manual_seed(0)                       # identical replicas on every rank
-    alg = create_alg(**alg_kwargs())
-    batch_bytes = Bg * (OBS_DIM + 1) * 4
-    n_sets = max(2, math.ceil(1.5 * L2_BYTES / batch_bytes))
-    host_sets = []
-    for i in range(n_sets):
-        d = idp_init_batch(Bg, seed=1000 * rank + i)
-        host_sets.append({k: v.pin_memory() for k, v in d.items()})
-    dev_sets = [{k: v.to(dev) for k, v in d.items()} for d in host_sets]
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(sets, steps, collect_kernel=False):
-        plan = next(iter(alg._plans.values())) if alg._plans else None
-        kms = []
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for i in range(steps):
-            alg.local_update(sets[i % len(sets)], i)
-            if collect_kernel and plan is not None:
-                import ctypes as C
-                ms = C.c_float()
-                _lib.check(_lib.lib().gops_b200_plan_last_kernel_ms(plan.handle, C.byref(ms)))
-                kms.append(ms.value)
-        e1.record()
-        barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item()), kms
-
-    timed(dev_sets, W)                                    # warm-up (creates the plan, compiles nothing)
-    plan = next(iter(alg._plans.values()))
-    _lib.check(_lib.lib().gops_b200_plan_enable_timing(plan.handle, 1))
-    timed(dev_sets, 1)
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    ms_total, kernel_ms = timed(dev_sets, K, collect_kernel=True)
-    clocks = sampler.stop()
-    _lib.check(_lib.lib().gops_b200_plan_enable_timing(plan.handle, 0))
-    timed(host_sets, W)
-    ms_e2e, _ = timed(host_sets, K)
-
-    env_steps = Bg * world * H
-    value = env_steps * K / (ms_total * 1e-3)
-    e2e = env_steps * K / (ms_e2e * 1e-3)
+    Bglobal = args.global_batch
+    per_gpu_strong = Bglobal // world
+    main_b = per_gpu_strong if args.scaling == "strong" else Bglobal
+    m = measure_c1(hx, main_b, K, W)
+    other = None
+    if world > 1:      # the other scaling mode, same run (value side only)
+        other_b = Bglobal if args.scaling == "strong" else per_gpu_strong
+        other = measure_c1(hx, other_b, K, W, want_kernel=True, want_e2e=False, want_sync=False)
+        other["batch_per_gpu"] = other_b
 
     if rank == 0:
-        import ctypes as C
-        info = (C.c_int32 * 4)()
-        _lib.check(_lib.lib().gops_b200_plan_launch_info(plan.handle, info))
         peaks = {}
         try:
             with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
                 peaks = json.load(f)
         except Exception:
             pass
+        peak_src = "MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)"
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
-        tens_peak = peaks.get("bf16_tflops_sustained", 1400.0)
-        peak_src = "measured" if peaks else "fallback"
-        k_ms = statistics.mean(kernel_ms) if kernel_ms else ms_total / K
+        burst = peaks.get("bf16_tflops", 1700.0)
+        sustained = peaks.get("bf16_tflops_sustained", 1400.0)
+        env_steps = main_b * world * H
+        value = env_steps * K / (m["ms_total"] * 1e-3)
+        e2e = env_steps * K / (m["ms_e2e"] * 1e-3)
+        k_ms = statistics.mean(m["kernel_ms"])
+        clocks = m["clocks"]
         sm_mhz = clocks["sm_mhz"] or peaks.get("sm_max_mhz", 1965.0)
         n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
         fp32_peak = n_sm * 128 * 2 * sm_mhz * 1e6 / 1e12
-        ach_tflops = Bg * H * FLOP_PER_ENV_STEP / (k_ms * 1e-3) / 1e12
-        ach_gbs = Bg * H * BYTES_PER_ENV_STEP / (k_ms * 1e-3) / 1e9
+        ach_tflops = main_b * H * FLOP_PER_ENV_STEP / (k_ms * 1e-3) / 1e12
+        ach_gbs = main_b * H * BYTES_PER_ENV_STEP / (k_ms * 1e-3) / 1e9
         traffic = None
         tfile = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tfile):
@@ -281,52 +432,72 @@ def main():
                 traffic = json.load(open(tfile)).get("rollout_kernel_dram_bytes_per_launch")
             except Exception:
                 pass
-        # Tensor roof for FP32-accurate GEMMs: the MLP layers run as 3xTF32 mma.sync (three TF32 MMAs per product);
-        # TF32 dense peak = measured bf16 peak / 2.  The FP32 FFMA roof is the one SURVEY 8(d) names for a CUDA-core
-        # implementation; both are reported, plus HBM.
-        tf32x3_peak = tens_peak / 2.0 / 3.0
-        roof = {"bound": "tensor", "achieved": ach_tflops, "peak": tf32x3_peak, "unit": "TFLOP/s",
-                "frac": ach_tflops / tf32x3_peak, "traffic": traffic,
-                "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peak_src}) / 2 (TF32) / 3 (3xTF32 split)",
-                "kernel_ms": k_ms, "kernel_share_of_step": k_ms * K / ms_total,
+        path = m["launch"]["kernel_path"]
+        # FP32-accurate tensor roof: BF16x3 = six bf16 MMAs per product (tc path), 3xTF32 = three TF32 MMAs at half the
+        # bf16 rate (mma path): both = bf16 peak / 6.  The kernel is event-timed alone -> burst peak.
+        tens_roof = burst / 6.0
+        m["launch"]["kernel_path_text"] = PATH_TEXT.get(path, path)
+        roof = {"bound": "tensor", "achieved": ach_tflops, "peak": tens_roof, "unit": "TFLOP/s",
+                "frac": ach_tflops / tens_roof, "traffic": traffic,
+                "peak_source": f"{peak_src} bf16_tflops (burst: kernel timed alone) / 6 (six bf16 MMAs per FP32-accurate product)",
+                "frac_of_sustained_peak": ach_tflops / (sustained / 6.0),
+                "kernel_ms": k_ms, "kernel_share_of_step": k_ms * K / m["ms_total"],
+                "non_kernel_ms_per_step": m["ms_total"] / K - k_ms,
                 "algorithmic_flop_per_env_step": FLOP_PER_ENV_STEP, "algorithmic_bytes_per_env_step": BYTES_PER_ENV_STEP,
                 "fp32_ffma": {"achieved_tflops": ach_tflops, "peak_tflops": fp32_peak, "frac": ach_tflops / fp32_peak,
                               "of": f"{n_sm} SM x 128 lanes x 2 x {sm_mhz:.0f} MHz sampled under load"},
                 "hbm": {"achieved_gbs": ach_gbs, "peak_gbs": hbm_peak, "frac": ach_gbs / hbm_peak, "of": peak_src},
-                "tensor_bf16": {"achieved_tflops": ach_tflops, "peak_tflops": tens_peak, "frac": ach_tflops / tens_peak,
-                                "of": peak_src + " bf16 sustained"},
-                "launch": {"grid": info[0], "block": info[1], "tile_samples": info[2], "smem_bytes": info[3]}}
+                "tensor_bf16": {"achieved_tflops": ach_tflops, "peak_tflops": burst, "frac": ach_tflops / burst,
+                                "of": peak_src + " bf16 burst"},
+                "launch": m["launch"]}
         cpu = None
-        if not args.no_cpu_baseline:
-            threads = best_cpu_threads(args.cpu_batch)
-            rate, sec = cpu_update_rate(args.cpu_batch, 3, 1, threads)
-            cpu = {"value": rate, "unit": "env-steps/s", "cores": threads, "kind": "port",
-                   "sample": f"B={args.cpu_batch}, H={H}, 3 updates after 1 warm-up (oracle/gops_oracle.py)"}
-        # kernels of this library per update: pack_params[_tcf], [pack_params_tc,] rollout_kernel, reduce_partials, adam
-        sm_count = torch.cuda.get_device_properties(0).multi_processor_count
-        forced = os.environ.get("GOPS_B200_ROLLOUT", "")
-        path = forced if forced in ("tc", "hy", "mma") else ("tc" if Bg >= sm_count * 512 else "mma")
-        launches_per_step = 5 if path == "hy" else 4
-        roof["launch"]["kernel_path"] = {
-            "tc": "full tcgen05: BF16x3 UMMA for every dense product, weight gradients accumulate in TMEM",
-            "hy": "hybrid: tcgen05/TMEM (3xTF32) forward sweep + mma.sync reverse sweep",
-            "mma": "mma.sync (3xTF32) forward and reverse sweeps"}[path]
-        if path == "tc":   # six bf16 MMAs per FP32-accurate product: the same roof as three TF32 MMAs at half the bf16 rate
-            roof["peak_source"] = (f"MEASURED_PEAKS.json bf16_tflops_sustained ({peak_src}) / 6 "
-                                   "(BF16x3: six bf16 products per FP32-accurate product)")
+        if not args.no_cpu_baseline and world == 1:
+            cpu = cpu_reference_leg(args.cpu_batch, 3, 1)
+        eager = None
+        if not args.no_eager and world == 1:
+            try:
+                from oracle import ref_runner
+                if ref_runner.available():
+                    eb = 1 << 16
+                    rate, sec = ref_runner.time_reference_updates(eb, 3, 2, H=H, device=f"cuda:{local_rank}")
+                    eager = {"value": rate, "unit": "env-steps/s", "ms_per_step": sec * 1e3,
+                             "what": f"unmodified gops FHADP.local_update with use_gpu=True (PyTorch eager) on this GPU, "
+                                     f"B={eb}, H={H}, 3 updates after 2 warm-ups (oracle/_ref)"}
+                    torch.cuda.empty_cache()
+            except Exception as e:          # the eager leg must never take the bench down
+                eager = {"unavailable": repr(e)[:200]}
+        configs = None
+        if not args.no_configs and world == 1:
+            try:
+                configs = secondary_configs(hx, peaks)
+            except Exception as e:
+                configs = [{"error": repr(e)[:300]}]
         line = {
             "metric": "batched env-steps/sec (FHADP rollout+update)", "value": value, "unit": "env-steps/s",
-            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_total / K, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": m["ms_total"] / K, "higher_is_better": True,
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"FHADP pyth_idpendulum H={H} FiniteHorizonPolicy[64,64] gelu, "
-                                   f"batch {Bg} per GPU (global {Bg * world})",
-                       "parallelism": f"dp{world}", "l2_policy": f"{n_sets} rotating input batches "
-                       f"({n_sets * batch_bytes / 2**20:.0f} MiB total > L2)"},
+                                   f"batch {main_b} per GPU (global {main_b * world})",
+                       "parallelism": f"dp{world}", "l2_policy": f"{m['n_sets']} rotating input batches "
+                       f"({m['n_sets'] * m['batch_bytes'] / 2**20:.0f} MiB total > L2)",
+                       "loss_readback": "pipelined: every step's 4-float tail is copied to pinned memory and read by "
+                                        "the host one step later (alg.loss_lag=1); sync_loss = same with loss_lag=0"},
             "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
-            "e2e": {"value": e2e, "unit": "env-steps/s", "h2d_bytes_per_step": batch_bytes, "d2h_bytes_per_step": 4,
-                    "ms_per_step": ms_e2e / K},
-            "gpu_launches": launches_per_step * K,
+            "e2e": {"value": e2e, "unit": "env-steps/s", "h2d_bytes_per_step": m["batch_bytes"], "d2h_bytes_per_step": 16,
+                    "ms_per_step": m["ms_e2e"] / K},
+            "sync_loss": {"value": env_steps * K / (m["ms_total_sync"] * 1e-3), "ms_per_step": m["ms_total_sync"] / K},
+            "gpu_launches": m["launches"],
         }
+        if other is not None:
+            ob = other["batch_per_gpu"]
+            line["weak" if args.scaling == "strong" else "strong"] = {
+                "value": ob * world * H * K / (other["ms_total"] * 1e-3), "unit": "env-steps/s",
+                "batch_per_gpu": ob, "global_batch": ob * world, "ms_per_step": other["ms_total"] / K,
+                "kernel_ms": statistics.mean(other["kernel_ms"]), "launch": other["launch"]}
+        if eager is not None:
+            line["gpu_eager_baseline"] = eager
+        if configs is not None:
+            line["configs"] = configs
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

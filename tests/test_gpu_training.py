@@ -65,3 +65,48 @@ def test_infadp_lq_approaches_lqr_gain(tmp_path):
     sd = torch.load(tmp_path / "apprfunc" / "apprfunc_8000.pkl")
     assert {"policy.pi.0.weight", "v.v.4.bias", "v_target.v.0.weight", "policy_target.pi.2.bias",
             "policy.act_high_lim"} <= set(sd)
+
+
+def test_device_samplers_match_the_oracle_laws():
+    """On-device initial-state samplers (trainer/device_sampler.py) vs. the oracle's restatement of the data envs'
+    reset laws: same reference points for the same (t0, path, speed), same ego-frame observation."""
+    from gops_b200.trainer import device_sampler as ds
+    from oracle import gops_oracle as orc
+    d = ds.sample_veh3dofconti(2048, 10, "cuda", seed=1)
+    ref = orc.RefTraj()
+    t0, p, s = d["ref_time"].cpu(), d["path_num"].cpu(), d["u_num"].cpu()
+    for i in (0, 4, 10):
+        tt = t0 + i * 0.1
+        want = torch.stack((ref.x(tt, p, s), ref.y(tt, p, s), ref.phi(tt, p, s), ref.u(tt, p, s)), 1)
+        got = d["ref_points"][:, i].cpu()
+        np.testing.assert_allclose(np.delete(got.numpy(), 2, 1), np.delete(want.numpy(), 2, 1), rtol=1e-5, atol=2e-4)
+        np.testing.assert_allclose(got[:, 2].numpy(), want[:, 2].numpy(), rtol=0, atol=8e-3)   # fp32 finite-difference phi
+    np.testing.assert_allclose(d["obs"].cpu().numpy(), orc.veh_obs(d["state"].cpu(), d["ref_points"].cpu()).numpy(),
+                               rtol=1e-5, atol=1e-5)
+    assert set(p.unique().tolist()) == {0.0, 1.0, 2.0, 3.0} and set(s.unique().tolist()) == {0.0, 1.0}
+    t = ds.sample_veh3dof_tracking(64, 20, "cuda", seed=2)
+    assert t["state"].context_state.reference.shape == (64, 41, 4) and t["obs"].shape == (64, 86)
+
+
+def test_trainer_evaluator_and_best_checkpoint(tmp_path):
+    """Vehicle sampler -> INFADP updates -> batched on-device evaluator -> `_opt.pkl` bookkeeping of
+    off_serial_trainer.py:126-141 (only after max_iteration / 5, previous best removed)."""
+    import os
+    from gops_b200.create_pkg.create_alg import create_alg
+    from gops_b200.trainer.device_trainer import DeviceEvaluator, DeviceStateSampler, OnDeviceSerialTrainer
+    torch.manual_seed(0)
+    kw = _kwargs("pyth_veh3dofconti", "INFADP", 46, 2, "relu", pre_horizon=10)
+    kw.update(policy_learning_rate=1e-3, value_learning_rate=1e-3)
+    alg = create_alg(**kw)
+    sampler = DeviceStateSampler("pyth_veh3dofconti", "cuda", 3, pre_horizon=10)
+    ev = DeviceEvaluator(alg, DeviceStateSampler("pyth_veh3dofconti", "cuda", 4, pre_horizon=10), num_eval_episode=64,
+                         max_step=50)
+    r0 = ev.run_evaluation(0)
+    tr = OnDeviceSerialTrainer(alg, sampler, replay_batch_size=2048, max_iteration=600, log_save_interval=100,
+                               save_folder=str(tmp_path), evaluator=ev, eval_interval=100)
+    tr.train()
+    tars = [tb["Evaluation/1. TAR-RL iter"] for _, tb in tr.history if "Evaluation/1. TAR-RL iter" in tb]
+    assert len(tars) >= 5 and all(np.isfinite(tars))
+    assert max(tars[2:]) > r0, (r0, tars)                    # tracking improves over the untrained policy
+    opt = [f for f in os.listdir(tmp_path / "apprfunc") if f.endswith("_opt.pkl")]
+    assert len(opt) == 1 and int(opt[0].split("_")[1]) >= 600 / 5, opt
