@@ -1,4 +1,4 @@
-"""Full tcgen05 rollout kernel (BF16x3 operands, TMEM-resident weight gradients, GOPS_B200_ROLLOUT=tc;
+"""Full tcgen05 rollout kernel (BF16x3 operands, TMEM weight-gradient accumulators; plan option kernel_path = "tc";
 csrc/mlp_tc_full.cuh) held to the same bars as the mma.sync kernel: golden vectors of the unmodified reference (loss,
 gradient, Adam step), the fp64 oracle on ragged batches, degenerate shapes and the no-grad trace."""
 import numpy as np
@@ -16,7 +16,9 @@ TC_GOLDEN = [n for n in base.GOLDEN
 
 @pytest.fixture(autouse=True)
 def _force_tc(monkeypatch):
-    monkeypatch.setenv("GOPS_B200_ROLLOUT", "tc")
+    """Every algorithm built in these tests asks its plans for the tcgen05 kernel (a plan option, asserted below)."""
+    from gops_b200.algorithm.base import FusedADPMixin
+    monkeypatch.setattr(FusedADPMixin, "kernel_path", "tc")
 
 
 @pytest.mark.parametrize("name", TC_GOLDEN)
@@ -57,8 +59,10 @@ def test_tcf_path_is_taken_and_deterministic(monkeypatch):
         return np.concatenate([p.grad.detach().cpu().numpy().ravel() for p in alg.networks.policy.parameters()])
 
     g_tc, g_tc2 = grads(), grads()
-    monkeypatch.setenv("GOPS_B200_ROLLOUT", "mma")
+    assert alg.last_kernel_path() == "tc"
+    alg.kernel_path = "mma"
     g_mma = grads()
+    assert alg.last_kernel_path() == "mma"
     assert np.array_equal(g_tc, g_tc2)
     assert not np.array_equal(g_tc, g_mma)
     assert np.linalg.norm(g_tc - g_mma) <= 2e-4 * np.linalg.norm(g_mma)

@@ -37,7 +37,7 @@ if "wide" in which:
     alg.set_parameters({"pre_horizon": 2})
     alg.local_update(to_dev(orc.sample_inputs("veh3dof_tracking", 70, 4, pre_horizon=10)), 0)
 if "tc" in which:          # tcgen05 / TMEM kernels: hybrid rollout (forced) and batched inference incl. a ragged tail
-    os.environ["GOPS_B200_ROLLOUT"] = "hy"
+    os.environ["GOPS_B200_ROLLOUT"] = "tc"
     alg = create_alg(**kwargs("pyth_idpendulum", "FHADP", 6, 1, 64, "gelu", pre_horizon=3, reward_scale=1.0))
     for B in (700, 130):
         alg.local_update(to_dev(orc.sample_inputs("pyth_idpendulum", B, 1)), 0)
