@@ -15,6 +15,7 @@
 #include "kernel.cuh"
 #include "aux_kernels.cuh"
 #include "mlp_tc.cuh"
+#include "rollout_tc2.cuh"
 #include <cuda_bf16.h>
 
 using namespace gops;
@@ -150,8 +151,10 @@ RolloutFn rollout_fn_vehconti(int hid, int cfg, int alg);
 RolloutFn rollout_fn_vehtrack(int hid, int cfg, int alg);
 StepFn step_fn_idp();
 StepFn step_fn_lq();
-RolloutFn rollout_fn_tc_idp(int alg);   // full tcgen05 kernels (BF16x3, TMEM-resident weight gradients)
+RolloutFn rollout_fn_tc_idp(int alg);   // round-1 tcgen05 kernel (one sub-tile at a time, 512 cooperating threads): A/B only
 RolloutFn rollout_fn_tc_lq(int alg);
+RolloutFn rollout_fn_tc2_idp(int alg);  // pipelined tcgen05 kernel: two independent 128-thread groups per CTA (rollout_tc2.cuh)
+RolloutFn rollout_fn_tc2_lq(int alg);
 }  // namespace gops
 
 namespace {
@@ -169,6 +172,13 @@ RolloutFn rollout_fn_tc(int model, int alg) {
   switch (model) {
     case GOPS_MODEL_IDPENDULUM: return rollout_fn_tc_idp(alg);
     case GOPS_MODEL_LQ: return rollout_fn_tc_lq(alg);
+    default: return nullptr;
+  }
+}
+RolloutFn rollout_fn_tc2(int model, int alg) {
+  switch (model) {
+    case GOPS_MODEL_IDPENDULUM: return rollout_fn_tc2_idp(alg);
+    case GOPS_MODEL_LQ: return rollout_fn_tc2_lq(alg);
     default: return nullptr;
   }
 }
@@ -203,7 +213,7 @@ struct gops_b200_plan {
   NetL pol_tcf, val_tcf;
   int w_floats_tcf = 0;
   float *blob_pol_tcf = nullptr, *blob_val_tcf = nullptr, *blob_vtg_tcf = nullptr;
-  bool tc_attr_set[4] = {};
+  bool tc_attr_set[4] = {}, tc2_attr_set[4] = {};
   float* osc = nullptr;   // obs scale | shift, 2 * obs_dim floats
   bool attr_set[4][4] = {};   // [alg][cfg]
   bool timing = false;
@@ -260,8 +270,8 @@ bool rollout_use_tc(const gops_b200_plan* pl, long long batch) {
   if (e && !strcmp(e, "mma")) path = GOPS_PATH_MMA;
   if (e && !strcmp(e, "tc")) path = GOPS_PATH_TC;
   if (path == GOPS_PATH_MMA) return false;
-  if (path == GOPS_PATH_TC) return true;
-  return batch >= (long long)pl->sm_count * 512;
+  (void)batch;      // the pipelined kernel schedules single 128-sample sub-tiles: it is the default at every batch size
+  return true;
 }
 __global__ void pack_params_tcf_kernel(const float* __restrict__ flat, NetL L, float* __restrict__ blob) {
   const int n = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
@@ -376,9 +386,11 @@ int launch_rollout(gops_b200_plan* pl, const gops_b200_batch* b, int alg, cudaSt
   }
   KParams& kp = pl->kp;
   if (rollout_use_tc(pl, b->batch)) {
-    RolloutFn fn = rollout_fn_tc(pl->desc.model, alg);
-    if (!fn) return fail("full tcgen05 rollout kernel not built for this env model");
-    const int S = 128, NT = 512;
+    const char* ev = getenv("GOPS_B200_TC_V1");      // A/B only: round-1 cooperative kernel
+    const bool v1 = ev && ev[0] == '1';
+    RolloutFn fn = v1 ? rollout_fn_tc(pl->desc.model, alg) : rollout_fn_tc2(pl->desc.model, alg);
+    if (!fn) return fail("tcgen05 rollout kernel not built for this env model");
+    const int S = 128, NT = v1 ? 512 : tc2::NT2;
     KParams k2 = kp;
     k2.pol = pl->pol_tcf;
     k2.val = pl->val_tcf;
@@ -397,16 +409,19 @@ int launch_rollout(gops_b200_plan* pl, const gops_b200_batch* b, int alg, cudaSt
     k2.part_stride = round4(upd.nparam + 4);
     kp.part_stride = k2.part_stride;
     k2.dw_floats = round4(upd.nacc);
-    const size_t smem = rollout_smem_bytes_tcf(k2);
-    if (smem > (size_t)pl->max_smem) return fail("full tcgen05 rollout kernel does not fit in shared memory");
-    if (!pl->tc_attr_set[alg]) {
+    const size_t smem = v1 ? rollout_smem_bytes_tcf(k2) : tc2::smem_bytes(k2.w_floats);
+    if (smem > (size_t)pl->max_smem) return fail("tcgen05 rollout kernel does not fit in shared memory");
+    bool& attr = v1 ? pl->tc_attr_set[alg] : pl->tc2_attr_set[alg];
+    if (!attr) {
       CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, pl->max_smem));
-      pl->tc_attr_set[alg] = true;
+      attr = true;
     }
     const long long slots = pl->sm_count;          // one CTA per SM (all 512 TMEM columns)
     const long long subtiles = (b->batch + S - 1) / S;
-    const int grid = (int)(subtiles < slots ? subtiles : slots);
-    if (ensure_scratch(pl, grid, NT, k2.horizon)) return 1;
+    const int rows = v1 ? 1 : tc2::NG;             // gradient partial rows (= independent groups) per CTA
+    const long long want = (subtiles + rows - 1) / rows;
+    const int grid = (int)(want < slots ? want : slots);
+    if (ensure_scratch(pl, grid, NT, k2.horizon, rows)) return 1;
     k2.tape = pl->tape;
     k2.ext_ref = pl->ext_ref;
     k2.xbuf = pl->xbuf;
@@ -419,7 +434,7 @@ int launch_rollout(gops_b200_plan* pl, const gops_b200_batch* b, int alg, cudaSt
     pl->last_grid = grid; pl->last_S = S; pl->last_NT = NT; pl->last_smem = smem; pl->last_path = GOPS_PATH_TC;
     if (alg != ALG_TRACE) {
       const int n = upd.nparam + 3;
-      reduce_partials_kernel<<<(n + 255) / 256, 256, 0, st>>>(pl->partial, grid, k2.part_stride, upd.nparam, grad_out,
+      reduce_partials_kernel<<<(n + 255) / 256, 256, 0, st>>>(pl->partial, grid * rows, k2.part_stride, upd.nparam, grad_out,
                                                              scalars_out);
       ++g_launches;
       CUDA_OK_L(cudaGetLastError(), "launch#3-tc");

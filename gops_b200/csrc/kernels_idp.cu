@@ -1,5 +1,6 @@
 // Instantiations of the fused rollout kernel for ModelIdp (own translation unit: parallel build).
 #include "kernel.cuh"
+#include "rollout_tc2.cuh"
 
 namespace gops {
 
@@ -30,6 +31,14 @@ RolloutFn rollout_fn_tc_idp(int alg) {   // full tcgen05 / TMEM path (BF16x3)
     case ALG_PIM: return rollout_kernel<ModelIdp, 64, 128, 512, ALG_PIM, true>;
     case ALG_PEV: return rollout_kernel<ModelIdp, 64, 128, 512, ALG_PEV, true>;
     default: return rollout_kernel<ModelIdp, 64, 128, 512, ALG_TRACE, true>;
+  }
+}
+RolloutFn rollout_fn_tc2_idp(int alg) {   // pipelined tcgen05 kernel (two independent groups per CTA)
+  switch (alg) {
+    case ALG_FHADP: return rollout_tc2_kernel<ModelIdp, ALG_FHADP>;
+    case ALG_PIM: return rollout_tc2_kernel<ModelIdp, ALG_PIM>;
+    case ALG_PEV: return rollout_tc2_kernel<ModelIdp, ALG_PEV>;
+    default: return rollout_tc2_kernel<ModelIdp, ALG_TRACE>;
   }
 }
 StepFn step_fn_idp() { return model_step_kernel<ModelIdp>; }

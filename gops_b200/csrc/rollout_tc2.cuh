@@ -1,0 +1,802 @@
+// Pipelined tcgen05 / TMEM rollout kernel (64-wide nets, <= 16 inputs, state == obs models): TWO INDEPENDENT 128-thread
+// groups per CTA, each owning one 128-sample sub-tile at a time.
+//
+//   thread = sample = TMEM lane.  A thread keeps its sample's model state and adjoint in registers for the whole
+//   horizon, writes its own observation row into the bf16x3 operand planes, reads its own accumulator row back
+//   (tcgen05.ld 32x32b: lane = row), applies bias / activation / output layer for all 64 columns and multiplies its own
+//   deltas: no observation / action tiles in shared memory, no cross-thread exchange, no CTA barrier in the sweeps.
+//   The only collective steps are the group's 128-thread named barrier in front of each MMA issue and the reductions
+//   over samples, which run on the tensor core (dW1, db1, dW2, db2: contraction over the 128 samples with the
+//   MN-major view of the same operand planes) or as warp shuffles (dW3, db3).
+//
+//   While one group waits for its MMA round trip (issue -> tensor pipe -> commit -> mbarrier), the other group's
+//   warps run their epilogue or dynamics: the two groups are never synchronised with each other (FHADP), so the tensor
+//   pipe and the CUDA cores overlap without any software pipelining.  Round 1's kernel marched all 512 threads through
+//   five issue -> wait -> epilogue round trips of ONE sub-tile (tensor pipe 17 % busy, issue slots 43 % busy).
+//
+// Arithmetic (unchanged bars: loss 1e-4, gradient 2e-4 against the CPU oracle):
+//   layer products        x . W^T      BF16x3 x BF16x3, six terms (FP32-accurate; the loss depends on these)
+//   delta / input grad    delta . W    delta in TWO bf16 planes (2^-17 relative: the gradient bar is 2e-4), W in three
+//   weight gradients      delta^T . h  [delta_b0 | delta_b1] stacked to M = 128 against (h_b0 + h_b1): four terms
+//   TMEM accumulators of the weight gradients are flushed into the group's FP32 global partial every FLUSH_EVERY
+//   horizon steps (the tensor core truncates when it adds into its accumulator).
+//
+// Shared memory (C1: 221 KB of 227): weights 31.5 KB (TMA-staged, shared by both groups) + per group: H1 planes 48 KB,
+// delta planes 32 KB (delta2, then delta1 in the same buffer once the MMAs reading delta2 have retired), observation
+// planes 12 KB.  TMEM: 240 of 256 columns per group (ACC 64 | act'(layer 1) 64 | dW2 64 | db2 16 | dW1 16 | db1 16).
+#pragma once
+#include "models.cuh"
+#include "mlp_tc_full.cuh"
+
+namespace gops {
+namespace tc2 {
+
+constexpr int GT = 128;                 // threads per group = samples per sub-tile = UMMA M
+constexpr int NG = 2;                   // groups per CTA
+constexpr int NT2 = GT * NG;
+constexpr uint32_t C_ACC = 0, C_D1 = 64, C_DW2 = 128, C_DB2 = 192, C_DW1 = 208, C_DB1 = 224, C_GROUP = 256;
+constexpr int HPL = tcf::HPLANE, XPL = tcf::XPLANE;
+constexpr int P_BYTES = 3 * HPL, Q_BYTES = 2 * HPL, XP_BYTES = 3 * XPL;
+constexpr int GROUP_BYTES = P_BYTES + Q_BYTES + XP_BYTES;
+constexpr int FLUSH_EVERY = 4;          // horizon steps between flushes of the TMEM weight-gradient accumulators
+constexpr int HDR_BYTES = 256;
+
+__host__ __device__ inline size_t smem_bytes(int w_floats) {
+  return HDR_BYTES + (size_t)w_floats * 4 + tcf::ONES_B + (size_t)NG * GROUP_BYTES + NG * 4 * (MAXA * 64 + MAXA) * 4;
+}
+
+__device__ __forceinline__ void group_sync(int g) { asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory"); }
+
+// 16 accumulator columns of this thread's lane, WITHOUT waiting (issue several, then tm_wait_ld once)
+__device__ __forceinline__ void tm_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, "
+      "[%16];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tm_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// 32 columns -> floats (two x16 loads in flight, one wait)
+__device__ __forceinline__ void tm_ld32(uint32_t taddr, float* v) {
+  uint32_t r[32];
+  tm_ld16(taddr, r);
+  tm_ld16(taddr + 16, r + 16);
+  tm_wait_ld();
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tm_st32(uint32_t taddr, const float* v) {
+  umma::tmem_st16(taddr, v);
+  umma::tmem_st16(taddr + 16, v + 16);
+}
+
+// (x0, x1) -> packed bf16x2 words of two planes (low half = x0)
+__device__ __forceinline__ void split2(float x0, float x1, uint32_t& p0, uint32_t& p1) {
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(p0) : "f"(x1), "f"(x0));
+  const float r0 = x0 - __uint_as_float(p0 << 16), r1 = x1 - __uint_as_float(p0 & 0xffff0000u);
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(p1) : "f"(r1), "f"(r0));
+}
+
+// Per-thread view of its group's resources
+struct Grp {
+  unsigned char *P, *Q, *Xp;        // H1 planes (3), delta planes (2), observation planes (3)
+  const unsigned char* ones;
+  uint64_t *bc, *bd2, *bd1;         // mbarriers: critical-path MMA groups / dW2+db2 / dW1+db1
+  uint32_t pc, pd2, pd1;            // their phases
+  uint32_t tm;                      // TMEM address of this thread's lane, column 0 of the group
+  uint32_t tmg;                     // TMEM address lane 0, column 0 of the group (MMA destinations)
+  uint32_t fresh;                   // 1: the next weight-gradient MMAs overwrite their accumulators
+  bool d2_pending, d1_pending;      // weight-gradient MMA groups in flight (their operand planes must not be rewritten)
+  int g, r;                         // group, row (= thread in group = sample of the sub-tile)
+  // staged weights of the network in use
+  const unsigned char *W1, *W2;
+  const float *W3, *b1, *b2, *b3;
+};
+
+__device__ __forceinline__ void bind(Grp& G, const float* Wsm, const NetL& L) {
+  G.W1 = reinterpret_cast<const unsigned char*>(Wsm + L.o_w1);
+  G.W2 = reinterpret_cast<const unsigned char*>(Wsm + L.o_w2);
+  G.W3 = Wsm + L.o_w3; G.b1 = Wsm + L.o_b1; G.b2 = Wsm + L.o_b2; G.b3 = Wsm + L.o_b3;
+}
+__device__ __forceinline__ void wait_c(Grp& G) { mbar_wait(G.bc, G.pc); G.pc ^= 1u; umma::fence_after_sync(); }
+__device__ __forceinline__ void wait_d2(Grp& G) {
+  if (G.d2_pending) { mbar_wait(G.bd2, G.pd2); G.pd2 ^= 1u; umma::fence_after_sync(); G.d2_pending = false; }
+}
+__device__ __forceinline__ void wait_d1(Grp& G) {
+  if (G.d1_pending) { mbar_wait(G.bd1, G.pd1); G.pd1 ^= 1u; umma::fence_after_sync(); G.d1_pending = false; }
+}
+// make this thread's shared-memory / TMEM writes visible to the MMA issuer, then meet the group
+__device__ __forceinline__ void publish(const Grp& G) {
+  fence_proxy_async();
+  umma::fence_before_sync();
+  group_sync(G.g);
+}
+
+// delta (2 planes, K-major A) x W^T (3 planes, MN-major B): a1b1, a0b2, a1b0, a0b1, a0b0 -- small terms first
+template <int KS>
+__device__ __forceinline__ void issue_dw(uint32_t d, const tcf::Op& A, const tcf::Op& B, uint32_t idesc) {
+  using namespace tcf;
+  const uint64_t a0 = dsc(A, 0), a1 = dsc(A, 1), b0 = dsc(B, 0), b1 = dsc(B, 1), b2 = dsc(B, 2);
+  const uint64_t ka = A.kadv >> 4, kb = B.kadv >> 4;
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks) mma_bf16(d, a1 + ks * ka, b1 + ks * kb, idesc, ks > 0 ? 1u : 0u);
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks) mma_bf16(d, a0 + ks * ka, b2 + ks * kb, idesc, 1u);
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks) mma_bf16(d, a1 + ks * ka, b0 + ks * kb, idesc, 1u);
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks) mma_bf16(d, a0 + ks * ka, b1 + ks * kb, idesc, 1u);
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks) mma_bf16(d, a0 + ks * ka, b0 + ks * kb, idesc, 1u);
+}
+// D (+)= [A_b0 | A_b1]^T (M = 128 stacked, MN-major) . (B_b0 + .. + B_b{bplanes-1}), 8 steps of 16 samples
+__device__ __forceinline__ void issue_wgrad(uint32_t d, const tcf::Op& A, const tcf::Op& B, uint32_t idesc, int bplanes,
+                                            uint32_t fresh) {
+  using namespace tcf;
+  const uint64_t a01 = dsc(A, 0), ka = A.kadv >> 4, kb = B.kadv >> 4;
+  for (int p = bplanes - 1; p >= 0; --p) {
+    const uint64_t b = dsc(B, p);
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks)
+      mma_bf16(d, a01 + ks * ka, b + ks * kb, idesc, (fresh && p == bplanes - 1 && ks == 0) ? 0u : 1u);
+  }
+}
+
+// this thread's input row (K1 = 16 values, zero padded) -> the three observation planes
+__device__ __forceinline__ void write_x_row(const Grp& G, const float* x) {
+  using namespace tcf;
+#pragma unroll
+  for (int ch = 0; ch < 2; ++ch) {
+    uint32_t w[3][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) split3(x[8 * ch + 2 * i], x[8 * ch + 2 * i + 1], w[0][i], w[1][i], w[2][i]);
+#pragma unroll
+    for (int p = 0; p < 3; ++p)
+      *reinterpret_cast<uint4*>(G.Xp + p * XPL + (ch * 128 + G.r) * 16) = make_uint4(w[p][0], w[p][1], w[p][2], w[p][3]);
+  }
+}
+
+// layer 1: X planes . W1^T -> accumulator; epilogue: + b1, activation -> H1 planes (FULL: act' parked in TMEM)
+template <bool FULL>
+__device__ __forceinline__ void layer1(Grp& G, const NetL& L, const float* x) {
+  using namespace tcf;
+  wait_d1(G);                                   // the dW1 MMAs of the previous step still read the X planes
+  write_x_row(G, x);
+  publish(G);
+  if (G.r == 0) {
+    umma::fence_after_sync();
+    issue6<1>(G.tmg + C_ACC, k_act(G.Xp, XPL), k_w(G.W1, W1PLANE), idesc_bf16(128, 64, false, false));
+    umma::commit(G.bc);
+  }
+  wait_d2(G);                                   // ... and the dW2 MMAs the H1 planes
+  wait_c(G);
+#pragma unroll
+  for (int hb = 0; hb < 2; ++hb) {
+    float v[32], d[32];
+    tm_ld32(G.tm + C_ACC + 32 * hb, v);
+#define GOPS_TC2_A1(A)                                                      \
+  _Pragma("unroll") for (int e = 0; e < 32; ++e) {                          \
+    const float pre = v[e] + G.b1[32 * hb + e];                             \
+    if constexpr (FULL) act_fwd_grad_t<A>(pre, v[e], d[e]);                 \
+    else v[e] = act_fwd_t<A>(pre);                                          \
+  }
+    GOPS_ACT_SWITCH(L.hact, GOPS_TC2_A1)
+#undef GOPS_TC2_A1
+    store16(G.P, HPL, 2 * hb, G.r, v);
+    store16(G.P, HPL, 2 * hb + 1, G.r, v + 16);
+    if constexpr (FULL) tm_st32(G.tm + C_D1 + 32 * hb, d);
+  }
+  if constexpr (FULL) umma::tmem_wait_st();
+}
+
+// layer 2 + output layer, forward only: returns z[a] = b3[a] + W3[a] . act(H1 . W2^T + b2)
+__device__ __forceinline__ void layer2_out(Grp& G, const NetL& L, float* z) {
+  using namespace tcf;
+  publish(G);
+  if (G.r == 0) {
+    umma::fence_after_sync();
+    issue6<4>(G.tmg + C_ACC, k_act(G.P, HPL), k_w(G.W2, W2PLANE), idesc_bf16(128, 64, false, false));
+    umma::commit(G.bc);
+  }
+#pragma unroll
+  for (int a = 0; a < MAXA; ++a) z[a] = a < L.out ? G.b3[a] : 0.f;
+  wait_c(G);
+#pragma unroll
+  for (int hb = 0; hb < 2; ++hb) {
+    float v[32];
+    tm_ld32(G.tm + C_ACC + 32 * hb, v);
+#define GOPS_TC2_A2(A) \
+  _Pragma("unroll") for (int e = 0; e < 32; ++e) v[e] = act_fwd_t<A>(v[e] + G.b2[32 * hb + e]);
+    GOPS_ACT_SWITCH(L.hact, GOPS_TC2_A2)
+#undef GOPS_TC2_A2
+#pragma unroll
+    for (int a = 0; a < MAXA; ++a)
+      if (a < L.out) {
+        const float* w = G.W3 + a * 64 + 32 * hb;
+        float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+        for (int e = 0; e < 32; e += 2) { s0 = fmaf(w[e], v[e], s0); s1 = fmaf(w[e + 1], v[e + 1], s1); }
+        z[a] += s0 + s1;
+      }
+  }
+  umma::fence_before_sync();      // the accumulator reads are ordered before the next MMA group (issued after a barrier)
+}
+
+// Per-thread accumulators of the output-layer gradients: after the transposing warp reduction lane l holds the warp's
+// column sum of column 16 b + col16(l) in slot b; they are combined across warps once, at the end of the kernel.
+struct Acc3 {
+  float w[MAXA][4];
+  float b[MAXA];
+};
+
+// layer 2 recompute fused with the start of the backward pass: z (if wanted), dW3 / db3 partial sums, and
+// delta2 = (W3^T zbar) * act'(pre2) -> the two delta planes.  zbar: this thread's output adjoint.
+template <bool WANT_DW>
+__device__ __forceinline__ void layer2_back(Grp& G, const NetL& L, const float* zbar, float* z, Acc3& acc3) {
+  using namespace tcf;
+  publish(G);
+  if (G.r == 0) {
+    umma::fence_after_sync();
+    issue6<4>(G.tmg + C_ACC, k_act(G.P, HPL), k_w(G.W2, W2PLANE), idesc_bf16(128, 64, false, false));
+    umma::commit(G.bc);
+  }
+  if (z != nullptr) {
+#pragma unroll
+    for (int a = 0; a < MAXA; ++a) z[a] = a < L.out ? G.b3[a] : 0.f;
+  }
+  const int lane = G.r & 31;
+  wait_c(G);
+#pragma unroll
+  for (int hb = 0; hb < 2; ++hb) {
+    float v[32], d[32];
+    tm_ld32(G.tm + C_ACC + 32 * hb, v);
+#define GOPS_TC2_A3(A) \
+  _Pragma("unroll") for (int e = 0; e < 32; ++e) act_fwd_grad_t<A>(v[e] + G.b2[32 * hb + e], v[e], d[e]);
+    GOPS_ACT_SWITCH(L.hact, GOPS_TC2_A3)
+#undef GOPS_TC2_A3
+    if (z != nullptr) {
+#pragma unroll
+      for (int a = 0; a < MAXA; ++a)
+        if (a < L.out) {
+          const float* w = G.W3 + a * 64 + 32 * hb;
+          float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+          for (int e = 0; e < 32; e += 2) { s0 = fmaf(w[e], v[e], s0); s1 = fmaf(w[e + 1], v[e + 1], s1); }
+          z[a] += s0 + s1;
+        }
+    }
+    if constexpr (WANT_DW) {
+#pragma unroll
+      for (int a = 0; a < MAXA; ++a)
+        if (a < L.out) {
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            float t[16];
+#pragma unroll
+            for (int e = 0; e < 16; ++e) t[e] = zbar[a] * v[16 * q + e];
+            warp_reduce16(t, lane);
+            acc3.w[a][2 * hb + q] += t[0];
+          }
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < 32; ++e) {
+      float gsum = 0.f;
+#pragma unroll
+      for (int a = 0; a < MAXA; ++a)
+        if (a < L.out) gsum = fmaf(G.W3[a * 64 + 32 * hb + e], zbar[a], gsum);
+      d[e] *= gsum;
+    }
+    // two delta planes: chunks 4 hb .. 4 hb + 3 of row r
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      uint32_t w0[4], w1[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) split2(d[8 * c + 2 * i], d[8 * c + 2 * i + 1], w0[i], w1[i]);
+      *reinterpret_cast<uint4*>(G.Q + ((4 * hb + c) * 128 + G.r) * 16) = make_uint4(w0[0], w0[1], w0[2], w0[3]);
+      *reinterpret_cast<uint4*>(G.Q + HPL + ((4 * hb + c) * 128 + G.r) * 16) = make_uint4(w1[0], w1[1], w1[2], w1[3]);
+    }
+  }
+  if constexpr (WANT_DW) {
+#pragma unroll
+    for (int a = 0; a < MAXA; ++a)
+      if (a < L.out) {
+        float s = zbar[a];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        acc3.b[a] += s;
+      }
+  }
+}
+
+// delta2 planes -> delta1 = (delta2 . W2) * act'(pre1) (same planes, once the readers of delta2 retired) ->
+// input gradient dx[0 .. 15] (want_dx) and the weight-gradient MMAs of both layers (WANT_DW).
+template <bool WANT_DW>
+__device__ __forceinline__ void backprop(Grp& G, const NetL& L, bool want_dx, float* dx) {
+  using namespace tcf;
+  publish(G);
+  if (G.r == 0) {
+    umma::fence_after_sync();
+    issue_dw<4>(G.tmg + C_ACC, k_act(G.Q, HPL), mn_w(G.W2, W2PLANE), idesc_bf16(128, 64, false, true));
+    umma::commit(G.bc);
+  }
+  if constexpr (WANT_DW) {
+    if (G.r == 32) {
+      umma::fence_after_sync();
+      const Op A = mn_act(G.Q, HPL);
+      issue_wgrad(G.tmg + C_DW2, A, mn_act(G.P, HPL), idesc_bf16(128, 64, true, true), 2, G.fresh);
+      const Op one{smem_u32(G.ones), 0u, 128u, 256u, 0u};
+      issue_wgrad(G.tmg + C_DB2, A, one, idesc_bf16(128, 16, true, true), 1, G.fresh);
+      umma::commit(G.bd2);
+    }
+    G.d2_pending = true;
+  }
+  wait_c(G);
+  uint32_t w0[32], w1[32];                       // delta1 planes of this row, held until delta2's readers retired
+#pragma unroll
+  for (int hb = 0; hb < 2; ++hb) {
+    float v[32], d1[32];
+    {
+      uint32_t ra[32], rb[32];
+      tm_ld16(G.tm + C_ACC + 32 * hb, ra);
+      tm_ld16(G.tm + C_ACC + 32 * hb + 16, ra + 16);
+      tm_ld16(G.tm + C_D1 + 32 * hb, rb);
+      tm_ld16(G.tm + C_D1 + 32 * hb + 16, rb + 16);
+      tm_wait_ld();
+#pragma unroll
+      for (int e = 0; e < 32; ++e) { v[e] = __uint_as_float(ra[e]); d1[e] = __uint_as_float(rb[e]); }
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) split2(v[2 * i] * d1[2 * i], v[2 * i + 1] * d1[2 * i + 1], w0[16 * hb + i], w1[16 * hb + i]);
+  }
+  if (!WANT_DW && !want_dx) {
+    umma::fence_before_sync();
+    return;
+  }
+  wait_d2(G);                                    // dW2 / db2 have consumed delta2 (and the H1 planes)
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    *reinterpret_cast<uint4*>(G.Q + (c * 128 + G.r) * 16) = make_uint4(w0[4 * c], w0[4 * c + 1], w0[4 * c + 2], w0[4 * c + 3]);
+    *reinterpret_cast<uint4*>(G.Q + HPL + (c * 128 + G.r) * 16) = make_uint4(w1[4 * c], w1[4 * c + 1], w1[4 * c + 2], w1[4 * c + 3]);
+  }
+  publish(G);
+  if (want_dx && G.r == 0) {
+    umma::fence_after_sync();
+    issue_dw<4>(G.tmg + C_ACC, k_act(G.Q, HPL), mn_w(G.W1, W1PLANE), idesc_bf16(128, 16, false, true));
+    umma::commit(G.bc);
+  }
+  if constexpr (WANT_DW) {
+    if (G.r == 32) {
+      umma::fence_after_sync();
+      const Op A = mn_act(G.Q, HPL);
+      issue_wgrad(G.tmg + C_DW1, A, mn_act(G.Xp, XPL), idesc_bf16(128, 16, true, true), 2, G.fresh);
+      const Op one{smem_u32(G.ones), 0u, 128u, 256u, 0u};
+      issue_wgrad(G.tmg + C_DB1, A, one, idesc_bf16(128, 16, true, true), 1, G.fresh);
+      umma::commit(G.bd1);
+    }
+    G.d1_pending = true;
+    G.fresh = 0u;
+  }
+  if (want_dx) {
+    wait_c(G);
+    uint32_t rr[16];
+    tm_ld16(G.tm + C_ACC, rr);
+    tm_wait_ld();
+#pragma unroll
+    for (int f = 0; f < 16; ++f) dx[f] = __uint_as_float(rr[f]);
+    umma::fence_before_sync();
+  }
+}
+
+// TMEM weight-gradient accumulators -> the group's FP32 global partial (torch flat layout), then mark them fresh.
+// Lanes 0..63 hold the delta_b0 share of gradient row j = lane, lanes 64..127 the delta_b1 share of row lane - 64.
+__device__ __forceinline__ void flush(Grp& G, const NetL& L, float* __restrict__ part) {
+  wait_d2(G);
+  wait_d1(G);
+  if (G.fresh) return;                           // nothing accumulated since the last flush
+  float* S = reinterpret_cast<float*>(G.P);      // scratch [64][84]: the H1 planes are dead here
+  float w2[64], w1[16], bb[2];
+  {
+    uint32_t ra[64], rb[16], rc[16], rd[16];
+    tm_ld16(G.tm + C_DW2, ra); tm_ld16(G.tm + C_DW2 + 16, ra + 16);
+    tm_ld16(G.tm + C_DW2 + 32, ra + 32); tm_ld16(G.tm + C_DW2 + 48, ra + 48);
+    tm_ld16(G.tm + C_DW1, rb); tm_ld16(G.tm + C_DB2, rc); tm_ld16(G.tm + C_DB1, rd);
+    tm_wait_ld();
+#pragma unroll
+    for (int e = 0; e < 64; ++e) w2[e] = __uint_as_float(ra[e]);
+#pragma unroll
+    for (int e = 0; e < 16; ++e) w1[e] = __uint_as_float(rb[e]);
+    bb[0] = __uint_as_float(rc[0]); bb[1] = __uint_as_float(rd[0]);
+  }
+  umma::fence_before_sync();
+  if (G.r >= 64) {
+    float* row = S + (G.r - 64) * 84;
+#pragma unroll
+    for (int e4 = 0; e4 < 16; ++e4) *reinterpret_cast<float4*>(row + 4 * e4) = make_float4(w2[4 * e4], w2[4 * e4 + 1], w2[4 * e4 + 2], w2[4 * e4 + 3]);
+#pragma unroll
+    for (int e4 = 0; e4 < 4; ++e4) *reinterpret_cast<float4*>(row + 64 + 4 * e4) = make_float4(w1[4 * e4], w1[4 * e4 + 1], w1[4 * e4 + 2], w1[4 * e4 + 3]);
+    row[80] = bb[0]; row[81] = bb[1];
+  }
+  group_sync(G.g);
+  if (G.r < 64) {
+    const float* row = S + G.r * 84;
+    float* pw2 = part + L.g_w2 + G.r * 64;
+#pragma unroll
+    for (int e4 = 0; e4 < 16; ++e4) {
+      const float4 o = *reinterpret_cast<const float4*>(row + 4 * e4);
+      float4 c = *reinterpret_cast<float4*>(pw2 + 4 * e4);
+      c.x += w2[4 * e4] + o.x; c.y += w2[4 * e4 + 1] + o.y; c.z += w2[4 * e4 + 2] + o.z; c.w += w2[4 * e4 + 3] + o.w;
+      *reinterpret_cast<float4*>(pw2 + 4 * e4) = c;
+    }
+    float* pw1 = part + L.g_w1 + G.r * L.in;
+#pragma unroll
+    for (int k = 0; k < 16; ++k)
+      if (k < L.in) pw1[k] += w1[k] + row[64 + k];
+    part[L.g_b2 + G.r] += bb[0] + row[80];
+    part[L.g_b1 + G.r] += bb[1] + row[81];
+  }
+  group_sync(G.g);                               // the scratch is the next step's H1 planes
+  G.fresh = 1u;
+}
+
+}  // namespace tc2
+
+// ---------------------------------------------------------------------------------------------------------------
+// The kernel.  grid = min(#SM, ceil(#sub-tiles / 2)) CTAs of 256 threads, one CTA per SM (TMEM: 512 columns).
+// Slot s = 2 * blockIdx.x + group owns the contiguous sub-tile range [NSUB s / slots, NSUB (s + 1) / slots).
+// INFADP swaps weight blobs (policy <-> v_target <-> v) through the one staging buffer: those swap points are CTA-wide
+// barriers, so both groups run the same number of (possibly empty) sub-tile iterations; FHADP groups never meet.
+// ---------------------------------------------------------------------------------------------------------------
+template <class M, int ALG>
+__global__ void __launch_bounds__(tc2::NT2, 1) rollout_tc2_kernel(const __grid_constant__ KParams p) {
+  using namespace tc2;
+  static_assert(M::KIND == 0, "tcgen05 rollout kernel: state == obs models");
+  constexpr int NS = M::NS, alg = ALG;
+  extern __shared__ __align__(16) float smem[];
+  unsigned char* sm = reinterpret_cast<unsigned char*>(smem);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm);           // [0] weights, [1 + 3 g ..] group g: bc, bd2, bd1
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(sm + 128);
+  float* Wsm = reinterpret_cast<float*>(sm + HDR_BYTES);
+  unsigned char* ones = sm + HDR_BYTES + (size_t)p.w_floats * 4;
+  unsigned char* gbase = ones + tcf::ONES_B;
+  float* red = reinterpret_cast<float*>(gbase + NG * GROUP_BYTES);   // [NG][4 warps][MAXA * 64 + MAXA]
+
+  const int tid = threadIdx.x;
+  Grp G;
+  G.g = tid >> 7;
+  G.r = tid & 127;
+  G.P = gbase + G.g * GROUP_BYTES;
+  G.Q = G.P + P_BYTES;
+  G.Xp = G.Q + Q_BYTES;
+  G.ones = ones;
+  G.bc = bars + 1 + 3 * G.g; G.bd2 = G.bc + 1; G.bd1 = G.bc + 2;
+  G.pc = G.pd2 = G.pd1 = 0u;
+  G.fresh = 1u;
+  G.d2_pending = G.d1_pending = false;
+
+  if (tid == 0) {
+    for (int i = 0; i < 1 + 3 * NG; ++i) mbar_init(bars + i, 1);
+    fence_mbar_init();
+  }
+  {  // `ones`: [2 mn-groups][16 rows][8 bf16], feature 0 = 1.0
+    uint16_t* o16 = reinterpret_cast<uint16_t*>(ones);
+    o16[tid] = (tid < 128 && (tid & 7) == 0) ? (uint16_t)0x3f80 : (uint16_t)0;
+  }
+  if (tid < 32) umma::tmem_alloc(tslot, 512);
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  {
+    const uint32_t base = *tslot;
+    G.tmg = base + C_GROUP * G.g;
+    G.tm = G.tmg + ((uint32_t)(32 * ((G.r >> 5) & 3)) << 16);
+  }
+  uint32_t wphase = 0;
+  auto stage = [&](const float* gsrc, int floats) {      // CTA-wide: both groups call it at the same program points
+    __syncthreads();
+    if (tid == 0) {
+      fence_proxy_async();
+      const uint32_t bytes = (uint32_t)floats * 4u;
+      mbar_expect_tx(bars, bytes);
+      for (uint32_t off = 0; off < bytes; off += 32768u) {
+        const uint32_t n = bytes - off < 32768u ? bytes - off : 32768u;
+        tma_bulk_g2s(reinterpret_cast<char*>(Wsm) + off, reinterpret_cast<const char*>(gsrc) + off, n, bars);
+      }
+    }
+    mbar_wait(bars, wphase);
+    wphase ^= 1u;
+  };
+
+  const NetL& P = p.pol;
+  const NetL& V = p.val;
+  const int H = p.horizon, obs_dim = P.obs, TCH = p.tape_ch;
+  const long long B = p.batch;
+  const int slot = blockIdx.x * NG + G.g, slots = gridDim.x * NG;
+  float* part = p.partial + (size_t)slot * p.part_stride;
+  for (int i = G.r; i < p.part_stride; i += GT) part[i] = 0.f;
+  float* tape = p.tape + (size_t)slot * (size_t)H * TCH * GT;
+  Acc3 acc3;
+#pragma unroll
+  for (int a = 0; a < MAXA; ++a) {
+    acc3.b[a] = 0.f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) acc3.w[a][q] = 0.f;
+  }
+  float loss_acc = 0.f, vmean_acc = 0.f, done_acc = 0.f;
+
+  stage(p.blob_pol, P.blob);
+  bind(G, Wsm, P);
+
+  const long long nsub = (B + GT - 1) / GT;
+  const long long s0 = nsub * slot / slots, s1 = nsub * (slot + 1) / slots;
+  // INFADP: equal iteration counts for both groups of the CTA (stage() is a CTA-wide barrier)
+  long long iters = s1 - s0;
+  if (alg == ALG_PIM || alg == ALG_PEV) {
+    const long long o0 = nsub * (slot ^ 1) / slots, o1 = nsub * ((slot ^ 1) + 1) / slots;
+    iters = (o1 - o0) > iters ? (o1 - o0) : iters;
+  }
+
+  for (long long it = 0; it < iters; ++it) {
+    const long long sub = s0 + it;
+    const bool have = sub < s1;                   // false: idle iteration that only takes part in the blob swaps
+    const long long gs = sub * GT + G.r;
+    const bool valid = have && gs < B;
+    float st[NS], x[16];
+#pragma unroll
+    for (int f = 0; f < 16; ++f) x[f] = 0.f;
+#pragma unroll
+    for (int f = 0; f < NS; ++f) st[f] = (valid && f < obs_dim) ? p.obs[gs * obs_dim + f] : 0.f;
+    bool dn = valid ? (p.done[gs] != 0.f) : true;
+    float vacc = 0.f;
+
+    // ================================ forward sweep ================================
+    if (have) {
+      for (int k = 0; k < H; ++k) {
+        if (alg == ALG_FHADP || alg == ALG_PIM) {
+#pragma unroll
+          for (int f = 0; f < NS; ++f) tape[(k * TCH + f) * GT + G.r] = st[f];
+          tape[(k * TCH + NS) * GT + G.r] = dn ? 1.f : 0.f;
+        }
+#pragma unroll
+        for (int f = 0; f < NS; ++f)
+          if (f < obs_dim) x[f] = st[f];
+        if (P.time_input) x[P.in - 1] = (float)(k + 1);
+        float z[MAXA], a[MAXA], g[MAXA], apol[MAXA];
+        layer1<false>(G, P, x);
+        layer2_out(G, P, z);
+        if (alg == ALG_FHADP || alg == ALG_PIM) {
+#pragma unroll
+          for (int j = 0; j < MAXA; ++j)
+            if (j < P.out) tape[(k * TCH + NS + 1 + j) * GT + G.r] = z[j];
+        }
+        process_action(p, P.out, z, a, g, apol);
+        const bool active = valid && (p.mask_at_done ? !dn : true);
+        float r = 0.f;
+        if (valid) {
+          float in[NS];
+#pragma unroll
+          for (int f = 0; f < NS; ++f) in[f] = (p.obs_scaling && f < obs_dim) ? st[f] / p.osc[f] - p.osh[f] : st[f];
+          if (active) {
+            bool md = false;
+            const int reps = p.repeat_num > 0 ? p.repeat_num : 1;
+            float rsum = 0.f, rj = 0.f;
+            for (int j = 0; j < reps; ++j) {
+              M::step(p, in, a, rj, md);
+              rsum += rj;
+            }
+            r = (p.repeat_num > 0 && p.sum_reward) ? rsum : rj;
+            dn = md;
+          }
+#pragma unroll
+          for (int f = 0; f < NS; ++f) {
+            float o = (p.obs_scaling && f < obs_dim) ? (in[f] + p.osh[f]) * p.osc[f] : in[f];
+            if (p.clip_obs) o = fminf(fmaxf(o, p.obs_low[f]), p.obs_high[f]);
+            st[f] = o;
+          }
+          if (p.reward_shaping) r = (r + p.reward_shift) * p.reward_scale;
+          vacc += r * p.gpow[k];
+        }
+        if (alg == ALG_TRACE && valid) {
+          const size_t row = (size_t)k * B + gs;
+          if (p.tr_obs)
+            for (int f = 0; f < obs_dim; ++f) p.tr_obs[row * obs_dim + f] = st[f];
+          if (p.tr_act)
+            for (int j = 0; j < P.out; ++j) p.tr_act[row * P.out + j] = apol[j];
+          if (p.tr_rew) p.tr_rew[row] = r;
+          if (p.tr_done) p.tr_done[row] = dn ? 1.f : 0.f;
+        }
+      }
+      if (valid && dn) done_acc += 1.f;
+    }
+    if (alg == ALG_TRACE) continue;
+
+    // ============================ terminal value (INFADP) ============================
+    float lam[NS];
+#pragma unroll
+    for (int f = 0; f < NS; ++f) lam[f] = 0.f;
+    if (alg != ALG_FHADP) {
+      stage(p.blob_vtg, V.blob);
+      bind(G, Wsm, V);
+      if (have) {
+        const float gn = p.gpow[H];
+        const bool term = valid && !dn;
+#pragma unroll
+        for (int f = 0; f < 16; ++f) x[f] = (f < NS && f < obs_dim) ? st[f < NS ? f : 0] : 0.f;
+        float zv[MAXA], zb[MAXA], dx[16];
+#pragma unroll
+        for (int j = 0; j < MAXA; ++j) zb[j] = 0.f;
+        if (alg == ALG_PIM) {
+          zb[0] = term ? -gn * p.inv_B : 0.f;
+          layer1<true>(G, V, x);
+          layer2_back<false>(G, V, zb, zv, acc3);
+          backprop<false>(G, V, true, dx);
+          if (term) {
+#pragma unroll
+            for (int f = 0; f < NS; ++f)
+              if (f < obs_dim) lam[f] = dx[f];
+          }
+        } else {
+          layer1<false>(G, V, x);
+          layer2_out(G, V, zv);
+        }
+        if (term) vacc += gn * zv[0];
+      }
+    }
+
+    if (alg == ALG_PEV) {
+      // loss_v = mean((v(o_0) - backup)^2), gradient w.r.t. the value net only
+      stage(p.blob_val, V.blob);
+      bind(G, Wsm, V);
+      if (have) {
+#pragma unroll
+        for (int f = 0; f < 16; ++f) x[f] = (valid && f < obs_dim) ? p.obs[gs * obs_dim + f] : 0.f;
+        float zv[MAXA], zb[MAXA], dx[16];
+#pragma unroll
+        for (int j = 0; j < MAXA; ++j) zb[j] = 0.f;
+        // the output adjoint needs v(o_0) first: forward to the output, then recompute layer 2 fused with the backward
+        layer1<true>(G, V, x);
+        layer2_out(G, V, zv);
+        if (valid) {
+          const float diff = zv[0] - vacc;
+          loss_acc += diff * diff * p.inv_B;
+          vmean_acc += zv[0] * p.inv_B;
+          zb[0] = 2.f * diff * p.inv_B;
+        }
+        layer2_back<true>(G, V, zb, nullptr, acc3);
+        backprop<true>(G, V, false, dx);
+        flush(G, V, part);
+      }
+      stage(p.blob_pol, P.blob);
+      bind(G, Wsm, P);
+      continue;
+    }
+
+    if (valid) loss_acc += -vacc * p.inv_B;
+    if (alg == ALG_PIM) {
+      stage(p.blob_pol, P.blob);
+      bind(G, Wsm, P);
+    }
+    if (!have) continue;
+
+    // ================================ reverse sweep ================================
+    for (int k = H - 1; k >= 0; --k) {
+#pragma unroll
+      for (int f = 0; f < NS; ++f) st[f] = tape[(k * TCH + f) * GT + G.r];
+      const bool dnk = tape[(k * TCH + NS) * GT + G.r] != 0.f;
+#pragma unroll
+      for (int f = 0; f < NS; ++f)
+        if (f < obs_dim) x[f] = st[f];
+      if (P.time_input) x[P.in - 1] = (float)(k + 1);
+      layer1<true>(G, P, x);                      // recompute: issue early, the adjoint below overlaps the MMA
+      const bool active = valid && (p.mask_at_done ? !dnk : true);
+      float zb[MAXA];
+#pragma unroll
+      for (int j = 0; j < MAXA; ++j) zb[j] = 0.f;
+      if (active) {
+        float z[MAXA], a[MAXA], g[MAXA], abar[MAXA];
+#pragma unroll
+        for (int j = 0; j < MAXA; ++j) z[j] = j < P.out ? tape[(k * TCH + NS + 1 + j) * GT + G.r] : 0.f;
+        process_action(p, P.out, z, a, g, nullptr);
+        const float rho = -p.gpow[k] * p.inv_B * (p.reward_shaping ? p.reward_scale : 1.f);
+#pragma unroll
+        for (int j = 0; j < MAXA; ++j) abar[j] = 0.f;
+        // lam = adjoint of the OUTER observation obs_{k+1}.  Chain of step k:
+        //   obs_k -(1/scale, -shift)-> inner_0 -[model step x reps, same action]-> inner_reps
+        //         -(+shift, *scale)-> clip -> obs_{k+1}
+        const int reps = p.repeat_num > 0 ? p.repeat_num : 1;
+        float in0[NS], cur[NS];
+#pragma unroll
+        for (int f = 0; f < NS; ++f) in0[f] = (p.obs_scaling && f < obs_dim) ? st[f] / p.osc[f] - p.osh[f] : st[f];
+        if (p.clip_obs) {            // clip passes gradient only where the raw next observation is inside
+          float rr;
+          bool md;
+#pragma unroll
+          for (int f = 0; f < NS; ++f) cur[f] = in0[f];
+          for (int j = 0; j < reps; ++j) M::step(p, cur, a, rr, md);
+#pragma unroll
+          for (int f = 0; f < NS; ++f) {
+            const float o = (p.obs_scaling && f < obs_dim) ? (cur[f] + p.osh[f]) * p.osc[f] : cur[f];
+            if (o < p.obs_low[f] || o > p.obs_high[f]) lam[f] = 0.f;
+          }
+        }
+        if (p.obs_scaling) {
+#pragma unroll
+          for (int f = 0; f < NS; ++f)
+            if (f < obs_dim) lam[f] *= p.osc[f];
+        }
+        for (int j = reps - 1; j >= 0; --j) {
+          float rr, aj[MAXA];
+          bool md;
+#pragma unroll
+          for (int f = 0; f < NS; ++f) cur[f] = in0[f];
+          for (int q = 0; q < j; ++q) M::step(p, cur, a, rr, md);      // state before repeat j
+          const float rho_j = (p.repeat_num == 0 || p.sum_reward || j == reps - 1) ? rho : 0.f;
+#pragma unroll
+          for (int q = 0; q < MAXA; ++q) aj[q] = 0.f;
+          M::step_bwd(p, cur, a, rho_j, lam, aj);
+#pragma unroll
+          for (int q = 0; q < MAXA; ++q) abar[q] += aj[q];
+        }
+        if (p.obs_scaling) {
+#pragma unroll
+          for (int f = 0; f < NS; ++f)
+            if (f < obs_dim) lam[f] /= p.osc[f];
+        }
+#pragma unroll
+        for (int j = 0; j < MAXA; ++j) zb[j] = abar[j] * g[j];
+      }
+      float dx[16];
+      layer2_back<true>(G, P, zb, nullptr, acc3);
+      backprop<true>(G, P, k > 0, dx);
+      if (active && k > 0) {
+#pragma unroll
+        for (int f = 0; f < NS; ++f)
+          if (f < obs_dim) lam[f] += dx[f];
+      }
+      if ((H - k) % FLUSH_EVERY == 0 || k == 0) flush(G, P, part);
+    }
+  }
+
+  // ============================ per-group partials ============================
+  if (alg != ALG_TRACE) {
+    tc2::wait_d2(G);
+    tc2::wait_d1(G);
+    const NetL& U = (alg == ALG_PEV) ? V : P;
+    const int lane = G.r & 31, w = G.r >> 5;
+    float* rg = red + (size_t)G.g * 4 * (MAXA * 64 + MAXA);
+    for (int a = 0; a < U.out; ++a) {
+      if ((lane & 1) == 0) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) rg[w * (MAXA * 64 + MAXA) + a * 64 + 16 * q + tcf::col16(lane)] = acc3.w[a][q];
+      }
+      if (lane == 0) rg[w * (MAXA * 64 + MAXA) + MAXA * 64 + a] = acc3.b[a];
+    }
+    group_sync(G.g);
+    const int stride = MAXA * 64 + MAXA;
+    for (int i = G.r; i < U.out * 64; i += GT) {
+      const int a = i >> 6, j = i & 63;
+      part[U.g_w3 + i] = (rg[a * 64 + j] + rg[stride + a * 64 + j]) + (rg[2 * stride + a * 64 + j] + rg[3 * stride + a * 64 + j]);
+    }
+    if (G.r < U.out)
+      part[U.g_b3 + G.r] = (rg[MAXA * 64 + G.r] + rg[stride + MAXA * 64 + G.r]) +
+                           (rg[2 * stride + MAXA * 64 + G.r] + rg[3 * stride + MAXA * 64 + G.r]);
+    group_sync(G.g);
+  }
+  {  // the three scalars of the group (fixed order)
+    float* sc = reinterpret_cast<float*>(G.P);
+    sc[G.r] = loss_acc; sc[GT + G.r] = vmean_acc; sc[2 * GT + G.r] = done_acc;
+    group_sync(G.g);
+    if (G.r < 3) {
+      const int nparam = (alg == ALG_PEV) ? V.nparam : P.nparam;
+      float s = 0.f;
+      for (int i = 0; i < GT; ++i) s += sc[G.r * GT + i];
+      part[nparam + G.r] = s;
+    }
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  if (tid < 32) umma::tmem_dealloc(*tslot, 512);
+}
+
+}  // namespace gops
