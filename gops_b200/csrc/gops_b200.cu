@@ -421,7 +421,7 @@ int launch_rollout(gops_b200_plan* pl, const gops_b200_batch* b, int alg, cudaSt
     const int rows = v1 ? 1 : tc2::NG;             // gradient partial rows (= independent groups) per CTA
     const long long want = (subtiles + rows - 1) / rows;
     const int grid = (int)(want < slots ? want : slots);
-    if (ensure_scratch(pl, grid, NT, k2.horizon, rows)) return 1;
+    if (ensure_scratch(pl, grid, v1 ? NT : tc2::NG * tc2::GT, k2.horizon, rows)) return 1;   // tape columns per CTA
     k2.tape = pl->tape;
     k2.ext_ref = pl->ext_ref;
     k2.xbuf = pl->xbuf;

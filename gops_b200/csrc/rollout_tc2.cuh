@@ -1,18 +1,22 @@
-// Pipelined tcgen05 / TMEM rollout kernel (64-wide nets, <= 16 inputs, state == obs models): TWO INDEPENDENT 128-thread
+// Pipelined tcgen05 / TMEM rollout kernel (64-wide nets, <= 16 inputs, state == obs models): TWO INDEPENDENT 256-thread
 // groups per CTA, each owning one 128-sample sub-tile at a time.
 //
-//   thread = sample = TMEM lane.  A thread keeps its sample's model state and adjoint in registers for the whole
-//   horizon, writes its own observation row into the bf16x3 operand planes, reads its own accumulator row back
-//   (tcgen05.ld 32x32b: lane = row), applies bias / activation / output layer for all 64 columns and multiplies its own
-//   deltas: no observation / action tiles in shared memory, no cross-thread exchange, no CTA barrier in the sweeps.
-//   The only collective steps are the group's 128-thread named barrier in front of each MMA issue and the reductions
-//   over samples, which run on the tensor core (dW1, db1, dW2, db2: contraction over the 128 samples with the
+//   row = sample = TMEM lane.  Each sample row is served by a thread PAIR (h = 0 owner, h = 1 helper; both sit on the
+//   row's TMEM lane quarter).  The owner keeps the sample's model state and adjoint in registers for the whole
+//   horizon, runs the dynamics / adjoint and writes the observation row straight into the bf16x3 operand planes; owner
+//   and helper each read their 32 accumulator columns of the row back (tcgen05.ld 32x32b: lane = row), apply bias /
+//   activation / output layer and multiply their deltas.  No observation / action tiles in shared memory; the only
+//   exchange is the helper's half of the output dot product and the owner's output adjoint (2 KB per group).
+//   The reductions over samples run on the tensor core (dW1, db1, dW2, db2: contraction over the 128 samples with the
 //   MN-major view of the same operand planes) or as warp shuffles (dW3, db3).
 //
 //   While one group waits for its MMA round trip (issue -> tensor pipe -> commit -> mbarrier), the other group's
 //   warps run their epilogue or dynamics: the two groups are never synchronised with each other (FHADP), so the tensor
 //   pipe and the CUDA cores overlap without any software pipelining.  Round 1's kernel marched all 512 threads through
 //   five issue -> wait -> epilogue round trips of ONE sub-tile (tensor pipe 17 % busy, issue slots 43 % busy).
+//   MMA issue is warp-uniform (group / warp ids come from __shfl_sync so that the descriptors live in uniform
+//   registers; one elected lane issues): the first version issued from `if (thread == 0)` and ptxas wrapped every
+//   UTCHMMA in a 9-instruction ELECT / R2UR.BROADCAST waterfall loop on the critical path.
 //
 // Arithmetic (unchanged bars: loss 1e-4, gradient 2e-4 against the CPU oracle):
 //   layer products        x . W^T      BF16x3 x BF16x3, six terms (FP32-accurate; the loss depends on these)
@@ -23,7 +27,8 @@
 //
 // Shared memory (C1: 221 KB of 227): weights 31.5 KB (TMA-staged, shared by both groups) + per group: H1 planes 48 KB,
 // delta planes 32 KB (delta2, then delta1 in the same buffer once the MMAs reading delta2 have retired), observation
-// planes 12 KB.  TMEM: 240 of 256 columns per group (ACC 64 | act'(layer 1) 64 | dW2 64 | db2 16 | dW1 16 | db1 16).
+// planes 12 KB, exchange 2 KB.  TMEM: 240 of 256 columns per group (ACC 64 | act'(layer 1) 64 | dW2 64 | db2 16 |
+// dW1 16 | db1 16).
 #pragma once
 #include "models.cuh"
 #include "mlp_tc_full.cuh"
@@ -31,21 +36,28 @@
 namespace gops {
 namespace tc2 {
 
-constexpr int GT = 128;                 // threads per group = samples per sub-tile = UMMA M
+constexpr int GT = 128;                 // rows (= samples) per sub-tile = UMMA M
+constexpr int GTH = 256;                // threads per group: owner half (h = 0) + helper half (h = 1)
 constexpr int NG = 2;                   // groups per CTA
-constexpr int NT2 = GT * NG;
+constexpr int NT2 = GTH * NG;
 constexpr uint32_t C_ACC = 0, C_D1 = 64, C_DW2 = 128, C_DB2 = 192, C_DW1 = 208, C_DB1 = 224, C_GROUP = 256;
 constexpr int HPL = tcf::HPLANE, XPL = tcf::XPLANE;
 constexpr int P_BYTES = 3 * HPL, Q_BYTES = 2 * HPL, XP_BYTES = 3 * XPL;
-constexpr int GROUP_BYTES = P_BYTES + Q_BYTES + XP_BYTES;
+constexpr int XCH_BYTES = 2 * GT * MAXA * 4;   // helper -> owner output partials | owner -> helper output adjoints
+constexpr int GROUP_BYTES = P_BYTES + Q_BYTES + XP_BYTES + XCH_BYTES;
 constexpr int FLUSH_EVERY = 4;          // horizon steps between flushes of the TMEM weight-gradient accumulators
 constexpr int HDR_BYTES = 256;
 
 __host__ __device__ inline size_t smem_bytes(int w_floats) {
-  return HDR_BYTES + (size_t)w_floats * 4 + tcf::ONES_B + (size_t)NG * GROUP_BYTES + NG * 4 * (MAXA * 64 + MAXA) * 4;
+  return HDR_BYTES + (size_t)w_floats * 4 + tcf::ONES_B + (size_t)NG * GROUP_BYTES;
 }
 
-__device__ __forceinline__ void group_sync(int g) { asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory"); }
+__device__ __forceinline__ void group_sync(int g) { asm volatile("bar.sync %0, 256;" ::"r"(1 + g) : "memory"); }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}\n" : "=r"(pred));
+  return pred != 0;
+}
 
 // 16 accumulator columns of this thread's lane, WITHOUT waiting (issue several, then tm_wait_ld once)
 __device__ __forceinline__ void tm_ld16(uint32_t taddr, uint32_t* r) {
@@ -78,9 +90,10 @@ __device__ __forceinline__ void split2(float x0, float x1, uint32_t& p0, uint32_
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(p1) : "f"(r1), "f"(r0));
 }
 
-// Per-thread view of its group's resources
+// Per-thread view of its group's resources.  g, h, wg are warp-uniform (derived from a __shfl_sync'ed warp id).
 struct Grp {
   unsigned char *P, *Q, *Xp;        // H1 planes (3), delta planes (2), observation planes (3)
+  float *zp, *zb;                   // exchange: helper -> owner output partials [128][MAXA]; owner -> helper adjoints
   const unsigned char* ones;
   uint64_t *bc, *bd2, *bd1;         // mbarriers: critical-path MMA groups / dW2+db2 / dW1+db1
   uint32_t pc, pd2, pd1;            // their phases
@@ -88,7 +101,7 @@ struct Grp {
   uint32_t tmg;                     // TMEM address lane 0, column 0 of the group (MMA destinations)
   uint32_t fresh;                   // 1: the next weight-gradient MMAs overwrite their accumulators
   bool d2_pending, d1_pending;      // weight-gradient MMA groups in flight (their operand planes must not be rewritten)
-  int g, r;                         // group, row (= thread in group = sample of the sub-tile)
+  int g, h, wg, r;                  // group, half (0 owner / 1 helper), warp in group, row (= sample of the sub-tile)
   // staged weights of the network in use
   const unsigned char *W1, *W2;
   const float *W3, *b1, *b2, *b3;
@@ -130,20 +143,21 @@ __device__ __forceinline__ void issue_dw(uint32_t d, const tcf::Op& A, const tcf
 #pragma unroll
   for (int ks = 0; ks < KS; ++ks) mma_bf16(d, a0 + ks * ka, b0 + ks * kb, idesc, 1u);
 }
-// D (+)= [A_b0 | A_b1]^T (M = 128 stacked, MN-major) . (B_b0 + .. + B_b{bplanes-1}), 8 steps of 16 samples
-__device__ __forceinline__ void issue_wgrad(uint32_t d, const tcf::Op& A, const tcf::Op& B, uint32_t idesc, int bplanes,
-                                            uint32_t fresh) {
+// D (+)= [A_b0 | A_b1]^T (M = 128 stacked, MN-major) . (B_b0 + .. + B_b{BP-1}), 8 steps of 16 samples
+template <int BP>
+__device__ __forceinline__ void issue_wgrad(uint32_t d, const tcf::Op& A, const tcf::Op& B, uint32_t idesc, uint32_t fresh) {
   using namespace tcf;
   const uint64_t a01 = dsc(A, 0), ka = A.kadv >> 4, kb = B.kadv >> 4;
-  for (int p = bplanes - 1; p >= 0; --p) {
+#pragma unroll
+  for (int p = BP - 1; p >= 0; --p) {
     const uint64_t b = dsc(B, p);
 #pragma unroll
     for (int ks = 0; ks < 8; ++ks)
-      mma_bf16(d, a01 + ks * ka, b + ks * kb, idesc, (fresh && p == bplanes - 1 && ks == 0) ? 0u : 1u);
+      mma_bf16(d, a01 + ks * ka, b + ks * kb, idesc, (p == BP - 1 && ks == 0) ? (fresh ? 0u : 1u) : 1u);
   }
 }
 
-// this thread's input row (K1 = 16 values, zero padded) -> the three observation planes
+// owner: this row's input (K1 = 16 values, zero padded) -> the three observation planes
 __device__ __forceinline__ void write_x_row(const Grp& G, const float* x) {
   using namespace tcf;
 #pragma unroll
@@ -157,198 +171,244 @@ __device__ __forceinline__ void write_x_row(const Grp& G, const float* x) {
   }
 }
 
-// layer 1: X planes . W1^T -> accumulator; epilogue: + b1, activation -> H1 planes (FULL: act' parked in TMEM)
-template <bool FULL>
-__device__ __forceinline__ void layer1(Grp& G, const NetL& L, const float* x) {
+// layer 1, first half: observation planes . W1^T issued; the caller may overlap work with the MMA before layer1_finish
+__device__ __forceinline__ void layer1_issue(Grp& G, const float* x) {
   using namespace tcf;
   wait_d1(G);                                   // the dW1 MMAs of the previous step still read the X planes
-  write_x_row(G, x);
+  if (G.h == 0) write_x_row(G, x);
   publish(G);
-  if (G.r == 0) {
-    umma::fence_after_sync();
-    issue6<1>(G.tmg + C_ACC, k_act(G.Xp, XPL), k_w(G.W1, W1PLANE), idesc_bf16(128, 64, false, false));
-    umma::commit(G.bc);
+  if (G.wg == 0) {
+    if (elect_one()) {
+      umma::fence_after_sync();
+      issue6<1>(G.tmg + C_ACC, k_act(G.Xp, XPL), k_w(G.W1, W1PLANE), idesc_bf16(128, 64, false, false));
+      umma::commit(G.bc);
+    }
   }
-  wait_d2(G);                                   // ... and the dW2 MMAs the H1 planes
+}
+// layer 1, second half: + b1, activation -> this thread's 32 columns of the H1 planes (FULL: act' parked in TMEM).
+// Two rolled passes of 16 columns: half the code and half the registers of one 32-column pass (the kernel is
+// instruction-fetch sensitive: 8 warps per SM sub-partition pair run different phases of a long straight-line body).
+template <bool FULL>
+__device__ __forceinline__ void layer1_finish(Grp& G, const NetL& L) {
+  using namespace tcf;
+  wait_d2(G);                                   // the dW2 MMAs of the previous step still read the H1 planes
   wait_c(G);
-#pragma unroll
-  for (int hb = 0; hb < 2; ++hb) {
-    float v[32], d[32];
-    tm_ld32(G.tm + C_ACC + 32 * hb, v);
+#pragma unroll 1
+  for (int cb = 0; cb < 2; ++cb) {
+    const int c16 = 2 * G.h + cb;               // 16-column block of the row
+    float v[16], d[16];
+    umma::tmem_ld16(G.tm + C_ACC + 16 * c16, v);
+    const float* bias = G.b1 + 16 * c16;
 #define GOPS_TC2_A1(A)                                                      \
-  _Pragma("unroll") for (int e = 0; e < 32; ++e) {                          \
-    const float pre = v[e] + G.b1[32 * hb + e];                             \
+  _Pragma("unroll") for (int e = 0; e < 16; ++e) {                          \
+    const float pre = v[e] + bias[e];                                       \
     if constexpr (FULL) act_fwd_grad_t<A>(pre, v[e], d[e]);                 \
     else v[e] = act_fwd_t<A>(pre);                                          \
   }
     GOPS_ACT_SWITCH(L.hact, GOPS_TC2_A1)
 #undef GOPS_TC2_A1
-    store16(G.P, HPL, 2 * hb, G.r, v);
-    store16(G.P, HPL, 2 * hb + 1, G.r, v + 16);
-    if constexpr (FULL) tm_st32(G.tm + C_D1 + 32 * hb, d);
+    store16(G.P, HPL, c16, G.r, v);
+    if constexpr (FULL) umma::tmem_st16(G.tm + C_D1 + 16 * c16, d);
   }
   if constexpr (FULL) umma::tmem_wait_st();
 }
 
-// layer 2 + output layer, forward only: returns z[a] = b3[a] + W3[a] . act(H1 . W2^T + b2)
+// layer 2 + output layer, forward only: the owner gets z[a] = b3[a] + W3[a] . act(H1 . W2^T + b2)
 __device__ __forceinline__ void layer2_out(Grp& G, const NetL& L, float* z) {
   using namespace tcf;
   publish(G);
-  if (G.r == 0) {
-    umma::fence_after_sync();
-    issue6<4>(G.tmg + C_ACC, k_act(G.P, HPL), k_w(G.W2, W2PLANE), idesc_bf16(128, 64, false, false));
-    umma::commit(G.bc);
+  if (G.wg == 0) {
+    if (elect_one()) {
+      umma::fence_after_sync();
+      issue6<4>(G.tmg + C_ACC, k_act(G.P, HPL), k_w(G.W2, W2PLANE), idesc_bf16(128, 64, false, false));
+      umma::commit(G.bc);
+    }
   }
-#pragma unroll
-  for (int a = 0; a < MAXA; ++a) z[a] = a < L.out ? G.b3[a] : 0.f;
   wait_c(G);
+  float zp[MAXA];
 #pragma unroll
-  for (int hb = 0; hb < 2; ++hb) {
-    float v[32];
-    tm_ld32(G.tm + C_ACC + 32 * hb, v);
-#define GOPS_TC2_A2(A) \
-  _Pragma("unroll") for (int e = 0; e < 32; ++e) v[e] = act_fwd_t<A>(v[e] + G.b2[32 * hb + e]);
+  for (int a = 0; a < MAXA; ++a) zp[a] = 0.f;
+#pragma unroll 1
+  for (int cb = 0; cb < 2; ++cb) {
+    const int c16 = 2 * G.h + cb;
+    float v[16];
+    umma::tmem_ld16(G.tm + C_ACC + 16 * c16, v);
+    const float* bias = G.b2 + 16 * c16;
+#define GOPS_TC2_A2(A) _Pragma("unroll") for (int e = 0; e < 16; ++e) v[e] = act_fwd_t<A>(v[e] + bias[e]);
     GOPS_ACT_SWITCH(L.hact, GOPS_TC2_A2)
 #undef GOPS_TC2_A2
 #pragma unroll
     for (int a = 0; a < MAXA; ++a)
       if (a < L.out) {
-        const float* w = G.W3 + a * 64 + 32 * hb;
+        const float* w = G.W3 + a * 64 + 16 * c16;
         float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-        for (int e = 0; e < 32; e += 2) { s0 = fmaf(w[e], v[e], s0); s1 = fmaf(w[e + 1], v[e + 1], s1); }
-        z[a] += s0 + s1;
+        for (int e = 0; e < 16; e += 2) { s0 = fmaf(w[e], v[e], s0); s1 = fmaf(w[e + 1], v[e + 1], s1); }
+        zp[a] += s0 + s1;
       }
   }
+  if (G.h == 1) {
+#pragma unroll
+    for (int a = 0; a < MAXA; ++a)
+      if (a < L.out) G.zp[G.r * MAXA + a] = zp[a];
+  }
   umma::fence_before_sync();      // the accumulator reads are ordered before the next MMA group (issued after a barrier)
+  group_sync(G.g);
+  if (G.h == 0) {
+#pragma unroll
+    for (int a = 0; a < MAXA; ++a) z[a] = a < L.out ? G.b3[a] + (zp[a] + G.zp[G.r * MAXA + a]) : 0.f;
+  }
 }
 
 // Per-thread accumulators of the output-layer gradients: after the transposing warp reduction lane l holds the warp's
-// column sum of column 16 b + col16(l) in slot b; they are combined across warps once, at the end of the kernel.
+// column sum of column 32 h + 16 q + col16(l) in slot q; they are combined across warps once, at the end of the kernel.
 struct Acc3 {
-  float w[MAXA][4];
+  float w0[MAXA], w1[MAXA];
   float b[MAXA];
 };
 
-// layer 2 recompute fused with the start of the backward pass: z (if wanted), dW3 / db3 partial sums, and
-// delta2 = (W3^T zbar) * act'(pre2) -> the two delta planes.  zbar: this thread's output adjoint.
-template <bool WANT_DW>
+// layer 2 recompute fused with the start of the backward pass: z for the owner (WANT_Z), dW3 / db3 partial sums, and
+// delta2 = (W3^T zbar) * act'(pre2) -> this thread's 32 columns of the two delta planes.
+// zbar: the owner's output adjoint of its row (the helper receives it through shared memory).
+template <bool WANT_DW, bool WANT_Z>
 __device__ __forceinline__ void layer2_back(Grp& G, const NetL& L, const float* zbar, float* z, Acc3& acc3) {
   using namespace tcf;
-  publish(G);
-  if (G.r == 0) {
-    umma::fence_after_sync();
-    issue6<4>(G.tmg + C_ACC, k_act(G.P, HPL), k_w(G.W2, W2PLANE), idesc_bf16(128, 64, false, false));
-    umma::commit(G.bc);
-  }
-  if (z != nullptr) {
+  if (G.h == 0) {
 #pragma unroll
-    for (int a = 0; a < MAXA; ++a) z[a] = a < L.out ? G.b3[a] : 0.f;
+    for (int a = 0; a < MAXA; ++a)
+      if (a < L.out) G.zb[G.r * MAXA + a] = zbar[a];
   }
+  publish(G);
+  if (G.wg == 0) {
+    if (elect_one()) {
+      umma::fence_after_sync();
+      issue6<4>(G.tmg + C_ACC, k_act(G.P, HPL), k_w(G.W2, W2PLANE), idesc_bf16(128, 64, false, false));
+      umma::commit(G.bc);
+    }
+  }
+  float zb[MAXA];
+#pragma unroll
+  for (int a = 0; a < MAXA; ++a) zb[a] = a < L.out ? G.zb[G.r * MAXA + a] : 0.f;
   const int lane = G.r & 31;
   wait_c(G);
+  float zp[MAXA];
 #pragma unroll
-  for (int hb = 0; hb < 2; ++hb) {
-    float v[32], d[32];
-    tm_ld32(G.tm + C_ACC + 32 * hb, v);
-#define GOPS_TC2_A3(A) \
-  _Pragma("unroll") for (int e = 0; e < 32; ++e) act_fwd_grad_t<A>(v[e] + G.b2[32 * hb + e], v[e], d[e]);
+  for (int a = 0; a < MAXA; ++a) zp[a] = 0.f;
+#pragma unroll 1
+  for (int cb = 0; cb < 2; ++cb) {
+    const int c16 = 2 * G.h + cb;
+    float v[16], d[16];
+    umma::tmem_ld16(G.tm + C_ACC + 16 * c16, v);
+    const float* bias = G.b2 + 16 * c16;
+#define GOPS_TC2_A3(A) _Pragma("unroll") for (int e = 0; e < 16; ++e) act_fwd_grad_t<A>(v[e] + bias[e], v[e], d[e]);
     GOPS_ACT_SWITCH(L.hact, GOPS_TC2_A3)
 #undef GOPS_TC2_A3
-    if (z != nullptr) {
+    const float* w3 = G.W3 + 16 * c16;
+    if constexpr (WANT_Z) {
 #pragma unroll
       for (int a = 0; a < MAXA; ++a)
         if (a < L.out) {
-          const float* w = G.W3 + a * 64 + 32 * hb;
           float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-          for (int e = 0; e < 32; e += 2) { s0 = fmaf(w[e], v[e], s0); s1 = fmaf(w[e + 1], v[e + 1], s1); }
-          z[a] += s0 + s1;
+          for (int e = 0; e < 16; e += 2) { s0 = fmaf(w3[a * 64 + e], v[e], s0); s1 = fmaf(w3[a * 64 + e + 1], v[e + 1], s1); }
+          zp[a] += s0 + s1;
         }
     }
     if constexpr (WANT_DW) {
 #pragma unroll
       for (int a = 0; a < MAXA; ++a)
         if (a < L.out) {
+          float t[16];
 #pragma unroll
-          for (int q = 0; q < 2; ++q) {
-            float t[16];
-#pragma unroll
-            for (int e = 0; e < 16; ++e) t[e] = zbar[a] * v[16 * q + e];
-            warp_reduce16(t, lane);
-            acc3.w[a][2 * hb + q] += t[0];
-          }
+          for (int e = 0; e < 16; ++e) t[e] = zb[a] * v[e];
+          warp_reduce16(t, lane);
+          acc3.w0[a] += cb == 0 ? t[0] : 0.f;
+          acc3.w1[a] += cb == 0 ? 0.f : t[0];
         }
     }
 #pragma unroll
-    for (int e = 0; e < 32; ++e) {
+    for (int e = 0; e < 16; ++e) {
       float gsum = 0.f;
 #pragma unroll
       for (int a = 0; a < MAXA; ++a)
-        if (a < L.out) gsum = fmaf(G.W3[a * 64 + 32 * hb + e], zbar[a], gsum);
+        if (a < L.out) gsum = fmaf(w3[a * 64 + e], zb[a], gsum);
       d[e] *= gsum;
     }
-    // two delta planes: chunks 4 hb .. 4 hb + 3 of row r
+    // two delta planes: chunks 2 c16, 2 c16 + 1 of row r
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 0; c < 2; ++c) {
       uint32_t w0[4], w1[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) split2(d[8 * c + 2 * i], d[8 * c + 2 * i + 1], w0[i], w1[i]);
-      *reinterpret_cast<uint4*>(G.Q + ((4 * hb + c) * 128 + G.r) * 16) = make_uint4(w0[0], w0[1], w0[2], w0[3]);
-      *reinterpret_cast<uint4*>(G.Q + HPL + ((4 * hb + c) * 128 + G.r) * 16) = make_uint4(w1[0], w1[1], w1[2], w1[3]);
+      *reinterpret_cast<uint4*>(G.Q + ((2 * c16 + c) * 128 + G.r) * 16) = make_uint4(w0[0], w0[1], w0[2], w0[3]);
+      *reinterpret_cast<uint4*>(G.Q + HPL + ((2 * c16 + c) * 128 + G.r) * 16) = make_uint4(w1[0], w1[1], w1[2], w1[3]);
     }
   }
   if constexpr (WANT_DW) {
+    if (G.h == 0) {
 #pragma unroll
-    for (int a = 0; a < MAXA; ++a)
-      if (a < L.out) {
-        float s = zbar[a];
+      for (int a = 0; a < MAXA; ++a)
+        if (a < L.out) {
+          float sz = zb[a];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        acc3.b[a] += s;
-      }
+          for (int o = 16; o > 0; o >>= 1) sz += __shfl_xor_sync(0xffffffffu, sz, o);
+          acc3.b[a] += sz;
+        }
+    }
+  }
+  if constexpr (WANT_Z) {
+    if (G.h == 1) {
+#pragma unroll
+      for (int a = 0; a < MAXA; ++a)
+        if (a < L.out) G.zp[G.r * MAXA + a] = zp[a];
+    }
+    group_sync(G.g);
+    if (G.h == 0) {
+#pragma unroll
+      for (int a = 0; a < MAXA; ++a) z[a] = a < L.out ? G.b3[a] + (zp[a] + G.zp[G.r * MAXA + a]) : 0.f;
+    }
   }
 }
 
 // delta2 planes -> delta1 = (delta2 . W2) * act'(pre1) (same planes, once the readers of delta2 retired) ->
-// input gradient dx[0 .. 15] (want_dx) and the weight-gradient MMAs of both layers (WANT_DW).
+// input gradient dx[0 .. 15] for the owner (want_dx) and the weight-gradient MMAs of both layers (WANT_DW).
 template <bool WANT_DW>
 __device__ __forceinline__ void backprop(Grp& G, const NetL& L, bool want_dx, float* dx) {
   using namespace tcf;
   publish(G);
-  if (G.r == 0) {
-    umma::fence_after_sync();
-    issue_dw<4>(G.tmg + C_ACC, k_act(G.Q, HPL), mn_w(G.W2, W2PLANE), idesc_bf16(128, 64, false, true));
-    umma::commit(G.bc);
+  if (G.wg == 0) {
+    if (elect_one()) {
+      umma::fence_after_sync();
+      issue_dw<4>(G.tmg + C_ACC, k_act(G.Q, HPL), mn_w(G.W2, W2PLANE), idesc_bf16(128, 64, false, true));
+      umma::commit(G.bc);
+    }
   }
   if constexpr (WANT_DW) {
-    if (G.r == 32) {
-      umma::fence_after_sync();
-      const Op A = mn_act(G.Q, HPL);
-      issue_wgrad(G.tmg + C_DW2, A, mn_act(G.P, HPL), idesc_bf16(128, 64, true, true), 2, G.fresh);
-      const Op one{smem_u32(G.ones), 0u, 128u, 256u, 0u};
-      issue_wgrad(G.tmg + C_DB2, A, one, idesc_bf16(128, 16, true, true), 1, G.fresh);
-      umma::commit(G.bd2);
+    if (G.wg == 1) {
+      if (elect_one()) {
+        umma::fence_after_sync();
+        const Op A = mn_act(G.Q, HPL);
+        issue_wgrad<2>(G.tmg + C_DW2, A, mn_act(G.P, HPL), idesc_bf16(128, 64, true, true), G.fresh);
+        const Op one{smem_u32(G.ones), 0u, 128u, 256u, 0u};
+        issue_wgrad<1>(G.tmg + C_DB2, A, one, idesc_bf16(128, 16, true, true), G.fresh);
+        umma::commit(G.bd2);
+      }
     }
     G.d2_pending = true;
   }
   wait_c(G);
-  uint32_t w0[32], w1[32];                       // delta1 planes of this row, held until delta2's readers retired
+  uint32_t w0[16], w1[16];                       // delta1 planes of this thread's 32 columns, held until delta2's readers retired
+  {
+    uint32_t ra[32], rb[32];
+    tm_ld16(G.tm + C_ACC + 32 * G.h, ra);
+    tm_ld16(G.tm + C_ACC + 32 * G.h + 16, ra + 16);
+    tm_ld16(G.tm + C_D1 + 32 * G.h, rb);
+    tm_ld16(G.tm + C_D1 + 32 * G.h + 16, rb + 16);
+    tm_wait_ld();
 #pragma unroll
-  for (int hb = 0; hb < 2; ++hb) {
-    float v[32], d1[32];
-    {
-      uint32_t ra[32], rb[32];
-      tm_ld16(G.tm + C_ACC + 32 * hb, ra);
-      tm_ld16(G.tm + C_ACC + 32 * hb + 16, ra + 16);
-      tm_ld16(G.tm + C_D1 + 32 * hb, rb);
-      tm_ld16(G.tm + C_D1 + 32 * hb + 16, rb + 16);
-      tm_wait_ld();
-#pragma unroll
-      for (int e = 0; e < 32; ++e) { v[e] = __uint_as_float(ra[e]); d1[e] = __uint_as_float(rb[e]); }
-    }
-#pragma unroll
-    for (int i = 0; i < 16; ++i) split2(v[2 * i] * d1[2 * i], v[2 * i + 1] * d1[2 * i + 1], w0[16 * hb + i], w1[16 * hb + i]);
+    for (int i = 0; i < 16; ++i)
+      split2(__uint_as_float(ra[2 * i]) * __uint_as_float(rb[2 * i]),
+             __uint_as_float(ra[2 * i + 1]) * __uint_as_float(rb[2 * i + 1]), w0[i], w1[i]);
   }
   if (!WANT_DW && !want_dx) {
     umma::fence_before_sync();
@@ -356,85 +416,101 @@ __device__ __forceinline__ void backprop(Grp& G, const NetL& L, bool want_dx, fl
   }
   wait_d2(G);                                    // dW2 / db2 have consumed delta2 (and the H1 planes)
 #pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    *reinterpret_cast<uint4*>(G.Q + (c * 128 + G.r) * 16) = make_uint4(w0[4 * c], w0[4 * c + 1], w0[4 * c + 2], w0[4 * c + 3]);
-    *reinterpret_cast<uint4*>(G.Q + HPL + (c * 128 + G.r) * 16) = make_uint4(w1[4 * c], w1[4 * c + 1], w1[4 * c + 2], w1[4 * c + 3]);
+  for (int c = 0; c < 4; ++c) {
+    *reinterpret_cast<uint4*>(G.Q + ((4 * G.h + c) * 128 + G.r) * 16) = make_uint4(w0[4 * c], w0[4 * c + 1], w0[4 * c + 2], w0[4 * c + 3]);
+    *reinterpret_cast<uint4*>(G.Q + HPL + ((4 * G.h + c) * 128 + G.r) * 16) = make_uint4(w1[4 * c], w1[4 * c + 1], w1[4 * c + 2], w1[4 * c + 3]);
   }
   publish(G);
-  if (want_dx && G.r == 0) {
-    umma::fence_after_sync();
-    issue_dw<4>(G.tmg + C_ACC, k_act(G.Q, HPL), mn_w(G.W1, W1PLANE), idesc_bf16(128, 16, false, true));
-    umma::commit(G.bc);
+  if (want_dx) {
+    if (G.wg == 0) {
+      if (elect_one()) {
+        umma::fence_after_sync();
+        issue_dw<4>(G.tmg + C_ACC, k_act(G.Q, HPL), mn_w(G.W1, W1PLANE), idesc_bf16(128, 16, false, true));
+        umma::commit(G.bc);
+      }
+    }
   }
   if constexpr (WANT_DW) {
-    if (G.r == 32) {
-      umma::fence_after_sync();
-      const Op A = mn_act(G.Q, HPL);
-      issue_wgrad(G.tmg + C_DW1, A, mn_act(G.Xp, XPL), idesc_bf16(128, 16, true, true), 2, G.fresh);
-      const Op one{smem_u32(G.ones), 0u, 128u, 256u, 0u};
-      issue_wgrad(G.tmg + C_DB1, A, one, idesc_bf16(128, 16, true, true), 1, G.fresh);
-      umma::commit(G.bd1);
+    if (G.wg == 1) {
+      if (elect_one()) {
+        umma::fence_after_sync();
+        const Op A = mn_act(G.Q, HPL);
+        issue_wgrad<2>(G.tmg + C_DW1, A, mn_act(G.Xp, XPL), idesc_bf16(128, 16, true, true), G.fresh);
+        const Op one{smem_u32(G.ones), 0u, 128u, 256u, 0u};
+        issue_wgrad<1>(G.tmg + C_DB1, A, one, idesc_bf16(128, 16, true, true), G.fresh);
+        umma::commit(G.bd1);
+      }
     }
     G.d1_pending = true;
     G.fresh = 0u;
   }
   if (want_dx) {
     wait_c(G);
-    uint32_t rr[16];
-    tm_ld16(G.tm + C_ACC, rr);
-    tm_wait_ld();
+    if (G.h == 0) {
+      uint32_t rr[16];
+      tm_ld16(G.tm + C_ACC, rr);
+      tm_wait_ld();
 #pragma unroll
-    for (int f = 0; f < 16; ++f) dx[f] = __uint_as_float(rr[f]);
+      for (int f = 0; f < 16; ++f) dx[f] = __uint_as_float(rr[f]);
+    }
     umma::fence_before_sync();
   }
 }
 
 // TMEM weight-gradient accumulators -> the group's FP32 global partial (torch flat layout), then mark them fresh.
-// Lanes 0..63 hold the delta_b0 share of gradient row j = lane, lanes 64..127 the delta_b1 share of row lane - 64.
+// Lanes 0..63 hold the delta_b0 share of gradient row j = lane, lanes 64..127 the delta_b1 share of row lane - 64;
+// thread (h, r) moves columns [32 h, 32 h + 32) of dW2, the owner half also dW1 / db2 / db1.
 __device__ __forceinline__ void flush(Grp& G, const NetL& L, float* __restrict__ part) {
   wait_d2(G);
   wait_d1(G);
-  if (G.fresh) return;                           // nothing accumulated since the last flush
+  if (G.fresh) return;                           // nothing accumulated since the last flush (uniform over the group)
   float* S = reinterpret_cast<float*>(G.P);      // scratch [64][84]: the H1 planes are dead here
-  float w2[64], w1[16], bb[2];
+  float w2[32], w1[16], bb[2];
   {
-    uint32_t ra[64], rb[16], rc[16], rd[16];
-    tm_ld16(G.tm + C_DW2, ra); tm_ld16(G.tm + C_DW2 + 16, ra + 16);
-    tm_ld16(G.tm + C_DW2 + 32, ra + 32); tm_ld16(G.tm + C_DW2 + 48, ra + 48);
-    tm_ld16(G.tm + C_DW1, rb); tm_ld16(G.tm + C_DB2, rc); tm_ld16(G.tm + C_DB1, rd);
+    uint32_t ra[32], rb[16], rc[16], rd[16];
+    tm_ld16(G.tm + C_DW2 + 32 * G.h, ra);
+    tm_ld16(G.tm + C_DW2 + 32 * G.h + 16, ra + 16);
+    if (G.h == 0) { tm_ld16(G.tm + C_DW1, rb); tm_ld16(G.tm + C_DB2, rc); tm_ld16(G.tm + C_DB1, rd); }
     tm_wait_ld();
 #pragma unroll
-    for (int e = 0; e < 64; ++e) w2[e] = __uint_as_float(ra[e]);
+    for (int e = 0; e < 32; ++e) w2[e] = __uint_as_float(ra[e]);
 #pragma unroll
-    for (int e = 0; e < 16; ++e) w1[e] = __uint_as_float(rb[e]);
-    bb[0] = __uint_as_float(rc[0]); bb[1] = __uint_as_float(rd[0]);
+    for (int e = 0; e < 16; ++e) w1[e] = G.h == 0 ? __uint_as_float(rb[e]) : 0.f;
+    bb[0] = G.h == 0 ? __uint_as_float(rc[0]) : 0.f;
+    bb[1] = G.h == 0 ? __uint_as_float(rd[0]) : 0.f;
   }
   umma::fence_before_sync();
   if (G.r >= 64) {
     float* row = S + (G.r - 64) * 84;
 #pragma unroll
-    for (int e4 = 0; e4 < 16; ++e4) *reinterpret_cast<float4*>(row + 4 * e4) = make_float4(w2[4 * e4], w2[4 * e4 + 1], w2[4 * e4 + 2], w2[4 * e4 + 3]);
+    for (int e4 = 0; e4 < 8; ++e4)
+      *reinterpret_cast<float4*>(row + 32 * G.h + 4 * e4) = make_float4(w2[4 * e4], w2[4 * e4 + 1], w2[4 * e4 + 2], w2[4 * e4 + 3]);
+    if (G.h == 0) {
 #pragma unroll
-    for (int e4 = 0; e4 < 4; ++e4) *reinterpret_cast<float4*>(row + 64 + 4 * e4) = make_float4(w1[4 * e4], w1[4 * e4 + 1], w1[4 * e4 + 2], w1[4 * e4 + 3]);
-    row[80] = bb[0]; row[81] = bb[1];
+      for (int e4 = 0; e4 < 4; ++e4)
+        *reinterpret_cast<float4*>(row + 64 + 4 * e4) = make_float4(w1[4 * e4], w1[4 * e4 + 1], w1[4 * e4 + 2], w1[4 * e4 + 3]);
+      row[80] = bb[0]; row[81] = bb[1];
+    }
   }
   group_sync(G.g);
   if (G.r < 64) {
     const float* row = S + G.r * 84;
-    float* pw2 = part + L.g_w2 + G.r * 64;
+    float* pw2 = part + L.g_w2 + G.r * 64 + 32 * G.h;
 #pragma unroll
-    for (int e4 = 0; e4 < 16; ++e4) {
-      const float4 o = *reinterpret_cast<const float4*>(row + 4 * e4);
+    for (int e4 = 0; e4 < 8; ++e4) {
+      const float4 o = *reinterpret_cast<const float4*>(row + 32 * G.h + 4 * e4);
       float4 c = *reinterpret_cast<float4*>(pw2 + 4 * e4);
       c.x += w2[4 * e4] + o.x; c.y += w2[4 * e4 + 1] + o.y; c.z += w2[4 * e4 + 2] + o.z; c.w += w2[4 * e4 + 3] + o.w;
       *reinterpret_cast<float4*>(pw2 + 4 * e4) = c;
     }
-    float* pw1 = part + L.g_w1 + G.r * L.in;
+    if (G.h == 0) {
+      float* pw1 = part + L.g_w1 + G.r * L.in;
 #pragma unroll
-    for (int k = 0; k < 16; ++k)
-      if (k < L.in) pw1[k] += w1[k] + row[64 + k];
-    part[L.g_b2 + G.r] += bb[0] + row[80];
-    part[L.g_b1 + G.r] += bb[1] + row[81];
+      for (int k = 0; k < 16; ++k)
+        if (k < L.in) pw1[k] += w1[k] + row[64 + k];
+      part[L.g_b2 + G.r] += bb[0] + row[80];
+      part[L.g_b1 + G.r] += bb[1] + row[81];
+    }
   }
   group_sync(G.g);                               // the scratch is the next step's H1 planes
   G.fresh = 1u;
@@ -443,7 +519,7 @@ __device__ __forceinline__ void flush(Grp& G, const NetL& L, float* __restrict__
 }  // namespace tc2
 
 // ---------------------------------------------------------------------------------------------------------------
-// The kernel.  grid = min(#SM, ceil(#sub-tiles / 2)) CTAs of 256 threads, one CTA per SM (TMEM: 512 columns).
+// The kernel.  grid = min(#SM, ceil(#sub-tiles / 2)) CTAs of 512 threads, one CTA per SM (TMEM: 512 columns).
 // Slot s = 2 * blockIdx.x + group owns the contiguous sub-tile range [NSUB s / slots, NSUB (s + 1) / slots).
 // INFADP swaps weight blobs (policy <-> v_target <-> v) through the one staging buffer: those swap points are CTA-wide
 // barriers, so both groups run the same number of (possibly empty) sub-tile iterations; FHADP groups never meet.
@@ -460,37 +536,42 @@ __global__ void __launch_bounds__(tc2::NT2, 1) rollout_tc2_kernel(const __grid_c
   float* Wsm = reinterpret_cast<float*>(sm + HDR_BYTES);
   unsigned char* ones = sm + HDR_BYTES + (size_t)p.w_floats * 4;
   unsigned char* gbase = ones + tcf::ONES_B;
-  float* red = reinterpret_cast<float*>(gbase + NG * GROUP_BYTES);   // [NG][4 warps][MAXA * 64 + MAXA]
 
   const int tid = threadIdx.x;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);      // warp-uniform by construction (uniform-register MMA issue)
   Grp G;
-  G.g = tid >> 7;
-  G.r = tid & 127;
+  G.g = warp >> 3;
+  G.wg = warp & 7;
+  G.h = G.wg >> 2;
+  G.r = 32 * (G.wg & 3) + (tid & 31);
   G.P = gbase + G.g * GROUP_BYTES;
   G.Q = G.P + P_BYTES;
   G.Xp = G.Q + Q_BYTES;
+  G.zp = reinterpret_cast<float*>(G.Xp + XP_BYTES);
+  G.zb = G.zp + GT * MAXA;
   G.ones = ones;
   G.bc = bars + 1 + 3 * G.g; G.bd2 = G.bc + 1; G.bd1 = G.bc + 2;
   G.pc = G.pd2 = G.pd1 = 0u;
   G.fresh = 1u;
   G.d2_pending = G.d1_pending = false;
+  const bool own = G.h == 0;
 
   if (tid == 0) {
     for (int i = 0; i < 1 + 3 * NG; ++i) mbar_init(bars + i, 1);
     fence_mbar_init();
   }
-  {  // `ones`: [2 mn-groups][16 rows][8 bf16], feature 0 = 1.0
+  if (tid < 256) {  // `ones`: [2 mn-groups][16 rows][8 bf16], feature 0 = 1.0
     uint16_t* o16 = reinterpret_cast<uint16_t*>(ones);
     o16[tid] = (tid < 128 && (tid & 7) == 0) ? (uint16_t)0x3f80 : (uint16_t)0;
   }
-  if (tid < 32) umma::tmem_alloc(tslot, 512);
+  if (warp == 0) umma::tmem_alloc(tslot, 512);
   umma::fence_before_sync();
   __syncthreads();
   umma::fence_after_sync();
   {
-    const uint32_t base = *tslot;
+    const uint32_t base = __shfl_sync(0xffffffffu, *tslot, 0);
     G.tmg = base + C_GROUP * G.g;
-    G.tm = G.tmg + ((uint32_t)(32 * ((G.r >> 5) & 3)) << 16);
+    G.tm = G.tmg + ((uint32_t)(32 * (G.wg & 3)) << 16);
   }
   uint32_t wphase = 0;
   auto stage = [&](const float* gsrc, int floats) {      // CTA-wide: both groups call it at the same program points
@@ -514,15 +595,11 @@ __global__ void __launch_bounds__(tc2::NT2, 1) rollout_tc2_kernel(const __grid_c
   const long long B = p.batch;
   const int slot = blockIdx.x * NG + G.g, slots = gridDim.x * NG;
   float* part = p.partial + (size_t)slot * p.part_stride;
-  for (int i = G.r; i < p.part_stride; i += GT) part[i] = 0.f;
+  for (int i = G.h * GT + G.r; i < p.part_stride; i += GTH) part[i] = 0.f;
   float* tape = p.tape + (size_t)slot * (size_t)H * TCH * GT;
   Acc3 acc3;
 #pragma unroll
-  for (int a = 0; a < MAXA; ++a) {
-    acc3.b[a] = 0.f;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) acc3.w[a][q] = 0.f;
-  }
+  for (int a = 0; a < MAXA; ++a) acc3.w0[a] = acc3.w1[a] = acc3.b[a] = 0.f;
   float loss_acc = 0.f, vmean_acc = 0.f, done_acc = 0.f;
 
   stage(p.blob_pol, P.blob);
@@ -546,68 +623,74 @@ __global__ void __launch_bounds__(tc2::NT2, 1) rollout_tc2_kernel(const __grid_c
 #pragma unroll
     for (int f = 0; f < 16; ++f) x[f] = 0.f;
 #pragma unroll
-    for (int f = 0; f < NS; ++f) st[f] = (valid && f < obs_dim) ? p.obs[gs * obs_dim + f] : 0.f;
-    bool dn = valid ? (p.done[gs] != 0.f) : true;
+    for (int f = 0; f < NS; ++f) st[f] = (own && valid && f < obs_dim) ? p.obs[gs * obs_dim + f] : 0.f;
+    bool dn = (own && valid) ? (p.done[gs] != 0.f) : true;
     float vacc = 0.f;
 
     // ================================ forward sweep ================================
     if (have) {
       for (int k = 0; k < H; ++k) {
-        if (alg == ALG_FHADP || alg == ALG_PIM) {
+        if (own) {
+          if (alg == ALG_FHADP || alg == ALG_PIM) {
 #pragma unroll
-          for (int f = 0; f < NS; ++f) tape[(k * TCH + f) * GT + G.r] = st[f];
-          tape[(k * TCH + NS) * GT + G.r] = dn ? 1.f : 0.f;
+            for (int f = 0; f < NS; ++f) tape[(k * TCH + f) * GT + G.r] = st[f];
+            tape[(k * TCH + NS) * GT + G.r] = dn ? 1.f : 0.f;
+          }
+#pragma unroll
+          for (int f = 0; f < NS; ++f)
+            if (f < obs_dim) x[f] = st[f];
+          if (P.time_input) x[P.in - 1] = (float)(k + 1);
         }
-#pragma unroll
-        for (int f = 0; f < NS; ++f)
-          if (f < obs_dim) x[f] = st[f];
-        if (P.time_input) x[P.in - 1] = (float)(k + 1);
-        float z[MAXA], a[MAXA], g[MAXA], apol[MAXA];
-        layer1<false>(G, P, x);
+        float z[MAXA];
+        layer1_issue(G, x);
+        layer1_finish<false>(G, P);
         layer2_out(G, P, z);
-        if (alg == ALG_FHADP || alg == ALG_PIM) {
+        if (own) {
+          float a[MAXA], g[MAXA], apol[MAXA];
+          if (alg == ALG_FHADP || alg == ALG_PIM) {
 #pragma unroll
-          for (int j = 0; j < MAXA; ++j)
-            if (j < P.out) tape[(k * TCH + NS + 1 + j) * GT + G.r] = z[j];
-        }
-        process_action(p, P.out, z, a, g, apol);
-        const bool active = valid && (p.mask_at_done ? !dn : true);
-        float r = 0.f;
-        if (valid) {
-          float in[NS];
+            for (int j = 0; j < MAXA; ++j)
+              if (j < P.out) tape[(k * TCH + NS + 1 + j) * GT + G.r] = z[j];
+          }
+          process_action(p, P.out, z, a, g, apol);
+          const bool active = valid && (p.mask_at_done ? !dn : true);
+          float r = 0.f;
+          if (valid) {
+            float in[NS];
 #pragma unroll
-          for (int f = 0; f < NS; ++f) in[f] = (p.obs_scaling && f < obs_dim) ? st[f] / p.osc[f] - p.osh[f] : st[f];
-          if (active) {
-            bool md = false;
-            const int reps = p.repeat_num > 0 ? p.repeat_num : 1;
-            float rsum = 0.f, rj = 0.f;
-            for (int j = 0; j < reps; ++j) {
-              M::step(p, in, a, rj, md);
-              rsum += rj;
+            for (int f = 0; f < NS; ++f) in[f] = (p.obs_scaling && f < obs_dim) ? st[f] / p.osc[f] - p.osh[f] : st[f];
+            if (active) {
+              bool md = false;
+              const int reps = p.repeat_num > 0 ? p.repeat_num : 1;
+              float rsum = 0.f, rj = 0.f;
+              for (int j = 0; j < reps; ++j) {
+                M::step(p, in, a, rj, md);
+                rsum += rj;
+              }
+              r = (p.repeat_num > 0 && p.sum_reward) ? rsum : rj;
+              dn = md;
             }
-            r = (p.repeat_num > 0 && p.sum_reward) ? rsum : rj;
-            dn = md;
-          }
 #pragma unroll
-          for (int f = 0; f < NS; ++f) {
-            float o = (p.obs_scaling && f < obs_dim) ? (in[f] + p.osh[f]) * p.osc[f] : in[f];
-            if (p.clip_obs) o = fminf(fmaxf(o, p.obs_low[f]), p.obs_high[f]);
-            st[f] = o;
+            for (int f = 0; f < NS; ++f) {
+              float o = (p.obs_scaling && f < obs_dim) ? (in[f] + p.osh[f]) * p.osc[f] : in[f];
+              if (p.clip_obs) o = fminf(fmaxf(o, p.obs_low[f]), p.obs_high[f]);
+              st[f] = o;
+            }
+            if (p.reward_shaping) r = (r + p.reward_shift) * p.reward_scale;
+            vacc += r * p.gpow[k];
           }
-          if (p.reward_shaping) r = (r + p.reward_shift) * p.reward_scale;
-          vacc += r * p.gpow[k];
-        }
-        if (alg == ALG_TRACE && valid) {
-          const size_t row = (size_t)k * B + gs;
-          if (p.tr_obs)
-            for (int f = 0; f < obs_dim; ++f) p.tr_obs[row * obs_dim + f] = st[f];
-          if (p.tr_act)
-            for (int j = 0; j < P.out; ++j) p.tr_act[row * P.out + j] = apol[j];
-          if (p.tr_rew) p.tr_rew[row] = r;
-          if (p.tr_done) p.tr_done[row] = dn ? 1.f : 0.f;
+          if (alg == ALG_TRACE && valid) {
+            const size_t row = (size_t)k * B + gs;
+            if (p.tr_obs)
+              for (int f = 0; f < obs_dim; ++f) p.tr_obs[row * obs_dim + f] = st[f];
+            if (p.tr_act)
+              for (int j = 0; j < P.out; ++j) p.tr_act[row * P.out + j] = apol[j];
+            if (p.tr_rew) p.tr_rew[row] = r;
+            if (p.tr_done) p.tr_done[row] = dn ? 1.f : 0.f;
+          }
         }
       }
-      if (valid && dn) done_acc += 1.f;
+      if (own && valid && dn) done_acc += 1.f;
     }
     if (alg == ALG_TRACE) continue;
 
@@ -620,16 +703,20 @@ __global__ void __launch_bounds__(tc2::NT2, 1) rollout_tc2_kernel(const __grid_c
       bind(G, Wsm, V);
       if (have) {
         const float gn = p.gpow[H];
-        const bool term = valid && !dn;
+        const bool term = own && valid && !dn;
 #pragma unroll
-        for (int f = 0; f < 16; ++f) x[f] = (f < NS && f < obs_dim) ? st[f < NS ? f : 0] : 0.f;
+        for (int f = 0; f < 16; ++f) x[f] = 0.f;
+#pragma unroll
+        for (int f = 0; f < NS; ++f)
+          if (f < obs_dim) x[f] = st[f];
         float zv[MAXA], zb[MAXA], dx[16];
 #pragma unroll
-        for (int j = 0; j < MAXA; ++j) zb[j] = 0.f;
+        for (int j = 0; j < MAXA; ++j) zb[j] = zv[j] = 0.f;
         if (alg == ALG_PIM) {
           zb[0] = term ? -gn * p.inv_B : 0.f;
-          layer1<true>(G, V, x);
-          layer2_back<false>(G, V, zb, zv, acc3);
+          layer1_issue(G, x);
+          layer1_finish<true>(G, V);
+          layer2_back<false, true>(G, V, zb, zv, acc3);
           backprop<false>(G, V, true, dx);
           if (term) {
 #pragma unroll
@@ -637,7 +724,8 @@ __global__ void __launch_bounds__(tc2::NT2, 1) rollout_tc2_kernel(const __grid_c
               if (f < obs_dim) lam[f] = dx[f];
           }
         } else {
-          layer1<false>(G, V, x);
+          layer1_issue(G, x);
+          layer1_finish<false>(G, V);
           layer2_out(G, V, zv);
         }
         if (term) vacc += gn * zv[0];
@@ -650,20 +738,21 @@ __global__ void __launch_bounds__(tc2::NT2, 1) rollout_tc2_kernel(const __grid_c
       bind(G, Wsm, V);
       if (have) {
 #pragma unroll
-        for (int f = 0; f < 16; ++f) x[f] = (valid && f < obs_dim) ? p.obs[gs * obs_dim + f] : 0.f;
+        for (int f = 0; f < 16; ++f) x[f] = (own && valid && f < obs_dim) ? p.obs[gs * obs_dim + f] : 0.f;
         float zv[MAXA], zb[MAXA], dx[16];
 #pragma unroll
-        for (int j = 0; j < MAXA; ++j) zb[j] = 0.f;
+        for (int j = 0; j < MAXA; ++j) zb[j] = zv[j] = 0.f;
         // the output adjoint needs v(o_0) first: forward to the output, then recompute layer 2 fused with the backward
-        layer1<true>(G, V, x);
+        layer1_issue(G, x);
+        layer1_finish<true>(G, V);
         layer2_out(G, V, zv);
-        if (valid) {
+        if (own && valid) {
           const float diff = zv[0] - vacc;
           loss_acc += diff * diff * p.inv_B;
           vmean_acc += zv[0] * p.inv_B;
           zb[0] = 2.f * diff * p.inv_B;
         }
-        layer2_back<true>(G, V, zb, nullptr, acc3);
+        layer2_back<true, false>(G, V, zb, nullptr, acc3);
         backprop<true>(G, V, false, dx);
         flush(G, V, part);
       }
@@ -672,7 +761,7 @@ __global__ void __launch_bounds__(tc2::NT2, 1) rollout_tc2_kernel(const __grid_c
       continue;
     }
 
-    if (valid) loss_acc += -vacc * p.inv_B;
+    if (own && valid) loss_acc += -vacc * p.inv_B;
     if (alg == ALG_PIM) {
       stage(p.blob_pol, P.blob);
       bind(G, Wsm, P);
@@ -680,74 +769,101 @@ __global__ void __launch_bounds__(tc2::NT2, 1) rollout_tc2_kernel(const __grid_c
     if (!have) continue;
 
     // ================================ reverse sweep ================================
+    // the owner prefetches step k - 1's tape entries while step k's adjoint and MMAs run
+    float nst[NS], nz[MAXA];
+    bool ndn = false;
+#pragma unroll
+    for (int j = 0; j < MAXA; ++j) nz[j] = 0.f;
+    if (own) {
+#pragma unroll
+      for (int f = 0; f < NS; ++f) nst[f] = tape[((H - 1) * TCH + f) * GT + G.r];
+      ndn = tape[((H - 1) * TCH + NS) * GT + G.r] != 0.f;
+#pragma unroll
+      for (int j = 0; j < MAXA; ++j)
+        if (j < P.out) nz[j] = tape[((H - 1) * TCH + NS + 1 + j) * GT + G.r];
+    }
     for (int k = H - 1; k >= 0; --k) {
+      float zt[MAXA];
+      bool dnk = ndn;
 #pragma unroll
-      for (int f = 0; f < NS; ++f) st[f] = tape[(k * TCH + f) * GT + G.r];
-      const bool dnk = tape[(k * TCH + NS) * GT + G.r] != 0.f;
+      for (int f = 0; f < NS; ++f) st[f] = nst[f];
 #pragma unroll
-      for (int f = 0; f < NS; ++f)
-        if (f < obs_dim) x[f] = st[f];
-      if (P.time_input) x[P.in - 1] = (float)(k + 1);
-      layer1<true>(G, P, x);                      // recompute: issue early, the adjoint below overlaps the MMA
-      const bool active = valid && (p.mask_at_done ? !dnk : true);
+      for (int j = 0; j < MAXA; ++j) zt[j] = nz[j];
+      if (own) {
+#pragma unroll
+        for (int f = 0; f < NS; ++f)
+          if (f < obs_dim) x[f] = st[f];
+        if (P.time_input) x[P.in - 1] = (float)(k + 1);
+      }
+      layer1_issue(G, x);                        // recompute: issued first, the adjoint below overlaps the MMA
       float zb[MAXA];
 #pragma unroll
       for (int j = 0; j < MAXA; ++j) zb[j] = 0.f;
-      if (active) {
-        float z[MAXA], a[MAXA], g[MAXA], abar[MAXA];
+      const bool active = own && valid && (p.mask_at_done ? !dnk : true);
+      if (own) {
+        if (k > 0) {
 #pragma unroll
-        for (int j = 0; j < MAXA; ++j) z[j] = j < P.out ? tape[(k * TCH + NS + 1 + j) * GT + G.r] : 0.f;
-        process_action(p, P.out, z, a, g, nullptr);
-        const float rho = -p.gpow[k] * p.inv_B * (p.reward_shaping ? p.reward_scale : 1.f);
+          for (int f = 0; f < NS; ++f) nst[f] = tape[((k - 1) * TCH + f) * GT + G.r];
+          ndn = tape[((k - 1) * TCH + NS) * GT + G.r] != 0.f;
 #pragma unroll
-        for (int j = 0; j < MAXA; ++j) abar[j] = 0.f;
-        // lam = adjoint of the OUTER observation obs_{k+1}.  Chain of step k:
-        //   obs_k -(1/scale, -shift)-> inner_0 -[model step x reps, same action]-> inner_reps
-        //         -(+shift, *scale)-> clip -> obs_{k+1}
-        const int reps = p.repeat_num > 0 ? p.repeat_num : 1;
-        float in0[NS], cur[NS];
+          for (int j = 0; j < MAXA; ++j)
+            if (j < P.out) nz[j] = tape[((k - 1) * TCH + NS + 1 + j) * GT + G.r];
+        }
+        if (active) {
+          float a[MAXA], g[MAXA], abar[MAXA];
+          process_action(p, P.out, zt, a, g, nullptr);
+          const float rho = -p.gpow[k] * p.inv_B * (p.reward_shaping ? p.reward_scale : 1.f);
 #pragma unroll
-        for (int f = 0; f < NS; ++f) in0[f] = (p.obs_scaling && f < obs_dim) ? st[f] / p.osc[f] - p.osh[f] : st[f];
-        if (p.clip_obs) {            // clip passes gradient only where the raw next observation is inside
-          float rr;
-          bool md;
+          for (int j = 0; j < MAXA; ++j) abar[j] = 0.f;
+          // lam = adjoint of the OUTER observation obs_{k+1}.  Chain of step k:
+          //   obs_k -(1/scale, -shift)-> inner_0 -[model step x reps, same action]-> inner_reps
+          //         -(+shift, *scale)-> clip -> obs_{k+1}
+          const int reps = p.repeat_num > 0 ? p.repeat_num : 1;
+          float in0[NS], cur[NS];
 #pragma unroll
-          for (int f = 0; f < NS; ++f) cur[f] = in0[f];
-          for (int j = 0; j < reps; ++j) M::step(p, cur, a, rr, md);
+          for (int f = 0; f < NS; ++f) in0[f] = (p.obs_scaling && f < obs_dim) ? st[f] / p.osc[f] - p.osh[f] : st[f];
+          if (p.clip_obs) {            // clip passes gradient only where the raw next observation is inside
+            float rr;
+            bool md;
 #pragma unroll
-          for (int f = 0; f < NS; ++f) {
-            const float o = (p.obs_scaling && f < obs_dim) ? (cur[f] + p.osh[f]) * p.osc[f] : cur[f];
-            if (o < p.obs_low[f] || o > p.obs_high[f]) lam[f] = 0.f;
+            for (int f = 0; f < NS; ++f) cur[f] = in0[f];
+            for (int j = 0; j < reps; ++j) M::step(p, cur, a, rr, md);
+#pragma unroll
+            for (int f = 0; f < NS; ++f) {
+              const float o = (p.obs_scaling && f < obs_dim) ? (cur[f] + p.osh[f]) * p.osc[f] : cur[f];
+              if (o < p.obs_low[f] || o > p.obs_high[f]) lam[f] = 0.f;
+            }
           }
+          if (p.obs_scaling) {
+#pragma unroll
+            for (int f = 0; f < NS; ++f)
+              if (f < obs_dim) lam[f] *= p.osc[f];
+          }
+          for (int j = reps - 1; j >= 0; --j) {
+            float rr, aj[MAXA];
+            bool md;
+#pragma unroll
+            for (int f = 0; f < NS; ++f) cur[f] = in0[f];
+            for (int q = 0; q < j; ++q) M::step(p, cur, a, rr, md);      // state before repeat j
+            const float rho_j = (p.repeat_num == 0 || p.sum_reward || j == reps - 1) ? rho : 0.f;
+#pragma unroll
+            for (int q = 0; q < MAXA; ++q) aj[q] = 0.f;
+            M::step_bwd(p, cur, a, rho_j, lam, aj);
+#pragma unroll
+            for (int q = 0; q < MAXA; ++q) abar[q] += aj[q];
+          }
+          if (p.obs_scaling) {
+#pragma unroll
+            for (int f = 0; f < NS; ++f)
+              if (f < obs_dim) lam[f] /= p.osc[f];
+          }
+#pragma unroll
+          for (int j = 0; j < MAXA; ++j) zb[j] = abar[j] * g[j];
         }
-        if (p.obs_scaling) {
-#pragma unroll
-          for (int f = 0; f < NS; ++f)
-            if (f < obs_dim) lam[f] *= p.osc[f];
-        }
-        for (int j = reps - 1; j >= 0; --j) {
-          float rr, aj[MAXA];
-          bool md;
-#pragma unroll
-          for (int f = 0; f < NS; ++f) cur[f] = in0[f];
-          for (int q = 0; q < j; ++q) M::step(p, cur, a, rr, md);      // state before repeat j
-          const float rho_j = (p.repeat_num == 0 || p.sum_reward || j == reps - 1) ? rho : 0.f;
-#pragma unroll
-          for (int q = 0; q < MAXA; ++q) aj[q] = 0.f;
-          M::step_bwd(p, cur, a, rho_j, lam, aj);
-#pragma unroll
-          for (int q = 0; q < MAXA; ++q) abar[q] += aj[q];
-        }
-        if (p.obs_scaling) {
-#pragma unroll
-          for (int f = 0; f < NS; ++f)
-            if (f < obs_dim) lam[f] /= p.osc[f];
-        }
-#pragma unroll
-        for (int j = 0; j < MAXA; ++j) zb[j] = abar[j] * g[j];
       }
+      layer1_finish<true>(G, P);
       float dx[16];
-      layer2_back<true>(G, P, zb, nullptr, acc3);
+      layer2_back<true, false>(G, P, zb, nullptr, acc3);
       backprop<true>(G, P, k > 0, dx);
       if (active && k > 0) {
 #pragma unroll
@@ -759,35 +875,43 @@ __global__ void __launch_bounds__(tc2::NT2, 1) rollout_tc2_kernel(const __grid_c
   }
 
   // ============================ per-group partials ============================
+  tc2::wait_d2(G);
+  tc2::wait_d1(G);
+  group_sync(G.g);
   if (alg != ALG_TRACE) {
-    tc2::wait_d2(G);
-    tc2::wait_d1(G);
     const NetL& U = (alg == ALG_PEV) ? V : P;
-    const int lane = G.r & 31, w = G.r >> 5;
-    float* rg = red + (size_t)G.g * 4 * (MAXA * 64 + MAXA);
-    for (int a = 0; a < U.out; ++a) {
-      if ((lane & 1) == 0) {
+    const int lane = G.r & 31, wq = G.wg & 3;
+    constexpr int stride = MAXA * 64 + MAXA;
+    float* rg = reinterpret_cast<float*>(G.P);                         // [4 quarters][stride]: the planes are dead
+    if ((lane & 1) == 0) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) rg[w * (MAXA * 64 + MAXA) + a * 64 + 16 * q + tcf::col16(lane)] = acc3.w[a][q];
-      }
-      if (lane == 0) rg[w * (MAXA * 64 + MAXA) + MAXA * 64 + a] = acc3.b[a];
+      for (int a = 0; a < MAXA; ++a)
+        if (a < U.out) {
+          rg[wq * stride + a * 64 + 32 * G.h + tcf::col16(lane)] = acc3.w0[a];
+          rg[wq * stride + a * 64 + 32 * G.h + 16 + tcf::col16(lane)] = acc3.w1[a];
+        }
+    }
+    if (own && lane == 0) {
+#pragma unroll
+      for (int a = 0; a < MAXA; ++a)
+        if (a < U.out) rg[wq * stride + MAXA * 64 + a] = acc3.b[a];
     }
     group_sync(G.g);
-    const int stride = MAXA * 64 + MAXA;
-    for (int i = G.r; i < U.out * 64; i += GT) {
+    const int t = G.h * GT + G.r;
+    for (int i = t; i < U.out * 64; i += GTH) {
       const int a = i >> 6, j = i & 63;
       part[U.g_w3 + i] = (rg[a * 64 + j] + rg[stride + a * 64 + j]) + (rg[2 * stride + a * 64 + j] + rg[3 * stride + a * 64 + j]);
     }
-    if (G.r < U.out)
-      part[U.g_b3 + G.r] = (rg[MAXA * 64 + G.r] + rg[stride + MAXA * 64 + G.r]) +
-                           (rg[2 * stride + MAXA * 64 + G.r] + rg[3 * stride + MAXA * 64 + G.r]);
+    if (t < U.out)
+      part[U.g_b3 + t] = (rg[MAXA * 64 + t] + rg[stride + MAXA * 64 + t]) +
+                         (rg[2 * stride + MAXA * 64 + t] + rg[3 * stride + MAXA * 64 + t]);
     group_sync(G.g);
   }
-  {  // the three scalars of the group (fixed order)
+  {  // the three scalars of the group (fixed order; only owner threads carry values)
     float* sc = reinterpret_cast<float*>(G.P);
-    sc[G.r] = loss_acc; sc[GT + G.r] = vmean_acc; sc[2 * GT + G.r] = done_acc;
+    if (own) { sc[G.r] = loss_acc; sc[GT + G.r] = vmean_acc; sc[2 * GT + G.r] = done_acc; }
     group_sync(G.g);
-    if (G.r < 3) {
+    if (own && G.r < 3) {
       const int nparam = (alg == ALG_PEV) ? V.nparam : P.nparam;
       float s = 0.f;
       for (int i = 0; i < GT; ++i) s += sc[G.r * GT + i];
@@ -796,7 +920,7 @@ __global__ void __launch_bounds__(tc2::NT2, 1) rollout_tc2_kernel(const __grid_c
   }
   umma::fence_before_sync();
   __syncthreads();
-  if (tid < 32) umma::tmem_dealloc(*tslot, 512);
+  if (warp == 0) umma::tmem_dealloc(__shfl_sync(0xffffffffu, *tslot, 0), 512);
 }
 
 }  // namespace gops
