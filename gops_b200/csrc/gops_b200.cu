@@ -426,10 +426,31 @@ int launch_rollout(gops_b200_plan* pl, const gops_b200_batch* b, int alg, cudaSt
     k2.ext_ref = pl->ext_ref;
     k2.xbuf = pl->xbuf;
     k2.partial = pl->partial;
+    const char* tlf = getenv("GOPS_B200_TIMELINE");      // development aid (build with -DGOPS_TC2_TIMELINE): clock64 stamps
+    long long* dbg = nullptr;
+    if (tlf && !v1) {
+      CUDA_OK(cudaMalloc(&dbg, 8192 * sizeof(long long)));
+      CUDA_OK(cudaMemset(dbg, 0, 8192 * sizeof(long long)));
+    }
+    k2.dbg = dbg;
     if (pl->timing) CUDA_OK(cudaEventRecord(pl->ev0, st));
     fn<<<grid, NT, smem, st>>>(k2);
     ++g_launches;
     CUDA_OK_L(cudaGetLastError(), "launch#2-tc");
+    if (dbg) {
+      std::vector<long long> h(8192);
+      CUDA_OK(cudaStreamSynchronize(st));
+      CUDA_OK(cudaMemcpy(h.data(), dbg, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+      cudaFree(dbg);
+      if (FILE* f = fopen(tlf, "w")) {
+        for (int who = 0; who < 2; ++who) {
+          const long long n = h[who * 4096 + 4095];
+          for (long long i = 0; i < n && i < 4000; ++i)
+            fprintf(f, "%d %lld %lld\n", who, h[who * 4096 + i] & 255, h[who * 4096 + i] >> 8);
+        }
+        fclose(f);
+      }
+    }
     if (pl->timing) CUDA_OK(cudaEventRecord(pl->ev1, st));
     pl->last_grid = grid; pl->last_S = S; pl->last_NT = NT; pl->last_smem = smem; pl->last_path = GOPS_PATH_TC;
     if (alg != ALG_TRACE) {

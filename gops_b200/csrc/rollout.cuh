@@ -81,6 +81,7 @@ struct KParams {
   int part_stride;
   // smem carve (floats)
   int w_floats, dw_floats, inp_max;
+  long long* dbg;          // development aid (GOPS_B200_TIMELINE): clock64 stamps of one owner and one helper thread
   // trace outputs (alg == ALG_TRACE)
   float* tr_obs; float* tr_act; float* tr_rew; float* tr_done;
   // wrappers

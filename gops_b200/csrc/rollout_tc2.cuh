@@ -102,11 +102,24 @@ struct Grp {
   uint32_t fresh;                   // 1: the next weight-gradient MMAs overwrite their accumulators
   bool d2_pending, d1_pending;      // weight-gradient MMA groups in flight (their operand planes must not be rewritten)
   int g, h, wg, r;                  // group, half (0 owner / 1 helper), warp in group, row (= sample of the sub-tile)
+#ifdef GOPS_TC2_TIMELINE
+  long long* dbg;                   // timeline stamps (development aid)
+  int dbgn;
+#endif
   // staged weights of the network in use
   const unsigned char *W1, *W2;
   const float *W3, *b1, *b2, *b3;
 };
 
+// timeline stamp: (clock << 8) | id, only for the two instrumented threads and only when a buffer was attached
+// (compiled in with -DGOPS_TC2_TIMELINE only: tools/timeline_report.py; profiles/r02_tc2_timeline.txt)
+__device__ __forceinline__ void TL(Grp& G, int id) {
+#ifdef GOPS_TC2_TIMELINE
+  if (G.dbg != nullptr && G.dbgn < 4000) G.dbg[G.dbgn++] = (clock64() << 8) | (long long)id;
+#else
+  (void)G; (void)id;
+#endif
+}
 __device__ __forceinline__ void bind(Grp& G, const float* Wsm, const NetL& L) {
   G.W1 = reinterpret_cast<const unsigned char*>(Wsm + L.o_w1);
   G.W2 = reinterpret_cast<const unsigned char*>(Wsm + L.o_w2);
@@ -126,18 +139,16 @@ __device__ __forceinline__ void publish(const Grp& G) {
   group_sync(G.g);
 }
 
-// delta (2 planes, K-major A) x W^T (3 planes, MN-major B): a1b1, a0b2, a1b0, a0b1, a0b0 -- small terms first
+// delta (2 planes, K-major A) x W^T (MN-major B): a1b0, a0b1, a0b0 -- small terms first.  The dropped terms (a1b1, a0b2)
+// are 2^-17 relative, the size of delta's own two-plane truncation; these products sit on the serial chain of the
+// reverse sweep (delta2 -> delta1 -> dX -> lambda), so 12 MMAs instead of 20 shorten every reverse step.
 template <int KS>
 __device__ __forceinline__ void issue_dw(uint32_t d, const tcf::Op& A, const tcf::Op& B, uint32_t idesc) {
   using namespace tcf;
-  const uint64_t a0 = dsc(A, 0), a1 = dsc(A, 1), b0 = dsc(B, 0), b1 = dsc(B, 1), b2 = dsc(B, 2);
+  const uint64_t a0 = dsc(A, 0), a1 = dsc(A, 1), b0 = dsc(B, 0), b1 = dsc(B, 1);
   const uint64_t ka = A.kadv >> 4, kb = B.kadv >> 4;
 #pragma unroll
-  for (int ks = 0; ks < KS; ++ks) mma_bf16(d, a1 + ks * ka, b1 + ks * kb, idesc, ks > 0 ? 1u : 0u);
-#pragma unroll
-  for (int ks = 0; ks < KS; ++ks) mma_bf16(d, a0 + ks * ka, b2 + ks * kb, idesc, 1u);
-#pragma unroll
-  for (int ks = 0; ks < KS; ++ks) mma_bf16(d, a1 + ks * ka, b0 + ks * kb, idesc, 1u);
+  for (int ks = 0; ks < KS; ++ks) mma_bf16(d, a1 + ks * ka, b0 + ks * kb, idesc, ks > 0 ? 1u : 0u);
 #pragma unroll
   for (int ks = 0; ks < KS; ++ks) mma_bf16(d, a0 + ks * ka, b1 + ks * kb, idesc, 1u);
 #pragma unroll
@@ -172,11 +183,26 @@ __device__ __forceinline__ void write_x_row(const Grp& G, const float* x) {
 }
 
 // layer 1, first half: observation planes . W1^T issued; the caller may overlap work with the MMA before layer1_finish
-__device__ __forceinline__ void layer1_issue(Grp& G, const float* x) {
+template <int NS>
+__device__ __forceinline__ void layer1_issue(Grp& G, const NetL& L, const float* st, float vt) {
   using namespace tcf;
+  TL(G, 1);
   wait_d1(G);                                   // the dW1 MMAs of the previous step still read the X planes
-  if (G.h == 0) write_x_row(G, x);
+  TL(G, 2);
+  if (G.h == 0) {
+    float x[16];
+#pragma unroll
+    for (int f = 0; f < 16; ++f) x[f] = (f < NS && f < L.obs) ? st[f < NS ? f : 0] : 0.f;
+    if (L.time_input) {
+#pragma unroll
+      for (int f = 0; f < 16; ++f)
+        if (f == L.in - 1) x[f] = vt;
+    }
+    write_x_row(G, x);
+  }
+  TL(G, 3);
   publish(G);
+  TL(G, 4);
   if (G.wg == 0) {
     if (elect_one()) {
       umma::fence_after_sync();
@@ -184,18 +210,22 @@ __device__ __forceinline__ void layer1_issue(Grp& G, const float* x) {
       umma::commit(G.bc);
     }
   }
+  TL(G, 5);
 }
 // layer 1, second half: + b1, activation -> this thread's 32 columns of the H1 planes (FULL: act' parked in TMEM).
 // Two rolled passes of 16 columns: half the code and half the registers of one 32-column pass (the kernel is
 // instruction-fetch sensitive: 8 warps per SM sub-partition pair run different phases of a long straight-line body).
+// [lo, hi): the 16-column blocks of the row this thread converts (forward sweep: owner 0-1, helper 2-3; reverse sweep:
+// the helper takes all four while the owner runs the adjoint of the dynamics).
 template <bool FULL>
-__device__ __forceinline__ void layer1_finish(Grp& G, const NetL& L) {
+__device__ __forceinline__ void layer1_finish(Grp& G, const NetL& L, int lo, int hi) {
   using namespace tcf;
+  TL(G, 6);
   wait_d2(G);                                   // the dW2 MMAs of the previous step still read the H1 planes
   wait_c(G);
+  TL(G, 7);
 #pragma unroll 1
-  for (int cb = 0; cb < 2; ++cb) {
-    const int c16 = 2 * G.h + cb;               // 16-column block of the row
+  for (int c16 = lo; c16 < hi; ++c16) {
     float v[16], d[16];
     umma::tmem_ld16(G.tm + C_ACC + 16 * c16, v);
     const float* bias = G.b1 + 16 * c16;
@@ -211,12 +241,14 @@ __device__ __forceinline__ void layer1_finish(Grp& G, const NetL& L) {
     if constexpr (FULL) umma::tmem_st16(G.tm + C_D1 + 16 * c16, d);
   }
   if constexpr (FULL) umma::tmem_wait_st();
+  TL(G, 8);
 }
 
 // layer 2 + output layer, forward only: the owner gets z[a] = b3[a] + W3[a] . act(H1 . W2^T + b2)
 __device__ __forceinline__ void layer2_out(Grp& G, const NetL& L, float* z) {
   using namespace tcf;
   publish(G);
+  TL(G, 9);
   if (G.wg == 0) {
     if (elect_one()) {
       umma::fence_after_sync();
@@ -225,6 +257,7 @@ __device__ __forceinline__ void layer2_out(Grp& G, const NetL& L, float* z) {
     }
   }
   wait_c(G);
+  TL(G, 10);
   float zp[MAXA];
 #pragma unroll
   for (int a = 0; a < MAXA; ++a) zp[a] = 0.f;
@@ -253,7 +286,9 @@ __device__ __forceinline__ void layer2_out(Grp& G, const NetL& L, float* z) {
       if (a < L.out) G.zp[G.r * MAXA + a] = zp[a];
   }
   umma::fence_before_sync();      // the accumulator reads are ordered before the next MMA group (issued after a barrier)
+  TL(G, 11);
   group_sync(G.g);
+  TL(G, 12);
   if (G.h == 0) {
 #pragma unroll
     for (int a = 0; a < MAXA; ++a) z[a] = a < L.out ? G.b3[a] + (zp[a] + G.zp[G.r * MAXA + a]) : 0.f;
@@ -278,7 +313,9 @@ __device__ __forceinline__ void layer2_back(Grp& G, const NetL& L, const float* 
     for (int a = 0; a < MAXA; ++a)
       if (a < L.out) G.zb[G.r * MAXA + a] = zbar[a];
   }
+  TL(G, 13);
   publish(G);
+  TL(G, 14);
   if (G.wg == 0) {
     if (elect_one()) {
       umma::fence_after_sync();
@@ -291,6 +328,7 @@ __device__ __forceinline__ void layer2_back(Grp& G, const NetL& L, const float* 
   for (int a = 0; a < MAXA; ++a) zb[a] = a < L.out ? G.zb[G.r * MAXA + a] : 0.f;
   const int lane = G.r & 31;
   wait_c(G);
+  TL(G, 15);
   float zp[MAXA];
 #pragma unroll
   for (int a = 0; a < MAXA; ++a) zp[a] = 0.f;
@@ -375,7 +413,9 @@ __device__ __forceinline__ void layer2_back(Grp& G, const NetL& L, const float* 
 template <bool WANT_DW>
 __device__ __forceinline__ void backprop(Grp& G, const NetL& L, bool want_dx, float* dx) {
   using namespace tcf;
+  TL(G, 16);
   publish(G);
+  TL(G, 17);
   if (G.wg == 0) {
     if (elect_one()) {
       umma::fence_after_sync();
@@ -397,6 +437,7 @@ __device__ __forceinline__ void backprop(Grp& G, const NetL& L, bool want_dx, fl
     G.d2_pending = true;
   }
   wait_c(G);
+  TL(G, 18);
   uint32_t w0[16], w1[16];                       // delta1 planes of this thread's 32 columns, held until delta2's readers retired
   {
     uint32_t ra[32], rb[32];
@@ -414,13 +455,16 @@ __device__ __forceinline__ void backprop(Grp& G, const NetL& L, bool want_dx, fl
     umma::fence_before_sync();
     return;
   }
+  TL(G, 19);
   wait_d2(G);                                    // dW2 / db2 have consumed delta2 (and the H1 planes)
+  TL(G, 20);
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
     *reinterpret_cast<uint4*>(G.Q + ((4 * G.h + c) * 128 + G.r) * 16) = make_uint4(w0[4 * c], w0[4 * c + 1], w0[4 * c + 2], w0[4 * c + 3]);
     *reinterpret_cast<uint4*>(G.Q + HPL + ((4 * G.h + c) * 128 + G.r) * 16) = make_uint4(w1[4 * c], w1[4 * c + 1], w1[4 * c + 2], w1[4 * c + 3]);
   }
   publish(G);
+  TL(G, 21);
   if (want_dx) {
     if (G.wg == 0) {
       if (elect_one()) {
@@ -446,6 +490,7 @@ __device__ __forceinline__ void backprop(Grp& G, const NetL& L, bool want_dx, fl
   }
   if (want_dx) {
     wait_c(G);
+    TL(G, 22);
     if (G.h == 0) {
       uint32_t rr[16];
       tm_ld16(G.tm + C_ACC, rr);
@@ -461,8 +506,10 @@ __device__ __forceinline__ void backprop(Grp& G, const NetL& L, bool want_dx, fl
 // Lanes 0..63 hold the delta_b0 share of gradient row j = lane, lanes 64..127 the delta_b1 share of row lane - 64;
 // thread (h, r) moves columns [32 h, 32 h + 32) of dW2, the owner half also dW1 / db2 / db1.
 __device__ __forceinline__ void flush(Grp& G, const NetL& L, float* __restrict__ part) {
+  TL(G, 23);
   wait_d2(G);
   wait_d1(G);
+  TL(G, 24);
   if (G.fresh) return;                           // nothing accumulated since the last flush (uniform over the group)
   float* S = reinterpret_cast<float*>(G.P);      // scratch [64][84]: the H1 planes are dead here
   float w2[32], w1[16], bb[2];
@@ -514,6 +561,7 @@ __device__ __forceinline__ void flush(Grp& G, const NetL& L, float* __restrict__
   }
   group_sync(G.g);                               // the scratch is the next step's H1 planes
   G.fresh = 1u;
+  TL(G, 25);
 }
 
 }  // namespace tc2
@@ -555,6 +603,11 @@ __global__ void __launch_bounds__(tc2::NT2, 1) rollout_tc2_kernel(const __grid_c
   G.fresh = 1u;
   G.d2_pending = G.d1_pending = false;
   const bool own = G.h == 0;
+#ifdef GOPS_TC2_TIMELINE
+  G.dbg = nullptr;
+  G.dbgn = 0;
+  if (p.dbg != nullptr && blockIdx.x == 0 && (tid == 0 || tid == 128)) G.dbg = p.dbg + (tid == 0 ? 0 : 4096);
+#endif
 
   if (tid == 0) {
     for (int i = 0; i < 1 + 3 * NG; ++i) mbar_init(bars + i, 1);
@@ -619,9 +672,7 @@ __global__ void __launch_bounds__(tc2::NT2, 1) rollout_tc2_kernel(const __grid_c
     const bool have = sub < s1;                   // false: idle iteration that only takes part in the blob swaps
     const long long gs = sub * GT + G.r;
     const bool valid = have && gs < B;
-    float st[NS], x[16];
-#pragma unroll
-    for (int f = 0; f < 16; ++f) x[f] = 0.f;
+    float st[NS];
 #pragma unroll
     for (int f = 0; f < NS; ++f) st[f] = (own && valid && f < obs_dim) ? p.obs[gs * obs_dim + f] : 0.f;
     bool dn = (own && valid) ? (p.done[gs] != 0.f) : true;
@@ -636,15 +687,12 @@ __global__ void __launch_bounds__(tc2::NT2, 1) rollout_tc2_kernel(const __grid_c
             for (int f = 0; f < NS; ++f) tape[(k * TCH + f) * GT + G.r] = st[f];
             tape[(k * TCH + NS) * GT + G.r] = dn ? 1.f : 0.f;
           }
-#pragma unroll
-          for (int f = 0; f < NS; ++f)
-            if (f < obs_dim) x[f] = st[f];
-          if (P.time_input) x[P.in - 1] = (float)(k + 1);
         }
         float z[MAXA];
-        layer1_issue(G, x);
-        layer1_finish<false>(G, P);
+        layer1_issue<NS>(G, P, st, (float)(k + 1));
+        layer1_finish<false>(G, P, 2 * G.h, 2 * G.h + 2);
         layer2_out(G, P, z);
+        TL(G, 30);
         if (own) {
           float a[MAXA], g[MAXA], apol[MAXA];
           if (alg == ALG_FHADP || alg == ALG_PIM) {
@@ -704,18 +752,13 @@ __global__ void __launch_bounds__(tc2::NT2, 1) rollout_tc2_kernel(const __grid_c
       if (have) {
         const float gn = p.gpow[H];
         const bool term = own && valid && !dn;
-#pragma unroll
-        for (int f = 0; f < 16; ++f) x[f] = 0.f;
-#pragma unroll
-        for (int f = 0; f < NS; ++f)
-          if (f < obs_dim) x[f] = st[f];
         float zv[MAXA], zb[MAXA], dx[16];
 #pragma unroll
         for (int j = 0; j < MAXA; ++j) zb[j] = zv[j] = 0.f;
         if (alg == ALG_PIM) {
           zb[0] = term ? -gn * p.inv_B : 0.f;
-          layer1_issue(G, x);
-          layer1_finish<true>(G, V);
+          layer1_issue<NS>(G, V, st, 0.f);
+          layer1_finish<true>(G, V, 2 * G.h, 2 * G.h + 2);
           layer2_back<false, true>(G, V, zb, zv, acc3);
           backprop<false>(G, V, true, dx);
           if (term) {
@@ -724,8 +767,8 @@ __global__ void __launch_bounds__(tc2::NT2, 1) rollout_tc2_kernel(const __grid_c
               if (f < obs_dim) lam[f] = dx[f];
           }
         } else {
-          layer1_issue(G, x);
-          layer1_finish<false>(G, V);
+          layer1_issue<NS>(G, V, st, 0.f);
+          layer1_finish<false>(G, V, 2 * G.h, 2 * G.h + 2);
           layer2_out(G, V, zv);
         }
         if (term) vacc += gn * zv[0];
@@ -737,14 +780,15 @@ __global__ void __launch_bounds__(tc2::NT2, 1) rollout_tc2_kernel(const __grid_c
       stage(p.blob_val, V.blob);
       bind(G, Wsm, V);
       if (have) {
+        float o0[NS];
 #pragma unroll
-        for (int f = 0; f < 16; ++f) x[f] = (own && valid && f < obs_dim) ? p.obs[gs * obs_dim + f] : 0.f;
+        for (int f = 0; f < NS; ++f) o0[f] = (own && valid && f < obs_dim) ? p.obs[gs * obs_dim + f] : 0.f;
         float zv[MAXA], zb[MAXA], dx[16];
 #pragma unroll
         for (int j = 0; j < MAXA; ++j) zb[j] = zv[j] = 0.f;
         // the output adjoint needs v(o_0) first: forward to the output, then recompute layer 2 fused with the backward
-        layer1_issue(G, x);
-        layer1_finish<true>(G, V);
+        layer1_issue<NS>(G, V, o0, 0.f);
+        layer1_finish<true>(G, V, 2 * G.h, 2 * G.h + 2);
         layer2_out(G, V, zv);
         if (own && valid) {
           const float diff = zv[0] - vacc;
@@ -769,45 +813,37 @@ __global__ void __launch_bounds__(tc2::NT2, 1) rollout_tc2_kernel(const __grid_c
     if (!have) continue;
 
     // ================================ reverse sweep ================================
-    // the owner prefetches step k - 1's tape entries while step k's adjoint and MMAs run
-    float nst[NS], nz[MAXA];
+    // the owner prefetches step k - 1's state while step k's adjoint and MMAs run
+    float nst[NS];
     bool ndn = false;
-#pragma unroll
-    for (int j = 0; j < MAXA; ++j) nz[j] = 0.f;
     if (own) {
 #pragma unroll
       for (int f = 0; f < NS; ++f) nst[f] = tape[((H - 1) * TCH + f) * GT + G.r];
       ndn = tape[((H - 1) * TCH + NS) * GT + G.r] != 0.f;
-#pragma unroll
-      for (int j = 0; j < MAXA; ++j)
-        if (j < P.out) nz[j] = tape[((H - 1) * TCH + NS + 1 + j) * GT + G.r];
     }
     for (int k = H - 1; k >= 0; --k) {
       float zt[MAXA];
-      bool dnk = ndn;
+      const bool dnk = ndn;
 #pragma unroll
       for (int f = 0; f < NS; ++f) st[f] = nst[f];
 #pragma unroll
-      for (int j = 0; j < MAXA; ++j) zt[j] = nz[j];
+      for (int j = 0; j < MAXA; ++j) zt[j] = 0.f;
       if (own) {
 #pragma unroll
-        for (int f = 0; f < NS; ++f)
-          if (f < obs_dim) x[f] = st[f];
-        if (P.time_input) x[P.in - 1] = (float)(k + 1);
+        for (int j = 0; j < MAXA; ++j)
+          if (j < P.out) zt[j] = tape[(k * TCH + NS + 1 + j) * GT + G.r];
       }
-      layer1_issue(G, x);                        // recompute: issued first, the adjoint below overlaps the MMA
+      layer1_issue<NS>(G, P, st, (float)(k + 1));     // recompute: issued first, the adjoint below overlaps the MMA
       float zb[MAXA];
 #pragma unroll
       for (int j = 0; j < MAXA; ++j) zb[j] = 0.f;
       const bool active = own && valid && (p.mask_at_done ? !dnk : true);
+      TL(G, 31);
       if (own) {
         if (k > 0) {
 #pragma unroll
           for (int f = 0; f < NS; ++f) nst[f] = tape[((k - 1) * TCH + f) * GT + G.r];
           ndn = tape[((k - 1) * TCH + NS) * GT + G.r] != 0.f;
-#pragma unroll
-          for (int j = 0; j < MAXA; ++j)
-            if (j < P.out) nz[j] = tape[((k - 1) * TCH + NS + 1 + j) * GT + G.r];
         }
         if (active) {
           float a[MAXA], g[MAXA], abar[MAXA];
@@ -861,7 +897,8 @@ __global__ void __launch_bounds__(tc2::NT2, 1) rollout_tc2_kernel(const __grid_c
           for (int j = 0; j < MAXA; ++j) zb[j] = abar[j] * g[j];
         }
       }
-      layer1_finish<true>(G, P);
+      TL(G, 32);
+      layer1_finish<true>(G, P, 0, G.h == 0 ? 0 : 4);      // the helper converts the whole row meanwhile
       float dx[16];
       layer2_back<true, false>(G, P, zb, nullptr, acc3);
       backprop<true>(G, P, k > 0, dx);
@@ -918,6 +955,9 @@ __global__ void __launch_bounds__(tc2::NT2, 1) rollout_tc2_kernel(const __grid_c
       part[nparam + G.r] = s;
     }
   }
+#ifdef GOPS_TC2_TIMELINE
+  if (G.dbg != nullptr) G.dbg[4095] = G.dbgn;
+#endif
   umma::fence_before_sync();
   __syncthreads();
   if (warp == 0) umma::tmem_dealloc(__shfl_sync(0xffffffffu, *tslot, 0), 512);
