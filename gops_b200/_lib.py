@@ -47,6 +47,7 @@ class PlanDesc(C.Structure):
         ("lq_Q", C.c_float * MAX_LQ_N), ("lq_R", C.c_float * MAX_ACT),
         ("lq_dt", C.c_float), ("lq_reward_scale", C.c_float), ("lq_reward_shift", C.c_float),
         ("veh_pre_horizon", C.c_int32), ("reftraj", RefTraj),
+        ("open_loop", C.c_int32),
     ]
 
 
@@ -84,6 +85,19 @@ PROTOTYPES = {
                                           C.c_void_p, C.c_void_p, C.c_void_p]),
     "gops_b200_model_step": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "gops_b200_mlpnet_create": (C.c_int, [C.POINTER(C.c_int32), C.c_int32, C.c_int32, C.c_int64, C.c_int32,
+                                          C.POINTER(C.c_void_p)]),
+    "gops_b200_mlpnet_destroy": (C.c_int, [C.c_void_p]),
+    "gops_b200_mlpnet_param_count": (C.c_int64, [C.c_void_p]),
+    "gops_b200_mlpnet_pack": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "gops_b200_mlpnet_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_int32,
+                                           C.c_void_p, C.c_int32, C.c_void_p]),
+    "gops_b200_mlpnet_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_void_p,
+                                            C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]),
+    "gops_b200_mlpnet_keep_deltas": (C.c_int, [C.c_void_p, C.c_int32]),
+    "gops_b200_mlpnet_wgrad_slots": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_int32,
+                                               C.c_int64, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_int32,
+                                               C.c_void_p]),
 }
 
 _lib = None

@@ -92,13 +92,15 @@ class AlgorithmBase(metaclass=ABCMeta):
 class RolloutPlan:
     """Owns one `gops_b200_plan` (C side) for a fixed (algorithm kind, horizon, gamma, env, nets)."""
 
-    def __init__(self, alg_kind: int, envmodel, policy, value, horizon: int, gamma: float, device=None):
+    def __init__(self, alg_kind: int, envmodel, policy, value, horizon: int, gamma: float, device=None,
+                 open_loop: bool = False):
         self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
         with torch.cuda.device(self.device):     # the C side allocates its scratch on the current device
-            self._create(alg_kind, envmodel, policy, value, horizon, gamma)
+            self._create(alg_kind, envmodel, policy, value, horizon, gamma, open_loop)
 
-    def _create(self, alg_kind, envmodel, policy, value, horizon, gamma):
+    def _create(self, alg_kind, envmodel, policy, value, horizon, gamma, open_loop):
         desc = _lib.PlanDesc()
+        desc.open_loop = int(open_loop)
         desc.alg, desc.horizon, desc.gamma = alg_kind, int(horizon), float(gamma)
         desc.policy = policy.mlp_desc()
         if value is not None:
@@ -169,12 +171,12 @@ class FusedADPMixin:
     kernel_path = "auto"     # 'auto' | 'mma' | 'tc' (RolloutPlan.set_path); tests state and assert the path here
     MAX_PLANS = 4            # LRU: annealing pre_horizon must not leak one tape + blobs per distinct value
 
-    def _plan(self, alg_kind, policy, value, horizon, gamma) -> RolloutPlan:
+    def _plan(self, alg_kind, policy, value, horizon, gamma, open_loop: bool = False) -> RolloutPlan:
         dev = self._device()
         key = (alg_kind, int(horizon), dev.index)
         plan = self._plans.pop(key, None)
         if plan is None:
-            plan = RolloutPlan(alg_kind, self.envmodel, policy, value, horizon, gamma, device=dev)
+            plan = RolloutPlan(alg_kind, self.envmodel, policy, value, horizon, gamma, device=dev, open_loop=open_loop)
             while len(self._plans) >= self.MAX_PLANS:
                 self._plans.pop(next(iter(self._plans)))          # least recently used; its __del__ frees the C plan
         self._plans[key] = plan                                   # most recently used last

@@ -6,7 +6,7 @@ StateValue :309-329); `forward` runs the fused sm_100a inference kernel
 (`gops_b200_mlp_forward`) instead of nn.Sequential.  Training never calls `forward`: the
 algorithms hand the flat parameter vector to the fused rollout kernel.
 """
-__all__ = ["DetermPolicy", "FiniteHorizonPolicy", "StateValue"]
+__all__ = ["DetermPolicy", "FiniteHorizonPolicy", "FiniteHorizonFullPolicy", "StateValue"]
 
 import ctypes as C
 
@@ -114,6 +114,60 @@ class FiniteHorizonPolicy(_FusedMlp):
 
     def forward(self, obs, virtual_t=1):
         return self._infer(obs, float(virtual_t), squash=True)
+
+
+class FiniteHorizonFullPolicy(nn.Module, Action_Distribution):
+    """Open-loop finite-horizon policy (reference mlp.py:114-145): ONE evaluation on obs emits the actions of all
+    `pre_horizon` steps; `forward` returns the first one.  Evaluated by the layer-wise tcgen05 MLP
+    (gops_b200_mlpnet_*); trained by FHADP2 through the fused open-loop rollout."""
+
+    def __init__(self, **kwargs):
+        super().__init__()
+        hidden = list(kwargs["hidden_sizes"])
+        if len(hidden) != 2 or hidden[0] != hidden[1] or hidden[0] > 256:
+            raise NotImplementedError(f"gops_b200 FiniteHorizonFullPolicy: two equal hidden layers <= 256, got {hidden}")
+        self._obs_dim, self.act_dim, self.pre_horizon = kwargs["obs_dim"], kwargs["act_dim"], kwargs["pre_horizon"]
+        if self.act_dim * self.pre_horizon > 256:
+            raise NotImplementedError("gops_b200 FiniteHorizonFullPolicy: act_dim * pre_horizon must be <= 256")
+        self._hidden, self._hidden_act = hidden[0], kwargs["hidden_activation"]
+        if kwargs.get("output_activation", "linear") != "linear":
+            raise NotImplementedError("gops_b200 fused MLP kernels support output_activation='linear' only")
+        self.pi = mlp([self._obs_dim] + hidden + [self.act_dim * self.pre_horizon],
+                      get_activation_func(self._hidden_act), get_activation_func("linear"))
+        self.register_buffer("act_high_lim", torch.from_numpy(np.asarray(kwargs["act_high_lim"], dtype=np.float32)))
+        self.register_buffer("act_low_lim", torch.from_numpy(np.asarray(kwargs["act_low_lim"], dtype=np.float32)))
+        self.action_distribution_cls = kwargs["action_distribution_cls"]
+        self.__dict__["_flat_params"] = FlatParams(self.pi)
+        self.__dict__["_net"] = None
+
+    @property
+    def flat_params(self) -> FlatParams:
+        return self.__dict__["_flat_params"]
+
+    def mlp_desc(self) -> _lib.MlpDesc:
+        return _lib.MlpDesc(self._obs_dim, 0, self._hidden, self.act_dim * self.pre_horizon,
+                            _lib.ACT_IDS[self._hidden_act], _lib.ACT_IDS["linear"])
+
+    def forward(self, obs):
+        return self.forward_all_policy(obs)[:, 0, :]
+
+    def forward_all_policy(self, obs):
+        from gops_b200.ops.layerwise_mlp import LayerwiseMlp
+        flat = self.flat_params.sync()
+        if not flat.is_cuda:
+            raise RuntimeError("gops_b200 apprfuncs run on a CUDA device only (no CPU fallback); call .cuda()")
+        src = obs.device
+        x = obs.detach().to(flat.device, torch.float32).reshape(-1, self._obs_dim).contiguous()
+        net = self.__dict__["_net"]
+        if net is None or net.max_batch < x.shape[0] or net.device != flat.device:
+            net = self.__dict__["_net"] = LayerwiseMlp([self._obs_dim, self._hidden, self._hidden,
+                                                        self.act_dim * self.pre_horizon], self._hidden_act,
+                                                       max_batch=max(x.shape[0], 1024), device=flat.device)
+        net.pack(flat)
+        z = net.forward(x, train=False).reshape(x.shape[0], self.pre_horizon, self.act_dim)
+        # the squashing below is 3 elementwise ops on [B, H, A] at inference time only (training fuses it)
+        act = (self.act_high_lim - self.act_low_lim) / 2 * torch.tanh(z) + (self.act_high_lim + self.act_low_lim) / 2
+        return act.to(src)
 
 
 class StateValue(_FusedMlp):

@@ -16,6 +16,7 @@
 #include "aux_kernels.cuh"
 #include "mlp_tc.cuh"
 #include "rollout_tc2.cuh"
+#include "lw_rollout.cuh"
 #include <cuda_bf16.h>
 
 using namespace gops;
@@ -52,6 +53,12 @@ int fail(const std::string& msg) {
   } while (0)
 
 int round4(int x) { return (x + 3) & ~3; }
+}  // namespace
+namespace gops {   // shared with the other translation units of the library (dense_tc.cu, dsac.cu)
+int dense_fail(const std::string& msg) { return fail(msg); }
+void dense_count_launch(int n) { g_launches += n; }
+}  // namespace gops
+namespace {
 
 // Every entry point runs on the device that owns its plan / buffers, whatever the caller's current device is
 // (networks on cuda:1 while cuda:0 is current must not put scratch on one GPU and the launch on the other).
@@ -153,6 +160,9 @@ StepFn step_fn_idp();
 StepFn step_fn_lq();
 RolloutFn rollout_fn_tc_idp(int alg);   // round-1 tcgen05 kernel (one sub-tile at a time, 512 cooperating threads): A/B only
 RolloutFn rollout_fn_tc_lq(int alg);
+LwFn lw_fn_idp(int which);              // layer-wise path (wide nets): 0 init, 1 forward step, 2 reverse step
+LwFn lw_fn_lq(int which);
+LwFn lw_fn_vehtrack(int which);
 RolloutFn rollout_fn_tc2_idp(int alg);  // pipelined tcgen05 kernel: two independent 128-thread groups per CTA (rollout_tc2.cuh)
 RolloutFn rollout_fn_tc2_lq(int alg);
 }  // namespace gops
@@ -179,6 +189,14 @@ RolloutFn rollout_fn_tc2(int model, int alg) {
   switch (model) {
     case GOPS_MODEL_IDPENDULUM: return rollout_fn_tc2_idp(alg);
     case GOPS_MODEL_LQ: return rollout_fn_tc2_lq(alg);
+    default: return nullptr;
+  }
+}
+LwFn lw_fn(int model, int which) {
+  switch (model) {
+    case GOPS_MODEL_IDPENDULUM: return lw_fn_idp(which);
+    case GOPS_MODEL_LQ: return lw_fn_lq(which);
+    case GOPS_MODEL_VEH3DOF_TRACKING: return lw_fn_vehtrack(which);
     default: return nullptr;
   }
 }
@@ -219,6 +237,11 @@ struct gops_b200_plan {
   bool timing = false;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int path = GOPS_PATH_AUTO, last_path = 0;
+  // layer-wise tcgen05 path of the wide nets (lw_rollout.cuh + dense_tc.cu)
+  gops_b200_mlpnet* lw_net = nullptr;
+  long long lw_cap = 0;
+  float *lw_S = nullptr, *lw_Dn = nullptr, *lw_X = nullptr, *lw_Z = nullptr, *lw_Zb = nullptr, *lw_lam = nullptr,
+        *lw_vacc = nullptr, *lw_dX = nullptr, *lw_sp = nullptr;
   int last_grid = 0, last_S = 0, last_NT = 0;
   size_t last_smem = 0;
 };
@@ -369,6 +392,139 @@ int launch_pack(const float* flat, const NetL& L, int hid, float* blob, cudaStre
   pack_params_kernel<<<hid > 64 ? 64 : 8, 256, 0, st>>>(flat, L, hid, blob);
   ++g_launches;
   CUDA_OK_L(cudaGetLastError(), "launch#1");
+  return 0;
+}
+
+// Wide nets (hidden 256), FHADP: the layer-wise tcgen05 path.  AUTO takes it wherever it is built; MMA keeps the fused
+// FP32-FFMA kernel (A/B baseline).
+bool rollout_use_layerwise(const gops_b200_plan* pl, int alg) {
+  if (pl->desc.open_loop) return alg == ALG_FHADP;
+  if (pl->kp.hid <= 64 || alg != ALG_FHADP || pl->kp.horizon > 128) return false;
+  if (!lw_fn(pl->desc.model, 0)) return false;
+  int path = pl->path;
+  const char* e = getenv("GOPS_B200_ROLLOUT");
+  if (e && !strcmp(e, "mma")) path = GOPS_PATH_MMA;
+  if (e && !strcmp(e, "tc")) path = GOPS_PATH_TC;
+  return path != GOPS_PATH_MMA;
+}
+
+int launch_rollout_layerwise(gops_b200_plan* pl, const gops_b200_batch* b, const float* policy_params, cudaStream_t st,
+                             float* grad_out, float* scalars_out) {
+  KParams& kp = pl->kp;
+  const int H = kp.horizon, A = kp.pol.out, in = kp.pol.in, ldx = round4(in), NS = model_ns(pl->desc.model);
+  const long long B = b->batch;
+  const bool open = pl->desc.open_loop != 0;
+  if (open) {       // FHADP2: one policy evaluation emits all H actions; the rollout kernels read them strided
+    if (B > pl->lw_cap || !pl->lw_net) {
+      if (pl->lw_net) gops_b200_mlpnet_destroy(pl->lw_net);
+      pl->lw_net = nullptr;
+      float** bufs[] = {&pl->lw_S, &pl->lw_Dn, &pl->lw_Z, &pl->lw_Zb, &pl->lw_lam, &pl->lw_vacc, &pl->lw_sp};
+      for (float** q : bufs) { cudaFree(*q); *q = nullptr; }
+      const long long cap = (B + 127) / 128 * 128;
+      const int32_t sizes[4] = {in, pl->desc.policy.hidden, pl->desc.policy.hidden, A * H};
+      if (gops_b200_mlpnet_create(sizes, 4, kp.pol.hact, cap, 1, &pl->lw_net)) return 1;
+      CUDA_OK(cudaMalloc(&pl->lw_S, sizeof(float) * (size_t)(H + 1) * NS * cap));
+      CUDA_OK(cudaMalloc(&pl->lw_Dn, sizeof(float) * (size_t)(H + 1) * cap));
+      CUDA_OK(cudaMalloc(&pl->lw_Z, sizeof(float) * (size_t)H * cap * A));
+      CUDA_OK(cudaMalloc(&pl->lw_Zb, sizeof(float) * (size_t)H * cap * A));
+      CUDA_OK(cudaMalloc(&pl->lw_lam, sizeof(float) * (size_t)NS * cap));
+      CUDA_OK(cudaMalloc(&pl->lw_vacc, sizeof(float) * (size_t)cap));
+      CUDA_OK(cudaMalloc(&pl->lw_sp, sizeof(float) * 2 * 256));
+      pl->lw_cap = cap;
+    }
+    kp.alg = ALG_FHADP;
+    kp.batch = B;
+    kp.obs = b->obs; kp.done = b->done; kp.state = b->state; kp.reference = b->reference;
+    kp.ref_t = b->ref_t; kp.ref_len = b->ref_len;
+    LwFn f_init = lw_fn(pl->desc.model, 0), f_step = lw_fn(pl->desc.model, 1), f_rev = lw_fn(pl->desc.model, 2);
+    LwArgs a;
+    memset(&a, 0, sizeof(a));
+    a.ldx = ldx; a.act_dim = A; a.bstride = pl->lw_cap; a.zs_k = A; a.zs_b = (long long)H * A;
+    a.S = pl->lw_S; a.Dn = pl->lw_Dn; a.X = nullptr; a.Z = pl->lw_Z; a.Zb = pl->lw_Zb; a.lam = pl->lw_lam; a.vacc = pl->lw_vacc;
+    const unsigned grid = (unsigned)((B + 127) / 128);
+    if (pl->timing) CUDA_OK(cudaEventRecord(pl->ev0, st));
+    if (gops_b200_mlpnet_pack(pl->lw_net, policy_params, st)) return 1;
+    if (gops_b200_mlpnet_forward(pl->lw_net, b->obs, kp.pol.obs, B, 0, 1, pl->lw_Z, H * A, st)) return 1;
+    f_init<<<grid, 128, 0, st>>>(kp, a);
+    for (int k = 0; k < H; ++k) {
+      a.k = k;
+      f_step<<<grid, 128, 0, st>>>(kp, a);
+    }
+    for (int k = H - 1; k >= 0; --k) {
+      a.k = k;
+      f_rev<<<grid, 128, 0, st>>>(kp, a);
+    }
+    g_launches += 1 + 2 * H;
+    if (gops_b200_mlpnet_backward(pl->lw_net, pl->lw_Zb, H * A, B, 0, grad_out, 0, nullptr, 0, st)) return 1;
+    const int nb = 64;
+    lw_scalars_kernel<<<nb, 256, 0, st>>>(pl->lw_vacc, pl->lw_Dn + (size_t)H * B, B, kp.inv_B, pl->lw_sp);
+    lw_scalars_final_kernel<<<1, 32, 0, st>>>(pl->lw_sp, nb, scalars_out);
+    g_launches += 2;
+    CUDA_OK_L(cudaGetLastError(), "open-loop rollout");
+    if (pl->timing) CUDA_OK(cudaEventRecord(pl->ev1, st));
+    pl->last_grid = (int)grid; pl->last_S = 128; pl->last_NT = 128; pl->last_smem = 0; pl->last_path = GOPS_PATH_TC;
+    return 0;
+  }
+  if (B > pl->lw_cap || !pl->lw_net) {
+    if (pl->lw_net) gops_b200_mlpnet_destroy(pl->lw_net);
+    pl->lw_net = nullptr;
+    float** bufs[] = {&pl->lw_S, &pl->lw_Dn, &pl->lw_X, &pl->lw_Z, &pl->lw_Zb, &pl->lw_lam, &pl->lw_vacc, &pl->lw_dX, &pl->lw_sp};
+    for (float** q : bufs) { cudaFree(*q); *q = nullptr; }
+    const long long cap = (B + 127) / 128 * 128;
+    const int32_t sizes[4] = {in, kp.hid, kp.hid, A};
+    if (gops_b200_mlpnet_create(sizes, 4, kp.pol.hact, cap, H, &pl->lw_net)) return 1;
+    if (gops_b200_mlpnet_keep_deltas(pl->lw_net, 1)) return 1;
+    CUDA_OK(cudaMalloc(&pl->lw_S, sizeof(float) * (size_t)(H + 1) * NS * cap));
+    CUDA_OK(cudaMalloc(&pl->lw_Dn, sizeof(float) * (size_t)(H + 1) * cap));
+    CUDA_OK(cudaMalloc(&pl->lw_X, sizeof(float) * (size_t)(H + 1) * cap * ldx));
+    CUDA_OK(cudaMalloc(&pl->lw_Z, sizeof(float) * (size_t)H * cap * A));
+    CUDA_OK(cudaMalloc(&pl->lw_Zb, sizeof(float) * (size_t)H * cap * A));
+    CUDA_OK(cudaMalloc(&pl->lw_lam, sizeof(float) * (size_t)NS * cap));
+    CUDA_OK(cudaMalloc(&pl->lw_vacc, sizeof(float) * (size_t)cap));
+    CUDA_OK(cudaMalloc(&pl->lw_dX, sizeof(float) * (size_t)cap * ldx));
+    CUDA_OK(cudaMalloc(&pl->lw_sp, sizeof(float) * 2 * 256));
+    pl->lw_cap = cap;
+  }
+  const long long cap = pl->lw_cap;
+  kp.alg = ALG_FHADP;
+  kp.batch = B;
+  kp.obs = b->obs; kp.done = b->done; kp.state = b->state; kp.reference = b->reference;
+  kp.ref_t = b->ref_t; kp.ref_len = b->ref_len;
+  LwFn f_init = lw_fn(pl->desc.model, 0), f_step = lw_fn(pl->desc.model, 1), f_rev = lw_fn(pl->desc.model, 2);
+  LwArgs a;
+  memset(&a, 0, sizeof(a));
+  a.ldx = ldx; a.act_dim = A; a.bstride = cap; a.zs_k = cap * A; a.zs_b = A;
+  a.S = pl->lw_S; a.Dn = pl->lw_Dn; a.X = pl->lw_X; a.Z = pl->lw_Z; a.Zb = pl->lw_Zb; a.lam = pl->lw_lam; a.vacc = pl->lw_vacc;
+  // S / Dn are indexed with the real batch as the row count
+  const unsigned grid = (unsigned)((B + 127) / 128);
+  if (pl->timing) CUDA_OK(cudaEventRecord(pl->ev0, st));
+  if (gops_b200_mlpnet_pack(pl->lw_net, policy_params, st)) return 1;
+  f_init<<<grid, 128, 0, st>>>(kp, a);
+  ++g_launches;
+  for (int k = 0; k < H; ++k) {
+    if (gops_b200_mlpnet_forward(pl->lw_net, pl->lw_X + (size_t)k * cap * ldx, ldx, B, k, 1, pl->lw_Z + (size_t)k * cap * A, A, st))
+      return 1;
+    a.k = k;
+    f_step<<<grid, 128, 0, st>>>(kp, a);
+    ++g_launches;
+  }
+  for (int k = H - 1; k >= 0; --k) {
+    a.k = k;
+    a.dX = k == H - 1 ? nullptr : pl->lw_dX;
+    f_rev<<<grid, 128, 0, st>>>(kp, a);
+    ++g_launches;
+    if (gops_b200_mlpnet_backward(pl->lw_net, pl->lw_Zb + (size_t)k * cap * A, A, B, k, nullptr, 0, k > 0 ? pl->lw_dX : nullptr, ldx,
+                                  st))
+      return 1;
+  }
+  if (gops_b200_mlpnet_wgrad_slots(pl->lw_net, 0, H, B, pl->lw_X, ldx, cap, pl->lw_Zb, A, cap, grad_out, 0, st)) return 1;
+  const int nb = 64;
+  lw_scalars_kernel<<<nb, 256, 0, st>>>(pl->lw_vacc, pl->lw_Dn + (size_t)H * B, B, kp.inv_B, pl->lw_sp);
+  lw_scalars_final_kernel<<<1, 32, 0, st>>>(pl->lw_sp, nb, scalars_out);
+  g_launches += 2;
+  CUDA_OK_L(cudaGetLastError(), "layer-wise rollout");
+  if (pl->timing) CUDA_OK(cudaEventRecord(pl->ev1, st));
+  pl->last_grid = (int)grid; pl->last_S = 128; pl->last_NT = 128; pl->last_smem = 0; pl->last_path = GOPS_PATH_TC;
   return 0;
 }
 
@@ -528,14 +684,24 @@ int gops_b200_plan_create(const gops_b200_plan_desc* d, gops_b200_plan** out) {
   *out = nullptr;
   if (d->alg < GOPS_ALG_FHADP || d->alg > GOPS_ALG_INFADP_VALUE) return fail("unknown algorithm kind");
   if (d->horizon < 1 || d->horizon > 4096) return fail("horizon out of range");
-  if (!rollout_fn(d->model, d->policy.hidden == 256 ? 256 : 64, 0, d->alg)) return fail("env model kind not built into this library");
+  if (!rollout_fn(d->model, d->policy.hidden == 64 ? 64 : 256, 0, d->alg)) return fail("env model kind not built into this library");
   gops_b200_plan* pl = new (std::nothrow) gops_b200_plan();
   if (!pl) return fail("out of host memory");
   pl->desc = *d;
   KParams& kp = pl->kp;
   memset(&kp, 0, sizeof(kp));
   std::string why;
-  if (!make_net(d->policy, kp.pol, why)) { delete pl; return fail("policy: " + why); }
+  gops_b200_mlp_desc pol_desc = d->policy;
+  if (d->open_loop) {
+    if (d->alg != GOPS_ALG_FHADP) { delete pl; return fail("open_loop (FHADP2) needs alg = GOPS_ALG_FHADP"); }
+    if (d->policy.time_input || d->policy.out_dim % d->horizon || d->policy.out_dim > 256) {
+      delete pl;
+      return fail("open_loop: policy.out_dim must be act_dim * horizon (<= 256), without time input");
+    }
+    pol_desc.out_dim = d->policy.out_dim / d->horizon;      // kp.pol describes ONE step's action block
+    if (pol_desc.hidden != 64 && pol_desc.hidden != 256) pol_desc.hidden = 256;   // geometry only; the mlpnet takes the real width
+  }
+  if (!make_net(pol_desc, kp.pol, why)) { delete pl; return fail("policy: " + why); }
   const bool infadp = d->alg != GOPS_ALG_FHADP;
   if (infadp) {
     if (!make_net(d->value, kp.val, why)) { delete pl; return fail("value: " + why); }
@@ -544,7 +710,7 @@ int gops_b200_plan_create(const gops_b200_plan_desc* d, gops_b200_plan** out) {
   } else {
     kp.val = kp.pol;
   }
-  const int act_dim = d->policy.out_dim;
+  const int act_dim = pol_desc.out_dim;
   int obs_dim_model = 0;
   if (d->model == GOPS_MODEL_IDPENDULUM) obs_dim_model = 6;
   if (d->model == GOPS_MODEL_LQ) {
@@ -564,7 +730,8 @@ int gops_b200_plan_create(const gops_b200_plan_desc* d, gops_b200_plan** out) {
   if (d->model == GOPS_MODEL_IDPENDULUM && act_dim != 1) { delete pl; return fail("idpendulum has 1 action"); }
 
   kp.horizon = d->horizon;
-  kp.hid = d->policy.hidden;
+  kp.hid = pol_desc.hidden;
+  if (d->open_loop && !lw_fn(d->model, 0)) { delete pl; return fail("open_loop (FHADP2) is not built for this env model"); }
   if (infadp && d->value.hidden != d->policy.hidden) { delete pl; return fail("policy and value hidden widths differ"); }
   kp.gamma = d->gamma;
   kp.w_floats = kp.pol.blob > kp.val.blob ? kp.pol.blob : kp.val.blob;
@@ -712,7 +879,7 @@ int gops_b200_plan_last_kernel_ms(gops_b200_plan* pl, float* ms) {
 int gops_b200_plan_set_path(gops_b200_plan* pl, int path) {
   if (!pl) return fail("null plan");
   if (path != GOPS_PATH_AUTO && path != GOPS_PATH_MMA && path != GOPS_PATH_TC) return fail("unknown kernel path");
-  if (path == GOPS_PATH_TC && !pl->tc_ok)
+  if (path == GOPS_PATH_TC && !pl->tc_ok && !(pl->kp.hid > 64 && pl->desc.alg == GOPS_ALG_FHADP && lw_fn(pl->desc.model, 0)))
     return fail("the tcgen05 rollout kernel is not built for this plan (needs 64-wide nets, <= 16 inputs, idpendulum / lq)");
   pl->path = path;
   return 0;
@@ -730,6 +897,12 @@ int gops_b200_plan_destroy(gops_b200_plan* pl) {
   if (!pl) return 0;
   DevGuard dg(pl->device);
   if (pl->ev0) { cudaEventDestroy(pl->ev0); cudaEventDestroy(pl->ev1); }
+  if (pl->lw_net) gops_b200_mlpnet_destroy(pl->lw_net);
+  {
+    float* lw[] = {pl->lw_S, pl->lw_Dn, pl->lw_X, pl->lw_Z, pl->lw_Zb, pl->lw_lam, pl->lw_vacc, pl->lw_dX, pl->lw_sp};
+    for (float* q : lw) cudaFree(q);
+    (void)cudaGetLastError();
+  }
   void* ptrs[] = {pl->gpow, pl->blob_pol, pl->blob_val, pl->blob_vtg, pl->tape, pl->partial, pl->ext_ref, pl->xbuf, pl->osc,
                   pl->blob_tc, pl->blob_pol_tcf, pl->blob_val_tcf, pl->blob_vtg_tcf};
   const char* names[] = {"gpow", "blob_pol", "blob_val", "blob_vtg", "tape", "partial", "ext_ref", "xbuf", "osc", "blob_tc",
@@ -763,6 +936,15 @@ int gops_b200_rollout_grad(gops_b200_plan* pl, const gops_b200_batch* b, const f
   DevGuard dg(pl->device);
   cudaStream_t st = (cudaStream_t)stream;
   const int alg = pl->desc.alg;
+  if (b && b->batch > 0 && b->obs && b->done && rollout_use_layerwise(pl, alg)) {
+    if (pl->desc.model == GOPS_MODEL_VEH3DOF_TRACKING) {
+      if (!b->state || !b->reference) return fail("veh3dof_tracking needs state (robot_state) and reference");
+      if (b->ref_t < 0 || b->ref_t + pl->kp.horizon + pl->kp.veh_P + 1 > b->ref_len)
+        return fail("veh3dof_tracking: reference too short for t + horizon + pre_horizon + 1 points");
+    }
+    pl->kp.inv_B = inv_batch_global;
+    return launch_rollout_layerwise(pl, b, policy_params, st, grad_out, scalars_out);
+  }
   const bool tcr = b && rollout_use_tc(pl, b->batch);
   if (tcr ? launch_pack_tcf(policy_params, pl->pol_tcf, pl->blob_pol_tcf, st)
           : launch_pack(policy_params, pl->kp.pol, pl->kp.hid, pl->blob_pol, st)) return 1;

@@ -1,5 +1,6 @@
 // Instantiations of the fused rollout kernel for ModelIdp (own translation unit: parallel build).
 #include "kernel.cuh"
+#include "lw_rollout.cuh"
 #include "rollout_tc2.cuh"
 
 namespace gops {
@@ -42,5 +43,13 @@ RolloutFn rollout_fn_tc2_idp(int alg) {   // pipelined tcgen05 kernel (two indep
   }
 }
 StepFn step_fn_idp() { return model_step_kernel<ModelIdp>; }
+
+LwFn lw_fn_idp(int which) {   // layer-wise path of the wide nets: init / forward step / reverse step
+  switch (which) {
+    case 0: return lw_init_kernel<ModelIdp>;
+    case 1: return lw_step_kernel<ModelIdp>;
+    default: return lw_reverse_kernel<ModelIdp>;
+  }
+}
 
 }  // namespace gops

@@ -1,5 +1,6 @@
 // Instantiations of the fused rollout kernel for ModelLq (own translation unit: parallel build).
 #include "kernel.cuh"
+#include "lw_rollout.cuh"
 #include "rollout_tc2.cuh"
 
 namespace gops {
@@ -42,5 +43,13 @@ RolloutFn rollout_fn_tc2_lq(int alg) {   // pipelined tcgen05 kernel (two indepe
   }
 }
 StepFn step_fn_lq() { return model_step_kernel<ModelLq>; }
+
+LwFn lw_fn_lq(int which) {   // layer-wise path of the wide nets: init / forward step / reverse step
+  switch (which) {
+    case 0: return lw_init_kernel<ModelLq>;
+    case 1: return lw_step_kernel<ModelLq>;
+    default: return lw_reverse_kernel<ModelLq>;
+  }
+}
 
 }  // namespace gops

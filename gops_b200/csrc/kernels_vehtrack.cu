@@ -1,5 +1,6 @@
 // Instantiations of the fused rollout kernel for ModelVehTrack (own translation unit: parallel build).
 #include "kernel.cuh"
+#include "lw_rollout.cuh"
 
 namespace gops {
 
@@ -22,6 +23,14 @@ RolloutFn rollout_fn_vehtrack(int hid, int cfg, int alg) {
     case ALG_PIM: return pick<ALG_PIM>(hid, cfg);
     case ALG_PEV: return pick<ALG_PEV>(hid, cfg);
     default: return pick<ALG_TRACE>(hid, cfg);
+  }
+}
+
+LwFn lw_fn_vehtrack(int which) {   // layer-wise path of the wide nets: init / forward step / reverse step
+  switch (which) {
+    case 0: return lw_init_kernel<ModelVehTrack>;
+    case 1: return lw_step_kernel<ModelVehTrack>;
+    default: return lw_reverse_kernel<ModelVehTrack>;
   }
 }
 

@@ -53,11 +53,7 @@ __host__ __device__ inline size_t smem_bytes(int w_floats) {
 }
 
 __device__ __forceinline__ void group_sync(int g) { asm volatile("bar.sync %0, 256;" ::"r"(1 + g) : "memory"); }
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}\n" : "=r"(pred));
-  return pred != 0;
-}
+using umma::elect_one;
 
 // 16 accumulator columns of this thread's lane, WITHOUT waiting (issue several, then tm_wait_ld once)
 __device__ __forceinline__ void tm_ld16(uint32_t taddr, uint32_t* r) {

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define GOPS_B200_ABI_VERSION 1
+#define GOPS_B200_ABI_VERSION 2   /* 2: plan_desc.open_loop, mlpnet_*, plan_set_path, launch_count */
 #define GOPS_B200_MAX_ACT 4   /* action dims supported by the fused kernels            */
 #define GOPS_B200_MAX_LQ_N 8  /* pyth_lq state dim upper bound (configs ship n <= 6)   */
 
@@ -105,6 +105,10 @@ typedef struct gops_b200_plan_desc {
   /* vehicle models */
   int32_t veh_pre_horizon;   /* P: obs_dim = 6 + 4 P                                             */
   gops_b200_reftraj reftraj;
+  /* FHADP2 (gops/algorithm/fhadp2.py:98-121): open-loop policy.  1 = `policy` is a FiniteHorizonFullPolicy
+   * (mlp.py:114-145): ONE evaluation on obs_0 emits all `horizon` actions, policy.out_dim = act_dim * horizon (<= 256),
+   * no time input; alg must be GOPS_ALG_FHADP.  Runs on the layer-wise tcgen05 path. */
+  int32_t open_loop;
 } gops_b200_plan_desc;
 
 /* Per-call inputs (one replay batch shard).  Unused pointers are NULL. */
@@ -211,6 +215,38 @@ int gops_b200_model_step(gops_b200_plan* plan, const gops_b200_batch* batch, con
 int gops_b200_rollout_trace(gops_b200_plan* plan, const gops_b200_batch* batch,
                             const float* policy_params, float* obs_out, float* act_out,
                             float* rew_out, float* done_out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Layer-wise MLP on the tensor cores (tcgen05 / TMEM, BF16x3): a trainable `mlp()` network of 1..8 Linear layers with
+ * widths <= 256, one hidden activation and a linear output -- reference gops/apprfunc/mlp.py:36-41 evaluated and
+ * differentiated layer by layer.  It is the path of the networks the fused rollout kernels do not cover:
+ * [256,256] policies (FHADP veh3dof_tracking), the [256,256,256] nets of DSAC (mlp.py:149-221, 271-296) and the
+ * open-loop FiniteHorizonFullPolicy of FHADP2 (mlp.py:114-145).
+ *   params: flat fp32 vector in torch parameters() order (W0, b0, W1, b1, ...), as everywhere in this header.
+ *   pack:   split the weights into bf16 planes once per parameter update (forward and transposed images).
+ *   forward(slot, train): y = net(x); with train != 0 the hidden activations and their derivatives are kept in `slot`
+ *           (x itself is NOT copied: it must stay valid until the matching backward).
+ *   backward(slot): given dL/dy of that forward pass, overwrite or accumulate the flat gradient (grad_flat may be NULL)
+ *           and / or write dL/dx (dx may be NULL).  Deterministic (fixed-order reductions).
+ */
+typedef struct gops_b200_mlpnet gops_b200_mlpnet;
+int gops_b200_mlpnet_create(const int32_t* sizes, int32_t n_sizes, int32_t hidden_act, int64_t max_batch,
+                            int32_t slots, gops_b200_mlpnet** out);
+int gops_b200_mlpnet_destroy(gops_b200_mlpnet* net);
+int64_t gops_b200_mlpnet_param_count(const gops_b200_mlpnet* net);
+int gops_b200_mlpnet_pack(gops_b200_mlpnet* net, const float* params, void* stream);
+int gops_b200_mlpnet_forward(gops_b200_mlpnet* net, const float* x, int32_t ldx, int64_t batch, int32_t slot,
+                             int32_t train, float* y, int32_t ldy, void* stream);
+int gops_b200_mlpnet_backward(gops_b200_mlpnet* net, const float* dy, int32_t lddy, int64_t batch, int32_t slot,
+                              float* grad_flat, int32_t accumulate, float* dx, int32_t lddx, void* stream);
+/* Rollouts (one forward / backward pass per horizon step, one slot per step): keep_deltas(1) makes every backward pass
+ * (called with grad_flat = NULL) leave its per-layer deltas in its slot; wgrad_slots then contracts the weight
+ * gradients over all `nslots` passes at once (x / dy: input and output adjoint of slot0; slot s of them starts
+ * x_stride / dy_stride rows further). */
+int gops_b200_mlpnet_keep_deltas(gops_b200_mlpnet* net, int32_t enable);
+int gops_b200_mlpnet_wgrad_slots(gops_b200_mlpnet* net, int32_t slot0, int32_t nslots, int64_t batch, const float* x,
+                                 int32_t ldx, int64_t x_stride, const float* dy, int32_t lddy, int64_t dy_stride,
+                                 float* grad_flat, int32_t accumulate, void* stream);
 
 #ifdef __cplusplus
 }

@@ -182,6 +182,15 @@ def main():
     d = orc.sample_inputs("pyth_idpendulum", 128, 22)
     d["obs"] = d["obs"] * torch.tensor([1.0, 0.2, 0.2, 0.2, 0.2, 0.2])     # near upright: finite 80-step rollouts
     run_case("fhadp_idp_h80_nomask", kw, d, [0])
+    # FHADP2 / FiniteHorizonFullPolicy (open-loop policy, fhadp2.py:98-121, mlp.py:114-145)
+    kw = base_kwargs("pyth_idpendulum", "FHADP2", 6, 1, (64, 64), "gelu", "FiniteHorizonFullPolicy", pre_horizon=20,
+                     reward_scale=1.0, policy_learning_rate=1e-3)
+    d = orc.sample_inputs("pyth_idpendulum", 256, 23)
+    d["obs"] = d["obs"] * torch.tensor([1.0, 0.3, 0.3, 0.3, 0.3, 0.3])
+    run_case("fhadp2_idp", kw, d, [0])
+    rec = dict(np.load(os.path.join(OUT, "fhadp2_idp.npz")))
+    rec["pre_horizon"] = np.int64(20)
+    np.savez_compressed(os.path.join(OUT, "fhadp2_idp.npz"), **rec)
     if "--only-new" in sys.argv:
         return
 

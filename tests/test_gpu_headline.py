@@ -3,7 +3,7 @@ kernel ran through the plan's launch record): fused sm_100a update vs. the fp32 
 
   C1  FHADP pyth_idpendulum   H=30  B=2^18 and a ragged 200 003          (tcgen05 kernel, many chunks per CTA)
   C2  INFADP pyth_veh3dofconti P=10 n=10 B=4096, PEV and PIM             (mma.sync kernel, 46 inputs)
-  C3  FHADP veh3dof_tracking  P=H=60 [256,256] elu B=8192 (one GPU's shard of 65 536)
+  C3  FHADP veh3dof_tracking  P=H=60 [256,256] elu B=8192 (one GPU's shard of 65 536): layer-wise tcgen05 path
   C5  INFADP pyth_lq s4a2     n=10  B=2^16 (PEV, PIM) and 2^20 (PIM)     (tcgen05 kernel)
 
 Bars: loss 1e-4 relative, gradient 2e-4 relative L2 (1e-3 for pyth_veh3dofconti, see test_gpu_parity.py), number of
@@ -112,8 +112,15 @@ def test_c3_fhadp_veh3dof_tracking_w256_b8192():
     pol = _spec(alg.networks.policy, "pi", "elu", True)
     env = orc.create_env_model("veh3dof_tracking", pre_horizon=H)
     ref_loss, ref_g, _ = oracle_chunked(lambda d: orc.fhadp_loss(pol, env, d, H, 1.0), data, pol.params(), chunk=1024)
-    alg._compute_gradient(_gpu_data("veh3dof_tracking", data))
+    gd = _gpu_data("veh3dof_tracking", data)
+    alg._compute_gradient(gd)
+    _check(alg, "policy", alg.tb_info["Loss/Actor loss-RL iter"], ref_loss, ref_g, GRAD_RTOL, "tc")
+    g_tc = alg.networks.policy.flat_params.gbuf.clone()
+    alg.kernel_path = "mma"                      # the fused FP32-FFMA kernel stays available as the A/B baseline
+    alg._compute_gradient(gd)
     _check(alg, "policy", alg.tb_info["Loss/Actor loss-RL iter"], ref_loss, ref_g, GRAD_RTOL, "mma")
+    g_mma = alg.networks.policy.flat_params.gbuf
+    assert (g_tc[:-4] - g_mma[:-4]).norm() <= 2e-4 * g_mma[:-4].norm()
 
 
 @pytest.mark.parametrize("B,its", [(1 << 16, (0, 1)), (1 << 20, (1,))])

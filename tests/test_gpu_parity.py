@@ -186,6 +186,8 @@ def _oracle_nets(alg, hidden_act, dtype):
     ("veh3dof_tracking", "FHADP", "elu", 250, 10),
     ("pyth_idpendulum", "FHADP", "gelu256", 300, 8),
     ("pyth_lq", "INFADP", "relu256", 200, 5),
+    ("pyth_lq", "FHADP", "elu256", 700, 12),              # layer-wise tcgen05 path (wide nets, FHADP)
+    ("veh3dof_tracking", "FHADP", "gelu256", 300, 10),
 ])
 def test_against_oracle_fp64(env_id, algname, act, B, H):
     """Fresh seeded inputs, ragged batch sizes (not multiples of the tile), fp64 oracle as truth."""
