@@ -6,7 +6,7 @@ StateValue :309-329); `forward` runs the fused sm_100a inference kernel
 (`gops_b200_mlp_forward`) instead of nn.Sequential.  Training never calls `forward`: the
 algorithms hand the flat parameter vector to the fused rollout kernel.
 """
-__all__ = ["DetermPolicy", "FiniteHorizonPolicy", "FiniteHorizonFullPolicy", "StateValue"]
+__all__ = ["DetermPolicy", "FiniteHorizonPolicy", "FiniteHorizonFullPolicy", "StochaPolicy", "ActionValueDistri", "StateValue"]
 
 import ctypes as C
 
@@ -168,6 +168,93 @@ class FiniteHorizonFullPolicy(nn.Module, Action_Distribution):
         # the squashing below is 3 elementwise ops on [B, H, A] at inference time only (training fuses it)
         act = (self.act_high_lim - self.act_low_lim) / 2 * torch.tanh(z) + (self.act_high_lim + self.act_low_lim) / 2
         return act.to(src)
+
+
+class _LayerwiseNet(nn.Module):
+    """A general `mlp()` network (any depth, widths <= 256) evaluated by the layer-wise tcgen05 MLP."""
+
+    _attr = "net"
+
+    def _build_net(self, sizes, hidden_activation, output_activation="linear"):
+        if output_activation != "linear":
+            raise NotImplementedError("gops_b200 fused MLP kernels support output_activation='linear' only")
+        if max(sizes) > 256 or len(sizes) > 9:
+            raise NotImplementedError(f"gops_b200 layer-wise MLP: widths <= 256, <= 8 layers, got {sizes}")
+        self._sizes, self._hidden_act = [int(v) for v in sizes], hidden_activation
+        setattr(self, self._attr, mlp(self._sizes, get_activation_func(hidden_activation), get_activation_func("linear")))
+        self.__dict__["_flat_params"] = FlatParams(getattr(self, self._attr))
+        self.__dict__["_nets"] = {}
+
+    @property
+    def flat_params(self) -> FlatParams:
+        return self.__dict__["_flat_params"]
+
+    def layerwise(self, max_batch: int, slots: int = 1, tag: str = "infer"):
+        """The library handle for this network (one per use: inference, training slots); created on first use."""
+        from gops_b200.ops.layerwise_mlp import LayerwiseMlp
+        flat = self.flat_params.sync()
+        if not flat.is_cuda:
+            raise RuntimeError("gops_b200 apprfuncs run on a CUDA device only (no CPU fallback); call .cuda()")
+        net = self.__dict__["_nets"].get(tag)
+        if net is None or net.max_batch < max_batch or net.slots < slots or net.device != flat.device:
+            net = self.__dict__["_nets"][tag] = LayerwiseMlp(self._sizes, self._hidden_act, max_batch=max(max_batch, 256),
+                                                             slots=slots, device=flat.device)
+        return net
+
+    def _raw(self, x: torch.Tensor) -> torch.Tensor:
+        flat = self.flat_params.sync()
+        net = self.layerwise(x.shape[0])
+        net.pack(flat)
+        return net.forward(x, train=False)
+
+
+class StochaPolicy(_LayerwiseNet, Action_Distribution):
+    """Stochastic policy: obs -> (mean, std) of the pre-squash Gaussian (reference mlp.py:149-221, std_type
+    "mlp_shared": one network emits mean and log_std)."""
+
+    _attr = "policy"
+
+    def __init__(self, **kwargs):
+        super().__init__()
+        self.std_type = kwargs["std_type"]
+        if self.std_type != "mlp_shared":
+            raise NotImplementedError(f"gops_b200 StochaPolicy implements std_type='mlp_shared', got {self.std_type}")
+        self._obs_dim, self.act_dim = kwargs["obs_dim"], kwargs["act_dim"]
+        self._build_net([self._obs_dim] + list(kwargs["hidden_sizes"]) + [self.act_dim * 2], kwargs["hidden_activation"],
+                        kwargs.get("output_activation", "linear"))
+        self.min_log_std, self.max_log_std = kwargs["min_log_std"], kwargs["max_log_std"]
+        self.register_buffer("act_high_lim", torch.from_numpy(np.asarray(kwargs["act_high_lim"], dtype=np.float32)))
+        self.register_buffer("act_low_lim", torch.from_numpy(np.asarray(kwargs["act_low_lim"], dtype=np.float32)))
+        self.action_distribution_cls = kwargs["action_distribution_cls"]
+
+    def forward(self, obs):
+        src = obs.device
+        flat = self.flat_params.sync()
+        x = obs.detach().to(flat.device, torch.float32).reshape(-1, self._obs_dim).contiguous()
+        logits = self._raw(x)
+        mean, log_std = torch.chunk(logits, chunks=2, dim=-1)
+        std = torch.clamp(log_std, self.min_log_std, self.max_log_std).exp()       # 2 elementwise ops, inference only
+        return torch.cat((mean, std), dim=-1).to(src)
+
+
+class ActionValueDistri(_LayerwiseNet):
+    """Distributional action value: (obs, act) -> (mean, softplus(raw std)) (reference mlp.py:271-296)."""
+
+    _attr = "q"
+
+    def __init__(self, **kwargs):
+        super().__init__()
+        self._obs_dim, self.act_dim = kwargs["obs_dim"], kwargs["act_dim"]
+        self._build_net([self._obs_dim + self.act_dim] + list(kwargs["hidden_sizes"]) + [2], kwargs["hidden_activation"],
+                        kwargs.get("output_activation", "linear"))
+
+    def forward(self, obs, act):
+        src = obs.device
+        flat = self.flat_params.sync()
+        x = torch.cat([obs, act], dim=-1).detach().to(flat.device, torch.float32).contiguous()
+        out = self._raw(x)
+        mean, raw = torch.chunk(out, chunks=2, dim=-1)
+        return torch.cat((mean, torch.nn.functional.softplus(raw)), dim=-1).to(src)
 
 
 class StateValue(_FusedMlp):

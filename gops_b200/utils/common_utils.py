@@ -6,7 +6,8 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-from gops_b200.utils.act_distribution_type import DiracDistribution, ValueDiracDistribution
+from gops_b200.utils.act_distribution_type import (DiracDistribution, TanhGaussDistribution,  # noqa: F401
+                                                    ValueDiracDistribution)
 
 _ACTIVATIONS = {"relu": nn.ReLU, "elu": nn.ELU, "gelu": nn.GELU, "selu": nn.SELU, "sigmoid": nn.Sigmoid,
                 "tanh": nn.Tanh, "linear": nn.Identity}

@@ -248,6 +248,31 @@ int gops_b200_mlpnet_wgrad_slots(gops_b200_mlpnet* net, int32_t slot0, int32_t n
                                  int32_t ldx, int64_t x_stride, const float* dy, int32_t lddy, int64_t dy_stride,
                                  float* grad_flat, int32_t accumulate, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * DSAC (gops/algorithm/dsac.py:155-290): the elementwise half of the update, each with its hand-derived gradient.
+ * The network evaluations between them are gops_b200_mlpnet_* calls.  Device pointers, asynchronous on `stream`.
+ *
+ * sample:   StochaPolicy head (mlp.py:203-221, "mlp_shared") + TanhGaussDistribution.rsample
+ *           (act_distribution_type.py:37-50).  logits [B][2A] raw policy-net outputs (mean | log_std), eps [B][A]
+ *           standard-normal noise.  act [B][A], logp [B].  If qin != NULL the critic input row [obs | act] is written
+ *           (ldq floats per row).  stats (optional, [2B]): tanh(mean_0) and std_0 per sample (tb scalars).
+ * sample_backward: d loss / d logits given d loss / d act (columns act_col0.. of a [B][ldda] matrix, e.g. the
+ *           critic's input gradient) and the coefficient of sum_b logp_b in the loss.
+ * q_loss:   dsac.py:219-262 (clipped TD target, bound / unbound form): gradient w.r.t. the critic output [B][2] and
+ *           out3 = {loss, mean q, mean q_std}.  z_next: standard-normal noise of the target critic sample.
+ * policy_loss: dsac.py:264-275: out5 = {loss, entropy, mean(logp + target_entropy), mean tanh(mean_0), mean std_0}. */
+int gops_b200_dsac_sample(const float* logits, const float* eps, int64_t batch, int32_t act_dim, float min_log_std,
+                          float max_log_std, const float* act_half, const float* act_mid, float* act, float* logp,
+                          const float* obs, int32_t obs_dim, float* qin, int32_t ldq, float* stats, void* stream);
+int gops_b200_dsac_sample_backward(const float* logits, const float* eps, int64_t batch, int32_t act_dim,
+                                   float min_log_std, float max_log_std, const float* act_half, const float* d_act,
+                                   int32_t ldda, int32_t act_col0, float logp_coeff, float* d_logits, void* stream);
+int gops_b200_dsac_q_loss(const float* q_out, const float* q_next_out, const float* z_next, const float* logp_next,
+                          const float* rew, const float* done, int64_t batch, float gamma, float alpha, int32_t bound,
+                          float* d_q_out, float* out3, void* stream);
+int gops_b200_dsac_policy_loss(const float* q_out, const float* logp_new, int64_t batch, float alpha,
+                               float target_entropy, float* d_q_out, float* out5, const float* stats, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -160,9 +160,64 @@ def run_trajectory(name, kw, batches, n_updates, remote_every=0):
     print(name, "losses", losses[0], losses[-1], "lr", lrs[0], lrs[-1])
 
 
+def run_dsac(name, n_iter=4, B=128, hidden=(64, 64, 64)):
+    """DSAC.local_update (dsac.py:121-290) on a fixed synthetic replay batch.  The reference draws its Gaussian noise from
+    torch's global generator inside the update; the draws are RECORDED here (wrappers around torch.normal and
+    torch.distributions.normal._standard_normal -- instrumentation of the generator script, the reference is untouched)
+    so that the parity tests can replay exactly the same noise: per update [eps_new, eps_next, z(unused), z_next, z(unused)]."""
+    from gops.create_pkg.create_alg import create_alg
+    import torch.distributions.normal as tdn
+
+    kw = base_kwargs("pyth_idpendulum", "DSAC", 6, 1, hidden, "gelu", "StochaPolicy",
+                     value_func_name="ActionValueDistri", policy_act_distribution="TanhGaussDistribution",
+                     value_learning_rate=3e-4, policy_learning_rate=3e-4, alpha_learning_rate=5e-3, gamma=0.99, tau=0.005,
+                     auto_alpha=True, alpha=0.2, delay_update=2, TD_bound=10, bound=True,
+                     policy_min_log_std=-20, policy_max_log_std=1, value_hidden_sizes=list(hidden),
+                     policy_hidden_sizes=list(hidden))
+    torch.manual_seed(777)
+    alg = create_alg(**kw)
+    g = torch.Generator().manual_seed(5)
+    obs = orc.sample_inputs("pyth_idpendulum", B, 60)["obs"]
+    data = {"obs": obs, "act": torch.rand(B, 1, generator=g) * 2 - 1, "rew": torch.randn(B, generator=g) * 3 + 5,
+            "obs2": obs + 0.05 * torch.randn(B, 6, generator=g), "done": (torch.rand(B, generator=g) < 0.05).float()}
+    rec = {"in_" + k: _np(v) for k, v in data.items()}
+    for k, v in _sd(alg).items():
+        rec["init/" + k] = v
+    noise = []
+    o_sn, o_nm = tdn._standard_normal, torch.normal
+
+    def sn(*a, **k):
+        x = o_sn(*a, **k); noise.append(x.clone()); return x
+
+    def nm(*a, **k):
+        x = o_nm(*a, **k); noise.append(x.clone()); return x
+    tdn._standard_normal, torch.normal = sn, nm
+    try:
+        torch.manual_seed(4242)
+        for it in range(n_iter):
+            noise.clear()
+            tb = alg.local_update({k: v.clone() for k, v in data.items()}, it)
+            assert len(noise) == 5, len(noise)
+            rec[f"it{it}/eps_new"], rec[f"it{it}/eps_next"], rec[f"it{it}/z_next"] = _np(noise[0]), _np(noise[1]), _np(noise[3])
+            for k, v in tb.items():
+                if "Time" not in k:
+                    rec[f"it{it}/tb/{k}"] = np.float64(v)
+            for nm_ in ("policy", "q"):
+                for pn, p in getattr(alg.networks, nm_).named_parameters():
+                    rec[f"it{it}/grad/{nm_}.{pn}"] = _np(p.grad).copy()
+            rec[f"it{it}/grad/log_alpha"] = _np(alg.networks.log_alpha.grad).copy()
+            for k, v in _sd(alg).items():
+                rec[f"it{it}/post/{k}"] = v
+    finally:
+        tdn._standard_normal, torch.normal = o_sn, o_nm
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **rec)
+    print(name, {k: float(v) for k, v in rec.items() if "it0/tb/" in k})
+
+
 def main():
     ref_shim.install()
     torch.set_num_threads(4)
+    run_dsac("dsac_idp")
 
     # K = 20 consecutive updates, LinearLR scheduler, every 5th through the remote-update entry points
     kw = base_kwargs("pyth_idpendulum", "FHADP", 6, 1, (64, 64), "gelu", "FiniteHorizonPolicy", pre_horizon=30,
