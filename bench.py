@@ -329,7 +329,7 @@ def secondary_configs(hx, peaks, K=10, W=3):
             flop = (flop_pev if phase == 0 else flop_pim) if infadp else flop_pim
             k_ms = statistics.mean(kms)
             ach = B * horizon * flop / (k_ms * 1e-3) / 1e12
-            wide_ffma = kw["policy_hidden_sizes"][0] > 64
+            wide_ffma = kw["policy_hidden_sizes"][0] > 64 and path != "tc"
             peak = ffma_peak if wide_ffma else burst / 6.0
             rows.append({
                 "name": name + ((" PEV" if phase == 0 else " PIM") if infadp else ""), "batch": B, "horizon": horizon,
@@ -351,6 +351,44 @@ def secondary_configs(hx, peaks, K=10, W=3):
     run("C3 FHADP veh3dof_tracking H=60 [256,256] B=8192/GPU",
         alg_kwargs("veh3dof_tracking", "FHADP", 256, "elu", 6 + 4 * 60, 2, pre_horizon=60, policy_learning_rate=1e-3),
         d, 60, None, 7.8e5)
+    # C4 DSAC idpendulum, [256,256,256] gelu, minibatch 8192 from the on-device replay buffer: one update = 5 network
+    # evaluations + 3 back-propagations on the layer-wise tcgen05 MLP (2.7 MFLOP algorithmic per sample)
+    try:
+        from gops_b200.trainer.device_buffer import DeviceReplayBuffer
+        torch.manual_seed(0)
+        dkw = alg_kwargs("pyth_idpendulum", "DSAC", 256, "gelu", 6, 1, policy_func_name="StochaPolicy",
+                         policy_hidden_sizes=[256, 256, 256], value_hidden_sizes=[256, 256, 256],
+                         policy_act_distribution="TanhGaussDistribution", policy_min_log_std=-20, policy_max_log_std=1,
+                         value_func_name="ActionValueDistri", value_learning_rate=3e-4, policy_learning_rate=3e-4,
+                         alpha_learning_rate=5e-5, gamma=0.99, tau=0.005, auto_alpha=True, alpha=0.2, delay_update=2,
+                         TD_bound=10, bound=True)
+        dsac = create_alg(**dkw)
+        buf = DeviceReplayBuffer(6, 1, 1 << 20, device=dev, seed=1)
+        o = ds.sample_idpendulum(1 << 18, dev, seed=2)["obs"]
+        buf.add_batch({"obs": o, "act": torch.rand(1 << 18, 1, device=dev) * 2 - 1, "rew": torch.randn(1 << 18, device=dev),
+                       "obs2": o + 0.01 * torch.randn_like(o), "done": torch.zeros(1 << 18, device=dev)})
+        MB = 8192
+        for i in range(W):
+            dsac.local_update(buf.sample_batch(MB), i)
+        torch.cuda.synchronize()
+        n0 = _lib.lib().gops_b200_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(K):
+            dsac.local_update(buf.sample_batch(MB), i)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / K
+        flop = 2.7e6
+        ach = MB * flop / (ms * 1e-3) / 1e12
+        rows.append({"name": "C4 DSAC idpendulum [256,256,256] minibatch 8192 (on-device replay buffer)", "batch": MB,
+                     "value": MB / (ms * 1e-3), "unit": "samples/s", "ms_per_step": ms, "kernel_path": "tc",
+                     "launches_per_update": (_lib.lib().gops_b200_launch_count() - n0) / K,
+                     "roofline": {"bound": "tensor", "achieved": ach, "peak": burst / 6.0, "unit": "TFLOP/s",
+                                  "frac": ach / (burst / 6.0), "algorithmic_flop_per_sample": flop}})
+        del dsac, buf
+    except Exception as e:      # a secondary config must never take the bench down
+        rows.append({"name": "C4 DSAC", "error": repr(e)[:300]})
     # C5 INFADP LQ s4a2 batch sweep
     for e in (10, 12, 14, 16, 18, 20):
         B = 1 << e

@@ -1,7 +1,8 @@
 """Layer-wise tcgen05 MLP (csrc/dense_tc.cu, BF16x3) against a plain PyTorch reference of the same network evaluated in
 fp64: outputs, parameter gradients (torch flat order) and input gradients, ragged batches, widths that are not
 multiples of the tile sizes, gradient accumulation, several live forward passes (slots).
-Bars: outputs 2e-6 relative to the output scale (FP32-accurate six-term products), gradients 1e-4 relative L2
+Bars: outputs 4e-6 relative to the output scale (FP32-accurate six-term products; FP32 accumulation over up to 256
+inputs per layer, three layers), gradients 1e-4 relative L2
 (two-plane deltas, three-term products)."""
 import numpy as np
 import pytest
@@ -46,7 +47,7 @@ def test_forward_backward_against_fp64(sizes, act, B):
     xg = x.cuda()
     y = net.forward(xg, slot=1)
     scale = float(y64.abs().max())
-    assert float((y.cpu().double() - y64.detach()).abs().max()) <= 2e-6 * max(1.0, scale)
+    assert float((y.cpu().double() - y64.detach()).abs().max()) <= 4e-6 * max(1.0, scale)
     grad = torch.zeros(net.nparam, device="cuda")
     dx = net.backward(dy.cuda(), slot=1, grad=grad, want_dx=True)
     torch.cuda.synchronize()
