@@ -71,7 +71,13 @@ struct DevGuard2 {
 template <int EPI, bool GRAD>
 int launch_gemm(gops_b200_mlpnet* net, const dense::GemmArgs& a, cudaStream_t st) {
   const size_t smem = dense::gemm_smem(a.n, GRAD);
-  DCUDA(cudaFuncSetAttribute(dense::dense_gemm_kernel<EPI, GRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  static bool attr_of[64] = {};        // per template instantiation and device: the widest tile (N = 128)
+  bool& attr = attr_of[net->device & 63];
+  if (!attr) {
+    DCUDA(cudaFuncSetAttribute(dense::dense_gemm_kernel<EPI, GRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)dense::gemm_smem(dense::NCMAX, GRAD)));
+    attr = true;
+  }
   dim3 grid((unsigned)((a.rows + dense::TM - 1) / dense::TM), (unsigned)dense::splits_of(a.n));
   dense::dense_gemm_kernel<EPI, GRAD><<<grid, dense::NTH, smem, st>>>(a);
   gops::dense_count_launch(1);

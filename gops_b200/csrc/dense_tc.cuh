@@ -90,24 +90,36 @@ struct GemmArgs {
 };
 
 // rows [r0, r0 + 128) x columns [k0, k0 + 64) of a row-major fp32 matrix -> NPL bf16 planes [8 chunks][128 rows][8]
-// (`PL`: byte stride between planes; the 8 chunks land at planes + chunk * 2048)
-template <int NPL>
-__device__ __forceinline__ void stage_tile(const float* __restrict__ src, int ld, long long r0, long long rows, int k0,
-                                           int kcols, unsigned char* planes, int PL = 8 * TM * 16) {
+// (`PL`: byte stride between planes; the 8 chunks land at planes + chunk * 2048).  Split into a LOAD half (global ->
+// registers; all 32-byte reads of a tile are issued back to back, so their HBM / L2 latencies overlap -- and callers
+// prefetch the next tile while the tensor core works on the current one) and a STORE half (split + shared stores).
+struct TileRegs {
+  float v[(8 * TM) / NTH][8];
+};
+__device__ __forceinline__ void load_tile(const float* __restrict__ src, int ld, long long r0, long long rows, int k0,
+                                          int kcols, TileRegs& t) {
 #pragma unroll
   for (int i = 0; i < (8 * TM) / NTH; ++i) {
     const int idx = threadIdx.x + NTH * i, kc = idx >> 7, r = idx & 127;
-    float v[8];
     const long long row = r0 + r;
     const int k = k0 + 8 * kc;
     if (row < rows && k + 8 <= kcols && ((ld & 3) == 0)) {
       const float4 a = *reinterpret_cast<const float4*>(src + row * ld + k);
       const float4 b = *reinterpret_cast<const float4*>(src + row * ld + k + 4);
-      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+      t.v[i][0] = a.x; t.v[i][1] = a.y; t.v[i][2] = a.z; t.v[i][3] = a.w;
+      t.v[i][4] = b.x; t.v[i][5] = b.y; t.v[i][6] = b.z; t.v[i][7] = b.w;
     } else {
 #pragma unroll
-      for (int e = 0; e < 8; ++e) v[e] = (row < rows && k + e < kcols) ? src[row * ld + k + e] : 0.f;
+      for (int e = 0; e < 8; ++e) t.v[i][e] = (row < rows && k + e < kcols) ? src[row * ld + k + e] : 0.f;
     }
+  }
+}
+template <int NPL>
+__device__ __forceinline__ void store_tile(const TileRegs& t, unsigned char* planes, int PL = 8 * TM * 16) {
+#pragma unroll
+  for (int i = 0; i < (8 * TM) / NTH; ++i) {
+    const int idx = threadIdx.x + NTH * i, kc = idx >> 7, r = idx & 127;
+    const float* v = t.v[i];
     uint32_t w[3][4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -152,6 +164,8 @@ __global__ void __launch_bounds__(NTH, 2) dense_gemm_kernel(const __grid_constan
   const size_t img = slice_bytes(nc);
   const unsigned char* Bsrc = g.Bimg + (size_t)split * nsl * img;
   uint32_t ph = 0;
+  TileRegs regs;
+  load_tile(g.A, g.lda, r0, g.rows, 0, g.k, regs);
   for (int t = 0; t < nsl; ++t) {
     if (tid == 0) {
       fence_proxy_async();
@@ -159,7 +173,7 @@ __global__ void __launch_bounds__(NTH, 2) dense_gemm_kernel(const __grid_constan
       for (size_t off = 0; off < img; off += 32768)
         tma_bulk_g2s(Bp + off, Bsrc + (size_t)t * img + off, (uint32_t)(img - off < 32768 ? img - off : 32768), bars);
     }
-    stage_tile<NPA>(g.A, g.lda, r0, g.rows, t * KS, g.k, Ap);
+    store_tile<NPA>(regs, Ap);
     fence_proxy_async();
     mbar_wait(bars, ph);
     __syncthreads();
@@ -191,6 +205,7 @@ __global__ void __launch_bounds__(NTH, 2) dense_gemm_kernel(const __grid_constan
         umma::commit(bars + 1);
       }
     }
+    if (t + 1 < nsl) load_tile(g.A, g.lda, r0, g.rows, (t + 1) * KS, g.k, regs);   // in flight while the tensor core works
     mbar_wait(bars + 1, ph);          // single-buffered operands: the slice's MMAs retire before the next staging
     umma::fence_after_sync();
     ph ^= 1u;
@@ -282,16 +297,24 @@ __global__ void __launch_bounds__(NTH, 1) dense_wgrad_kernel(const __grid_consta
   const long long t0 = (long long)blockIdx.y * g.tiles_per_chunk;
   const long long tps = (g.rows + TM - 1) / TM, ttot = tps * g.nslots;      // tiles per slab, tiles in total
   uint32_t ph = 0, first = 0u;
-  for (int t = 0; t < g.tiles_per_chunk; ++t) {
-    const long long tt = t0 + t;
-    if (tt >= ttot) break;
+  TileRegs ra, rb, rc, rd;
+  auto load4 = [&](long long tt) {
     const long long slab = tt / tps, r0 = (tt - slab * tps) * TM;
     const float* dYs = g.dY + slab * g.sy * g.ldy;
     const float* Xs = g.X + slab * g.sx * g.ldx;
-    stage_tile<2>(dYs, g.ldy, r0, g.rows, n0, g.n, Yp, PL);
-    stage_tile<2>(dYs, g.ldy, r0, g.rows, n0 + 64, g.n, Yp + 8 * TM * 16, PL);
-    stage_tile<2>(Xs, g.ldx, r0, g.rows, k0, g.k, Xp, PL);
-    if (kw > 64) stage_tile<2>(Xs, g.ldx, r0, g.rows, k0 + 64, g.k, Xp + 8 * TM * 16, PL);
+    load_tile(dYs, g.ldy, r0, g.rows, n0, g.n, ra);
+    load_tile(dYs, g.ldy, r0, g.rows, n0 + 64, g.n, rb);
+    load_tile(Xs, g.ldx, r0, g.rows, k0, g.k, rc);
+    if (kw > 64) load_tile(Xs, g.ldx, r0, g.rows, k0 + 64, g.k, rd);
+  };
+  if (t0 < ttot) load4(t0);
+  for (int t = 0; t < g.tiles_per_chunk; ++t) {
+    const long long tt = t0 + t;
+    if (tt >= ttot) break;
+    store_tile<2>(ra, Yp, PL);
+    store_tile<2>(rb, Yp + 8 * TM * 16, PL);
+    store_tile<2>(rc, Xp, PL);
+    if (kw > 64) store_tile<2>(rd, Xp + 8 * TM * 16, PL);
     fence_proxy_async();
     umma::fence_before_sync();
     __syncthreads();
@@ -313,6 +336,7 @@ __global__ void __launch_bounds__(NTH, 1) dense_wgrad_kernel(const __grid_consta
       }
     }
     first = 1u;
+    if (t + 1 < g.tiles_per_chunk && tt + 1 < ttot) load4(tt + 1);      // next tile's reads fly during the MMAs
     mbar_wait(bars, ph);
     umma::fence_after_sync();
     ph ^= 1u;

@@ -293,8 +293,9 @@ bool rollout_use_tc(const gops_b200_plan* pl, long long batch) {
   if (e && !strcmp(e, "mma")) path = GOPS_PATH_MMA;
   if (e && !strcmp(e, "tc")) path = GOPS_PATH_TC;
   if (path == GOPS_PATH_MMA) return false;
-  (void)batch;      // the pipelined kernel schedules single 128-sample sub-tiles: it is the default at every batch size
-  return true;
+  // the pipelined kernel schedules single 128-sample sub-tiles; below ~2^14 samples (fewer sub-tiles than SM slots) the
+  // mma.sync kernel with its 32-sample tiles spreads the batch over more SMs and finishes first (bench.py configs, C5 sweep)
+  return batch >= 16384;
 }
 __global__ void pack_params_tcf_kernel(const float* __restrict__ flat, NetL L, float* __restrict__ blob) {
   const int n = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
@@ -446,9 +447,11 @@ int launch_rollout_layerwise(gops_b200_plan* pl, const gops_b200_batch* b, const
     if (gops_b200_mlpnet_pack(pl->lw_net, policy_params, st)) return 1;
     if (gops_b200_mlpnet_forward(pl->lw_net, b->obs, kp.pol.obs, B, 0, 1, pl->lw_Z, H * A, st)) return 1;
     f_init<<<grid, 128, 0, st>>>(kp, a);
+    const int sub = pl->desc.model == GOPS_MODEL_VEH3DOF_TRACKING ? LW_SUB : 1;
+    const unsigned grid_step = (unsigned)((B * sub + 127) / 128);
     for (int k = 0; k < H; ++k) {
       a.k = k;
-      f_step<<<grid, 128, 0, st>>>(kp, a);
+      f_step<<<grid_step, 128, 0, st>>>(kp, a);
     }
     for (int k = H - 1; k >= 0; --k) {
       a.k = k;
@@ -501,11 +504,13 @@ int launch_rollout_layerwise(gops_b200_plan* pl, const gops_b200_batch* b, const
   if (gops_b200_mlpnet_pack(pl->lw_net, policy_params, st)) return 1;
   f_init<<<grid, 128, 0, st>>>(kp, a);
   ++g_launches;
+  const int sub = pl->desc.model == GOPS_MODEL_VEH3DOF_TRACKING ? LW_SUB : 1;
+  const unsigned grid_step = (unsigned)((B * sub + 127) / 128);
   for (int k = 0; k < H; ++k) {
     if (gops_b200_mlpnet_forward(pl->lw_net, pl->lw_X + (size_t)k * cap * ldx, ldx, B, k, 1, pl->lw_Z + (size_t)k * cap * A, A, st))
       return 1;
     a.k = k;
-    f_step<<<grid, 128, 0, st>>>(kp, a);
+    f_step<<<grid_step, 128, 0, st>>>(kp, a);
     ++g_launches;
   }
   for (int k = H - 1; k >= 0; --k) {

@@ -57,11 +57,17 @@ __global__ void lw_init_kernel(const __grid_constant__ KParams p, const __grid_c
   for (int f = 0; f < NS; ++f) a.lam[(size_t)f * B + b] = 0.f;
 }
 
-// forward step k (reference: one iteration of the loop in fhadp.py:118-123 through the wrapper chain)
+// forward step k (reference: one iteration of the loop in fhadp.py:118-123 through the wrapper chain).
+// SUB threads per sample: all of them run the (cheap) action / reward / state update redundantly, the observation
+// rebuild -- P + 1 ego-frame transforms per sample, the bulk of the work for the vehicle models -- is dealt over them.
+constexpr int LW_SUB = 8;
 template <class M>
 __global__ void lw_step_kernel(const __grid_constant__ KParams p, const __grid_constant__ LwArgs a) {
   constexpr int NS = M::NS;
-  const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  constexpr int SUB = M::KIND == 0 ? 1 : LW_SUB;
+  const long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long b = gt / SUB;
+  const int sub = (int)(gt % SUB);
   const long long B = p.batch;
   if (b >= B) return;
   const int k = a.k, obs_dim = p.pol.obs;
@@ -114,17 +120,30 @@ __global__ void lw_step_kernel(const __grid_constant__ KParams p, const __grid_c
             0.01f * (act[0] * act[0]) + 0.01f * (act[1] * act[1]));
       veh_step(vc, st, act);
       w.k0 = p.ref_t + k + 1;
-      if (wx) {
-        veh_write_obs<2, 1>(st, w, p.veh_P, xn, 1, o6);
-        if (p.obs_scaling) veh_scale_obs(p, obs_dim, xn, 1);
+      if (wx) {      // get_obs of the new state: point i of the window by sub-thread i mod SUB
+        float sn, cs, o4[4];
+        sincosf(-st[2], &sn, &cs);
+        for (int i = sub; i <= p.veh_P; i += SUB) {
+          w.get(i, q);
+          ego_obs(st, cs, sn, q[0], q[1], q[2], q[3], o4);
+          const int f0 = i == 0 ? 0 : 6 + 4 * (i - 1);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) xn[f0 + c] = p.obs_scaling ? (o4[c] + p.osh[f0 + c]) * p.osc[f0 + c] : o4[c];
+          if (i == 0) {
+            xn[4] = p.obs_scaling ? (st[4] + p.osh[4]) * p.osc[4] : st[4];
+            xn[5] = p.obs_scaling ? (st[5] + p.osh[5]) * p.osc[5] : st[5];
+          }
+        }
+        (void)o6;
       }
       w.get(0, q);
       dn = (fabsf(st[0] - q[0]) > 5.f) || (fabsf(st[1] - q[1]) > 2.f) ||
            (fabsf(angle_normalize(st[2] - q[2])) > 3.14159265358979323846f);
     } else if (wx) {
-      for (int f = 0; f < obs_dim; ++f) xn[f] = xk[f];               // MaskAtDone: the observation is frozen
+      for (int f = sub; f < obs_dim; f += SUB) xn[f] = xk[f];        // MaskAtDone: the observation is frozen
     }
   }
+  if (sub != 0) return;
   if (wx) {
     if (p.pol.time_input) xn[obs_dim] = (float)(k + 2);
     for (int f = obs_dim + p.pol.time_input; f < a.ldx; ++f) xn[f] = 0.f;
