@@ -48,6 +48,7 @@ class PlanDesc(C.Structure):
         ("lq_dt", C.c_float), ("lq_reward_scale", C.c_float), ("lq_reward_shift", C.c_float),
         ("veh_pre_horizon", C.c_int32), ("reftraj", RefTraj),
         ("open_loop", C.c_int32),
+        ("veh_errcstr", C.c_int32), ("veh_y_error_tol", C.c_float), ("veh_u_error_tol", C.c_float),
     ]
 
 
@@ -70,6 +71,7 @@ PROTOTYPES = {
     "gops_b200_plan_launch_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),
     "gops_b200_plan_set_path": (C.c_int, [C.c_void_p, C.c_int]),
     "gops_b200_plan_last_path": (C.c_int, [C.c_void_p]),
+    "gops_b200_plan_set_constraint": (C.c_int, [C.c_void_p, C.c_int, C.c_float]),
     "gops_b200_plan_param_count": (C.c_int64, [C.c_void_p, C.c_int]),
     "gops_b200_rollout_grad": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_void_p, C.c_void_p, C.c_void_p,
                                          C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -26,7 +26,7 @@ from gops_b200 import _lib
 from gops_b200.algorithm.base import AlgorithmBase, ApprBase
 from gops_b200.create_pkg.create_apprfunc import create_apprfunc
 from gops_b200.utils.common_utils import get_apprfunc_dict
-from gops_b200.utils.flat_params import FusedAdam, polyak_update
+from gops_b200.utils.flat_params import FusedAdam, ScalarAdam, polyak_update
 from gops_b200.utils.tensorboard_setup import tb_tags
 
 
@@ -56,33 +56,6 @@ class ApproxContainer(ApprBase):
 
     def create_action_distributions(self, logits):
         return self.policy.get_act_dist(logits)
-
-
-class ScalarAdam:
-    """torch.optim.Adam (default betas / eps, no weight decay) for a single fp32 scalar parameter, evaluated on the host
-    with numpy float32 arithmetic in torch's operation order (torch/optim/adam.py _single_tensor_adam)."""
-
-    def __init__(self, param: nn.Parameter, lr: float, betas=(0.9, 0.999), eps: float = 1e-8):
-        self.param, self.lr, self.betas, self.eps = param, lr, betas, eps
-        self.step_count, self.m, self.v = 0, np.float32(0), np.float32(0)
-        self.grad: Optional[float] = None
-
-    def zero_grad(self):
-        self.grad = None
-
-    def step(self):
-        if self.grad is None:
-            return
-        g = np.float32(self.grad)
-        b1, b2 = self.betas
-        self.step_count += 1
-        self.m = np.float32(self.m + (g - self.m) * np.float32(1 - b1))
-        self.v = np.float32(self.v * np.float32(b2) + np.float32(1 - b2) * (g * g))
-        bc1, bc2 = 1 - b1 ** self.step_count, 1 - b2 ** self.step_count
-        denom = np.float32(np.sqrt(self.v) / np.float32(math.sqrt(bc2)) + np.float32(self.eps))
-        value = np.float32(np.float32(self.param.item()) - np.float32(self.lr / bc1) * (self.m / denom))
-        with torch.no_grad():
-            self.param.fill_(float(value))
 
 
 class DSAC(AlgorithmBase):

@@ -53,7 +53,7 @@ __global__ void pack_params_kernel(const float* __restrict__ flat, NetL L, int H
 __global__ void reduce_partials_kernel(const float* __restrict__ partial, int n_cta, int stride, int nparam,
                                        float* __restrict__ grad, float* __restrict__ scalars) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= nparam + 3) return;
+  if (i >= nparam + 4) return;
   float s = 0.f;
   for (int c = 0; c < n_cta; ++c) s += partial[(size_t)c * stride + i];
   if (i < nparam) {

@@ -615,7 +615,7 @@ int launch_rollout(gops_b200_plan* pl, const gops_b200_batch* b, int alg, cudaSt
     if (pl->timing) CUDA_OK(cudaEventRecord(pl->ev1, st));
     pl->last_grid = grid; pl->last_S = S; pl->last_NT = NT; pl->last_smem = smem; pl->last_path = GOPS_PATH_TC;
     if (alg != ALG_TRACE) {
-      const int n = upd.nparam + 3;
+      const int n = upd.nparam + 4;
       reduce_partials_kernel<<<(n + 255) / 256, 256, 0, st>>>(pl->partial, grid * rows, k2.part_stride, upd.nparam, grad_out,
                                                              scalars_out);
       ++g_launches;
@@ -666,7 +666,7 @@ int launch_rollout(gops_b200_plan* pl, const gops_b200_batch* b, int alg, cudaSt
   if (pl->timing) CUDA_OK(cudaEventRecord(pl->ev1, st));
   pl->last_grid = grid; pl->last_S = S; pl->last_NT = NT; pl->last_smem = smem; pl->last_path = GOPS_PATH_MMA;
   if (alg != ALG_TRACE) {
-    const int n = upd.nparam + 3;
+    const int n = upd.nparam + 4;
     reduce_partials_kernel<<<(n + 255) / 256, 256, 0, st>>>(pl->partial, grid, kp.part_stride, upd.nparam, grad_out,
                                                            scalars_out);
     ++g_launches;
@@ -792,6 +792,8 @@ int gops_b200_plan_create(const gops_b200_plan_desc* d, gops_b200_plan** out) {
     q.sp_c1 = (float)(-r.sp_A / r.sp_omega); q.sp_c3 = (float)(r.sp_A / r.sp_omega * cos(r.sp_phi));
     q.sp_const = (float)r.sp_const;
   }
+  kp.cstr_mode = 0; kp.cstr_coef = 1.f;
+  kp.cstr_y_tol = d->veh_y_error_tol; kp.cstr_u_tol = d->veh_u_error_tol;
   kp.veh_P = d->veh_pre_horizon;
   kp.veh_Pdt = (float)((double)d->veh_pre_horizon * 0.1);   // self.pre_horizon * self.dt
 
@@ -890,6 +892,17 @@ int gops_b200_plan_set_path(gops_b200_plan* pl, int path) {
   return 0;
 }
 int gops_b200_plan_last_path(const gops_b200_plan* pl) { return pl ? pl->last_path : -1; }
+
+int gops_b200_plan_set_constraint(gops_b200_plan* pl, int mode, float coef) {
+  if (!pl) return fail("null plan");
+  if (mode < 0 || mode > 3) return fail("unknown constraint mode");
+  if (mode != 0 && !(pl->desc.model == GOPS_MODEL_VEH3DOFCONTI && pl->desc.veh_errcstr && pl->desc.alg == GOPS_ALG_FHADP))
+    return fail("constrained FHADP variants are built for pyth_veh3dofconti_errcstr (info['constraint'] provider) only");
+  if (mode != 0 && !(coef > 0.f)) return fail("constraint coefficient must be positive");
+  pl->kp.cstr_mode = mode;
+  pl->kp.cstr_coef = coef;
+  return 0;
+}
 
 int gops_b200_plan_launch_info(const gops_b200_plan* pl, int32_t* out4) {
   if (!pl || !out4) return fail("null argument");

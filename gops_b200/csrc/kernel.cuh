@@ -163,6 +163,34 @@ __global__ void __launch_bounds__(NT, 1) rollout_kernel(const __grid_constant__ 
 
   float* tape = p.tape + (size_t)blockIdx.x * (size_t)H * TCH * NT;
   float loss_acc = 0.f, vmean_acc = 0.f, done_acc = 0.f;
+  // constrained variants (pyth_veh3dofconti_errcstr, KIND 1): c = (|y_err| - tol_y, |u_err| - tol_u) of the INCOMING
+  // observation of every step (pyth_veh3dofconti_errcstr_model.py:46-55); info["constraint"] is not masked at done
+  constexpr float CSTR_EPS = 1e-8f;        // fhadp_interior.py:19 EPSILON
+  float feas_acc = 0.f, cint_acc = 0.f;
+  auto cstr_eval = [&](const float* o6, float& c_ext, float& c_lin, float& c_int, bool& infeasible) {
+    const float c0 = fabsf(o6[1]) - p.cstr_y_tol, c1 = fabsf(o6[3]) - p.cstr_u_tol;
+    const float p0 = fmaxf(c0, 0.f), p1 = fmaxf(c1, 0.f);
+    c_ext = p0 * p0 + p1 * p1;
+    c_lin = p0 + p1;
+    c_int = logf(-fminf(c0, 0.f) + CSTR_EPS) + logf(-fminf(c1, 0.f) + CSTR_EPS);
+    infeasible = !(c0 < 0.f) || !(c1 < 0.f);
+  };
+  // d(constraint cost of one step) / d(y_err, u_err), already weighted: w = gamma^k / B
+  auto cstr_grad = [&](const float* o6, float w, bool feasible, float& gy, float& gu) {
+    const float c0 = fabsf(o6[1]) - p.cstr_y_tol, c1 = fabsf(o6[3]) - p.cstr_u_tol;
+    const float s0 = o6[1] > 0.f ? 1.f : (o6[1] < 0.f ? -1.f : 0.f), s1 = o6[3] > 0.f ? 1.f : (o6[3] < 0.f ? -1.f : 0.f);
+    float d0, d1;
+    if (p.cstr_mode == 1 || (p.cstr_mode == 3 && !feasible)) {
+      d0 = p.cstr_coef * 2.f * fmaxf(c0, 0.f); d1 = p.cstr_coef * 2.f * fmaxf(c1, 0.f);
+    } else if (p.cstr_mode == 2) {
+      d0 = c0 > 0.f ? p.cstr_coef : 0.f; d1 = c1 > 0.f ? p.cstr_coef : 0.f;
+    } else {      // interior, feasible sample: (1 / penalty) * d log(-c + eps) / dc = 1 / (penalty (c - eps)) for c <= 0
+      d0 = c0 <= 0.f ? 1.f / (p.cstr_coef * (c0 - CSTR_EPS)) : 0.f;
+      d1 = c1 <= 0.f ? 1.f / (p.cstr_coef * (c1 - CSTR_EPS)) : 0.f;
+    }
+    gy = w * d0 * s0;
+    gu = w * d1 * s1;
+  };
 
   // balanced contiguous sample range of this CTA, processed in chunks of NT samples
   const long long r0 = B * blockIdx.x / gridDim.x, r1 = B * (blockIdx.x + 1) / gridDim.x;
@@ -177,6 +205,8 @@ __global__ void __launch_bounds__(NT, 1) rollout_kernel(const __grid_constant__ 
     const long long gs = pos + col;
     bool dn = valid ? (p.done[gs] != 0.f) : true;
     float vacc = 0.f;
+    float cacc_a = 0.f, cacc_b = 0.f;            // constrained variants: discounted exterior|linear sum, interior (log) sum
+    bool infeasible = false;
     int path = 0, spd = 0;                       // vehicle models: reference path / speed profile ids
     RefWindow<M::KIND, NT> win;
     win.base = nullptr; win.k0 = 0;
@@ -233,6 +263,21 @@ __global__ void __launch_bounds__(NT, 1) rollout_kernel(const __grid_constant__ 
         process_action(p, P.out, z, a, g, apol);
         const bool active = valid && (p.mask_at_done ? !dn : true);
         float r = 0.f;
+        if constexpr (M::KIND == 1) {
+          if (p.cstr_mode != 0 && valid) {
+            float oc[6], ce, cl, ci;
+            bool inf;
+#pragma unroll
+            for (int f = 0; f < 6; ++f) {
+              oc[f] = t.X[f * XS + col];
+              if (p.obs_scaling) oc[f] = oc[f] / p.osc[f] - p.osh[f];
+            }
+            cstr_eval(oc, ce, cl, ci, inf);
+            cacc_a += (p.cstr_mode == 2 ? cl : ce) * p.gpow[k];
+            cacc_b += ci * p.gpow[k];
+            infeasible = infeasible || inf;
+          }
+        }
         if constexpr (M::KIND == 0) {
           // state==obs models: `st` is the wrapper-level (outer) observation; ScaleObservation maps it to the
           // model's inner state and back, ActionRepeat repeats the masked model step with the same action
@@ -324,6 +369,13 @@ __global__ void __launch_bounds__(NT, 1) rollout_kernel(const __grid_constant__ 
       }
     }
     if (valid && dn) done_acc += 1.f;
+    float fz_y = 0.f, fz_u = 0.f;     // constrained variants: (y_err, u_err) of the observation a done sample is frozen at
+    if constexpr (M::KIND == 1) {
+      if (p.cstr_mode != 0) {
+        fz_y = t.X[1 * XS + col]; fz_u = t.X[3 * XS + col];
+        if (p.obs_scaling) { fz_y = fz_y / p.osc[1] - p.osh[1]; fz_u = fz_u / p.osc[3] - p.osh[3]; }
+      }
+    }
     if (alg == ALG_TRACE) continue;
 
     // ============================ terminal value (INFADP) ============================
@@ -392,9 +444,24 @@ __global__ void __launch_bounds__(NT, 1) rollout_kernel(const __grid_constant__ 
     }
 
     if (valid) loss_acc += -vacc * p.inv_B;
+    const bool feasible = !infeasible;
+    if constexpr (M::KIND == 1) {
+      if (p.cstr_mode != 0 && valid) {
+        // exterior: penalty * mean(v_c); Lagrangian: multiplier * mean(v_c);
+        // interior: mean(v_int * feasible) / penalty + penalty * mean(v_ext * ~feasible)   (fhadp_interior.py:78-84)
+        float cl;
+        if (p.cstr_mode == 3) cl = feasible ? cacc_b / p.cstr_coef : p.cstr_coef * cacc_a;
+        else cl = p.cstr_coef * cacc_a;
+        loss_acc += cl * p.inv_B;
+        vmean_acc += ((p.cstr_mode == 3 && feasible) ? 0.f : cacc_a) * p.inv_B;   // tb "constraint loss" (exterior part)
+        if (p.cstr_mode == 3) cint_acc += feasible ? cacc_b / p.cstr_coef * p.inv_B : 0.f;
+        feas_acc += feasible ? 1.f : 0.f;
+      }
+    }
     if (alg == ALG_PIM) stage(p.blob_pol, P.blob);
 
     // ================================ reverse sweep ================================
+    float cbar_y = 0.f, cbar_u = 0.f;   // constrained variants: adjoint of the FROZEN observation carried to the step that made it
     for (int k = H - 1; k >= 0; --k) {
       // per-sample adjoint of step k on every thread (state, done flag and policy output come from the tape)
       if constexpr (M::KIND != 0) {
@@ -532,6 +599,30 @@ __global__ void __launch_bounds__(NT, 1) rollout_kernel(const __grid_constant__ 
         MLP_BWD(true, P, ts, k > 0);
       }
       if constexpr (TC) tcf_flush<NT>(P, cf, part);
+      if constexpr (M::KIND == 1) {
+        if (p.cstr_mode != 0 && valid && k > 0) {
+          // The constraint of step k reads obs_k.  obs_k was MADE by step k - 1 iff the sample was live there (MaskAtDone
+          // freezes the observation afterwards): then its adjoint (this step's + the carry of the frozen copies) goes
+          // through get_obs onto state_k; else obs_k is a copy of obs_{k-1} and the adjoint is carried on.
+          const bool made_here = p.mask_at_done ? tape[((k - 1) * TCH + NS) * NT + tid] == 0.f : true;
+          const bool live = !(p.mask_at_done && dnk);
+          float oc[6] = {0.f, live ? o6[1] : fz_y, 0.f, live ? o6[3] : fz_u, 0.f, 0.f};
+          float gy, gu;
+          cstr_grad(oc, p.gpow[k] * p.inv_B, feasible, gy, gu);
+          gy += cbar_y; gu += cbar_u;
+          if (made_here) {
+            cbar_y = cbar_u = 0.f;
+            if (active) {
+              ro6[1] += gy; ro6[3] += gu;      // joins the reward's observation adjoint in veh_obs_bwd below
+            } else {                           // done AT step k - 1: only the constraint looks at this observation
+              const float e6[6] = {0.f, gy, 0.f, gu, 0.f, 0.f};
+              veh_obs_bwd<M::KIND, NT>(st, win, p.veh_P, t.X + col, XS, e6, p.obs_scaling ? p.osc : nullptr, lam);
+            }
+          } else {
+            cbar_y = gy; cbar_u = gu;
+          }
+        }
+      }
       if (active && k > 0) {
         if constexpr (M::KIND == 0) {
 #pragma unroll
@@ -567,12 +658,20 @@ __global__ void __launch_bounds__(NT, 1) rollout_kernel(const __grid_constant__ 
   float* red = t.H1;  // free at this point, HID*(S+4) >= 3*NT floats
   red[tid] = loss_acc;
   red[NT + tid] = vmean_acc;
-  red[2 * NT + tid] = done_acc;
+  red[2 * NT + tid] = p.cstr_mode == 3 ? cint_acc : done_acc;     // interior point: the weighted log-barrier term
   __syncthreads();
   if (tid < 3) {
     float s = 0.f;
     for (int i = 0; i < NT; ++i) s += red[tid * NT + i];
     part[nparam + tid] = s;
+  }
+  __syncthreads();
+  red[tid] = feas_acc;              // constrained variants: number of feasible samples (slot 3 of the scalar tail)
+  __syncthreads();
+  if (tid == 0) {
+    float s = 0.f;
+    for (int i = 0; i < NT; ++i) s += red[i];
+    part[nparam + 3] = s;
   }
   if constexpr (TC) {
     umma::fence_before_sync();

@@ -84,6 +84,10 @@ struct KParams {
   long long* dbg;          // development aid (GOPS_B200_TIMELINE): clock64 stamps of one owner and one helper thread
   // trace outputs (alg == ALG_TRACE)
   float* tr_obs; float* tr_act; float* tr_rew; float* tr_done;
+  // constrained FHADP variants (fhadp_exterior / fhadp_lagrangian / fhadp_interior.py): 0 none, 1 exterior penalty,
+  // 2 Lagrangian, 3 interior point; cstr_coef = penalty / multiplier; tolerances of the error-constraint vehicle model
+  int cstr_mode;
+  float cstr_coef, cstr_y_tol, cstr_u_tol;
   // wrappers
   int action_scale, clip_action, clip_obs, mask_at_done, reward_shaping;
   float reward_shift, reward_scale;

@@ -123,5 +123,6 @@ def fused_forward(top, obs, action, done, info):
             plan.handle, C.byref(b), _lib.ptr(act), _lib.ptr(nobs), _lib.ptr(rew), _lib.ptr(ndone),
             _lib.ptr(extra.get("state")), _lib.ptr(extra.get("ref_points")), _lib.ptr(extra.get("ref_time")),
             _lib.stream_ptr()))
+    extra["_obs_in"] = obs_d if not getattr(top, "_scales_obs", False) else obs_d     # constraint providers read the incoming obs
     next_info = base.make_next_info(info, extra)
     return nobs.to(src), rew.to(src), (ndone != 0).to(src), next_info

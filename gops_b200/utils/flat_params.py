@@ -5,7 +5,10 @@ The CUDA kernels take one contiguous parameter vector per network in torch `para
 a VIEW into such a vector, so the modules keep the reference's `state_dict` keys and ordinary
 `nn.Parameter`s while the kernels, the NCCL all-reduce and Adam work on a single buffer.
 """
-from typing import List
+import math
+from typing import List, Optional
+
+import numpy as np
 
 import torch
 
@@ -125,3 +128,30 @@ def polyak_update(target: FlatParams, src: FlatParams, tau: float):
         raise RuntimeError("gops_b200.polyak_update: parameters must live on a CUDA device (no CPU fallback)")
     with torch.cuda.device(t.device):
         _lib.check(_lib.lib().gops_b200_polyak(_lib.ptr(t), _lib.ptr(s), float(tau), t.numel(), _lib.stream_ptr()))
+
+
+class ScalarAdam:
+    """torch.optim.Adam (default betas / eps, no weight decay) for a single fp32 scalar parameter, evaluated on the host
+    with numpy float32 arithmetic in torch's operation order (torch/optim/adam.py _single_tensor_adam)."""
+
+    def __init__(self, param: torch.nn.Parameter, lr: float, betas=(0.9, 0.999), eps: float = 1e-8):
+        self.param, self.lr, self.betas, self.eps = param, lr, betas, eps
+        self.step_count, self.m, self.v = 0, np.float32(0), np.float32(0)
+        self.grad: Optional[float] = None
+
+    def zero_grad(self):
+        self.grad = None
+
+    def step(self):
+        if self.grad is None:
+            return
+        g = np.float32(self.grad)
+        b1, b2 = self.betas
+        self.step_count += 1
+        self.m = np.float32(self.m + (g - self.m) * np.float32(1 - b1))
+        self.v = np.float32(self.v * np.float32(b2) + np.float32(1 - b2) * (g * g))
+        bc1, bc2 = 1 - b1 ** self.step_count, 1 - b2 ** self.step_count
+        denom = np.float32(np.sqrt(self.v) / np.float32(math.sqrt(bc2)) + np.float32(self.eps))
+        value = np.float32(np.float32(self.param.item()) - np.float32(self.lr / bc1) * (self.m / denom))
+        with torch.no_grad():
+            self.param.fill_(float(value))

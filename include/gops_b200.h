@@ -109,6 +109,10 @@ typedef struct gops_b200_plan_desc {
    * (mlp.py:114-145): ONE evaluation on obs_0 emits all `horizon` actions, policy.out_dim = act_dim * horizon (<= 256),
    * no time input; alg must be GOPS_ALG_FHADP.  Runs on the layer-wise tcgen05 path. */
   int32_t open_loop;
+  /* pyth_veh3dofconti_errcstr (env_ocp/env_model/pyth_veh3dofconti_errcstr_model.py:19-55): the vehicle model that also
+   * returns info["constraint"] = (|y_err| - y_error_tol, |u_err| - u_error_tol) of the incoming observation. */
+  int32_t veh_errcstr;
+  float veh_y_error_tol, veh_u_error_tol;
 } gops_b200_plan_desc;
 
 /* Per-call inputs (one replay batch shard).  Unused pointers are NULL. */
@@ -156,6 +160,14 @@ int gops_b200_plan_launch_info(const gops_b200_plan* plan, int32_t* out4);
 #define GOPS_PATH_TC 2
 int gops_b200_plan_set_path(gops_b200_plan* plan, int path);
 int gops_b200_plan_last_path(const gops_b200_plan* plan);
+/* Constrained FHADP variants on a constraint-providing env model (plan_desc.veh_errcstr):
+ *   mode 1  exterior penalty   loss = -mean(v_r) + coef * mean(sum_k g^k sum_i max(c_i, 0)^2)     fhadp_exterior.py:55-70
+ *   mode 2  Lagrangian         loss = -mean(v_r) + coef * mean(sum_k g^k sum_i max(c_i, 0))       fhadp_lagrangian.py:59-71
+ *   mode 3  interior point     loss = -mean(v_r) + mean(feasible * sum_k g^k sum_i log(-min(c_i,0) + 1e-8)) / coef
+ *                                     + coef * mean(~feasible * sum_k g^k sum_i max(c_i,0)^2)     fhadp_interior.py:55-84
+ * coef = penalty / multiplier of the CURRENT update (the algorithms anneal it on the host).  scalars_out of
+ * rollout_grad then carries [0] total loss, [1] the exterior / linear constraint term (mean), [2] #done, [3] #feasible. */
+int gops_b200_plan_set_constraint(gops_b200_plan* plan, int mode, float coef);
 /* number of float32 parameters of the policy (which=0) / value (which=1) network */
 int64_t gops_b200_plan_param_count(const gops_b200_plan* plan, int which);
 

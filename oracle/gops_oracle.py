@@ -351,6 +351,20 @@ class Veh3dofContiModel(BaseModel):
         return nobs, reward, isdone, ninfo
 
 
+class Veh3dofContiErrCstrModel(Veh3dofContiModel):
+    """pyth_veh3dofconti_errcstr_model.py:19-55: the same model, plus info["constraint"] =
+    (|y_err| - y_error_tol, |u_err| - u_error_tol) of the INCOMING observation."""
+
+    def __init__(self, pre_horizon=10, y_error_tol=0.2, u_error_tol=2.0, **kw):
+        super().__init__(pre_horizon=pre_horizon, **kw)
+        self.y_error_tol, self.u_error_tol = y_error_tol, u_error_tol
+
+    def step(self, obs, action, done, info):
+        nobs, reward, isdone, ninfo = super().step(obs, action, done, info)
+        ninfo["constraint"] = torch.stack((obs[:, 1].abs() - self.y_error_tol, obs[:, 3].abs() - self.u_error_tol), dim=1)
+        return nobs, reward, isdone, ninfo
+
+
 class Veh3dofTrackingModel(BaseModel):
     """env_gen_ocp/env_model/veh3dof_tracking_model.py:11-102 via EnvModel.forward
     env_gen_ocp/env_model/pyth_base_model.py:109-119.  info = {"state": (robot_state[B,6],
@@ -384,7 +398,7 @@ MODEL_REGISTRY = {
     "pyth_lq": LqModel,
     "pyth_veh3dofconti": Veh3dofContiModel,
     "veh3dof_tracking": Veh3dofTrackingModel,
-}
+                  "pyth_veh3dofconti_errcstr": Veh3dofContiErrCstrModel}
 
 
 # --------------------------------------------------------------------------------------
@@ -509,6 +523,33 @@ def fhadp_loss(policy: NetSpec, env: WrappedModel, data: dict, pre_horizon: int,
         if trace is not None:
             trace.append((o.detach().clone(), a.detach().clone(), r.detach().clone(), d.clone()))
     return -v_pi.mean()
+
+
+def fhadp_constrained_loss(mode: str, policy: NetSpec, env: WrappedModel, data: dict, pre_horizon: int, gamma: float,
+                           coef: float):
+    """_compute_loss_policy of fhadp_exterior.py:55-70 ("exterior", coef = penalty), fhadp_lagrangian.py:59-71
+    ("lagrangian", coef = multiplier) and fhadp_interior.py:55-84 ("interior", coef = penalty).
+    Returns (loss_policy, loss_reward, loss_constraint, feasible_ratio)."""
+    o, d, info = data["obs"], data["done"], data
+    v_r, v_c, v_int, cs = 0, 0, 0, []
+    for step in range(pre_horizon):
+        a = policy.act(o, step + 1)
+        o, r, d, info = env.forward(o, a, d, info)
+        c = info["constraint"]
+        cs.append(c)
+        v_r = v_r + r * (gamma ** step)
+        if mode == "lagrangian":
+            v_c = v_c + torch.clamp_min(c, 0).sum(1) * (gamma ** step)
+        else:
+            v_c = v_c + (torch.clamp_min(c, 0) ** 2).sum(1) * (gamma ** step)
+        v_int = v_int + (-torch.clamp_max(c, 0) + 1e-8).log().sum(1) * (gamma ** step)
+    loss_reward = -v_r.mean()
+    feasible = (torch.stack(cs, dim=1) < 0).all(2).all(1)
+    if mode == "interior":
+        l_int, l_ext = (v_int * feasible).mean(), (v_c * ~feasible).mean()
+        return loss_reward + 1 / coef * l_int + coef * l_ext, loss_reward, l_ext, feasible.float().mean()
+    l_c = v_c.mean()
+    return loss_reward + coef * l_c, loss_reward, l_c, feasible.float().mean()
 
 
 def _rollout(policy: NetSpec, env, data, n, gamma):

@@ -214,10 +214,26 @@ def run_dsac(name, n_iter=4, B=128, hidden=(64, 64, 64)):
     print(name, {k: float(v) for k, v in rec.items() if "it0/tb/" in k})
 
 
+def run_constrained():
+    """fhadp_exterior / fhadp_lagrangian / fhadp_interior on the constraint-providing pyth_veh3dofconti_errcstr model:
+    two consecutive updates (penalty_delay = 1 / multiplier_delay = 1, so the second one runs with the annealed
+    coefficient), tolerances chosen so that the batch mixes feasible and infeasible samples."""
+    extra = {"FHADPExterior": dict(penalty=2.0, penalty_increase=1.5, penalty_delay=1),
+             "FHADPInterior": dict(penalty=2.0, penalty_increase=1.5, penalty_delay=1),
+             "FHADPLagrangian": dict(multiplier=1.5, multiplier_lr=5e-2, multiplier_delay=1)}
+    for algname, ex in extra.items():
+        kw = base_kwargs("pyth_veh3dofconti_errcstr", algname, 46, 2, (64, 64), "elu", "FiniteHorizonPolicy", pre_horizon=10,
+                         gamma=0.97, y_error_tol=1.2, u_error_tol=2.2, **ex)
+        d = orc.sample_inputs("pyth_veh3dofconti", 160, 70, pre_horizon=10)
+        d["done"][::9] = 1.0
+        run_case("cstr_" + algname.lower(), kw, d, [0, 1])
+
+
 def main():
     ref_shim.install()
     torch.set_num_threads(4)
     run_dsac("dsac_idp")
+    run_constrained()
 
     # K = 20 consecutive updates, LinearLR scheduler, every 5th through the remote-update entry points
     kw = base_kwargs("pyth_idpendulum", "FHADP", 6, 1, (64, 64), "gelu", "FiniteHorizonPolicy", pre_horizon=30,
