@@ -293,6 +293,7 @@ bool rollout_use_tc(const gops_b200_plan* pl, long long batch) {
   if (e && !strcmp(e, "mma")) path = GOPS_PATH_MMA;
   if (e && !strcmp(e, "tc")) path = GOPS_PATH_TC;
   if (path == GOPS_PATH_MMA) return false;
+  if (path == GOPS_PATH_TC) return true;
   // the pipelined kernel schedules single 128-sample sub-tiles; below ~2^14 samples (fewer sub-tiles than SM slots) the
   // mma.sync kernel with its 32-sample tiles spreads the batch over more SMs and finishes first (bench.py configs, C5 sweep)
   return batch >= 16384;
