@@ -158,8 +158,6 @@ RolloutFn rollout_fn_vehconti(int hid, int cfg, int alg);
 RolloutFn rollout_fn_vehtrack(int hid, int cfg, int alg);
 StepFn step_fn_idp();
 StepFn step_fn_lq();
-RolloutFn rollout_fn_tc_idp(int alg);   // round-1 tcgen05 kernel (one sub-tile at a time, 512 cooperating threads): A/B only
-RolloutFn rollout_fn_tc_lq(int alg);
 LwFn lw_fn_idp(int which);              // layer-wise path (wide nets): 0 init, 1 forward step, 2 reverse step
 LwFn lw_fn_lq(int which);
 LwFn lw_fn_vehtrack(int which);
@@ -175,13 +173,6 @@ RolloutFn rollout_fn(int model, int hid, int cfg, int alg) {
     case GOPS_MODEL_LQ: return rollout_fn_lq(hid, cfg, alg);
     case GOPS_MODEL_VEH3DOFCONTI: return rollout_fn_vehconti(hid, cfg, alg);
     case GOPS_MODEL_VEH3DOF_TRACKING: return rollout_fn_vehtrack(hid, cfg, alg);
-    default: return nullptr;
-  }
-}
-RolloutFn rollout_fn_tc(int model, int alg) {
-  switch (model) {
-    case GOPS_MODEL_IDPENDULUM: return rollout_fn_tc_idp(alg);
-    case GOPS_MODEL_LQ: return rollout_fn_tc_lq(alg);
     default: return nullptr;
   }
 }
@@ -279,10 +270,6 @@ void make_net_tcf(const NetL& base, NetL& L) {
   L.d_w3 = 0;
   L.d_b3 = L.out * 64;
   L.nacc = L.out * 64 + L.out;
-}
-size_t rollout_smem_bytes_tcf(const KParams& kp) {
-  return sizeof(float) * (size_t)(64 + kp.w_floats + kp.dw_floats + tcf::RED + kp.inp_max * 516 + 8 * 516) +
-         9 * tcf::HPLANE + 3 * tcf::XPLANE + tcf::ONES_B;
 }
 // Path of a launch: the plan option (gops_b200_plan_set_path), overridden by GOPS_B200_ROLLOUT=tc|mma; AUTO takes the
 // tcgen05 kernel wherever it is built for the plan (64-wide nets, <= 16 inputs, state == obs models)
@@ -548,9 +535,8 @@ int launch_rollout(gops_b200_plan* pl, const gops_b200_batch* b, int alg, cudaSt
   }
   KParams& kp = pl->kp;
   if (rollout_use_tc(pl, b->batch)) {
-    const char* ev = getenv("GOPS_B200_TC_V1");      // A/B only: round-1 cooperative kernel
-    const bool v1 = ev && ev[0] == '1';
-    RolloutFn fn = v1 ? rollout_fn_tc(pl->desc.model, alg) : rollout_fn_tc2(pl->desc.model, alg);
+    const bool v1 = false;
+    RolloutFn fn = rollout_fn_tc2(pl->desc.model, alg);
     if (!fn) return fail("tcgen05 rollout kernel not built for this env model");
     const int S = 128, NT = v1 ? 512 : tc2::NT2;
     KParams k2 = kp;
@@ -571,7 +557,7 @@ int launch_rollout(gops_b200_plan* pl, const gops_b200_batch* b, int alg, cudaSt
     k2.part_stride = round4(upd.nparam + 4);
     kp.part_stride = k2.part_stride;
     k2.dw_floats = round4(upd.nacc);
-    const size_t smem = v1 ? rollout_smem_bytes_tcf(k2) : tc2::smem_bytes(k2.w_floats);
+    const size_t smem = tc2::smem_bytes(k2.w_floats);
     if (smem > (size_t)pl->max_smem) return fail("tcgen05 rollout kernel does not fit in shared memory");
     bool& attr = v1 ? pl->tc_attr_set[alg] : pl->tc2_attr_set[alg];
     if (!attr) {
@@ -834,7 +820,7 @@ int gops_b200_plan_create(const gops_b200_plan_desc* d, gops_b200_plan** out) {
     kp.osh = pl->osc + od;
   }
   // full tcgen05 rollout kernel: 64-wide nets whose inputs fit one 16-wide K block, state == obs models
-  if (kp.hid == 64 && kp.pol.in <= tcf::K1 && (!infadp || kp.val.in <= tcf::K1) && rollout_fn_tc(d->model, d->alg)) {
+  if (kp.hid == 64 && kp.pol.in <= tcf::K1 && (!infadp || kp.val.in <= tcf::K1) && rollout_fn_tc2(d->model, d->alg)) {
     make_net_tcf(kp.pol, pl->pol_tcf);
     if (infadp) make_net_tcf(kp.val, pl->val_tcf); else pl->val_tcf = pl->pol_tcf;
     pl->w_floats_tcf = pl->pol_tcf.blob > pl->val_tcf.blob ? pl->pol_tcf.blob : pl->val_tcf.blob;

@@ -11,41 +11,18 @@ namespace gops {
 // HD = 256 (WG): they do not fit (519 KB of weights) -> weights are read from the packed blob in global memory
 // (L2 resident, generic loads), gradients accumulate directly in this CTA's global partial, X is a per-CTA global
 // scratch; only the activation tiles stay in shared memory.
-// TC (full tcgen05, HD = 64 / S = 128 / NT = 512, inputs <= 16): every dense product incl. the weight gradients runs
-// on the tensor cores in BF16x3 (mlp_tc_full.cuh); shared memory holds the operand planes instead of activation tiles,
-// the W1 / b1 / W2 / b2 gradient accumulators live in TMEM for the whole kernel.
-template <class M, int HD, int S, int NT, int ALG, bool TC = false>
+// (The tcgen05 / TMEM rollout kernel is rollout_tc2.cuh; this template is the mma.sync / FFMA family.)
+template <class M, int HD, int S, int NT, int ALG>
 __global__ void __launch_bounds__(NT, 1) rollout_kernel(const __grid_constant__ KParams p) {
   constexpr int SP = S + 4, XS = NT + 4, NS = M::NS, HID = HD;
   constexpr int alg = ALG;
   constexpr bool WG = HD > 64;
   constexpr int HDR = 4;               // header floats: weight mbarrier
-  static_assert(!TC || (HD == 64 && S == 128 && NT == 512), "full tcgen05 path: 64-wide nets, S = 128, NT = 512");
   extern __shared__ __align__(16) float smem[];
   uint64_t* mbar = reinterpret_cast<uint64_t*>(smem);
   float* part = p.partial + (size_t)blockIdx.x * p.part_stride;
   Tiles t;
-  TcfCtx cf;
-  if (TC) {
-    // [64 hdr: 0 weight mbarrier, 2 / 4 / 6 MMA mbarriers, 8 TMEM slot] W blob | dWs | red | R | P | Q | Xp | ones | X | Z
-    // (R's, P's and Q's third plane must be followed by >= 16 KB of mapped shared memory: the masked b2 MMA reads M = 128)
-    t.W = smem + 64;
-    t.dW = t.W + p.w_floats;
-    cf.dWs = t.dW;
-    cf.red = t.dW + p.dw_floats;
-    cf.R = reinterpret_cast<unsigned char*>(cf.red + tcf::RED);
-    cf.P = cf.R + 3 * tcf::HPLANE;
-    cf.Q = cf.P + 3 * tcf::HPLANE;
-    cf.Xp = cf.Q + 3 * tcf::HPLANE;
-    cf.ones = cf.Xp + 3 * tcf::XPLANE;
-    t.X = reinterpret_cast<float*>(cf.ones + tcf::ONES_B);
-    t.Z = t.X + p.inp_max * XS;
-    cf.bar = mbar + 1;
-    cf.ph0 = cf.ph1 = cf.ph2 = 0u;
-    cf.tmem = 0u;
-    t.H1 = reinterpret_cast<float*>(cf.P);   // scratch of the final scalar reduction
-    t.D1 = t.H2 = t.D2 = t.R = nullptr;
-  } else if (WG) {
+  if (WG) {
     t.W = const_cast<float*>(p.blob_pol);
     t.dW = part;
     t.X = p.xbuf + (size_t)blockIdx.x * p.inp_max * XS;
@@ -56,40 +33,24 @@ __global__ void __launch_bounds__(NT, 1) rollout_kernel(const __grid_constant__ 
     t.X = t.dW + p.dw_floats;
     t.H1 = t.X + p.inp_max * XS;
   }
-  if (!TC) {
-    t.D1 = t.H1 + HID * SP;
-    t.H2 = t.D1 + HID * SP;
-    t.D2 = t.H2 + HID * SP;
-    t.Z = t.D2 + HID * SP;      // [8][XS]: rows a (+ 4 + a: second half-stripe partial of the fused output layer)
-    t.R = t.Z + 8 * XS;         // wide nets only: staging region
-  }
+  t.D1 = t.H1 + HID * SP;
+  t.H2 = t.D1 + HID * SP;
+  t.D2 = t.H2 + HID * SP;
+  t.Z = t.D2 + HID * SP;      // [8][XS]: rows a (+ 4 + a: second half-stripe partial of the fused output layer)
+  t.R = t.Z + 8 * XS;         // wide nets only: staging region
 
   const int tid = threadIdx.x;
   // column (= sample slot of the chunk) owned by this thread.  Tensor-core path: the 64 threads of warp pair p own
   // exactly the 16-sample stripes {sub * S + 16 p .. + 15} that the pair's MLP GEMMs produce, so the pair never has
   // to synchronise with the rest of the CTA outside the weight-gradient reductions.
-  const int col = (WG || TC) ? tid : (((tid & 63) >> 4) * S + 16 * (tid >> 6) + (tid & 15));
+  const int col = WG ? tid : (((tid & 63) >> 4) * S + 16 * (tid >> 6) + (tid & 15));
   auto scope_sync = [&]() {
-    if (WG || TC) __syncthreads();
+    if (WG) __syncthreads();
     else pair_sync();
   };
-  // the staged blob of the full tcgen05 path: bf16 planes of W1 / W2, then fp32 W3, b1, b2, b3 (make_net_tcf offsets)
-  auto bind_tcf = [&](const NetL& L) {
-    cf.W1 = reinterpret_cast<unsigned char*>(t.W + L.o_w1);
-    cf.W2 = reinterpret_cast<unsigned char*>(t.W + L.o_w2);
-    cf.W3 = t.W + L.o_w3; cf.b1 = t.W + L.o_b1; cf.b2 = t.W + L.o_b2; cf.b3 = t.W + L.o_b3;
-  };
 // forward / backward of one sub-tile on the path this instantiation was built for
-#define MLP_FWD(FULL, OUT, L, ts, Zout)                                                           \
-  do {                                                                                            \
-    if constexpr (TC) { bind_tcf(L); mlp_forward_tcf<NT, FULL, OUT>(L, cf, (ts).X, XS, p.inp_max, Zout); } \
-    else mlp_forward<HD, S, NT, FULL, OUT>(L, ts, Zout);                                          \
-  } while (0)
-#define MLP_BWD(WANT_DW, L, ts, want_dx)                                                          \
-  do {                                                                                            \
-    if constexpr (TC) { bind_tcf(L); mlp_backward_tcf<NT, WANT_DW>(L, cf, (ts).X, XS, (ts).Z, want_dx); } \
-    else mlp_backward<HD, S, NT, WANT_DW>(L, ts, want_dx);                                        \
-  } while (0)
+#define MLP_FWD(FULL, OUT, L, ts, Zout) mlp_forward<HD, S, NT, FULL, OUT>(L, ts, Zout)
+#define MLP_BWD(WANT_DW, L, ts, want_dx) mlp_backward<HD, S, NT, WANT_DW>(L, ts, want_dx)
   const NetL& P = p.pol;
   const NetL& V = p.val;
   const int H = p.horizon, obs_dim = P.obs, TCH = p.tape_ch;
@@ -103,29 +64,6 @@ __global__ void __launch_bounds__(NT, 1) rollout_kernel(const __grid_constant__ 
   for (int i = tid; i < p.dw_floats; i += NT) t.dW[i] = 0.f;
   for (int i = tid; i < p.inp_max * XS; i += NT) t.X[i] = 0.f;   // pad rows of the observation tile stay zero
   for (int i = tid; i < 8 * XS; i += NT) t.Z[i] = 0.f;
-  if constexpr (TC) {
-    uint32_t* tslot = reinterpret_cast<uint32_t*>(smem + 8);
-    if (tid == 0) {
-      mbar_init(cf.bar, 1);
-      mbar_init(cf.bar + 1, 1);
-      mbar_init(cf.bar + 2, 1);
-      fence_mbar_init();
-    }
-    {  // `ones`: [2 mn-groups][16 rows][8 bf16], feature 0 = 1.0
-      uint16_t* o16 = reinterpret_cast<uint16_t*>(cf.ones);
-      if (tid < 256) o16[tid] = (tid < 128 && (tid & 7) == 0) ? (uint16_t)0x3f80 : (uint16_t)0;
-    }
-    if (tid < 32) umma::tmem_alloc(tslot, tcf::COLS);
-    umma::fence_before_sync();
-    __syncthreads();
-    umma::fence_after_sync();
-    cf.tmem = *tslot;
-    cf.fresh = 1u;
-    for (int i = tid; i < p.part_stride; i += NT) part[i] = 0.f;      // FP32 accumulators of the per-step flushes
-    fence_proxy_async();
-    umma::fence_before_sync();
-  }
-
   // TMA bulk copy of a packed weight blob into shared memory (all threads wait on the mbarrier)
   auto stage = [&](const float* gsrc, int floats) {
     __syncthreads();  // every reader of the previous blob is done
@@ -253,8 +191,8 @@ __global__ void __launch_bounds__(NT, 1) rollout_kernel(const __grid_constant__ 
       {
         float z[MAXA], a[MAXA], g[MAXA], apol[MAXA];
 #pragma unroll
-        for (int j = 0; j < MAXA; ++j)   // mma.sync path: two half-stripe partials; tcgen05 path: complete sums in row j
-          z[j] = j < P.out ? (TC ? t.Z[j * XS + col] : t.Z[j * XS + col] + t.Z[(4 + j) * XS + col]) : 0.f;
+        for (int j = 0; j < MAXA; ++j)   // two half-stripe partials of the fused output layer
+          z[j] = j < P.out ? t.Z[j * XS + col] + t.Z[(4 + j) * XS + col] : 0.f;
         if (alg == ALG_FHADP || alg == ALG_PIM) {
 #pragma unroll
           for (int j = 0; j < MAXA; ++j)
@@ -438,7 +376,6 @@ __global__ void __launch_bounds__(NT, 1) rollout_kernel(const __grid_constant__ 
         scope_sync();
         MLP_BWD(true, V, ts, false);
       }
-      if constexpr (TC) tcf_flush<NT>(V, cf, part);
       stage(p.blob_pol, P.blob);
       continue;
     }
@@ -598,7 +535,6 @@ __global__ void __launch_bounds__(NT, 1) rollout_kernel(const __grid_constant__ 
         MLP_FWD(true, false, P, ts, nullptr);
         MLP_BWD(true, P, ts, k > 0);
       }
-      if constexpr (TC) tcf_flush<NT>(P, cf, part);
       if constexpr (M::KIND == 1) {
         if (p.cstr_mode != 0 && valid && k > 0) {
           // The constraint of step k reads obs_k.  obs_k was MADE by step k - 1 iff the sample was live there (MaskAtDone
@@ -638,13 +574,7 @@ __global__ void __launch_bounds__(NT, 1) rollout_kernel(const __grid_constant__ 
   // ============================ per-CTA partials ============================
   __syncthreads();
   const int nparam = (alg == ALG_PEV) ? V.nparam : P.nparam;
-  if constexpr (TC) {
-    if (alg != ALG_TRACE) {   // W1, b1, W2, b2 were flushed per sub-tile (mlp_backward_tcf); W3 / b3 come from shared memory
-      const NetL& U = (alg == ALG_PEV) ? V : P;
-      for (int i = U.g_w3 + tid; i < nparam; i += NT)
-        part[i] = i < U.g_b3 ? t.dW[U.d_w3 + i - U.g_w3] : t.dW[U.d_b3 + i - U.g_b3];
-    }
-  } else if (alg != ALG_TRACE && !WG) {
+  if (alg != ALG_TRACE && !WG) {
     const NetL& U = (alg == ALG_PEV) ? V : P;
     for (int i = tid; i < nparam; i += NT) {      // accumulator layout -> torch flat layout
       int j;
@@ -672,11 +602,6 @@ __global__ void __launch_bounds__(NT, 1) rollout_kernel(const __grid_constant__ 
     float s = 0.f;
     for (int i = 0; i < NT; ++i) s += red[i];
     part[nparam + 3] = s;
-  }
-  if constexpr (TC) {
-    umma::fence_before_sync();
-    __syncthreads();
-    if (tid < 32) umma::tmem_dealloc(cf.tmem, tcf::COLS);
   }
 #undef MLP_FWD
 #undef MLP_BWD

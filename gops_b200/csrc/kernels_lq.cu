@@ -26,14 +26,6 @@ RolloutFn rollout_fn_lq(int hid, int cfg, int alg) {
     default: return pick<ALG_TRACE>(hid, cfg);
   }
 }
-RolloutFn rollout_fn_tc_lq(int alg) {   // full tcgen05 / TMEM path (BF16x3)
-  switch (alg) {
-    case ALG_FHADP: return rollout_kernel<ModelLq, 64, 128, 512, ALG_FHADP, true>;
-    case ALG_PIM: return rollout_kernel<ModelLq, 64, 128, 512, ALG_PIM, true>;
-    case ALG_PEV: return rollout_kernel<ModelLq, 64, 128, 512, ALG_PEV, true>;
-    default: return rollout_kernel<ModelLq, 64, 128, 512, ALG_TRACE, true>;
-  }
-}
 RolloutFn rollout_fn_tc2_lq(int alg) {   // pipelined tcgen05 kernel (two independent groups per CTA)
   switch (alg) {
     case ALG_FHADP: return rollout_tc2_kernel<ModelLq, ALG_FHADP>;

@@ -1,6 +1,6 @@
-// Full tcgen05 / TMEM MLP forward + backward for the fused rollout kernel (64-wide nets, inputs <= 16): every dense
-// product of the update -- layer GEMMs, delta back-propagation, input gradient AND the weight gradients (contraction
-// over samples) -- runs on the 5th-generation tensor cores; the weight gradients accumulate in TMEM for the whole kernel.
+// BF16x3 tcgen05 / TMEM primitives shared by the tensor-core kernels of this library (rollout_tc2.cuh, dense_tc.cuh):
+// operand descriptors of the canonical plane layout, the MMA issue helpers, the fp32 -> three-plane split and the
+// transposing warp reduction.  (Round 1's cooperative 512-thread kernel that lived here is replaced by rollout_tc2.cuh.)
 //
 // Arithmetic: BF16x3.  x = b0 + b1 + b2 (three bf16 planes, residual <= 2^-27 |x|), a product keeps the six terms of
 // order <= 2 (b0b0, b0b1, b1b0, b1b1, b0b2, b2b0; neglected <= 2^-26), FP32 accumulation in TMEM: at least as accurate
@@ -33,24 +33,6 @@ constexpr int W2PLANE = 8 * 64 * 16, W1PLANE = 2 * 64 * 16;
 constexpr int RED = 4 * (MAXA * 64 + MAXA);      // floats: quarter partials of dW3 / db3
 constexpr int ONES_B = 2 * 16 * 16;              // bytes: [2 mn-groups][16 rows][16 B]
 }  // namespace tcf
-
-struct TcfCtx {
-  unsigned char* W1;   // 3 planes [2][64][8] bf16
-  unsigned char* W2;   // 3 planes [8][64][8] bf16
-  const float* W3;     // fp32 [out][64]
-  const float *b1, *b2, *b3;
-  unsigned char* Xp;   // 3 planes [2][128][8]
-  unsigned char* P;    // 3 planes [8][128][8]   H1
-  unsigned char* Q;    // 3 planes [8][128][8]   delta2 (forward: fp32 output-partial scratch)
-  unsigned char* R;    // 3 planes [8][128][8]   delta1 (own buffer: H1 stays readable for the dW2 products in flight)
-  unsigned char* ones; // [2][16][8] bf16: feature 0 = 1
-  float* dWs;          // dW3 [out][64] | db3 [out]
-  uint32_t fresh;      // 1: the next weight-gradient MMA groups overwrite their TMEM accumulators (just flushed)
-  float* red;          // [tcf::RED]
-  uint64_t* bar;       // bar[0]: critical-path MMA groups (thread 0), bar[1] / bar[2]: dW2 / dW1 groups (thread 128)
-  uint32_t ph0, ph1, ph2;
-  uint32_t tmem;
-};
 
 namespace tcf {
 
@@ -122,28 +104,6 @@ __device__ __forceinline__ void issue_stack(uint32_t d, const Op& A, const Op& B
   for (int ks = 0; ks < 8; ++ks) mma_bf16(d, a2 + ks * ka, b0 + ks * kb, idesc, 1u, true);
 }
 
-__device__ __forceinline__ void wait0(TcfCtx& cx) {
-  mbar_wait(cx.bar, cx.ph0);
-  cx.ph0 ^= 1u;
-  umma::fence_after_sync();
-}
-__device__ __forceinline__ void wait1(TcfCtx& cx) {
-  mbar_wait(cx.bar + 1, cx.ph1);
-  cx.ph1 ^= 1u;
-  umma::fence_after_sync();
-}
-__device__ __forceinline__ void wait2(TcfCtx& cx) {
-  mbar_wait(cx.bar + 2, cx.ph2);
-  cx.ph2 ^= 1u;
-  umma::fence_after_sync();
-}
-__device__ __forceinline__ void publish_sync() {
-  fence_proxy_async();
-  umma::fence_before_sync();
-  __syncthreads();
-}
-constexpr int DW_ISSUER = 128;   // thread that issues the weight-gradient MMA groups (warp 4): off the critical path
-
 // (x0, x1) -> packed bf16x2 words of the three planes (low half = x0)
 __device__ __forceinline__ void split3(float x0, float x1, uint32_t& p0, uint32_t& p1, uint32_t& p2) {
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(p0) : "f"(x1), "f"(x0));
@@ -203,283 +163,6 @@ __device__ __forceinline__ void warp_reduce16(float* v, int lane) {
   v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
 }
 
-// hidden-layer epilogue: 16 accumulator columns -> + bias -> activation (FULL: park the derivative in TMEM) -> planes
-template <int ACT, bool FULL>
-__device__ __forceinline__ void epi_hidden(uint32_t t_acc, uint32_t t_dscr, const float* __restrict__ bias16,
-                                           unsigned char* planes, int c, int r) {
-  float v[16], d[16];
-  umma::tmem_ld16(t_acc, v);
-#pragma unroll
-  for (int e = 0; e < 16; ++e) {
-    const float pre = v[e] + bias16[e];
-    if constexpr (FULL) act_fwd_grad_t<ACT>(pre, v[e], d[e]);
-    else v[e] = act_fwd_t<ACT>(pre);
-  }
-  store16(planes, HPLANE, c, r, v);
-  if constexpr (FULL) {
-    umma::tmem_st16(t_dscr, d);
-    umma::tmem_wait_st();
-  }
-}
-// last hidden layer (FULL: derivative and activation parked in TMEM); OUT: this slice's output dot products
-template <int ACT, bool FULL, bool OUT>
-__device__ __forceinline__ void epi_last(uint32_t t_acc, uint32_t t_d2, uint32_t t_h2, const float* __restrict__ bias16,
-                                         const float* __restrict__ W3, int out, int c, float* zp) {
-  float v[16], d[16];
-  umma::tmem_ld16(t_acc, v);
-#pragma unroll
-  for (int e = 0; e < 16; ++e) {
-    const float pre = v[e] + bias16[e];
-    if constexpr (FULL) act_fwd_grad_t<ACT>(pre, v[e], d[e]);
-    else v[e] = act_fwd_t<ACT>(pre);
-  }
-  if constexpr (FULL) {
-    umma::tmem_st16(t_d2, d);
-    umma::tmem_st16(t_h2, v);
-    umma::tmem_wait_st();
-  }
-  if constexpr (OUT) {
-#pragma unroll
-    for (int a = 0; a < MAXA; ++a) {
-      zp[a] = 0.f;
-      if (a < out) {
-        const float* w = W3 + a * 64 + 16 * c;
-#pragma unroll
-        for (int e = 0; e < 16; ++e) zp[a] = fmaf(w[e], v[e], zp[a]);
-      }
-    }
-  }
-}
-
 }  // namespace tcf
-
-// X sub-tile ([feature][sample], leading dimension XS, `xrows` rows) -> Zout[a * XS + r] (OUT).  FULL: derivative of
-// layer 1, derivative and activation of layer 2 are parked in TMEM for mlp_backward_tcf.  Ends with a CTA barrier.
-template <int NT, bool FULL, bool OUT>
-__device__ __forceinline__ void mlp_forward_tcf(const NetL& L, TcfCtx& cx, const float* __restrict__ Xsub, int XS,
-                                                int xrows, float* __restrict__ Zout) {
-  static_assert(NT == 512, "cooperative tcgen05 MLP: 16 warps = 4 lane quarters x 4 column slices");
-  using namespace tcf;
-  const int tid = threadIdx.x, lane = tid & 31, q = (tid >> 5) & 3, c = tid >> 7, r = 32 * q + lane;
-  const uint32_t tl = cx.tmem + ((uint32_t)(32 * q) << 16) + 16 * c;
-  if (tid < 256) {   // observation planes: thread = (chunk tid >> 7, row tid & 127), 8 features
-    const int row = tid & 127, ch = tid >> 7;
-    uint32_t w[3][4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int f = 8 * ch + 2 * i;
-      split3(f < xrows ? Xsub[f * XS + row] : 0.f, f + 1 < xrows ? Xsub[(f + 1) * XS + row] : 0.f, w[0][i], w[1][i],
-             w[2][i]);
-    }
-#pragma unroll
-    for (int p = 0; p < 3; ++p)
-      *reinterpret_cast<uint4*>(cx.Xp + p * XPLANE + (ch * 128 + row) * 16) = make_uint4(w[p][0], w[p][1], w[p][2], w[p][3]);
-  }
-  publish_sync();
-  if (tid == 0) {
-    umma::fence_after_sync();
-    issue6<1>(cx.tmem + ACC, k_act(cx.Xp, XPLANE), k_w(cx.W1, W1PLANE), idesc_bf16(128, 64, false, false));
-    umma::commit(cx.bar);
-  }
-  wait0(cx);
-#define GOPS_TCF_H(A) epi_hidden<A, FULL>(tl + ACC, tl + D1S, cx.b1 + 16 * c, cx.P, c, r)
-  GOPS_ACT_SWITCH(L.hact, GOPS_TCF_H)
-#undef GOPS_TCF_H
-  publish_sync();
-  if (tid == 0) {
-    umma::fence_after_sync();
-    issue6<4>(cx.tmem + ACC, k_act(cx.P, HPLANE), k_w(cx.W2, W2PLANE), idesc_bf16(128, 64, false, false));
-    umma::commit(cx.bar);
-  }
-  wait0(cx);
-  float zp[MAXA];
-#define GOPS_TCF_L(A) epi_last<A, FULL, OUT>(tl + ACC, tl + D2S, tl + H2S, cx.b2 + 16 * c, cx.W3, L.out, c, zp)
-  GOPS_ACT_SWITCH(L.hact, GOPS_TCF_L)
-#undef GOPS_TCF_L
-  if constexpr (OUT) {
-    float* Zp = reinterpret_cast<float*>(cx.Q);          // [4 slices][MAXA][128] scratch (Q is free in the forward)
-#pragma unroll
-    for (int a = 0; a < MAXA; ++a)
-      if (a < L.out) Zp[(c * MAXA + a) * 128 + r] = zp[a];
-    umma::fence_before_sync();
-    __syncthreads();
-    if (tid < 128) {
-#pragma unroll
-      for (int a = 0; a < MAXA; ++a)
-        if (a < L.out)
-          Zout[a * XS + tid] = cx.b3[a] + ((Zp[a * 128 + tid] + Zp[(MAXA + a) * 128 + tid]) +
-                                           (Zp[(2 * MAXA + a) * 128 + tid] + Zp[(3 * MAXA + a) * 128 + tid]));
-    }
-    __syncthreads();
-  } else {
-    umma::fence_before_sync();
-    __syncthreads();
-  }
-}
-
-// Zbar in Zsub rows 0..out-1.  WANT_DW: accumulate the weight gradients (TMEM: W1, b1, W2, b2; shared: W3, b3);
-// want_dx: observation gradient into rows [0, L.obs) of the X sub-tile.  Needs a FULL forward of the same sub-tile.
-template <int NT, bool WANT_DW>
-__device__ __forceinline__ void mlp_backward_tcf(const NetL& L, TcfCtx& cx, float* __restrict__ Xsub, int XS,
-                                                 const float* __restrict__ Zsub, bool want_dx) {
-  using namespace tcf;
-  const int tid = threadIdx.x, lane = tid & 31, q = (tid >> 5) & 3, c = tid >> 7, r = 32 * q + lane;
-  const uint32_t tl = cx.tmem + ((uint32_t)(32 * q) << 16) + 16 * c;
-  // ---- delta2 = (W3^T zbar) * act'(pre2) -> Q planes;  dW3 / db3 quarter partials
-  {
-    float zb[MAXA];
-#pragma unroll
-    for (int a = 0; a < MAXA; ++a) zb[a] = a < L.out ? Zsub[a * XS + r] : 0.f;
-    float d[16];
-    umma::tmem_ld16(tl + D2S, d);
-#pragma unroll
-    for (int e = 0; e < 16; ++e) {
-      float g = 0.f;
-#pragma unroll
-      for (int a = 0; a < MAXA; ++a)
-        if (a < L.out) g = fmaf(cx.W3[a * 64 + 16 * c + e], zb[a], g);
-      d[e] *= g;
-    }
-    store16(cx.Q, HPLANE, c, r, d);
-    if constexpr (WANT_DW) {
-      float h2[16];
-      umma::tmem_ld16(tl + H2S, h2);
-#pragma unroll
-      for (int a = 0; a < MAXA; ++a)
-        if (a < L.out) {
-          float v[16];
-#pragma unroll
-          for (int e = 0; e < 16; ++e) v[e] = zb[a] * h2[e];
-          warp_reduce16(v, lane);
-          if ((lane & 1) == 0) cx.red[(q * MAXA + a) * 64 + 16 * c + col16(lane)] = v[0];
-          if (c == 0) {
-            float s = zb[a];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-            if (lane == 0) cx.red[4 * MAXA * 64 + q * MAXA + a] = s;
-          }
-        }
-    }
-  }
-  publish_sync();
-  if constexpr (WANT_DW) {   // fixed-order sum of the four lane quarters
-    if (tid < L.out * 64) {
-      const int a = tid >> 6, j = tid & 63;
-      cx.dWs[L.d_w3 + tid] += (cx.red[(0 * MAXA + a) * 64 + j] + cx.red[(1 * MAXA + a) * 64 + j]) +
-                              (cx.red[(2 * MAXA + a) * 64 + j] + cx.red[(3 * MAXA + a) * 64 + j]);
-    } else if (tid >= 256 && tid < 256 + L.out) {
-      const int a = tid - 256, o = 4 * MAXA * 64;
-      cx.dWs[L.d_b3 + a] += (cx.red[o + a] + cx.red[o + MAXA + a]) + (cx.red[o + 2 * MAXA + a] + cx.red[o + 3 * MAXA + a]);
-    }
-  }
-  if (tid == 0) {
-    umma::fence_after_sync();
-    issue6<4>(cx.tmem + ACC, k_act(cx.Q, HPLANE), mn_w(cx.W2, W2PLANE), idesc_bf16(128, 64, false, true));
-    umma::commit(cx.bar);
-  }
-  if constexpr (WANT_DW) {
-    if (tid == DW_ISSUER) {
-      umma::fence_after_sync();
-      const Op A = mn_act(cx.Q, HPLANE);
-      issue_stack(cx.tmem + DW2, A, mn_act(cx.P, HPLANE), idesc_bf16(128, 64, true, true), 3, cx.fresh);
-      const Op one{smem_u32(cx.ones), 0u, 128u, 256u, 0u};
-      issue_stack(cx.tmem + DB2, A, one, idesc_bf16(128, 16, true, true), 1, cx.fresh);
-      umma::commit(cx.bar + 1);
-    }
-  }
-  // ---- delta1 = (delta2 . W2) * act'(pre1) -> R planes
-  wait0(cx);
-  {
-    float v[16], d1[16];
-    umma::tmem_ld16(tl + ACC, v);
-    umma::tmem_ld16(tl + D1S, d1);
-#pragma unroll
-    for (int e = 0; e < 16; ++e) v[e] *= d1[e];
-    store16(cx.R, HPLANE, c, r, v);
-  }
-  if (!WANT_DW && !want_dx) {
-    umma::fence_before_sync();
-    __syncthreads();
-    return;
-  }
-  publish_sync();
-  if (tid == 0 && want_dx) {
-    umma::fence_after_sync();
-    issue6<4>(cx.tmem + ACC, k_act(cx.R, HPLANE), mn_w(cx.W1, W1PLANE), idesc_bf16(128, 16, false, true));
-    umma::commit(cx.bar);
-  }
-  if constexpr (WANT_DW) {
-    if (tid == DW_ISSUER) {
-      umma::fence_after_sync();
-      const Op A = mn_act(cx.R, HPLANE);
-      issue_stack(cx.tmem + DW1, A, mn_act(cx.Xp, XPLANE), idesc_bf16(128, 16, true, true), 3, cx.fresh);
-      const Op one{smem_u32(cx.ones), 0u, 128u, 256u, 0u};
-      issue_stack(cx.tmem + DB1, A, one, idesc_bf16(128, 16, true, true), 1, cx.fresh);
-      umma::commit(cx.bar + 2);
-    }
-  }
-  if (want_dx) {
-    wait0(cx);
-    if (c == 0) {
-      float v[16];
-      umma::tmem_ld16(tl + ACC, v);
-#pragma unroll
-      for (int f = 0; f < 16; ++f)
-        if (f < L.obs) Xsub[f * XS + r] = v[f];
-    }
-  }
-  if constexpr (WANT_DW) {   // the operand planes are rewritten by the next sub-tile
-    wait1(cx);
-    wait2(cx);
-    cx.fresh = 0u;
-  }
-  umma::fence_before_sync();
-  __syncthreads();
-}
-
-// Move the weight-gradient accumulators W1, b1, W2, b2 from TMEM into the CTA's FP32 global partial (torch flat layout,
-// round-to-nearest adds, fixed thread ownership, coalesced) and mark them fresh.  Called once per horizon step: the
-// tensor core ADDS INTO ITS ACCUMULATOR WITH TRUNCATION, and a chain of ~1e4 accumulations over the whole kernel biased
-// the gradient by ~1e-4 at B = 2^18 (caught by the batch-linearity test); 4 sub-tiles x 32 MMAs per flush keeps the
-// bias at the 1e-6 level of the mma.sync path.  All MMA groups must have been waited for (end of mlp_backward_tcf);
-// uses the P planes as scratch.
-template <int NT>
-__device__ __forceinline__ void tcf_flush(const NetL& L, TcfCtx& cx, float* __restrict__ part) {
-  using namespace tcf;
-  const int tid = threadIdx.x, lane = tid & 31, q = (tid >> 5) & 3, c = tid >> 7, r = 32 * q + lane;
-  const uint32_t tl = cx.tmem + ((uint32_t)(32 * q) << 16);
-  float* S2 = reinterpret_cast<float*>(cx.P);          // [128][68]: lanes 0..63 b0 (+ b2) share, 64..127 b1 share
-  float* S1 = S2 + 128 * 68;                             // [128][16] | b1 [128] | b2 [128]
-  float v[16];
-  umma::tmem_ld16(tl + DW2 + 16 * c, v);
-#pragma unroll
-  for (int e4 = 0; e4 < 4; ++e4)
-    *reinterpret_cast<float4*>(S2 + r * 68 + 16 * c + 4 * e4) = make_float4(v[4 * e4], v[4 * e4 + 1], v[4 * e4 + 2], v[4 * e4 + 3]);
-  if (c == 0) {
-    umma::tmem_ld16(tl + DW1, v);
-#pragma unroll
-    for (int e = 0; e < 16; ++e) S1[r * 16 + e] = v[e];
-  } else if (c == 1) {
-    umma::tmem_ld16(tl + DB1, v);
-    S1[2048 + r] = v[0];
-  } else if (c == 2) {
-    umma::tmem_ld16(tl + DB2, v);
-    S1[2048 + 128 + r] = v[0];
-  }
-  umma::fence_before_sync();
-  __syncthreads();
-  for (int i = tid; i < 64 * 64; i += NT) {
-    const int j = i >> 6, k = i & 63;
-    part[L.g_w2 + i] += S2[j * 68 + k] + S2[(64 + j) * 68 + k];
-  }
-  for (int i = tid; i < 64 * L.in; i += NT) {
-    const int j = i / L.in, k = i - j * L.in;
-    part[L.g_w1 + i] += S1[j * 16 + k] + S1[(64 + j) * 16 + k];
-  }
-  if (tid < 64) part[L.g_b1 + tid] += S1[2048 + tid] + S1[2048 + 64 + tid];
-  else if (tid < 128) part[L.g_b2 + tid - 64] += S1[2048 + 128 + tid - 64] + S1[2048 + 128 + tid];
-  __syncthreads();
-  cx.fresh = 1u;
-}
 
 }  // namespace gops
