@@ -35,11 +35,18 @@ def _objects():
 def test_rollout_objects_carry_tcgen05_tma_and_tf32_mma():
     c = _count(os.path.join(_objects(), "kernels_idp.o"),
                ["UTCHMMA", "LDTM", "STTM", "UTCBAR", "HMMA.1688.F32.TF32", "UBLKCP", "SYNCS"])
-    assert c["UTCHMMA"] > 100, c          # tcgen05.mma (bf16x3 full path + tf32 hybrid forward)
-    assert c["LDTM"] > 10 and c["STTM"] > 4, c   # tcgen05.ld / tcgen05.st (TMEM epilogues, parked derivatives)
+    assert c["UTCHMMA"] > 100, c          # tcgen05.mma (rollout_tc2: BF16x3 layer / delta / weight-gradient products)
+    assert c["LDTM"] > 10 and c["STTM"] >= 4, c  # tcgen05.ld / tcgen05.st (TMEM epilogues; act'(layer 1) parked in TMEM)
     assert c["UTCBAR"] > 8, c             # tcgen05.commit -> mbarrier
     assert c["HMMA.1688.F32.TF32"] > 100, c      # mma.sync 3xTF32 path
     assert c["UBLKCP"] > 4, c             # cp.async.bulk weight staging
+
+
+def test_layerwise_objects_carry_tcgen05():
+    """dense_tc.o: the forward / dgrad / wgrad GEMMs of the layer-wise path; kernels_vehtrack.o only hosts the per-step
+    kernels of C3 (its dense products run in dense_tc.o)."""
+    c = _count(os.path.join(_objects(), "dense_tc.o"), ["UTCHMMA", "LDTM", "UTCBAR", "UBLKCP"])
+    assert c["UTCHMMA"] >= 100 and c["LDTM"] >= 5 and c["UTCBAR"] >= 5 and c["UBLKCP"] >= 4, c
 
 
 def test_inference_object_carries_tcgen05():
