@@ -15,7 +15,7 @@ from gops_b200.create_pkg.create_alg import create_alg
 from oracle import gops_oracle as orc
 
 torch.manual_seed(0)
-which = sys.argv[1:] or ["idp", "lq", "veh", "wide", "tc"]
+which = sys.argv[1:] or ["idp", "lq", "veh", "wide", "tc", "lw", "dsac", "cstr"]
 if "idp" in which:
     alg = create_alg(**kwargs("pyth_idpendulum", "FHADP", 6, 1, 64, "gelu", pre_horizon=3, reward_scale=1.0))
     for B in (700, 130):     # cfg1/cfg2 tiles incl. ragged tails
@@ -51,5 +51,40 @@ if "tc" in which:          # tcgen05 / TMEM kernels: hybrid rollout (forced) and
     alg.networks.policy(torch.randn(4321, 4, device="cuda"))
     alg.networks.v(torch.randn(129, 4, device="cuda"))
     os.environ.pop("GOPS_B200_INFER")
+if "lw" in which:          # layer-wise tcgen05 path: wide FHADP (C3 shape, small), FHADP2, a bare LayerwiseMlp with ragged shapes
+    alg = create_alg(**kwargs("veh3dof_tracking", "FHADP", 46, 2, 256, "elu", pre_horizon=10))
+    alg.kernel_path = "tc"
+    alg.set_parameters({"pre_horizon": 3})
+    alg.local_update(to_dev(orc.sample_inputs("veh3dof_tracking", 200, 4, pre_horizon=10)), 0)
+    kw2 = kwargs("pyth_idpendulum", "FHADP2", 6, 1, 64, "gelu", pre_horizon=4, reward_scale=1.0)
+    kw2["policy_func_name"] = "FiniteHorizonFullPolicy"
+    alg = create_alg(**kw2)
+    alg.local_update(to_dev(orc.sample_inputs("pyth_idpendulum", 333, 5)), 0)
+    from gops_b200.ops.layerwise_mlp import LayerwiseMlp
+    net = LayerwiseMlp([19, 100, 37, 5], "tanh", max_batch=129)
+    flat = torch.randn(net.nparam, device="cuda") * 0.1
+    net.pack(flat)
+    net.forward(torch.randn(129, 19, device="cuda"))
+    g = torch.zeros(net.nparam, device="cuda")
+    net.backward(torch.randn(129, 5, device="cuda"), grad=g, want_dx=True)
+if "dsac" in which:
+    kw3 = kwargs("pyth_idpendulum", "DSAC", 6, 1, 64, "gelu")
+    kw3.update(policy_func_name="StochaPolicy", policy_hidden_sizes=[64, 64, 64], value_hidden_sizes=[64, 64, 64],
+               policy_act_distribution="TanhGaussDistribution", policy_min_log_std=-20, policy_max_log_std=1,
+               value_func_name="ActionValueDistri", alpha_learning_rate=1e-3, gamma=0.99, tau=0.005, auto_alpha=True,
+               alpha=0.2, delay_update=2, TD_bound=10, bound=True)
+    alg = create_alg(**kw3)
+    B = 300
+    d = {"obs": torch.randn(B, 6), "act": torch.rand(B, 1) * 2 - 1, "rew": torch.randn(B), "obs2": torch.randn(B, 6),
+         "done": torch.zeros(B)}
+    alg.local_update(d, 0)
+    alg.local_update(d, 1)
+if "cstr" in which:
+    kw4 = kwargs("pyth_veh3dofconti_errcstr", "FHADPInterior", 46, 2, 64, "elu", pre_horizon=10, y_error_tol=1.2, u_error_tol=2.2)
+    kw4["policy_func_name"] = "FiniteHorizonPolicy"
+    alg = create_alg(**kw4)
+    d = orc.sample_inputs("pyth_veh3dofconti", 150, 6, pre_horizon=10)
+    d["done"][::4] = 1.0
+    alg.local_update(to_dev(d), 0)
 torch.cuda.synchronize()
 print("sanitize_case done")
