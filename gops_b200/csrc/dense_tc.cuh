@@ -138,22 +138,24 @@ __device__ __forceinline__ void store_tile(const TileRegs& t, unsigned char* pla
 
 // One 128-row x NC-column output tile.  grid = (row tiles, column splits), 256 threads, <= 128 TMEM columns.
 // GRAD: gradient product (A in two planes, three terms); else forward product (three planes, six terms).
+// K slices are double buffered: while the tensor core works on slice t the CTA converts slice t + 1 into the other
+// operand buffer and its weight image arrives by TMA; MMAs retire in order, so one wait on the last commit ends the loop.
 template <int EPI, bool GRAD>
-__global__ void __launch_bounds__(NTH, 2) dense_gemm_kernel(const __grid_constant__ GemmArgs g) {
+__global__ void __launch_bounds__(NTH, 1) dense_gemm_kernel(const __grid_constant__ GemmArgs g) {
   extern __shared__ __align__(128) unsigned char dsm[];
-  uint64_t* bars = reinterpret_cast<uint64_t*>(dsm);           // [0] weights landed, [1] MMAs retired
-  uint32_t* tslot = reinterpret_cast<uint32_t*>(dsm + 32);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(dsm);           // [0..1] weights landed (per buffer), [2..3] MMAs retired
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(dsm + 64);
   constexpr int APL = 8 * TM * 16, NPA = GRAD ? 2 : 3;
-  unsigned char* Ap = dsm + 128;
-  unsigned char* Bp = Ap + NPA * APL;
   const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const int nc = nc_of(g.n), nsl = slices_of(g.k);
+  const size_t img = slice_bytes(nc);
+  unsigned char* Abuf = dsm + 128;
+  unsigned char* Bbuf = Abuf + 2 * NPA * APL;
   const int split = blockIdx.y;
   const long long r0 = (long long)blockIdx.x * TM;
   const uint32_t ncols = nc < 32 ? 32u : (nc <= 64 ? 64u : 128u);
   if (tid == 0) {
-    mbar_init(bars, 1);
-    mbar_init(bars + 1, 1);
+    for (int i = 0; i < 4; ++i) mbar_init(bars + i, 1);
     fence_mbar_init();
   }
   if (warp == 0) umma::tmem_alloc(tslot, ncols);
@@ -161,21 +163,29 @@ __global__ void __launch_bounds__(NTH, 2) dense_gemm_kernel(const __grid_constan
   __syncthreads();
   umma::fence_after_sync();
   const uint32_t tm = __shfl_sync(0xffffffffu, *tslot, 0);
-  const size_t img = slice_bytes(nc);
   const unsigned char* Bsrc = g.Bimg + (size_t)split * nsl * img;
-  uint32_t ph = 0;
   TileRegs regs;
   load_tile(g.A, g.lda, r0, g.rows, 0, g.k, regs);
   for (int t = 0; t < nsl; ++t) {
+    const int bf = t & 1;
+    const uint32_t ph = (uint32_t)(t >> 1) & 1u;
+    unsigned char* Ap = Abuf + bf * NPA * APL;
+    unsigned char* Bp = Bbuf + (size_t)bf * img;
+    if (t >= 2) {                                   // the MMAs of slice t - 2 read this buffer pair
+      mbar_wait(bars + 2 + bf, ph ^ 1u);
+      umma::fence_after_sync();
+    }
     if (tid == 0) {
       fence_proxy_async();
-      mbar_expect_tx(bars, (uint32_t)img);
+      mbar_expect_tx(bars + bf, (uint32_t)img);
       for (size_t off = 0; off < img; off += 32768)
-        tma_bulk_g2s(Bp + off, Bsrc + (size_t)t * img + off, (uint32_t)(img - off < 32768 ? img - off : 32768), bars);
+        tma_bulk_g2s(Bp + off, Bsrc + (size_t)t * img + off, (uint32_t)(img - off < 32768 ? img - off : 32768), bars + bf);
     }
     store_tile<NPA>(regs, Ap);
+    if (t + 1 < nsl) load_tile(g.A, g.lda, r0, g.rows, (t + 1) * KS, g.k, regs);   // next slice's reads are in flight
     fence_proxy_async();
-    mbar_wait(bars, ph);
+    mbar_wait(bars + bf, ph);
+    umma::fence_before_sync();
     __syncthreads();
     if (warp == 0) {
       if (umma::elect_one()) {
@@ -202,13 +212,14 @@ __global__ void __launch_bounds__(NTH, 2) dense_gemm_kernel(const __grid_constan
         for (int ks = 0; ks < 4; ++ks) mma_bf16(tm, a0 + ks * ka, b1 + ks * kb, idesc, 1u);
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) mma_bf16(tm, a0 + ks * ka, b0 + ks * kb, idesc, 1u);
-        umma::commit(bars + 1);
+        umma::commit(bars + 2 + bf);
       }
     }
-    if (t + 1 < nsl) load_tile(g.A, g.lda, r0, g.rows, (t + 1) * KS, g.k, regs);   // in flight while the tensor core works
-    mbar_wait(bars + 1, ph);          // single-buffered operands: the slice's MMAs retire before the next staging
+  }
+  {  // MMAs retire in order: the last slice's commit covers all of them
+    const int tl = nsl - 1;
+    mbar_wait(bars + 2 + (tl & 1), (uint32_t)(tl >> 1) & 1u);
     umma::fence_after_sync();
-    ph ^= 1u;
   }
   // ---- epilogue: thread = (row, half of the tile's columns), 16 columns per pass
   {
@@ -247,9 +258,15 @@ __global__ void __launch_bounds__(NTH, 2) dense_gemm_kernel(const __grid_constan
         }
         if constexpr (EPI == EPI_ACT) {
           if (g.D != nullptr) {
+            if (n0 + 16 <= g.n && (g.ldd & 3) == 0) {
 #pragma unroll
-            for (int e = 0; e < 16; ++e)
-              if (n0 + e < g.n) g.D[row * g.ldd + n0 + e] = d[e];
+              for (int e4 = 0; e4 < 4; ++e4)
+                *reinterpret_cast<float4*>(g.D + row * g.ldd + n0 + 4 * e4) = make_float4(d[4 * e4], d[4 * e4 + 1], d[4 * e4 + 2], d[4 * e4 + 3]);
+            } else {
+#pragma unroll
+              for (int e = 0; e < 16; ++e)
+                if (n0 + e < g.n) g.D[row * g.ldd + n0 + e] = d[e];
+            }
           }
         }
       }
@@ -260,7 +277,7 @@ __global__ void __launch_bounds__(NTH, 2) dense_gemm_kernel(const __grid_constan
   if (warp == 0) umma::tmem_dealloc(tm, ncols);
 }
 
-inline size_t gemm_smem(int n, bool grad) { return 128 + (size_t)(grad ? 2 : 3) * 8 * TM * 16 + slice_bytes(nc_of(n)); }
+inline size_t gemm_smem(int n, bool grad) { return 128 + 2 * ((size_t)(grad ? 2 : 3) * 8 * TM * 16 + slice_bytes(nc_of(n))); }
 
 // dW partial of one (128 output features, <= 128 input features) block over a chunk of the rows:
 // grid = (n blocks * k blocks, row chunks).  A = dY^T (2 planes), B = X^T (2 planes), contraction over rows: the planes are
