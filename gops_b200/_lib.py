@@ -110,6 +110,16 @@ PROTOTYPES = {
                                         C.c_int64, C.c_float, C.c_float, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gops_b200_dsac_policy_loss": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_float, C.c_void_p,
                                              C.c_void_p, C.c_void_p, C.c_void_p]),
+    "gops_b200_peer_create": (C.c_int, [C.c_int32, C.c_int32, C.c_int64, C.POINTER(C.c_void_p)]),
+    "gops_b200_peer_destroy": (C.c_int, [C.c_void_p]),
+    "gops_b200_peer_region_bytes": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
+    "gops_b200_peer_export": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "gops_b200_peer_connect": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "gops_b200_peer_local_base": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "gops_b200_peer_connect_local": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "gops_b200_peer_allreduce": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                           C.c_int32, C.c_double, C.c_double, C.c_double, C.c_double, C.c_void_p]),
+    "gops_b200_peer_error": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),
 }
 
 _lib = None

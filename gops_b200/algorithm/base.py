@@ -143,12 +143,20 @@ def shard_inv_batch(local_batch: int, world: int) -> float:
     return 1.0 / float(local_batch * world)
 
 
-def allreduce_flat(gbuf: torch.Tensor):
-    """ONE collective per optimizer step over [flat gradient | loss | critic mean | #done]."""
+def allreduce_flat(gbuf: torch.Tensor, optimizer=None) -> bool:
+    """ONE exchange per optimizer step over [flat gradient | loss | critic mean | #done].  Between GPUs of one node it
+    is a single kernel over NVLink peer memory (utils/peer_reduce.py) which also applies `optimizer`'s Adam step;
+    otherwise an NCCL / gloo all-reduce.  Returns True when the optimizer step has been applied here."""
     import torch.distributed as dist
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        if gbuf.is_cuda:
+            from gops_b200.utils.peer_reduce import group_peer
+            peer = group_peer(gbuf.numel(), gbuf.device)
+            if peer is not None:
+                peer.allreduce(gbuf, optimizer)
+                return optimizer is not None
         dist.all_reduce(gbuf, op=dist.ReduceOp.SUM)
-    return gbuf
+    return False
 
 
 class FusedADPMixin:
@@ -223,6 +231,18 @@ class FusedADPMixin:
             return dist, dist.get_world_size()
         return None, 1
 
+    def _launch_and_step(self, launch, optimizer):
+        """`launch()` (a fused rollout-gradient call) followed by `optimizer.step()`.  On several GPUs the step is
+        applied inside the gradient-exchange kernel instead of by a launch of its own."""
+        self._fuse_opt, self._opt_applied = optimizer, False
+        try:
+            out = launch()
+        finally:
+            self._fuse_opt = None
+        if not self._opt_applied:
+            optimizer.step()
+        return out
+
     def _rollout_grad(self, plan: RolloutPlan, data: dict, target: FlatParams, policy: FlatParams,
                       value: Optional[FlatParams], vtarget: Optional[FlatParams]) -> torch.Tensor:
         """Runs the fused kernel on this rank's shard and all-reduces [grad | loss | v-mean | #done].
@@ -249,5 +269,6 @@ class FusedADPMixin:
                 _lib.ptr(value.sync()) if value is not None else None,
                 _lib.ptr(vtarget.sync()) if vtarget is not None else None,
                 C.c_float(inv_B), _lib.ptr(gbuf), C.c_void_p(gbuf.data_ptr() + 4 * n), _lib.stream_ptr()))
-            allreduce_flat(gbuf)
+            opt, self._fuse_opt = getattr(self, "_fuse_opt", None), None
+            self._opt_applied = allreduce_flat(gbuf, opt)
         return gbuf[n:]

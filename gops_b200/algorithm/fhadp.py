@@ -55,8 +55,8 @@ class FHADP(AlgorithmBase, FusedADPMixin):
 
     def _local_update(self, data: DataDict, iteration: int) -> InfoDict:
         start_time = time.time()
-        tail = self._launch_gradient(data)
-        self.networks.policy_optimizer.step()          # launched behind the rollout: no host sync in between
+        # the optimizer step is launched behind the rollout, no host sync in between
+        tail = self._launch_and_step(lambda: self._launch_gradient(data), self.networks.policy_optimizer)
         self._publish(tail, start_time)
         return self.tb_info
 

@@ -51,8 +51,7 @@ class FHADP2(AlgorithmBase, FusedADPMixin):
 
     def _local_update(self, data, iteration: int):
         start_time = time.time()
-        tail = self._launch_gradient(data)
-        self.networks.policy_optimizer.step()
+        tail = self._launch_and_step(lambda: self._launch_gradient(data), self.networks.policy_optimizer)
         self._publish(tail, start_time)
         return self.tb_info
 

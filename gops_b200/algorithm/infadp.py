@@ -68,8 +68,14 @@ class INFADP(AlgorithmBase, FusedADPMixin):
 
     def local_update(self, data: dict, iteration: int) -> dict:
         start_time = time.time()
-        update_list, tail = self.__launch_gradient(data, iteration)
-        self.__update(update_list)                   # Adam + Polyak launched behind the rollout, no sync in between
+        # Adam + Polyak are launched behind the rollout, no sync in between
+        name = "v" if iteration % (self.pev_step + self.pim_step) < self.pev_step else "policy"
+        self._fuse_opt, self._opt_applied = self.networks.optimizer_dict[name], False
+        try:
+            update_list, tail = self.__launch_gradient(data, iteration)
+        finally:
+            self._fuse_opt = None
+        self.__update(update_list, stepped=self._opt_applied)
         self.__publish(update_list, tail, start_time)
         return self.tb_info
 
@@ -86,9 +92,10 @@ class INFADP(AlgorithmBase, FusedADPMixin):
                 p.grad = grad
         self.__update(list(update_info.keys()))
 
-    def __update(self, update_list):
+    def __update(self, update_list, stepped: bool = False):
         for net_name in update_list:
-            self.networks.optimizer_dict[net_name].step()
+            if not stepped:       # on several GPUs the gradient-exchange kernel has applied the step already
+                self.networks.optimizer_dict[net_name].step()
         for net_name in update_list:
             polyak_update(self.networks.target_net_dict[net_name].flat_params,
                           self.networks.net_dict[net_name].flat_params, self.tau)

@@ -2,6 +2,8 @@
 #pragma once
 #include "rollout.cuh"
 
+#include "adam_math.cuh"
+
 namespace gops {
 
 // ---------------------------------------------------------------------------------------------
@@ -69,13 +71,11 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
                             float step_size, float bc2_sqrt) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const float gi = g[i];
-  const float mi = m[i] + (gi - m[i]) * omb1;           // exp_avg.lerp_(grad, 1 - beta1)
-  const float vi = v[i] * b2 + omb2 * (gi * gi);         // exp_avg_sq.mul_(beta2).addcmul_(g, g, 1-beta2)
+  float pi = p[i], mi = m[i], vi = v[i];
+  adam_update(g[i], pi, mi, vi, omb1, b2, omb2, eps, step_size, bc2_sqrt);
+  p[i] = pi;
   m[i] = mi;
   v[i] = vi;
-  const float denom = sqrtf(vi) / bc2_sqrt + eps;              // (sqrt / bias_correction2_sqrt).add_(eps)
-  p[i] = p[i] - step_size * (mi / denom);                      // addcdiv_(exp_avg, denom, value=-step_size)
 }
 
 __global__ void polyak_kernel(float* __restrict__ tgt, const float* __restrict__ src, float tau, long long n) {

@@ -233,6 +233,11 @@ struct gops_b200_plan {
   long long lw_cap = 0;
   float *lw_S = nullptr, *lw_Dn = nullptr, *lw_X = nullptr, *lw_Z = nullptr, *lw_Zb = nullptr, *lw_lam = nullptr,
         *lw_vacc = nullptr, *lw_dX = nullptr, *lw_sp = nullptr;
+  std::vector<unsigned char> lw_key;      // the call the captured graph belongs to (KParams bytes + buffers + stream)
+  int lw_key_hits = 0;
+  cudaGraphExec_t lw_exec = nullptr;
+  cudaStream_t lw_cap_stream = nullptr;
+  long long lw_graph_launches = 0;
   int last_grid = 0, last_S = 0, last_NT = 0;
   size_t last_smem = 0;
 };
@@ -463,6 +468,8 @@ int launch_rollout_layerwise(gops_b200_plan* pl, const gops_b200_batch* b, const
     for (float** q : bufs) { cudaFree(*q); *q = nullptr; }
     const long long cap = (B + 127) / 128 * 128;
     const int32_t sizes[4] = {in, kp.hid, kp.hid, A};
+    if (pl->lw_exec) { cudaGraphExecDestroy(pl->lw_exec); pl->lw_exec = nullptr; }
+    pl->lw_key.clear();
     if (gops_b200_mlpnet_create(sizes, 4, kp.pol.hact, cap, H, &pl->lw_net)) return 1;
     if (gops_b200_mlpnet_keep_deltas(pl->lw_net, 1)) return 1;
     CUDA_OK(cudaMalloc(&pl->lw_S, sizeof(float) * (size_t)(H + 1) * NS * cap));
@@ -489,6 +496,9 @@ int launch_rollout_layerwise(gops_b200_plan* pl, const gops_b200_batch* b, const
   // S / Dn are indexed with the real batch as the row count
   const unsigned grid = (unsigned)((B + 127) / 128);
   if (pl->timing) CUDA_OK(cudaEventRecord(pl->ev0, st));
+  // The update is ~10 launches per horizon step, each a few microseconds: once the same call (same buffers, same
+  // constants) has been seen twice it is captured into a CUDA graph and replayed, which removes the launch gaps.
+  auto enqueue = [&](cudaStream_t st) -> int {
   if (gops_b200_mlpnet_pack(pl->lw_net, policy_params, st)) return 1;
   f_init<<<grid, 128, 0, st>>>(kp, a);
   ++g_launches;
@@ -516,6 +526,44 @@ int launch_rollout_layerwise(gops_b200_plan* pl, const gops_b200_batch* b, const
   lw_scalars_final_kernel<<<1, 32, 0, st>>>(pl->lw_sp, nb, scalars_out);
   g_launches += 2;
   CUDA_OK_L(cudaGetLastError(), "layer-wise rollout");
+  return 0;
+  };
+  std::vector<unsigned char> key(sizeof(KParams) + 4 * sizeof(void*));
+  memcpy(key.data(), &kp, sizeof(KParams));
+  const void* kptr[4] = {policy_params, grad_out, scalars_out, (const void*)st};
+  memcpy(key.data() + sizeof(KParams), kptr, sizeof(kptr));
+  const char* ge = getenv("GOPS_B200_GRAPH");
+  const bool graphs = !(ge && !strcmp(ge, "0"));
+  if (pl->lw_exec && key == pl->lw_key) {
+    CUDA_OK(cudaGraphLaunch(pl->lw_exec, st));
+    g_launches += pl->lw_graph_launches;
+  } else {
+    if (key == pl->lw_key) ++pl->lw_key_hits;
+    else {
+      pl->lw_key = key;
+      pl->lw_key_hits = 0;
+      if (pl->lw_exec) { cudaGraphExecDestroy(pl->lw_exec); pl->lw_exec = nullptr; }
+    }
+    if (graphs && pl->lw_key_hits >= 1) {
+      const long long n0 = g_launches;
+      // torch's default stream is the legacy stream, which cannot be captured: record on a private stream (nothing
+      // executes during capture), replay on the caller's
+      if (!pl->lw_cap_stream) CUDA_OK(cudaStreamCreateWithFlags(&pl->lw_cap_stream, cudaStreamNonBlocking));
+      CUDA_OK(cudaStreamBeginCapture(pl->lw_cap_stream, cudaStreamCaptureModeThreadLocal));
+      const int rc = enqueue(pl->lw_cap_stream);
+      cudaGraph_t g = nullptr;
+      const cudaError_t ce = cudaStreamEndCapture(pl->lw_cap_stream, &g);
+      if (rc) { if (g) cudaGraphDestroy(g); return 1; }
+      CUDA_OK(ce);
+      const cudaError_t ie = cudaGraphInstantiate(&pl->lw_exec, g, 0);
+      cudaGraphDestroy(g);
+      CUDA_OK(ie);
+      pl->lw_graph_launches = g_launches - n0;
+      CUDA_OK(cudaGraphLaunch(pl->lw_exec, st));
+    } else if (enqueue(st)) {
+      return 1;
+    }
+  }
   if (pl->timing) CUDA_OK(cudaEventRecord(pl->ev1, st));
   pl->last_grid = (int)grid; pl->last_S = 128; pl->last_NT = 128; pl->last_smem = 0; pl->last_path = GOPS_PATH_TC;
   return 0;
@@ -902,6 +950,8 @@ int gops_b200_plan_destroy(gops_b200_plan* pl) {
   if (!pl) return 0;
   DevGuard dg(pl->device);
   if (pl->ev0) { cudaEventDestroy(pl->ev0); cudaEventDestroy(pl->ev1); }
+  if (pl->lw_exec) cudaGraphExecDestroy(pl->lw_exec);
+  if (pl->lw_cap_stream) cudaStreamDestroy(pl->lw_cap_stream);
   if (pl->lw_net) gops_b200_mlpnet_destroy(pl->lw_net);
   {
     float* lw[] = {pl->lw_S, pl->lw_Dn, pl->lw_X, pl->lw_Z, pl->lw_Zb, pl->lw_lam, pl->lw_vacc, pl->lw_dX, pl->lw_sp};

@@ -103,8 +103,7 @@ class FusedAdam(torch.optim.Optimizer):
         if self.flat_params.gbuf is not None:
             self.flat_params.gbuf.zero_()
 
-    @torch.no_grad()
-    def step(self, closure=None):
+    def _state(self):
         fp = self.flat_params
         flat = fp.sync()
         if not flat.is_cuda:
@@ -114,6 +113,18 @@ class FusedAdam(torch.optim.Optimizer):
             self._m = torch.zeros_like(flat)
             self._v = torch.zeros_like(flat)
         self._step += 1
+        return fp, flat
+
+    @torch.no_grad()
+    def fused_state(self):
+        """(params, exp_avg, exp_avg_sq, step, group) of THIS step, for a kernel that applies Adam itself (the
+        peer-memory gradient exchange, utils/peer_reduce.py); counts as the step."""
+        _, flat = self._state()
+        return flat, self._m, self._v, self._step, self.param_groups[0]
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        fp, flat = self._state()
         g = self.param_groups[0]
         with torch.cuda.device(flat.device):      # launch on the parameters' device and its current stream
             _lib.check(_lib.lib().gops_b200_adam_step(

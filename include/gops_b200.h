@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define GOPS_B200_ABI_VERSION 2   /* 2: plan_desc.open_loop, mlpnet_*, plan_set_path, launch_count */
+#define GOPS_B200_ABI_VERSION 3   /* 2: plan_desc.open_loop, mlpnet_*, plan_set_path, launch_count; 3: peer_* */
 #define GOPS_B200_MAX_ACT 4   /* action dims supported by the fused kernels            */
 #define GOPS_B200_MAX_LQ_N 8  /* pyth_lq state dim upper bound (configs ship n <= 6)   */
 
@@ -284,6 +284,30 @@ int gops_b200_dsac_q_loss(const float* q_out, const float* q_next_out, const flo
                           float* d_q_out, float* out3, void* stream);
 int gops_b200_dsac_policy_loss(const float* q_out, const float* logp_new, int64_t batch, float alpha,
                                float target_entropy, float* d_q_out, float* out5, const float* stats, void* stream);
+
+/* ---- data-parallel gradient exchange over NVLink peer memory, fused with Adam (peer.cu) ---------------------------
+ * Replaces the gradient hand-over between replicas of the reference's synchronous trainer
+ * (gops/trainer/off_sync_trainer.py:97-120: workers' get_remote_update_info -> remote_update with the averaged
+ * gradient) and the optimizer step behind it (fhadp.py:89, infadp.py:123-124): ONE kernel per rank pushes its flat
+ * [gradient | loss | ...] vector into every peer's exchange region, waits for the peers' sequence flags, sums in rank
+ * order (bit-identical on all ranks) and applies Adam.  One object per rank; regions are shared with cudaIpc handles
+ * (one process per GPU: _export on every rank, exchange the 64-byte handles, _connect) or wired directly when the
+ * ranks live in one process (_local_base / _connect_local).  All ranks must issue the same sequence of calls. */
+#define GOPS_B200_IPC_HANDLE_BYTES 64
+typedef struct gops_b200_peer gops_b200_peer;
+int gops_b200_peer_create(int32_t world, int32_t rank, int64_t max_floats, gops_b200_peer** out);
+int gops_b200_peer_destroy(gops_b200_peer* peer);
+int gops_b200_peer_region_bytes(const gops_b200_peer* peer, int64_t* bytes);
+int gops_b200_peer_export(gops_b200_peer* peer, void* handle64);
+int gops_b200_peer_connect(gops_b200_peer* peer, const void* handles /* world x 64 bytes, rank order */);
+int gops_b200_peer_local_base(gops_b200_peer* peer, void** base);
+int gops_b200_peer_connect_local(gops_b200_peer* peer, void* const* bases /* world pointers, rank order */);
+/* buf[0..n) <- sum over ranks (in place).  params != NULL: Adam over the first nparam entries with the summed gradient,
+ * arguments as gops_b200_adam_step.  A peer that does not arrive within 4 s poisons buf with NaN and sets _error. */
+int gops_b200_peer_allreduce(gops_b200_peer* peer, float* buf, int64_t n, float* params, float* exp_avg,
+                             float* exp_avg_sq, int64_t nparam, int32_t step, double lr, double beta1, double beta2,
+                             double eps, void* stream);
+int gops_b200_peer_error(gops_b200_peer* peer, int32_t* err);
 
 #ifdef __cplusplus
 }

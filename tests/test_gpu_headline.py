@@ -123,6 +123,42 @@ def test_c3_fhadp_veh3dof_tracking_w256_b8192():
     assert (g_tc[:-4] - g_mma[:-4]).norm() <= 2e-4 * g_mma[:-4].norm()
 
 
+def test_layerwise_update_graph_replay_matches_eager():
+    """The layer-wise update is captured into a CUDA graph the second time the same call (buffers + constants) is
+    seen and replayed from the third on: replays must reproduce the eager launch sequence, follow new CONTENTS of the
+    same buffers, and a call with other buffers must not go through the stale graph."""
+    B, H = 640, 12
+    alg = _alg("veh3dof_tracking", "FHADP", "elu", 256, 6 + 4 * H, 2, seed=4, pre_horizon=H)
+    from gops_b200.env.env_gen_ocp.pyth_base import ContextState, State
+
+    def resident(seed):
+        d = orc.sample_inputs("veh3dof_tracking", B, seed=seed, pre_horizon=H)
+        robot, reference, t0 = d["state"]
+        return {"obs": d["obs"].cuda(), "done": d["done"].cuda(),
+                "state": State(robot_state=robot.cuda(), context_state=ContextState(reference=reference.cuda(), t=t0))}
+
+    d1, d2 = resident(41), resident(42)
+    gbuf = lambda: alg.networks.policy.flat_params.gbuf
+    out = []
+    for _ in range(4):                       # eager, eager (key seen twice -> capture), replay, replay
+        alg._compute_gradient(d1)
+        out.append((gbuf().clone(), float(alg.tb_info["Loss/Actor loss-RL iter"])))
+    for g, l in out[1:]:
+        assert abs(l - out[0][1]) <= 1e-6 * abs(out[0][1])
+        assert (g - out[0][0]).norm() <= 1e-6 * out[0][0].norm()
+    alg._compute_gradient(d2)                # other buffers: eager again
+    g2, l2 = gbuf().clone(), float(alg.tb_info["Loss/Actor loss-RL iter"])
+    assert abs(l2 - out[0][1]) > 1e-4 * abs(l2)
+    d1["obs"].copy_(d2["obs"])               # same buffers as the captured call, new contents: the replay reads them
+    d1["done"].copy_(d2["done"])
+    d1["state"].robot_state.copy_(d2["state"].robot_state)
+    d1["state"].context_state.reference.copy_(d2["state"].context_state.reference)
+    for _ in range(3):
+        alg._compute_gradient(d1)
+        assert abs(float(alg.tb_info["Loss/Actor loss-RL iter"]) - l2) <= 1e-6 * abs(l2)
+        assert (gbuf() - g2).norm() <= 1e-6 * g2.norm()
+
+
 @pytest.mark.parametrize("B,its", [(1 << 16, (0, 1)), (1 << 20, (1,))])
 def test_c5_infadp_lq_sweep_ends(B, its):
     n = 10
