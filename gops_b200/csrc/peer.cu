@@ -34,7 +34,7 @@ namespace {
 constexpr int kMaxWorld = 16;
 constexpr int kBlocks = 8;                 // CTAs per call; each owns a contiguous chunk and its own flags
 constexpr int kThreads = 256;
-constexpr long long kSpinLimitNs = 4000000000ll;     // a peer that never arrives must not hang the GPU
+constexpr long long kSpinLimitNs = 60000000000ll;    // 60 s: a peer that never arrives must not hang the GPU for good
 
 #define PCUDA(expr)                                                                                     \
   do {                                                                                                  \

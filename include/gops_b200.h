@@ -303,7 +303,7 @@ int gops_b200_peer_connect(gops_b200_peer* peer, const void* handles /* world x 
 int gops_b200_peer_local_base(gops_b200_peer* peer, void** base);
 int gops_b200_peer_connect_local(gops_b200_peer* peer, void* const* bases /* world pointers, rank order */);
 /* buf[0..n) <- sum over ranks (in place).  params != NULL: Adam over the first nparam entries with the summed gradient,
- * arguments as gops_b200_adam_step.  A peer that does not arrive within 4 s poisons buf with NaN and sets _error. */
+ * arguments as gops_b200_adam_step.  A peer that does not arrive within 60 s poisons buf with NaN and sets _error. */
 int gops_b200_peer_allreduce(gops_b200_peer* peer, float* buf, int64_t n, float* params, float* exp_avg,
                              float* exp_avg_sq, int64_t nparam, int32_t step, double lr, double beta1, double beta2,
                              double eps, void* stream);
