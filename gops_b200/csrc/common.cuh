@@ -72,6 +72,47 @@ __device__ __forceinline__ void gelu_parts(float x, float& cdf, float& pdf) {
   pdf = 0.39894228040143267794f * e;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Packed FP32 pairs (sm_100: FFMA2 / FMUL2 / FADD2 do two IEEE-rn operations per issue slot).  The epilogues are
+// issue-bound element-wise code over 16 independent columns per thread, so adjacent columns are processed as pairs:
+// same operations, same rounding, same order as the scalar forms above -- results are bit-identical.
+// ---------------------------------------------------------------------------------------------
+namespace f32x2 {
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pk(float lo, float hi) { u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void upk(u64 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ u64 fma(u64 a, u64 b, u64 c) { u64 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ u64 mul(u64 a, u64 b) { u64 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ u64 add(u64 a, u64 b) { u64 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ u64 rep(float c) { return pk(c, c); }
+__device__ __forceinline__ u64 ld(const float* p) { return *reinterpret_cast<const u64*>(p); }      // 8-byte aligned pair
+}  // namespace f32x2
+
+// gelu_parts for a pair: H = x cdf, D = cdf + x pdf (WANT_D).  0.5 is folded into the polynomial (an exact scaling).
+template <bool WANT_D>
+__device__ __forceinline__ void gelu_pair(f32x2::u64 X, f32x2::u64& H, f32x2::u64& D) {
+  using namespace f32x2;
+  float x0, x1, a0, a1, e0, e1, k0, k1;
+  upk(X, x0, x1);
+  upk(mul(mul(X, X), rep(-0.72134752044448170368f)), a0, a1);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(a0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(a1));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(k0) : "f"(fmaf(fabsf(x0), 0.23164189045f, 1.0f)));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(k1) : "f"(fmaf(fabsf(x1), 0.23164189045f, 1.0f)));
+  const u64 K = pk(k0, k1), E = pk(e0, e1);
+  u64 PL = fma(rep(0.5f * 1.061405429f), K, rep(0.5f * -1.453152027f));
+  PL = fma(PL, K, rep(0.5f * 1.421413741f));
+  PL = fma(PL, K, rep(0.5f * -0.284496736f));
+  PL = fma(PL, K, rep(0.5f * 0.254829592f));
+  const u64 HE = mul(mul(PL, K), E);                 // half erfc(|x| / sqrt 2)
+  float he0, he1, q0, q1;
+  upk(HE, he0, he1);
+  upk(fma(HE, rep(-1.f), rep(1.f)), q0, q1);
+  const u64 CDF = pk(x0 >= 0.f ? q0 : he0, x1 >= 0.f ? q1 : he1);
+  H = mul(X, CDF);
+  if constexpr (WANT_D) D = fma(X, mul(E, rep(0.39894228040143267794f)), CDF);
+}
+
 __device__ __forceinline__ float act_fwd(int act, float x) {
   switch (act) {
     case GOPS_ACT_RELU: return fmaxf(x, 0.f);
@@ -134,6 +175,34 @@ __device__ __forceinline__ void act_fwd_grad_t(float x, float& h, float& d) {
   } else if constexpr (ACT == GOPS_ACT_SIGMOID) { h = 1.f / (1.f + expf(-x)); d = h * (1.f - h); }
   else if constexpr (ACT == GOPS_ACT_TANH) { h = tanhf(x); d = 1.f - h * h; }
   else { h = x; d = 1.f; }
+}
+// Pair forms (adjacent columns): GELU runs packed, the others are two scalar evaluations.
+template <int ACT>
+__device__ __forceinline__ void act_fwd_pair_t(f32x2::u64 X, float& h0, float& h1) {
+  if constexpr (ACT == GOPS_ACT_GELU) {
+    f32x2::u64 Hh, D;
+    gelu_pair<false>(X, Hh, D);
+    f32x2::upk(Hh, h0, h1);
+  } else {
+    float x0, x1;
+    f32x2::upk(X, x0, x1);
+    h0 = act_fwd_t<ACT>(x0);
+    h1 = act_fwd_t<ACT>(x1);
+  }
+}
+template <int ACT>
+__device__ __forceinline__ void act_fwd_grad_pair_t(f32x2::u64 X, float& h0, float& h1, float& d0, float& d1) {
+  if constexpr (ACT == GOPS_ACT_GELU) {
+    f32x2::u64 Hh, D;
+    gelu_pair<true>(X, Hh, D);
+    f32x2::upk(Hh, h0, h1);
+    f32x2::upk(D, d0, d1);
+  } else {
+    float x0, x1;
+    f32x2::upk(X, x0, x1);
+    act_fwd_grad_t<ACT>(x0, h0, d0);
+    act_fwd_grad_t<ACT>(x1, h1, d1);
+  }
 }
 // GOPS_ACT_SWITCH(act, M): expands M(ACT) for the runtime activation id `act` (M is a one-argument macro)
 #define GOPS_ACT_SWITCH(act, M)                 \

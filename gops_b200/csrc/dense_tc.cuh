@@ -126,7 +126,8 @@ __device__ __forceinline__ void store_tile(const TileRegs& t, unsigned char* pla
       if constexpr (NPL == 3) tcf::split3(v[2 * j], v[2 * j + 1], w[0][j], w[1][j], w[2][j]);
       else {
         asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w[0][j]) : "f"(v[2 * j + 1]), "f"(v[2 * j]));
-        const float q0 = v[2 * j] - __uint_as_float(w[0][j] << 16), q1 = v[2 * j + 1] - __uint_as_float(w[0][j] & 0xffff0000u);
+        float q0, q1;
+        f32x2::upk(f32x2::fma(tcf::bf16x2_as_f32x2(w[0][j]), f32x2::rep(-1.f), f32x2::pk(v[2 * j], v[2 * j + 1])), q0, q1);
         asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w[1][j]) : "f"(q1), "f"(q0));
       }
     }
@@ -234,9 +235,9 @@ __global__ void __launch_bounds__(NTH, 1) dense_gemm_kernel(const __grid_constan
       if (row < g.rows) {
         if constexpr (EPI == EPI_ACT) {
 #define GOPS_DENSE_ACT(A)                                                                     \
-  _Pragma("unroll") for (int e = 0; e < 16; ++e) {                                            \
-    const float pre = v[e] + (n0 + e < g.n ? g.bias[n0 + e] : 0.f);                           \
-    act_fwd_grad_t<A>(pre, v[e], d[e]);                                                       \
+  _Pragma("unroll") for (int e = 0; e < 16; e += 2) {                                         \
+    const float b0 = n0 + e < g.n ? g.bias[n0 + e] : 0.f, b1 = n0 + e + 1 < g.n ? g.bias[n0 + e + 1] : 0.f; \
+    act_fwd_grad_pair_t<A>(f32x2::add(f32x2::pk(v[e], v[e + 1]), f32x2::pk(b0, b1)), v[e], v[e + 1], d[e], d[e + 1]); \
   }
           GOPS_ACT_SWITCH(g.act, GOPS_DENSE_ACT)
 #undef GOPS_DENSE_ACT

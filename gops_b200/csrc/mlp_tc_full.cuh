@@ -104,14 +104,24 @@ __device__ __forceinline__ void issue_stack(uint32_t d, const Op& A, const Op& B
   for (int ks = 0; ks < 8; ++ks) mma_bf16(d, a2 + ks * ka, b0 + ks * kb, idesc, 1u, true);
 }
 
-// (x0, x1) -> packed bf16x2 words of the three planes (low half = x0)
-__device__ __forceinline__ void split3(float x0, float x1, uint32_t& p0, uint32_t& p1, uint32_t& p2) {
-  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(p0) : "f"(x1), "f"(x0));
-  float r0 = x0 - __uint_as_float(p0 << 16), r1 = x1 - __uint_as_float(p0 & 0xffff0000u);
+// (x0, x1) -> packed bf16x2 words of the three planes (low half = x0); the residuals x - hi are formed by one packed
+// FMA per pair (hi * -1 + x: the same rounding as the subtraction)
+__device__ __forceinline__ f32x2::u64 bf16x2_as_f32x2(uint32_t p) {
+  return f32x2::pk(__uint_as_float(p << 16), __uint_as_float(p & 0xffff0000u));
+}
+__device__ __forceinline__ void split3(f32x2::u64 X, uint32_t& p0, uint32_t& p1, uint32_t& p2) {
+  float r0, r1;
+  f32x2::upk(X, r0, r1);
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(p0) : "f"(r1), "f"(r0));
+  f32x2::u64 R = f32x2::fma(bf16x2_as_f32x2(p0), f32x2::rep(-1.f), X);
+  f32x2::upk(R, r0, r1);
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(p1) : "f"(r1), "f"(r0));
-  r0 -= __uint_as_float(p1 << 16);
-  r1 -= __uint_as_float(p1 & 0xffff0000u);
+  R = f32x2::fma(bf16x2_as_f32x2(p1), f32x2::rep(-1.f), R);
+  f32x2::upk(R, r0, r1);
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(p2) : "f"(r1), "f"(r0));
+}
+__device__ __forceinline__ void split3(float x0, float x1, uint32_t& p0, uint32_t& p1, uint32_t& p2) {
+  split3(f32x2::pk(x0, x1), p0, p1, p2);
 }
 // 16 values of thread (q, c) -> its two 16-byte chunks (kc = 2c, 2c+1) of row r in the three planes of `buf`
 __device__ __forceinline__ void store16(unsigned char* buf, int plane_bytes, int c, int r, const float* v) {

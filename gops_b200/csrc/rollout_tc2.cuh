@@ -81,11 +81,14 @@ __device__ __forceinline__ void tm_st32(uint32_t taddr, const float* v) {
 }
 
 // (x0, x1) -> packed bf16x2 words of two planes (low half = x0)
-__device__ __forceinline__ void split2(float x0, float x1, uint32_t& p0, uint32_t& p1) {
-  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(p0) : "f"(x1), "f"(x0));
-  const float r0 = x0 - __uint_as_float(p0 << 16), r1 = x1 - __uint_as_float(p0 & 0xffff0000u);
+__device__ __forceinline__ void split2(f32x2::u64 X, uint32_t& p0, uint32_t& p1) {
+  float r0, r1;
+  f32x2::upk(X, r0, r1);
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(p0) : "f"(r1), "f"(r0));
+  f32x2::upk(f32x2::fma(tcf::bf16x2_as_f32x2(p0), f32x2::rep(-1.f), X), r0, r1);
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(p1) : "f"(r1), "f"(r0));
 }
+__device__ __forceinline__ void split2(float x0, float x1, uint32_t& p0, uint32_t& p1) { split2(f32x2::pk(x0, x1), p0, p1); }
 
 // Per-thread view of its group's resources.  g, h, wg are warp-uniform (derived from a __shfl_sync'ed warp id).
 struct Grp {
@@ -229,10 +232,10 @@ __device__ __forceinline__ void layer1_finish(Grp& G, const NetL& L, int lo, int
     umma::tmem_ld16(G.tm + C_ACC + 16 * c16, v);
     const float* bias = G.b1 + 16 * c16;
 #define GOPS_TC2_A1(A)                                                      \
-  _Pragma("unroll") for (int e = 0; e < 16; ++e) {                          \
-    const float pre = v[e] + bias[e];                                       \
-    if constexpr (FULL) act_fwd_grad_t<A>(pre, v[e], d[e]);                 \
-    else v[e] = act_fwd_t<A>(pre);                                          \
+  _Pragma("unroll") for (int e = 0; e < 16; e += 2) {                                         \
+    const f32x2::u64 pre = f32x2::add(f32x2::pk(v[e], v[e + 1]), f32x2::ld(bias + e));       \
+    if constexpr (FULL) act_fwd_grad_pair_t<A>(pre, v[e], v[e + 1], d[e], d[e + 1]);          \
+    else act_fwd_pair_t<A>(pre, v[e], v[e + 1]);                                              \
   }
     GOPS_ACT_SWITCH(L.hact, GOPS_TC2_A1)
 #undef GOPS_TC2_A1
@@ -266,16 +269,20 @@ __device__ __forceinline__ void layer2_out(Grp& G, const NetL& L, float* z) {
     float v[16];
     umma::tmem_ld16(G.tm + C_ACC + 16 * c16, v);
     const float* bias = G.b2 + 16 * c16;
-#define GOPS_TC2_A2(A) _Pragma("unroll") for (int e = 0; e < 16; ++e) v[e] = act_fwd_t<A>(v[e] + bias[e]);
+#define GOPS_TC2_A2(A)                               \
+  _Pragma("unroll") for (int e = 0; e < 16; e += 2)  \
+      act_fwd_pair_t<A>(f32x2::add(f32x2::pk(v[e], v[e + 1]), f32x2::ld(bias + e)), v[e], v[e + 1]);
     GOPS_ACT_SWITCH(L.hact, GOPS_TC2_A2)
 #undef GOPS_TC2_A2
 #pragma unroll
     for (int a = 0; a < MAXA; ++a)
       if (a < L.out) {
         const float* w = G.W3 + a * 64 + 16 * c16;
-        float s0 = 0.f, s1 = 0.f;
+        f32x2::u64 S = f32x2::rep(0.f);           // (even, odd) column partial sums
 #pragma unroll
-        for (int e = 0; e < 16; e += 2) { s0 = fmaf(w[e], v[e], s0); s1 = fmaf(w[e + 1], v[e + 1], s1); }
+        for (int e = 0; e < 16; e += 2) S = f32x2::fma(f32x2::ld(w + e), f32x2::pk(v[e], v[e + 1]), S);
+        float s0, s1;
+        f32x2::upk(S, s0, s1);
         zp[a] += s0 + s1;
       }
   }
@@ -337,7 +344,9 @@ __device__ __forceinline__ void layer2_back(Grp& G, const NetL& L, const float* 
     float v[16], d[16];
     umma::tmem_ld16(G.tm + C_ACC + 16 * c16, v);
     const float* bias = G.b2 + 16 * c16;
-#define GOPS_TC2_A3(A) _Pragma("unroll") for (int e = 0; e < 16; ++e) act_fwd_grad_t<A>(v[e] + bias[e], v[e], d[e]);
+#define GOPS_TC2_A3(A)                               \
+  _Pragma("unroll") for (int e = 0; e < 16; e += 2)  \
+      act_fwd_grad_pair_t<A>(f32x2::add(f32x2::pk(v[e], v[e + 1]), f32x2::ld(bias + e)), v[e], v[e + 1], d[e], d[e + 1]);
     GOPS_ACT_SWITCH(L.hact, GOPS_TC2_A3)
 #undef GOPS_TC2_A3
     const float* w3 = G.W3 + 16 * c16;
@@ -345,9 +354,11 @@ __device__ __forceinline__ void layer2_back(Grp& G, const NetL& L, const float* 
 #pragma unroll
       for (int a = 0; a < MAXA; ++a)
         if (a < L.out) {
-          float s0 = 0.f, s1 = 0.f;
+          f32x2::u64 S = f32x2::rep(0.f);
 #pragma unroll
-          for (int e = 0; e < 16; e += 2) { s0 = fmaf(w3[a * 64 + e], v[e], s0); s1 = fmaf(w3[a * 64 + e + 1], v[e + 1], s1); }
+          for (int e = 0; e < 16; e += 2) S = f32x2::fma(f32x2::ld(w3 + a * 64 + e), f32x2::pk(v[e], v[e + 1]), S);
+          float s0, s1;
+          f32x2::upk(S, s0, s1);
           zp[a] += s0 + s1;
         }
     }
@@ -357,26 +368,27 @@ __device__ __forceinline__ void layer2_back(Grp& G, const NetL& L, const float* 
         if (a < L.out) {
           float t[16];
 #pragma unroll
-          for (int e = 0; e < 16; ++e) t[e] = zb[a] * v[e];
+          for (int e = 0; e < 16; e += 2) f32x2::upk(f32x2::mul(f32x2::rep(zb[a]), f32x2::pk(v[e], v[e + 1])), t[e], t[e + 1]);
           warp_reduce16(t, lane);
           acc3.w0[a] += cb == 0 ? t[0] : 0.f;
           acc3.w1[a] += cb == 0 ? 0.f : t[0];
         }
     }
+    f32x2::u64 D2[8];                              // delta2 pairs = act'(pre2) * (W3^T zbar)
 #pragma unroll
-    for (int e = 0; e < 16; ++e) {
-      float gsum = 0.f;
+    for (int e = 0; e < 16; e += 2) {
+      f32x2::u64 gs = f32x2::rep(0.f);
 #pragma unroll
       for (int a = 0; a < MAXA; ++a)
-        if (a < L.out) gsum = fmaf(w3[a * 64 + e], zb[a], gsum);
-      d[e] *= gsum;
+        if (a < L.out) gs = f32x2::fma(f32x2::ld(w3 + a * 64 + e), f32x2::rep(zb[a]), gs);
+      D2[e / 2] = f32x2::mul(f32x2::pk(d[e], d[e + 1]), gs);
     }
     // two delta planes: chunks 2 c16, 2 c16 + 1 of row r
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
       uint32_t w0[4], w1[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) split2(d[8 * c + 2 * i], d[8 * c + 2 * i + 1], w0[i], w1[i]);
+      for (int i = 0; i < 4; ++i) split2(D2[4 * c + i], w0[i], w1[i]);
       *reinterpret_cast<uint4*>(G.Q + ((2 * c16 + c) * 128 + G.r) * 16) = make_uint4(w0[0], w0[1], w0[2], w0[3]);
       *reinterpret_cast<uint4*>(G.Q + HPL + ((2 * c16 + c) * 128 + G.r) * 16) = make_uint4(w1[0], w1[1], w1[2], w1[3]);
     }
@@ -447,8 +459,8 @@ __device__ __forceinline__ void backprop(Grp& G, const NetL& L, bool want_dx, fl
     tm_wait_ld();
 #pragma unroll
     for (int i = 0; i < 16; ++i)
-      split2(__uint_as_float(ra[2 * i]) * __uint_as_float(rb[2 * i]),
-             __uint_as_float(ra[2 * i + 1]) * __uint_as_float(rb[2 * i + 1]), w0[i], w1[i]);
+      split2(f32x2::mul(f32x2::pk(__uint_as_float(ra[2 * i]), __uint_as_float(ra[2 * i + 1])),
+                        f32x2::pk(__uint_as_float(rb[2 * i]), __uint_as_float(rb[2 * i + 1]))), w0[i], w1[i]);
   }
   if (!WANT_DW && !want_dx) {
     umma::fence_before_sync();
