@@ -54,6 +54,11 @@ __host__ __device__ inline size_t smem_bytes(int w_floats) {
 }
 
 __device__ __forceinline__ void group_sync(int g) { asm volatile("bar.sync %0, 256;" ::"r"(1 + g) : "memory"); }
+// Issue order of the two MMA streams of a backward stage: warp 0 (critical-path product) arrives after its commit,
+// warp 1 (weight-gradient products, twice the work) issues behind it -- the tensor pipe executes in arrival order, and
+// a critical product queued behind the weight gradients costs the whole group ~1 k cycles per stage.
+__device__ __forceinline__ void order_arrive(int g) { asm volatile("bar.arrive %0, 64;" ::"r"(3 + g) : "memory"); }
+__device__ __forceinline__ void order_wait(int g) { asm volatile("bar.sync %0, 64;" ::"r"(3 + g) : "memory"); }
 using umma::elect_one;
 
 // 16 accumulator columns of this thread's lane, WITHOUT waiting (issue several, then tm_wait_ld once)
@@ -433,9 +438,11 @@ __device__ __forceinline__ void backprop(Grp& G, const NetL& L, bool want_dx, fl
       issue_dw<4>(G.tmg + C_ACC, k_act(G.Q, HPL), mn_w(G.W2, W2PLANE), idesc_bf16(128, 64, false, true));
       umma::commit(G.bc);
     }
+    if constexpr (WANT_DW) order_arrive(G.g);
   }
   if constexpr (WANT_DW) {
     if (G.wg == 1) {
+      order_wait(G.g);
       if (elect_one()) {
         umma::fence_after_sync();
         const Op A = mn_act(G.Q, HPL);
@@ -476,17 +483,19 @@ __device__ __forceinline__ void backprop(Grp& G, const NetL& L, bool want_dx, fl
   }
   publish(G);
   TL(G, 21);
-  if (want_dx) {
-    if (G.wg == 0) {
+  if (G.wg == 0) {
+    if (want_dx) {
       if (elect_one()) {
         umma::fence_after_sync();
         issue_dw<4>(G.tmg + C_ACC, k_act(G.Q, HPL), mn_w(G.W1, W1PLANE), idesc_bf16(128, 16, false, true));
         umma::commit(G.bc);
       }
     }
+    if constexpr (WANT_DW) order_arrive(G.g);
   }
   if constexpr (WANT_DW) {
     if (G.wg == 1) {
+      order_wait(G.g);
       if (elect_one()) {
         umma::fence_after_sync();
         const Op A = mn_act(G.Q, HPL);
