@@ -40,7 +40,7 @@ constexpr int GT = 128;                 // rows (= samples) per sub-tile = UMMA 
 constexpr int GTH = 256;                // threads per group: owner half (h = 0) + helper half (h = 1)
 constexpr int NG = 2;                   // groups per CTA
 constexpr int NT2 = GTH * NG;
-constexpr uint32_t C_ACC = 0, C_D1 = 64, C_DW2 = 128, C_DB2 = 192, C_DW1 = 208, C_DB1 = 224, C_GROUP = 256;
+constexpr uint32_t C_ACC = 0, C_D1 = 64, C_DW2 = 128, C_DB2 = 192, C_DW1 = 208, C_DB1 = 224, C_DX = 240, C_GROUP = 256;
 constexpr int HPL = tcf::HPLANE, XPL = tcf::XPLANE;
 constexpr int P_BYTES = 3 * HPL, Q_BYTES = 2 * HPL, XP_BYTES = 3 * XPL;
 constexpr int XCH_BYTES = 2 * GT * MAXA * 4;   // helper -> owner output partials | owner -> helper output adjoints
@@ -100,8 +100,8 @@ struct Grp {
   unsigned char *P, *Q, *Xp;        // H1 planes (3), delta planes (2), observation planes (3)
   float *zp, *zb;                   // exchange: helper -> owner output partials [128][MAXA]; owner -> helper adjoints
   const unsigned char* ones;
-  uint64_t *bc, *bd2, *bd1;         // mbarriers: critical-path MMA groups / dW2+db2 / dW1+db1
-  uint32_t pc, pd2, pd1;            // their phases
+  uint64_t *bc, *bd2, *bd1, *bdx;   // mbarriers: critical-path MMA groups / dW2+db2 / dW1+db1 / deferred input gradient
+  uint32_t pc, pd2, pd1, pdx;       // their phases
   uint32_t tm;                      // TMEM address of this thread's lane, column 0 of the group
   uint32_t tmg;                     // TMEM address lane 0, column 0 of the group (MMA destinations)
   uint32_t fresh;                   // 1: the next weight-gradient MMAs overwrite their accumulators
@@ -426,8 +426,11 @@ __device__ __forceinline__ void layer2_back(Grp& G, const NetL& L, const float* 
 
 // delta2 planes -> delta1 = (delta2 . W2) * act'(pre1) (same planes, once the readers of delta2 retired) ->
 // input gradient dx[0 .. 15] for the owner (want_dx) and the weight-gradient MMAs of both layers (WANT_DW).
+// defer_dx: the input-gradient product goes to its own TMEM columns (C_DX) and mbarrier and is NOT waited for here; the
+// owner picks it up with collect_dx() when it needs the adjoint (reverse sweep: after the next step's layer-1 MMAs were
+// issued), which takes one MMA round trip off the serial chain of every step.
 template <bool WANT_DW>
-__device__ __forceinline__ void backprop(Grp& G, const NetL& L, bool want_dx, float* dx) {
+__device__ __forceinline__ void backprop(Grp& G, const NetL& L, bool want_dx, float* dx, bool defer_dx = false) {
   using namespace tcf;
   TL(G, 16);
   publish(G);
@@ -487,8 +490,8 @@ __device__ __forceinline__ void backprop(Grp& G, const NetL& L, bool want_dx, fl
     if (want_dx) {
       if (elect_one()) {
         umma::fence_after_sync();
-        issue_dw<4>(G.tmg + C_ACC, k_act(G.Q, HPL), mn_w(G.W1, W1PLANE), idesc_bf16(128, 16, false, true));
-        umma::commit(G.bc);
+        issue_dw<4>(G.tmg + (defer_dx ? C_DX : C_ACC), k_act(G.Q, HPL), mn_w(G.W1, W1PLANE), idesc_bf16(128, 16, false, true));
+        umma::commit(defer_dx ? G.bdx : G.bc);
       }
     }
     if constexpr (WANT_DW) order_arrive(G.g);
@@ -508,7 +511,7 @@ __device__ __forceinline__ void backprop(Grp& G, const NetL& L, bool want_dx, fl
     G.d1_pending = true;
     G.fresh = 0u;
   }
-  if (want_dx) {
+  if (want_dx && !defer_dx) {
     wait_c(G);
     TL(G, 22);
     if (G.h == 0) {
@@ -520,6 +523,19 @@ __device__ __forceinline__ void backprop(Grp& G, const NetL& L, bool want_dx, fl
     }
     umma::fence_before_sync();
   }
+}
+
+// owner half: the deferred input gradient of the previous backprop(..., defer_dx = true)
+__device__ __forceinline__ void collect_dx(Grp& G, float* dx) {
+  mbar_wait(G.bdx, G.pdx);
+  G.pdx ^= 1u;
+  umma::fence_after_sync();
+  uint32_t rr[16];
+  tm_ld16(G.tm + C_DX, rr);
+  tm_wait_ld();
+#pragma unroll
+  for (int f = 0; f < 16; ++f) dx[f] = __uint_as_float(rr[f]);
+  umma::fence_before_sync();
 }
 
 // TMEM weight-gradient accumulators -> the group's FP32 global partial (torch flat layout), then mark them fresh.
@@ -599,7 +615,7 @@ __global__ void __launch_bounds__(tc2::NT2, 1) rollout_tc2_kernel(const __grid_c
   constexpr int NS = M::NS, alg = ALG;
   extern __shared__ __align__(16) float smem[];
   unsigned char* sm = reinterpret_cast<unsigned char*>(smem);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sm);           // [0] weights, [1 + 3 g ..] group g: bc, bd2, bd1
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm);           // [0] weights, [1 + 4 g ..] group g: bc, bd2, bd1, bdx
   uint32_t* tslot = reinterpret_cast<uint32_t*>(sm + 128);
   float* Wsm = reinterpret_cast<float*>(sm + HDR_BYTES);
   unsigned char* ones = sm + HDR_BYTES + (size_t)p.w_floats * 4;
@@ -618,8 +634,8 @@ __global__ void __launch_bounds__(tc2::NT2, 1) rollout_tc2_kernel(const __grid_c
   G.zp = reinterpret_cast<float*>(G.Xp + XP_BYTES);
   G.zb = G.zp + GT * MAXA;
   G.ones = ones;
-  G.bc = bars + 1 + 3 * G.g; G.bd2 = G.bc + 1; G.bd1 = G.bc + 2;
-  G.pc = G.pd2 = G.pd1 = 0u;
+  G.bc = bars + 1 + 4 * G.g; G.bd2 = G.bc + 1; G.bd1 = G.bc + 2; G.bdx = G.bc + 3;
+  G.pc = G.pd2 = G.pd1 = G.pdx = 0u;
   G.fresh = 1u;
   G.d2_pending = G.d1_pending = false;
   const bool own = G.h == 0;
@@ -630,7 +646,7 @@ __global__ void __launch_bounds__(tc2::NT2, 1) rollout_tc2_kernel(const __grid_c
 #endif
 
   if (tid == 0) {
-    for (int i = 0; i < 1 + 3 * NG; ++i) mbar_init(bars + i, 1);
+    for (int i = 0; i < 1 + 4 * NG; ++i) mbar_init(bars + i, 1);
     fence_mbar_init();
   }
   if (tid < 256) {  // `ones`: [2 mn-groups][16 rows][8 bf16], feature 0 = 1.0
@@ -842,6 +858,7 @@ __global__ void __launch_bounds__(tc2::NT2, 1) rollout_tc2_kernel(const __grid_c
       for (int f = 0; f < NS; ++f) nst[f] = tape[((H - 1) * TCH + f) * GT + G.r];
       ndn = tape[((H - 1) * TCH + NS) * GT + G.r] != 0.f;
     }
+    bool dx_pending = false, dx_add = false;
     for (int k = H - 1; k >= 0; --k) {
       float zt[MAXA];
       const bool dnk = ndn;
@@ -855,6 +872,15 @@ __global__ void __launch_bounds__(tc2::NT2, 1) rollout_tc2_kernel(const __grid_c
           if (j < P.out) zt[j] = tape[(k * TCH + NS + 1 + j) * GT + G.r];
       }
       layer1_issue<NS>(G, P, st, (float)(k + 1));     // recompute: issued first, the adjoint below overlaps the MMA
+      if (own && dx_pending) {                        // input gradient of step k + 1 (its MMAs ran under the code above)
+        float dxn[16];
+        collect_dx(G, dxn);
+        if (dx_add) {
+#pragma unroll
+          for (int f = 0; f < NS; ++f)
+            if (f < obs_dim) lam[f] += dxn[f];
+        }
+      }
       float zb[MAXA];
 #pragma unroll
       for (int j = 0; j < MAXA; ++j) zb[j] = 0.f;
@@ -922,12 +948,9 @@ __global__ void __launch_bounds__(tc2::NT2, 1) rollout_tc2_kernel(const __grid_c
       layer1_finish<true>(G, P, 0, G.h == 0 ? 0 : 4);      // the helper converts the whole row meanwhile
       float dx[16];
       layer2_back<true, false>(G, P, zb, nullptr, acc3);
-      backprop<true>(G, P, k > 0, dx);
-      if (active && k > 0) {
-#pragma unroll
-        for (int f = 0; f < NS; ++f)
-          if (f < obs_dim) lam[f] += dx[f];
-      }
+      backprop<true>(G, P, k > 0, dx, true);
+      dx_pending = k > 0;
+      dx_add = active && k > 0;
       if ((H - k) % FLUSH_EVERY == 0 || k == 0) flush(G, P, part);
     }
   }
