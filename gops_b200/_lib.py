@@ -15,7 +15,7 @@ PATH_AUTO, PATH_MMA, PATH_TC = 0, 1, 2
 PATH_NAMES = {0: "none", 1: "mma", 2: "tc"}
 ACT_IDS = {"relu": 0, "elu": 1, "gelu": 2, "selu": 3, "sigmoid": 4, "tanh": 5, "linear": 6}
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libgops_b200.so")
+LIB_PATH = os.environ.get("GOPS_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libgops_b200.so")   # override: A/B runs of two builds
 
 
 class MlpDesc(C.Structure):
