@@ -393,12 +393,62 @@ class Veh3dofTrackingModel(BaseModel):
         return nobs, reward, isdone, {"state": (nrobot, reference, t + 1)}
 
 
+class Veh3dofTrackingDetourModel(BaseModel):
+    """env_gen_ocp/env_model/veh3dof_tracking_detour_model.py:13-176 via EnvModel.forward
+    env_gen_ocp/env_model/pyth_base_model.py:109-119: veh3dof_tracking plus ONE surrounding vehicle -- its ego-frame
+    pose (and raw speed) as four more observation entries (:62-76), the bicircle collision constraint 2 r - min dist of
+    the INCOMING state (:78-131, pyth_base_model.py:117-118), other reward weights / offset (:133-150) and a wider lateral
+    termination bound (:152-163).  info = {"state": (robot[B,6], reference[B,L,4], t:int, surr[B,P+1,n,5])}."""
+
+    def __init__(self, pre_horizon=10, max_steer=math.pi / 6, veh_length=4.8, veh_width=2.0, dtype=torch.float32, **_):
+        self.pre_horizon = pre_horizon
+        self.obs_dim, self.action_dim, self.dt = 6 + 4 * pre_horizon + 4, 2, 0.1
+        self.veh_length, self.veh_width = veh_length, veh_width
+        self._bounds(act_lo=[-max_steer, -3], act_hi=[max_steer, 3], dtype=dtype)
+
+    def get_obs(self, robot, reference, t, surr):
+        base = veh_obs(robot, reference[:, t:t + self.pre_horizon + 1])
+        c = surr[:, t]
+        sx, sy, sphi = ego_transform(robot[:, 0], robot[:, 1], robot[:, 2], c[..., 0], c[..., 1], c[..., 2])
+        so = torch.stack((sx, sy, sphi, c[..., 3]), 2).reshape(base.shape[0], -1)
+        return torch.cat((base, so), 1)
+
+    def get_constraint(self, robot, surr_t):
+        d, r = (self.veh_length - self.veh_width) / 2, 0.5 * self.veh_width
+        x, y, phi = robot[:, 0:1], robot[:, 1:2], robot[:, 2:3]
+        ego = [torch.cat((x + s * d * torch.cos(phi), y + s * d * torch.sin(phi)), 1) for s in (1.0, -1.0)]
+        sx, sy, sphi = surr_t[..., 0], surr_t[..., 1], surr_t[..., 2]
+        sur = [torch.stack((sx + s * d * torch.cos(sphi), sy + s * d * torch.sin(sphi)), 2) for s in (1.0, -1.0)]
+        min_dist = torch.full_like(x, float(np.finfo(np.float32).max))
+        for e in ego:
+            for q in sur:
+                dist = torch.linalg.norm(e.unsqueeze(1) - q, dim=2)
+                min_dist = torch.minimum(min_dist, dist.min(dim=1, keepdim=True).values)
+        return 2 * r - min_dist
+
+    def step(self, obs, action, done, info):
+        robot, reference, t, surr = info["state"]
+        nrobot = veh3dof_next_state(robot, action, self.dt)
+        nobs = self.get_obs(nrobot, reference, t + 1, surr)
+        r = reference[:, t]
+        steer, a_x = action[:, 0], action[:, 1]
+        reward = -0.01 * (10.0 * (robot[:, 0] - r[:, 0]) ** 2 + 10.0 * (robot[:, 1] - r[:, 1]) ** 2
+                          + 500 * angle_normalize(robot[:, 2] - r[:, 2]) ** 2 + 5.0 * (robot[:, 3] - r[:, 3]) ** 2
+                          + 1000 * robot[:, 5] ** 2 + 1000 * steer ** 2 + 50 * a_x ** 2) + 2.0
+        rn = reference[:, t + 1]
+        isdone = ((torch.abs(nrobot[:, 0] - rn[:, 0]) > 5) | (torch.abs(nrobot[:, 1] - rn[:, 1]) > 3)
+                  | (torch.abs(angle_normalize(nrobot[:, 2] - rn[:, 2])) > math.pi))
+        return nobs, reward, isdone, {"state": (nrobot, reference, t + 1, surr),
+                                      "constraint": self.get_constraint(robot, surr[:, t])}
+
+
 MODEL_REGISTRY = {
     "pyth_idpendulum": IdPendulumModel,
     "pyth_lq": LqModel,
     "pyth_veh3dofconti": Veh3dofContiModel,
     "veh3dof_tracking": Veh3dofTrackingModel,
-                  "pyth_veh3dofconti_errcstr": Veh3dofContiErrCstrModel}
+                  "pyth_veh3dofconti_errcstr": Veh3dofContiErrCstrModel,
+                  "veh3dof_tracking_detour": Veh3dofTrackingDetourModel}
 
 
 # --------------------------------------------------------------------------------------
@@ -617,7 +667,7 @@ def sample_inputs(env_id: str, batch: int, seed: int, *, pre_horizon: int = 10, 
         cfg = LQ_CONFIGS[lq_config]
         mean, std = torch.tensor(cfg["init_mean"], dtype=torch.float32), torch.tensor(cfg["init_std"], dtype=torch.float32)
         return {"obs": mean + std * torch.randn(batch, len(cfg["init_mean"]), generator=g), "done": torch.zeros(batch)}
-    if env_id in ("pyth_veh3dofconti", "veh3dof_tracking"):
+    if env_id in ("pyth_veh3dofconti", "veh3dof_tracking", "veh3dof_tracking_detour"):
         # pyth_veh3dofconti.py:144-191 ; env_gen_ocp/context/ref_traj.py:25-53
         ref = RefTraj()
         P = pre_horizon
@@ -639,5 +689,23 @@ def sample_inputs(env_id: str, batch: int, seed: int, *, pre_horizon: int = 10, 
         if env_id == "pyth_veh3dofconti":
             return {"obs": obs, "done": torch.zeros(batch), "state": state, "ref_points": ref_points,
                     "path_num": path, "u_num": spd, "ref_time": t0}
+        if env_id == "veh3dof_tracking_detour":
+            # env_gen_ocp/context/ref_traj_with_static_obstacle.py:76-127: one surrounding vehicle predicted over P + 1
+            # points (x, y, phi, u, delta); here ahead of the ego vehicle near the path (some samples start infeasible)
+            # and moving slowly along its heading
+            sp = ref_points[:, 0]
+            ahead, side = 4.0 + 12.0 * U(batch), (U(batch) * 2 - 1) * 3.0
+            sphi = sp[:, 2] + (U(batch) * 2 - 1) * 0.3
+            su = 2.0 * U(batch)
+            x0 = sp[:, 0] + ahead * torch.cos(sp[:, 2]) - side * torch.sin(sp[:, 2])
+            y0 = sp[:, 1] + ahead * torch.sin(sp[:, 2]) + side * torch.cos(sp[:, 2])
+            steps = torch.arange(P + 1, dtype=torch.float32).unsqueeze(0) * 0.1
+            surr = torch.stack((x0.unsqueeze(1) + su.unsqueeze(1) * torch.cos(sphi).unsqueeze(1) * steps,
+                                y0.unsqueeze(1) + su.unsqueeze(1) * torch.sin(sphi).unsqueeze(1) * steps,
+                                sphi.unsqueeze(1).expand(-1, P + 1), su.unsqueeze(1).expand(-1, P + 1),
+                                torch.zeros(batch, P + 1)), 2).unsqueeze(2).contiguous()
+            model = Veh3dofTrackingDetourModel(pre_horizon=P)
+            return {"obs": model.get_obs(state, ref_points, 0, surr), "done": torch.zeros(batch),
+                    "state": (state, ref_points, 0, surr)}
         return {"obs": obs, "done": torch.zeros(batch), "state": (state, ref_points, 0)}
     raise KeyError(env_id)

@@ -52,13 +52,15 @@ def base_kwargs(env_id, algorithm, obs_dim, act_dim, hidden, act, policy_name, *
 
 def to_ref_data(env_id, data):
     """Oracle input dict -> the dict the reference trainer would hand to local_update."""
-    out = {k: v for k, v in data.items() if k != "state" or env_id != "veh3dof_tracking"}
+    gen_ocp = env_id in ("veh3dof_tracking", "veh3dof_tracking_detour")
+    out = {k: v for k, v in data.items() if k != "state" or not gen_ocp}
     B = data["obs"].shape[0]
-    if env_id == "veh3dof_tracking":
+    if gen_ocp:
         from gops.env.env_gen_ocp.pyth_base import ContextState, State
-        robot, reference, t = data["state"]
+        robot, reference, t = data["state"][:3]
+        surr = data["state"][3].clone() if len(data["state"]) > 3 else None
         out["state"] = State(robot_state=robot.clone(),
-                             context_state=ContextState(reference=reference.clone(), constraint=None, t=t))
+                             context_state=ContextState(reference=reference.clone(), constraint=surr, t=t))
     out.setdefault("act", torch.zeros(B, 1))
     out.setdefault("rew", torch.zeros(B))
     out.setdefault("obs2", data["obs"].clone())
@@ -68,9 +70,11 @@ def to_ref_data(env_id, data):
 def flat_inputs(env_id, data):
     d = {}
     for k, v in data.items():
-        if k == "state" and env_id == "veh3dof_tracking":
+        if k == "state" and env_id in ("veh3dof_tracking", "veh3dof_tracking_detour"):
             d["in_robot_state"], d["in_reference"] = _np(v[0]), _np(v[1])
             d["in_t"] = np.int64(v[2])
+            if len(v) > 3:
+                d["in_surr"] = _np(v[3])
         else:
             d["in_" + k] = _np(v)
     return d
@@ -229,11 +233,30 @@ def run_constrained():
         run_case("cstr_" + algname.lower(), kw, d, [0, 1])
 
 
+def run_detour():
+    """env_gen_ocp veh3dof_tracking_detour (the model of example_train/fhadp/fhadp_mlp_veh3ddetour_serial.py): plain FHADP
+    and the three constrained variants, two consecutive updates each, a batch that mixes feasible and colliding rollouts
+    and samples that arrive done (their state keeps evolving behind the frozen observation, mask_at_done.py:26-40)."""
+    extra = {"FHADP": {}, "FHADPExterior": dict(penalty=2.0, penalty_increase=1.5, penalty_delay=1),
+             "FHADPInterior": dict(penalty=2.0, penalty_increase=1.5, penalty_delay=1),
+             "FHADPLagrangian": dict(multiplier=1.5, multiplier_lr=5e-2, multiplier_delay=1)}
+    for algname, ex in extra.items():
+        kw = base_kwargs("veh3dof_tracking_detour", algname, 50, 2, (64, 64), "elu", "FiniteHorizonPolicy", pre_horizon=10,
+                         gamma=0.97, **ex)
+        d = orc.sample_inputs("veh3dof_tracking_detour", 160, 71, pre_horizon=10)
+        d["done"][::9] = 1.0
+        run_case("detour_" + algname.lower(), kw, d, [0, 1])
+
+
 def main():
     ref_shim.install()
     torch.set_num_threads(4)
+    if "--detour" in sys.argv:
+        run_detour()
+        return
     run_dsac("dsac_idp")
     run_constrained()
+    run_detour()
 
     # K = 20 consecutive updates, LinearLR scheduler, every 5th through the remote-update entry points
     kw = base_kwargs("pyth_idpendulum", "FHADP", 6, 1, (64, 64), "gelu", "FiniteHorizonPolicy", pre_horizon=30,

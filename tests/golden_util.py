@@ -61,6 +61,8 @@ def inputs_from(rec, env_id, dtype=torch.float32):
         data[k[3:]] = torch.from_numpy(np.asarray(v))
     if env_id == "veh3dof_tracking":
         data["state"] = (data.pop("robot_state"), data.pop("reference"), int(data.pop("t")))
+    if env_id == "veh3dof_tracking_detour":
+        data["state"] = (data.pop("robot_state"), data.pop("reference"), int(data.pop("t")), data.pop("surr"))
     if dtype != torch.float32:
         def cast(x):
             if isinstance(x, tuple):
