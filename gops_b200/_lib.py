@@ -49,13 +49,15 @@ class PlanDesc(C.Structure):
         ("veh_pre_horizon", C.c_int32), ("reftraj", RefTraj),
         ("open_loop", C.c_int32),
         ("veh_errcstr", C.c_int32), ("veh_y_error_tol", C.c_float), ("veh_u_error_tol", C.c_float),
+        ("veh_detour", C.c_int32), ("veh_length", C.c_float), ("veh_width", C.c_float),
     ]
 
 
 class Batch(C.Structure):
     _fields_ = [("batch", C.c_int64), ("obs", C.c_void_p), ("done", C.c_void_p), ("state", C.c_void_p),
                 ("ref_points", C.c_void_p), ("path_num", C.c_void_p), ("u_num", C.c_void_p),
-                ("ref_time", C.c_void_p), ("reference", C.c_void_p), ("ref_t", C.c_int32), ("ref_len", C.c_int32)]
+                ("ref_time", C.c_void_p), ("reference", C.c_void_p), ("ref_t", C.c_int32), ("ref_len", C.c_int32),
+                ("surr", C.c_void_p), ("surr_len", C.c_int32)]
 
 
 # name -> (restype, argtypes); the parity test `test_abi_symbols` checks these against the header

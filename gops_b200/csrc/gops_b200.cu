@@ -161,6 +161,9 @@ StepFn step_fn_lq();
 LwFn lw_fn_idp(int which);              // layer-wise path (wide nets): 0 init, 1 forward step, 2 reverse step
 LwFn lw_fn_lq(int which);
 LwFn lw_fn_vehtrack(int which);
+LwFn lw_fn_vehtrack_detour(int which);    // veh3dof_tracking_detour: 1 forward step, 2 reverse step (lw_detour.cuh)
+void lw_launch_scalars_detour(const KParams& p, const float* vacc, const float* cacc, const float* dn_last, float* scalars,
+                              cudaStream_t st);
 RolloutFn rollout_fn_tc2_idp(int alg);  // pipelined tcgen05 kernel: two independent 128-thread groups per CTA (rollout_tc2.cuh)
 RolloutFn rollout_fn_tc2_lq(int alg);
 }  // namespace gops
@@ -232,7 +235,7 @@ struct gops_b200_plan {
   gops_b200_mlpnet* lw_net = nullptr;
   long long lw_cap = 0;
   float *lw_S = nullptr, *lw_Dn = nullptr, *lw_X = nullptr, *lw_Z = nullptr, *lw_Zb = nullptr, *lw_lam = nullptr,
-        *lw_vacc = nullptr, *lw_dX = nullptr, *lw_sp = nullptr;
+        *lw_vacc = nullptr, *lw_dX = nullptr, *lw_sp = nullptr, *lw_cacc = nullptr, *lw_xcar = nullptr;
   std::vector<unsigned char> lw_key;      // the call the captured graph belongs to (KParams bytes + buffers + stream)
   int lw_key_hits = 0;
   cudaGraphExec_t lw_exec = nullptr;
@@ -392,7 +395,7 @@ int launch_pack(const float* flat, const NetL& L, int hid, float* blob, cudaStre
 // Wide nets (hidden 256), FHADP: the layer-wise tcgen05 path.  AUTO takes it wherever it is built; MMA keeps the fused
 // FP32-FFMA kernel (A/B baseline).
 bool rollout_use_layerwise(const gops_b200_plan* pl, int alg) {
-  if (pl->desc.open_loop) return alg == ALG_FHADP;
+  if (pl->desc.open_loop || pl->desc.veh_detour) return alg == ALG_FHADP;
   if (pl->kp.hid <= 64 || alg != ALG_FHADP || pl->kp.horizon > 128) return false;
   if (!lw_fn(pl->desc.model, 0)) return false;
   int path = pl->path;
@@ -464,7 +467,8 @@ int launch_rollout_layerwise(gops_b200_plan* pl, const gops_b200_batch* b, const
   if (B > pl->lw_cap || !pl->lw_net) {
     if (pl->lw_net) gops_b200_mlpnet_destroy(pl->lw_net);
     pl->lw_net = nullptr;
-    float** bufs[] = {&pl->lw_S, &pl->lw_Dn, &pl->lw_X, &pl->lw_Z, &pl->lw_Zb, &pl->lw_lam, &pl->lw_vacc, &pl->lw_dX, &pl->lw_sp};
+    float** bufs[] = {&pl->lw_S, &pl->lw_Dn, &pl->lw_X, &pl->lw_Z, &pl->lw_Zb, &pl->lw_lam, &pl->lw_vacc, &pl->lw_dX, &pl->lw_sp,
+                      &pl->lw_cacc, &pl->lw_xcar};
     for (float** q : bufs) { cudaFree(*q); *q = nullptr; }
     const long long cap = (B + 127) / 128 * 128;
     const int32_t sizes[4] = {in, kp.hid, kp.hid, A};
@@ -481,6 +485,10 @@ int launch_rollout_layerwise(gops_b200_plan* pl, const gops_b200_batch* b, const
     CUDA_OK(cudaMalloc(&pl->lw_vacc, sizeof(float) * (size_t)cap));
     CUDA_OK(cudaMalloc(&pl->lw_dX, sizeof(float) * (size_t)cap * ldx));
     CUDA_OK(cudaMalloc(&pl->lw_sp, sizeof(float) * 2 * 256));
+    if (pl->desc.veh_detour) {
+      CUDA_OK(cudaMalloc(&pl->lw_cacc, sizeof(float) * 3 * (size_t)cap));
+      CUDA_OK(cudaMalloc(&pl->lw_xcar, sizeof(float) * (size_t)cap * ldx));
+    }
     pl->lw_cap = cap;
   }
   const long long cap = pl->lw_cap;
@@ -488,9 +496,13 @@ int launch_rollout_layerwise(gops_b200_plan* pl, const gops_b200_batch* b, const
   kp.batch = B;
   kp.obs = b->obs; kp.done = b->done; kp.state = b->state; kp.reference = b->reference;
   kp.ref_t = b->ref_t; kp.ref_len = b->ref_len;
-  LwFn f_init = lw_fn(pl->desc.model, 0), f_step = lw_fn(pl->desc.model, 1), f_rev = lw_fn(pl->desc.model, 2);
+  kp.surr = b->surr; kp.surr_len = b->surr_len;
+  const bool detour = pl->desc.veh_detour != 0;
+  LwFn f_init = lw_fn(pl->desc.model, 0), f_step = detour ? lw_fn_vehtrack_detour(1) : lw_fn(pl->desc.model, 1),
+       f_rev = detour ? lw_fn_vehtrack_detour(2) : lw_fn(pl->desc.model, 2);
   LwArgs a;
   memset(&a, 0, sizeof(a));
+  a.cacc = pl->lw_cacc; a.xcar = pl->lw_xcar;
   a.ldx = ldx; a.act_dim = A; a.bstride = cap; a.zs_k = cap * A; a.zs_b = A;
   a.S = pl->lw_S; a.Dn = pl->lw_Dn; a.X = pl->lw_X; a.Z = pl->lw_Z; a.Zb = pl->lw_Zb; a.lam = pl->lw_lam; a.vacc = pl->lw_vacc;
   // S / Dn are indexed with the real batch as the row count
@@ -502,6 +514,10 @@ int launch_rollout_layerwise(gops_b200_plan* pl, const gops_b200_batch* b, const
   if (gops_b200_mlpnet_pack(pl->lw_net, policy_params, st)) return 1;
   f_init<<<grid, 128, 0, st>>>(kp, a);
   ++g_launches;
+  if (detour) {
+    CUDA_OK(cudaMemsetAsync(pl->lw_cacc, 0, sizeof(float) * 3 * (size_t)B, st));
+    CUDA_OK(cudaMemsetAsync(pl->lw_xcar, 0, sizeof(float) * (size_t)B * ldx, st));
+  }
   const int sub = pl->desc.model == GOPS_MODEL_VEH3DOF_TRACKING ? LW_SUB : 1;
   const unsigned grid_step = (unsigned)((B * sub + 127) / 128);
   for (int k = 0; k < H; ++k) {
@@ -522,9 +538,14 @@ int launch_rollout_layerwise(gops_b200_plan* pl, const gops_b200_batch* b, const
   }
   if (gops_b200_mlpnet_wgrad_slots(pl->lw_net, 0, H, B, pl->lw_X, ldx, cap, pl->lw_Zb, A, cap, grad_out, 0, st)) return 1;
   const int nb = 64;
-  lw_scalars_kernel<<<nb, 256, 0, st>>>(pl->lw_vacc, pl->lw_Dn + (size_t)H * B, B, kp.inv_B, pl->lw_sp);
-  lw_scalars_final_kernel<<<1, 32, 0, st>>>(pl->lw_sp, nb, scalars_out);
-  g_launches += 2;
+  if (detour) {
+    lw_launch_scalars_detour(kp, pl->lw_vacc, pl->lw_cacc, pl->lw_Dn + (size_t)H * B, scalars_out, st);
+    g_launches += 1;
+  } else {
+    lw_scalars_kernel<<<nb, 256, 0, st>>>(pl->lw_vacc, pl->lw_Dn + (size_t)H * B, B, kp.inv_B, pl->lw_sp);
+    lw_scalars_final_kernel<<<1, 32, 0, st>>>(pl->lw_sp, nb, scalars_out);
+    g_launches += 2;
+  }
   CUDA_OK_L(cudaGetLastError(), "layer-wise rollout");
   return 0;
   };
@@ -760,8 +781,16 @@ int gops_b200_plan_create(const gops_b200_plan_desc* d, gops_b200_plan** out) {
   }
   if (d->model == GOPS_MODEL_VEH3DOFCONTI || d->model == GOPS_MODEL_VEH3DOF_TRACKING) {
     if (d->veh_pre_horizon < 1) { delete pl; return fail("veh_pre_horizon must be >= 1"); }
-    obs_dim_model = 6 + 4 * d->veh_pre_horizon;
+    obs_dim_model = 6 + 4 * d->veh_pre_horizon + (d->veh_detour ? 4 : 0);
     if (act_dim != 2) { delete pl; return fail("vehicle models have 2 actions"); }
+    if (d->veh_detour) {
+      if (d->model != GOPS_MODEL_VEH3DOF_TRACKING || d->alg != GOPS_ALG_FHADP || d->open_loop) {
+        delete pl;
+        return fail("veh3dof_tracking_detour is built for FHADP and its constrained variants (closed-loop policy) only");
+      }
+      if (d->obs_scaling) { delete pl; return fail("veh3dof_tracking_detour: ScaleObservation is not built"); }
+      if (!(d->veh_length > d->veh_width) || !(d->veh_width > 0.f)) { delete pl; return fail("veh3dof_tracking_detour: need veh_length > veh_width > 0"); }
+    }
     if (d->clip_obs) {
       // the vehicle models declare +-inf observation bounds (pyth_veh3dofconti_model.py:79-88): identity clip
     }
@@ -830,6 +859,9 @@ int gops_b200_plan_create(const gops_b200_plan_desc* d, gops_b200_plan** out) {
   kp.cstr_mode = 0; kp.cstr_coef = 1.f;
   kp.cstr_y_tol = d->veh_y_error_tol; kp.cstr_u_tol = d->veh_u_error_tol;
   kp.veh_P = d->veh_pre_horizon;
+  kp.veh_detour = d->veh_detour ? 1 : 0;
+  kp.veh_dc = (float)(((double)d->veh_length - (double)d->veh_width) / 2.0);   // d = (veh_length - veh_width) / 2
+  kp.veh_2r = (float)(2.0 * (0.5 * (double)d->veh_width));                       // 2 * r, r = 0.5 * veh_width
   kp.veh_Pdt = (float)((double)d->veh_pre_horizon * 0.1);   // self.pre_horizon * self.dt
 
   cudaError_t e = cudaGetDevice(&pl->device);
@@ -931,8 +963,11 @@ int gops_b200_plan_last_path(const gops_b200_plan* pl) { return pl ? pl->last_pa
 int gops_b200_plan_set_constraint(gops_b200_plan* pl, int mode, float coef) {
   if (!pl) return fail("null plan");
   if (mode < 0 || mode > 3) return fail("unknown constraint mode");
-  if (mode != 0 && !(pl->desc.model == GOPS_MODEL_VEH3DOFCONTI && pl->desc.veh_errcstr && pl->desc.alg == GOPS_ALG_FHADP))
-    return fail("constrained FHADP variants are built for pyth_veh3dofconti_errcstr (info['constraint'] provider) only");
+  const bool provider = (pl->desc.model == GOPS_MODEL_VEH3DOFCONTI && pl->desc.veh_errcstr) ||
+                        (pl->desc.model == GOPS_MODEL_VEH3DOF_TRACKING && pl->desc.veh_detour);
+  if (mode != 0 && !(provider && pl->desc.alg == GOPS_ALG_FHADP))
+    return fail("constrained FHADP variants are built for the info['constraint'] providers pyth_veh3dofconti_errcstr and "
+                "veh3dof_tracking_detour only");
   if (mode != 0 && !(coef > 0.f)) return fail("constraint coefficient must be positive");
   pl->kp.cstr_mode = mode;
   pl->kp.cstr_coef = coef;
@@ -954,7 +989,8 @@ int gops_b200_plan_destroy(gops_b200_plan* pl) {
   if (pl->lw_cap_stream) cudaStreamDestroy(pl->lw_cap_stream);
   if (pl->lw_net) gops_b200_mlpnet_destroy(pl->lw_net);
   {
-    float* lw[] = {pl->lw_S, pl->lw_Dn, pl->lw_X, pl->lw_Z, pl->lw_Zb, pl->lw_lam, pl->lw_vacc, pl->lw_dX, pl->lw_sp};
+    float* lw[] = {pl->lw_S, pl->lw_Dn, pl->lw_X, pl->lw_Z, pl->lw_Zb, pl->lw_lam, pl->lw_vacc, pl->lw_dX, pl->lw_sp, pl->lw_cacc,
+                   pl->lw_xcar};
     for (float* q : lw) cudaFree(q);
     (void)cudaGetLastError();
   }
@@ -996,6 +1032,8 @@ int gops_b200_rollout_grad(gops_b200_plan* pl, const gops_b200_batch* b, const f
       if (!b->state || !b->reference) return fail("veh3dof_tracking needs state (robot_state) and reference");
       if (b->ref_t < 0 || b->ref_t + pl->kp.horizon + pl->kp.veh_P + 1 > b->ref_len)
         return fail("veh3dof_tracking: reference too short for t + horizon + pre_horizon + 1 points");
+      if (pl->desc.veh_detour && (!b->surr || b->ref_t + pl->kp.horizon + 1 > b->surr_len))
+        return fail("veh3dof_tracking_detour needs the surrounding-vehicle predictions (ContextState.constraint), t + horizon + 1 points");
     }
     pl->kp.inv_B = inv_batch_global;
     return launch_rollout_layerwise(pl, b, policy_params, st, grad_out, scalars_out);
@@ -1209,6 +1247,9 @@ int gops_b200_model_step(gops_b200_plan* pl, const gops_b200_batch* b, const flo
   ENTRY("float* next_ref_time, void* stream) {");
   if (!pl || !b || !action || !next_obs || !reward || !next_done) return fail("null argument");
   if (b->batch <= 0 || !b->obs || !b->done) return fail("bad batch");
+  if (pl->desc.veh_detour)
+    return fail("model_step: stepping veh3dof_tracking_detour is not built (the model runs inside the fused FHADP / "
+                "FHADPExterior / FHADPLagrangian / FHADPInterior update)");
   DevGuard dg(pl->device);
   KParams& kp = pl->kp;
   kp.batch = b->batch; kp.obs = b->obs; kp.done = b->done;

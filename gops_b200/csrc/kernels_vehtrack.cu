@@ -1,6 +1,7 @@
 // Instantiations of the fused rollout kernel for ModelVehTrack (own translation unit: parallel build).
 #include "kernel.cuh"
 #include "lw_rollout.cuh"
+#include "lw_detour.cuh"
 
 namespace gops {
 
@@ -32,6 +33,14 @@ LwFn lw_fn_vehtrack(int which) {   // layer-wise path of the wide nets: init / f
     case 1: return lw_step_kernel<ModelVehTrack>;
     default: return lw_reverse_kernel<ModelVehTrack>;
   }
+}
+
+LwFn lw_fn_vehtrack_detour(int which) {   // veh3dof_tracking_detour: forward step / reverse step (init is shared)
+  return which == 1 ? lw_step_detour_kernel : lw_reverse_detour_kernel;
+}
+void lw_launch_scalars_detour(const KParams& p, const float* vacc, const float* cacc, const float* dn_last, float* scalars,
+                              cudaStream_t st) {
+  lw_scalars_detour_kernel<<<1, 256, 0, st>>>(p, vacc, cacc, dn_last, scalars);
 }
 
 }  // namespace gops

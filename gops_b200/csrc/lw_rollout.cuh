@@ -28,6 +28,8 @@ struct LwArgs {
   float* lam;              // [NS][B] adjoint of the state entering the next reverse step
   const float* dX;         // [bstride][ldx] input gradient of step k + 1 (reverse) or nullptr
   float* vacc;             // [B] discounted reward sums
+  float* cacc;             // detour: [3][B] discounted constraint sums (exterior or Lagrangian | interior log) and the infeasible flag
+  float* xcar;             // detour: [B][ldx] adjoint handed back by frozen copies of an observation row
 };
 
 // copy the caller's batch into step 0: X_0 = [obs | time 1], S_0, Dn_0

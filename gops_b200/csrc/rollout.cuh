@@ -88,6 +88,11 @@ struct KParams {
   // 2 Lagrangian, 3 interior point; cstr_coef = penalty / multiplier; tolerances of the error-constraint vehicle model
   int cstr_mode;
   float cstr_coef, cstr_y_tol, cstr_u_tol;
+  // env_gen_ocp veh3dof_tracking_detour (lw_detour.cuh): surrounding-vehicle predictions [B][surr_len][1][5] (x, y, phi, u,
+  // delta), circle offset d = (length - width) / 2 and 2 r = width of the bicircle collision model
+  int veh_detour, surr_len;
+  const float* surr;
+  float veh_dc, veh_2r;
   // wrappers
   int action_scale, clip_action, clip_obs, mask_at_done, reward_shaping;
   float reward_shift, reward_scale;

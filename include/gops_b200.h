@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define GOPS_B200_ABI_VERSION 3   /* 2: plan_desc.open_loop, mlpnet_*, plan_set_path, launch_count; 3: peer_* */
+#define GOPS_B200_ABI_VERSION 4   /* 2: plan_desc.open_loop, mlpnet_*, plan_set_path, launch_count; 3: peer_*; 4: veh_detour, batch.surr */
 #define GOPS_B200_MAX_ACT 4   /* action dims supported by the fused kernels            */
 #define GOPS_B200_MAX_LQ_N 8  /* pyth_lq state dim upper bound (configs ship n <= 6)   */
 
@@ -113,6 +113,11 @@ typedef struct gops_b200_plan_desc {
    * returns info["constraint"] = (|y_err| - y_error_tol, |u_err| - u_error_tol) of the incoming observation. */
   int32_t veh_errcstr;
   float veh_y_error_tol, veh_u_error_tol;
+  /* env_gen_ocp veh3dof_tracking_detour (env_gen_ocp/env_model/veh3dof_tracking_detour_model.py:13-176): model must be
+   * GOPS_MODEL_VEH3DOF_TRACKING; obs_dim = 6 + 4 P + 4 (one surrounding vehicle), info["constraint"] = the bicircle
+   * collision constraint of the incoming state.  FHADP and its constrained variants, on the layer-wise tcgen05 path. */
+  int32_t veh_detour;
+  float veh_length, veh_width;
 } gops_b200_plan_desc;
 
 /* Per-call inputs (one replay batch shard).  Unused pointers are NULL. */
@@ -128,6 +133,8 @@ typedef struct gops_b200_batch {
   const float* reference;    /* [batch][ref_len][4] veh3dof_tracking ContextState.reference      */
   int32_t ref_t;             /* veh3dof_tracking ContextState.t (shared python int)              */
   int32_t ref_len;           /* veh3dof_tracking: points per sample in `reference`               */
+  const float* surr;         /* [batch][surr_len][1][5] veh3dof_tracking_detour ContextState.constraint (x, y, phi, u, delta) */
+  int32_t surr_len;          /* predictions per sample in `surr` (>= ref_t + horizon + 1)        */
 } gops_b200_batch;
 
 typedef struct gops_b200_plan gops_b200_plan;

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(handle, n), f"{n} declared in include/gops_b200.h but not exported"
     assert sorted(_lib.PROTOTYPES) == names, "ctypes prototypes and header are out of sync"
-    assert _lib.lib().gops_b200_version() == 3
+    assert _lib.lib().gops_b200_version() == 4
 
 
 def test_error_reporting_without_gpu_or_with_bad_args():
