@@ -126,3 +126,22 @@ def sample_veh3dof_tracking(batch, pre_horizon, device, seed=0, gen=None, traj=N
     _, _, _, ref, state = _vehicle_draw(batch, 2 * pre_horizon + 1, device, g, traj or RefTrajectory())
     return {"obs": ego_observation(state, ref[:, :pre_horizon + 1]), "done": torch.zeros(batch, device=device),
             "state": State(robot_state=state, context_state=ContextState(reference=ref.contiguous(), t=0))}
+
+
+def sample_veh3dof_tracking_detour(batch, pre_horizon, device, seed=0, gen=None, traj=None) -> Dict[str, torch.Tensor]:
+    """veh3dof_tracking plus the surrounding vehicle of the detour task: a STATIC vehicle 20 m ahead of the reference's
+    first point and 1 m to its left (env_gen_ocp/context/ref_traj_with_static_obstacle.py:76-97), predicted over
+    pre_horizon + 1 points as [x, y, phi, u, delta] (:119-127) in ContextState.constraint [B, P + 1, 1, 5]; the
+    observation gets its ego-frame pose and speed appended (env_model/veh3dof_tracking_detour_model.py:62-76)."""
+    from gops_b200.env.env_gen_ocp.pyth_base import ContextState, State
+    g = gen or _gen(device, seed)
+    _, _, _, ref, state = _vehicle_draw(batch, 2 * pre_horizon + 1, device, g, traj or RefTrajectory())
+    surr0 = torch.stack((ref[:, 0, 0] + 20.0, ref[:, 0, 1] + 1.0, torch.zeros(batch, device=device),
+                         torch.zeros(batch, device=device), torch.zeros(batch, device=device)), 1)
+    surr = surr0[:, None, None, :].expand(batch, pre_horizon + 1, 1, 5).contiguous()
+    sx, sy = surr0[:, 0:1] - state[:, 0:1], surr0[:, 1:2] - state[:, 1:2]
+    c, s = torch.cos(state[:, 2:3]), torch.sin(state[:, 2:3])
+    surr_obs = torch.cat((sx * c + sy * s, -sx * s + sy * c, wrap_angle(surr0[:, 2:3] - state[:, 2:3]), surr0[:, 3:4]), 1)
+    obs = torch.cat((ego_observation(state, ref[:, :pre_horizon + 1]), surr_obs), 1)
+    return {"obs": obs, "done": torch.zeros(batch, device=device),
+            "state": State(robot_state=state, context_state=ContextState(reference=ref.contiguous(), constraint=surr, t=0))}

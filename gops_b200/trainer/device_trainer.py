@@ -34,6 +34,8 @@ class DeviceStateSampler:
             self._draw = lambda b: ds.sample_veh3dofconti(b, P, self.device, gen=self.gen)
         elif env_id == "veh3dof_tracking":
             self._draw = lambda b: ds.sample_veh3dof_tracking(b, P, self.device, gen=self.gen)
+        elif env_id == "veh3dof_tracking_detour":
+            self._draw = lambda b: ds.sample_veh3dof_tracking_detour(b, P, self.device, gen=self.gen)
         else:
             raise NotImplementedError(f"DeviceStateSampler: no on-device initial-state law for {env_id}")
 

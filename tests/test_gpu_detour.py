@@ -124,3 +124,22 @@ def test_stepping_the_model_is_reported_as_not_built():
     d = _gpu_data(orc.sample_inputs("veh3dof_tracking_detour", 4, seed=1, pre_horizon=10))
     with pytest.raises(RuntimeError, match="not built"):
         env.forward(d["obs"].cuda(), torch.zeros(4, 2, device="cuda"), d["done"].cuda(), {"state": d["state"]})
+
+
+def test_device_sampler_feeds_the_interior_point_update():
+    """N2 meets N3: batches drawn on the device (static obstacle 20 m ahead, the reference's detour context) through the
+    example's configuration -- FHADPInterior, [256, 256] elu, pre_horizon 30 -- a few updates, finite and improving."""
+    from gops_b200.trainer.device_trainer import DeviceStateSampler
+    torch.manual_seed(0)
+    P = 30
+    alg = _alg("FHADPInterior", hidden=256, P=P, gamma=1.0, penalty=1.0, penalty_increase=1.1, penalty_delay=100,
+               policy_learning_rate=3e-5)
+    sampler = DeviceStateSampler("veh3dof_tracking_detour", "cuda", seed=5, pre_horizon=P)
+    data = sampler.sample(2048)
+    assert data["obs"].shape == (2048, 6 + 4 * P + 4) and data["state"].context_state.constraint.shape == (2048, P + 1, 1, 5)
+    losses = []
+    for it in range(6):
+        tb = alg.local_update(data, it)
+        losses.append(tb["Loss/Actor loss-RL iter"])
+        assert np.isfinite(losses[-1]) and 0.0 <= tb["Loss/Feasible ratio-RL iter"] <= 1.0
+    assert losses[-1] < losses[0]
