@@ -784,6 +784,7 @@ int gops_b200_plan_create(const gops_b200_plan_desc* d, gops_b200_plan** out) {
     obs_dim_model = 6 + 4 * d->veh_pre_horizon + (d->veh_detour ? 4 : 0);
     if (act_dim != 2) { delete pl; return fail("vehicle models have 2 actions"); }
     if (d->veh_detour) {
+      if (d->veh_detour != 1 && d->veh_detour != 2) { delete pl; return fail("veh_detour: 1 (detour) or 2 (surrcstr)"); }
       if (d->model != GOPS_MODEL_VEH3DOF_TRACKING || d->alg != GOPS_ALG_FHADP || d->open_loop) {
         delete pl;
         return fail("veh3dof_tracking_detour is built for FHADP and its constrained variants (closed-loop policy) only");
@@ -862,6 +863,16 @@ int gops_b200_plan_create(const gops_b200_plan_desc* d, gops_b200_plan** out) {
   kp.veh_detour = d->veh_detour ? 1 : 0;
   kp.veh_dc = (float)(((double)d->veh_length - (double)d->veh_width) / 2.0);   // d = (veh_length - veh_width) / 2
   kp.veh_2r = (float)(2.0 * (0.5 * (double)d->veh_width));                       // 2 * r, r = 0.5 * veh_width
+  {
+    // veh3dof_tracking_detour_model.py:133-163 (1) / veh3dof_tracking_surrcstr_model.py:88,138-171 (2)
+    const float det[7] = {10.f, 10.f, 500.f, 5.f, 1000.f, 1000.f, 50.f}, sur[7] = {0.04f, 0.04f, 0.02f, 0.02f, 0.01f, 0.01f, 0.01f};
+    const bool sc = d->veh_detour == 2;
+    for (int i = 0; i < 7; ++i) kp.veh_rc[i] = sc ? sur[i] : det[i];
+    kp.veh_rscale = sc ? 1.f : 0.01f;
+    kp.veh_roff = sc ? 0.f : 2.f;
+    kp.veh_ydone = sc ? 2.f : 3.f;
+    if (sc) kp.veh_2r = (float)(2.0 * (sqrt(2.0) / 2.0 * (double)d->veh_width));   // r = np.sqrt(2) / 2 * veh_width
+  }
   kp.veh_Pdt = (float)((double)d->veh_pre_horizon * 0.1);   // self.pre_horizon * self.dt
 
   cudaError_t e = cudaGetDevice(&pl->device);

@@ -1,5 +1,6 @@
-// env_gen_ocp veh3dof_tracking_detour on the layer-wise path (lw_rollout.cuh): the tracking model plus ONE surrounding
-// vehicle (reference: gops/env/env_gen_ocp/env_model/veh3dof_tracking_detour_model.py:13-176, EnvModel.forward
+// env_gen_ocp veh3dof_tracking_detour / veh3dof_tracking_surrcstr on the layer-wise path (lw_rollout.cuh): the tracking
+// model plus ONE surrounding vehicle (reference: gops/env/env_gen_ocp/env_model/veh3dof_tracking_detour_model.py:13-176,
+// veh3dof_tracking_surrcstr_model.py:13-181 -- same structure, other circle radius / reward / bound; EnvModel.forward
 // env_model/pyth_base_model.py:109-119, MaskAtDone wrapper/mask_at_done.py:26-40) and the constrained FHADP variants on
 // it (fhadp_exterior.py:55-70, fhadp_lagrangian.py:59-71, fhadp_interior.py:55-84).
 //
@@ -81,8 +82,9 @@ __global__ void lw_step_detour_kernel(const __grid_constant__ KParams p, const _
       w.k0 = p.ref_t + k;
       w.get(0, q);
       const float ex = st[0] - q[0], ey = st[1] - q[1], ep = angle_normalize(st[2] - q[2]), eu = st[3] - q[3];
-      r = -0.01f * (10.f * (ex * ex) + 10.f * (ey * ey) + 500.f * (ep * ep) + 5.f * (eu * eu) + 1000.f * (st[5] * st[5]) +
-                    1000.f * (act[0] * act[0]) + 50.f * (act[1] * act[1])) + 2.f;
+      r = -p.veh_rscale * (p.veh_rc[0] * (ex * ex) + p.veh_rc[1] * (ey * ey) + p.veh_rc[2] * (ep * ep) + p.veh_rc[3] * (eu * eu) +
+                           p.veh_rc[4] * (st[5] * st[5]) + p.veh_rc[5] * (act[0] * act[0]) + p.veh_rc[6] * (act[1] * act[1])) +
+          p.veh_roff;
     }
   }
   const VehC vc = veh_const();
@@ -111,7 +113,7 @@ __global__ void lw_step_detour_kernel(const __grid_constant__ KParams p, const _
   }
   if (sub != 0) return;
   w.get(0, q);
-  const bool term = (fabsf(st[0] - q[0]) > 5.f) || (fabsf(st[1] - q[1]) > 3.f) ||
+  const bool term = (fabsf(st[0] - q[0]) > 5.f) || (fabsf(st[1] - q[1]) > p.veh_ydone) ||
                     (fabsf(angle_normalize(st[2] - q[2])) > 3.14159265358979323846f);
   if (p.pol.time_input) xn[obs_dim] = (float)(k + 2);
   for (int f = obs_dim + p.pol.time_input; f < a.ldx; ++f) xn[f] = 0.f;
@@ -190,18 +192,19 @@ __global__ void lw_reverse_detour_kernel(const __grid_constant__ KParams p, cons
   veh_step_bwd(vc, st, act, lam, abar);          // the state chain runs through done samples too
   if (!frozen) {                                 // reward of step k (masked once done)
     const float rho = -p.gpow[k] * p.inv_B * (p.reward_shaping ? p.reward_scale : 1.f);
-    abar[0] += rho * (-20.f * act[0]);
-    abar[1] += rho * (-1.f * act[1]);
+    const float r2 = -2.f * p.veh_rscale;
+    abar[0] += rho * (r2 * p.veh_rc[5] * act[0]);
+    abar[1] += rho * (r2 * p.veh_rc[6] * act[1]);
     RefWindow<2, 1> w;
     w.base = p.reference + (size_t)b * p.ref_len * 4;
     w.k0 = p.ref_t + k;
     float q[4];
     w.get(0, q);
-    lam[0] += rho * (-0.2f * (st[0] - q[0]));
-    lam[1] += rho * (-0.2f * (st[1] - q[1]));
-    lam[2] += rho * (-10.f * angle_normalize(st[2] - q[2]));
-    lam[3] += rho * (-0.1f * (st[3] - q[3]));
-    lam[5] += rho * (-20.f * st[5]);
+    lam[0] += rho * (r2 * p.veh_rc[0] * (st[0] - q[0]));
+    lam[1] += rho * (r2 * p.veh_rc[1] * (st[1] - q[1]));
+    lam[2] += rho * (r2 * p.veh_rc[2] * angle_normalize(st[2] - q[2]));
+    lam[3] += rho * (r2 * p.veh_rc[3] * (st[3] - q[3]));
+    lam[5] += rho * (r2 * p.veh_rc[4] * st[5]);
   }
   if (p.cstr_mode != 0) {                        // constraint of the incoming state of step k
     float gc[3];

@@ -93,6 +93,8 @@ struct KParams {
   int veh_detour, surr_len;
   const float* surr;
   float veh_dc, veh_2r;
+  // reward r = -veh_rscale * sum_i veh_rc[i] * (ex, ey, ephi, eu, w, steer, a_x)_i^2 + veh_roff; lateral termination bound
+  float veh_rscale, veh_roff, veh_rc[7], veh_ydone;
   // wrappers
   int action_scale, clip_action, clip_obs, mask_at_done, reward_shaping;
   float reward_shift, reward_scale;

@@ -18,6 +18,8 @@ from gops_b200.env.env_ocp.env_model.pyth_base_model import PythBaseModel
 
 
 class Veh3DoFTrackingDetourModel(Veh3DoFTrackingModel):
+    VARIANT = 1          # plan_desc.veh_detour: 1 detour, 2 surrcstr (veh3dof_tracking_surrcstr_model.py)
+
     def __init__(self, pre_horizon: int = 10, max_steer: float = math.pi / 6, device: Union[torch.device, str, None] = None,
                  veh_length: float = 4.8, veh_width: float = 2.0, **kwargs):
         self.pre_horizon = pre_horizon
@@ -27,7 +29,7 @@ class Veh3DoFTrackingDetourModel(Veh3DoFTrackingModel):
 
     def fill_plan_desc(self, desc):
         super().fill_plan_desc(desc)
-        desc.veh_detour = 1
+        desc.veh_detour = self.VARIANT
         desc.veh_length, desc.veh_width = self.veh_length, self.veh_width
 
     def fill_batch(self, batch, info, f32, keep):

@@ -113,9 +113,10 @@ typedef struct gops_b200_plan_desc {
    * returns info["constraint"] = (|y_err| - y_error_tol, |u_err| - u_error_tol) of the incoming observation. */
   int32_t veh_errcstr;
   float veh_y_error_tol, veh_u_error_tol;
-  /* env_gen_ocp veh3dof_tracking_detour (env_gen_ocp/env_model/veh3dof_tracking_detour_model.py:13-176): model must be
-   * GOPS_MODEL_VEH3DOF_TRACKING; obs_dim = 6 + 4 P + 4 (one surrounding vehicle), info["constraint"] = the bicircle
-   * collision constraint of the incoming state.  FHADP and its constrained variants, on the layer-wise tcgen05 path. */
+  /* env_gen_ocp veh3dof_tracking_detour (1; env_gen_ocp/env_model/veh3dof_tracking_detour_model.py:13-176) or
+   * veh3dof_tracking_surrcstr (2; veh3dof_tracking_surrcstr_model.py:13-181): model must be GOPS_MODEL_VEH3DOF_TRACKING;
+   * obs_dim = 6 + 4 P + 4 (one surrounding vehicle), info["constraint"] = the bicircle collision constraint of the
+   * incoming state.  FHADP and its constrained variants, on the layer-wise tcgen05 path. */
   int32_t veh_detour;
   float veh_length, veh_width;
 } gops_b200_plan_desc;

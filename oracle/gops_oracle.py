@@ -413,8 +413,15 @@ class Veh3dofTrackingDetourModel(BaseModel):
         so = torch.stack((sx, sy, sphi, c[..., 3]), 2).reshape(base.shape[0], -1)
         return torch.cat((base, so), 1)
 
+    y_done, radius_factor = 3, 0.5
+
+    def reward(self, robot, r, steer, a_x):
+        return -0.01 * (10.0 * (robot[:, 0] - r[:, 0]) ** 2 + 10.0 * (robot[:, 1] - r[:, 1]) ** 2
+                        + 500 * angle_normalize(robot[:, 2] - r[:, 2]) ** 2 + 5.0 * (robot[:, 3] - r[:, 3]) ** 2
+                        + 1000 * robot[:, 5] ** 2 + 1000 * steer ** 2 + 50 * a_x ** 2) + 2.0
+
     def get_constraint(self, robot, surr_t):
-        d, r = (self.veh_length - self.veh_width) / 2, 0.5 * self.veh_width
+        d, r = (self.veh_length - self.veh_width) / 2, self.radius_factor * self.veh_width
         x, y, phi = robot[:, 0:1], robot[:, 1:2], robot[:, 2:3]
         ego = [torch.cat((x + s * d * torch.cos(phi), y + s * d * torch.sin(phi)), 1) for s in (1.0, -1.0)]
         sx, sy, sphi = surr_t[..., 0], surr_t[..., 1], surr_t[..., 2]
@@ -432,14 +439,23 @@ class Veh3dofTrackingDetourModel(BaseModel):
         nobs = self.get_obs(nrobot, reference, t + 1, surr)
         r = reference[:, t]
         steer, a_x = action[:, 0], action[:, 1]
-        reward = -0.01 * (10.0 * (robot[:, 0] - r[:, 0]) ** 2 + 10.0 * (robot[:, 1] - r[:, 1]) ** 2
-                          + 500 * angle_normalize(robot[:, 2] - r[:, 2]) ** 2 + 5.0 * (robot[:, 3] - r[:, 3]) ** 2
-                          + 1000 * robot[:, 5] ** 2 + 1000 * steer ** 2 + 50 * a_x ** 2) + 2.0
+        reward = self.reward(robot, r, steer, a_x)
         rn = reference[:, t + 1]
-        isdone = ((torch.abs(nrobot[:, 0] - rn[:, 0]) > 5) | (torch.abs(nrobot[:, 1] - rn[:, 1]) > 3)
+        isdone = ((torch.abs(nrobot[:, 0] - rn[:, 0]) > 5) | (torch.abs(nrobot[:, 1] - rn[:, 1]) > self.y_done)
                   | (torch.abs(angle_normalize(nrobot[:, 2] - rn[:, 2])) > math.pi))
         return nobs, reward, isdone, {"state": (nrobot, reference, t + 1, surr),
                                       "constraint": self.get_constraint(robot, surr[:, t])}
+
+
+class Veh3dofTrackingSurrCstrModel(Veh3dofTrackingDetourModel):
+    """env_gen_ocp/env_model/veh3dof_tracking_surrcstr_model.py:13-181: the detour model's structure with the tracking
+    model's reward (:138-158) and lateral bound (:160-171) and circle radius sqrt(2)/2 * veh_width (:88)."""
+    y_done, radius_factor = 2, math.sqrt(2) / 2
+
+    def reward(self, robot, r, steer, a_x):
+        return -(0.04 * (robot[:, 0] - r[:, 0]) ** 2 + 0.04 * (robot[:, 1] - r[:, 1]) ** 2
+                 + 0.02 * angle_normalize(robot[:, 2] - r[:, 2]) ** 2 + 0.02 * (robot[:, 3] - r[:, 3]) ** 2
+                 + 0.01 * robot[:, 5] ** 2 + 0.01 * steer ** 2 + 0.01 * a_x ** 2)
 
 
 MODEL_REGISTRY = {
@@ -448,7 +464,8 @@ MODEL_REGISTRY = {
     "pyth_veh3dofconti": Veh3dofContiModel,
     "veh3dof_tracking": Veh3dofTrackingModel,
                   "pyth_veh3dofconti_errcstr": Veh3dofContiErrCstrModel,
-                  "veh3dof_tracking_detour": Veh3dofTrackingDetourModel}
+                  "veh3dof_tracking_detour": Veh3dofTrackingDetourModel,
+                  "veh3dof_tracking_surrcstr": Veh3dofTrackingSurrCstrModel}
 
 
 # --------------------------------------------------------------------------------------
@@ -667,7 +684,7 @@ def sample_inputs(env_id: str, batch: int, seed: int, *, pre_horizon: int = 10, 
         cfg = LQ_CONFIGS[lq_config]
         mean, std = torch.tensor(cfg["init_mean"], dtype=torch.float32), torch.tensor(cfg["init_std"], dtype=torch.float32)
         return {"obs": mean + std * torch.randn(batch, len(cfg["init_mean"]), generator=g), "done": torch.zeros(batch)}
-    if env_id in ("pyth_veh3dofconti", "veh3dof_tracking", "veh3dof_tracking_detour"):
+    if env_id in ("pyth_veh3dofconti", "veh3dof_tracking", "veh3dof_tracking_detour", "veh3dof_tracking_surrcstr"):
         # pyth_veh3dofconti.py:144-191 ; env_gen_ocp/context/ref_traj.py:25-53
         ref = RefTraj()
         P = pre_horizon
@@ -689,7 +706,7 @@ def sample_inputs(env_id: str, batch: int, seed: int, *, pre_horizon: int = 10, 
         if env_id == "pyth_veh3dofconti":
             return {"obs": obs, "done": torch.zeros(batch), "state": state, "ref_points": ref_points,
                     "path_num": path, "u_num": spd, "ref_time": t0}
-        if env_id == "veh3dof_tracking_detour":
+        if env_id in ("veh3dof_tracking_detour", "veh3dof_tracking_surrcstr"):
             # env_gen_ocp/context/ref_traj_with_static_obstacle.py:76-127: one surrounding vehicle predicted over P + 1
             # points (x, y, phi, u, delta); here ahead of the ego vehicle near the path (some samples start infeasible)
             # and moving slowly along its heading

@@ -52,7 +52,7 @@ def base_kwargs(env_id, algorithm, obs_dim, act_dim, hidden, act, policy_name, *
 
 def to_ref_data(env_id, data):
     """Oracle input dict -> the dict the reference trainer would hand to local_update."""
-    gen_ocp = env_id in ("veh3dof_tracking", "veh3dof_tracking_detour")
+    gen_ocp = env_id in ("veh3dof_tracking", "veh3dof_tracking_detour", "veh3dof_tracking_surrcstr")
     out = {k: v for k, v in data.items() if k != "state" or not gen_ocp}
     B = data["obs"].shape[0]
     if gen_ocp:
@@ -70,7 +70,7 @@ def to_ref_data(env_id, data):
 def flat_inputs(env_id, data):
     d = {}
     for k, v in data.items():
-        if k == "state" and env_id in ("veh3dof_tracking", "veh3dof_tracking_detour"):
+        if k == "state" and env_id in ("veh3dof_tracking", "veh3dof_tracking_detour", "veh3dof_tracking_surrcstr"):
             d["in_robot_state"], d["in_reference"] = _np(v[0]), _np(v[1])
             d["in_t"] = np.int64(v[2])
             if len(v) > 3:
@@ -246,6 +246,12 @@ def run_detour():
         d = orc.sample_inputs("veh3dof_tracking_detour", 160, 71, pre_horizon=10)
         d["done"][::9] = 1.0
         run_case("detour_" + algname.lower(), kw, d, [0, 1])
+    # veh3dof_tracking_surrcstr: same structure, other radius / reward / bound -- one constrained case
+    kw = base_kwargs("veh3dof_tracking_surrcstr", "FHADPExterior", 50, 2, (64, 64), "elu", "FiniteHorizonPolicy", pre_horizon=10,
+                     gamma=0.97, **extra["FHADPExterior"])
+    d = orc.sample_inputs("veh3dof_tracking_surrcstr", 160, 72, pre_horizon=10)
+    d["done"][::9] = 1.0
+    run_case("surrcstr_fhadpexterior", kw, d, [0, 1])
 
 
 def main():

@@ -1,4 +1,5 @@
-"""env_gen_ocp veh3dof_tracking_detour (N3: the model of the reference's fhadp_mlp_veh3ddetour example) with FHADP and the
+"""env_gen_ocp veh3dof_tracking_detour (N3: the model of the reference's fhadp_mlp_veh3ddetour example) and its sibling
+veh3dof_tracking_surrcstr with FHADP and the
 constrained variants FHADPExterior / FHADPLagrangian / FHADPInterior on the layer-wise tcgen05 path (csrc/lw_detour.cuh):
 against the unmodified reference's golden vectors (two consecutive updates) and against the fp64 oracle on a fresh
 ragged batch with done samples -- whose state keeps evolving behind the frozen observation and keeps paying the
@@ -19,9 +20,9 @@ MODE = {"FHADPExterior": "exterior", "FHADPLagrangian": "lagrangian", "FHADPInte
 GRAD_RTOL = 2e-4
 
 
-def _alg(algname, hidden=64, P=10, **over):
+def _alg(algname, hidden=64, P=10, env_id="veh3dof_tracking_detour", **over):
     from gops_b200.create_pkg.create_alg import create_alg
-    kw = dict(env_id="veh3dof_tracking_detour", algorithm=algname, seed=0, trainer="off_serial_trainer", use_gpu=True,
+    kw = dict(env_id=env_id, algorithm=algname, seed=0, trainer="off_serial_trainer", use_gpu=True,
               action_type="continu", obsv_dim=6 + 4 * P + 4, action_dim=2, action_high_limit=np.ones(2, np.float32),
               action_low_limit=-np.ones(2, np.float32), policy_func_name="FiniteHorizonPolicy", policy_func_type="MLP",
               policy_hidden_sizes=[hidden, hidden], policy_hidden_activation="elu", policy_act_distribution="default",
@@ -39,10 +40,10 @@ def _gpu_data(data):
     return out
 
 
-def _noise_floor(rec, it, mode, coef):
+def _noise_floor(rec, it, mode, coef, env_id="veh3dof_tracking_detour"):
     """Distance between the reference's own fp32 gradient and the fp64 evaluation of the same formulas: the log barrier
     (and the norm in the collision distance) amplify fp32 round-off for samples near the boundary."""
-    env64 = orc.create_env_model("veh3dof_tracking_detour", dtype=torch.float64, pre_horizon=10)
+    env64 = orc.create_env_model(env_id, dtype=torch.float64, pre_horizon=10)
     pol64 = net_from(rec, "init/" if it == 0 else "it0/post/", "policy", "elu", torch.float64, requires_grad=True)
     pol64.time_input = True
     d64 = inputs_from(rec, "veh3dof_tracking_detour", torch.float64)
@@ -55,10 +56,11 @@ def _noise_floor(rec, it, mode, coef):
     return rel_l2([t.grad.numpy() for pair in pol64.layers for t in pair], [rec[k] for k in order])
 
 
-@pytest.mark.parametrize("algname", sorted(EXTRA))
-def test_two_updates_follow_the_reference(algname):
-    rec = load("detour_" + algname.lower())
-    alg = _alg(algname)
+@pytest.mark.parametrize("algname,case", [(a, "detour") for a in sorted(EXTRA)] + [("FHADPExterior", "surrcstr")])
+def test_two_updates_follow_the_reference(algname, case):
+    rec = load(case + "_" + algname.lower())
+    env_id = "veh3dof_tracking_" + case
+    alg = _alg(algname, env_id=env_id)
     alg.load_state_dict({k[5:]: torch.from_numpy(v) for k, v in rec.items() if k.startswith("init/")})
     data = _gpu_data(inputs_from(rec, "veh3dof_tracking_detour"))
     for it in (0, 1):
@@ -76,19 +78,19 @@ def test_two_updates_follow_the_reference(algname):
         coef = None
         if algname in MODE:
             coef = 2.0 * 1.5 ** it if algname != "FHADPLagrangian" else float(rec[f"it{it}/tb/Loss/Lagrange multiplier-RL iter"])
-        bar = max(GRAD_RTOL, 3.0 * _noise_floor(rec, it, MODE.get(algname), coef))
+        bar = max(GRAD_RTOL, 3.0 * _noise_floor(rec, it, MODE.get(algname), coef, env_id))
         assert err < bar, (it, err, bar)
 
 
-@pytest.mark.parametrize("hidden", [64, 256])
-@pytest.mark.parametrize("algname", sorted(EXTRA))
-def test_against_fp64_oracle_with_done_samples(algname, hidden):
+@pytest.mark.parametrize("algname,hidden,env_id", [(a, h, "veh3dof_tracking_detour") for a in sorted(EXTRA) for h in (64, 256)]
+                         + [("FHADPInterior", 256, "veh3dof_tracking_surrcstr"), ("FHADP", 64, "veh3dof_tracking_surrcstr")])
+def test_against_fp64_oracle_with_done_samples(algname, hidden, env_id):
     B, P = 777, 12
     torch.manual_seed(B + hidden)
-    alg = _alg(algname, hidden=hidden, P=P, reward_scale=0.5, reward_shift=0.3)
-    data = orc.sample_inputs("veh3dof_tracking_detour", B, seed=B, pre_horizon=P)
+    alg = _alg(algname, hidden=hidden, P=P, env_id=env_id, reward_scale=0.5, reward_shift=0.3)
+    data = orc.sample_inputs(env_id, B, seed=B, pre_horizon=P)
     data["done"][::5] = 1.0
-    env = orc.create_env_model("veh3dof_tracking_detour", dtype=torch.float64, pre_horizon=P, reward_scale=0.5, reward_shift=0.3)
+    env = orc.create_env_model(env_id, dtype=torch.float64, pre_horizon=P, reward_scale=0.5, reward_shift=0.3)
     pi = alg.networks.policy.pi
     layers = [(pi[j].weight.detach().cpu().double().requires_grad_(True), pi[j].bias.detach().cpu().double().requires_grad_(True))
               for j in (0, 2, 4)]

@@ -11,7 +11,7 @@ from oracle import gops_oracle as orc
 MODES = {"cstr_fhadpexterior": ("exterior", (2.0, 3.0)), "cstr_fhadpinterior": ("interior", (2.0, 3.0)),
          "cstr_fhadplagrangian": ("lagrangian", None),
          "detour_fhadpexterior": ("exterior", (2.0, 3.0)), "detour_fhadpinterior": ("interior", (2.0, 3.0)),
-         "detour_fhadplagrangian": ("lagrangian", None)}
+         "detour_fhadplagrangian": ("lagrangian", None), "surrcstr_fhadpexterior": ("exterior", (2.0, 3.0))}
 
 
 @pytest.mark.parametrize("name", sorted(MODES))
@@ -19,8 +19,8 @@ def test_constrained_losses_and_gradients(name):
     torch.set_num_threads(4)
     mode, coefs = MODES[name]
     rec = load(name)
-    if name.startswith("detour"):
-        env = orc.create_env_model("veh3dof_tracking_detour", pre_horizon=10)
+    if name.startswith("detour") or name.startswith("surrcstr"):
+        env = orc.create_env_model("veh3dof_tracking_" + name.split("_")[0], pre_horizon=10)
         data = inputs_from(rec, "veh3dof_tracking_detour")
     else:
         env = orc.create_env_model("pyth_veh3dofconti_errcstr", pre_horizon=10, y_error_tol=1.2, u_error_tol=2.2)
