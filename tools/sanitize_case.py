@@ -15,7 +15,7 @@ from gops_b200.create_pkg.create_alg import create_alg
 from oracle import gops_oracle as orc
 
 torch.manual_seed(0)
-which = sys.argv[1:] or ["idp", "lq", "veh", "wide", "tc", "lw", "dsac", "cstr"]
+which = sys.argv[1:] or ["idp", "lq", "veh", "wide", "tc", "lw", "dsac", "cstr", "detour", "peer"]
 if "idp" in which:
     alg = create_alg(**kwargs("pyth_idpendulum", "FHADP", 6, 1, 64, "gelu", pre_horizon=3, reward_scale=1.0))
     for B in (700, 130):     # cfg1/cfg2 tiles incl. ragged tails
@@ -86,5 +86,27 @@ if "cstr" in which:
     d = orc.sample_inputs("pyth_veh3dofconti", 150, 6, pre_horizon=10)
     d["done"][::4] = 1.0
     alg.local_update(to_dev(d), 0)
+if "detour" in which:      # surrounding-vehicle model + interior point on the layer-wise path (lw_detour.cuh), done samples, ragged batch
+    from gops_b200.env.env_gen_ocp.pyth_base import ContextState, State
+    kw5 = kwargs("veh3dof_tracking_detour", "FHADPInterior", 50, 2, 64, "elu", pre_horizon=10, penalty=2.0)
+    kw5["policy_func_name"] = "FiniteHorizonPolicy"
+    alg = create_alg(**kw5)
+    d = orc.sample_inputs("veh3dof_tracking_detour", 150, 7, pre_horizon=10)
+    d["done"][::4] = 1.0
+    robot, ref, t, surr = d["state"]
+    dd = {"obs": d["obs"].cuda(), "done": d["done"].cuda(),
+          "state": State(robot_state=robot.cuda(), context_state=ContextState(reference=ref.cuda(), constraint=surr.cuda(), t=t))}
+    for i in range(3):       # eager, capture, replay
+        alg.local_update(dd, i)
+if "peer" in which:        # exchange + Adam kernel, single rank (the sanitizer serialises kernels: peers cannot spin on each other)
+    from gops_b200.utils.peer_reduce import PeerReduce
+    from gops_b200 import _lib
+    import ctypes as C
+    pr = PeerReduce(1, 0, 1000)
+    buf, par, m, v = (torch.randn(777, device="cuda") for _ in range(4))
+    v.abs_()
+    _lib.check(_lib.lib().gops_b200_peer_allreduce(pr.handle, _lib.ptr(buf), 777, _lib.ptr(par), _lib.ptr(m), _lib.ptr(v), 773, 3,
+                                                   1e-3, 0.9, 0.999, 1e-8, _lib.stream_ptr()))
+    pr.allreduce(torch.randn(5, device="cuda"))
 torch.cuda.synchronize()
 print("sanitize_case done")
