@@ -89,3 +89,17 @@ def test_flat_params_views_survive_module_moves():
     pol.double().float()                         # a dtype round trip re-allocates parameters ...
     flat2 = fp.sync()                            # ... and sync() re-flattens them
     assert flat2.data_ptr() == next(pol.pi.parameters()).data.data_ptr()
+
+
+def test_peer_exchange_is_not_selected_without_nccl(monkeypatch):
+    """utils/peer_reduce.group_peer: the peer-memory path needs an initialised NCCL group of >= 2 ranks on one host; in
+    every other situation the caller falls through to dist.all_reduce (and a wrong mode string is an error)."""
+    from gops_b200.utils import peer_reduce
+    assert peer_reduce.group_peer(1000, torch.device("cpu")) is None            # no process group
+    monkeypatch.setenv("GOPS_B200_ALLREDUCE", "nccl")
+    assert peer_reduce.mode() == "nccl" and peer_reduce.group_peer(1000, torch.device("cpu")) is None
+    monkeypatch.setenv("GOPS_B200_ALLREDUCE", "ring")
+    with pytest.raises(RuntimeError, match="auto, p2p or nccl"):
+        peer_reduce.mode()
+    monkeypatch.setenv("GOPS_B200_ALLREDUCE", "auto")
+    assert peer_reduce.group_peer(peer_reduce.MAX_P2P_FLOATS + 1, torch.device("cpu")) is None   # bandwidth regime: NCCL
