@@ -164,8 +164,8 @@ LwFn lw_fn_vehtrack(int which);
 LwFn lw_fn_vehtrack_detour(int which);    // veh3dof_tracking_detour: 1 forward step, 2 reverse step (lw_detour.cuh)
 void lw_launch_scalars_detour(const KParams& p, const float* vacc, const float* cacc, const float* dn_last, float* scalars,
                               cudaStream_t st);
-RolloutFn rollout_fn_tc2_idp(int alg);  // pipelined tcgen05 kernel: two independent 128-thread groups per CTA (rollout_tc2.cuh)
-RolloutFn rollout_fn_tc2_lq(int alg);
+RolloutFn rollout_fn_tc2_idp(int alg, int hact);  // pipelined tcgen05 kernel: two independent 128-thread groups per CTA (rollout_tc2.cuh)
+RolloutFn rollout_fn_tc2_lq(int alg, int hact);
 }  // namespace gops
 
 namespace {
@@ -179,13 +179,14 @@ RolloutFn rollout_fn(int model, int hid, int cfg, int alg) {
     default: return nullptr;
   }
 }
-RolloutFn rollout_fn_tc2(int model, int alg) {
+RolloutFn rollout_fn_tc2(int model, int alg, int hact = -1) {      // hact: the nets' common hidden activation, or -1
   switch (model) {
-    case GOPS_MODEL_IDPENDULUM: return rollout_fn_tc2_idp(alg);
-    case GOPS_MODEL_LQ: return rollout_fn_tc2_lq(alg);
+    case GOPS_MODEL_IDPENDULUM: return rollout_fn_tc2_idp(alg, hact);
+    case GOPS_MODEL_LQ: return rollout_fn_tc2_lq(alg, hact);
     default: return nullptr;
   }
 }
+
 LwFn lw_fn(int model, int which) {
   switch (model) {
     case GOPS_MODEL_IDPENDULUM: return lw_fn_idp(which);
@@ -605,7 +606,8 @@ int launch_rollout(gops_b200_plan* pl, const gops_b200_batch* b, int alg, cudaSt
   KParams& kp = pl->kp;
   if (rollout_use_tc(pl, b->batch)) {
     const bool v1 = false;
-    RolloutFn fn = rollout_fn_tc2(pl->desc.model, alg);
+    const int hact = (alg == ALG_FHADP || pl->pol_tcf.hact == pl->val_tcf.hact) ? pl->pol_tcf.hact : -1;
+    RolloutFn fn = rollout_fn_tc2(pl->desc.model, alg, hact);
     if (!fn) return fail("tcgen05 rollout kernel not built for this env model");
     const int S = 128, NT = v1 ? 512 : tc2::NT2;
     KParams k2 = kp;

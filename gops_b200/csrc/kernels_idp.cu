@@ -26,7 +26,15 @@ RolloutFn rollout_fn_idp(int hid, int cfg, int alg) {
     default: return pick<ALG_TRACE>(hid, cfg);
   }
 }
-RolloutFn rollout_fn_tc2_idp(int alg) {   // pipelined tcgen05 kernel (two independent groups per CTA)
+RolloutFn rollout_fn_tc2_idp(int alg, int hact) {   // pipelined tcgen05 kernel (two independent groups per CTA)
+  if (hact == GOPS_ACT_GELU) {                       // activation fixed at compile time (rollout_tc2.cuh, GOPS_TC2_ACT_SWITCH)
+    switch (alg) {
+      case ALG_FHADP: return rollout_tc2_kernel<ModelIdp, ALG_FHADP, GOPS_ACT_GELU>;
+      case ALG_PIM: return rollout_tc2_kernel<ModelIdp, ALG_PIM, GOPS_ACT_GELU>;
+      case ALG_PEV: return rollout_tc2_kernel<ModelIdp, ALG_PEV, GOPS_ACT_GELU>;
+      default: return rollout_tc2_kernel<ModelIdp, ALG_TRACE, GOPS_ACT_GELU>;
+    }
+  }
   switch (alg) {
     case ALG_FHADP: return rollout_tc2_kernel<ModelIdp, ALG_FHADP>;
     case ALG_PIM: return rollout_tc2_kernel<ModelIdp, ALG_PIM>;
@@ -34,6 +42,7 @@ RolloutFn rollout_fn_tc2_idp(int alg) {   // pipelined tcgen05 kernel (two indep
     default: return rollout_tc2_kernel<ModelIdp, ALG_TRACE>;
   }
 }
+
 StepFn step_fn_idp() { return model_step_kernel<ModelIdp>; }
 
 LwFn lw_fn_idp(int which) {   // layer-wise path of the wide nets: init / forward step / reverse step

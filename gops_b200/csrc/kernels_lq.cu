@@ -26,7 +26,15 @@ RolloutFn rollout_fn_lq(int hid, int cfg, int alg) {
     default: return pick<ALG_TRACE>(hid, cfg);
   }
 }
-RolloutFn rollout_fn_tc2_lq(int alg) {   // pipelined tcgen05 kernel (two independent groups per CTA)
+RolloutFn rollout_fn_tc2_lq(int alg, int hact) {   // pipelined tcgen05 kernel (two independent groups per CTA)
+  if (hact == GOPS_ACT_GELU) {                       // activation fixed at compile time (rollout_tc2.cuh, GOPS_TC2_ACT_SWITCH)
+    switch (alg) {
+      case ALG_FHADP: return rollout_tc2_kernel<ModelLq, ALG_FHADP, GOPS_ACT_GELU>;
+      case ALG_PIM: return rollout_tc2_kernel<ModelLq, ALG_PIM, GOPS_ACT_GELU>;
+      case ALG_PEV: return rollout_tc2_kernel<ModelLq, ALG_PEV, GOPS_ACT_GELU>;
+      default: return rollout_tc2_kernel<ModelLq, ALG_TRACE, GOPS_ACT_GELU>;
+    }
+  }
   switch (alg) {
     case ALG_FHADP: return rollout_tc2_kernel<ModelLq, ALG_FHADP>;
     case ALG_PIM: return rollout_tc2_kernel<ModelLq, ALG_PIM>;
@@ -34,6 +42,7 @@ RolloutFn rollout_fn_tc2_lq(int alg) {   // pipelined tcgen05 kernel (two indepe
     default: return rollout_tc2_kernel<ModelLq, ALG_TRACE>;
   }
 }
+
 StepFn step_fn_lq() { return model_step_kernel<ModelLq>; }
 
 LwFn lw_fn_lq(int which) {   // layer-wise path of the wide nets: init / forward step / reverse step

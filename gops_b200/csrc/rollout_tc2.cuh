@@ -219,12 +219,19 @@ __device__ __forceinline__ void layer1_issue(Grp& G, const NetL& L, const float*
   }
   TL(G, 5);
 }
+// AF: hidden activation fixed at compile time (>= 0), or -1 = dispatch on the runtime id.  The register allocation of the
+// kernel is decided by its most demanding path: with the activation fixed (the headline configurations use GELU) the other
+// six epilogue variants are not compiled in.
+#define GOPS_TC2_ACT_SWITCH(AF, act, M)     \
+  if constexpr ((AF) >= 0) { M(AF); }       \
+  else { GOPS_ACT_SWITCH(act, M) }
+
 // layer 1, second half: + b1, activation -> this thread's 32 columns of the H1 planes (FULL: act' parked in TMEM).
 // Two rolled passes of 16 columns: half the code and half the registers of one 32-column pass (the kernel is
 // instruction-fetch sensitive: 8 warps per SM sub-partition pair run different phases of a long straight-line body).
 // [lo, hi): the 16-column blocks of the row this thread converts (forward sweep: owner 0-1, helper 2-3; reverse sweep:
 // the helper takes all four while the owner runs the adjoint of the dynamics).
-template <bool FULL>
+template <bool FULL, int AF>
 __device__ __forceinline__ void layer1_finish(Grp& G, const NetL& L, int lo, int hi) {
   using namespace tcf;
   TL(G, 6);
@@ -242,7 +249,7 @@ __device__ __forceinline__ void layer1_finish(Grp& G, const NetL& L, int lo, int
     if constexpr (FULL) act_fwd_grad_pair_t<A>(pre, v[e], v[e + 1], d[e], d[e + 1]);          \
     else act_fwd_pair_t<A>(pre, v[e], v[e + 1]);                                              \
   }
-    GOPS_ACT_SWITCH(L.hact, GOPS_TC2_A1)
+    GOPS_TC2_ACT_SWITCH(AF, L.hact, GOPS_TC2_A1)
 #undef GOPS_TC2_A1
     store16(G.P, HPL, c16, G.r, v);
     if constexpr (FULL) umma::tmem_st16(G.tm + C_D1 + 16 * c16, d);
@@ -252,6 +259,7 @@ __device__ __forceinline__ void layer1_finish(Grp& G, const NetL& L, int lo, int
 }
 
 // layer 2 + output layer, forward only: the owner gets z[a] = b3[a] + W3[a] . act(H1 . W2^T + b2)
+template <int AF>
 __device__ __forceinline__ void layer2_out(Grp& G, const NetL& L, float* z) {
   using namespace tcf;
   publish(G);
@@ -277,7 +285,7 @@ __device__ __forceinline__ void layer2_out(Grp& G, const NetL& L, float* z) {
 #define GOPS_TC2_A2(A)                               \
   _Pragma("unroll") for (int e = 0; e < 16; e += 2)  \
       act_fwd_pair_t<A>(f32x2::add(f32x2::pk(v[e], v[e + 1]), f32x2::ld(bias + e)), v[e], v[e + 1]);
-    GOPS_ACT_SWITCH(L.hact, GOPS_TC2_A2)
+    GOPS_TC2_ACT_SWITCH(AF, L.hact, GOPS_TC2_A2)
 #undef GOPS_TC2_A2
 #pragma unroll
     for (int a = 0; a < MAXA; ++a)
@@ -316,7 +324,7 @@ struct Acc3 {
 // layer 2 recompute fused with the start of the backward pass: z for the owner (WANT_Z), dW3 / db3 partial sums, and
 // delta2 = (W3^T zbar) * act'(pre2) -> this thread's 32 columns of the two delta planes.
 // zbar: the owner's output adjoint of its row (the helper receives it through shared memory).
-template <bool WANT_DW, bool WANT_Z>
+template <bool WANT_DW, bool WANT_Z, int AF>
 __device__ __forceinline__ void layer2_back(Grp& G, const NetL& L, const float* zbar, float* z, Acc3& acc3) {
   using namespace tcf;
   if (G.h == 0) {
@@ -352,7 +360,7 @@ __device__ __forceinline__ void layer2_back(Grp& G, const NetL& L, const float* 
 #define GOPS_TC2_A3(A)                               \
   _Pragma("unroll") for (int e = 0; e < 16; e += 2)  \
       act_fwd_grad_pair_t<A>(f32x2::add(f32x2::pk(v[e], v[e + 1]), f32x2::ld(bias + e)), v[e], v[e + 1], d[e], d[e + 1]);
-    GOPS_ACT_SWITCH(L.hact, GOPS_TC2_A3)
+    GOPS_TC2_ACT_SWITCH(AF, L.hact, GOPS_TC2_A3)
 #undef GOPS_TC2_A3
     const float* w3 = G.W3 + 16 * c16;
     if constexpr (WANT_Z) {
@@ -608,7 +616,7 @@ __device__ __forceinline__ void flush(Grp& G, const NetL& L, float* __restrict__
 // INFADP swaps weight blobs (policy <-> v_target <-> v) through the one staging buffer: those swap points are CTA-wide
 // barriers, so both groups run the same number of (possibly empty) sub-tile iterations; FHADP groups never meet.
 // ---------------------------------------------------------------------------------------------------------------
-template <class M, int ALG>
+template <class M, int ALG, int AF = -1>
 __global__ void __launch_bounds__(tc2::NT2, 1) rollout_tc2_kernel(const __grid_constant__ KParams p) {
   using namespace tc2;
   static_assert(M::KIND == 0, "tcgen05 rollout kernel: state == obs models");
@@ -727,8 +735,8 @@ __global__ void __launch_bounds__(tc2::NT2, 1) rollout_tc2_kernel(const __grid_c
         }
         float z[MAXA];
         layer1_issue<NS>(G, P, st, (float)(k + 1));
-        layer1_finish<false>(G, P, 2 * G.h, 2 * G.h + 2);
-        layer2_out(G, P, z);
+        layer1_finish<false, AF>(G, P, 2 * G.h, 2 * G.h + 2);
+        layer2_out<AF>(G, P, z);
         TL(G, 30);
         if (own) {
           float a[MAXA], g[MAXA], apol[MAXA];
@@ -795,8 +803,8 @@ __global__ void __launch_bounds__(tc2::NT2, 1) rollout_tc2_kernel(const __grid_c
         if (alg == ALG_PIM) {
           zb[0] = term ? -gn * p.inv_B : 0.f;
           layer1_issue<NS>(G, V, st, 0.f);
-          layer1_finish<true>(G, V, 2 * G.h, 2 * G.h + 2);
-          layer2_back<false, true>(G, V, zb, zv, acc3);
+          layer1_finish<true, AF>(G, V, 2 * G.h, 2 * G.h + 2);
+          layer2_back<false, true, AF>(G, V, zb, zv, acc3);
           backprop<false>(G, V, true, dx);
           if (term) {
 #pragma unroll
@@ -805,8 +813,8 @@ __global__ void __launch_bounds__(tc2::NT2, 1) rollout_tc2_kernel(const __grid_c
           }
         } else {
           layer1_issue<NS>(G, V, st, 0.f);
-          layer1_finish<false>(G, V, 2 * G.h, 2 * G.h + 2);
-          layer2_out(G, V, zv);
+          layer1_finish<false, AF>(G, V, 2 * G.h, 2 * G.h + 2);
+          layer2_out<AF>(G, V, zv);
         }
         if (term) vacc += gn * zv[0];
       }
@@ -825,15 +833,15 @@ __global__ void __launch_bounds__(tc2::NT2, 1) rollout_tc2_kernel(const __grid_c
         for (int j = 0; j < MAXA; ++j) zb[j] = zv[j] = 0.f;
         // the output adjoint needs v(o_0) first: forward to the output, then recompute layer 2 fused with the backward
         layer1_issue<NS>(G, V, o0, 0.f);
-        layer1_finish<true>(G, V, 2 * G.h, 2 * G.h + 2);
-        layer2_out(G, V, zv);
+        layer1_finish<true, AF>(G, V, 2 * G.h, 2 * G.h + 2);
+        layer2_out<AF>(G, V, zv);
         if (own && valid) {
           const float diff = zv[0] - vacc;
           loss_acc += diff * diff * p.inv_B;
           vmean_acc += zv[0] * p.inv_B;
           zb[0] = 2.f * diff * p.inv_B;
         }
-        layer2_back<true, false>(G, V, zb, nullptr, acc3);
+        layer2_back<true, false, AF>(G, V, zb, nullptr, acc3);
         backprop<true>(G, V, false, dx);
         flush(G, V, part);
       }
@@ -945,9 +953,9 @@ __global__ void __launch_bounds__(tc2::NT2, 1) rollout_tc2_kernel(const __grid_c
         }
       }
       TL(G, 32);
-      layer1_finish<true>(G, P, 0, G.h == 0 ? 0 : 4);      // the helper converts the whole row meanwhile
+      layer1_finish<true, AF>(G, P, 0, G.h == 0 ? 0 : 4);      // the helper converts the whole row meanwhile
       float dx[16];
-      layer2_back<true, false>(G, P, zb, nullptr, acc3);
+      layer2_back<true, false, AF>(G, P, zb, nullptr, acc3);
       backprop<true>(G, P, k > 0, dx, true);
       dx_pending = k > 0;
       dx_add = active && k > 0;
