@@ -162,6 +162,8 @@ LwFn lw_fn_idp(int which);              // layer-wise path (wide nets): 0 init, 
 LwFn lw_fn_lq(int which);
 LwFn lw_fn_vehtrack(int which);
 LwFn lw_fn_vehtrack_detour(int which);    // veh3dof_tracking_detour: 1 forward step, 2 reverse step (lw_detour.cuh)
+void launch_veh_step_detour(const KParams& p, const float* action, float* next_obs, float* reward, float* next_done,
+                            float* next_state, cudaStream_t st);
 void lw_launch_scalars_detour(const KParams& p, const float* vacc, const float* cacc, const float* dn_last, float* scalars,
                               cudaStream_t st);
 RolloutFn rollout_fn_tc2_idp(int alg, int hact);  // pipelined tcgen05 kernel: two independent 128-thread groups per CTA (rollout_tc2.cuh)
@@ -1260,9 +1262,6 @@ int gops_b200_model_step(gops_b200_plan* pl, const gops_b200_batch* b, const flo
   ENTRY("float* next_ref_time, void* stream) {");
   if (!pl || !b || !action || !next_obs || !reward || !next_done) return fail("null argument");
   if (b->batch <= 0 || !b->obs || !b->done) return fail("bad batch");
-  if (pl->desc.veh_detour)
-    return fail("model_step: stepping veh3dof_tracking_detour is not built (the model runs inside the fused FHADP / "
-                "FHADPExterior / FHADPLagrangian / FHADPInterior update)");
   DevGuard dg(pl->device);
   KParams& kp = pl->kp;
   kp.batch = b->batch; kp.obs = b->obs; kp.done = b->done;
@@ -1276,9 +1275,13 @@ int gops_b200_model_step(gops_b200_plan* pl, const gops_b200_batch* b, const flo
       return fail("model_step: pyth_veh3dofconti needs ref_points, path_num, u_num, ref_time and their outputs");
     if (!conti && (!b->reference || b->ref_t < 0 || b->ref_t + kp.veh_P + 2 > b->ref_len))
       return fail("model_step: veh3dof_tracking reference too short for t + 1 + pre_horizon + 1 points");
+    if (pl->desc.veh_detour && (!b->surr || b->ref_t + 2 > b->surr_len))
+      return fail("model_step: veh3dof_tracking_detour needs the surrounding-vehicle predictions for t and t + 1");
     kp.state = b->state; kp.ref_points = b->ref_points; kp.path_num = b->path_num; kp.u_num = b->u_num;
     kp.ref_time = b->ref_time; kp.reference = b->reference; kp.ref_t = b->ref_t; kp.ref_len = b->ref_len;
-    if (conti) veh_step_kernel<1><<<grid, 128, 0, st>>>(kp, action, next_obs, reward, next_done, next_state,
+    kp.surr = b->surr; kp.surr_len = b->surr_len;
+    if (pl->desc.veh_detour) launch_veh_step_detour(kp, action, next_obs, reward, next_done, next_state, st);
+    else if (conti) veh_step_kernel<1><<<grid, 128, 0, st>>>(kp, action, next_obs, reward, next_done, next_state,
                                                         next_ref_points, next_ref_time);
     else veh_step_kernel<2><<<grid, 128, 0, st>>>(kp, action, next_obs, reward, next_done, next_state,
                                                   next_ref_points, next_ref_time);

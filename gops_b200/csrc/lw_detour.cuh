@@ -224,6 +224,62 @@ __global__ void lw_reverse_detour_kernel(const __grid_constant__ KParams p, cons
   for (int f = 0; f < NS; ++f) a.lam[(size_t)f * B + b] = lam[f];
 }
 
+// single model step (EnvModel.forward inside the wrapper chain, as veh_step_kernel<2> for the plain tracking model):
+// next_obs / reward / next_done / next_state of the detour / surrcstr variant; info["constraint"] of the incoming state is
+// evaluated by the Python model class (element-wise torch code on the device tensors, like pyth_veh3dofconti_errcstr)
+__global__ void veh_step_detour_kernel(const __grid_constant__ KParams p, const float* __restrict__ action,
+                                       float* __restrict__ next_obs, float* __restrict__ reward, float* __restrict__ next_done,
+                                       float* __restrict__ next_state) {
+  const long long gs = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gs >= p.batch) return;
+  const int obs_dim = p.pol.obs, P = p.veh_P;
+  const VehC vc = veh_const();
+  float a[MAXA], s[6];
+#pragma unroll
+  for (int j = 0; j < MAXA; ++j) {
+    float gg = 1.f;
+    a[j] = j < 2 ? wrap_action(p, j, action[gs * 2 + j], gg) : 0.f;
+  }
+#pragma unroll
+  for (int f = 0; f < 6; ++f) s[f] = p.state[gs * 6 + f];
+  const bool dn = p.done[gs] != 0.f;
+  const float* obs = p.obs + gs * obs_dim;
+  float* nobs = next_obs + gs * obs_dim;
+  RefWindow<2, 1> w;
+  w.base = p.reference + gs * (size_t)p.ref_len * 4;
+  w.k0 = p.ref_t;
+  float q[4];
+  w.get(0, q);
+  const float ex = s[0] - q[0], ey = s[1] - q[1], ep = angle_normalize(s[2] - q[2]), eu = s[3] - q[3];
+  float r = -p.veh_rscale * (p.veh_rc[0] * (ex * ex) + p.veh_rc[1] * (ey * ey) + p.veh_rc[2] * (ep * ep) + p.veh_rc[3] * (eu * eu) +
+                             p.veh_rc[4] * (s[5] * s[5]) + p.veh_rc[5] * (a[0] * a[0]) + p.veh_rc[6] * (a[1] * a[1])) +
+            p.veh_roff;
+  veh_step(vc, s, a);
+  w.k0 = p.ref_t + 1;
+  float o6[6];
+  veh_write_obs<2, 1>(s, w, P, nobs, 1, o6);
+  {
+    float sn, cs, o4[4];
+    sincosf(-s[2], &sn, &cs);
+    const float* sp = detour_surr(p, gs, 1);
+    ego_obs(s, cs, sn, sp[0], sp[1], sp[2], 0.f, o4);
+    nobs[6 + 4 * P] = o4[0]; nobs[6 + 4 * P + 1] = o4[1]; nobs[6 + 4 * P + 2] = o4[2]; nobs[6 + 4 * P + 3] = sp[3];
+  }
+  w.get(0, q);
+  bool md = (fabsf(s[0] - q[0]) > 5.f) || (fabsf(s[1] - q[1]) > p.veh_ydone) ||
+            (fabsf(angle_normalize(s[2] - q[2])) > 3.14159265358979323846f);
+#pragma unroll
+  for (int f = 0; f < 6; ++f) next_state[gs * 6 + f] = s[f];
+  if (p.mask_at_done && dn) {     // MaskAtDone: frozen observation, zero reward; info["state"] still advances
+    r = 0.f;
+    for (int f = 0; f < obs_dim; ++f) nobs[f] = obs[f];
+  }
+  if (p.mask_at_done) md = md || dn;
+  if (p.reward_shaping) r = (r + p.reward_shift) * p.reward_scale;
+  reward[gs] = r;
+  next_done[gs] = md ? 1.f : 0.f;
+}
+
 // [loss | exterior / Lagrangian constraint mean | interior term or #done | #feasible] in fixed order (one block)
 __global__ void lw_scalars_detour_kernel(const __grid_constant__ KParams p, const float* __restrict__ vacc,
                                          const float* __restrict__ cacc, const float* __restrict__ dn_last,

@@ -5,8 +5,7 @@ surrounding vehicle's ego-frame pose and speed (:62-76), other reward weights an
 info["constraint"] = 2 r - min distance of the bicircle collision model of the incoming state (:78-131) -- the constraint
 provider of FHADPExterior / FHADPLagrangian / FHADPInterior.  ContextState.constraint holds the surrounding vehicle's
 predictions [B, pre_horizon + 1, 1, 5] = (x, y, phi, u, delta) (context/ref_traj_with_static_obstacle.py:119-127).
-Kernels: csrc/lw_detour.cuh on the layer-wise tcgen05 path (the fused update only; `forward` -- stepping the model -- raises
-"not built")."""
+Kernels: csrc/lw_detour.cuh (the fused update on the layer-wise tcgen05 path; `forward` = veh_step_detour_kernel)."""
 import math
 from typing import Union
 
@@ -44,6 +43,30 @@ class Veh3DoFTrackingDetourModel(Veh3DoFTrackingModel):
         surr = f32(surr)
         keep.append(surr)
         batch.surr, batch.surr_len = surr.data_ptr(), int(surr.shape[1])
+
+
+    RADIUS_FACTOR = 0.5      # r = 0.5 * veh_width (veh3dof_tracking_detour_model.py:83)
+
+    def get_constraint(self, state: State) -> torch.Tensor:
+        """2 r - min distance between the two circles of the ego vehicle and of the surrounding vehicle at ContextState.t
+        (reference :78-131), element-wise torch code on the caller's (device) tensors: info["constraint"] of `forward`."""
+        d, r = (self.veh_length - self.veh_width) / 2, self.RADIUS_FACTOR * self.veh_width
+        rs = state.robot_state
+        surr = state.context_state.constraint[:, int(state.context_state.t)].to(rs.device)        # [B, n, 5]
+        best = None
+        for sg in (1.0, -1.0):
+            ex, ey = rs[:, 0:1] + sg * d * torch.cos(rs[:, 2:3]), rs[:, 1:2] + sg * d * torch.sin(rs[:, 2:3])
+            for tg in (1.0, -1.0):
+                qx = surr[..., 0] + tg * d * torch.cos(surr[..., 2])
+                qy = surr[..., 1] + tg * d * torch.sin(surr[..., 2])
+                dist = torch.sqrt((ex - qx) ** 2 + (ey - qy) ** 2).min(dim=1, keepdim=True).values
+                best = dist if best is None else torch.minimum(best, dist)
+        return 2 * r - best
+
+    def make_next_info(self, info, extra):
+        next_info = super().make_next_info(info, extra)
+        next_info["constraint"] = self.get_constraint(info["state"])          # of the INCOMING state (pyth_base_model.py:117-118)
+        return next_info
 
 
 def env_model_creator(**kwargs) -> Veh3DoFTrackingDetourModel:

@@ -7,6 +7,7 @@ from gops_b200.env.env_gen_ocp.env_model.veh3dof_tracking_detour_model import Ve
 
 class Veh3DoFTrackingSurrCstrModel(Veh3DoFTrackingDetourModel):
     VARIANT = 2
+    RADIUS_FACTOR = 2 ** 0.5 / 2      # r = np.sqrt(2) / 2 * veh_width (veh3dof_tracking_surrcstr_model.py:88)
 
 
 def env_model_creator(**kwargs) -> Veh3DoFTrackingSurrCstrModel:

@@ -120,12 +120,30 @@ def test_against_fp64_oracle_with_done_samples(algname, hidden, env_id):
     assert rel_l2(got, want) < bar
 
 
-def test_stepping_the_model_is_reported_as_not_built():
+@pytest.mark.parametrize("env_id", ["veh3dof_tracking_detour", "veh3dof_tracking_surrcstr"])
+def test_single_step_forward_matches_the_oracle(env_id):
+    """envmodel.forward (EnvModel.forward inside the wrapper chain): three consecutive steps incl. samples that arrive done
+    -- frozen observation, zero reward, state still advancing -- and info["constraint"] of the incoming state."""
     from gops_b200.create_pkg.create_env_model import create_env_model
-    env = create_env_model(env_id="veh3dof_tracking_detour", pre_horizon=10)
-    d = _gpu_data(orc.sample_inputs("veh3dof_tracking_detour", 4, seed=1, pre_horizon=10))
-    with pytest.raises(RuntimeError, match="not built"):
-        env.forward(d["obs"].cuda(), torch.zeros(4, 2, device="cuda"), d["done"].cuda(), {"state": d["state"]})
+    B, P = 300, 10
+    env = create_env_model(env_id=env_id, pre_horizon=P, reward_scale=0.5, reward_shift=0.1)
+    ref = orc.create_env_model(env_id, pre_horizon=P, reward_scale=0.5, reward_shift=0.1)
+    d = orc.sample_inputs(env_id, B, seed=9, pre_horizon=P)
+    d["done"][::4] = 1.0
+    g = _gpu_data(d)
+    obs, done, info = g["obs"].cuda(), g["done"].cuda(), {"state": g["state"]}
+    o_ref, d_ref, i_ref = d["obs"], d["done"], d
+    gen = torch.Generator().manual_seed(3)
+    for _ in range(3):
+        act = torch.rand(B, 2, generator=gen) * 2.4 - 1.2            # beyond the action box: exercises scale + clip
+        obs, rew, done, info = env.forward(obs, act.cuda(), done, info)
+        o_ref, r_ref, d_ref, i_ref = ref.forward(o_ref, act, d_ref, i_ref)
+        assert torch.allclose(obs.cpu(), o_ref, rtol=1e-5, atol=2e-5)
+        assert torch.allclose(rew.cpu(), r_ref, rtol=1e-5, atol=1e-5)
+        assert torch.equal(done.cpu().bool(), d_ref.bool())
+        assert torch.allclose(info["state"].robot_state.cpu(), i_ref["state"][0], rtol=1e-5, atol=1e-5)
+        assert torch.allclose(info["constraint"].cpu(), i_ref["constraint"], rtol=1e-5, atol=1e-5)
+        done = done.float()
 
 
 def test_device_sampler_feeds_the_interior_point_update():
