@@ -163,3 +163,17 @@ def test_device_sampler_feeds_the_interior_point_update():
         losses.append(tb["Loss/Actor loss-RL iter"])
         assert np.isfinite(losses[-1]) and 0.0 <= tb["Loss/Feasible ratio-RL iter"] <= 1.0
     assert losses[-1] < losses[0]
+
+
+def test_example_script_trains_and_evaluates():
+    """example_train/fhadp_mlp_veh3ddetour_b200.py for a few iterations: device sampler -> interior-point update ->
+    batched evaluation through envmodel.forward (the detour model's own single-step kernel)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "example_train", "fhadp_mlp_veh3ddetour_b200.py"),
+                          "--max_iteration", "21", "--eval_interval", "10", "--replay_batch_size", "1024", "--pre_horizon", "12"],
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "Loss/Feasible ratio-RL iter" in out.stdout and "TAR" in out.stdout, out.stdout[-2000:]
