@@ -242,6 +242,7 @@ struct gops_b200_plan {
   std::vector<unsigned char> lw_key;      // the call the captured graph belongs to (KParams bytes + buffers + stream)
   int lw_key_hits = 0;
   cudaGraphExec_t lw_exec = nullptr;
+  bool lw_graph_off = false;              // a capture attempt failed: this plan launches eagerly from then on
   cudaStream_t lw_cap_stream = nullptr;
   long long lw_graph_launches = 0;
   int last_grid = 0, last_S = 0, last_NT = 0;
@@ -568,25 +569,33 @@ int launch_rollout_layerwise(gops_b200_plan* pl, const gops_b200_batch* b, const
       pl->lw_key_hits = 0;
       if (pl->lw_exec) { cudaGraphExecDestroy(pl->lw_exec); pl->lw_exec = nullptr; }
     }
-    if (graphs && pl->lw_key_hits >= 1) {
+    bool replayed = false;
+    if (graphs && !pl->lw_graph_off && pl->lw_key_hits >= 1) {
       const long long n0 = g_launches;
       // torch's default stream is the legacy stream, which cannot be captured: record on a private stream (nothing
-      // executes during capture), replay on the caller's
-      if (!pl->lw_cap_stream) CUDA_OK(cudaStreamCreateWithFlags(&pl->lw_cap_stream, cudaStreamNonBlocking));
-      CUDA_OK(cudaStreamBeginCapture(pl->lw_cap_stream, cudaStreamCaptureModeThreadLocal));
-      const int rc = enqueue(pl->lw_cap_stream);
-      cudaGraph_t g = nullptr;
-      const cudaError_t ce = cudaStreamEndCapture(pl->lw_cap_stream, &g);
-      if (rc) { if (g) cudaGraphDestroy(g); return 1; }
-      CUDA_OK(ce);
-      const cudaError_t ie = cudaGraphInstantiate(&pl->lw_exec, g, 0);
-      cudaGraphDestroy(g);
-      CUDA_OK(ie);
-      pl->lw_graph_launches = g_launches - n0;
-      CUDA_OK(cudaGraphLaunch(pl->lw_exec, st));
-    } else if (enqueue(st)) {
-      return 1;
+      // executes during capture), replay on the caller's.  Capture is an optimisation only: if any step of it fails the
+      // plan keeps launching eagerly (nothing has run yet at that point) and does not try again.
+      bool ok = pl->lw_cap_stream != nullptr || cudaStreamCreateWithFlags(&pl->lw_cap_stream, cudaStreamNonBlocking) == cudaSuccess;
+      ok = ok && cudaStreamBeginCapture(pl->lw_cap_stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+      if (ok) {
+        const int rc = enqueue(pl->lw_cap_stream);
+        cudaGraph_t g = nullptr;
+        const cudaError_t ce = cudaStreamEndCapture(pl->lw_cap_stream, &g);
+        ok = rc == 0 && ce == cudaSuccess && g != nullptr && cudaGraphInstantiate(&pl->lw_exec, g, 0) == cudaSuccess;
+        if (g) cudaGraphDestroy(g);
+      }
+      if (ok) {
+        pl->lw_graph_launches = g_launches - n0;
+        CUDA_OK(cudaGraphLaunch(pl->lw_exec, st));
+        replayed = true;
+      } else {
+        (void)cudaGetLastError();
+        if (pl->lw_exec) { cudaGraphExecDestroy(pl->lw_exec); pl->lw_exec = nullptr; }
+        pl->lw_graph_off = true;
+        g_launches = n0;
+      }
     }
+    if (!replayed && enqueue(st)) return 1;
   }
   if (pl->timing) CUDA_OK(cudaEventRecord(pl->ev1, st));
   pl->last_grid = (int)grid; pl->last_S = 128; pl->last_NT = 128; pl->last_smem = 0; pl->last_path = GOPS_PATH_TC;
