@@ -16,8 +16,7 @@ import torch
 from bench import usable_cores
 torch.set_num_threads(usable_cores())
 from gops_b200.create_pkg.create_alg import create_alg
-from gops_b200.env.env_gen_ocp.pyth_base import ContextState, State
-from oracle import gops_oracle as orc
+from gops_b200.trainer import device_sampler as ds
 
 
 def kwargs(env_id, alg, obs_dim, act_dim, hid, act, **extra):
@@ -50,15 +49,19 @@ def time_updates(alg, data, iters, n=12, warm=3):
     return out
 
 
-def to_dev(d):
-    out = {}
-    for k, v in d.items():
-        if isinstance(v, tuple):
-            robot, ref, t = v
-            out[k] = State(robot_state=robot.cuda(), context_state=ContextState(reference=ref.cuda(), t=t))
-        else:
-            out[k] = v.cuda()
-    return out
+def sample(env_id, batch, seed, pre_horizon=10, lq_config="s4a2"):
+    """Synthetic update inputs drawn on the device (the reset laws of gops_b200/trainer/device_sampler.py)."""
+    if env_id == "pyth_idpendulum":
+        return ds.sample_idpendulum(batch, "cuda", seed)
+    if env_id == "pyth_lq":
+        return ds.sample_lq(batch, lq_config, "cuda", seed)
+    if env_id in ("pyth_veh3dofconti", "pyth_veh3dofconti_errcstr"):
+        return ds.sample_veh3dofconti(batch, pre_horizon, "cuda", seed)
+    if env_id == "veh3dof_tracking":
+        return ds.sample_veh3dof_tracking(batch, pre_horizon, "cuda", seed)
+    if env_id == "veh3dof_tracking_detour":
+        return ds.sample_veh3dof_tracking_detour(batch, pre_horizon, "cuda", seed)
+    raise KeyError(env_id)
 
 
 def main():
@@ -66,13 +69,13 @@ def main():
     res = []
     # C2: INFADP veh3dofconti B=4096, P=10, forward_step=10, [64,64] relu
     alg = create_alg(**kwargs("pyth_veh3dofconti", "INFADP", 46, 2, 64, "relu", pre_horizon=10))
-    data = to_dev(orc.sample_inputs("pyth_veh3dofconti", 4096, 1, pre_horizon=10))
+    data = sample("pyth_veh3dofconti", 4096, 1, pre_horizon=10)
     ms = time_updates(alg, data, [0, 1])
     res.append({"config": "C2 INFADP veh3dofconti B=4096 n=10 [64,64] relu", "ms_pev": ms[0], "ms_pim": ms[1],
                 "env_steps_per_s_pev": 4096 * 10 / ms[0] * 1e3, "env_steps_per_s_pim": 4096 * 10 / ms[1] * 1e3})
     # C3: FHADP veh3dof_tracking H=P=60, [256,256] elu, 8192 samples per GPU (65536 over 8 GPUs)
     alg = create_alg(**kwargs("veh3dof_tracking", "FHADP", 246, 2, 256, "elu", pre_horizon=60))
-    data = to_dev(orc.sample_inputs("veh3dof_tracking", 8192, 2, pre_horizon=60))
+    data = sample("veh3dof_tracking", 8192, 2, pre_horizon=60)
     ms = time_updates(alg, data, [0], n=5, warm=2)
     res.append({"config": "C3 FHADP veh3dof_tracking H=60 B=8192/GPU [256,256] elu", "ms": ms[0],
                 "env_steps_per_s": 8192 * 60 / ms[0] * 1e3})
@@ -80,13 +83,13 @@ def main():
     for logb in (10, 12, 14, 16, 18, 20):
         B = 1 << logb
         alg = create_alg(**kwargs("pyth_lq", "INFADP", 4, 2, 64, "gelu", lq_config="s4a2", reward_scale=1.0))
-        data = to_dev(orc.sample_inputs("pyth_lq", B, 3, lq_config="s4a2"))
+        data = sample("pyth_lq", B, 3)
         ms = time_updates(alg, data, [0, 1], n=8)
         res.append({"config": f"C5 INFADP LQ s4a2 B=2^{logb} n=10 [64,64] gelu", "ms_pev": ms[0], "ms_pim": ms[1],
                     "env_steps_per_s_pev": B * 10 / ms[0] * 1e3, "env_steps_per_s_pim": B * 10 / ms[1] * 1e3})
     # C1 small-batch point: the reference's own CPU-runnable case (B=256, H=30)
     alg = create_alg(**kwargs("pyth_idpendulum", "FHADP", 6, 1, 64, "gelu", pre_horizon=30, reward_scale=1.0))
-    data = to_dev(orc.sample_inputs("pyth_idpendulum", 256, 4))
+    data = sample("pyth_idpendulum", 256, 4)
     ms = time_updates(alg, data, [0])
     res.append({"config": "C1 FHADP idpendulum B=256 H=30 (reference's CPU config)", "ms": ms[0],
                 "env_steps_per_s": 256 * 30 / ms[0] * 1e3})

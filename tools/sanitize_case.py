@@ -10,40 +10,39 @@ import numpy as np
 import torch
 
 sys.path.insert(0, os.path.join(ROOT, "tools"))
-from bench_configs import kwargs, to_dev
+from bench_configs import kwargs, sample
 from gops_b200.create_pkg.create_alg import create_alg
-from oracle import gops_oracle as orc
 
 torch.manual_seed(0)
 which = sys.argv[1:] or ["idp", "lq", "veh", "wide", "tc", "lw", "dsac", "cstr", "detour", "peer"]
 if "idp" in which:
     alg = create_alg(**kwargs("pyth_idpendulum", "FHADP", 6, 1, 64, "gelu", pre_horizon=3, reward_scale=1.0))
     for B in (700, 130):     # cfg1/cfg2 tiles incl. ragged tails
-        alg.local_update(to_dev(orc.sample_inputs("pyth_idpendulum", B, 1)), 0)
+        alg.local_update(sample("pyth_idpendulum", B, 1), 0)
 if "lq" in which:
     alg = create_alg(**kwargs("pyth_lq", "INFADP", 4, 2, 64, "relu", lq_config="s4a2", reward_scale=1.0))
     alg.set_parameters({"forward_step": 3})
-    d = to_dev(orc.sample_inputs("pyth_lq", 300, 2, lq_config="s4a2"))
+    d = sample("pyth_lq", 300, 2)
     alg.local_update(d, 0)
     alg.local_update(d, 1)
 if "veh" in which:
     alg = create_alg(**kwargs("pyth_veh3dofconti", "INFADP", 46, 2, 64, "relu", pre_horizon=10))
     alg.set_parameters({"forward_step": 2})
-    d = to_dev(orc.sample_inputs("pyth_veh3dofconti", 200, 3, pre_horizon=10))
+    d = sample("pyth_veh3dofconti", 200, 3, pre_horizon=10)
     alg.local_update(d, 0)
     alg.local_update(d, 1)
 if "wide" in which:
     alg = create_alg(**kwargs("veh3dof_tracking", "FHADP", 46, 2, 256, "elu", pre_horizon=10))
     alg.set_parameters({"pre_horizon": 2})
-    alg.local_update(to_dev(orc.sample_inputs("veh3dof_tracking", 70, 4, pre_horizon=10)), 0)
+    alg.local_update(sample("veh3dof_tracking", 70, 4, pre_horizon=10), 0)
 if "tc" in which:          # tcgen05 / TMEM kernels: hybrid rollout (forced) and batched inference incl. a ragged tail
     os.environ["GOPS_B200_ROLLOUT"] = "tc"
     alg = create_alg(**kwargs("pyth_idpendulum", "FHADP", 6, 1, 64, "gelu", pre_horizon=3, reward_scale=1.0))
     for B in (700, 130):
-        alg.local_update(to_dev(orc.sample_inputs("pyth_idpendulum", B, 1)), 0)
+        alg.local_update(sample("pyth_idpendulum", B, 1), 0)
     alg = create_alg(**kwargs("pyth_lq", "INFADP", 4, 2, 64, "relu", lq_config="s4a2", reward_scale=1.0))
     alg.set_parameters({"forward_step": 3})
-    d = to_dev(orc.sample_inputs("pyth_lq", 300, 2, lq_config="s4a2"))
+    d = sample("pyth_lq", 300, 2)
     alg.local_update(d, 0)
     alg.local_update(d, 1)
     os.environ.pop("GOPS_B200_ROLLOUT")
@@ -55,11 +54,11 @@ if "lw" in which:          # layer-wise tcgen05 path: wide FHADP (C3 shape, smal
     alg = create_alg(**kwargs("veh3dof_tracking", "FHADP", 46, 2, 256, "elu", pre_horizon=10))
     alg.kernel_path = "tc"
     alg.set_parameters({"pre_horizon": 3})
-    alg.local_update(to_dev(orc.sample_inputs("veh3dof_tracking", 200, 4, pre_horizon=10)), 0)
+    alg.local_update(sample("veh3dof_tracking", 200, 4, pre_horizon=10), 0)
     kw2 = kwargs("pyth_idpendulum", "FHADP2", 6, 1, 64, "gelu", pre_horizon=4, reward_scale=1.0)
     kw2["policy_func_name"] = "FiniteHorizonFullPolicy"
     alg = create_alg(**kw2)
-    alg.local_update(to_dev(orc.sample_inputs("pyth_idpendulum", 333, 5)), 0)
+    alg.local_update(sample("pyth_idpendulum", 333, 5), 0)
     from gops_b200.ops.layerwise_mlp import LayerwiseMlp
     net = LayerwiseMlp([19, 100, 37, 5], "tanh", max_batch=129)
     flat = torch.randn(net.nparam, device="cuda") * 0.1
@@ -83,19 +82,15 @@ if "cstr" in which:
     kw4 = kwargs("pyth_veh3dofconti_errcstr", "FHADPInterior", 46, 2, 64, "elu", pre_horizon=10, y_error_tol=1.2, u_error_tol=2.2)
     kw4["policy_func_name"] = "FiniteHorizonPolicy"
     alg = create_alg(**kw4)
-    d = orc.sample_inputs("pyth_veh3dofconti", 150, 6, pre_horizon=10)
+    d = sample("pyth_veh3dofconti", 150, 6, pre_horizon=10)
     d["done"][::4] = 1.0
-    alg.local_update(to_dev(d), 0)
+    alg.local_update(d, 0)
 if "detour" in which:      # surrounding-vehicle model + interior point on the layer-wise path (lw_detour.cuh), done samples, ragged batch
-    from gops_b200.env.env_gen_ocp.pyth_base import ContextState, State
     kw5 = kwargs("veh3dof_tracking_detour", "FHADPInterior", 50, 2, 64, "elu", pre_horizon=10, penalty=2.0)
     kw5["policy_func_name"] = "FiniteHorizonPolicy"
     alg = create_alg(**kw5)
-    d = orc.sample_inputs("veh3dof_tracking_detour", 150, 7, pre_horizon=10)
-    d["done"][::4] = 1.0
-    robot, ref, t, surr = d["state"]
-    dd = {"obs": d["obs"].cuda(), "done": d["done"].cuda(),
-          "state": State(robot_state=robot.cuda(), context_state=ContextState(reference=ref.cuda(), constraint=surr.cuda(), t=t))}
+    dd = sample("veh3dof_tracking_detour", 150, 7, pre_horizon=10)
+    dd["done"][::4] = 1.0
     for i in range(3):       # eager, capture, replay
         alg.local_update(dd, i)
 if "peer" in which:        # exchange + Adam kernel, single rank (the sanitizer serialises kernels: peers cannot spin on each other)
