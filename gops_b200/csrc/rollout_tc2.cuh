@@ -45,9 +45,10 @@ constexpr int HPL = tcf::HPLANE, XPL = tcf::XPLANE;
 constexpr int P_BYTES = 3 * HPL, Q_BYTES = 2 * HPL, XP_BYTES = 3 * XPL;
 constexpr int XCH_BYTES = 2 * GT * MAXA * 4;   // helper -> owner output partials | owner -> helper output adjoints
 constexpr int GROUP_BYTES = P_BYTES + Q_BYTES + XP_BYTES + XCH_BYTES;
-constexpr int FLUSH_EVERY = 15;         // horizon steps between flushes of the TMEM weight-gradient accumulators
-                                        // (<= 15 x 24 truncating accumulations per element: bias ~4e-6, bars 2e-4;
-                                        //  every 8 steps cost 3 % more time, a whole-kernel chain biased by 1.3e-4)
+constexpr int FLUSH_EVERY = 30;         // horizon steps between flushes of the TMEM weight-gradient accumulators
+                                        // (<= 30 x 24 truncating accumulations per element.  Measured on the golden cases,
+                                        //  forced onto this kernel: gradient rel. L2 error 3.2e-6 at 15 steps, 4.8e-6 at 30,
+                                        //  bars 2e-4; every 8 steps cost 4 % more time; round 1's whole-kernel chain: 1.3e-4)
 constexpr int HDR_BYTES = 256;
 
 __host__ __device__ inline size_t smem_bytes(int w_floats) {
